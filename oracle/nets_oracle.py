@@ -1,0 +1,430 @@
+"""Oracle restatement of the reference's TensorFlow-0.x/slim training graphs in torch (CPU).
+
+PARITY UNPINNED: the arithmetic lives in ``tensorflow`` + ``tensorflow.contrib.slim``
+(imported at /root/reference/base_network.py:4-5; no version pin exists in the reference, API
+vintage => TF r0.10-r0.11).  Neither is in /root/reference nor in this image and the reference
+holds no numeric test for this path, so this file restates the *published* op semantics
+ and is anchored on the reference's call sites cited per function.
+fp64 = truth; fp32 = the "reference CPU path" that bench.py times.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Reference defects at HEAD are resolved as SURVEY.md Appendix C fixes them (C-1: opts=None means
+no dropout; C-2: the pixel critic flattens the conv trunk before hidden1).
+"""
+import collections
+import math
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------- definitions
+
+FC = collections.namedtuple("FC", "scope out act")          # act in {'relu','tanh',None}
+
+
+class NetDef(object):
+  """One reference network: optional conv trunk -> flatten -> FC stack (optional action concat)."""
+
+  def __init__(self, ns, state_shape, pixels, fc, concat_at=None, action_dim=0):
+    self.ns, self.state_shape, self.pixels = ns, tuple(state_shape), bool(pixels)
+    self.fc, self.concat_at, self.action_dim = list(fc), concat_at, action_dim
+    if pixels:
+      H, W = state_shape[0], state_shape[1]
+      self.H, self.W = H, W
+      self.cin = int(np.prod(state_shape[2:]))      # (H,W,3,C,R) -> 3*C*R, base_network.py:88-90
+      h, w = H, W
+      for _ in range(3):
+        h, w = h // 2, w // 2                       # max_pool2d 2x2/2 VALID, base_network.py:107,115,123
+      self.feat = h * w * 10
+    else:
+      self.cin = 0
+      self.feat = int(np.prod(state_shape))         # slim.flatten, base_network.py:133
+
+  def var_shapes(self):
+    """[(name, shape)] in TF variable-creation order."""
+    out = []
+    if self.pixels:
+      cin = self.cin
+      for name, k in (("conv1", 5), ("conv2", 5), ("conv3", 3)):   # base_network.py:103-123
+        out.append(("%s/%s/weights" % (self.ns, name), (k, k, cin, 10)))
+        out.append(("%s/%s/biases" % (self.ns, name), (10,)))
+        cin = 10
+    d = self.feat
+    for i, l in enumerate(self.fc):
+      if self.concat_at == i:
+        d += self.action_dim
+      out.append(("%s/%s/weights" % (self.ns, l.scope), (d, l.out)))
+      out.append(("%s/%s/biases" % (self.ns, l.scope), (l.out,)))
+      d = l.out
+    return out
+
+  def num_params(self):
+    return sum(int(np.prod(s)) for _, s in self.var_shapes())
+
+
+def _hidden(sizes):
+  if isinstance(sizes, str):
+    sizes = [int(s) for s in sizes.split(",")]          # base_network.py:60-61
+  return [FC("h%d" % i, s, "relu") for i, s in enumerate(sizes)]   # base_network.py:63-68
+
+
+def ddpg_actor(ns, state_shape, pixels, hidden="100,100,50", action_dim=2):
+  """ddpg_cartpole.py:90-100"""
+  return NetDef(ns, state_shape, pixels, _hidden(hidden) + [FC("output_action", action_dim, "tanh")])
+
+
+def ddpg_critic(ns, state_shape, pixels, hidden="100,100,50", action_dim=2):
+  """ddpg_cartpole.py:161-184 (pixel branch repaired per Appendix C-2)"""
+  if pixels:
+    fc = [FC("hidden1", 200, "relu"), FC("hidden2", 50, "relu"), FC("hidden3", 50, "relu"),
+          FC("q_value", 1, None)]
+    return NetDef(ns, state_shape, True, fc, concat_at=2, action_dim=action_dim)
+  return NetDef(ns, state_shape, False, _hidden(hidden) + [FC("q_value", 1, None)],
+                concat_at=0, action_dim=action_dim)
+
+
+def naf_value(ns, state_shape, pixels, hidden="100,50"):
+  """naf_cartpole.py:96-109"""
+  return NetDef(ns, state_shape, pixels, _hidden(hidden) + [FC("fc", 1, None)])
+
+
+def naf_mu(state_shape, pixels, hidden="100,50", action_dim=2):
+  """naf_cartpole.py:147-161"""
+  return NetDef("naf/output_action", state_shape, pixels, _hidden(hidden) + [FC("fc", action_dim, "tanh")])
+
+
+def naf_l(state_shape, pixels, hidden="100,50", action_dim=2):
+  """naf_cartpole.py:172-184"""
+  return NetDef("naf/l_values", state_shape, pixels,
+                _hidden(hidden) + [FC("fc", action_dim * (action_dim + 1) // 2, None)])
+
+
+def lrpg_model(state_shape, hidden="100,50", num_actions=5):
+  """lrpg_cartpole.py:80-88"""
+  return NetDef("model", state_shape, False, _hidden(hidden) + [FC("fully_connected", num_actions, None)])
+
+
+def init_params(netdef, rs, dtype=torch.float64):
+  """xavier-uniform weights / zero biases (slim defaults, Appendix A-4/A-6); action heads
+  U(+-1e-3) (ddpg_cartpole.py:94, naf_cartpole.py:155).  The reference never seeds TF, so
+  parity tests always inject weights; this is only a generator of plausible values."""
+  P = collections.OrderedDict()
+  for name, shape in netdef.var_shapes():
+    if name.endswith("biases"):
+      v = np.zeros(shape)
+    elif len(shape) == 4:
+      kh, kw, ci, co = shape
+      lim = math.sqrt(6.0 / (kh * kw * ci + kh * kw * co))
+      v = rs.uniform(-lim, lim, shape)
+    else:
+      lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+      if name.endswith("output_action/weights") or name == "naf/output_action/fc/weights":
+        lim = 1e-3
+      v = rs.uniform(-lim, lim, shape)
+    P[name] = torch.tensor(v.astype(np.float32), dtype=dtype)   # values are fp32-representable
+  return P
+
+
+def retarget(P, src_ns, dst_ns):
+  """same tensors under the target namespace (base_network.py:28)"""
+  return collections.OrderedDict((dst_ns + k[len(src_ns):], v.clone()) for k, v in P.items())
+
+
+def flat(P, names=None):
+  names = names or list(P.keys())
+  return torch.cat([P[n].reshape(-1) for n in names])
+
+
+# ----------------------------------------------------------------------------- forward
+
+def whiten(x):
+  """base_network.py:95-99: per-channel batch moments (population variance), eps 1e-6,
+  x*inv - mean*inv (tf.nn.batch_normalization with scale=offset=None)."""
+  mean = x.mean(dim=(0, 1, 2))
+  var = ((x - mean) ** 2).mean(dim=(0, 1, 2))
+  inv = torch.rsqrt(var + 1e-6)
+  return x * inv - mean * inv
+
+
+def conv_trunk(nd, P, state):
+  """base_network.py:73-127 -> (B, h, w, 10) NHWC"""
+  B = state.shape[0]
+  x = state.reshape(B, nd.H, nd.W, nd.cin)             # plain reshape, Appendix A-2
+  x = whiten(x).permute(0, 3, 1, 2)
+  for name, k in (("conv1", 5), ("conv2", 5), ("conv3", 3)):
+    W = P["%s/%s/weights" % (nd.ns, name)].permute(3, 2, 0, 1)   # HWIO -> OIHW
+    b = P["%s/%s/biases" % (nd.ns, name)]
+    x = F.relu(F.conv2d(x, W, b, stride=1, padding=k // 2))       # SAME, cross-correlation
+    x = F.max_pool2d(x, 2)                                        # stride 2, VALID (floor)
+  return x.permute(0, 2, 3, 1)
+
+
+def forward(nd, P, state, action=None, dtype=None, return_hidden=False):
+  dtype = dtype or next(iter(P.values())).dtype
+  state = torch.as_tensor(np.asarray(state)) if not torch.is_tensor(state) else state
+  x = state.to(dtype)                                  # fp16 replay states are cast by the feed
+  B = x.shape[0]
+  if nd.pixels:
+    x = conv_trunk(nd, P, x).reshape(B, -1)            # flatten row-major (h,w,c), Appendix A-1
+  else:
+    x = x.reshape(B, -1)
+  for i, l in enumerate(nd.fc):
+    if nd.concat_at == i:
+      x = torch.cat([x, action.to(dtype)], dim=1)     # ddpg_cartpole.py:170,175
+    x = x @ P["%s/%s/weights" % (nd.ns, l.scope)] + P["%s/%s/biases" % (nd.ns, l.scope)]
+    if l.act == "relu":
+      x = F.relu(x)
+    elif l.act == "tanh":
+      x = torch.tanh(x)
+  return x
+
+
+def _names(nd):
+  return [n for n, _ in nd.var_shapes()]
+
+
+def _leaf(P, names):
+  for n in names:
+    P[n] = P[n].detach().clone().requires_grad_(True)
+  return [P[n] for n in names]
+
+
+# ----------------------------------------------------------------------------- clip / optimisers
+
+def global_norm(grads):
+  return torch.sqrt(sum((g * g).sum() for g in grads))
+
+
+def clip_by_global_norm(grads, clip):
+  """util.py:45-50 -> tf.clip_by_global_norm: g * clip*min(1/norm, 1/clip)  (Appendix A-10)"""
+  if clip is None:
+    return list(grads), None
+  norm = global_norm(grads)
+  scale = clip * torch.minimum(1.0 / norm, torch.tensor(1.0 / clip, dtype=norm.dtype))
+  return [g * scale for g in grads], norm
+
+
+class Optimiser(object):
+  """util.py:73-76 -> tf.train.{GradientDescent,Momentum,Adam}Optimizer (Appendix A-9)"""
+
+  def __init__(self, kind, learning_rate, momentum=0.0, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    self.kind, self.lr = kind, learning_rate
+    self.momentum, self.b1, self.b2, self.eps = momentum, beta1, beta2, epsilon
+    self.t, self.slots = 0, {}
+
+  def apply(self, params, grads):
+    """in-place on the list of tensors `params`"""
+    self.t += 1
+    for i, (p, g) in enumerate(zip(params, grads)):
+      if self.kind == "GradientDescent":
+        p -= self.lr * g
+      elif self.kind == "Momentum":
+        acc = self.slots.setdefault(i, torch.zeros_like(p))
+        acc.mul_(self.momentum).add_(g)
+        p -= self.lr * acc
+      elif self.kind == "Adam":
+        m, v = self.slots.setdefault(i, (torch.zeros_like(p), torch.zeros_like(p)))
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        m += (1.0 - self.b1) * (g - m)
+        v += (1.0 - self.b2) * (g * g - v)
+        p -= lr_t * m / (torch.sqrt(v) + self.eps)        # epsilon-hat placement
+      else:
+        raise ValueError(self.kind)
+
+
+def soft_update(target, source, coeff):
+  """base_network.py:31: t <- t - c*(t - s), evaluated in that association"""
+  return target - coeff * (target - source)
+
+
+# ----------------------------------------------------------------------------- DDPG
+
+def ddpg_actor_grads(actor, critic, P, s1):
+  """ddpg_cartpole.py:102-119,220-222: grads = d mu/d theta . (-dQ(s1,mu(s1))/da), batch SUM."""
+  names = _names(actor)
+  leaves = _leaf(P, names)
+  mu = forward(actor, P, s1)
+  a_in = mu.detach().clone().requires_grad_(True)        # stop_gradient(actor.output_action) :162
+  q = forward(critic, P, s1, a_in)
+  dqda, = torch.autograd.grad(q.sum(), a_in)
+  grads = torch.autograd.grad(mu, leaves, grad_outputs=-dqda)
+  for n in names:
+    P[n] = P[n].detach()
+  return [g.detach() for g in grads], mu.detach(), q.detach(), dqda.detach()
+
+
+def ddpg_critic_loss(critic, tactor, tcritic, P, batch, discount):
+  """ddpg_cartpole.py:186-209 -> (loss, td, q)"""
+  s1, a, r, mask, s2 = batch
+  dt = next(iter(P.values())).dtype
+  with torch.no_grad():
+    mu2 = forward(tactor, P, s2)
+    q2 = forward(tcritic, P, s2, mu2)
+    y = torch.as_tensor(r).to(dt) + torch.as_tensor(mask).to(dt) * discount * q2
+  q = forward(critic, P, s1, torch.as_tensor(a).to(dt))
+  td = q - y
+  return (td ** 2).mean(), td, q
+
+
+def ddpg_critic_grads(critic, tactor, tcritic, P, batch, discount):
+  names = _names(critic)
+  leaves = _leaf(P, names)
+  loss, td, q = ddpg_critic_loss(critic, tactor, tcritic, P, batch, discount)
+  grads = torch.autograd.grad(loss, leaves)
+  for n in names:
+    P[n] = P[n].detach()
+  return [g.detach() for g in grads], loss.detach(), td.detach(), q.detach()
+
+
+class DDPGOracle(object):
+  """The reference DDPG inner loop body (ddpg_cartpole.py:331-337) on explicit weights."""
+
+  def __init__(self, state_shape, pixels, P, actor_hidden="100,100,50", critic_hidden="100,100,50",
+               action_dim=2, actor_lr=1e-3, critic_lr=1e-2, discount=0.99, clip=5.0, tau=1e-4):
+    self.actor = ddpg_actor("actor", state_shape, pixels, actor_hidden, action_dim)
+    self.critic = ddpg_critic("critic", state_shape, pixels, critic_hidden, action_dim)
+    self.tactor = ddpg_actor("target_actor", state_shape, pixels, actor_hidden, action_dim)
+    self.tcritic = ddpg_critic("target_critic", state_shape, pixels, critic_hidden, action_dim)
+    self.P = P
+    self.actor_lr, self.critic_lr, self.discount, self.clip, self.tau = actor_lr, critic_lr, discount, clip, tau
+
+  def actor_train(self, s1):
+    g, mu, q, dqda = ddpg_actor_grads(self.actor, self.critic, self.P, s1)
+    gc, norm = clip_by_global_norm(g, self.clip)
+    for n, gi in zip(_names(self.actor), gc):
+      self.P[n] = self.P[n] - self.actor_lr * gi
+    return dict(grads=g, clipped=gc, norm=norm, mu=mu, q=q, dqda=dqda)
+
+  def critic_train(self, batch):
+    g, loss, td, q = ddpg_critic_grads(self.critic, self.tactor, self.tcritic, self.P, batch, self.discount)
+    gc, norm = clip_by_global_norm(g, self.clip)
+    for n, gi in zip(_names(self.critic), gc):
+      self.P[n] = self.P[n] - self.critic_lr * gi
+    return dict(grads=g, clipped=gc, norm=norm, loss=loss, td=td, q=q)
+
+  def check_loss(self, batch):
+    with torch.no_grad():
+      return ddpg_critic_loss(self.critic, self.tactor, self.tcritic, self.P, batch, self.discount)
+
+  def update_targets(self, coeff=None):
+    c = self.tau if coeff is None else coeff
+    for src, dst in ((self.actor, self.tactor), (self.critic, self.tcritic)):
+      for ns_, nd_ in zip(_names(src), _names(dst)):
+        self.P[nd_] = soft_update(self.P[nd_], self.P[ns_], c)
+
+  def action_given(self, state):
+    with torch.no_grad():
+      return forward(self.actor, self.P, torch.as_tensor(np.asarray(state))[None])
+
+
+# ----------------------------------------------------------------------------- NAF
+
+def naf_quantities(value, mu_net, l_net, P, s1, action, action_dim):
+  """naf_cartpole.py:147-221 -> (l_values, L, V, mu, A, Q)"""
+  dt = next(iter(P.values())).dtype
+  V = forward(value, P, s1)
+  mu = forward(mu_net, P, s1)
+  l = forward(l_net, P, s1)
+  B = l.shape[0]
+  rows = []
+  for r in range(action_dim):                               # naf_cartpole.py:195-203
+    off = r * (r + 1) // 2
+    lower = l[:, off:off + r]
+    diag = torch.exp(l[:, off + r:off + r + 1])
+    upper = torch.zeros(B, action_dim - r - 1, dtype=dt)
+    rows.append(torch.cat([lower, diag, upper], dim=1))
+  L = torch.stack(rows, dim=1)                              # (B, A, A)
+  Pm = L @ L.transpose(1, 2)                                # :212
+  d = (torch.as_tensor(action).to(dt) - mu).unsqueeze(-1)   # :166-167
+  A = (-0.5 * (d.transpose(1, 2) @ (Pm @ d))).reshape(-1, 1)   # :215-218
+  return l, L, V, mu, A, V + A
+
+
+class NAFOracle(object):
+  """naf_cartpole.py:367-373 body: naf.train(batch) then (every batches_per_step) target update."""
+
+  def __init__(self, state_shape, pixels, P, hidden="100,50", action_dim=2, discount=0.99, clip=5.0,
+               tau=1e-4, optimiser="GradientDescent", optimiser_args=None):
+    self.value = naf_value("value", state_shape, pixels, hidden)
+    self.tvalue = naf_value("target_value", state_shape, pixels, hidden)
+    self.mu = naf_mu(state_shape, pixels, hidden, action_dim)
+    self.l = naf_l(state_shape, pixels, hidden, action_dim)
+    self.P, self.A, self.discount, self.clip, self.tau = P, action_dim, discount, clip, tau
+    self.opt = Optimiser(optimiser, **(optimiser_args or {"learning_rate": 1e-3}))
+    self.train_names = _names(self.value) + _names(self.mu) + _names(self.l)
+
+  def _loss(self, batch):
+    s1, a, r, mask, s2 = batch
+    dt = next(iter(self.P.values())).dtype
+    l, L, V, mu, A, Q = naf_quantities(self.value, self.mu, self.l, self.P, s1, a, self.A)
+    with torch.no_grad():
+      V2 = forward(self.tvalue, self.P, s2)
+      y = torch.as_tensor(r).to(dt) + torch.as_tensor(mask).to(dt) * self.discount * V2   # :225-227
+    loss = ((Q - y) ** 2).mean()                                                        # :230
+    return loss, l, L, V, A, V2
+
+  def train(self, batch):
+    leaves = _leaf(self.P, self.train_names)
+    loss, l, L, V, A, V2 = self._loss(batch)
+    grads = [g.detach() for g in torch.autograd.grad(loss, leaves)]
+    for n in self.train_names:
+      self.P[n] = self.P[n].detach()
+    if not (torch.isfinite(l).all() and torch.isfinite(L).all() and torch.isfinite(loss)):
+      raise FloatingPointError("check_numerics")                                        # :242-245
+    gc, norm = clip_by_global_norm(grads, self.clip)
+    params = [self.P[n] for n in self.train_names]
+    self.opt.apply(params, gc)
+    return dict(loss=loss.detach(), grads=grads, clipped=gc, norm=norm)
+
+  def debug_values(self, batch):
+    with torch.no_grad():
+      loss, l, L, V, A, V2 = self._loss(batch)
+    return [np.squeeze(v.numpy()) for v in (l, loss, V, A, V2)]                         # :274-284
+
+  def update_targets(self, coeff=None):
+    c = self.tau if coeff is None else coeff
+    for ns_, nd_ in zip(_names(self.value), _names(self.tvalue)):
+      self.P[nd_] = soft_update(self.P[nd_], self.P[ns_], c)
+
+  def action_given(self, state):
+    with torch.no_grad():
+      return forward(self.mu, self.P, torch.as_tensor(np.asarray(state))[None])
+
+
+# ----------------------------------------------------------------------------- LRPG
+
+def standardise(t):
+  """util.py:37-43 (population std, no epsilon)"""
+  mean = t.mean()
+  return (t - mean) / torch.sqrt(((t - mean) ** 2).mean())
+
+
+class LRPGOracle(object):
+  """lrpg_cartpole.py:80-130,165-182"""
+
+  def __init__(self, state_shape, P, hidden="100,50", num_actions=5, clip=5.0,
+               optimiser="GradientDescent", optimiser_args=None):
+    self.model = lrpg_model(state_shape, hidden, num_actions)
+    self.P, self.clip, self.num_actions = P, clip, num_actions
+    self.opt = Optimiser(optimiser, **(optimiser_args or {"learning_rate": 1e-3}))
+    self.names = _names(self.model)
+
+  def logits(self, observations):
+    with torch.no_grad():
+      return forward(self.model, self.P, observations)
+
+  def train(self, observations, actions, advantages):
+    dt = next(iter(self.P.values())).dtype
+    leaves = _leaf(self.P, self.names)
+    logits = forward(self.model, self.P, observations)
+    logp = F.log_softmax(logits, dim=1)
+    mask = F.one_hot(torch.as_tensor(np.asarray(actions), dtype=torch.int64), self.num_actions).to(dt)
+    alp = (logp * mask).sum(dim=1)
+    loss = -(alp * standardise(torch.as_tensor(np.asarray(advantages)).to(dt))).sum()
+    grads = [g.detach() for g in torch.autograd.grad(loss, leaves)]
+    for n in self.names:
+      self.P[n] = self.P[n].detach()
+    gc, norm = clip_by_global_norm(grads, self.clip)
+    self.opt.apply([self.P[n] for n in self.names], gc)
+    return dict(loss=loss.detach(), grads=grads, clipped=gc, norm=norm, logits=logits.detach())

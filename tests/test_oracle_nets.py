@@ -1,0 +1,136 @@
+"""Independent checks of the torch oracle's semantics (parity is unpinned by the reference, so the
+restatement is cross-checked against explicit numpy loops and closed forms from SURVEY.md App. A)."""
+import json
+import os
+import numpy as np
+import torch
+import pytest
+
+from oracle import nets_oracle as no
+
+
+def naive_trunk(x, Ws, bs):
+  """explicit loops: whitening, SAME cross-correlation, ReLU, 2x2/2 VALID max-pool"""
+  x = x.astype(np.float64)
+  mean = x.mean(axis=(0, 1, 2)); var = ((x - mean) ** 2).mean(axis=(0, 1, 2))
+  x = (x - mean) / np.sqrt(var + 1e-6)
+  for W, b in zip(Ws, bs):
+    k = W.shape[0]; p = k // 2
+    B, H, Wd, C = x.shape
+    xp = np.zeros((B, H + 2 * p, Wd + 2 * p, C)); xp[:, p:p + H, p:p + Wd] = x
+    y = np.zeros((B, H, Wd, W.shape[3]))
+    for ky in range(k):
+      for kx in range(k):
+        y += np.einsum("bhwc,co->bhwo", xp[:, ky:ky + H, kx:kx + Wd], W[ky, kx])
+    y = np.maximum(y + b, 0)
+    h2, w2 = H // 2, Wd // 2
+    y = y[:, :h2 * 2, :w2 * 2].reshape(B, h2, 2, w2, 2, -1).max(axis=(2, 4))
+    x = y
+  return x
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 3, 1, 2), (22, 18, 3, 2, 1)])
+def test_trunk_matches_explicit_loops(shape):
+  rs = np.random.RandomState(0)
+  nd = no.ddpg_actor("actor", shape, True)
+  P = no.init_params(nd, rs)
+  for k in P:
+    if k.endswith("biases"):
+      P[k] = torch.tensor(rs.uniform(-0.1, 0.1, tuple(P[k].shape)))
+  s = (rs.randint(0, 256, (3,) + shape).astype(np.float16) / np.float16(255))
+  got = no.conv_trunk(nd, P, torch.tensor(s.astype(np.float64))).numpy()
+  x = s.reshape(3, shape[0], shape[1], -1)
+  want = naive_trunk(x, [P["actor/conv%d/weights" % i].numpy() for i in (1, 2, 3)],
+                     [P["actor/conv%d/biases" % i].numpy() for i in (1, 2, 3)])
+  assert got.shape == want.shape
+  np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+def test_naf_closed_form_a7():
+  """Appendix A-7 closed forms for A=2 vs the generic L.L^T graph and autograd"""
+  rs = np.random.RandomState(1)
+  B = 9
+  l = torch.tensor(rs.uniform(-1, 1, (B, 3)), requires_grad=True)
+  mu = torch.tensor(rs.uniform(-1, 1, (B, 2)), requires_grad=True)
+  V = torch.tensor(rs.uniform(-1, 1, (B, 1)), requires_grad=True)
+  u = torch.tensor(rs.uniform(-1, 1, (B, 2)))
+  y = torch.tensor(rs.uniform(-1, 1, (B, 1)))
+  L = torch.zeros(B, 2, 2, dtype=torch.float64)
+  L = torch.stack([torch.stack([torch.exp(l[:, 0]), torch.zeros(B, dtype=torch.float64)], 1),
+                   torch.stack([l[:, 1], torch.exp(l[:, 2])], 1)], 1)
+  d = (u - mu).unsqueeze(-1)
+  A = (-0.5 * d.transpose(1, 2) @ (L @ L.transpose(1, 2)) @ d).reshape(-1, 1)
+  Q = V + A
+  loss = ((Q - y) ** 2).mean()
+  gl, gmu, gV = torch.autograd.grad(loss, [l, mu, V])
+  with torch.no_grad():
+    L00, L10, L11 = torch.exp(l[:, 0]), l[:, 1], torch.exp(l[:, 2])
+    d0, d1 = u[:, 0] - mu[:, 0], u[:, 1] - mu[:, 1]
+    z0, z1 = L00 * d0 + L10 * d1, L11 * d1
+    Acf = -0.5 * (z0 ** 2 + z1 ** 2)
+    delta = 2 * (V[:, 0] + Acf - y[:, 0]) / B
+    np.testing.assert_allclose(Acf.numpy(), A[:, 0].detach().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(gV[:, 0].numpy(), delta.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(gmu[:, 0].numpy(), (delta * (L00 * z0)).numpy(), rtol=1e-10)
+    np.testing.assert_allclose(gmu[:, 1].numpy(), (delta * (L10 * z0 + L11 * z1)).numpy(), rtol=1e-10)
+    np.testing.assert_allclose(gl[:, 0].numpy(), (-delta * d0 * z0 * L00).numpy(), rtol=1e-10)
+    np.testing.assert_allclose(gl[:, 1].numpy(), (-delta * d1 * z0).numpy(), rtol=1e-10)
+    np.testing.assert_allclose(gl[:, 2].numpy(), (-delta * d1 * z1 * L11).numpy(), rtol=1e-10)
+
+
+def test_clip_and_optimisers():
+  g = [torch.tensor([3.0, 4.0], dtype=torch.float64), torch.tensor([12.0], dtype=torch.float64)]
+  gc, norm = no.clip_by_global_norm(g, 5.0)
+  assert abs(float(norm) - 13.0) < 1e-12
+  np.testing.assert_allclose(torch.cat(gc).numpy(), np.array([3, 4, 12]) * 5 / 13)
+  gc, _ = no.clip_by_global_norm([x * 0.1 for x in g], 5.0)        # below the clip: unchanged
+  np.testing.assert_allclose(torch.cat(gc).numpy(), np.array([.3, .4, 1.2]))
+  # Adam, epsilon-hat placement (Appendix A-9): first step = lr*sqrt(1-b2)/(1-b1) * (1-b1) g / (sqrt((1-b2) g^2) + eps)
+  p = [torch.tensor([1.0], dtype=torch.float64)]
+  opt = no.Optimiser("Adam", 0.1)
+  opt.apply(p, [torch.tensor([2.0], dtype=torch.float64)])
+  lr_t = 0.1 * np.sqrt(1 - 0.999) / (1 - 0.9)
+  want = 1.0 - lr_t * (0.1 * 2.0) / (np.sqrt(0.001 * 4.0) + 1e-8)
+  assert abs(float(p[0]) - want) < 1e-12
+  p = [torch.tensor([1.0], dtype=torch.float64)]
+  opt = no.Optimiser("Momentum", 0.1, momentum=0.9)
+  opt.apply(p, [torch.tensor([2.0], dtype=torch.float64)]); opt.apply(p, [torch.tensor([1.0], dtype=torch.float64)])
+  assert abs(float(p[0]) - (1 - 0.1 * 2 - 0.1 * (0.9 * 2 + 1))) < 1e-12
+
+
+def test_soft_update_association():
+  t = torch.tensor([1.0, 2.0], dtype=torch.float32); s = torch.tensor([3.0, -1.0], dtype=torch.float32)
+  np.testing.assert_array_equal(no.soft_update(t, s, 0.25).numpy(), (t - 0.25 * (t - s)).numpy())
+
+
+def test_actor_gradient_is_batch_sum_of_dq_da():
+  """Appendix A-8: the actor update direction equals -d/dtheta sum_b Q(s_b, mu_theta(s_b))"""
+  rs = np.random.RandomState(3)
+  shape = (2, 2, 7)
+  P = {}
+  a, c = no.ddpg_actor("actor", shape, False), no.ddpg_critic("critic", shape, False)
+  P.update(no.init_params(a, rs)); P.update(no.init_params(c, rs))
+  s1 = torch.tensor(rs.uniform(-1, 1, (6,) + shape))
+  g, mu, q, dqda = no.ddpg_actor_grads(a, c, P, s1)
+  leaves = no._leaf(P, no._names(a))
+  obj = -no.forward(c, P, s1, no.forward(a, P, s1)).sum()
+  want = torch.autograd.grad(obj, leaves)
+  for x, y in zip(g, want):
+    np.testing.assert_allclose(x.numpy(), y.numpy(), rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["ddpg_pixel", "ddpg_lowdim"])
+def test_oracle_reproduces_committed_golden(golden_dir, name):
+  g = np.load(os.path.join(golden_dir, "nets_%s.npz" % name))
+  meta = json.loads(str(g["meta"]))
+  P = {k[3:]: torch.tensor(g[k].astype(np.float64)) for k in g.files if k.startswith("P0/")}
+  o = no.DDPGOracle(tuple(meta["state_shape"]), meta["pixels"], P)
+  for step in range(2):
+    batch = tuple(g["step%d/%s" % (step, f)] for f in ("s1", "a", "r", "m", "s2"))
+    ra = o.actor_train(batch[0])
+    np.testing.assert_allclose(torch.cat([x.reshape(-1) for x in ra["grads"]]).numpy(), g["step%d/actor_grads" % step], rtol=1e-9, atol=1e-13)
+    rc = o.critic_train(batch)
+    np.testing.assert_allclose(float(rc["loss"]), float(g["step%d/loss" % step]), rtol=1e-10)
+    o.update_targets(0.05)
+  for k, v in o.P.items():
+    np.testing.assert_allclose(v.numpy(), g["Pfinal/" + k], rtol=1e-9, atol=1e-13)
