@@ -1,0 +1,339 @@
+// Agent-level hot-path steps: DDPG (ddpg_cartpole.py:102-119,186-248,331-337), NAF
+// (naf_cartpole.py:147-284,367-373), LRPG (lrpg_cartpole.py:80-130,165-182).
+// Every step is "backward" (forward + loss + gradients into the flat gradient buffer) followed by
+// "apply" (global-norm clip + optimiser); a data-parallel host all-reduces the flat buffer in between.
+#include "agents.cuh"
+
+namespace cpp {
+
+static inline int64_t pad4(int64_t n) { return round_up(n, 4); }
+
+struct Carver {
+  char* base; size_t off = 0;
+  explicit Carver(void* b) : base(reinterpret_cast<char*>(b)) {}
+  template <typename T> T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += (size_t)round_up((int64_t)(count * sizeof(T)), 256);
+    return p;
+  }
+};
+
+// ============================================================================ DDPG
+int DDPG::init(const cpp_ddpg_config& c) {
+  cfg = c;
+  CPP_REQUIRE(c.max_batch >= 1, "max_batch=%d", c.max_batch);
+  CPP_TRY(actor.init(c.actor));
+  CPP_TRY(critic.init(c.critic));
+  CPP_REQUIRE(critic.concat_at >= 0 && critic.out_width() == 1, "critic must take an action and output one q value");
+  CPP_REQUIRE(actor.out_width() == critic.action_dim, "actor output %d != critic action_dim %d", actor.out_width(), critic.action_dim);
+  CPP_REQUIRE(actor.pixels == critic.pixels, "actor and critic read the same state");
+  n_a = actor.nparams; n_c = critic.nparams;
+  off_c = pad4(n_a); off_loss = off_c + pad4(n_c); total = off_loss + 4;
+  return CPP_OK;
+}
+
+void DDPG::carve(void* ws, bool assign) {
+  Carver cv(ws);
+  const int B = cfg.max_batch, A = critic.action_dim, C = actor.pixels ? actor.spec.Cin : 1;
+  char* wa = cv.take<char>(actor.workspace_bytes(B));
+  char* wc = cv.take<char>(critic.workspace_bytes(B));
+  const size_t wt_b = actor.workspace_bytes(B) > critic.workspace_bytes(B) ? actor.workspace_bytes(B) : critic.workspace_bytes(B);
+  char* wt = cv.take<char>(wt_b);
+  float* mu_ = cv.take<float>((size_t)B * A); float* dqda_ = cv.take<float>((size_t)B * A); float* neg_ = cv.take<float>((size_t)B * A);
+  float* mu2_ = cv.take<float>((size_t)B * A);
+  float* q_ = cv.take<float>(B); float* q2_ = cv.take<float>(B); float* td_ = cv.take<float>(B); float* dq_ = cv.take<float>(B);
+  float* ones_ = cv.take<float>(B);
+  float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
+  double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(norm_scratch_doubles());
+  float* sc = cv.take<float>(4);
+  ws_bytes = cv.off;
+  if (assign) {
+    ws_actor = wa; ws_critic = wc; ws_target = wt; mu = mu_; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
+    ones = ones_; mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
+  }
+}
+
+int DDPG::bind(const cpp_ddpg_buffers& b) {
+  CPP_REQUIRE(b.params && b.target_params && b.grads && b.workspace, "null buffer");
+  CPP_REQUIRE((((uintptr_t)b.params | (uintptr_t)b.target_params | (uintptr_t)b.grads | (uintptr_t)b.workspace) & 255) == 0,
+              "buffers must be 256-byte aligned");
+  carve(nullptr, false);
+  CPP_REQUIRE(b.workspace_bytes >= (int64_t)ws_bytes, "workspace too small: %lld < %lld", (long long)b.workspace_bytes, (long long)ws_bytes);
+  buf = b; bound = true;
+  carve(b.workspace, true);
+  ones_ready = false; pinned1 = pinned2 = nullptr;
+  return CPP_OK;
+}
+
+int DDPG::stats_for(const void* x, int is_f16, int B, float* dst, const float* pinned, const float** out, cudaStream_t s) {
+  *out = nullptr;
+  if (!actor.pixels) return CPP_OK;
+  if (pinned) { *out = pinned; return CPP_OK; }
+  CPP_TRY(launch_channel_moments(x, is_f16, (int64_t)B * actor.spec.H * actor.spec.W, actor.spec.Cin, mom_scratch, dst, s));
+  *out = dst;
+  return CPP_OK;
+}
+
+#define CPP_NEED_BOUND() do { if (!bound) { set_error("agent buffers not bound (call *_bind first)"); return CPP_ERR_STATE; } } while (0)
+#define CPP_NEED_BATCH(B) CPP_REQUIRE((B) >= 1 && (B) <= cfg.max_batch, "batch %d outside [1, max_batch=%d]", (B), cfg.max_batch)
+
+int DDPG::actor_backward(const void* s1, int is_f16, int B, int B_global, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B); (void)B_global;   // actor gradient is a batch SUM (SURVEY A-8)
+  const int A = critic.action_dim;
+  const float* m1;
+  CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
+  cur_m1 = m1;
+  CPP_TRY(actor.forward(buf.params, s1, is_f16, m1, nullptr, B, ws_actor, mu, s));
+  CPP_TRY(critic.forward(buf.params + off_c, s1, is_f16, m1, mu, B, ws_critic, nullptr, s));
+  if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s)); ones_ready = true; }
+  // q_gradients_wrt_actions: tf.gradients(q_value, input_action), ddpg_cartpole.py:220-222
+  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, s));
+  CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, s));                       // tf.neg(...), :113
+  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s));
+  critic_trunk_valid = true; trunk_B = B;
+  return CPP_OK;
+}
+
+int DDPG::actor_apply(cudaStream_t s) {
+  CPP_NEED_BOUND();
+  CPP_TRY(launch_global_norm_scale(buf.grads, pad4(n_a), cfg.gradient_clip, norm_scratch, scale2, s));
+  CPP_TRY(launch_optimiser(0, buf.params, buf.grads, scale2, pad4(n_a), cfg.actor_lr, 0, 0, 0, 0, nullptr, nullptr, nullptr, s));
+  return CPP_OK;
+}
+
+int DDPG::critic_forward_td(const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
+                            int is_f16, int B, int B_global, bool reuse, float* td_out, float* dq_out, float* loss_flag, cudaStream_t s) {
+  const float *m1, *m2;
+  CPP_TRY(stats_for(s2, is_f16, B, mi2, pinned2, &m2, s));
+  reuse = reuse && critic_trunk_valid && trunk_B == B && critic.concat_at > 0;
+  if (reuse) m1 = cur_m1;
+  else CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
+  cur_m1 = m1;
+  // bellman_rhs: target actor/critic on state_2, ddpg_cartpole.py:198-202
+  CPP_TRY(actor.forward(buf.target_params, s2, is_f16, m2, nullptr, B, ws_target, mu2, s));
+  CPP_TRY(critic.forward(buf.target_params + off_c, s2, is_f16, m2, mu2, B, ws_target, q2, s));
+  CPP_TRY(critic.forward(buf.params + off_c, s1, is_f16, m1, action, B, ws_critic, q, s, reuse ? critic.concat_at : 0));
+  CPP_TRY(launch_td_mse(q, q2, reward, mask, cfg.discount, B, B_global, td_out, dq_out, loss_flag, s));
+  return CPP_OK;
+}
+
+int DDPG::critic_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
+                          int is_f16, int B, int B_global, int reuse, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  CPP_TRY(critic_forward_td(s1, action, reward, mask, s2, is_f16, B, B_global, reuse != 0, td, dq, buf.grads + off_loss, s));
+  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, cur_m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s));
+  critic_trunk_valid = false;
+  return CPP_OK;
+}
+
+int DDPG::critic_apply(cudaStream_t s) {
+  CPP_NEED_BOUND();
+  CPP_TRY(launch_global_norm_scale(buf.grads + off_c, pad4(n_c), cfg.gradient_clip, norm_scratch, scale2 + 2, s));
+  CPP_TRY(launch_optimiser(0, buf.params + off_c, buf.grads + off_c, scale2 + 2, pad4(n_c), cfg.critic_lr, 0, 0, 0, 0, nullptr, nullptr, nullptr, s));
+  critic_trunk_valid = false;
+  return CPP_OK;
+}
+
+int DDPG::check_loss(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                     int B, float* loss, float* td_out, float* q_out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  CPP_TRY(critic_forward_td(s1, action, reward, mask, s2, is_f16, B, B, false, td_out, nullptr, scale2, s));
+  critic_trunk_valid = false;
+  CPP_CHECK_CUDA(cudaMemcpyAsync(loss, scale2, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CPP_CHECK_CUDA(cudaMemcpyAsync(q_out, q, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return CPP_OK;
+}
+
+int DDPG::action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  const float* m;
+  CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));     // statistics of the fed batch itself (B=1 in rollouts)
+  CPP_TRY(actor.forward(buf.params, state, is_f16, m, nullptr, B, ws_target, out, s));
+  return CPP_OK;
+}
+
+int DDPG::update_targets(float coeff, cudaStream_t s) {
+  CPP_NEED_BOUND();
+  return launch_soft_update(buf.target_params, buf.params, coeff, off_loss, s);
+}
+
+// ============================================================================ NAF
+int NAF::init(const cpp_naf_config& c) {
+  cfg = c;
+  CPP_REQUIRE(c.max_batch >= 1, "max_batch=%d", c.max_batch);
+  CPP_TRY(value.init(c.value)); CPP_TRY(mu.init(c.mu)); CPP_TRY(l.init(c.l));
+  A = c.action_dim;
+  CPP_REQUIRE(A >= 1 && A <= 8, "action_dim=%d unsupported", A);
+  CPP_REQUIRE(value.out_width() == 1 && mu.out_width() == A && l.out_width() == A * (A + 1) / 2, "NAF head widths do not match action_dim");
+  CPP_REQUIRE(value.pixels == mu.pixels && mu.pixels == l.pixels, "NAF nets read the same state");
+  CPP_REQUIRE(c.optimiser >= 0 && c.optimiser <= 2, "optimiser kind %d", c.optimiser);
+  n_v = value.nparams; n_m = mu.nparams; n_l = l.nparams;
+  off_m = pad4(n_v); off_l = off_m + pad4(n_m); off_loss = off_l + pad4(n_l); total = off_loss + 4;
+  return CPP_OK;
+}
+
+void NAF::carve(void* ws, bool assign) {
+  Carver cv(ws);
+  const int B = cfg.max_batch, C = value.pixels ? value.spec.Cin : 1, NL = A * (A + 1) / 2;
+  char* wv = cv.take<char>(value.workspace_bytes(B)); char* wm = cv.take<char>(mu.workspace_bytes(B));
+  char* wl = cv.take<char>(l.workspace_bytes(B)); char* wt = cv.take<char>(value.workspace_bytes(B));
+  float* V_ = cv.take<float>(B); float* V2_ = cv.take<float>(B); float* mu_ = cv.take<float>((size_t)B * A); float* lv_ = cv.take<float>((size_t)B * NL);
+  float* dV_ = cv.take<float>(B); float* dmu_ = cv.take<float>((size_t)B * A); float* dl_ = cv.take<float>((size_t)B * NL);
+  float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
+  double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(norm_scratch_doubles());
+  float* sc = cv.take<float>(4);
+  ws_bytes = cv.off;
+  if (assign) {
+    ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; V = V_; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
+    mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
+  }
+}
+
+int NAF::bind(const cpp_naf_buffers& b) {
+  CPP_REQUIRE(b.params && b.target_params && b.grads && b.workspace, "null buffer");
+  CPP_REQUIRE(cfg.optimiser == 0 || b.slots != nullptr, "optimiser needs slots");
+  CPP_REQUIRE(cfg.optimiser != 2 || b.opt_state != nullptr, "Adam needs opt_state");
+  carve(nullptr, false);
+  CPP_REQUIRE(b.workspace_bytes >= (int64_t)ws_bytes, "workspace too small: %lld < %lld", (long long)b.workspace_bytes, (long long)ws_bytes);
+  buf = b; bound = true;
+  carve(b.workspace, true);
+  pinned1 = pinned2 = nullptr;
+  return CPP_OK;
+}
+
+int NAF::stats_for(const void* x, int is_f16, int B, float* dst, const float* pinned, const float** out, cudaStream_t s) {
+  *out = nullptr;
+  if (!value.pixels) return CPP_OK;
+  if (pinned) { *out = pinned; return CPP_OK; }
+  CPP_TRY(launch_channel_moments(x, is_f16, (int64_t)B * value.spec.H * value.spec.W, value.spec.Cin, mom_scratch, dst, s));
+  *out = dst;
+  return CPP_OK;
+}
+
+int NAF::forward_all(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                     int B, int B_global, bool grads, float* adv_out, float* loss_flag, cudaStream_t s) {
+  const float *m1, *m2;
+  CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
+  CPP_TRY(stats_for(s2, is_f16, B, mi2, pinned2, &m2, s));
+  cur_m1 = m1;
+  CPP_TRY(value.forward(buf.params, s1, is_f16, m1, nullptr, B, ws_v, V, s));
+  CPP_TRY(mu.forward(buf.params + off_m, s1, is_f16, m1, nullptr, B, ws_m, muo, s));
+  CPP_TRY(l.forward(buf.params + off_l, s1, is_f16, m1, nullptr, B, ws_l, lv, s));
+  CPP_TRY(value.forward(buf.target_params, s2, is_f16, m2, nullptr, B, ws_t, V2, s));       // target_value_net, naf_cartpole.py:225-227
+  CPP_TRY(launch_naf_head(V, muo, lv, action, reward, mask, V2, cfg.discount, B, A, B_global,
+                          grads ? dV : nullptr, dmu, dl, adv_out, loss_flag, s));
+  return CPP_OK;
+}
+
+int NAF::backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                  int B, int B_global, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  CPP_TRY(forward_all(s1, action, reward, mask, s2, is_f16, B, B_global, true, nullptr, buf.grads + off_loss, s));
+  CPP_TRY(value.backward(buf.params, s1, is_f16, cur_m1, B, ws_v, dV, buf.grads, nullptr, s));
+  CPP_TRY(mu.backward(buf.params + off_m, s1, is_f16, cur_m1, B, ws_m, dmu, buf.grads + off_m, nullptr, s));
+  CPP_TRY(l.backward(buf.params + off_l, s1, is_f16, cur_m1, B, ws_l, dl, buf.grads + off_l, nullptr, s));
+  return CPP_OK;
+}
+
+int NAF::apply(int check, float* loss_host, cudaStream_t s) {
+  CPP_NEED_BOUND();
+  CPP_TRY(launch_global_norm_scale(buf.grads, off_loss, cfg.gradient_clip, norm_scratch, scale2, s));
+  // the update is skipped on device when the non-finite flag is set (tf.check_numerics aborts the step)
+  CPP_TRY(launch_optimiser(cfg.optimiser, buf.params, buf.grads, scale2, off_loss, cfg.lr, cfg.momentum, cfg.beta1, cfg.beta2,
+                           cfg.eps, buf.slots, buf.opt_state, check ? buf.grads + off_loss + 1 : nullptr, s));
+  if (loss_host != nullptr || check) {
+    float lf[2];
+    CPP_CHECK_CUDA(cudaMemcpyAsync(lf, buf.grads + off_loss, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CPP_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (loss_host) *loss_host = lf[0];
+    if (check && (lf[1] != 0.f || !isfinite(lf[0]))) {
+      set_error("check_numerics: non-finite l_values / L / loss (naf_cartpole.py:242-245)");
+      return CPP_ERR_NUMERICS;
+    }
+  }
+  return CPP_OK;
+}
+
+int NAF::debug_values(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                      int B, float* l_out, float* loss, float* V_out, float* A_out, float* V2_out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  CPP_TRY(forward_all(s1, action, reward, mask, s2, is_f16, B, B, false, A_out, scale2, s));
+  const int NL = A * (A + 1) / 2;
+  CPP_CHECK_CUDA(cudaMemcpyAsync(l_out, lv, (size_t)B * NL * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CPP_CHECK_CUDA(cudaMemcpyAsync(loss, scale2, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CPP_CHECK_CUDA(cudaMemcpyAsync(V_out, V, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CPP_CHECK_CUDA(cudaMemcpyAsync(V2_out, V2, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return CPP_OK;
+}
+
+int NAF::action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  const float* m;
+  CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));
+  return mu.forward(buf.params + off_m, state, is_f16, m, nullptr, B, ws_t, out, s);
+}
+
+int NAF::value_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  const float* m;
+  CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));
+  return value.forward(buf.params, state, is_f16, m, nullptr, B, ws_t, out, s);
+}
+
+int NAF::update_targets(float coeff, cudaStream_t s) {
+  CPP_NEED_BOUND();
+  return launch_soft_update(buf.target_params, buf.params, coeff, pad4(n_v), s);
+}
+
+// ============================================================================ LRPG
+int LRPG::init(const cpp_lrpg_config& c) {
+  cfg = c;
+  CPP_REQUIRE(c.max_batch >= 1, "max_batch=%d", c.max_batch);
+  CPP_TRY(model.init(c.model));
+  CPP_REQUIRE(!model.pixels, "lrpg_cartpole.py:42 asserts low-dim state");
+  n = model.nparams;
+  return CPP_OK;
+}
+
+void LRPG::carve(void* ws, bool assign) {
+  Carver cv(ws);
+  const int B = cfg.max_batch, K = model.out_width();
+  char* wm = cv.take<char>(model.workspace_bytes(B));
+  float* lg = cv.take<float>((size_t)B * K); float* dlg = cv.take<float>((size_t)B * K);
+  double* nsc = cv.take<double>(norm_scratch_doubles()); float* sc = cv.take<float>(4);
+  ws_bytes = cv.off;
+  if (assign) { ws_m = wm; logits = lg; dlogits = dlg; norm_scratch = nsc; scale2 = sc; }
+}
+
+int LRPG::bind(const cpp_lrpg_buffers& b) {
+  CPP_REQUIRE(b.params && b.grads && b.workspace, "null buffer");
+  CPP_REQUIRE(cfg.optimiser == 0 || b.slots != nullptr, "optimiser needs slots");
+  CPP_REQUIRE(cfg.optimiser != 2 || b.opt_state != nullptr, "Adam needs opt_state");
+  carve(nullptr, false);
+  CPP_REQUIRE(b.workspace_bytes >= (int64_t)ws_bytes, "workspace too small");
+  buf = b; bound = true;
+  carve(b.workspace, true);
+  return CPP_OK;
+}
+
+int LRPG::train(const float* obs, const int32_t* actions, const float* adv, int N, float* loss_host, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(N);
+  CPP_TRY(model.forward(buf.params, obs, 0, nullptr, nullptr, N, ws_m, logits, s));
+  CPP_TRY(launch_lrpg_loss(logits, actions, adv, N, model.out_width(), dlogits, scale2 + 2, s));
+  CPP_TRY(model.backward(buf.params, obs, 0, nullptr, N, ws_m, dlogits, buf.grads, nullptr, s));
+  CPP_TRY(launch_global_norm_scale(buf.grads, pad4(n), cfg.gradient_clip, norm_scratch, scale2, s));
+  CPP_TRY(launch_optimiser(cfg.optimiser, buf.params, buf.grads, scale2, pad4(n), cfg.lr, cfg.momentum, cfg.beta1, cfg.beta2,
+                           cfg.eps, buf.slots, buf.opt_state, nullptr, s));
+  if (loss_host) {
+    CPP_CHECK_CUDA(cudaMemcpyAsync(loss_host, scale2 + 2, sizeof(float), cudaMemcpyDeviceToHost, s));
+    CPP_CHECK_CUDA(cudaStreamSynchronize(s));
+  }
+  return CPP_OK;
+}
+
+int LRPG::get_logits(const float* obs, int N, float* out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(N);
+  return model.forward(buf.params, obs, 0, nullptr, nullptr, N, ws_m, out, s);
+}
+
+}  // namespace cpp

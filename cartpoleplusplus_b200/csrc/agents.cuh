@@ -1,0 +1,88 @@
+// Agent-level step objects behind the C ABI (see include/cartpolepp.h).
+#pragma once
+#include "net.cuh"
+
+namespace cpp {
+
+struct DDPG {
+  cpp_ddpg_config cfg;
+  Net actor, critic;
+  int64_t n_a = 0, n_c = 0, off_c = 0, off_loss = 0, total = 0;
+  cpp_ddpg_buffers buf{};
+  bool bound = false;
+  size_t ws_bytes = 0;
+  // carved workspace
+  char *ws_actor = nullptr, *ws_critic = nullptr, *ws_target = nullptr;
+  float *mu = nullptr, *dqda = nullptr, *neg = nullptr, *mu2 = nullptr, *q = nullptr, *q2 = nullptr, *td = nullptr, *dq = nullptr;
+  float *ones = nullptr, *mi1 = nullptr, *mi2 = nullptr, *scale2 = nullptr;
+  double *mom_scratch = nullptr, *norm_scratch = nullptr;
+  const float *pinned1 = nullptr, *pinned2 = nullptr, *cur_m1 = nullptr;
+  bool ones_ready = false, critic_trunk_valid = false;
+  int trunk_B = 0;
+
+  int init(const cpp_ddpg_config& c);
+  void carve(void* ws, bool assign);
+  int bind(const cpp_ddpg_buffers& b);
+  int stats_for(const void* x, int is_f16, int B, float* dst, const float* pinned, const float** out, cudaStream_t s);
+  int actor_backward(const void* s1, int is_f16, int B, int B_global, cudaStream_t s);
+  int actor_apply(cudaStream_t s);
+  int critic_forward_td(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                        int B, int B_global, bool reuse, float* td_out, float* dq_out, float* loss_flag, cudaStream_t s);
+  int critic_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                      int B, int B_global, int reuse, cudaStream_t s);
+  int critic_apply(cudaStream_t s);
+  int check_loss(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
+                 float* loss, float* td_out, float* q_out, cudaStream_t s);
+  int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
+  int update_targets(float coeff, cudaStream_t s);
+};
+
+struct NAF {
+  cpp_naf_config cfg;
+  Net value, mu, l;
+  int A = 2;
+  int64_t n_v = 0, n_m = 0, n_l = 0, off_m = 0, off_l = 0, off_loss = 0, total = 0;
+  cpp_naf_buffers buf{};
+  bool bound = false;
+  size_t ws_bytes = 0;
+  char *ws_v = nullptr, *ws_m = nullptr, *ws_l = nullptr, *ws_t = nullptr;
+  float *V = nullptr, *V2 = nullptr, *muo = nullptr, *lv = nullptr, *dV = nullptr, *dmu = nullptr, *dl = nullptr;
+  float *mi1 = nullptr, *mi2 = nullptr, *scale2 = nullptr;
+  double *mom_scratch = nullptr, *norm_scratch = nullptr;
+  const float *pinned1 = nullptr, *pinned2 = nullptr, *cur_m1 = nullptr;
+
+  int init(const cpp_naf_config& c);
+  void carve(void* ws, bool assign);
+  int bind(const cpp_naf_buffers& b);
+  int stats_for(const void* x, int is_f16, int B, float* dst, const float* pinned, const float** out, cudaStream_t s);
+  int forward_all(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
+                  int B_global, bool grads, float* adv_out, float* loss_flag, cudaStream_t s);
+  int backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
+               int B_global, cudaStream_t s);
+  int apply(int check, float* loss_host, cudaStream_t s);
+  int debug_values(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
+                   float* l_out, float* loss, float* V_out, float* A_out, float* V2_out, cudaStream_t s);
+  int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
+  int value_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
+  int update_targets(float coeff, cudaStream_t s);
+};
+
+struct LRPG {
+  cpp_lrpg_config cfg;
+  Net model;
+  int64_t n = 0;
+  cpp_lrpg_buffers buf{};
+  bool bound = false;
+  size_t ws_bytes = 0;
+  char* ws_m = nullptr;
+  float *logits = nullptr, *dlogits = nullptr, *scale2 = nullptr;
+  double* norm_scratch = nullptr;
+
+  int init(const cpp_lrpg_config& c);
+  void carve(void* ws, bool assign);
+  int bind(const cpp_lrpg_buffers& b);
+  int train(const float* obs, const int32_t* actions, const float* adv, int N, float* loss_host, cudaStream_t s);
+  int get_logits(const float* obs, int N, float* out, cudaStream_t s);
+};
+
+}  // namespace cpp

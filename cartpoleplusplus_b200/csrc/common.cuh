@@ -1,0 +1,88 @@
+// Shared helpers for libcartpolepp (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/cartpolepp.h"
+
+namespace cpp {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define CPP_CHECK_CUDA(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      cpp::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e), \
+                     cudaGetErrorString(_e));                                           \
+      return CPP_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+extern long long g_launch_count;    // kernels launched by this library (capi.cu)
+#define CPP_CHECK_LAUNCH() do { ++cpp::g_launch_count; CPP_CHECK_CUDA(cudaGetLastError()); } while (0)
+
+#define CPP_REQUIRE(cond, ...)                \
+  do {                                        \
+    if (!(cond)) {                            \
+      cpp::set_error(__VA_ARGS__);            \
+      return CPP_ERR_INVALID;                 \
+    }                                         \
+  } while (0)
+
+#define CPP_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != CPP_OK) return _s; \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+constexpr int kNumSMs = 148;      // B200
+constexpr int kConvCout = 10;     // every conv of the reference trunk has 10 filters (base_network.py:103,111,119)
+
+// ---- kernels launched from more than one translation unit (declared here, defined in the .cu named)
+
+// elementwise.cu
+int launch_state_to_f32(const void* state, int is_f16, int B, int dim, float* dst, int ld, cudaStream_t s);
+int launch_copy_cols(const float* src, int src_ld, int B, int cols, float* dst, int dst_ld, int dst_col0, cudaStream_t s);
+int launch_act_grad(const float* d_out, int d_ld, const float* out, int out_ld, int act, int B, int n, float* d_pre, int p_ld, cudaStream_t s);
+int launch_colsum(const float* x, int ld, int B, int n, float* out, cudaStream_t s);
+int launch_scale_copy(const float* src, float scale, int64_t n, float* dst, cudaStream_t s);
+int launch_fill(float* dst, float v, int64_t n, cudaStream_t s);
+
+// fc.cu : C[M,N] = opA(A)[M,K] * opB(B)[K,N]  (+ epilogue)
+enum { EPI_NONE = 0, EPI_BIAS_ACT = 1, EPI_RELU_MASK = 2 };
+struct GemmArgs {
+  const float* A; int lda; int transA;      // transA: A stored [K][M]
+  const float* B; int ldb; int transB;      // transB: B stored [N][K]
+  float* C; int ldc;
+  int M, N, K;
+  int epi; const float* bias; int act;      // EPI_BIAS_ACT
+  const float* aux; int aux_ld; int mask_cols;   // EPI_RELU_MASK: C[m][n] *= (aux[m][n] > 0) for n < mask_cols
+};
+int launch_gemm(const GemmArgs& g, cudaStream_t s);
+
+// conv.cu
+struct ConvLayer {
+  int H, W, Cin, KS;                // input spatial size / channels, kernel size (5 or 3); Cout = 10
+  int PH() const { return H / 2; }
+  int PW() const { return W / 2; }
+};
+// y = maxpool2x2(relu(conv_same(x, w) + b)); x is fp16 + whitening (mean_inv != NULL) or fp32
+int launch_conv_fwd(const ConvLayer& L, const void* x, int x_is_f16, const float* mean_inv,
+                    const float* w, const float* b, int B, float* pooled, uint8_t* amax, cudaStream_t s);
+// d(x) of the layer, from the pooled-output gradient: dx f32 [B][H][W][Cin==10]
+int launch_conv_dgrad(const ConvLayer& L, const float* d_pooled, const uint8_t* amax, const float* w,
+                      int B, float* dx, cudaStream_t s);
+// d(w), d(b); partials scratch f32[conv_wgrad_scratch_floats(L)]
+int64_t conv_wgrad_scratch_floats(const ConvLayer& L);
+int launch_conv_wgrad(const ConvLayer& L, const void* x, int x_is_f16, const float* mean_inv,
+                      const float* d_pooled, const uint8_t* amax, int B,
+                      float* dw, float* db, float* scratch, cudaStream_t s);
+
+}  // namespace cpp

@@ -1,0 +1,198 @@
+// Net: parameter layout, activation workspace, forward and backward of one reference network.
+#include "net.cuh"
+
+namespace cpp {
+
+int Net::init(const cpp_net_spec& s) {
+  spec = s;
+  pixels = s.pixels != 0;
+  n_fc = s.n_fc;
+  concat_at = s.concat_at;
+  action_dim = s.action_dim;
+  CPP_REQUIRE(n_fc >= 1 && n_fc <= CPP_MAX_FC, "n_fc=%d out of range", n_fc);
+  CPP_REQUIRE(concat_at < n_fc, "concat_at=%d out of range", concat_at);
+  CPP_REQUIRE(concat_at < 0 || action_dim >= 1, "action concat needs action_dim >= 1");
+  vars.clear();
+  int64_t off = 0;
+  auto add_var = [&](int nd, int64_t a, int64_t b, int64_t c, int64_t d) {
+    VarInfo v; v.offset = off; v.ndim = nd; v.shape[0] = a; v.shape[1] = b; v.shape[2] = c; v.shape[3] = d;
+    int64_t n = 1; for (int i = 0; i < nd; ++i) n *= v.shape[i];
+    vars.push_back(v); off += n;
+  };
+  if (pixels) {
+    CPP_REQUIRE(s.H >= 8 && s.W >= 8 && s.Cin >= 1, "pixel state %dx%dx%d too small (three 2x2 pools)", s.H, s.W, s.Cin);
+    CPP_REQUIRE(!(concat_at == 0), "action concat in front of the first FC layer is a low-dim-only layout");
+    int h = s.H, w = s.W, cin = s.Cin;
+    const int ks[3] = {5, 5, 3};                       // base_network.py:103,111,119
+    for (int i = 0; i < 3; ++i) {
+      conv[i].H = h; conv[i].W = w; conv[i].Cin = cin; conv[i].KS = ks[i];
+      off_conv_w[i] = off; add_var(4, ks[i], ks[i], cin, kConvCout);
+      off_conv_b[i] = off; add_var(1, kConvCout, 1, 1, 1);
+      h /= 2; w /= 2; cin = kConvCout;
+    }
+    feat = h * w * kConvCout;
+  } else {
+    CPP_REQUIRE(s.input_dim >= 1, "input_dim=%d", s.input_dim);
+    feat = s.input_dim;
+  }
+  int d = feat;
+  for (int i = 0; i < n_fc; ++i) {
+    CPP_REQUIRE(s.fc_out[i] >= 1, "fc_out[%d]=%d", i, s.fc_out[i]);
+    CPP_REQUIRE(s.fc_act[i] >= 0 && s.fc_act[i] <= 2, "fc_act[%d]=%d", i, s.fc_act[i]);
+    CPP_REQUIRE(i == n_fc - 1 || s.fc_act[i] == 1, "hidden FC layers are ReLU in the reference (layer %d)", i);
+    in_dim[i] = d + (concat_at == i ? action_dim : 0);
+    out_dim[i] = s.fc_out[i];
+    act[i] = s.fc_act[i];
+    off_fc_w[i] = off; add_var(2, in_dim[i], out_dim[i], 1, 1);
+    off_fc_b[i] = off; add_var(1, out_dim[i], 1, 1, 1);
+    d = out_dim[i];
+  }
+  for (int i = 0; i < n_fc; ++i) out_ld[i] = (i + 1 < n_fc) ? in_dim[i + 1] : out_dim[i];
+  nparams = off;
+  return CPP_OK;
+}
+
+Net::Layout Net::layout(int B) const {
+  Layout L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (size_t)round_up((int64_t)bytes, 256); return o; };
+  if (B < 1) B = 1;
+  if (pixels) {
+    for (int i = 0; i < 3; ++i) {
+      const size_t n = (size_t)B * conv[i].PH() * conv[i].PW() * kConvCout;
+      L.pooled[i] = take(n * sizeof(float));
+      L.amax[i] = take(n);
+    }
+    // gradients wrt pooled2 / pooled1 (dense, the size of conv3 / conv2 inputs)
+    L.dpool[0] = take((size_t)B * conv[2].H * conv[2].W * kConvCout * sizeof(float));
+    L.dpool[1] = take((size_t)B * conv[1].H * conv[1].W * kConvCout * sizeof(float));
+    int64_t wg = 0;
+    for (int i = 0; i < 3; ++i) { const int64_t w = conv_wgrad_scratch_floats(conv[i]); if (w > wg) wg = w; }
+    L.wgrad = take((size_t)wg * sizeof(float));
+  } else {
+    L.x0 = take((size_t)B * in_dim[0] * sizeof(float));
+  }
+  int maxw = feat;
+  for (int i = 0; i < n_fc; ++i) {
+    L.h[i] = take((size_t)B * out_ld[i] * sizeof(float));
+    if (in_dim[i] > maxw) maxw = in_dim[i];
+    if (out_dim[i] > maxw) maxw = out_dim[i];
+  }
+  L.dA = take((size_t)B * maxw * sizeof(float));
+  L.dB = take((size_t)B * maxw * sizeof(float));
+  L.total = off;
+  return L;
+}
+
+const float* Net::fc_input(const Layout& L, char* ws, int i, int* ld) const {
+  if (i == 0) {
+    if (pixels) { *ld = feat; return reinterpret_cast<const float*>(ws + L.pooled[2]); }
+    *ld = in_dim[0];
+    return reinterpret_cast<const float*>(ws + L.x0);
+  }
+  *ld = out_ld[i - 1];
+  return reinterpret_cast<const float*>(ws + L.h[i - 1]);
+}
+
+int Net::forward(const float* params, const void* state, int is_f16, const float* mean_inv, const float* action,
+                 int B, void* ws_, float* out, cudaStream_t s, int first_fc) const {
+  CPP_REQUIRE(B >= 1, "batch %d", B);
+  CPP_REQUIRE(concat_at < 0 || action != nullptr, "this network needs an action input");
+  char* ws = reinterpret_cast<char*>(ws_);
+  const Layout L = layout(B);
+  if (first_fc == 0) {
+    if (pixels) {
+      CPP_REQUIRE(mean_inv != nullptr, "pixel network needs whitening statistics");
+      const void* x = state; int xf16 = is_f16; const float* mi = mean_inv;
+      for (int i = 0; i < 3; ++i) {
+        float* pooled = reinterpret_cast<float*>(ws + L.pooled[i]);
+        uint8_t* amax = reinterpret_cast<uint8_t*>(ws + L.amax[i]);
+        CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
+        x = pooled; xf16 = 0; mi = nullptr;
+      }
+    } else {
+      CPP_TRY(launch_state_to_f32(state, is_f16, B, feat, reinterpret_cast<float*>(ws + L.x0), in_dim[0], s));
+    }
+  }
+  for (int i = first_fc; i < n_fc; ++i) {
+    int ld;
+    const float* x = fc_input(L, ws, i, &ld);
+    if (concat_at == i)   // tf.concat(1, [hidden, action]), ddpg_cartpole.py:170,175
+      CPP_TRY(launch_copy_cols(action, action_dim, B, action_dim, const_cast<float*>(x), ld, in_dim[i] - action_dim, s));
+    GemmArgs g{};
+    g.A = x; g.lda = ld; g.transA = 0;
+    g.B = params + off_fc_w[i]; g.ldb = out_dim[i]; g.transB = 0;
+    g.C = reinterpret_cast<float*>(ws + L.h[i]); g.ldc = out_ld[i];
+    g.M = B; g.N = out_dim[i]; g.K = in_dim[i];
+    g.epi = EPI_BIAS_ACT; g.bias = params + off_fc_b[i]; g.act = act[i];
+    CPP_TRY(launch_gemm(g, s));
+  }
+  if (out != nullptr) {
+    const int n = out_dim[n_fc - 1];
+    CPP_CHECK_CUDA(cudaMemcpyAsync(out, ws + L.h[n_fc - 1], (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return CPP_OK;
+}
+
+int Net::backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
+                  const float* d_out, float* grads, float* d_action, cudaStream_t s) const {
+  CPP_REQUIRE(B >= 1, "batch %d", B);
+  CPP_REQUIRE(d_action == nullptr || concat_at >= 0, "d_action requested from a network without action input");
+  char* ws = reinterpret_cast<char*>(ws_);
+  const Layout L = layout(B);
+  float* dcur = reinterpret_cast<float*>(ws + L.dA);
+  float* dnext = reinterpret_cast<float*>(ws + L.dB);
+  const int last = n_fc - 1;
+  // gradient wrt the last pre-activation
+  CPP_TRY(launch_act_grad(d_out, out_dim[last], reinterpret_cast<const float*>(ws + L.h[last]), out_ld[last], act[last], B,
+                          out_dim[last], dcur, out_dim[last], s));
+  int dld = out_dim[last];
+  const int stop_at = (grads == nullptr) ? concat_at : 0;   // only d_action wanted: stop once it is known
+  for (int i = last; i >= stop_at; --i) {
+    int xld;
+    const float* x = fc_input(L, ws, i, &xld);
+    if (grads != nullptr) {
+      GemmArgs g{};                                        // dW = x^T . dPre
+      g.A = x; g.lda = xld; g.transA = 1;
+      g.B = dcur; g.ldb = dld; g.transB = 0;
+      g.C = grads + off_fc_w[i]; g.ldc = out_dim[i];
+      g.M = in_dim[i]; g.N = out_dim[i]; g.K = B; g.epi = EPI_NONE;
+      CPP_TRY(launch_gemm(g, s));
+      CPP_TRY(launch_colsum(dcur, dld, B, out_dim[i], grads + off_fc_b[i], s));
+    }
+    const bool need_dx = (i > stop_at) || (i == 0 && pixels && grads != nullptr) || (concat_at == i && d_action != nullptr);
+    if (!need_dx) break;
+    GemmArgs g{};                                          // dX = dPre . W^T, masked by the ReLU of the layer below
+    g.A = dcur; g.lda = dld; g.transA = 0;
+    g.B = params + off_fc_w[i]; g.ldb = out_dim[i]; g.transB = 1;
+    g.C = dnext; g.ldc = in_dim[i];
+    g.M = B; g.N = in_dim[i]; g.K = out_dim[i];
+    if (i > 0) { g.epi = EPI_RELU_MASK; g.aux = x; g.aux_ld = xld; g.mask_cols = out_dim[i - 1]; }
+    else g.epi = EPI_NONE;
+    CPP_TRY(launch_gemm(g, s));
+    if (concat_at == i && d_action != nullptr)
+      CPP_TRY(launch_copy_cols(dnext + (in_dim[i] - action_dim), in_dim[i], B, action_dim, d_action, action_dim, 0, s));
+    float* t = dcur; dcur = dnext; dnext = t;
+    dld = in_dim[i];
+  }
+  if (!pixels || grads == nullptr) return CPP_OK;
+
+  // conv trunk: dcur = d(pooled3) as (B, F); base_network.py:103-123 backwards
+  const float* gp = dcur;
+  for (int i = 2; i >= 0; --i) {
+    const void* x; int xf16; const float* mi;
+    if (i == 0) { x = state; xf16 = is_f16; mi = mean_inv; }
+    else { x = ws + L.pooled[i - 1]; xf16 = 0; mi = nullptr; }
+    const uint8_t* amax = reinterpret_cast<const uint8_t*>(ws + L.amax[i]);
+    CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, gp, amax, B, grads + off_conv_w[i], grads + off_conv_b[i],
+                              reinterpret_cast<float*>(ws + L.wgrad), s));
+    if (i > 0) {
+      float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
+      CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));
+      gp = dx;
+    }
+  }
+  return CPP_OK;
+}
+
+}  // namespace cpp

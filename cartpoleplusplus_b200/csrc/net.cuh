@@ -1,0 +1,64 @@
+// One reference network (base_network.Network subclass): optional conv trunk -> flatten -> FC stack.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace cpp {
+
+struct VarInfo { int64_t offset; int ndim; int64_t shape[4]; };
+
+struct Net {
+  cpp_net_spec spec;
+  bool pixels = false;
+  ConvLayer conv[3];
+  int feat = 0;                       // flattened trunk features, or input_dim
+  int n_fc = 0;
+  int in_dim[CPP_MAX_FC], out_dim[CPP_MAX_FC], act[CPP_MAX_FC], out_ld[CPP_MAX_FC];
+  int concat_at = -1, action_dim = 0;
+  int64_t off_conv_w[3], off_conv_b[3], off_fc_w[CPP_MAX_FC], off_fc_b[CPP_MAX_FC];
+  int64_t nparams = 0;
+  std::vector<VarInfo> vars;
+
+  struct Layout {
+    size_t pooled[3], amax[3], x0, h[CPP_MAX_FC], dA, dB, dpool[2], wgrad, total;
+  };
+
+  int init(const cpp_net_spec& s);
+  Layout layout(int B) const;
+  size_t workspace_bytes(int B) const { return layout(B).total; }
+  int out_width() const { return out_dim[n_fc - 1]; }
+
+  // pointer to the input of FC layer i inside ws, and its leading dimension
+  const float* fc_input(const Layout& L, char* ws, int i, int* ld) const;
+
+  // first_fc == 0: full forward.  first_fc == k > 0: activations below FC layer k are reused from the
+  // previous forward held in ws (k must be <= concat_at or the action unchanged); action is re-copied.
+  int forward(const float* params, const void* state, int is_f16, const float* mean_inv, const float* action,
+              int B, void* ws, float* out, cudaStream_t s, int first_fc = 0) const;
+  // grads == nullptr: only d_action is produced (stops at the concat layer).
+  int backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
+               const float* d_out, float* grads, float* d_action, cudaStream_t s) const;
+};
+
+// elementwise.cu
+int64_t moments_scratch_doubles(int C);
+int launch_channel_moments(const void* x, int is_f16, int64_t n_pix_total, int C, double* scratch, float* mean_inv, cudaStream_t s);
+int launch_td_mse(const float* q, const float* q2, const float* reward, const float* mask, float gamma, int B, int B_global,
+                  float* td, float* dq, float* loss_flag, cudaStream_t s);
+int launch_naf_head(const float* V, const float* mu, const float* lv, const float* u, const float* reward, const float* mask,
+                    const float* V2, float gamma, int B, int A, int B_global, float* dV, float* dmu, float* dl,
+                    float* adv, float* loss_flag, cudaStream_t s);
+int launch_lrpg_loss(const float* logits, const int32_t* actions, const float* adv, int N, int K, float* dlogits, float* loss, cudaStream_t s);
+int64_t norm_scratch_doubles();
+int launch_global_norm_scale(const float* grads, int64_t n, float clip, double* scratch, float* out2, cudaStream_t s);
+int launch_optimiser(int kind, float* params, const float* grads, const float* scale, int64_t n, float lr, float momentum,
+                     float beta1, float beta2, float eps, float* slots, float* opt_state, const float* skip, cudaStream_t s);
+int launch_soft_update(float* target, const float* source, float coeff, int64_t n, cudaStream_t s);
+int launch_gather(const void* slab, const int32_t* s1_idx, const int32_t* s2_idx, const float* action, const float* reward,
+                  const float* mask, const int64_t* idxs, int B, int64_t row_elems, int A, void* o1, void* o2, float* oa,
+                  float* orw, float* om, cudaStream_t s);
+int launch_slot_stats(const void* slab, const int32_t* slots, int n, int64_t n_pix, int C, double* stats, cudaStream_t s);
+int launch_moments_from_slots(const double* stats, const int32_t* slot_table, const int64_t* idxs, int B, int64_t n_pix, int C,
+                              float* mean_inv, cudaStream_t s);
+
+}  // namespace cpp

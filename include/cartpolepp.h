@@ -1,0 +1,262 @@
+/*
+ * cartpolepp.h - C ABI of libcartpolepp.so: the cartpole++ RL-training hot path on B200 (sm_100a).
+ *
+ * The reference (matpalm/cartpoleplusplus) has no FFI: its seam is "a Python method that performs one
+ * tf.Session.run(op, feed_dict)" plus ReplayMemory.batch.  Each entry point
+ * below names the reference call it replaces (file:line relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer documented "dev" is CUDA device memory owned by
+ *     the caller (the Python host allocates it with torch), "host" is host memory.
+ *   - every function returns 0 on success or a negative cpp_status; cpp_last_error() gives the text
+ *     (thread local).  Nothing throws across the ABI, nothing allocates device memory.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless documented.
+ *   - single caller thread per object (the reference is single threaded).
+ */
+#ifndef CARTPOLEPP_H_
+#define CARTPOLEPP_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define CPP_ABI_VERSION 1
+#define CPP_MAX_FC 8
+
+typedef enum {
+  CPP_OK = 0,
+  CPP_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  CPP_ERR_CUDA = -2,         /* CUDA runtime error */
+  CPP_ERR_STATE = -3,        /* object not bound / wrong call order (e.g. update_weights on a non target net) */
+  CPP_ERR_NUMERICS = -4,     /* non-finite value where the reference's tf.check_numerics would raise */
+  CPP_ERR_NCCL = -5
+} cpp_status;
+
+int cpp_version(void);
+const char* cpp_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches) */
+int64_t cpp_launch_count(void);
+
+/* ------------------------------------------------------------------ a1: index sampling (host)
+ * replaces np.random.randint(0, size, n) in ReplayMemory.random_indexes, replay_memory.py:123-129.
+ * MT19937 with numpy-legacy seeding and masked rejection; bit exact with numpy's RandomState. */
+typedef struct cpp_mt19937 cpp_mt19937;
+int cpp_mt_create(cpp_mt19937** out);
+int cpp_mt_destroy(cpp_mt19937* mt);
+int cpp_mt_seed(cpp_mt19937* mt, uint32_t seed);                         /* == np.random.seed(int) */
+int cpp_mt_set_state(cpp_mt19937* mt, const uint32_t* key624, int32_t pos);   /* np.random.get_state()[1:3] */
+int cpp_mt_get_state(const cpp_mt19937* mt, uint32_t* key624, int32_t* pos);
+int cpp_mt_randint(cpp_mt19937* mt, int64_t high, int64_t n, int64_t* out_host);
+
+/* ------------------------------------------------------------------ a2: replay gather (device)
+ * replaces the five fancy-index gathers of ReplayMemory.batch, replay_memory.py:131-138.
+ * state slab fp16 [n_slots][row_elems]; s1_idx/s2_idx int32[N]; action f32[N][A]; reward/mask f32[N].
+ * idxs int64[B] (dev).  Outputs: s1/s2 fp16 [B][row_elems], action [B][A], reward/mask [B]. */
+int cpp_replay_gather(const void* state_slab, const int32_t* s1_idx, const int32_t* s2_idx,
+                      const float* action, const float* reward, const float* mask,
+                      const int64_t* idxs, int32_t B, int64_t row_elems, int32_t action_dim,
+                      void* out_s1, void* out_s2, float* out_action, float* out_reward, float* out_mask,
+                      void* stream);
+/* per-slot per-channel (sum x, sum x^2) in fp64, computed when a state is stored (8f row 1 / 8e):
+ * slot_stats f64[n_slots][2*C]; rows int32[n] lists the slots to (re)compute. */
+int cpp_slot_stats(const void* state_slab, const int32_t* slots, int32_t n, int64_t n_pix, int32_t C,
+                   double* slot_stats, void* stream);
+/* whitening moments of a batch from the per-slot sums of the B selected slots -> mean_inv f32[2*C] */
+int cpp_moments_from_slots(const double* slot_stats, const int32_t* slot_table, const int64_t* idxs,
+                           int32_t B, int64_t n_pix, int32_t C, float* mean_inv, void* stream);
+/* whitening moments straight from a batch (tf.nn.moments, base_network.py:95-96): x is fp16 (is_f16=1)
+ * or fp32 [n_pix_total][C]; scratch f64[cpp_moments_scratch_doubles(C)]; mean_inv f32[2*C] =
+ * {mean_c}, {rsqrt(var_c + 1e-6)} */
+int64_t cpp_moments_scratch_doubles(int32_t C);
+int cpp_channel_moments(const void* x, int32_t is_f16, int64_t n_pix_total, int32_t C,
+                        double* scratch, float* mean_inv, void* stream);
+
+/* ------------------------------------------------------------------ a3-a6: networks
+ * One reference network = optional conv trunk (Network.simple_conv_net_on, base_network.py:73-127)
+ * -> flatten -> FC stack (hidden_layers_starting_at :58-71) with an optional concat of the action
+ * in front of FC layer `concat_at` (CriticNetwork, ddpg_cartpole.py:161-184).
+ * Parameters live in ONE flat fp32 buffer in TF variable-creation order: conv{1,2,3}/{weights HWIO,
+ * biases}, then per FC layer {weights [in][out], biases}. */
+typedef struct {
+  int32_t pixels;              /* 1: state is (H,W,Cin) image, Cin = 3*cameras*repeats; 0: flat vector */
+  int32_t H, W, Cin;
+  int32_t input_dim;           /* pixels==0: prod(state_shape) */
+  int32_t n_fc;
+  int32_t fc_out[CPP_MAX_FC];
+  int32_t fc_act[CPP_MAX_FC];  /* 0 linear, 1 relu, 2 tanh */
+  int32_t concat_at;           /* -1: no action input */
+  int32_t action_dim;
+} cpp_net_spec;
+
+typedef struct cpp_net cpp_net;
+int cpp_net_create(const cpp_net_spec* spec, cpp_net** out);
+int cpp_net_destroy(cpp_net* net);
+int64_t cpp_net_num_params(const cpp_net* net);
+int32_t cpp_net_num_vars(const cpp_net* net);
+int cpp_net_var_info(const cpp_net* net, int32_t i, int64_t* offset, int32_t* ndim, int64_t* shape4);
+int32_t cpp_net_feature_dim(const cpp_net* net);
+/* bytes of activation workspace one forward(+backward) at batch B needs */
+int64_t cpp_net_workspace_bytes(const cpp_net* net, int32_t B);
+
+/* forward: state fp16/fp32 [B][...]; mean_inv f32[2*Cin] (pixels only; whitening stats of the batch);
+ * action f32[B][A] or NULL; out f32[B][fc_out[last]].  ws is kept for a following backward. */
+int cpp_net_forward(const cpp_net* net, const float* params, const void* state, int32_t state_is_f16,
+                    const float* mean_inv, const float* action, int32_t B, void* ws, float* out, void* stream);
+/* backward of the last forward held in ws: d_out f32[B][out] (gradient wrt the post-activation output);
+ * grads f32[num_params] is OVERWRITTEN (may be NULL: only d_action wanted); d_action f32[B][A] or NULL. */
+int cpp_net_backward(const cpp_net* net, const float* params, const void* state, int32_t state_is_f16,
+                     const float* mean_inv, int32_t B, void* ws, const float* d_out,
+                     float* grads, float* d_action, void* stream);
+
+/* single conv layer of the trunk, for kernel-level parity tests and the roofline timing in bench.py:
+ * slim.conv2d(KSxKS, 10 filters, SAME) + ReLU + slim.max_pool2d(2x2) (base_network.py:103-107).
+ * x: fp16 (whitened on the fly with mean_inv) or fp32 NHWC [B][H][W][Cin]; w HWIO; pooled f32 [B][H/2][W/2][10];
+ * amax u8 same shape (argmax position 0..3, 4 = ReLU closed). */
+int cpp_conv_forward(const void* x, int32_t x_is_f16, const float* mean_inv, const float* w, const float* bias,
+                     int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS, float* pooled, uint8_t* amax, void* stream);
+/* gradient wrt the layer input (needs Cin == 10): dx f32 [B][H][W][10] */
+int cpp_conv_dgrad(const float* d_pooled, const uint8_t* amax, const float* w, int32_t B, int32_t H, int32_t W,
+                   int32_t KS, float* dx, void* stream);
+/* gradient wrt weights (HWIO) and biases; scratch f32[cpp_conv_wgrad_scratch_floats()] */
+int64_t cpp_conv_wgrad_scratch_floats(int32_t H, int32_t W, int32_t Cin, int32_t KS);
+int cpp_conv_wgrad(const void* x, int32_t x_is_f16, const float* mean_inv, const float* d_pooled, const uint8_t* amax,
+                   int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS, float* dw, float* db, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------ a11-a13: clip / optimiser / target copy
+ * util.clip_and_debug_gradients util.py:45-58 (tf.clip_by_global_norm): writes
+ * scale = clip*min(1/||g||, 1/clip) and ||g|| to out2 f32[2] (dev); scratch f64[cpp_norm_scratch_doubles()].
+ * clip <= 0 disables clipping (scale = 1). */
+int64_t cpp_norm_scratch_doubles(void);
+int cpp_global_norm_scale(const float* grads, int64_t n, float clip, double* scratch, float* out2, void* stream);
+/* util.construct_optimiser util.py:73-76: kind 0 GradientDescent, 1 Momentum, 2 Adam.  g is multiplied by
+ * *scale (dev, may be NULL).  slots: Momentum f32[n], Adam f32[2n]; opt_state f32[2] (beta powers, dev). */
+int cpp_optimiser_apply(int32_t kind, float* params, const float* grads, const float* scale, int64_t n,
+                        float lr, float momentum, float beta1, float beta2, float eps,
+                        float* slots, float* opt_state, void* stream);
+/* Network._create_variables_copy_op base_network.py:20-33: t <- t - c*(t - s) */
+int cpp_soft_update(float* target, const float* source, float coeff, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ a7-a9: DDPG agent
+ * ActorNetwork.train ddpg_cartpole.py:140-145, CriticNetwork.train :230-237, check_loss :239-248,
+ * action_given :121-138 (noise stays on the host), update_weights base_network.py:45-49. */
+typedef struct {
+  cpp_net_spec actor, critic;
+  float actor_lr, critic_lr, discount, gradient_clip, target_update_rate;
+  int32_t max_batch;
+  int32_t world_size, rank;    /* data parallel: grads are summed over ranks before clip+apply */
+} cpp_ddpg_config;
+
+typedef struct {
+  float* params;          /* [actor | critic] contiguous, fp32 */
+  float* target_params;   /* [target_actor | target_critic] */
+  float* grads;           /* [actor | critic | loss | nonfinite flag] : the flat all-reduce buffer */
+  void* workspace; int64_t workspace_bytes;   /* >= cpp_ddpg_workspace_bytes() */
+} cpp_ddpg_buffers;
+
+typedef struct cpp_ddpg cpp_ddpg;
+int cpp_ddpg_create(const cpp_ddpg_config* cfg, cpp_ddpg** out);
+int cpp_ddpg_destroy(cpp_ddpg* a);
+int64_t cpp_ddpg_workspace_bytes(const cpp_ddpg* a);
+/* flat-buffer layout (floats): out5 = {n_actor, n_critic, offset_critic, offset_loss, total}; every part starts
+ * 16-byte aligned, gaps stay zero; grads[offset_loss] = loss, [offset_loss+1] = non-finite count */
+int cpp_ddpg_layout(const cpp_ddpg* a, int64_t* out5);
+int cpp_ddpg_bind(cpp_ddpg* a, const cpp_ddpg_buffers* b);
+/* whitening statistics: by default computed from the batch handed to each call; a data-parallel or
+ * replay-resident caller may pin them (mean_inv f32[2*Cin] dev for s1 and s2) for the next calls */
+int cpp_ddpg_set_moments(cpp_ddpg* a, const float* mean_inv_s1, const float* mean_inv_s2);
+/* phase A: forward/backward only -> grads[actor part]; phase B: clip + SGD.  actor_train = A;B.
+ * Between A and B a data-parallel host all-reduces (sum) the actor part of `grads`. */
+int cpp_ddpg_actor_backward(cpp_ddpg* a, const void* s1, int32_t is_f16, int32_t B, int32_t B_global, void* stream);
+int cpp_ddpg_actor_apply(cpp_ddpg* a, void* stream);
+int cpp_ddpg_actor_train(cpp_ddpg* a, const void* s1, int32_t is_f16, int32_t B, void* stream);
+int cpp_ddpg_critic_backward(cpp_ddpg* a, const void* s1, const float* action, const float* reward,
+                             const float* mask, const void* s2, int32_t is_f16, int32_t B, int32_t B_global,
+                             int32_t reuse_s1_trunk, void* stream);
+int cpp_ddpg_critic_apply(cpp_ddpg* a, void* stream);
+int cpp_ddpg_critic_train(cpp_ddpg* a, const void* s1, const float* action, const float* reward,
+                          const float* mask, const void* s2, int32_t is_f16, int32_t B, void* stream);
+/* out: loss f32[1], td f32[B], q f32[B] (dev) */
+int cpp_ddpg_check_loss(cpp_ddpg* a, const void* s1, const float* action, const float* reward,
+                        const float* mask, const void* s2, int32_t is_f16, int32_t B,
+                        float* loss, float* td, float* q, void* stream);
+int cpp_ddpg_action_given(cpp_ddpg* a, const void* state, int32_t is_f16, int32_t B, float* out_action, void* stream);
+int cpp_ddpg_update_targets(cpp_ddpg* a, float coeff, void* stream);
+
+/* ------------------------------------------------------------------ a10: NAF agent
+ * NafNetwork.train naf_cartpole.py:264-272, debug_values :274-284, action_given :247-262,
+ * ValueNetwork.value_given :111-114, target update :373. */
+typedef struct {
+  cpp_net_spec value, mu, l;
+  float discount, gradient_clip, target_update_rate;
+  int32_t optimiser;            /* 0 GradientDescent 1 Momentum 2 Adam */
+  float lr, momentum, beta1, beta2, eps;
+  int32_t max_batch, action_dim;
+  int32_t world_size, rank;
+} cpp_naf_config;
+
+typedef struct {
+  float* params;          /* [value | naf/output_action | naf/l_values] */
+  float* target_params;   /* [target_value] */
+  float* grads;           /* [value | mu | l | loss | nonfinite flag] */
+  float* slots;           /* optimiser slots: 0 / n / 2n floats */
+  float* opt_state;       /* f32[2] */
+  void* workspace; int64_t workspace_bytes;
+} cpp_naf_buffers;
+
+typedef struct cpp_naf cpp_naf;
+int cpp_naf_create(const cpp_naf_config* cfg, cpp_naf** out);
+int cpp_naf_destroy(cpp_naf* a);
+int64_t cpp_naf_workspace_bytes(const cpp_naf* a);
+/* out7 = {n_value, n_mu, n_l, offset_mu, offset_l, offset_loss, total} */
+int cpp_naf_layout(const cpp_naf* a, int64_t* out7);
+int cpp_naf_bind(cpp_naf* a, const cpp_naf_buffers* b);
+int cpp_naf_set_moments(cpp_naf* a, const float* mean_inv_s1, const float* mean_inv_s2);
+int cpp_naf_backward(cpp_naf* a, const void* s1, const float* action, const float* reward, const float* mask,
+                     const void* s2, int32_t is_f16, int32_t B, int32_t B_global, void* stream);
+/* returns CPP_ERR_NUMERICS (after a stream sync) when check=1 and l_values/L/loss were non-finite */
+int cpp_naf_apply(cpp_naf* a, int32_t check, float* loss_host, void* stream);
+int cpp_naf_train(cpp_naf* a, const void* s1, const float* action, const float* reward, const float* mask,
+                  const void* s2, int32_t is_f16, int32_t B, float* loss_host, void* stream);
+/* out (dev): l_values [B][A(A+1)/2], loss[1], V[B], A[B], V2[B] */
+int cpp_naf_debug_values(cpp_naf* a, const void* s1, const float* action, const float* reward, const float* mask,
+                         const void* s2, int32_t is_f16, int32_t B,
+                         float* l_values, float* loss, float* V, float* Aout, float* V2, void* stream);
+int cpp_naf_action_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_action, void* stream);
+int cpp_naf_value_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_value, void* stream);
+int cpp_naf_update_targets(cpp_naf* a, float coeff, void* stream);
+
+/* ------------------------------------------------------------------ a14: LRPG
+ * LikelihoodRatioPolicyGradientAgent graph lrpg_cartpole.py:80-130, train :165-182, util.standardise util.py:37-43 */
+typedef struct {
+  cpp_net_spec model;
+  float gradient_clip;
+  int32_t optimiser; float lr, momentum, beta1, beta2, eps;
+  int32_t max_batch;
+} cpp_lrpg_config;
+typedef struct {
+  float* params; float* grads; float* slots; float* opt_state;
+  void* workspace; int64_t workspace_bytes;
+} cpp_lrpg_buffers;
+typedef struct cpp_lrpg cpp_lrpg;
+int cpp_lrpg_create(const cpp_lrpg_config* cfg, cpp_lrpg** out);
+int cpp_lrpg_destroy(cpp_lrpg* a);
+int64_t cpp_lrpg_workspace_bytes(const cpp_lrpg* a);
+int64_t cpp_lrpg_num_params(const cpp_lrpg* a);      /* buffers hold this rounded up to a multiple of 4 floats */
+int cpp_lrpg_bind(cpp_lrpg* a, const cpp_lrpg_buffers* b);
+/* observations f32[N][input_dim], actions int32[N], advantages f32[N] (dev) */
+int cpp_lrpg_train(cpp_lrpg* a, const float* observations, const int32_t* actions, const float* advantages,
+                   int32_t N, float* loss_host, void* stream);
+int cpp_lrpg_logits(cpp_lrpg* a, const float* observations, int32_t N, float* logits, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif  /* CARTPOLEPP_H_ */

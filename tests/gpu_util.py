@@ -1,0 +1,89 @@
+"""Helpers shared by the GPU parity tests: build the drop-in agents with injected weights."""
+import json
+import os
+import numpy as np
+import torch
+
+from cartpoleplusplus_b200 import base_network, ddpg_cartpole, naf_cartpole, lrpg_cartpole
+from cartpoleplusplus_b200.replay_memory import Batch
+
+TOL = 1e-5      # north star: outputs within 1e-5 rel of the CPU reference
+
+
+def rel_err(got, want):
+  """per-tensor max|a-b| / max|b| (SURVEY.md 7.2 'Parity definition')"""
+  got = np.asarray(got, dtype=np.float64).reshape(-1)
+  want = np.asarray(want, dtype=np.float64).reshape(-1)
+  assert got.shape == want.shape, (got.shape, want.shape)
+  den = max(np.abs(want).max(), 1e-30)
+  return float(np.abs(got - want).max() / den)
+
+
+def assert_close(got, want, tol=TOL, what=""):
+  e = rel_err(got, want)
+  assert e <= tol, "%s: rel err %.3e > %.1e" % (what, e, tol)
+  return e
+
+
+def load_golden(golden_dir, name):
+  g = np.load(os.path.join(golden_dir, "nets_%s.npz" % name))
+  return g, json.loads(str(g["meta"]))
+
+
+def pixel_flags(shape):
+  H, W, _, C, R = shape
+  return ["--use-raw-pixels", "--render-height=%d" % H, "--render-width=%d" % W, "--num-cameras=%d" % C,
+          "--action-repeats=%d" % R]
+
+
+def make_ddpg(shape, pixels, values=None, batch_size=8, extra=()):
+  argv = ["--batch-size=%d" % batch_size] + (pixel_flags(shape) if pixels else ["--action-repeats=%d" % shape[0]]) + list(extra)
+  o = ddpg_cartpole.set_opts(ddpg_cartpole.default_opts(argv))
+  s1, s2 = base_network.Placeholder(shape, "s1"), base_network.Placeholder(shape, "s2")
+  actor = ddpg_cartpole.ActorNetwork("actor", s1, 2)
+  critic = ddpg_cartpole.CriticNetwork("critic", actor)
+  tactor = ddpg_cartpole.ActorNetwork("target_actor", s2, 2)
+  tcritic = ddpg_cartpole.CriticNetwork("target_critic", tactor)
+  actor.init_ops_for_training(critic)
+  critic.init_ops_for_training(tcritic)
+  nets = dict(actor=actor, critic=critic, target_actor=tactor, target_critic=tcritic)
+  if values is not None:
+    for n in nets.values():
+      n.set_variables(values)
+  return nets, actor._engine, o
+
+
+def make_naf(shape, pixels, values=None, batch_size=8, optimiser="GradientDescent", optimiser_args=None, extra=()):
+  argv = ["--batch-size=%d" % batch_size, "--optimiser=%s" % optimiser,
+          "--optimiser-args=%s" % json.dumps(optimiser_args or {"learning_rate": 0.001})]
+  argv += (pixel_flags(shape) if pixels else ["--action-repeats=%d" % shape[0]]) + list(extra)
+  o = naf_cartpole.set_opts(naf_cartpole.default_opts(argv))
+  s1, s2 = base_network.Placeholder(shape, "s1"), base_network.Placeholder(shape, "s2")
+  value = naf_cartpole.ValueNetwork("value", s1, o.hidden_layers)
+  tvalue = naf_cartpole.ValueNetwork("target_value", s2, o.hidden_layers)
+  naf = naf_cartpole.NafNetwork("naf", s1, s2, value, tvalue, 2)
+  nets = dict(value=value, target_value=tvalue, mu=naf.mu_net, l=naf.l_net)
+  if values is not None:
+    for n in nets.values():
+      n.set_variables(values)
+  return naf, nets, naf._engine, o
+
+
+def golden_values(g, prefix="P0/"):
+  return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}
+
+
+def golden_batch(g, step):
+  return Batch(g["step%d/s1" % step], g["step%d/a" % step], g["step%d/r" % step], g["step%d/m" % step], g["step%d/s2" % step])
+
+
+def flat_of(net):
+  return net.flat_params().detach().cpu().numpy()
+
+
+def names_of(net):
+  return [v.name for v in net._variables()]
+
+
+def golden_flat(g, net, prefix):
+  return np.concatenate([np.asarray(g[prefix + n], dtype=np.float64).reshape(-1) for n in names_of(net)])

@@ -1,0 +1,257 @@
+"""GPU parity of the network arithmetic (a3-a14) through the drop-in classes / C ABI against the fp64 oracle:
+committed golden vectors (small), live oracle runs at BASELINE sizes, and size-independent properties.
+Tolerance: 1e-5 relative (north star), measured per tensor as max|a-b|/max|b|."""
+import json
+import numpy as np
+import pytest
+import torch
+
+from tests import gpu_util as U
+from oracle import nets_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------ DDPG
+@pytest.mark.parametrize("name", ["ddpg_pixel", "ddpg_pixel_odd", "ddpg_lowdim"])
+def test_ddpg_golden(golden_dir, name):
+  g, meta = U.load_golden(golden_dir, name)
+  shape, pixels = tuple(meta["state_shape"]), meta["pixels"]
+  nets, eng, o = U.make_ddpg(shape, pixels, U.golden_values(g), batch_size=meta["B"])
+  worst = {}
+  for step in range(2):
+    batch = U.golden_batch(g, step)
+    loss, td, q = nets["critic"].check_loss(batch)                        # a9: the reference's own observable
+    worst["check_loss"] = U.assert_close(loss, g["step%d/check_loss" % step], what="check_loss")
+    worst["check_td"] = U.assert_close(td, g["step%d/check_td" % step], what="td")
+    worst["check_q"] = U.assert_close(q, g["step%d/check_q" % step], what="q")
+    eng.actor_backward(batch.state_1)
+    ga = eng.buffers["grads"][:eng.n_actor].cpu().numpy()
+    worst["actor_grads"] = U.assert_close(ga, g["step%d/actor_grads" % step], what="actor grads")
+    eng.actor_apply()
+    eng.critic_backward(batch)
+    gc = eng.buffers["grads"][eng.off_critic:eng.off_critic + eng.n_critic].cpu().numpy()
+    worst["critic_grads"] = U.assert_close(gc, g["step%d/critic_grads" % step], what="critic grads")
+    U.assert_close(eng.last_loss(), g["step%d/loss" % step], what="loss")
+    eng.critic_apply()
+    for t, s_ in (("target_actor", "actor"), ("target_critic", "critic")):
+      nets[t]._run_copy_op(nets[t]._create_variables_copy_op(nets[s_], 0.05))
+  for k, net in nets.items():
+    worst["P_" + k] = U.assert_close(U.flat_of(net), U.golden_flat(g, net, "Pfinal/"), what="params " + k)
+  act = nets["actor"].action_given(U.golden_batch(g, 1).state_1[0])
+  assert act.shape == (1, 2)
+  U.assert_close(act, g["action_given0"], what="action_given")
+  print(name, json.dumps(worst))
+
+
+def test_ddpg_train_api_equals_backward_apply(golden_dir):
+  """actor.train / critic.train (the reference methods) == backward + apply; reusing the critic trunk computed
+  during actor.train gives bit-identical critic gradients"""
+  g, meta = U.load_golden(golden_dir, "ddpg_pixel")
+  shape = tuple(meta["state_shape"])
+  batch = U.golden_batch(g, 0)
+  res = []
+  for mode in range(3):
+    nets, eng, o = U.make_ddpg(shape, True, U.golden_values(g), batch_size=meta["B"])
+    if mode == 0:
+      nets["actor"].train(batch.state_1); nets["critic"].train(batch)
+    elif mode == 1:
+      eng.actor_backward(batch.state_1); eng.actor_apply(); eng.critic_backward(batch); eng.critic_apply()
+    else:
+      eng.actor_train(batch.state_1); eng.critic_train(batch, reuse_s1_trunk=True)
+    res.append(torch.cat([eng.buffers["params"], eng.buffers["grads"]]).cpu().numpy())
+  assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+
+
+def _oracle_ddpg(shape, pixels, B, seed, dtype=torch.float64):
+  from oracle.make_golden import ddpg_params, _batch
+  rs = np.random.RandomState(seed)
+  P = ddpg_params(rs, shape, pixels)
+  batch = _batch(rs, B, shape)
+  return P, batch
+
+
+@pytest.mark.parametrize("shape,B", [((64, 64, 3, 1, 3), 256), ((50, 50, 3, 1, 2), 128)], ids=["c3", "default50"])
+def test_ddpg_full_size_vs_live_oracle(shape, B):
+  """BASELINE config 3 (64x64, R=3, C=1, batch 256) and the reference's default 50x50 render"""
+  P, batch = _oracle_ddpg(shape, True, B, 77)
+  values = {k: v.numpy() for k, v in P.items()}
+  nets, eng, o = U.make_ddpg(shape, True, values, batch_size=B)
+  orc = no.DDPGOracle(shape, True, P)
+  b = U.Batch(*batch)
+  l0, td0, q0 = orc.check_loss(batch)
+  loss, td, q = nets["critic"].check_loss(b)
+  e = dict(loss=U.assert_close(loss, l0.numpy(), what="loss"), td=U.assert_close(td, td0.numpy(), what="td"),
+           q=U.assert_close(q, q0.numpy(), what="q"))
+  ra = orc.actor_train(batch[0])
+  eng.actor_backward(b.state_1)
+  e["actor_grads"] = U.assert_close(eng.buffers["grads"][:eng.n_actor].cpu().numpy(),
+                                    torch.cat([x.reshape(-1) for x in ra["grads"]]).numpy(), what="actor grads")
+  eng.actor_apply()
+  rc = orc.critic_train(batch)
+  eng.critic_backward(b, reuse_s1_trunk=True)
+  e["critic_grads"] = U.assert_close(eng.buffers["grads"][eng.off_critic:eng.off_critic + eng.n_critic].cpu().numpy(),
+                                     torch.cat([x.reshape(-1) for x in rc["grads"]]).numpy(), what="critic grads")
+  eng.critic_apply()
+  for k in ("actor", "critic"):
+    want = np.concatenate([orc.P[n].numpy().reshape(-1) for n in U.names_of(nets[k])])
+    e["P_" + k] = U.assert_close(U.flat_of(nets[k]), want, what="params " + k)
+  # the fp32 CPU path's own error against fp64, for context
+  print("full-size errors vs fp64 oracle:", json.dumps(e))
+
+
+def test_ddpg_data_parallel_linearity():
+  """8e on one GPU: gradients of two half batches computed with B_global = B (and the global-batch whitening
+  statistics pinned) sum to the full-batch gradients - the algebra the NCCL all-reduce relies on"""
+  import ctypes as C
+  from cartpoleplusplus_b200 import _lib
+  shape, B = (32, 32, 3, 1, 2), 32
+  P, batch = _oracle_ddpg(shape, True, B, 5)
+  values = {k: v.numpy() for k, v in P.items()}
+  nets, eng, o = U.make_ddpg(shape, True, values, batch_size=B)
+  b = U.Batch(*[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in batch])
+  eng.actor_backward(b.state_1); eng.critic_backward(b)
+  full = eng.buffers["grads"].clone()
+  lib = _lib.lib()
+  # global statistics of s1 / s2
+  mi = []
+  for s in (b.state_1, b.state_2):
+    scratch = torch.zeros(int(lib.cpp_moments_scratch_doubles(6)), dtype=torch.float64, device="cuda")
+    out = torch.zeros(12, dtype=torch.float32, device="cuda")
+    _lib.check(lib.cpp_channel_moments(_lib.ptr(s), 1, C.c_int64(B * 32 * 32), 6, _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr()))
+    mi.append(out)
+  _lib.check(lib.cpp_ddpg_set_moments(eng.handle, _lib.ptr(mi[0]), _lib.ptr(mi[1])))
+  eng.world_size = 2
+  acc = torch.zeros_like(full)
+  for r in range(2):
+    sl = slice(r * B // 2, (r + 1) * B // 2)
+    hb = U.Batch(*[x[sl].contiguous() for x in b])
+    eng.actor_backward(hb.state_1); eng.critic_backward(hb)
+    acc += eng.buffers["grads"]
+  eng.world_size = 1
+  _lib.check(lib.cpp_ddpg_set_moments(eng.handle, None, None))
+  U.assert_close(acc[:eng.off_loss + 1].cpu().numpy(), full[:eng.off_loss + 1].cpu().numpy(), tol=2e-6, what="sharded grads + loss")
+
+
+def test_target_update_properties():
+  shape = (2, 2, 7)
+  nets, eng, o = U.make_ddpg(shape, False, None, batch_size=4)
+  t0 = U.flat_of(nets["target_actor"]).copy(); s0 = U.flat_of(nets["actor"]).copy()
+  nets["target_actor"]._run_copy_op(nets["target_actor"]._create_variables_copy_op(nets["actor"], 0.0))
+  assert np.array_equal(U.flat_of(nets["target_actor"]), t0)                       # c = 0: untouched
+  with pytest.raises(Exception, match="not a target network"):
+    nets["actor"].update_weights()                                                  # base_network.py:47-48
+  nets["target_actor"].set_as_target_network_for(nets["actor"], 0.25)
+  want = t0 - np.float32(1.0) * (t0 - s0)                                            # Appendix A-11: not always == s0
+  assert np.array_equal(U.flat_of(nets["target_actor"]), want)
+  nets["target_actor"].update_weights()
+  t1 = want
+  assert np.array_equal(U.flat_of(nets["target_actor"]), t1 - np.float32(0.25) * (t1 - s0))
+  assert np.array_equal(U.flat_of(nets["actor"]), s0)
+
+
+# ------------------------------------------------------------------------------------------ NAF
+@pytest.mark.parametrize("name", ["naf_pixel", "naf_lowdim"])
+def test_naf_golden(golden_dir, name):
+  g, meta = U.load_golden(golden_dir, name)
+  shape, pixels = tuple(meta["state_shape"]), meta["pixels"]
+  naf, nets, eng, o = U.make_naf(shape, pixels, U.golden_values(g), batch_size=meta["B"],
+                                 optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"])
+  worst = {}
+  for step in range(3):
+    batch = U.golden_batch(g, step)
+    dv = naf.debug_values(batch)
+    for f, v in zip(("l_values", "dbg_loss", "V", "A", "V2"), dv):
+      worst[f] = max(worst.get(f, 0), U.assert_close(v, g["step%d/%s" % (step, f)], what=f))
+    eng.backward(batch)
+    gr = eng.buffers["grads"].cpu().numpy()
+    got = np.concatenate([gr[:eng.n_v], gr[eng.off_m:eng.off_m + eng.n_m], gr[eng.off_l:eng.off_l + eng.n_l]])
+    worst["grads"] = max(worst.get("grads", 0), U.assert_close(got, g["step%d/grads" % step], what="grads"))
+    loss = eng.apply(True)
+    U.assert_close(loss, g["step%d/loss" % step], what="loss")
+    nets["target_value"]._run_copy_op(nets["target_value"]._create_variables_copy_op(nets["value"], 0.05))
+  # Adam / Momentum accumulate per-step rounding: allow 3 steps' worth
+  for k, net in nets.items():
+    worst["P_" + k] = U.assert_close(U.flat_of(net), U.golden_flat(g, net, "Pfinal/"), tol=3e-5, what="params " + k)
+  act = naf.action_given(U.golden_batch(g, 2).state_1[0], add_noise=False)
+  U.assert_close(act, g["action_given0"], what="action_given")
+  print(name, json.dumps(worst))
+
+
+def test_naf_full_size_c4_shard_vs_live_oracle():
+  """BASELINE config 4 (64x64, R=3, C=2 -> 18 channels): one 128-sample shard of the 512 batch"""
+  from oracle.make_golden import _batch
+  shape, B = (64, 64, 3, 2, 3), 128
+  rs = np.random.RandomState(91)
+  P = {}
+  for d in (no.naf_value("value", shape, True), no.naf_mu(shape, True), no.naf_l(shape, True)):
+    P.update(no.init_params(d, rs))
+  P.update(no.retarget({k: v for k, v in P.items() if k.startswith("value/")}, "value", "target_value"))
+  batch = _batch(rs, B, shape)
+  naf, nets, eng, o = U.make_naf(shape, True, {k: v.numpy() for k, v in P.items()}, batch_size=B,
+                                 optimiser="Momentum", optimiser_args={"learning_rate": 0.01, "momentum": 0.9})
+  orc = no.NAFOracle(shape, True, P, optimiser="Momentum", optimiser_args={"learning_rate": 0.01, "momentum": 0.9})
+  r = orc.train(batch)
+  eng.backward(U.Batch(*batch))
+  gr = eng.buffers["grads"].cpu().numpy()
+  got = np.concatenate([gr[:eng.n_v], gr[eng.off_m:eng.off_m + eng.n_m], gr[eng.off_l:eng.off_l + eng.n_l]])
+  e = dict(grads=U.assert_close(got, torch.cat([x.reshape(-1) for x in r["grads"]]).numpy(), what="grads"))
+  e["loss"] = U.assert_close(eng.apply(True), float(r["loss"]), what="loss")
+  for k in ("value", "mu", "l"):
+    want = np.concatenate([orc.P[n].numpy().reshape(-1) for n in U.names_of(nets[k])])
+    e["P_" + k] = U.assert_close(U.flat_of(nets[k]), want, what="params " + k)
+  print("c4 shard errors vs fp64 oracle:", json.dumps(e))
+
+
+def test_naf_check_numerics_raises():
+  from cartpoleplusplus_b200 import CppError
+  shape = (2, 2, 7)
+  naf, nets, eng, o = U.make_naf(shape, False, None, batch_size=4)
+  before = eng.buffers["params"].clone()
+  rs = np.random.RandomState(0)
+  s = rs.uniform(-1, 1, (4,) + shape).astype(np.float16)
+  bad = U.Batch(s, np.array([[np.inf, 0]] * 4, np.float32), np.ones((4, 1), np.float32), np.ones((4, 1), np.float32), s)
+  with pytest.raises(CppError) as ei:
+    naf.train(bad)
+  assert ei.value.status == -4                                          # CPP_ERR_NUMERICS
+  assert torch.equal(eng.buffers["params"], before)                     # the step was not applied
+
+
+# ------------------------------------------------------------------------------------------ LRPG
+def test_lrpg_golden(golden_dir):
+  from cartpoleplusplus_b200 import lrpg_cartpole
+  from cartpoleplusplus_b200.synthetic_env import SyntheticCartpole
+  g, meta = U.load_golden(golden_dir, "lrpg")
+  o = lrpg_cartpole.set_opts(lrpg_cartpole.default_opts(["--optimiser=Adam", "--optimiser-args={\"learning_rate\": 0.01}"]))
+  agent = lrpg_cartpole.LikelihoodRatioPolicyGradientAgent(SyntheticCartpole(o, discrete_actions=True))
+  agent.set_variables(U.golden_values(g))
+  worst = {}
+  for step in (0, 2):
+    obs, act, adv = g["step%d/obs" % step], g["step%d/act" % step], g["step%d/adv" % step]
+    worst["logits"] = U.assert_close(agent.logits_given(obs), g["step%d/logits" % step], what="logits")
+    loss = agent.train(list(obs), list(act), list(adv))
+    worst["loss"] = U.assert_close(loss, g["step%d/loss" % step], what="loss")
+    gr = agent._engine.buffers["grads"][:agent._engine.n].cpu().numpy()
+    worst["grads"] = U.assert_close(gr, g["step%d/grads" % step], what="grads")
+  worst["P"] = U.assert_close(U.flat_of(agent), U.golden_flat(g, agent, "Pfinal/"), tol=3e-5, what="params")
+  print("lrpg", json.dumps(worst))
+
+
+def test_empty_and_oversize_batches_are_rejected():
+  from cartpoleplusplus_b200 import CppError
+  nets, eng, o = U.make_ddpg((2, 2, 7), False, None, batch_size=4)
+  with pytest.raises(CppError):
+    eng.actor_backward(np.zeros((0, 2, 2, 7), np.float16))
+
+
+def test_step_is_deterministic():
+  """fixed-order reductions everywhere: two identical runs give identical bits (needed for DP replicas)"""
+  P, batch = _oracle_ddpg((32, 32, 3, 2, 1), True, 16, 9)
+  outs = []
+  for _ in range(2):
+    nets, eng, o = U.make_ddpg((32, 32, 3, 2, 1), True, {k: v.numpy() for k, v in P.items()}, batch_size=16)
+    b = U.Batch(*batch)
+    for _ in range(3):
+      nets["actor"].train(b.state_1); nets["critic"].train(b)
+    outs.append(eng.buffers["params"].cpu().numpy())
+  assert np.array_equal(outs[0], outs[1])
