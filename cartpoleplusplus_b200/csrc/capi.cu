@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <new>
 #include "agents.cuh"
+#include "conv_tc.cuh"
 
 namespace cpp {
 long long g_launch_count = 0;
@@ -141,6 +142,18 @@ int cpp_conv_wgrad(const void* x, int32_t x_is_f16, const float* mean_inv, const
   CPP_REQUIRE(!x_is_f16 || mean_inv != nullptr, "fp16 input needs whitening stats");
   ConvLayer L; L.H = H; L.W = W; L.Cin = Cin; L.KS = KS;
   return launch_conv_wgrad(L, x, x_is_f16, mean_inv, d_pooled, amax, B, dw, db, scratch, ST(stream));
+  API_END
+}
+
+int64_t cpp_conv_tc_scratch_bytes(int32_t nets, int32_t H, int32_t W, int32_t Cin, int32_t KS) {
+  return tc::conv_tc_scratch_bytes(nets, H, W, Cin, KS);
+}
+int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int32_t nets, const float* const* w,
+                        const float* const* bias, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS,
+                        float* const* pooled, uint8_t* const* amax, void* scratch, void* stream) {
+  API_BEGIN
+  NEED(x_f16); NEED(w); NEED(bias); NEED(pooled); NEED(amax); NEED(scratch);
+  return tc::launch_conv_fwd_tc(x_f16, rows, mean_inv, nets, w, bias, B, H, W, Cin, KS, pooled, amax, scratch, ST(stream));
   API_END
 }
 

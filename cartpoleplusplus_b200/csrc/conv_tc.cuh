@@ -1,0 +1,56 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for the reference conv trunk
+// (Network.simple_conv_net_on, base_network.py:73-127).  See conv_tc.cu for the design.
+#pragma once
+#include "common.cuh"
+
+namespace cpp {
+namespace tc {
+
+constexpr int kMaxNets = 3;     // sibling networks that read the same input (actor+critic; NAF value/mu/l)
+constexpr int kMaxPairs = 64;   // K16 MMAs per accumulator
+constexpr int kPieces = 2;      // fp16 pieces per fp32 weight (hi + lo): 22 mantissa bits
+
+// one K8 slab of the implicit GEMM: 8 consecutive K entries that sit in ONE 16-byte shared-memory row
+struct Slab {
+  int8_t kind;   // 0: 8 channels of one tap (set = channel group); 1: remainder channels packed along kx; 2: zero
+  int8_t set;    // channel group g (kind 0) or packed slab j (kind 1)
+  int8_t ky, kx; // tap (kx unused for kind 1)
+};
+
+struct FwdPlan {
+  // ---- problem
+  const __half* x;          // fp16 NHWC images
+  const int32_t* rows;      // optional: image b of the batch is x + rows[b] * H*W*C (fused replay gather)
+  const __half* bpack;      // packed weights, canonical K-major UMMA layout (built by the prep kernel)
+  const float* corr;        // [(2*PAD+1)^2][nets][10] bias - border-aware mean term, then [1] = 2^-S
+  float* pooled[kMaxNets];
+  uint8_t* amax[kMaxNets];
+  int B, H, W, C, PH, PW, Pq, KS, PAD;
+  int nets, N;              // MMA N = round_up(nets * kPieces * 10, 16)
+  // ---- shared-memory geometry
+  int G8, R, nR;            // full 8-channel groups, remainder channels, packed slabs per ky
+  int n_planes, rows_alloc, plane_bytes;
+  int crh, stage_bytes, use_bulk;   // parity rows per staging group, staging buffer bytes, TMA bulk copy usable
+  int tiles_per_image, tiles_per_unit, units_per_image, n_units;
+  int n_pairs;
+  int smem_bytes;
+  Slab slab[kMaxPairs][2];
+};
+
+struct PrepArgs {
+  const float* w[kMaxNets];      // HWIO (KS,KS,C,10)
+  const float* bias[kMaxNets];
+  const float* mean_inv;         // [mean(C) | inv(C)] or NULL (no whitening fold)
+  __half* bpack;
+  float* corr;
+};
+
+int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS);
+bool conv_tc_supported(int nets, int H, int W, int C, int KS);
+// y_n = maxpool2x2(relu(conv_same(whiten(x), w_n) + b_n)) for n < nets sibling networks in ONE pass over x
+int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int nets,
+                       const float* const* w, const float* const* bias, int B, int H, int W, int C, int KS,
+                       float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s);
+
+}  // namespace tc
+}  // namespace cpp

@@ -127,6 +127,19 @@ int64_t cpp_conv_wgrad_scratch_floats(int32_t H, int32_t W, int32_t Cin, int32_t
 int cpp_conv_wgrad(const void* x, int32_t x_is_f16, const float* mean_inv, const float* d_pooled, const uint8_t* amax,
                    int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS, float* dw, float* db, float* scratch, void* stream);
 
+/* the same layer on the 5th-gen tensor cores (tcgen05.mma, fp16 x fp16 -> fp32 in TMEM) for `nets` (<= 3) sibling
+ * networks that read the same input in ONE pass over x: actor+critic on state_1, the two targets on state_2
+ * (ddpg_cartpole.py:270-273), NAF's value/mu/l trunks (naf_cartpole.py:104,150,175).  x fp16 NHWC (the replay
+ * layout, replay_memory.py:32); rows (dev, optional) = slab row of every batch image, which fuses the gather of
+ * ReplayMemory.batch (replay_memory.py:134,138) into the layer; mean_inv as above (folded into the weights);
+ * w/bias/pooled/amax: HOST arrays of `nets` device pointers; scratch (dev, 256-byte aligned) of
+ * cpp_conv_tc_scratch_bytes() holds the packed weights.  fp32 weights enter as two fp16 pieces (22 mantissa
+ * bits), pixels are exact fp16, accumulation is fp32: results agree with cpp_conv_forward to ~1e-6 relative. */
+int64_t cpp_conv_tc_scratch_bytes(int32_t nets, int32_t H, int32_t W, int32_t Cin, int32_t KS);
+int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int32_t nets,
+                        const float* const* w, const float* const* bias, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                        int32_t KS, float* const* pooled, uint8_t* const* amax, void* scratch, void* stream);
+
 /* ------------------------------------------------------------------ a11-a13: clip / optimiser / target copy
  * util.clip_and_debug_gradients util.py:45-58 (tf.clip_by_global_norm): writes
  * scale = clip*min(1/||g||, 1/clip) and ||g|| to out2 f32[2] (dev); scratch f64[cpp_norm_scratch_doubles()].

@@ -1,0 +1,117 @@
+"""tcgen05 conv forward (cpp_conv_forward_tc) against an fp64 reference and against the exact-fp32 CUDA-core kernel
+(cpp_conv_forward), at the conv1 shapes of the BASELINE configs, with sibling networks fused along N, odd sizes,
+near-constant ("sparse scene") images that stress the whitening fold, and the fused replay-row gather."""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import gpu_util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+  from cartpoleplusplus_b200 import _lib as L
+  return L, L.lib()
+
+
+def make_input(rs, B, H, W, Cin, sparse):
+  if sparse:   # constant background, <= 3 % coloured pixels: tiny channel variance -> large inv
+    k = np.full((B, H, W, Cin), 40, dtype=np.int64)
+    m = rs.rand(B, H, W, 1) < 0.03
+    k = np.where(m, rs.randint(0, 256, (B, H, W, Cin)), k)
+  else:
+    k = rs.randint(0, 256, (B, H, W, Cin))
+  return (k.astype(np.float16) / np.float16(255))
+
+
+def run_tc(B, H, W, Cin, KS, nets, seed, sparse=False, gather=False):
+  L, lib = _lib()
+  rs = np.random.RandomState(seed)
+  dev = "cuda"
+  x_h = make_input(rs, B, H, W, Cin, sparse)
+  rows = None
+  if gather:   # the batch is rows[b] of a bigger slab
+    n_slab = 3 * B
+    slab_h = make_input(rs, n_slab, H, W, Cin, sparse)
+    rows_h = rs.randint(0, n_slab, B).astype(np.int32)
+    x_h = slab_h[rows_h]
+    slab = torch.from_numpy(slab_h).to(dev)
+    rows = torch.from_numpy(rows_h).to(dev)
+  x = torch.from_numpy(x_h).to(dev)
+  scratch = torch.zeros(int(lib.cpp_moments_scratch_doubles(Cin)), dtype=torch.float64, device=dev)
+  mi = torch.zeros(2 * Cin, dtype=torch.float32, device=dev)
+  L.check(lib.cpp_channel_moments(L.ptr(x), 1, C.c_int64(B * H * W), Cin, L.ptr(scratch), L.ptr(mi), L.stream_ptr()))
+  x64 = torch.from_numpy(x_h.astype(np.float64))
+  mean = x64.mean(dim=(0, 1, 2)); var = ((x64 - mean) ** 2).mean(dim=(0, 1, 2))
+  xw = ((x64 - mean) * torch.rsqrt(var + 1e-6)).permute(0, 3, 1, 2).contiguous()
+  lim = np.sqrt(6.0 / (KS * KS * (Cin + 10)))
+  PH, PW = H // 2, W // 2
+  ws, bs, pooled, amax, ref = [], [], [], [], []
+  for n in range(nets):
+    w_h = rs.uniform(-lim, lim, (KS, KS, Cin, 10)).astype(np.float32)
+    b_h = rs.uniform(-0.1, 0.1, 10).astype(np.float32)
+    ws.append(torch.from_numpy(w_h).to(dev)); bs.append(torch.from_numpy(b_h).to(dev))
+    pooled.append(torch.full((B, PH, PW, 10), -7.0, dtype=torch.float32, device=dev))
+    amax.append(torch.full((B, PH, PW, 10), 9, dtype=torch.uint8, device=dev))
+    y = F.conv2d(xw, torch.from_numpy(w_h.astype(np.float64)).permute(3, 2, 0, 1).contiguous(),
+                 torch.from_numpy(b_h.astype(np.float64)), padding=KS // 2)
+    ref.append(y)
+  nb = int(lib.cpp_conv_tc_scratch_bytes(nets, H, W, Cin, KS))
+  assert nb > 0
+  scr = torch.zeros(nb, dtype=torch.uint8, device=dev)
+  src = slab if gather else x
+  L.check(lib.cpp_conv_forward_tc(L.ptr(src), L.ptr(rows), L.ptr(mi), nets, L.ptr_array(ws), L.ptr_array(bs), B, H, W, Cin, KS,
+                                  L.ptr_array(pooled), L.ptr_array(amax), L.ptr(scr), L.stream_ptr()))
+  torch.cuda.synchronize()
+  errs = []
+  for n in range(nets):
+    y = ref[n]
+    ref_pool = F.max_pool2d(F.relu(y), 2).permute(0, 2, 3, 1).numpy()
+    got = pooled[n].cpu().numpy()
+    errs.append(U.assert_close(got, ref_pool, what="tc conv fwd net %d %dx%dx%d k%d" % (n, H, W, Cin, KS)))
+    a = amax[n].cpu().numpy().astype(np.int64)
+    yw = y[:, :, :PH * 2, :PW * 2].reshape(B, 10, PH, 2, PW, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, PH, PW, 10, 4).numpy()
+    closed = a == 4
+    assert a.max() <= 4
+    assert np.array_equal(closed, got == 0)
+    picked = np.take_along_axis(yw, np.minimum(a, 3)[..., None], axis=-1)[..., 0]
+    scale = np.abs(yw).max()
+    assert np.all(np.abs(picked - yw.max(-1))[~closed] <= 1e-5 * scale)
+    assert np.all(yw.max(-1)[closed] <= 1e-5 * scale)
+    # the exact-fp32 CUDA-core kernel on the same input: same values to fp32 rounding
+    p2 = torch.zeros((B, PH, PW, 10), dtype=torch.float32, device=dev); a2 = torch.zeros((B, PH, PW, 10), dtype=torch.uint8, device=dev)
+    L.check(lib.cpp_conv_forward(L.ptr(x), 1, L.ptr(mi), L.ptr(ws[n]), L.ptr(bs[n]), B, H, W, Cin, KS, L.ptr(p2), L.ptr(a2), L.stream_ptr()))
+    U.assert_close(got, p2.cpu().numpy(), what="tc vs fp32 kernel")
+  return errs
+
+
+@pytest.mark.parametrize("B,H,W,Cin,KS,nets", [
+    (8, 64, 64, 9, 5, 2),       # c3 conv1, actor+critic
+    (4, 64, 64, 18, 5, 3),      # c4 conv1, NAF value/mu/l
+    (2, 128, 128, 24, 5, 2),    # c5 conv1
+    (3, 64, 64, 9, 5, 1),       # a single network (action_given)
+    (2, 50, 50, 6, 5, 2),       # reference default render size, R=2 (6 channels: padded group)
+    (2, 32, 48, 8, 5, 2),       # exactly one channel group, W != H
+    (3, 33, 31, 9, 5, 2),       # odd sizes: VALID pooling drops the last row/column
+    (4, 32, 32, 10, 3, 1),      # 3x3 kernel, 8+2 channels
+])
+def test_conv_tc_forward(B, H, W, Cin, KS, nets):
+  errs = run_tc(B, H, W, Cin, KS, nets, seed=B * 1000 + H + Cin)
+  print("tc conv fwd B%d %dx%dx%d k%d nets%d: rel err vs fp64" % (B, H, W, Cin, KS, nets), ["%.2e" % e for e in errs])
+
+
+def test_conv_tc_sparse_scene():
+  errs = run_tc(4, 64, 64, 9, 5, 2, seed=5, sparse=True)
+  print("tc conv fwd sparse scene: rel err vs fp64", ["%.2e" % e for e in errs])
+
+
+def test_conv_tc_fused_gather():
+  run_tc(6, 64, 64, 9, 5, 2, seed=11, gather=True)
+
+
+def test_conv_tc_full_batch_c3():
+  errs = run_tc(256, 64, 64, 9, 5, 2, seed=3)
+  print("tc conv fwd c3 full batch: rel err vs fp64", ["%.2e" % e for e in errs])
