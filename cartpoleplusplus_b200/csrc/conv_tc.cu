@@ -29,7 +29,7 @@ namespace cpp {
 namespace tc {
 
 constexpr int CO = kConvCout;
-constexpr int kThreads = 256;
+constexpr int kSmemLimit = 224 * 1024;   // dynamic shared memory one CTA may use (227 KB max on sm_100)
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -170,205 +170,299 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
+// Warp-specialised, persistent (one CTA per SM):
+//   warps 0-3  epilogue : TMEM -> registers (tcgen05.ld), pieces summed, scale, border-aware bias, ReLU, 2x2 max-pool
+//   warps 4-7  fill     : TMA bulk copies of raw image rows into a staging ring, re-laid into the parity planes
+//   warp  8    MMA      : one elected lane issues the tcgen05.mma stream
+// Two plane buffers (fill of unit u+1 overlaps the MMAs of unit u) and two sets of TMEM accumulators (MMAs of
+// tile t+1 overlap the epilogue of tile t), all handed over through mbarriers.
+constexpr int kEpiWarps = 4, kFillWarps = 8;
+constexpr int kThreads2 = 32 * (kEpiWarps + kFillWarps + 1);
+enum { BAR_FULL_PL = 0, BAR_EMPTY_PL = 2, BAR_FULL_ACC = 4, BAR_EMPTY_ACC = 6, BAR_STAGE = 8, BAR_COUNT = 10 };
+
 struct SmemLayout { uint32_t planes, bsm, stage, corr, bars, tmem, total; };
 
 __host__ __device__ inline SmemLayout smem_layout(const FwdPlan& P) {
   SmemLayout L;
   uint32_t off = 0;
-  L.planes = off; off += (uint32_t)P.n_planes * P.plane_bytes;
+  L.planes = off; off += 2u * (uint32_t)P.unit_bytes;
   L.bsm = off; off += (uint32_t)P.n_pairs * 2 * P.N * 16;
-  L.stage = off; off += (uint32_t)P.stage_bytes;
+  L.stage = off; off += 2u * (uint32_t)P.stage_bytes;
   const int ncls = 2 * P.PAD + 1;
   L.corr = off; off += (uint32_t)((ncls * ncls * P.nets * CO + 4) * 4);
   off = (off + 15) & ~15u;
-  L.bars = off; off += 32;
+  L.bars = off; off += BAR_COUNT * 8;
   L.tmem = off; off += 16;
   L.total = off;
   return L;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) conv_fwd_tc_kernel(const __grid_constant__ FwdPlan P) {
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// up to 8 halfs (zero padded) from a 2-byte aligned shared-memory address
+__device__ __forceinline__ uint4 load8h(const unsigned short* p, int nch) {
+  if (nch >= 8) {
+    if ((reinterpret_cast<uintptr_t>(p) & 2) == 0) {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+      return make_uint4(q[0], q[1], q[2], q[3]);
+    }
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p + 1);
+    const uint32_t a = p[0], b = q[0], c = q[1], d = q[2], e = p[7];
+    return make_uint4(a | (b << 16), (b >> 16) | (c << 16), (c >> 16) | (d << 16), (d >> 16) | (e << 16));
+  }
+  uint32_t h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) h[e] = e < nch ? (uint32_t)p[e] : 0u;
+  return make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+}
+
+template <int KS, int R>
+__global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_constant__ FwdPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const SmemLayout L = smem_layout(P);
-  uint8_t* planes = smem + L.planes;
+  uint8_t* planes_base = smem + L.planes;
   uint8_t* bsm = smem + L.bsm;
-  __half* stage = reinterpret_cast<__half*>(smem + L.stage);
+  uint8_t* stage_base = smem + L.stage;
   float* corr_s = reinterpret_cast<float*>(smem + L.corr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);     // [0] staging full, [1] accumulators ready
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = P.H, W = P.W, C = P.C, PH = P.PH, PW = P.PW, Pq = P.Pq, KS = P.KS, PAD = P.PAD, N = P.N;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler
+  constexpr int PAD = KS / 2;
+  const int H = P.H, W = P.W, C = P.C, PH = P.PH, PW = P.PW, Pq = P.Pq, N = P.N;
   const int ncls = 2 * PAD + 1, ncorr = ncls * ncls * P.nets * CO;
 
   // ---- one-time setup: barriers, TMEM, weights, correction table
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[BAR_FULL_PL + i], kFillWarps); mbar_init(&bars[BAR_EMPTY_PL + i], 1);
+      mbar_init(&bars[BAR_FULL_ACC + i], 1); mbar_init(&bars[BAR_EMPTY_ACC + i], kEpiWarps);
+      mbar_init(&bars[BAR_STAGE + i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kEpiWarps + kFillWarps) tmem_alloc(tmem_slot, 512);
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.bpack);
     uint4* dst = reinterpret_cast<uint4*>(bsm);
-    for (int i = tid; i < P.n_pairs * 2 * N; i += kThreads) dst[i] = src[i];
-    for (int i = tid; i < ncorr + 1; i += kThreads) corr_s[i] = P.corr[i];
+    for (int i = tid; i < P.n_pairs * 2 * N; i += kThreads2) dst[i] = src[i];
+    for (int i = tid; i < ncorr + 1; i += kThreads2) corr_s[i] = P.corr[i];
   }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const float scale_inv = corr_s[ncorr];
-  const uint32_t idesc = make_idesc(N);
-  const uint32_t planes_addr = smem_u32(planes), bsm_addr = smem_u32(bsm);
-  uint32_t ph_stage = 0, ph_mma = 0;
-  const size_t img_elems = (size_t)H * W * C;
-  const int n_groups = (P.rows_alloc + P.crh - 1) / P.crh;
 
-  for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-    const int b = unit / P.units_per_image, u = unit - b * P.units_per_image;
-    const int t0 = u * P.tiles_per_unit, t1 = min(t0 + P.tiles_per_unit, P.tiles_per_image);
-    const int py_first = (128 * t0) / Pq, yh0 = py_first - 1;
-    const __half* img = P.x + (size_t)(P.rows ? P.rows[b] : b) * img_elems;
-
-    // ---- fill the parity planes of this unit, one staging group (crh parity rows = 2*crh raw rows) at a time
-    for (int g = 0; g < n_groups; ++g) {
-      const int rho0 = g * P.crh, rho1 = min(rho0 + P.crh, P.rows_alloc);
-      const int yc0 = max(0, 2 * (yh0 + rho0)), yc1 = min(H, 2 * (yh0 + rho1));
-      const bool have = yc1 > yc0;
-      if (have) {
-        const uint32_t bytes = (uint32_t)(yc1 - yc0) * W * C * 2;
-        if (P.use_bulk) {
-          if (tid == 0) {
-            fence_proxy_async();                       // staging was read through the generic proxy just before
-            mbar_expect_tx(&bars[0], bytes);
-            bulk_g2s(stage, img + (size_t)yc0 * W * C, bytes, &bars[0]);
-          }
-          mbar_wait(&bars[0], ph_stage);
-          ph_stage ^= 1;
-        } else {
-          const __half* src = img + (size_t)yc0 * W * C;
-          for (int i = tid; i < (yc1 - yc0) * W * C; i += kThreads) stage[i] = src[i];
-          __syncthreads();
-        }
-      }
-      const int per_plane = (rho1 - rho0) * Pq;
-      for (int it = tid; it < P.n_planes * per_plane; it += kThreads) {
-        const int pl = it / per_plane, rem = it - pl * per_plane;
-        const int rho = rho0 + rem / Pq, kap = rem % Pq;
-        const int yh = yh0 + rho;
-        __align__(16) __half v[8];
+  if (warp < kEpiWarps) {
+    // =========================================================================== epilogue warps
+    const float scale_inv = corr_s[ncorr];
+    const int quarter = warp;                                      // TMEM lanes 32*quarter .. +31
+    uint32_t tc = 0;
+    for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
+      const int b = unit / P.units_per_image, u = unit - b * P.units_per_image;
+      const int t0 = u * P.tiles_per_unit, t1 = min(t0 + P.tiles_per_unit, P.tiles_per_image);
+      for (int t = t0; t < t1; ++t, ++tc) {
+        const uint32_t ab = tc & 1;
+        mbar_wait(&bars[BAR_FULL_ACC + ab], (tc >> 1) & 1);
+        tc_fence_after();
+        const int q = 128 * t + 32 * quarter + lane;
+        const int py = q / Pq, px = q - py * Pq;
+        const bool valid = py < PH && px < PW;
+        for (int net = 0; net < P.nets; ++net) {
+          float best[CO];
+          int arg[CO];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __float2half_rn(0.f);
-        if (pl < 4 * P.G8) {                           // 8 channels of pixel (2*yh + yp, 2*(kap-1) + xp)
-          const int gq = pl >> 2, yp = (pl >> 1) & 1, xp = pl & 1;
-          const int y = 2 * yh + yp, x = 2 * (kap - 1) + xp;
-          if (have && y >= yc0 && y < yc1 && x >= 0 && x < W) {
-            const __half* sp = stage + ((size_t)(y - yc0) * W + x) * C + 8 * gq;
-            const int nch = min(8, C - 8 * gq);
+          for (int o = 0; o < CO; ++o) { best[o] = 0.f; arg[o] = 0; }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) if (e < nch) v[e] = sp[e];
-          }
-        } else {                                       // remainder channels packed along kx
-          const int q = pl - 4 * P.G8, j = q >> 2, yp = (q >> 1) & 1, dx = q & 1;
-          const int y = 2 * yh + yp, px = kap - 1;
-          if (have && y >= yc0 && y < yc1 && px >= 0 && px < PW) {
-            const __half* sp = stage + (size_t)(y - yc0) * W * C + 8 * P.G8;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int E = 8 * j + e;
-              if (E < KS * P.R) {
-                const int kx = E / P.R, cr = E - kx * P.R;
-                const int x = 2 * px + dx + kx - PAD;
-                if (x >= 0 && x < W) v[e] = sp[(size_t)x * C + cr];
-              }
-            }
-          }
-        }
-        *reinterpret_cast<uint4*>(planes + (size_t)pl * P.plane_bytes + ((size_t)rho * Pq + kap) * 16) = *reinterpret_cast<const uint4*>(v);
-      }
-      __syncthreads();                                 // staging is free again
-    }
-    fence_proxy_async();                               // plane writes (generic proxy) -> visible to the tensor core (async proxy)
-    __syncthreads();
-
-    for (int t = t0; t < t1; ++t) {
-      // ---- MMA: 4 accumulators (one per position of the 2x2 pool window) x n_pairs K16 instructions
-      if (warp == 0) {
-        if (lane == 0) {
-          tc_fence_after();
-          const int q_off = 128 * t - py_first * Pq;
           for (int a = 0; a < 4; ++a) {
-            const int dy = a >> 1, dx = a & 1;
-            for (int i = 0; i < P.n_pairs; ++i) {
-              uint32_t addr[2];
+            uint32_t r[20];
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)((ab * 4 + a) * N + net * kPieces * CO);
+            tmem_ld16(taddr, r);
+            tmem_ld4(taddr + 16, r + 16);
+            tmem_ld_wait();
+            const int y = 2 * py + (a >> 1), x = 2 * px + (a & 1);
+            const int yc = y < PAD ? y : (y >= H - PAD ? 2 * PAD - (H - 1 - y) : PAD);
+            const int xc = x < PAD ? x : (x >= W - PAD ? 2 * PAD - (W - 1 - x) : PAD);
+            const float* cr = corr_s + ((valid ? (yc * ncls + xc) : 0) * P.nets + net) * CO;
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const Slab sl = P.slab[i][h];
-                const int ty = dy + sl.ky - PAD, yp = ty & 1, oy = (ty >> 1) + 1;
-                if (sl.kind == 0) {
-                  const int tx = dx + sl.kx - PAD, xp = tx & 1, ox = (tx >> 1) + 1;
-                  addr[h] = planes_addr + (uint32_t)((sl.set * 4 + yp * 2 + xp) * P.plane_bytes + (q_off + oy * Pq + ox) * 16);
-                } else if (sl.kind == 1) {
-                  addr[h] = planes_addr + (uint32_t)((4 * P.G8 + sl.set * 4 + yp * 2 + dx) * P.plane_bytes + (q_off + oy * Pq + 1) * 16);
-                } else {
-                  addr[h] = addr[0] + 16;              // zero weights: any initialised shared memory will do
-                }
-              }
-              const uint64_t adesc = make_desc(addr[0], addr[1] - addr[0], 128);
-              const uint64_t bdesc = make_desc(bsm_addr + (uint32_t)i * 2 * N * 16, (uint32_t)N * 16, 128);
-              umma_f16(tmem_base + (uint32_t)(a * N), adesc, bdesc, idesc, i > 0 ? 1u : 0u);
+            for (int o = 0; o < CO; ++o) {
+              const float v = fmaf(__uint_as_float(r[o]) + __uint_as_float(r[CO + o]), scale_inv, cr[o]);
+              if (a == 0) { best[o] = v; arg[o] = 0; }
+              else if (v > best[o]) { best[o] = v; arg[o] = a; }
             }
           }
-          umma_commit(&bars[1]);
+          if (valid) {
+            const size_t base = (((size_t)b * PH + py) * PW + px) * CO;
+            float* op = P.pooled[net] + base;
+            uint8_t* ap = P.amax[net] + base;
+#pragma unroll
+            for (int o = 0; o < CO; o += 2) {
+              *reinterpret_cast<float2*>(op + o) = make_float2(fmaxf(best[o], 0.f), fmaxf(best[o + 1], 0.f));
+              const uint16_t pk = (uint16_t)((best[o] > 0.f ? arg[o] : 4) | ((best[o + 1] > 0.f ? arg[o + 1] : 4) << 8));
+              *reinterpret_cast<uint16_t*>(ap + o) = pk;
+            }
+          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BAR_EMPTY_ACC + ab]);     // this warp's quarter of the accumulators is drained
+      }
+    }
+  } else if (warp < kEpiWarps + kFillWarps) {
+    // =========================================================================== fill warps
+    const int ftid = tid - 32 * kEpiWarps, nfill = 32 * kFillWarps;
+    const size_t img_elems = (size_t)H * W * C;
+    const int n_groups = (P.rows_alloc + P.crh - 1) / P.crh;
+    const int rowC = W * C;
+    uint32_t it = 0, icnt = 0, wcnt = 0;                           // units done; staging copies issued / consumed
+    for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x, ++it) {
+      const int b = unit / P.units_per_image, u = unit - b * P.units_per_image;
+      const int t0 = u * P.tiles_per_unit;
+      const int py_first = (128 * t0) / Pq, yh0 = py_first - 1;
+      const __half* img = P.x + (size_t)(P.rows ? P.rows[b] : b) * img_elems;
+      const uint32_t buf = it & 1;
+      mbar_wait(&bars[BAR_EMPTY_PL + buf], ((it >> 1) & 1) ^ 1);   // the MMAs that read this buffer two units ago are done
+      uint8_t* planes = planes_base + (size_t)buf * P.unit_bytes;
+
+      auto group_rows = [&](int g, int& rho0, int& rho1, int& yc0, int& yc1) {
+        rho0 = g * P.crh; rho1 = min(rho0 + P.crh, P.rows_alloc);
+        yc0 = max(0, 2 * (yh0 + rho0)); yc1 = min(H, 2 * (yh0 + rho1));
+      };
+      auto issue = [&](int g) {                                    // thread ftid == 0 only
+        int rho0, rho1, yc0, yc1;
+        group_rows(g, rho0, rho1, yc0, yc1);
+        if (yc1 > yc0) {
+          const uint32_t sb = icnt & 1, bytes = (uint32_t)(yc1 - yc0) * rowC * 2;
+          fence_proxy_async();                                     // the buffer was read through the generic proxy before
+          mbar_expect_tx(&bars[BAR_STAGE + sb], bytes);
+          bulk_g2s(stage_base + (size_t)sb * P.stage_bytes, img + (size_t)yc0 * rowC, bytes, &bars[BAR_STAGE + sb]);
+          ++icnt;
+        }
+      };
+      if (P.use_bulk && ftid == 0) issue(0);
+      for (int g = 0; g < n_groups; ++g) {
+        int rho0, rho1, yc0, yc1;
+        group_rows(g, rho0, rho1, yc0, yc1);
+        const bool have = yc1 > yc0;
+        const unsigned short* stage = nullptr;
+        if (P.use_bulk) {
+          if (ftid == 0 && g + 1 < n_groups) issue(g + 1);         // prefetch: its buffer was released by the barrier below
+          if (have) {
+            const uint32_t sb = wcnt & 1;
+            mbar_wait(&bars[BAR_STAGE + sb], (wcnt >> 1) & 1);
+            stage = reinterpret_cast<const unsigned short*>(stage_base + (size_t)sb * P.stage_bytes);
+            ++wcnt;
+          }
+        } else if (have) {                                         // rows not 16-byte granular: plain loads
+          unsigned short* st = reinterpret_cast<unsigned short*>(stage_base);
+          const unsigned short* src = reinterpret_cast<const unsigned short*>(img) + (size_t)yc0 * rowC;
+          for (int i = ftid; i < (yc1 - yc0) * rowC; i += nfill) st[i] = src[i];
+          named_bar_sync(1, nfill);
+          stage = st;
+        }
+        const int npos = (rho1 - rho0) * Pq;
+        for (int pos = ftid; pos < npos; pos += nfill) {
+          const int rl = pos / Pq, kap = pos - rl * Pq;
+          const int rho = rho0 + rl, yh = yh0 + rho, xh = kap - 1;
+          uint8_t* dst = planes + ((size_t)rho * Pq + kap) * 16;
+#pragma unroll
+          for (int yp = 0; yp < 2; ++yp) {
+            const int y = 2 * yh + yp;
+            const bool yok = have && y >= yc0 && y < yc1;
+            const unsigned short* rowp = stage + (yok ? (y - yc0) : 0) * rowC;
+#pragma unroll
+            for (int xp = 0; xp < 2; ++xp) {
+              const int x = 2 * xh + xp;
+              const bool ok = yok && x >= 0 && x < W;
+              for (int gq = 0; gq < P.G8; ++gq) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (ok) v = load8h(rowp + x * C + 8 * gq, C - 8 * gq);
+                *reinterpret_cast<uint4*>(dst + (size_t)(gq * 4 + yp * 2 + xp) * P.plane_bytes) = v;
+              }
+            }
+            if constexpr (R > 0) {
+              // remainder channels: the KS taps along x of the R channels share 16-byte rows, one per output column.
+              // Output columns 2*xh (dx = 0) and 2*xh + 1 (dx = 1) read pixels 2*xh - PAD .. 2*xh + 1 + PAD.
+              constexpr int NPIX = KS + 1, NE = KS * R, NJ = (NE + 7) / 8;
+              uint32_t pix[NPIX][R > 0 ? R : 1];
+              const bool cok = yok && xh >= 0 && xh < PW;
+#pragma unroll
+              for (int i = 0; i < NPIX; ++i) {
+                const int x = 2 * xh - PAD + i;
+                const bool ok = cok && x >= 0 && x < W;
+#pragma unroll
+                for (int c = 0; c < R; ++c) pix[i][c] = ok ? (uint32_t)rowp[x * C + 8 * P.G8 + c] : 0u;
+              }
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                  uint32_t h[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int E = 8 * j + e;                       // compile time: kx = E / R, channel = E % R
+                    h[e] = E < NE ? pix[dx + E / R][E % R] : 0u;
+                  }
+                  *reinterpret_cast<uint4*>(dst + (size_t)(4 * P.G8 + j * 4 + yp * 2 + dx) * P.plane_bytes) =
+                      make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                }
+            }
+          }
+        }
+        named_bar_sync(1, nfill);                                  // every fill thread is done with this staging buffer
+      }
+      fence_proxy_async();                                         // generic-proxy plane writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BAR_FULL_PL + buf]);
+    }
+  } else {
+    // =========================================================================== MMA warp (one elected lane issues)
+    const uint32_t idesc = make_idesc(N);
+    const uint32_t hi = (128u >> 4) | (1u << 14);                  // SBO = 128 bytes, descriptor version 1, no swizzle
+    const uint32_t b_lo0 = ((smem_u32(bsm) & 0x3FFFFu) >> 4) | ((uint32_t)N << 16);   // LBO = N * 16 bytes
+    uint32_t it = 0, tc = 0;
+    for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x, ++it) {
+      const int u = unit % P.units_per_image;
+      const int t0 = u * P.tiles_per_unit, t1 = min(t0 + P.tiles_per_unit, P.tiles_per_image);
+      const int py_first = (128 * t0) / Pq;
+      const uint32_t buf = it & 1;
+      mbar_wait(&bars[BAR_FULL_PL + buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t pl16 = (smem_u32(planes_base + (size_t)buf * P.unit_bytes) & 0x3FFFFu) >> 4;
+      for (int t = t0; t < t1; ++t, ++tc) {
+        const uint32_t ab = tc & 1;
+        mbar_wait(&bars[BAR_EMPTY_ACC + ab], ((tc >> 1) & 1) ^ 1); // the epilogue drained these accumulators
+        tc_fence_after();
+        const uint32_t a_add = pl16 + (uint32_t)(128 * t - py_first * Pq);
+        for (int a = 0; a < 4; ++a) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((ab * 4 + a) * N);
+          for (int i = 0; i < P.n_pairs; ++i) {
+            const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(P.adesc_lo[a][i] + a_add);
+            const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(i * 2 * N));
+            if (elect_one()) umma_f16(d_tmem, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
+          }
+        }
+        if (elect_one()) umma_commit(&bars[BAR_FULL_ACC + ab]);
         __syncwarp();
       }
-      mbar_wait(&bars[1], ph_mma);
-      ph_mma ^= 1;
-      tc_fence_after();
-
-      // ---- epilogue: lane = pooled position; sum the weight pieces, rescale, add the border-aware bias, max-pool
-      const int quarter = warp & 3;
-      const int q = 128 * t + 32 * quarter + lane;
-      const int py = q / Pq, px = q - py * Pq;
-      const bool valid = py < PH && px < PW;
-      for (int net = warp >> 2; net < P.nets; net += kThreads / 128) {
-        float best[CO];
-        int arg[CO];
-#pragma unroll
-        for (int o = 0; o < CO; ++o) { best[o] = 0.f; arg[o] = 0; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          uint32_t r[20];
-          const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(a * N + net * kPieces * CO);
-          tmem_ld16(taddr, r);
-          tmem_ld4(taddr + 16, r + 16);
-          tmem_ld_wait();
-          const int y = 2 * py + (a >> 1), x = 2 * px + (a & 1);
-          const int yc = y < PAD ? y : (y >= H - PAD ? 2 * PAD - (H - 1 - y) : PAD);
-          const int xc = x < PAD ? x : (x >= W - PAD ? 2 * PAD - (W - 1 - x) : PAD);
-          const float* cr = corr_s + ((valid ? (yc * ncls + xc) : 0) * P.nets + net) * CO;
-#pragma unroll
-          for (int o = 0; o < CO; ++o) {
-            const float v = fmaf(__uint_as_float(r[o]) + __uint_as_float(r[CO + o]), scale_inv, cr[o]);
-            if (a == 0) { best[o] = v; arg[o] = 0; }
-            else if (v > best[o]) { best[o] = v; arg[o] = a; }
-          }
-        }
-        if (valid) {
-          const size_t base = (((size_t)b * PH + py) * PW + px) * CO;
-          float* op = P.pooled[net] + base;
-          uint8_t* ap = P.amax[net] + base;
-#pragma unroll
-          for (int o = 0; o < CO; o += 2) {
-            *reinterpret_cast<float2*>(op + o) = make_float2(fmaxf(best[o], 0.f), fmaxf(best[o + 1], 0.f));
-            const uint16_t pk = (uint16_t)((best[o] > 0.f ? arg[o] : 4) | ((best[o + 1] > 0.f ? arg[o + 1] : 4) << 8));
-            *reinterpret_cast<uint16_t*>(ap + o) = pk;
-          }
-        }
-      }
-      tc_fence_before();
-      __syncthreads();                                 // TMEM and (after the last tile) the planes are free again
+      if (elect_one()) umma_commit(&bars[BAR_EMPTY_PL + buf]);     // all MMAs that read this plane buffer have completed
+      __syncwarp();
     }
   }
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + kFillWarps) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------ host: plan
@@ -381,7 +475,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P) 
   P->PH = H / 2; P->PW = W / 2;
   P->Pq = (W + 1) / 2 + 1;      // parity-plane pitch: ceil(W/2) pixels + one zero column shared by neighbouring rows
   P->nets = nets; P->N = (int)round_up(nets * kPieces * CO, 16);
-  CPP_REQUIRE(4 * P->N <= 256, "conv_tc: N=%d does not fit the TMEM allocation", P->N);
+  CPP_REQUIRE(8 * P->N <= 512, "conv_tc: N=%d does not fit two sets of TMEM accumulators", P->N);
   const int rem = C % 8;
   if (rem == 1 || rem == 2) { P->G8 = C / 8; P->R = rem; P->nR = (KS * rem + 7) / 8; }
   else { P->G8 = (C + 7) / 8; P->R = 0; P->nR = 0; }
@@ -432,26 +526,57 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P) 
 
   P->tiles_per_image = (int)ceil_div((int64_t)P->PH * P->Pq, 128);
   const int row_bytes = W * C * 2;
-  P->crh = std::max(1, 8192 / (2 * row_bytes));
+  P->crh = 1;
   P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
   P->use_bulk = (row_bytes % 16 == 0) && (((size_t)H * W * C * 2) % 16 == 0);
+  auto size_unit = [&](int tpu) {
+    P->tiles_per_unit = tpu;
+    P->rows_alloc = (P->Pq - 1 + 128 * tpu - 1 + 2 * P->Pq + 2) / P->Pq + 1;
+    P->plane_bytes = P->rows_alloc * P->Pq * 16;
+    P->unit_bytes = P->n_planes * P->plane_bytes;
+    return (int)smem_layout(*P).total;
+  };
   int best_tpu = 0;
-  for (int pass = 0; pass < 2 && best_tpu == 0; ++pass) {
-    const int limit = pass == 0 ? 110 * 1024 : 220 * 1024;      // two CTAs per SM if possible
-    for (int tpu = std::min(P->tiles_per_image, 8); tpu >= 1; --tpu) {
-      P->tiles_per_unit = tpu;
-      P->rows_alloc = (P->Pq - 1 + 128 * tpu - 1 + 2 * P->Pq + 2) / P->Pq + 1;
-      P->plane_bytes = P->rows_alloc * P->Pq * 16;
-      if ((int)smem_layout(*P).total <= limit) { best_tpu = tpu; break; }
-    }
-  }
+  for (int tpu = std::min(P->tiles_per_image, 8); tpu >= 1; --tpu)
+    if (size_unit(tpu) <= kSmemLimit) { best_tpu = tpu; break; }
   CPP_REQUIRE(best_tpu > 0, "conv_tc: %dx%dx%d does not fit shared memory", H, W, C);
   P->units_per_image = (int)ceil_div(P->tiles_per_image, best_tpu);
-  P->tiles_per_unit = (int)ceil_div(P->tiles_per_image, P->units_per_image);
-  P->rows_alloc = (P->Pq - 1 + 128 * P->tiles_per_unit - 1 + 2 * P->Pq + 2) / P->Pq + 1;
-  P->plane_bytes = P->rows_alloc * P->Pq * 16;
+  P->smem_bytes = size_unit((int)ceil_div(P->tiles_per_image, P->units_per_image));
   P->n_units = B * P->units_per_image;
+  // staging ring: as many parity rows per TMA copy as the remaining shared memory allows (fewer, longer copies)
+  while (P->crh < P->rows_alloc) {
+    ++P->crh;
+    P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
+    if ((int)smem_layout(*P).total > kSmemLimit || 2 * P->crh * row_bytes > 32 * 1024) {
+      --P->crh;
+      P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
+      break;
+    }
+  }
   P->smem_bytes = (int)smem_layout(*P).total;
+
+  // low words of the A descriptors for plane buffer 0 at pooled offset 0: (address >> 4) | (LBO >> 4) << 16
+  for (int a = 0; a < 4; ++a) {
+    const int dy = a >> 1, dx = a & 1;
+    for (int i = 0; i < P->n_pairs; ++i) {
+      int64_t addr[2];
+      for (int h = 0; h < 2; ++h) {
+        const Slab sl = P->slab[i][h];
+        const int ty = dy + sl.ky - PAD, yp = ty & 1, oy = (ty >> 1) + 1;
+        if (sl.kind == 0) {
+          const int tx = dx + sl.kx - PAD, xp = tx & 1, ox = (tx >> 1) + 1;
+          addr[h] = (int64_t)(sl.set * 4 + yp * 2 + xp) * P->plane_bytes + (int64_t)(oy * P->Pq + ox) * 16;
+        } else if (sl.kind == 1) {
+          addr[h] = (int64_t)(4 * P->G8 + sl.set * 4 + yp * 2 + dx) * P->plane_bytes + (int64_t)(oy * P->Pq + 1) * 16;
+        } else {
+          addr[h] = addr[0] + 16;      // zero weights: any initialised shared memory will do
+        }
+      }
+      const int64_t lbo = addr[1] - addr[0];
+      CPP_REQUIRE(lbo > 0 && lbo < (1 << 18) && addr[0] % 16 == 0, "conv_tc: bad slab pair");
+      P->adesc_lo[a][i] = (uint32_t)(addr[0] >> 4) | ((uint32_t)(lbo >> 4) << 16);
+    }
+  }
   return CPP_OK;
 }
 
@@ -468,6 +593,19 @@ int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS) {
   if (build_plan(nets, 1, H, W, C, KS, &P) != CPP_OK) return -1;
   const int ncls = 2 * P.PAD + 1;
   return (int64_t)bpack_bytes(P) + (int64_t)round_up((int64_t)(ncls * ncls * nets * CO + 4) * 4, 256);
+}
+
+template <int KS, int R>
+static int launch_main(const FwdPlan& P, int grid, cudaStream_t s) {
+  auto k = conv_fwd_tc_kernel<KS, R>;
+  static bool configured = false;
+  if (!configured) {
+    CPP_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    configured = true;
+  }
+  k<<<grid, kThreads2, P.smem_bytes, s>>>(P);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
 }
 
 int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int nets,
@@ -489,16 +627,15 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);
   conv_tc_prep_kernel<<<1, 256, 0, s>>>(P, A);
   CPP_CHECK_LAUNCH();
-  static int configured = 0;
-  if (P.smem_bytes > configured) {
-    CPP_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = 220 * 1024;
+  const int grid = std::min(P.n_units, kNumSMs);            // persistent: one CTA per SM (it owns all 512 TMEM columns)
+  if (KS == 5) {
+    if (P.R == 0) return launch_main<5, 0>(P, grid, s);
+    if (P.R == 1) return launch_main<5, 1>(P, grid, s);
+    return launch_main<5, 2>(P, grid, s);
   }
-  const int ctas_per_sm = P.smem_bytes <= 110 * 1024 ? 2 : 1;
-  const int grid = std::min(P.n_units, ctas_per_sm * kNumSMs);
-  conv_fwd_tc_kernel<<<grid, kThreads, P.smem_bytes, s>>>(P);
-  CPP_CHECK_LAUNCH();
-  return CPP_OK;
+  if (P.R == 0) return launch_main<3, 0>(P, grid, s);
+  if (P.R == 1) return launch_main<3, 1>(P, grid, s);
+  return launch_main<3, 2>(P, grid, s);
 }
 
 }  // namespace tc

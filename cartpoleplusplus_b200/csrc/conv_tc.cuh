@@ -29,12 +29,13 @@ struct FwdPlan {
   int nets, N;              // MMA N = round_up(nets * kPieces * 10, 16)
   // ---- shared-memory geometry
   int G8, R, nR;            // full 8-channel groups, remainder channels, packed slabs per ky
-  int n_planes, rows_alloc, plane_bytes;
+  int n_planes, rows_alloc, plane_bytes, unit_bytes;
   int crh, stage_bytes, use_bulk;   // parity rows per staging group, staging buffer bytes, TMA bulk copy usable
   int tiles_per_image, tiles_per_unit, units_per_image, n_units;
   int n_pairs;
   int smem_bytes;
   Slab slab[kMaxPairs][2];
+  uint32_t adesc_lo[4][kMaxPairs];   // low word of every A descriptor (pool position a, instruction i), buffer 0, q = 0
 };
 
 struct PrepArgs {
