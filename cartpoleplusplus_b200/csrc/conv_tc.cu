@@ -104,7 +104,7 @@ __host__ __device__ inline uint32_t make_idesc(int N) {
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
-// One block.  (1) S: power of two that brings max |w * inv| just under 2^15; (2) B operand in canonical K-major
+// Every block recomputes (1), the blocks share (2) and (3).  (1) S: power of two that brings max |w * inv| just under 2^15; (2) B operand in canonical K-major
 // layout [pair][half][n][8], n = (net * pieces + piece) * 10 + o; (3) corr[yc][xc][net][o] = bias - sum over the
 // taps that fall inside the image of mean_c * inv_c * w (fp64), and 2^-S.
 __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant__ FwdPlan P, const __grid_constant__ PrepArgs A) {
@@ -128,12 +128,13 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
     if (m > 0.f && isfinite(m)) frexpf(m, &e);      // m < 2^e
     else e = 15;
     s_scale = ldexpf(1.f, 15 - e);
-    A.corr[(2 * P.PAD + 1) * (2 * P.PAD + 1) * P.nets * CO] = ldexpf(1.f, e - 15);
+    if (blockIdx.x == 0) A.corr[(2 * P.PAD + 1) * (2 * P.PAD + 1) * P.nets * CO] = ldexpf(1.f, e - 15);
   }
   __syncthreads();
   const float scale = s_scale;
   const int N = P.N, used = P.nets * kPieces * CO, total = P.n_pairs * 2 * N * 8;
-  for (int idx = tid; idx < total; idx += blockDim.x) {
+  const int gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
+  for (int idx = gtid; idx < total; idx += gthreads) {
     const int e = idx & 7, n = (idx >> 3) % N, h = ((idx >> 3) / N) & 1, i = (idx >> 3) / (2 * N);
     const Slab sl = P.slab[i][h];
     float v = 0.f;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
     A.bpack[idx] = out;
   }
   const int ncls = 2 * P.PAD + 1;
-  for (int idx = tid; idx < ncls * ncls * P.nets * CO; idx += blockDim.x) {
+  for (int idx = gtid; idx < ncls * ncls * P.nets * CO; idx += gthreads) {
     const int o = idx % CO, net = (idx / CO) % P.nets, xc = (idx / (CO * P.nets)) % ncls, yc = idx / (CO * P.nets * ncls);
     double acc = (double)A.bias[net][o];
     if (A.mean_inv) {
@@ -225,6 +226,25 @@ __device__ __forceinline__ uint4 load8h(const unsigned short* p, int nch) {
   return make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
 }
 
+// Work distribution: the tiles of the whole batch (image-major) are split into one contiguous range per CTA
+// (near-perfect balance); a CTA walks its range in units of <= tiles_per_unit tiles that never cross an image.
+struct UnitIter {
+  int g, g_end, tpi, tpu;
+  int b, t0, t1;
+  __device__ UnitIter(const FwdPlan& P) {
+    const long long total = (long long)P.B * P.tiles_per_image;
+    g = (int)(total * blockIdx.x / gridDim.x); g_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    tpi = P.tiles_per_image; tpu = P.tiles_per_unit;
+  }
+  __device__ bool next() {
+    if (g >= g_end) return false;
+    b = g / tpi; t0 = g - b * tpi;
+    t1 = min(min(tpi, t0 + tpu), t0 + (g_end - g));
+    g += t1 - t0;
+    return true;
+  }
+};
+
 template <int KS, int R>
 __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_constant__ FwdPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -269,10 +289,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
     const float scale_inv = corr_s[ncorr];
     const int quarter = warp;                                      // TMEM lanes 32*quarter .. +31
     uint32_t tc = 0;
-    for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-      const int b = unit / P.units_per_image, u = unit - b * P.units_per_image;
-      const int t0 = u * P.tiles_per_unit, t1 = min(t0 + P.tiles_per_unit, P.tiles_per_image);
-      for (int t = t0; t < t1; ++t, ++tc) {
+    for (UnitIter ui(P); ui.next();) {
+      const int b = ui.b;
+      for (int t = ui.t0; t < ui.t1; ++t, ++tc) {
         const uint32_t ab = tc & 1;
         mbar_wait(&bars[BAR_FULL_ACC + ab], (tc >> 1) & 1);
         tc_fence_after();
@@ -326,10 +345,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
     const int n_groups = (P.rows_alloc + P.crh - 1) / P.crh;
     const int rowC = W * C;
     uint32_t it = 0, icnt = 0, wcnt = 0;                           // units done; staging copies issued / consumed
-    for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x, ++it) {
-      const int b = unit / P.units_per_image, u = unit - b * P.units_per_image;
-      const int t0 = u * P.tiles_per_unit;
-      const int py_first = (128 * t0) / Pq, yh0 = py_first - 1;
+    for (UnitIter ui(P); ui.next(); ++it) {
+      const int b = ui.b;
+      const int py_first = (128 * ui.t0) / Pq, yh0 = py_first - 1;
       const __half* img = P.x + (size_t)(P.rows ? P.rows[b] : b) * img_elems;
       const uint32_t buf = it & 1;
       mbar_wait(&bars[BAR_EMPTY_PL + buf], ((it >> 1) & 1) ^ 1);   // the MMAs that read this buffer two units ago are done
@@ -432,9 +450,8 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
     const uint32_t hi = (128u >> 4) | (1u << 14);                  // SBO = 128 bytes, descriptor version 1, no swizzle
     const uint32_t b_lo0 = ((smem_u32(bsm) & 0x3FFFFu) >> 4) | ((uint32_t)N << 16);   // LBO = N * 16 bytes
     uint32_t it = 0, tc = 0;
-    for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x, ++it) {
-      const int u = unit % P.units_per_image;
-      const int t0 = u * P.tiles_per_unit, t1 = min(t0 + P.tiles_per_unit, P.tiles_per_image);
+    for (UnitIter ui(P); ui.next(); ++it) {
+      const int t0 = ui.t0, t1 = ui.t1;
       const int py_first = (128 * t0) / Pq;
       const uint32_t buf = it & 1;
       mbar_wait(&bars[BAR_FULL_PL + buf], (it >> 1) & 1);
@@ -526,14 +543,16 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P) 
 
   P->tiles_per_image = (int)ceil_div((int64_t)P->PH * P->Pq, 128);
   const int row_bytes = W * C * 2;
-  P->crh = 1;
-  P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
   P->use_bulk = (row_bytes % 16 == 0) && (((size_t)H * W * C * 2) % 16 == 0);
+  // shared-memory budget: two staging buffers of up to 16 KB first (few, long TMA copies), then the largest unit
+  // (fewer halo rows re-staged per tile) whose two plane buffers still fit
   auto size_unit = [&](int tpu) {
     P->tiles_per_unit = tpu;
     P->rows_alloc = (P->Pq - 1 + 128 * tpu - 1 + 2 * P->Pq + 2) / P->Pq + 1;
     P->plane_bytes = P->rows_alloc * P->Pq * 16;
     P->unit_bytes = P->n_planes * P->plane_bytes;
+    P->crh = std::max(1, std::min(P->rows_alloc, 16384 / (2 * row_bytes)));
+    P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
     return (int)smem_layout(*P).total;
   };
   int best_tpu = 0;
@@ -541,19 +560,8 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P) 
     if (size_unit(tpu) <= kSmemLimit) { best_tpu = tpu; break; }
   CPP_REQUIRE(best_tpu > 0, "conv_tc: %dx%dx%d does not fit shared memory", H, W, C);
   P->units_per_image = (int)ceil_div(P->tiles_per_image, best_tpu);
-  P->smem_bytes = size_unit((int)ceil_div(P->tiles_per_image, P->units_per_image));
+  P->smem_bytes = size_unit(best_tpu);
   P->n_units = B * P->units_per_image;
-  // staging ring: as many parity rows per TMA copy as the remaining shared memory allows (fewer, longer copies)
-  while (P->crh < P->rows_alloc) {
-    ++P->crh;
-    P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
-    if ((int)smem_layout(*P).total > kSmemLimit || 2 * P->crh * row_bytes > 32 * 1024) {
-      --P->crh;
-      P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
-      break;
-    }
-  }
-  P->smem_bytes = (int)smem_layout(*P).total;
 
   // low words of the A descriptors for plane buffer 0 at pooled offset 0: (address >> 4) | (LBO >> 4) << 16
   for (int a = 0; a < 4; ++a) {
@@ -625,9 +633,9 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   }
   A.mean_inv = mean_inv;
   A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);
-  conv_tc_prep_kernel<<<1, 256, 0, s>>>(P, A);
+  conv_tc_prep_kernel<<<16, 256, 0, s>>>(P, A);
   CPP_CHECK_LAUNCH();
-  const int grid = std::min(P.n_units, kNumSMs);            // persistent: one CTA per SM (it owns all 512 TMEM columns)
+  const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, kNumSMs);   // persistent: one CTA per SM (it owns all 512 TMEM columns)
   if (KS == 5) {
     if (P.R == 0) return launch_main<5, 0>(P, grid, s);
     if (P.R == 1) return launch_main<5, 1>(P, grid, s);

@@ -14,7 +14,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   d |= (uint64_t)layout << 61;
   return d;
 }
-__global__ void __launch_bounds__(128, 1) k(int M, int N, int iters, int layout, int a_shift, int a_step, int n_acc, long long* out) {
+__global__ void __launch_bounds__(128, 1) k(int M, int N, int iters, int layout, int sbo_sw, int a_shift, int a_step, int n_acc, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -32,25 +32,32 @@ __global__ void __launch_bounds__(128, 1) k(int M, int N, int iters, int layout,
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
   long long t0 = 0, t1 = 0;
-  if (tid == 0) {
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (warp == 0) {
     const uint32_t a_base = smem_u32(smem) + a_shift, b_base = smem_u32(smem) + 128 * 1024;
+    const uint32_t hi_a = layout == 0 ? ((128u >> 4) | (1u << 14)) : ((uint32_t)(sbo_sw >> 4) | (1u << 14) | ((uint32_t)layout << 29));
+    const uint32_t lo_a0 = layout == 0 ? (((a_base & 0x3FFFF) >> 4) | (((2048u + 16u) >> 4) << 16)) : (((a_base & 0x3FFFF) >> 4) | (1u << 16));
+    const uint32_t lo_b = layout == 0 ? (((b_base & 0x3FFFF) >> 4) | ((uint32_t)N << 16)) : (((b_base & 0x3FFFF) >> 4) | (1u << 16));
     t0 = clock64();
     for (int i = 0; i < iters; ++i) {
-      uint64_t ad, bd;
-      const uint32_t aa = a_base + (uint32_t)((i % 16) * a_step);
-      if (layout == 0) { ad = make_desc(aa, 2048 + 16, 128, 0); bd = make_desc(b_base, (uint32_t)N * 16, 128, 0); }
-      else { ad = make_desc(aa, 16, 1024, 2); bd = make_desc(b_base, 16, 1024, 2); }   // SW128 K-major: 8 rows x 128B atoms
-      const uint32_t d = tmem + (uint32_t)((i % n_acc) * N);
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                   ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(i >= n_acc ? 1u : 0u) : "memory");
+      const uint64_t ad = ((uint64_t)hi_a << 32) | (uint64_t)(lo_a0 + (uint32_t)((i & 15) * (a_step >> 4)));
+      const uint64_t bd = ((uint64_t)hi_a << 32) | (uint64_t)lo_b;
+      const uint32_t d = tmem + (uint32_t)((i & (n_acc - 1)) * N);
+      uint32_t pred;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+      if (pred)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(i >= n_acc ? 1u : 0u) : "memory");
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    if (pred) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     uint32_t ok;
     do {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
     } while (!ok);
     t1 = clock64();
-    out[blockIdx.x] = t1 - t0;
+    if (tid == 0) out[blockIdx.x] = t1 - t0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -60,19 +67,33 @@ int main() {
   long long* out; cudaMalloc(&out, 148 * sizeof(long long));
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 4096;
-  auto run = [&](int M, int N, int layout, int shift, int step, int nacc, int grid) {
-    k<<<grid, 128, 200 * 1024>>>(M, N, iters, layout, shift, step, nacc, out);
+  auto run = [&](int M, int N, int layout, int sbo_sw, int shift, int step, int nacc, int grid) {
+    if (nacc * N > 512) nacc = 512 / N;
+    int p2 = 1; while (p2 * 2 <= nacc) p2 *= 2; nacc = p2;
+    k<<<grid, 128, 200 * 1024>>>(M, N, iters, layout, sbo_sw, shift, step, nacc, out);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[148]; cudaMemcpy(h, out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
     long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-    printf("M=%3d N=%3d layout=%d shift=%4d step=%5d nacc=%d grid=%3d : %7.1f cyc/mma  (%s)\n", M, N, layout, shift, step, nacc, grid, (double)mx / iters, cudaGetErrorString(e));
+    printf("M=%3d N=%3d layout=%d sbo=%4d shift=%4d step=%5d nacc=%d grid=%3d : %7.1f cyc/mma  (%s)\n", M, N, layout, sbo_sw, shift, step, nacc, grid, (double)mx / iters, cudaGetErrorString(e));
   };
   const int Ns[] = {16, 32, 48, 64, 96, 128, 256};
-  for (int N : Ns) run(128, N, 0, 0, 0, 1, 148);
-  for (int N : Ns) run(128, N, 0, 0, 0, 4, 148);
-  for (int N : Ns) run(128, N, 0, 16, 528, 4, 148);      // unaligned start, moving A window
-  for (int N : Ns) run(128, N, 2, 0, 0, 4, 148);         // 128B swizzle
-  for (int N : {16, 32, 48, 64}) run(64, N, 0, 0, 0, 4, 148);
-  for (int N : {48, 64}) run(128, N, 0, 0, 0, 4, 1);     // a single SM: no power/clock effects
+  printf("-- no swizzle, K-major, dense (SBO=128, LBO=2064)\n");
+  for (int N : Ns) run(128, N, 0, 0, 0, 0, 4, 148);
+  printf("-- no swizzle, unaligned start (+16), moving window\n");
+  for (int N : Ns) run(128, N, 0, 0, 16, 528, 4, 148);
+  printf("-- 128B swizzle K-major (SBO=1024)\n");
+  for (int N : Ns) run(128, N, 2, 1024, 0, 0, 4, 148);
+  printf("-- 64B swizzle K-major (SBO=512)\n");
+  for (int N : Ns) run(128, N, 4, 512, 0, 0, 4, 148);
+  printf("-- 32B swizzle K-major (SBO=256)\n");
+  for (int N : Ns) run(128, N, 6, 256, 0, 0, 4, 148);
+  printf("-- 32B swizzle, start shifted by 32B multiples\n");
+  for (int N : {48, 64}) run(128, N, 6, 256, 32, 32 * 33, 4, 148);
+  printf("-- M=64\n");
+  for (int N : {16, 32, 48, 64, 128}) run(64, N, 0, 0, 0, 0, 4, 148);
+  for (int N : {16, 32, 48, 64, 128}) run(64, N, 6, 256, 0, 0, 4, 148);
+  printf("-- single SM\n");
+  for (int N : {48, 64, 256}) run(128, N, 0, 0, 0, 0, 4, 1);
+  for (int N : {48, 64, 256}) run(128, N, 2, 1024, 0, 0, 4, 1);
   return 0;
 }
