@@ -41,6 +41,7 @@ def parse_args():
   ap.add_argument("--impl", type=str, default="native", choices=["native", "reference"])
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--skip-e2e", action="store_true")
+  ap.add_argument("--skip-roofline", action="store_true")
   return ap.parse_args()
 
 
@@ -234,18 +235,22 @@ def run_native(args):
     e2e = dict(value=G * args.steps / (ems / 1e3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                ms_per_step=ems / args.steps, api="DDPGEngine.train_step(Batch of pinned host tensors) + last_loss()")
 
-  # ---- roofline of the dominant kernel: conv1 forward (5x5, 9->10 ch, 64x64, B=256), timed alone with CUDA events
+  # ---- roofline of the dominant tensor-core kernel: conv1 forward of actor+critic on state_1 in one tcgen05 pass
+  # (5x5, 9 -> 2x10 ch, 64x64, B=256), timed alone with CUDA events on the launching stream, L2 flushed in between
   roof = None
-  if dp.rank == 0:
+  if dp.rank == 0 and not args.skip_roofline:
     peaks = measured_peaks()
     x = out.state_1
-    w = actor.get_variable("actor/conv1/weights"); bvar = actor.get_variable("actor/conv1/biases")
-    pooled = torch.empty((BATCH, 32, 32, 10), dtype=torch.float32, device=dev)
-    amax = torch.empty((BATCH, 32, 32, 10), dtype=torch.uint8, device=dev)
+    ws_ = [actor.get_variable("actor/conv1/weights"), critic.get_variable("critic/conv1/weights")]
+    bs_ = [actor.get_variable("actor/conv1/biases"), critic.get_variable("critic/conv1/biases")]
+    pooled = [torch.empty((BATCH, 32, 32, 10), dtype=torch.float32, device=dev) for _ in range(2)]
+    amax = [torch.empty((BATCH, 32, 32, 10), dtype=torch.uint8, device=dev) for _ in range(2)]
+    scr = torch.zeros(int(lib.cpp_conv_tc_scratch_bytes(2, 64, 64, 9, 5)), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    wp, bp, pp, ap = _lib.ptr_array(ws_), _lib.ptr_array(bs_), _lib.ptr_array(pooled), _lib.ptr_array(amax)
     def conv1():
-      _lib.check(lib.cpp_conv_forward(_lib.ptr(x), 1, _lib.ptr(m1), _lib.ptr(w), _lib.ptr(bvar), BATCH, 64, 64, 9, 5,
-                                      _lib.ptr(pooled), _lib.ptr(amax), _lib.stream_ptr()))
+      _lib.check(lib.cpp_conv_forward_tc(_lib.ptr(x), None, _lib.ptr(m1), 2, wp, bp, BATCH, 64, 64, 9, 5, pp, ap, _lib.ptr(scr),
+                                         _lib.stream_ptr()))
     for _ in range(3):
       conv1()
     ts = []
@@ -255,12 +260,13 @@ def run_native(args):
       a.record(); conv1(); b_.record(); torch.cuda.synchronize()
       ts.append(a.elapsed_time(b_))
     kms = float(np.mean(ts))
-    flops = 2.0 * BATCH * 64 * 64 * 10 * 25 * 9             # conv1 MACs/sample = H*W*10*25*Cin
+    flops = 2.0 * 2 * BATCH * 64 * 64 * 10 * 25 * 9         # conv1 MACs/sample = H*W*10*25*Cin, two sibling nets
     ach = flops / (kms * 1e-3) / 1e12
-    roof = dict(kernel="conv_kernel<5,0,0> (conv1 5x5 fwd + bias + ReLU + 2x2 maxpool, fp32 FFMA)", bound="tensor",
+    roof = dict(kernel="conv_fwd_tc_kernel<5,1> + weight prep (conv1 5x5 fwd of actor+critic, whitening fold, bias, ReLU, 2x2 maxpool; "
+                       "tcgen05.mma kind::f16, fp32 weights as 2 fp16 pieces)", bound="tensor",
                 achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=None,
                 peak_source=peaks["source"] + " bf16 dense (burst)", kernel_ms=kms, algorithmic_flops_per_launch=flops,
-                note="exact-fp32 CUDA-core kernel measured against the bf16 tensor peak")
+                note="algorithmic (useful) FLOPs: N = 20 real filters of 48 issued columns, K = 225 of 256 issued")
 
   cpu = None
   if dp.rank == 0 and not args.skip_cpu_baseline:

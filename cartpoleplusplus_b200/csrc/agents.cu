@@ -2,6 +2,7 @@
 // (naf_cartpole.py:147-284,367-373), LRPG (lrpg_cartpole.py:80-130,165-182).
 // Every step is "backward" (forward + loss + gradients into the flat gradient buffer) followed by
 // "apply" (global-norm clip + optimiser); a data-parallel host all-reduces the flat buffer in between.
+#include <algorithm>
 #include "agents.cuh"
 
 namespace cpp {
@@ -39,6 +40,9 @@ void DDPG::carve(void* ws, bool assign) {
   char* wc = cv.take<char>(critic.workspace_bytes(B));
   const size_t wt_b = actor.workspace_bytes(B) > critic.workspace_bytes(B) ? actor.workspace_bytes(B) : critic.workspace_bytes(B);
   char* wt = cv.take<char>(wt_b);
+  char* wt2 = cv.take<char>(critic.workspace_bytes(B));
+  void* ts1 = cv.take<char>((size_t)trunk_group_scratch_bytes(2, actor));
+  void* ts2 = cv.take<char>((size_t)trunk_group_scratch_bytes(2, actor));
   float* mu_ = cv.take<float>((size_t)B * A); float* dqda_ = cv.take<float>((size_t)B * A); float* neg_ = cv.take<float>((size_t)B * A);
   float* mu2_ = cv.take<float>((size_t)B * A);
   float* q_ = cv.take<float>(B); float* q2_ = cv.take<float>(B); float* td_ = cv.take<float>(B); float* dq_ = cv.take<float>(B);
@@ -48,7 +52,7 @@ void DDPG::carve(void* ws, bool assign) {
   float* sc = cv.take<float>(4);
   ws_bytes = cv.off;
   if (assign) {
-    ws_actor = wa; ws_critic = wc; ws_target = wt; mu = mu_; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
+    ws_actor = wa; ws_critic = wc; ws_target = wt; ws_target2 = wt2; tc_scr1 = ts1; tc_scr2 = ts2; mu = mu_; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
     ones = ones_; mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
   }
 }
@@ -83,8 +87,14 @@ int DDPG::actor_backward(const void* s1, int is_f16, int B, int B_global, cudaSt
   const float* m1;
   CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
   cur_m1 = m1;
-  CPP_TRY(actor.forward(buf.params, s1, is_f16, m1, nullptr, B, ws_actor, mu, s));
-  CPP_TRY(critic.forward(buf.params + off_c, s1, is_f16, m1, mu, B, ws_critic, nullptr, s));
+  {  // actor and critic trunks read the same whitened state_1: conv1 of both in one tensor-core pass
+    const Net* g[2] = {&actor, &critic};
+    const float* pp[2] = {buf.params, buf.params + off_c};
+    char* wss[2] = {ws_actor, ws_critic};
+    CPP_TRY(trunk_forward_group(2, g, pp, wss, s1, is_f16, m1, B, tc_scr1, s));
+  }
+  CPP_TRY(actor.forward_fc(buf.params, nullptr, B, ws_actor, mu, s));
+  CPP_TRY(critic.forward_fc(buf.params + off_c, mu, B, ws_critic, nullptr, s));
   if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s)); ones_ready = true; }
   // q_gradients_wrt_actions: tf.gradients(q_value, input_action), ddpg_cartpole.py:220-222
   CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, s));
@@ -110,9 +120,21 @@ int DDPG::critic_forward_td(const void* s1, const float* action, const float* re
   else CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
   cur_m1 = m1;
   // bellman_rhs: target actor/critic on state_2, ddpg_cartpole.py:198-202
-  CPP_TRY(actor.forward(buf.target_params, s2, is_f16, m2, nullptr, B, ws_target, mu2, s));
-  CPP_TRY(critic.forward(buf.target_params + off_c, s2, is_f16, m2, mu2, B, ws_target, q2, s));
-  CPP_TRY(critic.forward(buf.params + off_c, s1, is_f16, m1, action, B, ws_critic, q, s, reuse ? critic.concat_at : 0));
+  {
+    const Net* g[2] = {&actor, &critic};
+    const float* pp[2] = {buf.target_params, buf.target_params + off_c};
+    char* wss[2] = {ws_target, ws_target2};
+    CPP_TRY(trunk_forward_group(2, g, pp, wss, s2, is_f16, m2, B, tc_scr2, s));
+  }
+  CPP_TRY(actor.forward_fc(buf.target_params, nullptr, B, ws_target, mu2, s));
+  CPP_TRY(critic.forward_fc(buf.target_params + off_c, mu2, B, ws_target2, q2, s));
+  if (!reuse) {
+    const Net* g[1] = {&critic};
+    const float* pp[1] = {buf.params + off_c};
+    char* wss[1] = {ws_critic};
+    CPP_TRY(trunk_forward_group(1, g, pp, wss, s1, is_f16, m1, B, tc_scr1, s));
+  }
+  CPP_TRY(critic.forward_fc(buf.params + off_c, action, B, ws_critic, q, s, reuse ? critic.concat_at : 0));
   CPP_TRY(launch_td_mse(q, q2, reward, mask, cfg.discount, B, B_global, td_out, dq_out, loss_flag, s));
   return CPP_OK;
 }
@@ -148,7 +170,11 @@ int DDPG::action_given(const void* state, int is_f16, int B, float* out, cudaStr
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
   const float* m;
   CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));     // statistics of the fed batch itself (B=1 in rollouts)
-  CPP_TRY(actor.forward(buf.params, state, is_f16, m, nullptr, B, ws_target, out, s));
+  const Net* g[1] = {&actor};
+  const float* pp[1] = {buf.params};
+  char* wss[1] = {ws_target};
+  CPP_TRY(trunk_forward_group(1, g, pp, wss, state, is_f16, m, B, tc_scr2, s));
+  CPP_TRY(actor.forward_fc(buf.params, nullptr, B, ws_target, out, s));
   return CPP_OK;
 }
 
@@ -176,7 +202,10 @@ void NAF::carve(void* ws, bool assign) {
   Carver cv(ws);
   const int B = cfg.max_batch, C = value.pixels ? value.spec.Cin : 1, NL = A * (A + 1) / 2;
   char* wv = cv.take<char>(value.workspace_bytes(B)); char* wm = cv.take<char>(mu.workspace_bytes(B));
-  char* wl = cv.take<char>(l.workspace_bytes(B)); char* wt = cv.take<char>(value.workspace_bytes(B));
+  char* wl = cv.take<char>(l.workspace_bytes(B));
+  char* wt = cv.take<char>(std::max(value.workspace_bytes(B), std::max(mu.workspace_bytes(B), l.workspace_bytes(B))));
+  void* ts1 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
+  void* ts2 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
   float* V_ = cv.take<float>(B); float* V2_ = cv.take<float>(B); float* mu_ = cv.take<float>((size_t)B * A); float* lv_ = cv.take<float>((size_t)B * NL);
   float* dV_ = cv.take<float>(B); float* dmu_ = cv.take<float>((size_t)B * A); float* dl_ = cv.take<float>((size_t)B * NL);
   float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
@@ -184,7 +213,7 @@ void NAF::carve(void* ws, bool assign) {
   float* sc = cv.take<float>(4);
   ws_bytes = cv.off;
   if (assign) {
-    ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; V = V_; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
+    ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; tc_scr1 = ts1; tc_scr2 = ts2; V = V_; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
     mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
   }
 }
@@ -216,10 +245,22 @@ int NAF::forward_all(const void* s1, const float* action, const float* reward, c
   CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
   CPP_TRY(stats_for(s2, is_f16, B, mi2, pinned2, &m2, s));
   cur_m1 = m1;
-  CPP_TRY(value.forward(buf.params, s1, is_f16, m1, nullptr, B, ws_v, V, s));
-  CPP_TRY(mu.forward(buf.params + off_m, s1, is_f16, m1, nullptr, B, ws_m, muo, s));
-  CPP_TRY(l.forward(buf.params + off_l, s1, is_f16, m1, nullptr, B, ws_l, lv, s));
-  CPP_TRY(value.forward(buf.target_params, s2, is_f16, m2, nullptr, B, ws_t, V2, s));       // target_value_net, naf_cartpole.py:225-227
+  {  // value / mu / l trunks read the same whitened state_1 (naf_cartpole.py:104,150,175)
+    const Net* g[3] = {&value, &mu, &l};
+    const float* pp[3] = {buf.params, buf.params + off_m, buf.params + off_l};
+    char* wss[3] = {ws_v, ws_m, ws_l};
+    CPP_TRY(trunk_forward_group(3, g, pp, wss, s1, is_f16, m1, B, tc_scr1, s));
+  }
+  CPP_TRY(value.forward_fc(buf.params, nullptr, B, ws_v, V, s));
+  CPP_TRY(mu.forward_fc(buf.params + off_m, nullptr, B, ws_m, muo, s));
+  CPP_TRY(l.forward_fc(buf.params + off_l, nullptr, B, ws_l, lv, s));
+  {  // target_value_net on state_2, naf_cartpole.py:225-227
+    const Net* g[1] = {&value};
+    const float* pp[1] = {buf.target_params};
+    char* wss[1] = {ws_t};
+    CPP_TRY(trunk_forward_group(1, g, pp, wss, s2, is_f16, m2, B, tc_scr2, s));
+  }
+  CPP_TRY(value.forward_fc(buf.target_params, nullptr, B, ws_t, V2, s));
   CPP_TRY(launch_naf_head(V, muo, lv, action, reward, mask, V2, cfg.discount, B, A, B_global,
                           grads ? dV : nullptr, dmu, dl, adv_out, loss_flag, s));
   return CPP_OK;
@@ -270,14 +311,22 @@ int NAF::action_given(const void* state, int is_f16, int B, float* out, cudaStre
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
   const float* m;
   CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));
-  return mu.forward(buf.params + off_m, state, is_f16, m, nullptr, B, ws_t, out, s);
+  const Net* g[1] = {&mu};
+  const float* pp[1] = {buf.params + off_m};
+  char* wss[1] = {ws_t};
+  CPP_TRY(trunk_forward_group(1, g, pp, wss, state, is_f16, m, B, tc_scr2, s));
+  return mu.forward_fc(buf.params + off_m, nullptr, B, ws_t, out, s);
 }
 
 int NAF::value_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
   const float* m;
   CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));
-  return value.forward(buf.params, state, is_f16, m, nullptr, B, ws_t, out, s);
+  const Net* g[1] = {&value};
+  const float* pp[1] = {buf.params};
+  char* wss[1] = {ws_t};
+  CPP_TRY(trunk_forward_group(1, g, pp, wss, state, is_f16, m, B, tc_scr2, s));
+  return value.forward_fc(buf.params, nullptr, B, ws_t, out, s);
 }
 
 int NAF::update_targets(float coeff, cudaStream_t s) {

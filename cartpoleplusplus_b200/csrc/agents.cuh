@@ -12,7 +12,8 @@ struct DDPG {
   bool bound = false;
   size_t ws_bytes = 0;
   // carved workspace
-  char *ws_actor = nullptr, *ws_critic = nullptr, *ws_target = nullptr;
+  char *ws_actor = nullptr, *ws_critic = nullptr, *ws_target = nullptr, *ws_target2 = nullptr;
+  void *tc_scr1 = nullptr, *tc_scr2 = nullptr;   // packed conv1 weights of the state_1 / state_2 trunk groups (conv_tc.cu)
   float *mu = nullptr, *dqda = nullptr, *neg = nullptr, *mu2 = nullptr, *q = nullptr, *q2 = nullptr, *td = nullptr, *dq = nullptr;
   float *ones = nullptr, *mi1 = nullptr, *mi2 = nullptr, *scale2 = nullptr;
   double *mom_scratch = nullptr, *norm_scratch = nullptr;
@@ -46,6 +47,7 @@ struct NAF {
   bool bound = false;
   size_t ws_bytes = 0;
   char *ws_v = nullptr, *ws_m = nullptr, *ws_l = nullptr, *ws_t = nullptr;
+  void *tc_scr1 = nullptr, *tc_scr2 = nullptr;
   float *V = nullptr, *V2 = nullptr, *muo = nullptr, *lv = nullptr, *dV = nullptr, *dmu = nullptr, *dl = nullptr;
   float *mi1 = nullptr, *mi2 = nullptr, *scale2 = nullptr;
   double *mom_scratch = nullptr, *norm_scratch = nullptr;

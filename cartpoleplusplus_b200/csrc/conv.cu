@@ -345,13 +345,22 @@ __global__ void __launch_bounds__(256, 2) conv_wgrad_kernel(WgradParams p) {
   for (int i = tid; i < p.nout; i += nthr) out[i] = red[i];
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nparts, int nout, int nw,
-                                       float* __restrict__ dw, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nout) return;
+// block (32, 8): column x sums the partials of output i, row y covers a contiguous range of CTAs; fixed order
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int nout, int nw,
+                                                              float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sh[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
+  const int per = (nparts + 7) / 8, k0 = y * per, k1 = min(nparts, k0 + per);
   float s = 0.f;
-  for (int k = 0; k < nparts; ++k) s += partials[(size_t)k * nout + i];
-  if (i < nw) dw[i] = s; else db[i - nw] = s;
+  if (i < nout) for (int k = k0; k < k1; ++k) s += partials[(size_t)k * nout + i];
+  sh[y][threadIdx.x] = s;
+  __syncthreads();
+  if (y == 0 && i < nout) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sh[r][threadIdx.x];
+    if (i < nw) dw[i] = t; else db[i - nw] = t;
+  }
 }
 
 struct WgradPlan { int G, TWt, chpitch, tiles_x, tiles_y, nout, threads, grid_cap; size_t smem; };
@@ -411,7 +420,7 @@ int launch_conv_wgrad(const ConvLayer& L, const void* x, int x_is_f16, const flo
   if (grid < 1) grid = 1;
   if (x_is_f16) { CPP_TRY((L.KS == 5 ? launch_wgrad_t<5, 0>(p, w, grid, s) : launch_wgrad_t<3, 0>(p, w, grid, s))); }
   else { CPP_TRY((L.KS == 5 ? launch_wgrad_t<5, 1>(p, w, grid, s) : launch_wgrad_t<3, 1>(p, w, grid, s))); }
-  reduce_partials_kernel<<<(unsigned)ceil_div(w.nout, 128), 128, 0, s>>>(scratch, grid, w.nout, w.nout - CO, dw, db);
+  reduce_partials_kernel<<<(unsigned)ceil_div(w.nout, 32), dim3(32, 8), 0, s>>>(scratch, grid, w.nout, w.nout - CO, dw, db);
   CPP_CHECK_LAUNCH();
   return CPP_OK;
 }

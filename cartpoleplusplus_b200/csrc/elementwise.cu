@@ -208,16 +208,19 @@ __global__ void __launch_bounds__(256) slot_stats_kernel(const __half* __restric
   }
 }
 
-__global__ void moments_from_slots_kernel(const double* __restrict__ stats, const int32_t* __restrict__ slot_table,
-                                          const int64_t* __restrict__ idxs, int B, double n_per_channel, int C,
-                                          float* __restrict__ mean_inv) {
-  const int c = threadIdx.x;
+// one warp per channel: lane l sums slots l, l+32, ... in fp64, then a fixed-order shuffle reduction (deterministic)
+__global__ void __launch_bounds__(256) moments_from_slots_kernel(const double* __restrict__ stats, const int32_t* __restrict__ slot_table,
+                                                                 const int64_t* __restrict__ idxs, int B, double n_per_channel, int C,
+                                                                 float* __restrict__ mean_inv) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < B; ++b) {
+  for (int b = lane; b < B; b += 32) {
     const size_t slot = (size_t)slot_table[idxs[b]];
     s1 += stats[slot * 2 * C + c]; s2 += stats[slot * 2 * C + C + c];
   }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane != 0) return;
   const double mean = s1 / n_per_channel;
   double var = s2 / n_per_channel - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -593,7 +596,7 @@ int launch_slot_stats(const void* slab, const int32_t* slots, int n, int64_t n_p
 }
 int launch_moments_from_slots(const double* stats, const int32_t* slot_table, const int64_t* idxs, int B, int64_t n_pix, int C,
                               float* mean_inv, cudaStream_t s) {
-  moments_from_slots_kernel<<<1, (unsigned)round_up(C, 32), 0, s>>>(stats, slot_table, idxs, B, (double)B * (double)n_pix, C, mean_inv);
+  moments_from_slots_kernel<<<(unsigned)ceil_div(C, 8), 256, 0, s>>>(stats, slot_table, idxs, B, (double)B * (double)n_pix, C, mean_inv);
   CPP_CHECK_LAUNCH();
   return CPP_OK;
 }

@@ -6,50 +6,72 @@
 
 namespace cpp {
 
-constexpr int BM = 32, BN = 64, BK = 16;
+constexpr int BM = 32, BN = 32, BK = 32;     // small tiles: the layers are tiny, parallelism comes from the CTA count
 
+// 128 threads, thread (tm, tn) owns a 2 x 4 block of C.  The next K tile is fetched into registers while the current one is
+// multiplied out of shared memory (the layers are latency bound: K <= 2560, M or N <= 256).
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(128) gemm_kernel(GemmArgs g) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
-  const int tm = tid / 16, tn = tid % 16;
+  const int tm = tid / 8, tn = tid % 8;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[4][4];
+  float acc[2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  constexpr int NA = (BM * BK) / 128, NB = (BN * BK) / 128;
+  float ra[NA], rb[NB];
 
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < (BM * BK) / 128; ++i) {
+    for (int i = 0; i < NA; ++i) {
       const int e = tid + i * 128;
       int m, k;
       if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
       const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < g.M && gk < g.K) v = TA ? g.A[(size_t)gk * g.lda + gm] : g.A[(size_t)gm * g.lda + gk];
-      As[k][m] = v;
+      ra[i] = (gm < g.M && gk < g.K) ? (TA ? g.A[(size_t)gk * g.lda + gm] : g.A[(size_t)gm * g.lda + gk]) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < (BN * BK) / 128; ++i) {
+    for (int i = 0; i < NB; ++i) {
       const int e = tid + i * 128;
       int n, k;
       if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
       const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < g.N && gk < g.K) v = TB ? g.B[(size_t)gn * g.ldb + gk] : g.B[(size_t)gk * g.ldb + gn];
-      Bs[k][n] = v;
+      rb[i] = (gn < g.N && gk < g.K) ? (TB ? g.B[(size_t)gn * g.ldb + gk] : g.B[(size_t)gk * g.ldb + gn]) : 0.f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int e = tid + i * 128;
+      int m, k;
+      if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      As[k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int e = tid + i * 128;
+      int n, k;
+      if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      Bs[k][n] = rb[i];
+    }
+  };
+
+  fetch(0);
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    stash();
     __syncthreads();
+    if (k0 + BK < g.K) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][4 * tm]);
+      const float2 a = *reinterpret_cast<const float2*>(&As[kk][2 * tm]);
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][4 * tn]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float av[2] = {a.x, a.y}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -57,8 +79,8 @@ __global__ void __launch_bounds__(128) gemm_kernel(GemmArgs g) {
   }
 
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + 4 * tm + i;
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + 2 * tm + i;
     if (m >= g.M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -1,5 +1,7 @@
 // Net: parameter layout, activation workspace, forward and backward of one reference network.
+#include <stdlib.h>
 #include "net.cuh"
+#include "conv_tc.cuh"
 
 namespace cpp {
 
@@ -94,26 +96,32 @@ const float* Net::fc_input(const Layout& L, char* ws, int i, int* ld) const {
   return reinterpret_cast<const float*>(ws + L.h[i - 1]);
 }
 
-int Net::forward(const float* params, const void* state, int is_f16, const float* mean_inv, const float* action,
-                 int B, void* ws_, float* out, cudaStream_t s, int first_fc) const {
+int Net::forward_trunk(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
+                       cudaStream_t s, int first_conv) const {
+  CPP_REQUIRE(B >= 1, "batch %d", B);
+  char* ws = reinterpret_cast<char*>(ws_);
+  const Layout L = layout(B);
+  if (pixels) {
+    CPP_REQUIRE(first_conv > 0 || mean_inv != nullptr, "pixel network needs whitening statistics");
+    const void* x = state; int xf16 = is_f16; const float* mi = mean_inv;
+    if (first_conv > 0) { x = ws + L.pooled[first_conv - 1]; xf16 = 0; mi = nullptr; }
+    for (int i = first_conv; i < 3; ++i) {
+      float* pooled = reinterpret_cast<float*>(ws + L.pooled[i]);
+      uint8_t* amax = reinterpret_cast<uint8_t*>(ws + L.amax[i]);
+      CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
+      x = pooled; xf16 = 0; mi = nullptr;
+    }
+  } else {
+    CPP_TRY(launch_state_to_f32(state, is_f16, B, feat, reinterpret_cast<float*>(ws + L.x0), in_dim[0], s));
+  }
+  return CPP_OK;
+}
+
+int Net::forward_fc(const float* params, const float* action, int B, void* ws_, float* out, cudaStream_t s, int first_fc) const {
   CPP_REQUIRE(B >= 1, "batch %d", B);
   CPP_REQUIRE(concat_at < 0 || action != nullptr, "this network needs an action input");
   char* ws = reinterpret_cast<char*>(ws_);
   const Layout L = layout(B);
-  if (first_fc == 0) {
-    if (pixels) {
-      CPP_REQUIRE(mean_inv != nullptr, "pixel network needs whitening statistics");
-      const void* x = state; int xf16 = is_f16; const float* mi = mean_inv;
-      for (int i = 0; i < 3; ++i) {
-        float* pooled = reinterpret_cast<float*>(ws + L.pooled[i]);
-        uint8_t* amax = reinterpret_cast<uint8_t*>(ws + L.amax[i]);
-        CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
-        x = pooled; xf16 = 0; mi = nullptr;
-      }
-    } else {
-      CPP_TRY(launch_state_to_f32(state, is_f16, B, feat, reinterpret_cast<float*>(ws + L.x0), in_dim[0], s));
-    }
-  }
   for (int i = first_fc; i < n_fc; ++i) {
     int ld;
     const float* x = fc_input(L, ws, i, &ld);
@@ -131,6 +139,49 @@ int Net::forward(const float* params, const void* state, int is_f16, const float
     const int n = out_dim[n_fc - 1];
     CPP_CHECK_CUDA(cudaMemcpyAsync(out, ws + L.h[n_fc - 1], (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
+  return CPP_OK;
+}
+
+int Net::forward(const float* params, const void* state, int is_f16, const float* mean_inv, const float* action,
+                 int B, void* ws, float* out, cudaStream_t s, int first_fc) const {
+  if (first_fc == 0) CPP_TRY(forward_trunk(params, state, is_f16, mean_inv, B, ws, s, 0));
+  return forward_fc(params, action, B, ws, out, s, first_fc);
+}
+
+bool conv1_tc_enabled() {
+  static const bool on = [] { const char* e = getenv("CARTPOLEPP_CONV1"); return !(e && std::string(e) == "ffma"); }();
+  return on;
+}
+
+int64_t trunk_group_scratch_bytes(int n, const Net& net) {
+  if (!net.pixels) return 0;
+  const int64_t b = tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
+  return b > 0 ? b : 0;
+}
+
+int trunk_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
+                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s) {
+  CPP_REQUIRE(n >= 1 && n <= tc::kMaxNets, "trunk group of %d networks", n);
+  const Net& n0 = *nets[0];
+  int first_conv = 0;
+  if (n0.pixels && is_f16 && tc_scratch != nullptr && conv1_tc_enabled() &&
+      tc::conv_tc_supported(n, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin, n0.conv[0].KS)) {
+    CPP_REQUIRE(mean_inv != nullptr, "pixel network needs whitening statistics");
+    const float *w[tc::kMaxNets], *b[tc::kMaxNets];
+    float* pooled[tc::kMaxNets]; uint8_t* amax[tc::kMaxNets];
+    for (int i = 0; i < n; ++i) {
+      const Net& ni = *nets[i];
+      CPP_REQUIRE(ni.pixels && ni.conv[0].H == n0.conv[0].H && ni.conv[0].W == n0.conv[0].W && ni.conv[0].Cin == n0.conv[0].Cin,
+                  "sibling networks must read the same state");
+      const Net::Layout L = ni.layout(B);
+      w[i] = params[i] + ni.off_conv_w[0]; b[i] = params[i] + ni.off_conv_b[0];
+      pooled[i] = reinterpret_cast<float*>(ws[i] + L.pooled[0]); amax[i] = reinterpret_cast<uint8_t*>(ws[i] + L.amax[0]);
+    }
+    CPP_TRY(tc::launch_conv_fwd_tc(state, nullptr, mean_inv, n, w, b, B, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin,
+                                   n0.conv[0].KS, pooled, amax, tc_scratch, s));
+    first_conv = 1;
+  }
+  for (int i = 0; i < n; ++i) CPP_TRY(nets[i]->forward_trunk(params[i], state, is_f16, mean_inv, B, ws[i], s, first_conv));
   return CPP_OK;
 }
 

@@ -35,10 +35,24 @@ struct Net {
   // previous forward held in ws (k must be <= concat_at or the action unchanged); action is re-copied.
   int forward(const float* params, const void* state, int is_f16, const float* mean_inv, const float* action,
               int B, void* ws, float* out, cudaStream_t s, int first_fc = 0) const;
+  // the two halves of forward(): conv trunk (first_conv == 1: conv1 is already in ws, written by the tensor-core
+  // kernel) or the fp16/fp32 -> fp32 state copy of a low-dim network; then the FC stack from layer first_fc
+  int forward_trunk(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
+                    cudaStream_t s, int first_conv = 0) const;
+  int forward_fc(const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s, int first_fc = 0) const;
   // grads == nullptr: only d_action is produced (stops at the concat layer).
   int backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
                const float* d_out, float* grads, float* d_action, cudaStream_t s) const;
 };
+
+// Conv trunks of n (<= 3) sibling networks that read the SAME state (actor+critic on state_1, the two targets on
+// state_2, ddpg_cartpole.py:270-273; NAF's value/mu/l, naf_cartpole.py:104,150,175): conv1 of all of them in one
+// tcgen05 pass over the pixels (conv_tc.cu) when the state is fp16 and tc_scratch is given, conv2/conv3 per net.
+// Falls back to the exact-fp32 CUDA-core conv1 for fp32 states (action_given from the env) or CARTPOLEPP_CONV1=ffma.
+int64_t trunk_group_scratch_bytes(int n, const Net& net);
+int trunk_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
+                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s);
+bool conv1_tc_enabled();
 
 // elementwise.cu
 int64_t moments_scratch_doubles(int C);
