@@ -43,6 +43,7 @@ void DDPG::carve(void* ws, bool assign) {
   char* wt2 = cv.take<char>(critic.workspace_bytes(B));
   void* ts1 = cv.take<char>((size_t)trunk_group_scratch_bytes(2, actor));
   void* ts2 = cv.take<char>((size_t)trunk_group_scratch_bytes(2, actor));
+  void* wgs = cv.take<char>((size_t)std::max(conv1_wgrad_group_scratch_bytes(1, actor), conv1_wgrad_group_scratch_bytes(2, actor)));
   float* mu_ = cv.take<float>((size_t)B * A); float* dqda_ = cv.take<float>((size_t)B * A); float* neg_ = cv.take<float>((size_t)B * A);
   float* mu2_ = cv.take<float>((size_t)B * A);
   float* q_ = cv.take<float>(B); float* q2_ = cv.take<float>(B); float* td_ = cv.take<float>(B); float* dq_ = cv.take<float>(B);
@@ -52,7 +53,7 @@ void DDPG::carve(void* ws, bool assign) {
   float* sc = cv.take<float>(4);
   ws_bytes = cv.off;
   if (assign) {
-    ws_actor = wa; ws_critic = wc; ws_target = wt; ws_target2 = wt2; tc_scr1 = ts1; tc_scr2 = ts2; mu = mu_; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
+    ws_actor = wa; ws_critic = wc; ws_target = wt; ws_target2 = wt2; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; mu = mu_; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
     ones = ones_; mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
   }
 }
@@ -99,7 +100,11 @@ int DDPG::actor_backward(const void* s1, int is_f16, int B, int B_global, cudaSt
   // q_gradients_wrt_actions: tf.gradients(q_value, input_action), ddpg_cartpole.py:220-222
   CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, s));
   CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, s));                       // tf.neg(...), :113
-  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s));
+  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s, 1));
+  {
+    const Net* g[1] = {&actor}; char* wss[1] = {ws_actor}; float* gr[1] = {buf.grads};
+    CPP_TRY(conv1_wgrad_group(1, g, wss, gr, s1, is_f16, m1, B, wg_scr, s));
+  }
   critic_trunk_valid = true; trunk_B = B;
   return CPP_OK;
 }
@@ -143,7 +148,45 @@ int DDPG::critic_backward(const void* s1, const float* action, const float* rewa
                           int is_f16, int B, int B_global, int reuse, cudaStream_t s) {
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
   CPP_TRY(critic_forward_td(s1, action, reward, mask, s2, is_f16, B, B_global, reuse != 0, td, dq, buf.grads + off_loss, s));
-  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, cur_m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s));
+  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, cur_m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s, 1));
+  {
+    const Net* g[1] = {&critic}; char* wss[1] = {ws_critic}; float* gr[1] = {buf.grads + off_c};
+    CPP_TRY(conv1_wgrad_group(1, g, wss, gr, s1, is_f16, cur_m1, B, wg_scr, s));
+  }
+  critic_trunk_valid = false;
+  return CPP_OK;
+}
+
+int DDPG::step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
+                        int is_f16, int B, int B_global, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  const int A = critic.action_dim;
+  const float* m1;
+  CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
+  cur_m1 = m1;
+  {
+    const Net* g[2] = {&actor, &critic};
+    const float* pp[2] = {buf.params, buf.params + off_c};
+    char* wss[2] = {ws_actor, ws_critic};
+    CPP_TRY(trunk_forward_group(2, g, pp, wss, s1, is_f16, m1, B, tc_scr1, s));
+  }
+  // ---- actor.train(state_1): ddpg_cartpole.py:102-119,140-145
+  CPP_TRY(actor.forward_fc(buf.params, nullptr, B, ws_actor, mu, s));
+  CPP_TRY(critic.forward_fc(buf.params + off_c, mu, B, ws_critic, nullptr, s));
+  if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s)); ones_ready = true; }
+  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, s));
+  CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, s));
+  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s, 1));
+  // ---- critic.train(batch): :186-218,230-237.  The critic trunk on state_1 is the one computed above (the critic's
+  // parameters have not changed); only the layers from the action concat upwards are re-evaluated at the batch actions.
+  critic_trunk_valid = true; trunk_B = B;
+  CPP_TRY(critic_forward_td(s1, action, reward, mask, s2, is_f16, B, B_global, true, td, dq, buf.grads + off_loss, s));
+  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s, 1));
+  // ---- conv1 weight gradients of both networks in one pass over state_1
+  {
+    const Net* g[2] = {&actor, &critic}; char* wss[2] = {ws_actor, ws_critic}; float* gr[2] = {buf.grads, buf.grads + off_c};
+    CPP_TRY(conv1_wgrad_group(2, g, wss, gr, s1, is_f16, m1, B, wg_scr, s));
+  }
   critic_trunk_valid = false;
   return CPP_OK;
 }
@@ -206,6 +249,7 @@ void NAF::carve(void* ws, bool assign) {
   char* wt = cv.take<char>(std::max(value.workspace_bytes(B), std::max(mu.workspace_bytes(B), l.workspace_bytes(B))));
   void* ts1 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
   void* ts2 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
+  void* wgs = cv.take<char>((size_t)conv1_wgrad_group_scratch_bytes(3, value));
   float* V_ = cv.take<float>(B); float* V2_ = cv.take<float>(B); float* mu_ = cv.take<float>((size_t)B * A); float* lv_ = cv.take<float>((size_t)B * NL);
   float* dV_ = cv.take<float>(B); float* dmu_ = cv.take<float>((size_t)B * A); float* dl_ = cv.take<float>((size_t)B * NL);
   float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
@@ -213,7 +257,7 @@ void NAF::carve(void* ws, bool assign) {
   float* sc = cv.take<float>(4);
   ws_bytes = cv.off;
   if (assign) {
-    ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; tc_scr1 = ts1; tc_scr2 = ts2; V = V_; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
+    ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; V = V_; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
     mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
   }
 }
@@ -270,9 +314,14 @@ int NAF::backward(const void* s1, const float* action, const float* reward, cons
                   int B, int B_global, cudaStream_t s) {
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
   CPP_TRY(forward_all(s1, action, reward, mask, s2, is_f16, B, B_global, true, nullptr, buf.grads + off_loss, s));
-  CPP_TRY(value.backward(buf.params, s1, is_f16, cur_m1, B, ws_v, dV, buf.grads, nullptr, s));
-  CPP_TRY(mu.backward(buf.params + off_m, s1, is_f16, cur_m1, B, ws_m, dmu, buf.grads + off_m, nullptr, s));
-  CPP_TRY(l.backward(buf.params + off_l, s1, is_f16, cur_m1, B, ws_l, dl, buf.grads + off_l, nullptr, s));
+  CPP_TRY(value.backward(buf.params, s1, is_f16, cur_m1, B, ws_v, dV, buf.grads, nullptr, s, 1));
+  CPP_TRY(mu.backward(buf.params + off_m, s1, is_f16, cur_m1, B, ws_m, dmu, buf.grads + off_m, nullptr, s, 1));
+  CPP_TRY(l.backward(buf.params + off_l, s1, is_f16, cur_m1, B, ws_l, dl, buf.grads + off_l, nullptr, s, 1));
+  {  // conv1 weight gradients of the three networks in one pass over state_1
+    const Net* g[3] = {&value, &mu, &l}; char* wss[3] = {ws_v, ws_m, ws_l};
+    float* gr[3] = {buf.grads, buf.grads + off_m, buf.grads + off_l};
+    CPP_TRY(conv1_wgrad_group(3, g, wss, gr, s1, is_f16, cur_m1, B, wg_scr, s));
+  }
   return CPP_OK;
 }
 

@@ -14,6 +14,7 @@ struct DDPG {
   // carved workspace
   char *ws_actor = nullptr, *ws_critic = nullptr, *ws_target = nullptr, *ws_target2 = nullptr;
   void *tc_scr1 = nullptr, *tc_scr2 = nullptr;   // packed conv1 weights of the state_1 / state_2 trunk groups (conv_tc.cu)
+  void* wg_scr = nullptr;                          // conv1 weight-gradient partials (conv_wgrad_mma.cu)
   float *mu = nullptr, *dqda = nullptr, *neg = nullptr, *mu2 = nullptr, *q = nullptr, *q2 = nullptr, *td = nullptr, *dq = nullptr;
   float *ones = nullptr, *mi1 = nullptr, *mi2 = nullptr, *scale2 = nullptr;
   double *mom_scratch = nullptr, *norm_scratch = nullptr;
@@ -32,6 +33,10 @@ struct DDPG {
   int critic_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
                       int B, int B_global, int reuse, cudaStream_t s);
   int critic_apply(cudaStream_t s);
+  // one whole grad-step (ddpg_cartpole.py:332-334) as backward-of-both then apply-of-both: the critic gradient does not
+  // depend on the actor update, so actor.train(s1); critic.train(batch) can share every pass over state_1
+  int step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                    int B, int B_global, cudaStream_t s);
   int check_loss(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
                  float* loss, float* td_out, float* q_out, cudaStream_t s);
   int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
@@ -47,7 +52,7 @@ struct NAF {
   bool bound = false;
   size_t ws_bytes = 0;
   char *ws_v = nullptr, *ws_m = nullptr, *ws_l = nullptr, *ws_t = nullptr;
-  void *tc_scr1 = nullptr, *tc_scr2 = nullptr;
+  void *tc_scr1 = nullptr, *tc_scr2 = nullptr, *wg_scr = nullptr;
   float *V = nullptr, *V2 = nullptr, *muo = nullptr, *lv = nullptr, *dV = nullptr, *dmu = nullptr, *dl = nullptr;
   float *mi1 = nullptr, *mi2 = nullptr, *scale2 = nullptr;
   double *mom_scratch = nullptr, *norm_scratch = nullptr;

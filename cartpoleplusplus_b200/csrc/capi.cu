@@ -4,6 +4,8 @@
 #include <new>
 #include "agents.cuh"
 #include "conv_tc.cuh"
+#include "conv_wgrad_mma.cuh"
+#include <string.h>
 
 namespace cpp {
 long long g_launch_count = 0;
@@ -35,6 +37,15 @@ extern "C" {
 int cpp_version(void) { return CPP_ABI_VERSION; }
 const char* cpp_last_error(void) { return get_error(); }
 int64_t cpp_launch_count(void) { return g_launch_count; }
+
+int cpp_set_option(const char* name, int32_t value) {
+  API_BEGIN
+  NEED(name);
+  if (strcmp(name, "conv1_tc") == 0) { set_conv1_tc_enabled(value); return CPP_OK; }
+  set_error("unknown option `%s`", name);
+  return CPP_ERR_INVALID;
+  API_END
+}
 
 // ---------------------------------------------------------------- replay / moments
 int cpp_replay_gather(const void* slab, const int32_t* s1_idx, const int32_t* s2_idx, const float* action, const float* reward,
@@ -157,6 +168,18 @@ int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mea
   API_END
 }
 
+int64_t cpp_conv_wgrad_mma_scratch_bytes(int32_t nets, int32_t H, int32_t W, int32_t Cin, int32_t KS) {
+  return wg::conv_wgrad_mma_scratch_bytes(nets, H, W, Cin, KS);
+}
+int cpp_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int32_t x_is_pieces, int32_t nets, const float* const* d_pooled,
+                       const uint8_t* const* amax, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS, float* const* dw,
+                       float* const* db, void* scratch, void* stream) {
+  API_BEGIN
+  NEED(x_f16); NEED(d_pooled); NEED(amax); NEED(dw); NEED(db); NEED(scratch);
+  return wg::launch_conv_wgrad_mma(x_f16, mean_inv, x_is_pieces, nets, d_pooled, amax, B, H, W, Cin, KS, dw, db, scratch, ST(stream));
+  API_END
+}
+
 // ---------------------------------------------------------------- clip / optimiser / target copy
 int64_t cpp_norm_scratch_doubles(void) { return norm_scratch_doubles(); }
 int cpp_global_norm_scale(const float* grads, int64_t n, float clip, double* scratch, float* out2, void* stream) {
@@ -230,6 +253,21 @@ int cpp_ddpg_critic_train(cpp_ddpg* a, const void* s1, const float* action, cons
   API_BEGIN
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
   CPP_TRY(a->a.critic_backward(s1, action, reward, mask, s2, is_f16, B, B, 0, ST(stream)));
+  return a->a.critic_apply(ST(stream));
+  API_END
+}
+int cpp_ddpg_step_backward(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask,
+                           const void* s2, int32_t is_f16, int32_t B, int32_t B_global, void* stream) {
+  API_BEGIN
+  NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
+  CPP_REQUIRE(B_global >= B, "B_global %d < B %d", B_global, B);
+  return a->a.step_backward(s1, action, reward, mask, s2, is_f16, B, B_global, ST(stream));
+  API_END
+}
+int cpp_ddpg_step_apply(cpp_ddpg* a, void* stream) {
+  API_BEGIN
+  NEED(a);
+  CPP_TRY(a->a.actor_apply(ST(stream)));
   return a->a.critic_apply(ST(stream));
   API_END
 }

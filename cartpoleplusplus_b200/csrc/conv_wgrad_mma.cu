@@ -1,0 +1,430 @@
+// Weight / bias gradient of one conv layer of the reference trunk (slim.conv2d + relu + max_pool2d, base_network.py:103-123,
+// differentiated by tf.gradients in ddpg_cartpole.py:111,213 / naf_cartpole.py:233) on the tensor cores:
+//
+//   dW_n[ky][kx][c][o] = sum_{b,y,x} xhat[b][y+ky-P][x+kx-P][c] * dY_n[b][y][x][o]          db_n[o] = sum dY_n
+//   dY_n[b][y][x][o]   = d_pooled_n[b][y/2][x/2][o] if (y,x) is the arg-max of its 2x2 window and the ReLU is open, else 0
+//
+// as ONE GEMM  G[(ky,kx,c), (n,piece,o)] = X^T . dY  whose reduction dimension is the pixel index:
+//  * the sibling networks n (actor+critic on state_1; NAF value/mu/l) share X, so they sit side by side along N, and every
+//    fp32 gradient enters as two fp16 pieces (hi + lo, 22 mantissa bits, scaled by a power of two taken from max|d_pooled|) so
+//    that the fp16 x fp16 -> fp32 MMA stays inside the 1e-5 parity budget; the replay pixels are exact fp16 operands.
+//  * the whitening xhat = (x - mean_c) inv_c with ZERO padding of xhat (base_network.py:95-99 then SAME conv) is folded out:
+//    the kernel multiplies RAW pixels plus one constant-one channel (1 inside the image, 0 in the padding), giving
+//    S[(ky,kx),o] = sum over the positions whose tap lies inside the image of dY, and the finalize kernel forms
+//    dW = inv_c (G - mean_c S), db = S[centre tap].
+//  * im2col-free: a band of input rows is staged ONCE in shared memory as 16-byte channel-group vectors per pixel
+//    (plane layout [group][row][col]); the A fragment of tap (ky,kx) for 16 consecutive output pixels is then
+//    ldmatrix.trans on 16 consecutive vectors of the same plane shifted by (ky,kx) - no data is replicated per tap.
+//    Channels beyond a multiple of 8 (9+1 = 8 + 2, 18+1 = 16 + 3, 24+1 = 24 + 1) are packed along kx into extra planes.
+//  * why mma.sync and not tcgen05 here: the reduction runs over pixels, so both operands are "MN-major" with a per-tap
+//    address pattern that a single UMMA shared-memory descriptor cannot express for M = 128 rows (wgrad).
+//  * deterministic: every CTA owns a contiguous range of bands and a private partial (flushed with plain fp32 adds every
+//    few bands, which also bounds the length of the tensor-core accumulation chains); partials are reduced in fixed order.
+#include <algorithm>
+#include "conv_wgrad_mma.cuh"
+
+namespace cpp {
+namespace wg {
+
+constexpr int CO = kConvCout;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// power of two that brings max|g| just under 2^15 (1 when the tensor is all zero or not finite)
+__device__ __forceinline__ float scale_for(float mx) {
+  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+  int e;
+  frexpf(mx, &e);                       // mx < 2^e
+  return ldexpf(1.f, 15 - e);
+}
+
+// ------------------------------------------------------------------------------------------ max |d_pooled| per network
+__global__ void __launch_bounds__(256) wgrad_absmax_kernel(const __grid_constant__ Plan P) {
+  __shared__ float sh[8];
+  const int net = blockIdx.y;
+  const float* g = P.g[net];
+  const int64_t n = (int64_t)P.B * P.PH * P.PW * CO;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, sh[i]);
+    atomicMax(reinterpret_cast<int*>(P.gmax + net), __float_as_int(m));      // non-negative floats order like ints
+  }
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+struct Smem { uint32_t planes, dy, raw, total; };
+__host__ __device__ inline Smem smem_layout(const Plan& P) {
+  Smem L;
+  uint32_t off = 0;
+  L.planes = off; off += (uint32_t)P.nvec * P.plane_bytes;
+  L.dy = off; off += (uint32_t)kBandRows * P.Wp * P.NTp * 16;
+  L.raw = off; off += (uint32_t)P.raw_bytes;
+  L.total = off;
+  return L;
+}
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_wgrad_mma_kernel(const __grid_constant__ Plan P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const Smem L = smem_layout(P);
+  uint8_t* planes = smem + L.planes;
+  __half* dys = reinterpret_cast<__half*>(smem + L.dy);
+  const unsigned short* raw = reinterpret_cast<const unsigned short*>(smem + L.raw);
+
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int H = P.H, W = P.W, C = P.C, KS = P.KS, PAD = P.PAD, PH = P.PH, PW = P.PW;
+  const int Wp = P.Wp, pitch = P.pitch, rows_in = P.rows_in, NTp = P.NTp, nets = P.nets;
+  const int rowC = W * C;
+
+  // zero the dY staging once: the columns between nets*20 and NT*8 are never written again
+  for (int i = tid; i < kBandRows * Wp * NTp * 4; i += nthr) reinterpret_cast<uint32_t*>(dys)[i] = 0u;
+
+  float scale[kMaxNets];
+#pragma unroll
+  for (int n = 0; n < kMaxNets; ++n) scale[n] = n < nets ? scale_for(P.gmax[n]) : 1.f;
+
+  // per-lane fragment address bases.  A (x4.trans): matrix id = lane / 8 -> (slab = id & 1, K half = id >> 1), row = lane % 8
+  uint32_t a_base[MT];
+  const uint32_t planes_u32 = smem_u32(planes), dy_u32 = smem_u32(dys);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int T = warp * MT + mt;
+    int s = 2 * T + ((lane >> 3) & 1);
+    if (s >= P.n_slabs) s = 0;                                           // padding rows: any valid address, result ignored
+    a_base[mt] = planes_u32 + (uint32_t)P.slab_off[s] + (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * 16);
+  }
+  // B (x4.trans) for the n-tile pair (2j, 2j+1): id -> (K half = id & 1, tile = 2j + (id >> 1))
+  const uint32_t b_lane = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * NTp * 16 + (lane >> 4) * 16);
+
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
+
+  float* part = P.partials + (size_t)blockIdx.x * P.part_floats;
+  bool first_flush = true;
+  auto flush = [&]() {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float* p = part + ((size_t)((warp * MT + mt) * NT + nt) * 4 + r) * 32 + lane;
+          *p = first_flush ? acc[mt][nt][r] : (*p + acc[mt][nt][r]);
+          acc[mt][nt][r] = 0.f;
+        }
+    first_flush = false;
+  };
+
+  const int band0 = (int)((long long)P.total_bands * blockIdx.x / gridDim.x);
+  const int band1 = (int)((long long)P.total_bands * (blockIdx.x + 1) / gridDim.x);
+  int since_flush = 0;
+  for (int band = band0; band < band1; ++band) {
+    const int b = band / P.bands_per_image, y0 = (band - b * P.bands_per_image) * kBandRows;
+    const int ylo = max(0, y0 - PAD), yhi = min(H, y0 + kBandRows + PAD);
+    __syncthreads();                                                     // previous band's MMAs are done with the staging
+    // ---- raw rows [ylo, yhi) of image b: one contiguous chunk
+    {
+      const __half* src = P.x + ((size_t)b * H + ylo) * rowC;
+      const int n_el = (yhi - ylo) * rowC;
+      if (((rowC * 2) & 15) == 0 && ((((size_t)H * rowC * 2) & 15) == 0)) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(smem + L.raw);
+        for (int i = tid; i < n_el / 8; i += nthr) d4[i] = __ldg(s4 + i);
+      } else {
+        unsigned short* d = reinterpret_cast<unsigned short*>(smem + L.raw);
+        const unsigned short* s2 = reinterpret_cast<const unsigned short*>(src);
+        for (int i = tid; i < n_el; i += nthr) d[i] = s2[i];
+      }
+    }
+    // ---- dY pieces of the band, from the pooled gradient and the arg-max side band
+    {
+      const int hp = kBandRows / 2, wp2 = Wp / 2;
+      const int items = hp * wp2 * nets * CO;
+      for (int it = tid; it < items; it += nthr) {
+        const int o = it % CO, net = (it / CO) % nets, pxl = (it / (CO * nets)) % wp2, pyl = it / (CO * nets * wp2);
+        const int py = (y0 >> 1) + pyl, px = pxl;
+        float gv = 0.f; int a = 4;
+        if (py < PH && px < PW) {
+          const size_t idx = (((size_t)b * PH + py) * PW + px) * CO + o;
+          a = P.amax[net][idx];
+          if (a < 4) gv = P.g[net][idx] * scale[net];
+        }
+        const __half hi = __float2half_rn(gv);
+        const __half lo = __float2half_rn(gv - __half2float(hi));
+        const __half z = __float2half_rn(0.f);
+        const int col = net * 2 * CO + o;
+#pragma unroll
+        for (int pa = 0; pa < 4; ++pa) {
+          __half* d = dys + ((size_t)((2 * pyl + (pa >> 1)) * Wp + 2 * pxl + (pa & 1)) * NTp) * 8 + col;
+          d[0] = (pa == a) ? hi : z;
+          d[CO] = (pa == a) ? lo : z;
+        }
+      }
+    }
+    __syncthreads();                                                     // raw rows are in shared memory
+    // ---- planes: 16-byte channel-group vectors per pixel (zero padding; constant-one channel at index C)
+    {
+      const int per_plane = rows_in * pitch;
+      const unsigned short ONE = 0x3C00;                                 // fp16 1.0
+      for (int it = tid; it < P.nvec * per_plane; it += nthr) {
+        const int v = it / per_plane, rem = it - v * per_plane, lr = rem / pitch, lc = rem - lr * pitch;
+        const int y = y0 - PAD + lr;
+        const bool yok = y >= ylo && y < yhi;
+        const unsigned short* rowp = raw + (size_t)(yok ? (y - ylo) : 0) * rowC;
+        uint32_t h[8];
+        if (v < P.G8) {
+          const int xin = lc - PAD;
+          const bool ok = yok && xin >= 0 && xin < W;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int ch = 8 * v + e;
+            h[e] = !ok ? 0u : (ch < C ? (uint32_t)rowp[xin * C + ch] : (ch == C ? (uint32_t)ONE : 0u));
+          }
+        } else {
+          const int j = v - P.G8;                                         // packed: entry E = 8j + e <-> (kx = E / R, channel 8 G8 + E % R)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int E = 8 * j + e, kx = E / P.R, ch = 8 * P.G8 + E - kx * P.R;
+            const int xin = lc + kx - PAD;
+            const bool ok = yok && kx < KS && xin >= 0 && xin < W && lc < Wp;
+            h[e] = !ok ? 0u : (ch < C ? (uint32_t)rowp[xin * C + ch] : (ch == C ? (uint32_t)ONE : 0u));
+          }
+        }
+        *reinterpret_cast<uint4*>(planes + (size_t)v * P.plane_bytes + (size_t)rem * 16) =
+            make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+      }
+    }
+    __syncthreads();
+    // ---- MMAs: K runs over the band's output pixels, 16 per step
+    if (warp < P.NW) {
+      const int ly_end = min(kBandRows, H - y0);
+      for (int ly = 0; ly < ly_end; ++ly)
+        for (int x0 = 0; x0 < Wp; x0 += 16) {
+          uint32_t bf[(NT + 1) / 2][4];
+          const uint32_t b_addr = dy_u32 + (uint32_t)((ly * Wp + x0) * NTp * 16) + b_lane;
+#pragma unroll
+          for (int j = 0; j < (NT + 1) / 2; ++j) ldsm_x4_t(b_addr + (uint32_t)(j * 32), bf[j]);
+          const uint32_t a_off = (uint32_t)((ly * pitch + x0) * 16);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            uint32_t af[4];
+            ldsm_x4_t(a_base[mt] + a_off, af);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_16816(acc[mt][nt], af, bf[nt >> 1][(nt & 1) * 2], bf[nt >> 1][(nt & 1) * 2 + 1]);
+          }
+        }
+    }
+    if (++since_flush >= P.flush_every) { flush(); since_flush = 0; }
+  }
+  if (since_flush > 0 || first_flush) flush();
+}
+
+// ------------------------------------------------------------------------------------------ reduce + finalize
+// gsum[i] = sum over CTAs of partials[cta][i] in fixed order; block (32, 8)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ Plan P, int nparts) {
+  __shared__ float sh[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
+  const int per = (nparts + 7) / 8, k0 = y * per, k1 = min(nparts, k0 + per);
+  float s = 0.f;
+  if (i < P.part_floats) for (int k = k0; k < k1; ++k) s += P.partials[(size_t)k * P.part_floats + i];
+  sh[y][threadIdx.x] = s;
+  __syncthreads();
+  if (y == 0 && i < P.part_floats) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sh[r][threadIdx.x];
+    P.gsum[i] = t;
+  }
+}
+
+__device__ __forceinline__ int row_of(const Plan& P, int ky, int kx, int ch) {       // -> slab * 8 + m
+  if (ch < 8 * P.G8) return (((ch >> 3) * P.KS + ky) * P.KS + kx) * 8 + (ch & 7);
+  const int E = kx * P.R + (ch - 8 * P.G8);
+  return (P.KS * P.KS * P.G8 + (E >> 3) * P.KS + ky) * 8 + (E & 7);
+}
+__device__ __forceinline__ float g_at(const Plan& P, int row, int n) {
+  const int s = row >> 3, m = row & 7, T = s >> 1, half = s & 1;
+  const int nt = n >> 3, cn = n & 7;
+  const int idx = ((T * P.NT + nt) * 4 + half * 2 + (cn & 1)) * 32 + m * 4 + (cn >> 1);     // T = warp * MT + mt
+  return P.gsum[idx];
+}
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const __grid_constant__ Plan P) {
+  const int KS = P.KS, Cr = P.dup ? P.C / 2 : P.C;
+  const int nw = KS * KS * Cr * CO;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nets * (nw + CO)) return;
+  const int net = i / (nw + CO), j = i - net * (nw + CO);
+  const float inv_scale = 1.f / scale_for(P.gmax[net]);
+  if (j >= nw) {                                                          // bias gradient: constant-one channel, centre tap
+    const int o = j - nw, row = row_of(P, P.PAD, P.PAD, P.C);
+    const float s = g_at(P, row, net * 2 * CO + o) + g_at(P, row, (net * 2 + 1) * CO + o);
+    P.db[net][o] = s * inv_scale;
+    return;
+  }
+  const int o = j % CO, c = (j / CO) % Cr, kx = (j / (CO * Cr)) % KS, ky = j / (CO * Cr * KS);
+  const int n0 = net * 2 * CO + o, n1 = n0 + CO;
+  float gsum = g_at(P, row_of(P, ky, kx, c), n0) + g_at(P, row_of(P, ky, kx, c), n1);
+  if (P.dup) gsum += g_at(P, row_of(P, ky, kx, c + Cr), n0) + g_at(P, row_of(P, ky, kx, c + Cr), n1);
+  float v = gsum * inv_scale;
+  if (P.mean_inv) {
+    const int rs = row_of(P, ky, kx, P.C);
+    const float ssum = (g_at(P, rs, n0) + g_at(P, rs, n1)) * inv_scale;
+    v = P.mean_inv[P.C + c] * (v - P.mean_inv[c] * ssum);
+  }
+  P.dw[net][j] = v;
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
+  CPP_REQUIRE(KS == 5 || KS == 3, "wgrad_mma: kernel size %d", KS);
+  CPP_REQUIRE(nets >= 1 && nets <= kMaxNets, "wgrad_mma: %d sibling networks", nets);
+  CPP_REQUIRE(H >= 2 && W >= 2 && C >= 1, "wgrad_mma: input %dx%dx%d", H, W, C);
+  P->B = B; P->H = H; P->W = W; P->C = C; P->KS = KS; P->PAD = KS / 2; P->PH = H / 2; P->PW = W / 2; P->nets = nets;
+  P->CE = C + 1;
+  P->G8 = P->CE / 8; P->R = P->CE % 8;
+  P->nR = (KS * P->R + 7) / 8;
+  if (P->R > 0 && P->nR >= KS) { P->G8 += 1; P->R = 0; P->nR = 0; }          // packing along kx would not save slabs
+  P->nvec = P->G8 + P->nR;
+  P->Wp = (int)round_up(W, 16);
+  P->pitch = P->Wp + 2 * P->PAD;
+  P->rows_in = kBandRows + 2 * P->PAD;
+  P->plane_bytes = P->rows_in * P->pitch * 16;
+  int ns = 0;
+  for (int g = 0; g < P->G8; ++g)
+    for (int ky = 0; ky < KS; ++ky)
+      for (int kx = 0; kx < KS; ++kx) {
+        CPP_REQUIRE(ns < kMaxSlabs, "wgrad_mma: too many channel groups (C=%d)", C);
+        P->slab[ns] = Slab{0, (int8_t)g, (int8_t)ky, (int8_t)kx};
+        P->slab_off[ns] = g * P->plane_bytes + (ky * P->pitch + kx) * 16;
+        ++ns;
+      }
+  for (int j = 0; j < P->nR; ++j)
+    for (int ky = 0; ky < KS; ++ky) {
+      CPP_REQUIRE(ns < kMaxSlabs, "wgrad_mma: too many channel groups (C=%d)", C);
+      P->slab[ns] = Slab{1, (int8_t)j, (int8_t)ky, 0};
+      P->slab_off[ns] = (P->G8 + j) * P->plane_bytes + (ky * P->pitch) * 16;
+      ++ns;
+    }
+  P->n_slabs = ns;
+  P->m_tiles = (ns + 1) / 2;
+  P->MT = (int)ceil_div(P->m_tiles, kMaxWarps);
+  CPP_REQUIRE(P->MT <= 5, "wgrad_mma: %d gradient rows do not fit the register tile", ns * 8);
+  P->NW = (int)ceil_div(P->m_tiles, P->MT);
+  const int N = nets * 2 * CO;
+  P->NT = (N + 7) / 8;
+  if (P->NT == 4) P->NT = 5;                                                  // instantiated widths: 3, 5, 8
+  if (P->NT == 6 || P->NT == 7) P->NT = 8;
+  P->NTp = P->NT | 1;
+  P->bands_per_image = (int)ceil_div(H, kBandRows);
+  P->total_bands = B * P->bands_per_image;
+  P->raw_bytes = (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
+  P->smem_bytes = (int)smem_layout(*P).total;
+  CPP_REQUIRE(P->smem_bytes <= 220 * 1024, "wgrad_mma: %dx%dx%d does not fit shared memory", H, W, C);
+  const int occ = (P->MT * P->NT <= 16 && P->smem_bytes <= 100 * 1024) ? 2 : 1;
+  P->grid = std::max(1, std::min(P->total_bands, kNumSMs * occ));
+  // bound the tensor-core accumulation chains to ~128 MMA steps between fp32 flushes
+  const int steps_per_band = kBandRows * (P->Wp / 16);
+  P->flush_every = std::max(1, 128 / steps_per_band);
+  P->part_floats = P->NW * P->MT * P->NT * 128;
+  return CPP_OK;
+}
+
+static inline size_t al256(size_t b) { return (size_t)round_up((int64_t)b, 256); }
+
+bool conv_wgrad_mma_supported(int nets, int H, int W, int C, int KS) {
+  Plan P{};
+  return build_plan(nets, 1, H, W, C, KS, &P) == CPP_OK;
+}
+
+int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS) {
+  Plan P{};
+  if (build_plan(nets, 1, H, W, C, KS, &P) != CPP_OK) return -1;
+  return (int64_t)(al256(16) + al256((size_t)2 * kNumSMs * P.part_floats * 4) + al256((size_t)P.part_floats * 4));
+}
+
+template <int MT, int NT>
+static int launch_main(const Plan& P, cudaStream_t s) {
+  auto k = conv_wgrad_mma_kernel<MT, NT>;
+  static bool configured = false;
+  if (!configured) {
+    CPP_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  k<<<P.grid, 32 * P.NW, P.smem_bytes, s>>>(P);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
+template <int MT>
+static int launch_nt(const Plan& P, cudaStream_t s) {
+  if (P.NT == 3) return launch_main<MT, 3>(P, s);
+  if (P.NT == 5) return launch_main<MT, 5>(P, s);
+  if (P.NT == 8) return launch_main<MT, 8>(P, s);
+  set_error("wgrad_mma: N tile count %d not instantiated", P.NT);
+  return CPP_ERR_INVALID;
+}
+
+int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int nets, const float* const* d_pooled,
+                          const uint8_t* const* amax, int B, int H, int W, int C, int KS, float* const* dw, float* const* db,
+                          void* scratch, cudaStream_t s) {
+  if (B <= 0) return CPP_OK;
+  Plan P{};
+  CPP_TRY(build_plan(nets, B, H, W, C, KS, &P));
+  CPP_REQUIRE(!dup || (C % 2 == 0 && mean_inv == nullptr), "wgrad_mma: piece input needs an even channel count and no whitening");
+  CPP_REQUIRE(((uintptr_t)scratch & 255) == 0, "wgrad_mma: unaligned scratch");
+  P.x = reinterpret_cast<const __half*>(x_f16); P.mean_inv = mean_inv; P.dup = dup;
+  for (int n = 0; n < nets; ++n) {
+    CPP_REQUIRE(d_pooled[n] && amax[n] && dw[n] && db[n], "wgrad_mma: null pointer for network %d", n);
+    P.g[n] = d_pooled[n]; P.amax[n] = amax[n]; P.dw[n] = dw[n]; P.db[n] = db[n];
+  }
+  char* sc = reinterpret_cast<char*>(scratch);
+  P.gmax = reinterpret_cast<float*>(sc); sc += al256(16);
+  P.partials = reinterpret_cast<float*>(sc); sc += al256((size_t)2 * kNumSMs * P.part_floats * 4);
+  P.gsum = reinterpret_cast<float*>(sc);
+  CPP_CHECK_CUDA(cudaMemsetAsync(P.gmax, 0, 16, s));
+  {
+    const int64_t n = (int64_t)B * P.PH * P.PW * CO;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, ceil_div(n, 256 * 8)));
+    wgrad_absmax_kernel<<<dim3(blocks, nets), 256, 0, s>>>(P);
+    CPP_CHECK_LAUNCH();
+  }
+  int st;
+  switch (P.MT) {
+    case 1: st = launch_nt<1>(P, s); break;
+    case 2: st = launch_nt<2>(P, s); break;
+    case 3: st = launch_nt<3>(P, s); break;
+    case 4: st = launch_nt<4>(P, s); break;
+    default: st = launch_nt<5>(P, s); break;
+  }
+  CPP_TRY(st);
+  wgrad_reduce_kernel<<<(unsigned)ceil_div(P.part_floats, 32), dim3(32, 8), 0, s>>>(P, P.grid);
+  CPP_CHECK_LAUNCH();
+  const int Cr = dup ? C / 2 : C;
+  const int total = nets * (KS * KS * Cr * CO + CO);
+  wgrad_finalize_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(P);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
+}  // namespace wg
+}  // namespace cpp

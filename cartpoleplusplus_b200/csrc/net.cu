@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include "net.cuh"
 #include "conv_tc.cuh"
+#include "conv_wgrad_mma.cuh"
 
 namespace cpp {
 
@@ -148,9 +149,39 @@ int Net::forward(const float* params, const void* state, int is_f16, const float
   return forward_fc(params, action, B, ws, out, s, first_fc);
 }
 
+static int g_conv1_tc_override = -1;
+void set_conv1_tc_enabled(int on) { g_conv1_tc_override = on; }
 bool conv1_tc_enabled() {
-  static const bool on = [] { const char* e = getenv("CARTPOLEPP_CONV1"); return !(e && std::string(e) == "ffma"); }();
-  return on;
+  static const bool env_on = [] { const char* e = getenv("CARTPOLEPP_CONV1"); return !(e && std::string(e) == "ffma"); }();
+  return g_conv1_tc_override < 0 ? env_on : g_conv1_tc_override != 0;
+}
+
+int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net) {
+  if (!net.pixels) return 0;
+  const int64_t b = wg::conv_wgrad_mma_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
+  return b > 0 ? b : 0;
+}
+
+int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* const* grads, const void* state, int is_f16,
+                      const float* mean_inv, int B, void* scratch, cudaStream_t s) {
+  const Net& n0 = *nets[0];
+  if (!n0.pixels) return CPP_OK;
+  CPP_REQUIRE(n >= 1 && n <= wg::kMaxNets, "conv1 wgrad group of %d networks", n);
+  const ConvLayer& c1 = n0.conv[0];
+  const float* gp[wg::kMaxNets]; const uint8_t* am[wg::kMaxNets]; float* dw[wg::kMaxNets]; float* db[wg::kMaxNets];
+  for (int i = 0; i < n; ++i) {
+    const Net::Layout L = nets[i]->layout(B);
+    gp[i] = reinterpret_cast<const float*>(ws[i] + L.dpool[1]);
+    am[i] = reinterpret_cast<const uint8_t*>(ws[i] + L.amax[0]);
+    dw[i] = grads[i] + nets[i]->off_conv_w[0]; db[i] = grads[i] + nets[i]->off_conv_b[0];
+  }
+  if (is_f16 && scratch != nullptr && conv1_tc_enabled() && wg::conv_wgrad_mma_supported(n, c1.H, c1.W, c1.Cin, c1.KS))
+    return wg::launch_conv_wgrad_mma(state, mean_inv, 0, n, gp, am, B, c1.H, c1.W, c1.Cin, c1.KS, dw, db, scratch, s);
+  for (int i = 0; i < n; ++i) {
+    const Net::Layout L = nets[i]->layout(B);
+    CPP_TRY(launch_conv_wgrad(c1, state, is_f16, mean_inv, gp[i], am[i], B, dw[i], db[i], reinterpret_cast<float*>(ws[i] + L.wgrad), s));
+  }
+  return CPP_OK;
 }
 
 int64_t trunk_group_scratch_bytes(int n, const Net& net) {
@@ -186,7 +217,7 @@ int trunk_forward_group(int n, const Net* const* nets, const float* const* param
 }
 
 int Net::backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
-                  const float* d_out, float* grads, float* d_action, cudaStream_t s) const {
+                  const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1) const {
   CPP_REQUIRE(B >= 1, "batch %d", B);
   CPP_REQUIRE(d_action == nullptr || concat_at >= 0, "d_action requested from a network without action input");
   char* ws = reinterpret_cast<char*>(ws_);
@@ -235,6 +266,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     if (i == 0) { x = state; xf16 = is_f16; mi = mean_inv; }
     else { x = ws + L.pooled[i - 1]; xf16 = 0; mi = nullptr; }
     const uint8_t* amax = reinterpret_cast<const uint8_t*>(ws + L.amax[i]);
+    if (i == 0 && defer_conv1) break;                       // gp == ws + L.dpool[1]: picked up by conv1_wgrad_group
     CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, gp, amax, B, grads + off_conv_w[i], grads + off_conv_b[i],
                               reinterpret_cast<float*>(ws + L.wgrad), s));
     if (i > 0) {

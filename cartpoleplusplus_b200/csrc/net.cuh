@@ -40,9 +40,10 @@ struct Net {
   int forward_trunk(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
                     cudaStream_t s, int first_conv = 0) const;
   int forward_fc(const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s, int first_fc = 0) const;
-  // grads == nullptr: only d_action is produced (stops at the concat layer).
+  // grads == nullptr: only d_action is produced (stops at the concat layer).  defer_conv1: stop in front of conv1's
+  // weight gradient (its input gradient d(pooled1) stays in ws) so that conv1_wgrad_group can do it for all siblings.
   int backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
-               const float* d_out, float* grads, float* d_action, cudaStream_t s) const;
+               const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1 = 0) const;
 };
 
 // Conv trunks of n (<= 3) sibling networks that read the SAME state (actor+critic on state_1, the two targets on
@@ -53,6 +54,12 @@ int64_t trunk_group_scratch_bytes(int n, const Net& net);
 int trunk_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
                         int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s);
 bool conv1_tc_enabled();
+void set_conv1_tc_enabled(int on);     // -1: back to the CARTPOLEPP_CONV1 environment default
+// conv1 weight/bias gradients of n sibling networks whose backward passes were run with defer_conv1 (tensor cores,
+// conv_wgrad_mma.cu, when the state is fp16 and scratch is given; the exact-fp32 CUDA-core kernel otherwise)
+int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net);
+int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* const* grads, const void* state, int is_f16,
+                      const float* mean_inv, int B, void* scratch, cudaStream_t s);
 
 // elementwise.cu
 int64_t moments_scratch_doubles(int C);

@@ -269,15 +269,11 @@ class DDPGEngine(EngineBase):
     if moments is not None:
       _lib.check(self.lib.cpp_ddpg_set_moments(self.handle, _lib.ptr(moments[0]), _lib.ptr(moments[1])))
     Bg = B * self.world_size
-    _lib.check(self.lib.cpp_ddpg_actor_backward(self.handle, _lib.ptr(s1), state_flag(s1), B, Bg, st))
+    _lib.check(self.lib.cpp_ddpg_step_backward(self.handle, _lib.ptr(s1), _lib.ptr(a), _lib.ptr(r), _lib.ptr(m), _lib.ptr(s2),
+                                               state_flag(s1), B, Bg, st))
     if self.dp is not None:
-      self.dp.all_reduce_sum(self.buffers["grads"][:self.off_critic])
-    _lib.check(self.lib.cpp_ddpg_actor_apply(self.handle, st))
-    _lib.check(self.lib.cpp_ddpg_critic_backward(self.handle, _lib.ptr(s1), _lib.ptr(a), _lib.ptr(r), _lib.ptr(m), _lib.ptr(s2),
-                                                 state_flag(s1), B, Bg, 1, st))
-    if self.dp is not None:
-      self.dp.all_reduce_sum(self.buffers["grads"][self.off_critic:])
-    _lib.check(self.lib.cpp_ddpg_critic_apply(self.handle, st))
+      self.dp.all_reduce_sum(self.buffers["grads"])        # the single gradient all-reduce of the step
+    _lib.check(self.lib.cpp_ddpg_step_apply(self.handle, st))
     if moments is not None:
       _lib.check(self.lib.cpp_ddpg_set_moments(self.handle, None, None))
 

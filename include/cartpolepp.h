@@ -42,6 +42,10 @@ const char* cpp_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches) */
 int64_t cpp_launch_count(void);
 
+/* runtime switches (tests and A/B timing): "conv1_tc" = 1 routes conv1 forward / weight gradient of fp16 states through the
+ * tensor-core kernels (default, also CARTPOLEPP_CONV1=tc), 0 through the exact-fp32 CUDA-core kernels, -1 = environment default */
+int cpp_set_option(const char* name, int32_t value);
+
 /* ------------------------------------------------------------------ a1: index sampling (host)
  * replaces np.random.randint(0, size, n) in ReplayMemory.random_indexes, replay_memory.py:123-129.
  * MT19937 with numpy-legacy seeding and masked rejection; bit exact with numpy's RandomState. */
@@ -140,6 +144,17 @@ int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mea
                         const float* const* w, const float* const* bias, int32_t B, int32_t H, int32_t W, int32_t Cin,
                         int32_t KS, float* const* pooled, uint8_t* const* amax, void* scratch, void* stream);
 
+/* weight and bias gradients of the same layer for `nets` (<= 3) sibling networks in ONE pass over x on the tensor cores
+ * (mma.sync m16n8k16, fp16 x fp16 -> fp32): tf.gradients of the conv1 variables in ddpg_cartpole.py:111,213 /
+ * naf_cartpole.py:233.  x fp16 NHWC (exact replay pixels); d_pooled/amax/dw/db: HOST arrays of `nets` device pointers;
+ * every fp32 gradient enters as two fp16 pieces, the whitening is folded out through a constant-one channel.
+ * x_is_pieces = 1: x holds [hi(Cin/2) | lo(Cin/2)] pieces of an fp32 activation (conv2/conv3), mean_inv must be NULL and
+ * dw has Cin/2 input channels.  scratch: cpp_conv_wgrad_mma_scratch_bytes(), 256-byte aligned. */
+int64_t cpp_conv_wgrad_mma_scratch_bytes(int32_t nets, int32_t H, int32_t W, int32_t Cin, int32_t KS);
+int cpp_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int32_t x_is_pieces, int32_t nets, const float* const* d_pooled,
+                       const uint8_t* const* amax, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS,
+                       float* const* dw, float* const* db, void* scratch, void* stream);
+
 /* ------------------------------------------------------------------ a11-a13: clip / optimiser / target copy
  * util.clip_and_debug_gradients util.py:45-58 (tf.clip_by_global_norm): writes
  * scale = clip*min(1/||g||, 1/clip) and ||g|| to out2 f32[2] (dev); scratch f64[cpp_norm_scratch_doubles()].
@@ -193,6 +208,12 @@ int cpp_ddpg_critic_backward(cpp_ddpg* a, const void* s1, const float* action, c
 int cpp_ddpg_critic_apply(cpp_ddpg* a, void* stream);
 int cpp_ddpg_critic_train(cpp_ddpg* a, const void* s1, const float* action, const float* reward,
                           const float* mask, const void* s2, int32_t is_f16, int32_t B, void* stream);
+/* one whole grad-step, actor.train(state_1); critic.train(batch) (ddpg_cartpole.py:332-334), as ONE backward (both flat
+ * gradient parts + loss) and ONE apply: the critic gradient does not depend on the actor update, so the results are those
+ * of the two reference calls while every pass over state_1 is shared.  A data-parallel host all-reduces `grads` in between. */
+int cpp_ddpg_step_backward(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask,
+                           const void* s2, int32_t is_f16, int32_t B, int32_t B_global, void* stream);
+int cpp_ddpg_step_apply(cpp_ddpg* a, void* stream);
 /* out: loss f32[1], td f32[B], q f32[B] (dev) */
 int cpp_ddpg_check_loss(cpp_ddpg* a, const void* s1, const float* action, const float* reward,
                         const float* mask, const void* s2, int32_t is_f16, int32_t B,

@@ -118,3 +118,28 @@ def names_of(net):
 
 def golden_flat(g, net, prefix):
   return np.concatenate([np.asarray(g[prefix + n], dtype=np.float64).reshape(-1) for n in names_of(net)])
+
+
+def set_route(tc):
+  """pin conv1 to the tensor-core kernels (True) or the exact-fp32 CUDA-core kernels (False); None = default"""
+  from cartpoleplusplus_b200 import _lib
+  _lib.check(_lib.lib().cpp_set_option(b"conv1_tc", -1 if tc is None else int(bool(tc))))
+
+
+def assert_flat_grads_close(got_flat, want_flat, cpu32_flat, nets, tc_route, what="grads"):
+  """golden-vector gradient check.  CUDA-core route: the whole vector within 1e-5 (or the fp32 CPU path's own error).
+  Tensor-core route: conv1 outputs carry ~1e-6 relative error instead of ~1e-7, which makes a max-pool / ReLU gate that
+  sits within rounding of a tie ten times more likely to route differently from the fp64 oracle even in the small golden
+  cases; there the per-variable flip-aware criterion of assert_grads_close applies."""
+  got_flat = np.asarray(got_flat, dtype=np.float64).reshape(-1)
+  want_flat = np.asarray(want_flat, dtype=np.float64).reshape(-1); cpu32_flat = np.asarray(cpu32_flat, dtype=np.float64).reshape(-1)
+  if not tc_route:
+    return assert_close(got_flat, want_flat, what=what, cpu32=cpu32_flat)
+  names, w64, w32, off = [], [], [], 0
+  for net in nets:
+    for v in net._variables():
+      n = int(np.prod(v.shape))
+      names.append(v.name); w64.append(want_flat[off:off + n]); w32.append(cpu32_flat[off:off + n]); off += n
+  assert off == want_flat.size, (off, want_flat.size)
+  rep = assert_grads_close(got_flat, w64, w32, names, what=what)
+  return max(v[0] for v in rep.values())
