@@ -67,49 +67,55 @@ __global__ void __launch_bounds__(256) wgrad_absmax_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
-struct Smem { uint32_t planes, dy, raw, total; };
+// Shared memory: two staging buffers (x planes + dY pieces) and one raw-row buffer.  While the MMAs of band i run out of
+// buffer i&1, the raw rows of band i+1 arrive through cp.async and its pooled gradients / arg-max bytes sit in registers;
+// afterwards they are re-laid into buffer (i+1)&1.  Two CTAs per SM overlap one CTA's re-layout with the other's MMAs.
+struct Smem { uint32_t planes, dy, raw, buf_stride, total; };
 __host__ __device__ inline Smem smem_layout(const Plan& P) {
   Smem L;
-  uint32_t off = 0;
-  L.planes = off; off += (uint32_t)P.nvec * P.plane_bytes;
-  L.dy = off; off += (uint32_t)kBandRows * P.Wp * P.NTp * 16;
-  L.raw = off; off += (uint32_t)P.raw_bytes;
-  L.total = off;
+  const uint32_t planes_b = (uint32_t)P.nvec * P.plane_bytes, dy_b = (uint32_t)P.band_rows * P.Wp * P.NTp * 16;
+  L.planes = 0; L.dy = planes_b; L.buf_stride = planes_b + dy_b;
+  L.raw = 2 * L.buf_stride;
+  L.total = L.raw + (uint32_t)P.raw_bytes + 16;          // + 16: the B-fragment load of an odd tile count reads one vector past the end
   return L;
 }
+
+constexpr int kDyItems = 2;        // (2x2 window, network) items a thread may own per band
 
 template <int MT, int NT>
 __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_wgrad_mma_kernel(const __grid_constant__ Plan P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const Smem L = smem_layout(P);
-  uint8_t* planes = smem + L.planes;
-  __half* dys = reinterpret_cast<__half*>(smem + L.dy);
   const unsigned short* raw = reinterpret_cast<const unsigned short*>(smem + L.raw);
 
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int H = P.H, W = P.W, C = P.C, KS = P.KS, PAD = P.PAD, PH = P.PH, PW = P.PW;
-  const int Wp = P.Wp, pitch = P.pitch, rows_in = P.rows_in, NTp = P.NTp, nets = P.nets;
+  const int Wp = P.Wp, pitch = P.pitch, rows_in = P.rows_in, NTp = P.NTp, nets = P.nets, BR = P.band_rows;
   const int rowC = W * C;
+  const int raw_mode = (((rowC * 2) & 15) == 0 && ((((size_t)H * rowC * 2) & 15) == 0)) ? 16
+                     : ((((rowC * 2) & 3) == 0 && ((((size_t)H * rowC * 2) & 3) == 0)) ? 4 : 0);
 
-  // zero the dY staging once: the columns between nets*20 and NT*8 are never written again
-  for (int i = tid; i < kBandRows * Wp * NTp * 4; i += nthr) reinterpret_cast<uint32_t*>(dys)[i] = 0u;
+  // zero both dY buffers once: the columns between nets*20 and NT*8 are never written again
+  for (int b2 = 0; b2 < 2; ++b2) {
+    uint32_t* d = reinterpret_cast<uint32_t*>(smem + b2 * L.buf_stride + L.dy);
+    for (int i = tid; i < BR * Wp * NTp * 4; i += nthr) d[i] = 0u;
+  }
 
-  float scale[kMaxNets];
-#pragma unroll
-  for (int n = 0; n < kMaxNets; ++n) scale[n] = n < nets ? scale_for(P.gmax[n]) : 1.f;
+  __shared__ float s_scale[kMaxNets];
+  if (tid < kMaxNets) s_scale[tid] = tid < nets ? scale_for(P.gmax[tid]) : 1.f;
 
   // per-lane fragment address bases.  A (x4.trans): matrix id = lane / 8 -> (slab = id & 1, K half = id >> 1), row = lane % 8
   uint32_t a_base[MT];
-  const uint32_t planes_u32 = smem_u32(planes), dy_u32 = smem_u32(dys);
+  const uint32_t smem_u = smem_u32(smem);
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int T = warp * MT + mt;
     int s = 2 * T + ((lane >> 3) & 1);
     if (s >= P.n_slabs) s = 0;                                           // padding rows: any valid address, result ignored
-    a_base[mt] = planes_u32 + (uint32_t)P.slab_off[s] + (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * 16);
+    a_base[mt] = smem_u + L.planes + (uint32_t)P.slab_off[s] + (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * 16);
   }
   // B (x4.trans) for the n-tile pair (2j, 2j+1): id -> (K half = id & 1, tile = 2j + (id >> 1))
-  const uint32_t b_lane = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * NTp * 16 + (lane >> 4) * 16);
+  const uint32_t b_lane = smem_u + L.dy + (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * NTp * 16 + (lane >> 4) * 16);
 
   float acc[MT][NT][4];
 #pragma unroll
@@ -135,96 +141,153 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     first_flush = false;
   };
 
-  const int band0 = (int)((long long)P.total_bands * blockIdx.x / gridDim.x);
-  const int band1 = (int)((long long)P.total_bands * (blockIdx.x + 1) / gridDim.x);
-  int since_flush = 0;
-  for (int band = band0; band < band1; ++band) {
-    const int b = band / P.bands_per_image, y0 = (band - b * P.bands_per_image) * kBandRows;
-    const int ylo = max(0, y0 - PAD), yhi = min(H, y0 + kBandRows + PAD);
-    __syncthreads();                                                     // previous band's MMAs are done with the staging
-    // ---- raw rows [ylo, yhi) of image b: one contiguous chunk
-    {
-      const __half* src = P.x + ((size_t)b * H + ylo) * rowC;
-      const int n_el = (yhi - ylo) * rowC;
-      if (((rowC * 2) & 15) == 0 && ((((size_t)H * rowC * 2) & 15) == 0)) {
-        const uint4* s4 = reinterpret_cast<const uint4*>(src);
-        uint4* d4 = reinterpret_cast<uint4*>(smem + L.raw);
-        for (int i = tid; i < n_el / 8; i += nthr) d4[i] = __ldg(s4 + i);
-      } else {
-        unsigned short* d = reinterpret_cast<unsigned short*>(smem + L.raw);
-        const unsigned short* s2 = reinterpret_cast<const unsigned short*>(src);
-        for (int i = tid; i < n_el; i += nthr) d[i] = s2[i];
+  // ---- staging pieces
+  const int hp = BR / 2, wp2 = Wp / 2, dy_items = hp * wp2 * nets;
+  float2 gq[kDyItems][5];
+  unsigned short aq[kDyItems][5];
+  auto band_rows_of = [&](int band, int& b, int& y0, int& ylo, int& yhi) {
+    b = band / P.bands_per_image; y0 = (band - b * P.bands_per_image) * BR;
+    ylo = max(0, y0 - PAD); yhi = min(H, y0 + BR + PAD);
+  };
+  // (1) global -> shared / registers, asynchronous
+  auto issue_loads = [&](int band) {
+    int b, y0, ylo, yhi;
+    band_rows_of(band, b, y0, ylo, yhi);
+    const __half* src = P.x + ((size_t)b * H + ylo) * rowC;
+    const int n_bytes = (yhi - ylo) * rowC * 2;
+    const uint32_t dst = smem_u + L.raw;
+    if (raw_mode == 16) {
+      for (int i = tid * 16; i < n_bytes; i += nthr * 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i), "l"(reinterpret_cast<const char*>(src) + i) : "memory");
+    } else if (raw_mode == 4) {
+      for (int i = tid * 4; i < n_bytes; i += nthr * 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i), "l"(reinterpret_cast<const char*>(src) + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < kDyItems; ++k) {
+      const int it = tid + k * nthr;
+#pragma unroll
+      for (int v = 0; v < 5; ++v) { gq[k][v] = make_float2(0.f, 0.f); aq[k][v] = 0x0404; }
+      if (it < dy_items) {
+        const int net = it % nets, pxl = (it / nets) % wp2, pyl = it / (nets * wp2);
+        const int py = (y0 >> 1) + pyl;
+        if (py < PH && pxl < PW) {
+          const size_t idx = (((size_t)b * PH + py) * PW + pxl) * CO;
+          const float2* gp = reinterpret_cast<const float2*>(P.g[net] + idx);
+          const unsigned short* ap = reinterpret_cast<const unsigned short*>(P.amax[net] + idx);
+#pragma unroll
+          for (int v = 0; v < 5; ++v) { gq[k][v] = __ldg(gp + v); aq[k][v] = __ldg(ap + v); }
+        }
       }
     }
-    // ---- dY pieces of the band, from the pooled gradient and the arg-max side band
-    {
-      const int hp = kBandRows / 2, wp2 = Wp / 2;
-      const int items = hp * wp2 * nets * CO;
-      for (int it = tid; it < items; it += nthr) {
-        const int o = it % CO, net = (it / CO) % nets, pxl = (it / (CO * nets)) % wp2, pyl = it / (CO * nets * wp2);
-        const int py = (y0 >> 1) + pyl, px = pxl;
-        float gv = 0.f; int a = 4;
-        if (py < PH && px < PW) {
-          const size_t idx = (((size_t)b * PH + py) * PW + px) * CO + o;
-          a = P.amax[net][idx];
-          if (a < 4) gv = P.g[net][idx] * scale[net];
+  };
+  // (2) registers -> dY pieces of buffer `buf`; raw rows that cp.async cannot move (2-byte granular) are copied here
+  auto stage_dy = [&](int band, int buf) {
+    int b, y0, ylo, yhi;
+    band_rows_of(band, b, y0, ylo, yhi);
+    if (raw_mode == 0) {
+      unsigned short* d = reinterpret_cast<unsigned short*>(smem + L.raw);
+      const unsigned short* s2 = reinterpret_cast<const unsigned short*>(P.x + ((size_t)b * H + ylo) * rowC);
+      for (int i = tid; i < (yhi - ylo) * rowC; i += nthr) d[i] = s2[i];
+    }
+    __half* dys = reinterpret_cast<__half*>(smem + buf * L.buf_stride + L.dy);
+#pragma unroll
+    for (int k = 0; k < kDyItems; ++k) {
+      const int it = tid + k * nthr;
+      if (it < dy_items) {
+        const int net = it % nets, pxl = (it / nets) % wp2, pyl = it / (nets * wp2);
+        const float sc = s_scale[net];
+        uint32_t hi2[5], lo2[5];                       // 10 filters as 5 half2 words
+        uint32_t am[10];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          const float g0 = gq[k][v].x * sc, g1 = gq[k][v].y * sc;
+          const __half h0 = __float2half_rn(g0), h1 = __float2half_rn(g1);
+          const __half l0 = __float2half_rn(g0 - __half2float(h0)), l1 = __float2half_rn(g1 - __half2float(h1));
+          hi2[v] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          lo2[v] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          am[2 * v] = aq[k][v] & 0xff; am[2 * v + 1] = aq[k][v] >> 8;
         }
-        const __half hi = __float2half_rn(gv);
-        const __half lo = __float2half_rn(gv - __half2float(hi));
-        const __half z = __float2half_rn(0.f);
-        const int col = net * 2 * CO + o;
 #pragma unroll
         for (int pa = 0; pa < 4; ++pa) {
-          __half* d = dys + ((size_t)((2 * pyl + (pa >> 1)) * Wp + 2 * pxl + (pa & 1)) * NTp) * 8 + col;
-          d[0] = (pa == a) ? hi : z;
-          d[CO] = (pa == a) ? lo : z;
+          uint32_t w[10];                              // [hi(10) | lo(10)] halves of this pixel and network
+#pragma unroll
+          for (int v = 0; v < 5; ++v) {
+            const uint32_t m = (am[2 * v] == (uint32_t)pa ? 0x0000ffffu : 0u) | (am[2 * v + 1] == (uint32_t)pa ? 0xffff0000u : 0u);
+            w[v] = hi2[v] & m; w[5 + v] = lo2[v] & m;
+          }
+          uint2* d = reinterpret_cast<uint2*>(dys + ((size_t)((2 * pyl + (pa >> 1)) * Wp + 2 * pxl + (pa & 1)) * NTp) * 8 + net * 2 * CO);
+#pragma unroll
+          for (int v = 0; v < 5; ++v) d[v] = make_uint2(w[2 * v], w[2 * v + 1]);
         }
       }
     }
-    __syncthreads();                                                     // raw rows are in shared memory
-    // ---- planes: 16-byte channel-group vectors per pixel (zero padding; constant-one channel at index C)
-    {
-      const int per_plane = rows_in * pitch;
-      const unsigned short ONE = 0x3C00;                                 // fp16 1.0
-      for (int it = tid; it < P.nvec * per_plane; it += nthr) {
-        const int v = it / per_plane, rem = it - v * per_plane, lr = rem / pitch, lc = rem - lr * pitch;
-        const int y = y0 - PAD + lr;
-        const bool yok = y >= ylo && y < yhi;
-        const unsigned short* rowp = raw + (size_t)(yok ? (y - ylo) : 0) * rowC;
-        uint32_t h[8];
-        if (v < P.G8) {
-          const int xin = lc - PAD;
-          const bool ok = yok && xin >= 0 && xin < W;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  };
+  // (3) raw rows -> planes of buffer `buf`: 16-byte channel-group vectors per pixel (zero padding; constant-one channel at C)
+  auto stage_planes = [&](int band, int buf) {
+    int b, y0, ylo, yhi;
+    band_rows_of(band, b, y0, ylo, yhi);
+    uint8_t* planes = smem + buf * L.buf_stride + L.planes;
+    const int per_plane = rows_in * pitch;
+    const uint32_t ONE = 0x3C00u;                                          // fp16 1.0
+    for (int it = tid; it < P.nvec * per_plane; it += nthr) {
+      const int v = it / per_plane, rem = it - v * per_plane, lr = rem / pitch, lc = rem - lr * pitch;
+      const int y = y0 - PAD + lr;
+      const bool yok = y >= ylo && y < yhi;
+      const unsigned short* rowp = raw + (size_t)(yok ? (y - ylo) : 0) * rowC;
+      uint32_t h[8];
+      if (v < P.G8) {
+        const int xin = lc - PAD;
+        const bool ok = yok && xin >= 0 && xin < W;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int ch = 8 * v + e;
-            h[e] = !ok ? 0u : (ch < C ? (uint32_t)rowp[xin * C + ch] : (ch == C ? (uint32_t)ONE : 0u));
-          }
-        } else {
-          const int j = v - P.G8;                                         // packed: entry E = 8j + e <-> (kx = E / R, channel 8 G8 + E % R)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int E = 8 * j + e, kx = E / P.R, ch = 8 * P.G8 + E - kx * P.R;
-            const int xin = lc + kx - PAD;
-            const bool ok = yok && kx < KS && xin >= 0 && xin < W && lc < Wp;
-            h[e] = !ok ? 0u : (ch < C ? (uint32_t)rowp[xin * C + ch] : (ch == C ? (uint32_t)ONE : 0u));
-          }
+        for (int e = 0; e < 8; ++e) {
+          const int ch = 8 * v + e;
+          h[e] = !ok ? 0u : (ch < C ? (uint32_t)rowp[xin * C + ch] : (ch == C ? ONE : 0u));
         }
-        *reinterpret_cast<uint4*>(planes + (size_t)v * P.plane_bytes + (size_t)rem * 16) =
-            make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+      } else {
+        const int j = v - P.G8;                                            // packed: entry E = 8j + e <-> (kx = E / R, channel 8 G8 + E % R)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int E = 8 * j + e, kx = E / P.R, ch = 8 * P.G8 + E - kx * P.R;
+          const int xin = lc + kx - PAD;
+          const bool ok = yok && kx < KS && xin >= 0 && xin < W && lc < Wp;
+          h[e] = !ok ? 0u : (ch < C ? (uint32_t)rowp[xin * C + ch] : (ch == C ? ONE : 0u));
+        }
       }
+      *reinterpret_cast<uint4*>(planes + (size_t)v * P.plane_bytes + (size_t)rem * 16) =
+          make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
     }
+  };
+
+  const int band0 = (int)((long long)P.total_bands * blockIdx.x / gridDim.x);
+  const int band1 = (int)((long long)P.total_bands * (blockIdx.x + 1) / gridDim.x);
+  __syncthreads();                                                         // s_scale, zeroed dY buffers
+  if (band0 < band1) {
+    issue_loads(band0);
+    stage_dy(band0, 0);
     __syncthreads();
+    stage_planes(band0, 0);
+  }
+  __syncthreads();
+  int since_flush = 0;
+  for (int band = band0; band < band1; ++band) {
+    const int buf = (band - band0) & 1;
+    const bool has_next = band + 1 < band1;
+    if (has_next) issue_loads(band + 1);
     // ---- MMAs: K runs over the band's output pixels, 16 per step
-    if (warp < P.NW) {
-      const int ly_end = min(kBandRows, H - y0);
+    {
+      const int y0 = (band % P.bands_per_image) * BR;
+      const int ly_end = min(BR, H - y0);
+      const uint32_t boff = (uint32_t)buf * L.buf_stride;
       for (int ly = 0; ly < ly_end; ++ly)
         for (int x0 = 0; x0 < Wp; x0 += 16) {
           uint32_t bf[(NT + 1) / 2][4];
-          const uint32_t b_addr = dy_u32 + (uint32_t)((ly * Wp + x0) * NTp * 16) + b_lane;
+          const uint32_t b_addr = b_lane + boff + (uint32_t)((ly * Wp + x0) * NTp * 16);
 #pragma unroll
           for (int j = 0; j < (NT + 1) / 2; ++j) ldsm_x4_t(b_addr + (uint32_t)(j * 32), bf[j]);
-          const uint32_t a_off = (uint32_t)((ly * pitch + x0) * 16);
+          const uint32_t a_off = boff + (uint32_t)((ly * pitch + x0) * 16);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             uint32_t af[4];
@@ -234,6 +297,12 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
           }
         }
     }
+    if (has_next) {
+      stage_dy(band + 1, buf ^ 1);                                         // buffer buf^1 was last read one iteration ago
+      __syncthreads();                                                     // raw rows of band+1 are complete in shared memory
+      stage_planes(band + 1, buf ^ 1);
+    }
+    __syncthreads();                                                       // band+1 staged; every warp is done reading `buf` and raw
     if (++since_flush >= P.flush_every) { flush(); since_flush = 0; }
   }
   if (since_flush > 0 || first_flush) flush();
@@ -307,7 +376,8 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
   P->nvec = P->G8 + P->nR;
   P->Wp = (int)round_up(W, 16);
   P->pitch = P->Wp + 2 * P->PAD;
-  P->rows_in = kBandRows + 2 * P->PAD;
+  P->band_rows = kBandRows;
+  P->rows_in = P->band_rows + 2 * P->PAD;
   P->plane_bytes = P->rows_in * P->pitch * 16;
   int ns = 0;
   for (int g = 0; g < P->G8; ++g)
@@ -335,15 +405,28 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
   if (P->NT == 4) P->NT = 5;                                                  // instantiated widths: 3, 5, 8
   if (P->NT == 6 || P->NT == 7) P->NT = 8;
   P->NTp = P->NT | 1;
-  P->bands_per_image = (int)ceil_div(H, kBandRows);
-  P->total_bands = B * P->bands_per_image;
   P->raw_bytes = (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
   P->smem_bytes = (int)smem_layout(*P).total;
+  if (P->smem_bytes > 220 * 1024) {        // wide images: two-row bands keep both staging buffers inside one SM's shared memory
+    P->band_rows = 2;
+    P->rows_in = P->band_rows + 2 * P->PAD;
+    P->plane_bytes = P->rows_in * P->pitch * 16;
+    for (int i = 0; i < ns; ++i) {
+      const Slab& sl = P->slab[i];
+      P->slab_off[i] = sl.kind == 0 ? sl.set * P->plane_bytes + (sl.ky * P->pitch + sl.kx) * 16
+                                    : (P->G8 + sl.set) * P->plane_bytes + (sl.ky * P->pitch) * 16;
+    }
+    P->raw_bytes = (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
+    P->smem_bytes = (int)smem_layout(*P).total;
+  }
   CPP_REQUIRE(P->smem_bytes <= 220 * 1024, "wgrad_mma: %dx%dx%d does not fit shared memory", H, W, C);
-  const int occ = (P->MT * P->NT <= 16 && P->smem_bytes <= 100 * 1024) ? 2 : 1;
+  P->bands_per_image = (int)ceil_div(H, P->band_rows);
+  P->total_bands = B * P->bands_per_image;
+  CPP_REQUIRE((P->band_rows / 2) * (P->Wp / 2) * nets <= kDyItems * 32 * P->NW, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
+  const int occ = (P->MT * P->NT <= 16 && P->smem_bytes <= 110 * 1024) ? 2 : 1;
   P->grid = std::max(1, std::min(P->total_bands, kNumSMs * occ));
   // bound the tensor-core accumulation chains to ~128 MMA steps between fp32 flushes
-  const int steps_per_band = kBandRows * (P->Wp / 16);
+  const int steps_per_band = P->band_rows * (P->Wp / 16);
   P->flush_every = std::max(1, 128 / steps_per_band);
   P->part_floats = P->NW * P->MT * P->NT * 128;
   return CPP_OK;

@@ -10,7 +10,7 @@ namespace wg {
 constexpr int kMaxNets = 3;
 constexpr int kMaxSlabs = 96;      // K8 slabs of (tap, channel group) rows of the gradient matrix
 constexpr int kMaxWarps = 8;
-constexpr int kBandRows = 4;       // conv-output rows staged per work unit
+constexpr int kBandRows = 4;       // conv-output rows staged per work unit (2 for very wide images)
 
 struct Slab {
   int8_t kind;    // 0: 8 channels of one tap (ky, kx, group); 1: remainder channels packed along kx (ky, slab j); 2: unused
@@ -34,7 +34,7 @@ struct Plan {
   // ---- geometry
   int CE;                          // channels incl. the constant-one channel appended at index C
   int G8, R, nR, nvec;             // full 8-channel groups, remainder channels, packed slabs per ky, smem vectors per pixel
-  int Wp, pitch, rows_in;          // W rounded up to 16; plane row pitch (pixels); input rows per band
+  int Wp, pitch, rows_in, band_rows;   // W rounded up to 16; plane row pitch (pixels); input / output rows per band
   int n_slabs, m_tiles, MT, NW;    // M tiles of 16 rows (2 slabs); M tiles per warp; warps
   int NT, NTp;                     // N tiles of 8 columns (nets * 2 pieces * 10 filters); vectors per pixel of the dY staging (odd)
   int bands_per_image, total_bands, grid, flush_every;
