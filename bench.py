@@ -250,7 +250,7 @@ def run_native(args):
     wp, bp, pp, ap = _lib.ptr_array(ws_), _lib.ptr_array(bs_), _lib.ptr_array(pooled), _lib.ptr_array(amax)
     def conv1():
       _lib.check(lib.cpp_conv_forward_tc(_lib.ptr(x), None, _lib.ptr(m1), 2, wp, bp, BATCH, 64, 64, 9, 5, pp, ap, _lib.ptr(scr),
-                                         _lib.stream_ptr()))
+                                         _lib.stream_ptr(), 0, None))
     for _ in range(3):
       conv1()
     ts = []

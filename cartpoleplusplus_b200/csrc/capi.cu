@@ -161,10 +161,12 @@ int64_t cpp_conv_tc_scratch_bytes(int32_t nets, int32_t H, int32_t W, int32_t Ci
 }
 int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int32_t nets, const float* const* w,
                         const float* const* bias, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS,
-                        float* const* pooled, uint8_t* const* amax, void* scratch, void* stream) {
+                        float* const* pooled, uint8_t* const* amax, void* scratch, void* stream, int32_t x_is_pieces,
+                        void* const* pooled_hl) {
   API_BEGIN
   NEED(x_f16); NEED(w); NEED(bias); NEED(pooled); NEED(amax); NEED(scratch);
-  return tc::launch_conv_fwd_tc(x_f16, rows, mean_inv, nets, w, bias, B, H, W, Cin, KS, pooled, amax, scratch, ST(stream));
+  return tc::launch_conv_fwd_tc(x_f16, rows, mean_inv, nets, w, bias, B, H, W, Cin, KS, pooled, amax, scratch, ST(stream),
+                                x_is_pieces, reinterpret_cast<__half* const*>(pooled_hl));
   API_END
 }
 

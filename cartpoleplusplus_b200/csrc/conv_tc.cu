@@ -111,11 +111,11 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
   __shared__ float red[256];
   __shared__ float s_scale;
   const int tid = threadIdx.x;
-  const int KS = P.KS, C = P.C, nw = KS * KS * C * CO;
+  const int KS = P.KS, C = P.C, Cw = P.Cw, nw = KS * KS * Cw * CO;
   float mx = 0.f;
   for (int n = 0; n < P.nets; ++n)
     for (int i = tid; i < nw; i += blockDim.x) {
-      const int ch = (i / CO) % C;
+      const int ch = (i / CO) % Cw;
       const float inv = A.mean_inv ? A.mean_inv[C + ch] : 1.f;
       mx = fmaxf(mx, fabsf(A.w[n][i] * inv));
     }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
     if (valid) {
       const int net = n / (kPieces * CO), piece = (n / CO) % kPieces, o = n % CO;
       const float inv = A.mean_inv ? A.mean_inv[C + ch] : 1.f;
-      v = A.w[net][((ky * KS + kx) * C + ch) * CO + o] * inv * scale;
+      v = A.w[net][((ky * KS + kx) * Cw + (ch < Cw ? ch : ch - Cw)) * CO + o] * inv * scale;
       const __half hi = __float2half_rn(v);
       out = (piece == 0) ? hi : __float2half_rn(v - __half2float(hi));
     }
@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
       const int kx0 = xc < P.PAD ? P.PAD - xc : 0, kx1 = xc > P.PAD ? KS - 1 - (xc - P.PAD) : KS - 1;
       for (int ky = ky0; ky <= ky1; ++ky)
         for (int kx = kx0; kx <= kx1; ++kx)
-          for (int ch = 0; ch < C; ++ch)
-            acc -= (double)A.mean_inv[ch] * (double)A.mean_inv[C + ch] * (double)A.w[net][((ky * KS + kx) * C + ch) * CO + o];
+          for (int ch = 0; ch < Cw; ++ch)       // whitening is never combined with piece inputs: Cw == C here
+            acc -= (double)A.mean_inv[ch] * (double)A.mean_inv[C + ch] * (double)A.w[net][((ky * KS + kx) * Cw + ch) * CO + o];
     }
     A.corr[idx] = (float)acc;
   }
@@ -330,6 +330,16 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
               *reinterpret_cast<float2*>(op + o) = make_float2(fmaxf(best[o], 0.f), fmaxf(best[o + 1], 0.f));
               const uint16_t pk = (uint16_t)((best[o] > 0.f ? arg[o] : 4) | ((best[o + 1] > 0.f ? arg[o + 1] : 4) << 8));
               *reinterpret_cast<uint16_t*>(ap + o) = pk;
+            }
+            if (P.pooled_hl[net] != nullptr) {                     // the same values as fp16 pieces for the next layer's MMAs
+              __half2* hp = reinterpret_cast<__half2*>(P.pooled_hl[net] + 2 * base);
+#pragma unroll
+              for (int o = 0; o < CO; o += 2) {
+                const float v0 = fmaxf(best[o], 0.f), v1 = fmaxf(best[o + 1], 0.f);
+                const __half h0 = __float2half_rn(fminf(v0, 65504.f)), h1 = __float2half_rn(fminf(v1, 65504.f));
+                hp[o >> 1] = __halves2half2(h0, h1);
+                hp[(CO + o) >> 1] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+              }
             }
           }
         }
@@ -618,10 +628,13 @@ static int launch_main(const FwdPlan& P, int grid, cudaStream_t s) {
 
 int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int nets,
                        const float* const* w, const float* const* bias, int B, int H, int W, int C, int KS,
-                       float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s) {
+                       float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s,
+                       int x_is_pieces, __half* const* pooled_hl) {
   if (B <= 0) return CPP_OK;
   FwdPlan P{};
   CPP_TRY(build_plan(nets, B, H, W, C, KS, &P));
+  CPP_REQUIRE(!x_is_pieces || (C % 2 == 0 && mean_inv == nullptr), "conv_tc: piece input needs an even channel count and no whitening");
+  P.Cw = x_is_pieces ? C / 2 : C;
   CPP_REQUIRE(((uintptr_t)x_f16 & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
   P.x = reinterpret_cast<const __half*>(x_f16); P.rows = rows;
   P.bpack = reinterpret_cast<const __half*>(scratch);
@@ -630,6 +643,7 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   for (int n = 0; n < nets; ++n) {
     CPP_REQUIRE(w[n] && bias[n] && pooled[n] && amax[n], "conv_tc: null pointer for network %d", n);
     A.w[n] = w[n]; A.bias[n] = bias[n]; P.pooled[n] = pooled[n]; P.amax[n] = amax[n];
+    P.pooled_hl[n] = pooled_hl ? pooled_hl[n] : nullptr;
   }
   A.mean_inv = mean_inv;
   A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);

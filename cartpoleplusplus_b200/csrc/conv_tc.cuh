@@ -25,7 +25,9 @@ struct FwdPlan {
   const float* corr;        // [(2*PAD+1)^2][nets][10] bias - border-aware mean term, then [1] = 2^-S
   float* pooled[kMaxNets];
   uint8_t* amax[kMaxNets];
+  __half* pooled_hl[kMaxNets];   // optional: the pooled output again as fp16 pieces [B][PH][PW][hi(10) | lo(10)] for the next layer
   int B, H, W, C, PH, PW, Pq, KS, PAD;
+  int Cw;                   // weight input channels: C, or C/2 when x holds [hi | lo] pieces of an fp32 activation
   int nets, N;              // MMA N = round_up(nets * kPieces * 10, 16)
   // ---- shared-memory geometry
   int G8, R, nR;            // full 8-channel groups, remainder channels, packed slabs per ky
@@ -48,10 +50,13 @@ struct PrepArgs {
 
 int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS);
 bool conv_tc_supported(int nets, int H, int W, int C, int KS);
-// y_n = maxpool2x2(relu(conv_same(whiten(x), w_n) + b_n)) for n < nets sibling networks in ONE pass over x
+// y_n = maxpool2x2(relu(conv_same(whiten(x), w_n) + b_n)) for n < nets sibling networks in ONE pass over x.
+// x_is_pieces: x holds [hi(C/2) | lo(C/2)] fp16 pieces of an fp32 activation (conv2/conv3), w has C/2 input channels,
+// mean_inv must be NULL.  pooled_hl (optional, may be NULL or hold NULLs): fp16 piece copy of the output.
 int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int nets,
                        const float* const* w, const float* const* bias, int B, int H, int W, int C, int KS,
-                       float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s);
+                       float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s,
+                       int x_is_pieces = 0, __half* const* pooled_hl = nullptr);
 
 }  // namespace tc
 }  // namespace cpp

@@ -40,6 +40,23 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// up to 8 halfs (zero padded) from a 2-byte aligned shared-memory address
+__device__ __forceinline__ uint4 load8h(const unsigned short* p, int nch) {
+  if (nch >= 8) {
+    if ((reinterpret_cast<uintptr_t>(p) & 2) == 0) {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+      return make_uint4(q[0], q[1], q[2], q[3]);
+    }
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p + 1);
+    const uint32_t a = p[0], b = q[0], c = q[1], d = q[2], e = p[7];
+    return make_uint4(a | (b << 16), (b >> 16) | (c << 16), (c >> 16) | (d << 16), (d >> 16) | (e << 16));
+  }
+  uint32_t h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) h[e] = e < nch ? (uint32_t)p[e] : 0u;
+  return make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+}
+
 // power of two that brings max|g| just under 2^15 (1 when the tensor is all zero or not finite)
 __device__ __forceinline__ float scale_for(float mx) {
   if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
@@ -102,7 +119,12 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   }
 
   __shared__ float s_scale[kMaxNets];
+  __shared__ int s_pk[8][8];                    // packed planes: entry (j, e) -> kx | channel << 8 (kx = 255: unused entry)
   if (tid < kMaxNets) s_scale[tid] = tid < nets ? scale_for(P.gmax[tid]) : 1.f;
+  if (tid < 64) {
+    const int E = tid, kx = P.R > 0 ? E / P.R : 255;
+    s_pk[tid >> 3][tid & 7] = (P.R > 0 && kx < KS) ? (kx | ((8 * P.G8 + E - kx * P.R) << 8)) : 255;
+  }
 
   // per-lane fragment address bases.  A (x4.trans): matrix id = lane / 8 -> (slab = id & 1, K half = id >> 1), row = lane % 8
   uint32_t a_base[MT];
@@ -141,8 +163,9 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     first_flush = false;
   };
 
-  // ---- staging pieces
-  const int hp = BR / 2, wp2 = Wp / 2, dy_items = hp * wp2 * nets;
+  // ---- staging pieces.  dY item = (output row r of the band, window column, network): the two pixels (x even / odd) of one
+  // window row; its 10 pooled gradients and arg-max bytes are prefetched into registers one band ahead.
+  const int wp2 = Wp / 2, dy_items = BR * wp2 * nets;
   float2 gq[kDyItems][5];
   unsigned short aq[kDyItems][5];
   auto band_rows_of = [&](int band, int& b, int& y0, int& ylo, int& yhi) {
@@ -170,8 +193,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
 #pragma unroll
       for (int v = 0; v < 5; ++v) { gq[k][v] = make_float2(0.f, 0.f); aq[k][v] = 0x0404; }
       if (it < dy_items) {
-        const int net = it % nets, pxl = (it / nets) % wp2, pyl = it / (nets * wp2);
-        const int py = (y0 >> 1) + pyl;
+        const int net = it % nets, t2 = it / nets, pxl = t2 % wp2, r = t2 / wp2;
+        const int py = (y0 + r) >> 1;
         if (py < PH && pxl < PW) {
           const size_t idx = (((size_t)b * PH + py) * PW + pxl) * CO;
           const float2* gp = reinterpret_cast<const float2*>(P.g[net] + idx);
@@ -196,68 +219,77 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     for (int k = 0; k < kDyItems; ++k) {
       const int it = tid + k * nthr;
       if (it < dy_items) {
-        const int net = it % nets, pxl = (it / nets) % wp2, pyl = it / (nets * wp2);
+        const int net = it % nets, t2 = it / nets, pxl = t2 % wp2, r = t2 / wp2;
         const float sc = s_scale[net];
-        uint32_t hi2[5], lo2[5];                       // 10 filters as 5 half2 words
-        uint32_t am[10];
+        const uint32_t pa0 = (uint32_t)(((y0 + r) & 1) << 1);            // window positions of this row: pa0 (x even), pa0 + 1 (x odd)
+        uint32_t w0[10], w1[10];                                         // [hi(10) | lo(10)] halves of the two pixels, as half2 words
 #pragma unroll
         for (int v = 0; v < 5; ++v) {
           const float g0 = gq[k][v].x * sc, g1 = gq[k][v].y * sc;
           const __half h0 = __float2half_rn(g0), h1 = __float2half_rn(g1);
           const __half l0 = __float2half_rn(g0 - __half2float(h0)), l1 = __float2half_rn(g1 - __half2float(h1));
-          hi2[v] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          lo2[v] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-          am[2 * v] = aq[k][v] & 0xff; am[2 * v + 1] = aq[k][v] >> 8;
+          const uint32_t hi2 = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          const uint32_t lo2 = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          const uint32_t a0 = aq[k][v] & 0xffu, a1 = aq[k][v] >> 8;
+          const uint32_t m0 = (a0 == pa0 ? 0x0000ffffu : 0u) | (a1 == pa0 ? 0xffff0000u : 0u);
+          const uint32_t m1 = (a0 == pa0 + 1 ? 0x0000ffffu : 0u) | (a1 == pa0 + 1 ? 0xffff0000u : 0u);
+          w0[v] = hi2 & m0; w0[5 + v] = lo2 & m0; w1[v] = hi2 & m1; w1[5 + v] = lo2 & m1;
         }
+        uint2* d0 = reinterpret_cast<uint2*>(dys + ((size_t)(r * Wp + 2 * pxl) * NTp) * 8 + net * 2 * CO);
+        uint2* d1 = reinterpret_cast<uint2*>(dys + ((size_t)(r * Wp + 2 * pxl + 1) * NTp) * 8 + net * 2 * CO);
 #pragma unroll
-        for (int pa = 0; pa < 4; ++pa) {
-          uint32_t w[10];                              // [hi(10) | lo(10)] halves of this pixel and network
-#pragma unroll
-          for (int v = 0; v < 5; ++v) {
-            const uint32_t m = (am[2 * v] == (uint32_t)pa ? 0x0000ffffu : 0u) | (am[2 * v + 1] == (uint32_t)pa ? 0xffff0000u : 0u);
-            w[v] = hi2[v] & m; w[5 + v] = lo2[v] & m;
-          }
-          uint2* d = reinterpret_cast<uint2*>(dys + ((size_t)((2 * pyl + (pa >> 1)) * Wp + 2 * pxl + (pa & 1)) * NTp) * 8 + net * 2 * CO);
-#pragma unroll
-          for (int v = 0; v < 5; ++v) d[v] = make_uint2(w[2 * v], w[2 * v + 1]);
-        }
+        for (int v = 0; v < 5; ++v) { d0[v] = make_uint2(w0[2 * v], w0[2 * v + 1]); d1[v] = make_uint2(w1[2 * v], w1[2 * v + 1]); }
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   };
-  // (3) raw rows -> planes of buffer `buf`: 16-byte channel-group vectors per pixel (zero padding; constant-one channel at C)
+  // (3) raw rows -> planes of buffer `buf`: 16-byte channel-group vectors per pixel (zero padding; constant-one channel at C).
+  // One warp per (plane, input row), lanes along the columns: no per-vector index arithmetic.
   auto stage_planes = [&](int band, int buf) {
     int b, y0, ylo, yhi;
     band_rows_of(band, b, y0, ylo, yhi);
     uint8_t* planes = smem + buf * L.buf_stride + L.planes;
-    const int per_plane = rows_in * pitch;
     const uint32_t ONE = 0x3C00u;                                          // fp16 1.0
-    for (int it = tid; it < P.nvec * per_plane; it += nthr) {
-      const int v = it / per_plane, rem = it - v * per_plane, lr = rem / pitch, lc = rem - lr * pitch;
+    const int nwarps = nthr >> 5;
+    for (int item = warp; item < P.nvec * rows_in; item += nwarps) {
+      const int v = item / rows_in, lr = item - v * rows_in;
       const int y = y0 - PAD + lr;
-      const bool yok = y >= ylo && y < yhi;
-      const unsigned short* rowp = raw + (size_t)(yok ? (y - ylo) : 0) * rowC;
-      uint32_t h[8];
+      uint4* dst = reinterpret_cast<uint4*>(planes + (size_t)v * P.plane_bytes + (size_t)lr * pitch * 16);
+      if (y < ylo || y >= yhi) {
+        for (int lc = lane; lc < pitch; lc += 32) dst[lc] = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      const unsigned short* rowp = raw + (size_t)(y - ylo) * rowC;
       if (v < P.G8) {
-        const int xin = lc - PAD;
-        const bool ok = yok && xin >= 0 && xin < W;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ch = 8 * v + e;
-          h[e] = !ok ? 0u : (ch < C ? (uint32_t)rowp[xin * C + ch] : (ch == C ? ONE : 0u));
+        const int nch = min(8, C - 8 * v), one_at = C - 8 * v;            // one_at in [0, 8): the constant-one channel sits in this group
+        for (int lc = lane; lc < pitch; lc += 32) {
+          const int xin = lc - PAD;
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if (xin >= 0 && xin < W) {
+            val = load8h(rowp + xin * C + 8 * v, nch);
+            if (one_at >= 0 && one_at < 8) {
+              const uint32_t o1 = ONE << ((one_at & 1) * 16);
+              if ((one_at >> 1) == 0) val.x |= o1; else if ((one_at >> 1) == 1) val.y |= o1; else if ((one_at >> 1) == 2) val.z |= o1; else val.w |= o1;
+            }
+          }
+          dst[lc] = val;
         }
       } else {
-        const int j = v - P.G8;                                            // packed: entry E = 8j + e <-> (kx = E / R, channel 8 G8 + E % R)
+        const int j = v - P.G8;                                            // packed: entry e <-> (kx, channel) from the table
+        int kxs[8], chs[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int E = 8 * j + e, kx = E / P.R, ch = 8 * P.G8 + E - kx * P.R;
-          const int xin = lc + kx - PAD;
-          const bool ok = yok && kx < KS && xin >= 0 && xin < W && lc < Wp;
-          h[e] = !ok ? 0u : (ch < C ? (uint32_t)rowp[xin * C + ch] : (ch == C ? ONE : 0u));
+        for (int e = 0; e < 8; ++e) { kxs[e] = s_pk[j][e] & 0xff; chs[e] = s_pk[j][e] >> 8; }
+        for (int lc = lane; lc < pitch; lc += 32) {
+          uint32_t h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int xin = lc + kxs[e] - PAD;
+            const bool ok = kxs[e] < KS && xin >= 0 && xin < W && lc < Wp;
+            h[e] = !ok ? 0u : (chs[e] < C ? (uint32_t)rowp[xin * C + chs[e]] : ONE);
+          }
+          dst[lc] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
         }
       }
-      *reinterpret_cast<uint4*>(planes + (size_t)v * P.plane_bytes + (size_t)rem * 16) =
-          make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
     }
   };
 
@@ -422,7 +454,8 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
   CPP_REQUIRE(P->smem_bytes <= 220 * 1024, "wgrad_mma: %dx%dx%d does not fit shared memory", H, W, C);
   P->bands_per_image = (int)ceil_div(H, P->band_rows);
   P->total_bands = B * P->bands_per_image;
-  CPP_REQUIRE((P->band_rows / 2) * (P->Wp / 2) * nets <= kDyItems * 32 * P->NW, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
+  CPP_REQUIRE(P->band_rows * (P->Wp / 2) * nets <= kDyItems * 32 * P->NW, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
+  CPP_REQUIRE(P->nR <= 8, "wgrad_mma: too many packed planes");
   const int occ = (P->MT * P->NT <= 16 && P->smem_bytes <= 110 * 1024) ? 2 : 1;
   P->grid = std::max(1, std::min(P->total_bands, kNumSMs * occ));
   // bound the tensor-core accumulation chains to ~128 MMA steps between fp32 flushes

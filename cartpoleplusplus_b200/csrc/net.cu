@@ -1,5 +1,6 @@
 // Net: parameter layout, activation workspace, forward and backward of one reference network.
 #include <stdlib.h>
+#include <algorithm>
 #include "net.cuh"
 #include "conv_tc.cuh"
 #include "conv_wgrad_mma.cuh"
@@ -65,6 +66,7 @@ Net::Layout Net::layout(int B) const {
       const size_t n = (size_t)B * conv[i].PH() * conv[i].PW() * kConvCout;
       L.pooled[i] = take(n * sizeof(float));
       L.amax[i] = take(n);
+      if (i < 2) L.hl[i] = take(n * 2 * sizeof(__half));       // [hi(10) | lo(10)] fp16 pieces of pooled[i]
     }
     // gradients wrt pooled2 / pooled1 (dense, the size of conv3 / conv2 inputs)
     L.dpool[0] = take((size_t)B * conv[2].H * conv[2].W * kConvCout * sizeof(float));
@@ -97,8 +99,14 @@ const float* Net::fc_input(const Layout& L, char* ws, int i, int* ld) const {
   return reinterpret_cast<const float*>(ws + L.h[i - 1]);
 }
 
+bool Net::tc_route(int is_f16) const {
+  return pixels && is_f16 && conv1_tc_enabled() && tc::conv_tc_supported(1, conv[0].H, conv[0].W, conv[0].Cin, conv[0].KS) &&
+         tc::conv_tc_supported(1, conv[1].H, conv[1].W, 2 * kConvCout, conv[1].KS) &&
+         tc::conv_tc_supported(1, conv[2].H, conv[2].W, 2 * kConvCout, conv[2].KS);
+}
+
 int Net::forward_trunk(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
-                       cudaStream_t s, int first_conv) const {
+                       cudaStream_t s, int first_conv, void* tc_scratch) const {
   CPP_REQUIRE(B >= 1, "batch %d", B);
   char* ws = reinterpret_cast<char*>(ws_);
   const Layout L = layout(B);
@@ -109,7 +117,16 @@ int Net::forward_trunk(const float* params, const void* state, int is_f16, const
     for (int i = first_conv; i < 3; ++i) {
       float* pooled = reinterpret_cast<float*>(ws + L.pooled[i]);
       uint8_t* amax = reinterpret_cast<uint8_t*>(ws + L.amax[i]);
-      CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
+      if (i > 0 && first_conv > 0 && tc_scratch != nullptr) {
+        // tensor cores: the layer below left its output as fp16 pieces; this layer leaves pieces for the next one
+        const float* w[1] = {params + off_conv_w[i]}; const float* b[1] = {params + off_conv_b[i]};
+        float* po[1] = {pooled}; uint8_t* am[1] = {amax};
+        __half* hl[1] = {i < 2 ? reinterpret_cast<__half*>(ws + L.hl[i]) : nullptr};
+        CPP_TRY(tc::launch_conv_fwd_tc(ws + L.hl[i - 1], nullptr, nullptr, 1, w, b, B, conv[i].H, conv[i].W, 2 * kConvCout, conv[i].KS,
+                                       po, am, tc_scratch, s, 1, hl));
+      } else {
+        CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
+      }
       x = pooled; xf16 = 0; mi = nullptr;
     }
   } else {
@@ -158,7 +175,8 @@ bool conv1_tc_enabled() {
 
 int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net) {
   if (!net.pixels) return 0;
-  const int64_t b = wg::conv_wgrad_mma_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
+  int64_t b = wg::conv_wgrad_mma_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
+  for (int i = 1; i < 3; ++i) b = std::max(b, wg::conv_wgrad_mma_scratch_bytes(1, net.conv[i].H, net.conv[i].W, 2 * kConvCout, net.conv[i].KS));
   return b > 0 ? b : 0;
 }
 
@@ -175,7 +193,7 @@ int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* con
     am[i] = reinterpret_cast<const uint8_t*>(ws[i] + L.amax[0]);
     dw[i] = grads[i] + nets[i]->off_conv_w[0]; db[i] = grads[i] + nets[i]->off_conv_b[0];
   }
-  if (is_f16 && scratch != nullptr && conv1_tc_enabled() && wg::conv_wgrad_mma_supported(n, c1.H, c1.W, c1.Cin, c1.KS))
+  if (scratch != nullptr && n0.tc_route(is_f16) && wg::conv_wgrad_mma_supported(n, c1.H, c1.W, c1.Cin, c1.KS))
     return wg::launch_conv_wgrad_mma(state, mean_inv, 0, n, gp, am, B, c1.H, c1.W, c1.Cin, c1.KS, dw, db, scratch, s);
   for (int i = 0; i < n; ++i) {
     const Net::Layout L = nets[i]->layout(B);
@@ -186,7 +204,8 @@ int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* con
 
 int64_t trunk_group_scratch_bytes(int n, const Net& net) {
   if (!net.pixels) return 0;
-  const int64_t b = tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
+  int64_t b = tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
+  for (int i = 1; i < 3; ++i) b = std::max(b, tc::conv_tc_scratch_bytes(1, net.conv[i].H, net.conv[i].W, 2 * kConvCout, net.conv[i].KS));
   return b > 0 ? b : 0;
 }
 
@@ -195,11 +214,12 @@ int trunk_forward_group(int n, const Net* const* nets, const float* const* param
   CPP_REQUIRE(n >= 1 && n <= tc::kMaxNets, "trunk group of %d networks", n);
   const Net& n0 = *nets[0];
   int first_conv = 0;
-  if (n0.pixels && is_f16 && tc_scratch != nullptr && conv1_tc_enabled() &&
-      tc::conv_tc_supported(n, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin, n0.conv[0].KS)) {
+  const bool tc_ok = tc_scratch != nullptr && n0.tc_route(is_f16) &&
+                     tc::conv_tc_supported(n, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin, n0.conv[0].KS);
+  if (tc_ok) {
     CPP_REQUIRE(mean_inv != nullptr, "pixel network needs whitening statistics");
     const float *w[tc::kMaxNets], *b[tc::kMaxNets];
-    float* pooled[tc::kMaxNets]; uint8_t* amax[tc::kMaxNets];
+    float* pooled[tc::kMaxNets]; uint8_t* amax[tc::kMaxNets]; __half* hl[tc::kMaxNets];
     for (int i = 0; i < n; ++i) {
       const Net& ni = *nets[i];
       CPP_REQUIRE(ni.pixels && ni.conv[0].H == n0.conv[0].H && ni.conv[0].W == n0.conv[0].W && ni.conv[0].Cin == n0.conv[0].Cin,
@@ -207,17 +227,19 @@ int trunk_forward_group(int n, const Net* const* nets, const float* const* param
       const Net::Layout L = ni.layout(B);
       w[i] = params[i] + ni.off_conv_w[0]; b[i] = params[i] + ni.off_conv_b[0];
       pooled[i] = reinterpret_cast<float*>(ws[i] + L.pooled[0]); amax[i] = reinterpret_cast<uint8_t*>(ws[i] + L.amax[0]);
+      hl[i] = reinterpret_cast<__half*>(ws[i] + L.hl[0]);
     }
     CPP_TRY(tc::launch_conv_fwd_tc(state, nullptr, mean_inv, n, w, b, B, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin,
-                                   n0.conv[0].KS, pooled, amax, tc_scratch, s));
+                                   n0.conv[0].KS, pooled, amax, tc_scratch, s, 0, hl));
     first_conv = 1;
   }
-  for (int i = 0; i < n; ++i) CPP_TRY(nets[i]->forward_trunk(params[i], state, is_f16, mean_inv, B, ws[i], s, first_conv));
+  for (int i = 0; i < n; ++i)
+    CPP_TRY(nets[i]->forward_trunk(params[i], state, is_f16, mean_inv, B, ws[i], s, first_conv, tc_ok ? tc_scratch : nullptr));
   return CPP_OK;
 }
 
 int Net::backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
-                  const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1) const {
+                  const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1, void* wg_scratch) const {
   CPP_REQUIRE(B >= 1, "batch %d", B);
   CPP_REQUIRE(d_action == nullptr || concat_at >= 0, "d_action requested from a network without action input");
   char* ws = reinterpret_cast<char*>(ws_);
@@ -267,8 +289,16 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     else { x = ws + L.pooled[i - 1]; xf16 = 0; mi = nullptr; }
     const uint8_t* amax = reinterpret_cast<const uint8_t*>(ws + L.amax[i]);
     if (i == 0 && defer_conv1) break;                       // gp == ws + L.dpool[1]: picked up by conv1_wgrad_group
-    CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, gp, amax, B, grads + off_conv_w[i], grads + off_conv_b[i],
-                              reinterpret_cast<float*>(ws + L.wgrad), s));
+    if (i > 0 && wg_scratch != nullptr && tc_route(is_f16) &&
+        wg::conv_wgrad_mma_supported(1, conv[i].H, conv[i].W, 2 * kConvCout, conv[i].KS)) {
+      const float* g1[1] = {gp}; const uint8_t* a1[1] = {amax};
+      float* dw[1] = {grads + off_conv_w[i]}; float* db[1] = {grads + off_conv_b[i]};
+      CPP_TRY(wg::launch_conv_wgrad_mma(ws + L.hl[i - 1], nullptr, 1, 1, g1, a1, B, conv[i].H, conv[i].W, 2 * kConvCout, conv[i].KS,
+                                        dw, db, wg_scratch, s));
+    } else {
+      CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, gp, amax, B, grads + off_conv_w[i], grads + off_conv_b[i],
+                                reinterpret_cast<float*>(ws + L.wgrad), s));
+    }
     if (i > 0) {
       float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
       CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));

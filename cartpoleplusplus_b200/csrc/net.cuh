@@ -20,7 +20,7 @@ struct Net {
   std::vector<VarInfo> vars;
 
   struct Layout {
-    size_t pooled[3], amax[3], x0, h[CPP_MAX_FC], dA, dB, dpool[2], wgrad, total;
+    size_t pooled[3], amax[3], hl[2], x0, h[CPP_MAX_FC], dA, dB, dpool[2], wgrad, total;
   };
 
   int init(const cpp_net_spec& s);
@@ -37,13 +37,19 @@ struct Net {
               int B, void* ws, float* out, cudaStream_t s, int first_fc = 0) const;
   // the two halves of forward(): conv trunk (first_conv == 1: conv1 is already in ws, written by the tensor-core
   // kernel) or the fp16/fp32 -> fp32 state copy of a low-dim network; then the FC stack from layer first_fc
+  // tc_scratch != NULL with first_conv == 1: conv1 came from the tensor-core kernel together with its fp16 piece copy
+  // (Layout::hl[0]); conv2/conv3 then run on the tensor cores from the pieces as well.
   int forward_trunk(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
-                    cudaStream_t s, int first_conv = 0) const;
+                    cudaStream_t s, int first_conv = 0, void* tc_scratch = nullptr) const;
+  // does this network take the tensor-core route for a state of this dtype (same answer in forward and backward)
+  bool tc_route(int is_f16) const;
   int forward_fc(const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s, int first_fc = 0) const;
   // grads == nullptr: only d_action is produced (stops at the concat layer).  defer_conv1: stop in front of conv1's
   // weight gradient (its input gradient d(pooled1) stays in ws) so that conv1_wgrad_group can do it for all siblings.
+  // wg_scratch != NULL on the tensor-core route: conv2/conv3 weight gradients from the fp16 piece copies (conv_wgrad_mma.cu).
   int backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
-               const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1 = 0) const;
+               const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1 = 0,
+               void* wg_scratch = nullptr) const;
 };
 
 // Conv trunks of n (<= 3) sibling networks that read the SAME state (actor+critic on state_1, the two targets on

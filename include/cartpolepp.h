@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define CPP_ABI_VERSION 1
+#define CPP_ABI_VERSION 2
 #define CPP_MAX_FC 8
 
 typedef enum {
@@ -138,11 +138,15 @@ int cpp_conv_wgrad(const void* x, int32_t x_is_f16, const float* mean_inv, const
  * ReplayMemory.batch (replay_memory.py:134,138) into the layer; mean_inv as above (folded into the weights);
  * w/bias/pooled/amax: HOST arrays of `nets` device pointers; scratch (dev, 256-byte aligned) of
  * cpp_conv_tc_scratch_bytes() holds the packed weights.  fp32 weights enter as two fp16 pieces (22 mantissa
- * bits), pixels are exact fp16, accumulation is fp32: results agree with cpp_conv_forward to ~1e-6 relative. */
+ * bits), pixels are exact fp16, accumulation is fp32: results agree with cpp_conv_forward to ~1e-6 relative.
+ * conv2/conv3 (base_network.py:111-123): x_is_pieces = 1, x holds the fp32 activation of the layer below as fp16 pieces
+ * [B][H][W][hi(Cin/2) | lo(Cin/2)], w has Cin/2 input channels, mean_inv = NULL.  pooled_hl (HOST array of `nets` device
+ * pointers or NULL): the pooled output once more as fp16 pieces [B][H/2][W/2][hi(10) | lo(10)] for the next layer. */
 int64_t cpp_conv_tc_scratch_bytes(int32_t nets, int32_t H, int32_t W, int32_t Cin, int32_t KS);
 int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int32_t nets,
                         const float* const* w, const float* const* bias, int32_t B, int32_t H, int32_t W, int32_t Cin,
-                        int32_t KS, float* const* pooled, uint8_t* const* amax, void* scratch, void* stream);
+                        int32_t KS, float* const* pooled, uint8_t* const* amax, void* scratch, void* stream,
+                        int32_t x_is_pieces, void* const* pooled_hl);
 
 /* weight and bias gradients of the same layer for `nets` (<= 3) sibling networks in ONE pass over x on the tensor cores
  * (mma.sync m16n8k16, fp16 x fp16 -> fp32): tf.gradients of the conv1 variables in ddpg_cartpole.py:111,213 /

@@ -64,7 +64,7 @@ def run_tc(B, H, W, Cin, KS, nets, seed, sparse=False, gather=False):
   scr = torch.zeros(nb, dtype=torch.uint8, device=dev)
   src = slab if gather else x
   L.check(lib.cpp_conv_forward_tc(L.ptr(src), L.ptr(rows), L.ptr(mi), nets, L.ptr_array(ws), L.ptr_array(bs), B, H, W, Cin, KS,
-                                  L.ptr_array(pooled), L.ptr_array(amax), L.ptr(scr), L.stream_ptr()))
+                                  L.ptr_array(pooled), L.ptr_array(amax), L.ptr(scr), L.stream_ptr(), 0, None))
   torch.cuda.synchronize()
   errs = []
   for n in range(nets):
@@ -115,3 +115,57 @@ def test_conv_tc_fused_gather():
 def test_conv_tc_full_batch_c3():
   errs = run_tc(256, 64, 64, 9, 5, 2, seed=3)
   print("tc conv fwd c3 full batch: rel err vs fp64", ["%.2e" % e for e in errs])
+
+
+def run_tc_pieces(B, H, W, KS, seed):
+  """conv2 / conv3 on the tensor cores: the input is an fp32 activation handed over as [hi | lo] fp16 pieces, the output
+  comes back as fp32 + arg-max + its own fp16 piece copy for the next layer"""
+  L, lib = _lib()
+  rs = np.random.RandomState(seed)
+  dev = "cuda"
+  Cin = 10
+  x32 = (np.maximum(rs.randn(B, H, W, Cin), 0) * 10.0 ** rs.uniform(-2, 1)).astype(np.float32)
+  hi = x32.astype(np.float16); lo = (x32 - hi.astype(np.float32)).astype(np.float16)
+  x = torch.from_numpy(np.concatenate([hi, lo], axis=-1)).to(dev)
+  x64 = torch.from_numpy(hi.astype(np.float64) + lo.astype(np.float64)).permute(0, 3, 1, 2).contiguous()
+  lim = np.sqrt(6.0 / (KS * KS * (Cin + 10)))
+  w_h = rs.uniform(-lim, lim, (KS, KS, Cin, 10)).astype(np.float32); b_h = rs.uniform(-0.1, 0.1, 10).astype(np.float32)
+  w, b = torch.from_numpy(w_h).to(dev), torch.from_numpy(b_h).to(dev)
+  PH, PW = H // 2, W // 2
+  pooled = torch.full((B, PH, PW, 10), -7.0, dtype=torch.float32, device=dev)
+  amax = torch.full((B, PH, PW, 10), 9, dtype=torch.uint8, device=dev)
+  hl = torch.full((B, PH, PW, 20), -7.0, dtype=torch.float16, device=dev)
+  nb = int(lib.cpp_conv_tc_scratch_bytes(1, H, W, 2 * Cin, KS))
+  assert nb > 0
+  scr = torch.zeros(nb, dtype=torch.uint8, device=dev)
+  L.check(lib.cpp_conv_forward_tc(L.ptr(x), None, None, 1, L.ptr_array([w]), L.ptr_array([b]), B, H, W, 2 * Cin, KS,
+                                  L.ptr_array([pooled]), L.ptr_array([amax]), L.ptr(scr), L.stream_ptr(), 1, L.ptr_array([hl])))
+  torch.cuda.synchronize()
+  y = F.conv2d(x64, torch.from_numpy(w_h.astype(np.float64)).permute(3, 2, 0, 1).contiguous(), torch.from_numpy(b_h.astype(np.float64)),
+               padding=KS // 2)
+  ref_pool = F.max_pool2d(F.relu(y), 2).permute(0, 2, 3, 1).numpy()
+  got = pooled.cpu().numpy()
+  e = U.assert_close(got, ref_pool, what="tc conv from pieces %dx%d k%d" % (H, W, KS))
+  a = amax.cpu().numpy().astype(np.int64)
+  yw = y[:, :, :PH * 2, :PW * 2].reshape(B, 10, PH, 2, PW, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, PH, PW, 10, 4).numpy()
+  closed = a == 4
+  assert a.max() <= 4 and np.array_equal(closed, got == 0)
+  picked = np.take_along_axis(yw, np.minimum(a, 3)[..., None], axis=-1)[..., 0]
+  scale = np.abs(yw).max()
+  assert np.all(np.abs(picked - yw.max(-1))[~closed] <= 1e-5 * scale)
+  h = hl.cpu().numpy().astype(np.float64)
+  rec = h[..., :10] + h[..., 10:]
+  assert np.array_equal(h[..., :10].astype(np.float16), got.astype(np.float16))          # hi = round-to-nearest fp16 of the fp32 value
+  assert np.abs(rec - got).max() <= 2.0 ** -20 * max(np.abs(got).max(), 1e-30)
+  # the exact-fp32 CUDA-core kernel on the fp32 activation
+  p2 = torch.zeros((B, PH, PW, 10), dtype=torch.float32, device=dev); a2 = torch.zeros((B, PH, PW, 10), dtype=torch.uint8, device=dev)
+  x32d = torch.from_numpy(x32).to(dev)
+  L.check(lib.cpp_conv_forward(L.ptr(x32d), 0, None, L.ptr(w), L.ptr(b), B, H, W, Cin, KS, L.ptr(p2), L.ptr(a2), L.stream_ptr()))
+  U.assert_close(got, p2.cpu().numpy(), what="tc from pieces vs fp32 kernel")
+  return e
+
+
+@pytest.mark.parametrize("B,H,W,KS", [(8, 32, 32, 5), (8, 16, 16, 3), (2, 64, 64, 5), (4, 32, 32, 3), (3, 25, 25, 5), (3, 12, 12, 3),
+                                      (256, 32, 32, 5), (256, 16, 16, 3)])
+def test_conv_tc_from_pieces(B, H, W, KS):
+  print("tc conv from pieces B%d %dx%d k%d: rel err vs fp64 %.2e" % (B, H, W, KS, run_tc_pieces(B, H, W, KS, seed=B + H + KS)))
