@@ -100,7 +100,7 @@ int DDPG::actor_backward(const void* s1, int is_f16, int B, int B_global, cudaSt
   // q_gradients_wrt_actions: tf.gradients(q_value, input_action), ddpg_cartpole.py:220-222
   CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, s));
   CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, s));                       // tf.neg(...), :113
-  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s, 1, wg_scr));
+  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s, 1, wg_scr, tc_scr1));
   {
     const Net* g[1] = {&actor}; char* wss[1] = {ws_actor}; float* gr[1] = {buf.grads};
     CPP_TRY(conv1_wgrad_group(1, g, wss, gr, s1, is_f16, m1, B, wg_scr, s));
@@ -148,7 +148,7 @@ int DDPG::critic_backward(const void* s1, const float* action, const float* rewa
                           int is_f16, int B, int B_global, int reuse, cudaStream_t s) {
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
   CPP_TRY(critic_forward_td(s1, action, reward, mask, s2, is_f16, B, B_global, reuse != 0, td, dq, buf.grads + off_loss, s));
-  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, cur_m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s, 1, wg_scr));
+  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, cur_m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s, 1, wg_scr, tc_scr1));
   {
     const Net* g[1] = {&critic}; char* wss[1] = {ws_critic}; float* gr[1] = {buf.grads + off_c};
     CPP_TRY(conv1_wgrad_group(1, g, wss, gr, s1, is_f16, cur_m1, B, wg_scr, s));
@@ -176,12 +176,12 @@ int DDPG::step_backward(const void* s1, const float* action, const float* reward
   if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s)); ones_ready = true; }
   CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, s));
   CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, s));
-  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s, 1, wg_scr));
+  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s, 1, wg_scr, tc_scr1));
   // ---- critic.train(batch): :186-218,230-237.  The critic trunk on state_1 is the one computed above (the critic's
   // parameters have not changed); only the layers from the action concat upwards are re-evaluated at the batch actions.
   critic_trunk_valid = true; trunk_B = B;
   CPP_TRY(critic_forward_td(s1, action, reward, mask, s2, is_f16, B, B_global, true, td, dq, buf.grads + off_loss, s));
-  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s, 1, wg_scr));
+  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s, 1, wg_scr, tc_scr1));
   // ---- conv1 weight gradients of both networks in one pass over state_1
   {
     const Net* g[2] = {&actor, &critic}; char* wss[2] = {ws_actor, ws_critic}; float* gr[2] = {buf.grads, buf.grads + off_c};
@@ -314,9 +314,9 @@ int NAF::backward(const void* s1, const float* action, const float* reward, cons
                   int B, int B_global, cudaStream_t s) {
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
   CPP_TRY(forward_all(s1, action, reward, mask, s2, is_f16, B, B_global, true, nullptr, buf.grads + off_loss, s));
-  CPP_TRY(value.backward(buf.params, s1, is_f16, cur_m1, B, ws_v, dV, buf.grads, nullptr, s, 1, wg_scr));
-  CPP_TRY(mu.backward(buf.params + off_m, s1, is_f16, cur_m1, B, ws_m, dmu, buf.grads + off_m, nullptr, s, 1, wg_scr));
-  CPP_TRY(l.backward(buf.params + off_l, s1, is_f16, cur_m1, B, ws_l, dl, buf.grads + off_l, nullptr, s, 1, wg_scr));
+  CPP_TRY(value.backward(buf.params, s1, is_f16, cur_m1, B, ws_v, dV, buf.grads, nullptr, s, 1, wg_scr, tc_scr1));
+  CPP_TRY(mu.backward(buf.params + off_m, s1, is_f16, cur_m1, B, ws_m, dmu, buf.grads + off_m, nullptr, s, 1, wg_scr, tc_scr1));
+  CPP_TRY(l.backward(buf.params + off_l, s1, is_f16, cur_m1, B, ws_l, dl, buf.grads + off_l, nullptr, s, 1, wg_scr, tc_scr1));
   {  // conv1 weight gradients of the three networks in one pass over state_1
     const Net* g[3] = {&value, &mu, &l}; char* wss[3] = {ws_v, ws_m, ws_l};
     float* gr[3] = {buf.grads, buf.grads + off_m, buf.grads + off_l};

@@ -148,25 +148,33 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
     if (valid) {
       const int net = n / (kPieces * CO), piece = (n / CO) % kPieces, o = n % CO;
       const float inv = A.mean_inv ? A.mean_inv[C + ch] : 1.f;
-      v = A.w[net][((ky * KS + kx) * Cw + (ch < Cw ? ch : ch - Cw)) * CO + o] * inv * scale;
+      const int chw = ch < Cw ? ch : ch - Cw;
+      const float wv = P.dgrad ? A.w[net][(((KS - 1 - ky) * KS + (KS - 1 - kx)) * CO + o) * CO + chw]      // flipped taps, in/out swapped
+                               : A.w[net][((ky * KS + kx) * Cw + chw) * CO + o];
+      v = wv * inv * scale;
       const __half hi = __float2half_rn(v);
       out = (piece == 0) ? hi : __float2half_rn(v - __half2float(hi));
     }
     A.bpack[idx] = out;
   }
+  // (3) one warp per table entry: the lanes split the taps x channels of the border-aware mean term (fp64, fixed order)
   const int ncls = 2 * P.PAD + 1;
-  for (int idx = gtid; idx < ncls * ncls * P.nets * CO; idx += gthreads) {
+  const int lane = tid & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
+  for (int idx = gwarp; idx < ncls * ncls * P.nets * CO; idx += gwarps) {
     const int o = idx % CO, net = (idx / CO) % P.nets, xc = (idx / (CO * P.nets)) % ncls, yc = idx / (CO * P.nets * ncls);
-    double acc = (double)A.bias[net][o];
+    double acc = 0.0;
     if (A.mean_inv) {
       const int ky0 = yc < P.PAD ? P.PAD - yc : 0, ky1 = yc > P.PAD ? KS - 1 - (yc - P.PAD) : KS - 1;
       const int kx0 = xc < P.PAD ? P.PAD - xc : 0, kx1 = xc > P.PAD ? KS - 1 - (xc - P.PAD) : KS - 1;
-      for (int ky = ky0; ky <= ky1; ++ky)
-        for (int kx = kx0; kx <= kx1; ++kx)
-          for (int ch = 0; ch < Cw; ++ch)       // whitening is never combined with piece inputs: Cw == C here
-            acc -= (double)A.mean_inv[ch] * (double)A.mean_inv[C + ch] * (double)A.w[net][((ky * KS + kx) * Cw + ch) * CO + o];
+      const int nky = ky1 - ky0 + 1, nkx = kx1 - kx0 + 1, terms = nky * nkx * Cw;
+      for (int t = lane; t < terms; t += 32) {
+        const int ch = t % Cw, kx = kx0 + (t / Cw) % nkx, ky = ky0 + t / (Cw * nkx);
+        acc -= (double)A.mean_inv[ch] * (double)A.mean_inv[C + ch] * (double)A.w[net][((ky * KS + kx) * Cw + ch) * CO + o];
+      }
     }
-    A.corr[idx] = (float)acc;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if (lane == 0) A.corr[idx] = (float)((A.bias[net] ? (double)A.bias[net][o] : 0.0) + acc);
   }
 }
 
@@ -298,6 +306,30 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
         const int q = 128 * t + 32 * quarter + lane;
         const int py = q / Pq, px = q - py * Pq;
         const bool valid = py < PH && px < PW;
+        if (P.dgrad) {
+          // input-gradient mode: no bias / ReLU / pool, the four window positions are four output pixels
+          const float osc = scale_inv * P.out_scale[0];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            uint32_t r[20];
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)((ab * 4 + a) * N);
+            tmem_ld16(taddr, r);
+            tmem_ld4(taddr + 16, r + 16);
+            tmem_ld_wait();
+            const int y = 2 * py + (a >> 1), x = 2 * px + (a & 1);
+            if (valid && y < H && x < W) {
+              float* op = P.pooled[0] + (((size_t)b * H + y) * W + x) * CO;
+#pragma unroll
+              for (int o = 0; o < CO; o += 2)
+                *reinterpret_cast<float2*>(op + o) = make_float2((__uint_as_float(r[o]) + __uint_as_float(r[CO + o])) * osc,
+                                                                 (__uint_as_float(r[o + 1]) + __uint_as_float(r[CO + o + 1])) * osc);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[BAR_EMPTY_ACC + ab]);
+          continue;
+        }
         for (int net = 0; net < P.nets; ++net) {
           float best[CO];
           int arg[CO];
@@ -493,13 +525,14 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------ host: plan
-static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P) {
+static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, int dgrad = 0) {
   CPP_REQUIRE(KS == 5 || KS == 3, "conv_tc: kernel size %d", KS);
   CPP_REQUIRE(nets >= 1 && nets <= kMaxNets, "conv_tc: %d sibling networks", nets);
   const int PAD = KS / 2;
   CPP_REQUIRE(H >= 2 * PAD && W >= 2 * PAD && H >= 2 && W >= 2, "conv_tc: input %dx%d too small", H, W);
   P->B = B; P->H = H; P->W = W; P->C = C; P->KS = KS; P->PAD = PAD;
-  P->PH = H / 2; P->PW = W / 2;
+  P->PH = dgrad ? (H + 1) / 2 : H / 2; P->PW = dgrad ? (W + 1) / 2 : W / 2;      // dgrad covers every input pixel, VALID pooling drops odd edges
+  P->dgrad = dgrad;
   P->Pq = (W + 1) / 2 + 1;      // parity-plane pitch: ceil(W/2) pixels + one zero column shared by neighbouring rows
   P->nets = nets; P->N = (int)round_up(nets * kPieces * CO, 16);
   CPP_REQUIRE(8 * P->N <= 512, "conv_tc: N=%d does not fit two sets of TMEM accumulators", P->N);
@@ -647,7 +680,7 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   }
   A.mean_inv = mean_inv;
   A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);
-  conv_tc_prep_kernel<<<16, 256, 0, s>>>(P, A);
+  conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
   CPP_CHECK_LAUNCH();
   const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, kNumSMs);   // persistent: one CTA per SM (it owns all 512 TMEM columns)
   if (KS == 5) {
@@ -658,6 +691,95 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   if (P.R == 0) return launch_main<3, 0>(P, grid, s);
   if (P.R == 1) return launch_main<3, 1>(P, grid, s);
   return launch_main<3, 2>(P, grid, s);
+}
+
+int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
+                         void* scratch, cudaStream_t s) {
+  if (B <= 0) return CPP_OK;
+  FwdPlan P{};
+  CPP_TRY(build_plan(1, B, H, W, 2 * CO, KS, &P, 1));
+  CPP_REQUIRE(((uintptr_t)dy_pieces & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
+  P.Cw = CO;
+  P.x = reinterpret_cast<const __half*>(dy_pieces); P.rows = nullptr;
+  P.bpack = reinterpret_cast<const __half*>(scratch);
+  P.corr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(scratch) + bpack_bytes(P));
+  P.out_scale = inv_scale;
+  P.pooled[0] = dx; P.amax[0] = nullptr; P.pooled_hl[0] = nullptr;
+  PrepArgs A{};
+  A.w[0] = w; A.bias[0] = nullptr; A.mean_inv = nullptr;
+  A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);
+  conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
+  CPP_CHECK_LAUNCH();
+  const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, kNumSMs);
+  return KS == 5 ? launch_main<5, 0>(P, grid, s) : launch_main<3, 0>(P, grid, s);
+}
+
+// one thread per 2x2 window (and per odd-edge pixel): 4 pixels x [hi(10) | lo(10)]
+__global__ void __launch_bounds__(256) unpool_split_kernel(const float* __restrict__ g, const uint8_t* __restrict__ amax, int B, int H, int W,
+                                                           const float* __restrict__ gmax, float* __restrict__ inv_scale,
+                                                           __half* __restrict__ out) {
+  const int PH = H / 2, PW = W / 2, PHc = (H + 1) / 2, PWc = (W + 1) / 2;
+  float scale = 1.f;
+  {
+    const float mx = gmax[0];
+    if (mx > 0.f && isfinite(mx)) { int e; frexpf(mx, &e); scale = ldexpf(1.f, 15 - e); }
+  }
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) inv_scale[0] = 1.f / scale;
+  if (i >= (int64_t)B * PHc * PWc) return;
+  const int px = (int)(i % PWc), py = (int)((i / PWc) % PHc), b = (int)(i / ((int64_t)PWc * PHc));
+  float gv[CO]; int a[CO];
+  const bool inside = py < PH && px < PW;
+#pragma unroll
+  for (int o = 0; o < CO; ++o) { gv[o] = 0.f; a[o] = 4; }
+  if (inside) {
+    const size_t idx = (((size_t)b * PH + py) * PW + px) * CO;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) { gv[o] = g[idx + o] * scale; a[o] = amax[idx + o]; }
+  }
+#pragma unroll
+  for (int pa = 0; pa < 4; ++pa) {
+    const int y = 2 * py + (pa >> 1), x = 2 * px + (pa & 1);
+    if (y >= H || x >= W) continue;
+    __half2* d = reinterpret_cast<__half2*>(out + (((size_t)b * H + y) * W + x) * 2 * CO);
+#pragma unroll
+    for (int o = 0; o < CO; o += 2) {
+      const float v0 = a[o] == pa ? gv[o] : 0.f, v1 = a[o + 1] == pa ? gv[o + 1] : 0.f;
+      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+      d[o >> 1] = __halves2half2(h0, h1);
+      d[(CO + o) >> 1] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+  __shared__ float sh[8];
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, sh[i]);
+    atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));             // non-negative floats order like ints: deterministic
+  }
+}
+
+int launch_unpool_split(const float* d_pooled, const uint8_t* amax, int B, int H, int W, float* gmax, float* inv_scale,
+                        __half* dy_pieces, cudaStream_t s) {
+  if (B <= 0) return CPP_OK;
+  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * CO;
+  CPP_CHECK_CUDA(cudaMemsetAsync(gmax, 0, sizeof(float), s));
+  if (n > 0) {
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, ceil_div(n, 256 * 8)));
+    absmax_kernel<<<blocks, 256, 0, s>>>(d_pooled, n, gmax);
+    CPP_CHECK_LAUNCH();
+  }
+  const int64_t items = (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2);
+  unpool_split_kernel<<<(unsigned)ceil_div(items, 256), 256, 0, s>>>(d_pooled, amax, B, H, W, gmax, inv_scale, dy_pieces);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
 }
 
 }  // namespace tc

@@ -28,6 +28,9 @@ struct FwdPlan {
   __half* pooled_hl[kMaxNets];   // optional: the pooled output again as fp16 pieces [B][PH][PW][hi(10) | lo(10)] for the next layer
   int B, H, W, C, PH, PW, Pq, KS, PAD;
   int Cw;                   // weight input channels: C, or C/2 when x holds [hi | lo] pieces of an fp32 activation
+  int dgrad;                // 1: input-gradient mode - x = un-pooled output gradient pieces, taps flipped and channels transposed,
+                            //    no bias / ReLU / pool: every conv position is written to the dense fp32 output pooled[n] [B][H][W][10]
+  const float* out_scale;   // dgrad: device scalar the result is multiplied with (undoes the power-of-two scaling of the pieces)
   int nets, N;              // MMA N = round_up(nets * kPieces * 10, 16)
   // ---- shared-memory geometry
   int G8, R, nR;            // full 8-channel groups, remainder channels, packed slabs per ky
@@ -57,6 +60,15 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
                        const float* const* w, const float* const* bias, int B, int H, int W, int C, int KS,
                        float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s,
                        int x_is_pieces = 0, __half* const* pooled_hl = nullptr);
+// gradient wrt the input of a 10 -> 10 channel layer (conv2 / conv3): dx = conv_same(dY, flip(w)^T) on the tensor cores.
+// dy_pieces fp16 [B][H][W][hi(10) | lo(10)] = the un-pooled output gradient times *inv_scale^-1 (launch_unpool_split);
+// dx fp32 [B][H][W][10].
+int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
+                         void* scratch, cudaStream_t s);
+// un-pool + split: d_pooled fp32 [B][H/2][W/2][10] and the arg-max side band -> dy_pieces fp16 [B][H][W][hi | lo], scaled by
+// a power of two from max|d_pooled| (gmax: device float, zeroed and filled here); inv_scale receives 1/scale
+int launch_unpool_split(const float* d_pooled, const uint8_t* amax, int B, int H, int W, float* gmax, float* inv_scale,
+                        __half* dy_pieces, cudaStream_t s);
 
 }  // namespace tc
 }  // namespace cpp

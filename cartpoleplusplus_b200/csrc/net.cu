@@ -74,6 +74,8 @@ Net::Layout Net::layout(int B) const {
     int64_t wg = 0;
     for (int i = 0; i < 3; ++i) { const int64_t w = conv_wgrad_scratch_floats(conv[i]); if (w > wg) wg = w; }
     L.wgrad = take((size_t)wg * sizeof(float));
+    L.dyp = take((size_t)B * conv[1].H * conv[1].W * 2 * kConvCout * sizeof(__half));   // un-pooled gradient pieces (dgrad on tensor cores)
+    L.gsc = take(4 * sizeof(float));
   } else {
     L.x0 = take((size_t)B * in_dim[0] * sizeof(float));
   }
@@ -239,7 +241,8 @@ int trunk_forward_group(int n, const Net* const* nets, const float* const* param
 }
 
 int Net::backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
-                  const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1, void* wg_scratch) const {
+                  const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1, void* wg_scratch,
+                  void* tc_scratch) const {
   CPP_REQUIRE(B >= 1, "batch %d", B);
   CPP_REQUIRE(d_action == nullptr || concat_at >= 0, "d_action requested from a network without action input");
   char* ws = reinterpret_cast<char*>(ws_);
@@ -301,7 +304,14 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     }
     if (i > 0) {
       float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
-      CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));
+      if (tc_scratch != nullptr && tc_route(is_f16)) {
+        float* gsc = reinterpret_cast<float*>(ws + L.gsc);
+        __half* dyp = reinterpret_cast<__half*>(ws + L.dyp);
+        CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, dyp, s));
+        CPP_TRY(tc::launch_conv_dgrad_tc(dyp, gsc + 1, params + off_conv_w[i], B, conv[i].H, conv[i].W, conv[i].KS, dx, tc_scratch, s));
+      } else {
+        CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));
+      }
       gp = dx;
     }
   }

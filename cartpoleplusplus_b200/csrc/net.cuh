@@ -20,7 +20,7 @@ struct Net {
   std::vector<VarInfo> vars;
 
   struct Layout {
-    size_t pooled[3], amax[3], hl[2], x0, h[CPP_MAX_FC], dA, dB, dpool[2], wgrad, total;
+    size_t pooled[3], amax[3], hl[2], x0, h[CPP_MAX_FC], dA, dB, dpool[2], wgrad, dyp, gsc, total;
   };
 
   int init(const cpp_net_spec& s);
@@ -46,10 +46,11 @@ struct Net {
   int forward_fc(const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s, int first_fc = 0) const;
   // grads == nullptr: only d_action is produced (stops at the concat layer).  defer_conv1: stop in front of conv1's
   // weight gradient (its input gradient d(pooled1) stays in ws) so that conv1_wgrad_group can do it for all siblings.
-  // wg_scratch != NULL on the tensor-core route: conv2/conv3 weight gradients from the fp16 piece copies (conv_wgrad_mma.cu).
+  // wg_scratch != NULL on the tensor-core route: conv2/conv3 weight gradients from the fp16 piece copies (conv_wgrad_mma.cu);
+  // tc_scratch != NULL: conv3/conv2 input gradients through the tcgen05 kernel in dgrad mode (conv_tc.cu).
   int backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
                const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1 = 0,
-               void* wg_scratch = nullptr) const;
+               void* wg_scratch = nullptr, void* tc_scratch = nullptr) const;
 };
 
 // Conv trunks of n (<= 3) sibling networks that read the SAME state (actor+critic on state_1, the two targets on

@@ -148,6 +148,13 @@ int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mea
                         int32_t KS, float* const* pooled, uint8_t* const* amax, void* scratch, void* stream,
                         int32_t x_is_pieces, void* const* pooled_hl);
 
+/* gradient wrt the input of a 10 -> 10 channel layer (conv2/conv3; same contract as cpp_conv_dgrad) on the tensor cores:
+ * the pooled gradient is un-pooled through the arg-max side band into fp16 pieces (scaled by a power of two from its
+ * max) and convolved with the flipped, transposed filters by the tcgen05 kernel in dense-output mode.
+ * scratch: cpp_conv_dgrad_tc_scratch_bytes(), 256-byte aligned. */
+int64_t cpp_conv_dgrad_tc_scratch_bytes(int32_t B, int32_t H, int32_t W, int32_t KS);
+int cpp_conv_dgrad_tc(const float* d_pooled, const uint8_t* amax, const float* w, int32_t B, int32_t H, int32_t W, int32_t KS,
+                      float* dx, void* scratch, void* stream);
 /* weight and bias gradients of the same layer for `nets` (<= 3) sibling networks in ONE pass over x on the tensor cores
  * (mma.sync m16n8k16, fp16 x fp16 -> fp32): tf.gradients of the conv1 variables in ddpg_cartpole.py:111,213 /
  * naf_cartpole.py:233.  x fp16 NHWC (exact replay pixels); d_pooled/amax/dw/db: HOST arrays of `nets` device pointers;

@@ -169,3 +169,42 @@ def run_tc_pieces(B, H, W, KS, seed):
                                       (256, 32, 32, 5), (256, 16, 16, 3)])
 def test_conv_tc_from_pieces(B, H, W, KS):
   print("tc conv from pieces B%d %dx%d k%d: rel err vs fp64 %.2e" % (B, H, W, KS, run_tc_pieces(B, H, W, KS, seed=B + H + KS)))
+
+
+def run_dgrad_tc(B, H, W, KS, seed):
+  """input gradient of a 10 -> 10 layer on the tensor cores vs fp64 autograd with the same routing, and vs the CUDA-core kernel"""
+  L, lib = _lib()
+  rs = np.random.RandomState(seed)
+  dev = "cuda"
+  PH, PW = H // 2, W // 2
+  lim = np.sqrt(6.0 / (KS * KS * 20))
+  w_h = rs.uniform(-lim, lim, (KS, KS, 10, 10)).astype(np.float32)
+  a = rs.randint(0, 5, (B, PH, PW, 10))                                 # any routing, incl. closed gates (4)
+  gp_h = (rs.randn(B, PH, PW, 10) * 10.0 ** rs.uniform(-7, 0)).astype(np.float32)
+  onehot = np.zeros((B, PH, PW, 10, 4))
+  np.put_along_axis(onehot, np.minimum(a, 3)[..., None], 1.0, axis=-1)
+  onehot[a == 4] = 0.0
+  gfull = np.zeros((B, 10, H, W))
+  gfull[:, :, :PH * 2, :PW * 2] = (onehot * gp_h.astype(np.float64)[..., None]).reshape(B, PH, PW, 10, 2, 2).transpose(0, 3, 1, 4, 2, 5).reshape(B, 10, PH * 2, PW * 2)
+  xin = torch.zeros((B, 10, H, W), dtype=torch.float64, requires_grad=True)
+  y = F.conv2d(xin, torch.from_numpy(w_h.astype(np.float64)).permute(3, 2, 0, 1).contiguous(), padding=KS // 2)
+  gx, = torch.autograd.grad(y, [xin], grad_outputs=torch.from_numpy(gfull))
+  want = gx.permute(0, 2, 3, 1).numpy()
+  gp = torch.from_numpy(gp_h).to(dev); am = torch.from_numpy(a.astype(np.uint8)).to(dev); w = torch.from_numpy(w_h).to(dev)
+  dx = torch.full((B, H, W, 10), 7.0, dtype=torch.float32, device=dev)
+  nb = int(lib.cpp_conv_dgrad_tc_scratch_bytes(B, H, W, KS))
+  assert nb > 0
+  scr = torch.zeros(nb, dtype=torch.uint8, device=dev)
+  L.check(lib.cpp_conv_dgrad_tc(L.ptr(gp), L.ptr(am), L.ptr(w), B, H, W, KS, L.ptr(dx), L.ptr(scr), L.stream_ptr()))
+  torch.cuda.synchronize()
+  e = U.assert_close(dx.cpu().numpy(), want, what="dgrad_tc %dx%d k%d" % (H, W, KS))
+  dx2 = torch.zeros((B, H, W, 10), dtype=torch.float32, device=dev)
+  L.check(lib.cpp_conv_dgrad(L.ptr(gp), L.ptr(am), L.ptr(w), B, H, W, KS, L.ptr(dx2), L.stream_ptr()))
+  U.assert_close(dx.cpu().numpy(), dx2.cpu().numpy(), what="dgrad_tc vs fp32 kernel")
+  return e
+
+
+@pytest.mark.parametrize("B,H,W,KS", [(8, 32, 32, 5), (8, 16, 16, 3), (2, 64, 64, 5), (3, 25, 25, 5), (3, 12, 13, 3), (256, 32, 32, 5),
+                                      (256, 16, 16, 3), (1, 4, 4, 3)])
+def test_conv_dgrad_tc(B, H, W, KS):
+  print("dgrad_tc B%d %dx%d k%d: rel err vs fp64 %.2e" % (B, H, W, KS, run_dgrad_tc(B, H, W, KS, seed=B + H + KS)))
