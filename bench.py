@@ -194,9 +194,9 @@ def run_native(args):
   def timed(fn, steps, warmup, clocks=None):
     for i in range(warmup):
       fn(i)
-    dp.barrier(); torch.cuda.synchronize()
     if clocks:
-      clocks.start(); time.sleep(0.25)
+      clocks.start(); time.sleep(0.25)       # before the barrier: a rank that sleeps after it stalls its peers' first collective
+    dp.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.cpp_launch_count()
     e0.record()

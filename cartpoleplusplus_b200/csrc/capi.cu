@@ -9,6 +9,7 @@
 
 namespace cpp {
 long long g_launch_count = 0;
+int g_cta_cap = 148;
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;

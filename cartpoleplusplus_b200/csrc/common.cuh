@@ -23,6 +23,8 @@ const char* get_error();
   } while (0)
 
 extern long long g_launch_count;    // kernels launched by this library (capi.cu)
+extern int g_cta_cap;               // SMs a persistent kernel may occupy (agents lower it while independent chains share the GPU)
+static inline int sm_budget() { return g_cta_cap < 1 ? 1 : (g_cta_cap > 148 ? 148 : g_cta_cap); }
 #define CPP_CHECK_LAUNCH() do { ++cpp::g_launch_count; CPP_CHECK_CUDA(cudaGetLastError()); } while (0)
 
 #define CPP_REQUIRE(cond, ...)                \

@@ -682,7 +682,7 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);
   conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
   CPP_CHECK_LAUNCH();
-  const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, kNumSMs);   // persistent: one CTA per SM (it owns all 512 TMEM columns)
+  const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, sm_budget());   // persistent: one CTA per SM (it owns all 512 TMEM columns)
   if (KS == 5) {
     if (P.R == 0) return launch_main<5, 0>(P, grid, s);
     if (P.R == 1) return launch_main<5, 1>(P, grid, s);
@@ -710,7 +710,7 @@ int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const fl
   A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);
   conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
   CPP_CHECK_LAUNCH();
-  const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, kNumSMs);
+  const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, sm_budget());
   return KS == 5 ? launch_main<5, 0>(P, grid, s) : launch_main<3, 0>(P, grid, s);
 }
 

@@ -457,7 +457,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
   CPP_REQUIRE(P->band_rows * (P->Wp / 2) * nets <= kDyItems * 32 * P->NW, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
   CPP_REQUIRE(P->nR <= 8, "wgrad_mma: too many packed planes");
   const int occ = (P->MT * P->NT <= 16 && P->smem_bytes <= 110 * 1024) ? 2 : 1;
-  P->grid = std::max(1, std::min(P->total_bands, kNumSMs * occ));
+  P->grid = std::max(1, std::min(P->total_bands, sm_budget() * occ));
   // bound the tensor-core accumulation chains to ~128 MMA steps between fp32 flushes
   const int steps_per_band = P->band_rows * (P->Wp / 16);
   P->flush_every = std::max(1, 128 / steps_per_band);

@@ -137,12 +137,14 @@ int Net::forward_trunk(const float* params, const void* state, int is_f16, const
   return CPP_OK;
 }
 
-int Net::forward_fc(const float* params, const float* action, int B, void* ws_, float* out, cudaStream_t s, int first_fc) const {
+int Net::forward_fc(const float* params, const float* action, int B, void* ws_, float* out, cudaStream_t s, int first_fc,
+                    int end_fc) const {
   CPP_REQUIRE(B >= 1, "batch %d", B);
-  CPP_REQUIRE(concat_at < 0 || action != nullptr, "this network needs an action input");
+  if (end_fc < 0 || end_fc > n_fc) end_fc = n_fc;
+  CPP_REQUIRE(concat_at < 0 || concat_at < first_fc || concat_at >= end_fc || action != nullptr, "this network needs an action input");
   char* ws = reinterpret_cast<char*>(ws_);
   const Layout L = layout(B);
-  for (int i = first_fc; i < n_fc; ++i) {
+  for (int i = first_fc; i < end_fc; ++i) {
     int ld;
     const float* x = fc_input(L, ws, i, &ld);
     if (concat_at == i)   // tf.concat(1, [hidden, action]), ddpg_cartpole.py:170,175
@@ -155,7 +157,7 @@ int Net::forward_fc(const float* params, const float* action, int B, void* ws_, 
     g.epi = EPI_BIAS_ACT; g.bias = params + off_fc_b[i]; g.act = act[i];
     CPP_TRY(launch_gemm(g, s));
   }
-  if (out != nullptr) {
+  if (out != nullptr && end_fc == n_fc) {
     const int n = out_dim[n_fc - 1];
     CPP_CHECK_CUDA(cudaMemcpyAsync(out, ws + L.h[n_fc - 1], (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
@@ -211,32 +213,38 @@ int64_t trunk_group_scratch_bytes(int n, const Net& net) {
   return b > 0 ? b : 0;
 }
 
-int trunk_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
-                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s) {
+int conv1_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
+                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s, int* took_tc) {
   CPP_REQUIRE(n >= 1 && n <= tc::kMaxNets, "trunk group of %d networks", n);
   const Net& n0 = *nets[0];
-  int first_conv = 0;
+  *took_tc = 0;
   const bool tc_ok = tc_scratch != nullptr && n0.tc_route(is_f16) &&
                      tc::conv_tc_supported(n, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin, n0.conv[0].KS);
-  if (tc_ok) {
-    CPP_REQUIRE(mean_inv != nullptr, "pixel network needs whitening statistics");
-    const float *w[tc::kMaxNets], *b[tc::kMaxNets];
-    float* pooled[tc::kMaxNets]; uint8_t* amax[tc::kMaxNets]; __half* hl[tc::kMaxNets];
-    for (int i = 0; i < n; ++i) {
-      const Net& ni = *nets[i];
-      CPP_REQUIRE(ni.pixels && ni.conv[0].H == n0.conv[0].H && ni.conv[0].W == n0.conv[0].W && ni.conv[0].Cin == n0.conv[0].Cin,
-                  "sibling networks must read the same state");
-      const Net::Layout L = ni.layout(B);
-      w[i] = params[i] + ni.off_conv_w[0]; b[i] = params[i] + ni.off_conv_b[0];
-      pooled[i] = reinterpret_cast<float*>(ws[i] + L.pooled[0]); amax[i] = reinterpret_cast<uint8_t*>(ws[i] + L.amax[0]);
-      hl[i] = reinterpret_cast<__half*>(ws[i] + L.hl[0]);
-    }
-    CPP_TRY(tc::launch_conv_fwd_tc(state, nullptr, mean_inv, n, w, b, B, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin,
-                                   n0.conv[0].KS, pooled, amax, tc_scratch, s, 0, hl));
-    first_conv = 1;
+  if (!tc_ok) return CPP_OK;
+  CPP_REQUIRE(mean_inv != nullptr, "pixel network needs whitening statistics");
+  const float *w[tc::kMaxNets], *b[tc::kMaxNets];
+  float* pooled[tc::kMaxNets]; uint8_t* amax[tc::kMaxNets]; __half* hl[tc::kMaxNets];
+  for (int i = 0; i < n; ++i) {
+    const Net& ni = *nets[i];
+    CPP_REQUIRE(ni.pixels && ni.conv[0].H == n0.conv[0].H && ni.conv[0].W == n0.conv[0].W && ni.conv[0].Cin == n0.conv[0].Cin,
+                "sibling networks must read the same state");
+    const Net::Layout L = ni.layout(B);
+    w[i] = params[i] + ni.off_conv_w[0]; b[i] = params[i] + ni.off_conv_b[0];
+    pooled[i] = reinterpret_cast<float*>(ws[i] + L.pooled[0]); amax[i] = reinterpret_cast<uint8_t*>(ws[i] + L.amax[0]);
+    hl[i] = reinterpret_cast<__half*>(ws[i] + L.hl[0]);
   }
+  CPP_TRY(tc::launch_conv_fwd_tc(state, nullptr, mean_inv, n, w, b, B, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin,
+                                 n0.conv[0].KS, pooled, amax, tc_scratch, s, 0, hl));
+  *took_tc = 1;
+  return CPP_OK;
+}
+
+int trunk_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
+                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s) {
+  int took_tc = 0;
+  CPP_TRY(conv1_forward_group(n, nets, params, ws, state, is_f16, mean_inv, B, tc_scratch, s, &took_tc));
   for (int i = 0; i < n; ++i)
-    CPP_TRY(nets[i]->forward_trunk(params[i], state, is_f16, mean_inv, B, ws[i], s, first_conv, tc_ok ? tc_scratch : nullptr));
+    CPP_TRY(nets[i]->forward_trunk(params[i], state, is_f16, mean_inv, B, ws[i], s, took_tc, took_tc ? tc_scratch : nullptr));
   return CPP_OK;
 }
 

@@ -43,7 +43,9 @@ struct Net {
                     cudaStream_t s, int first_conv = 0, void* tc_scratch = nullptr) const;
   // does this network take the tensor-core route for a state of this dtype (same answer in forward and backward)
   bool tc_route(int is_f16) const;
-  int forward_fc(const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s, int first_fc = 0) const;
+  // layers [first_fc, end_fc) (end_fc < 0: to the last one; `out` is only written when the last layer is included)
+  int forward_fc(const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s, int first_fc = 0,
+                 int end_fc = -1) const;
   // grads == nullptr: only d_action is produced (stops at the concat layer).  defer_conv1: stop in front of conv1's
   // weight gradient (its input gradient d(pooled1) stays in ws) so that conv1_wgrad_group can do it for all siblings.
   // wg_scratch != NULL on the tensor-core route: conv2/conv3 weight gradients from the fp16 piece copies (conv_wgrad_mma.cu);
@@ -60,6 +62,10 @@ struct Net {
 int64_t trunk_group_scratch_bytes(int n, const Net& net);
 int trunk_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
                         int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s);
+// the two halves of trunk_forward_group, for callers that run the per-network tails on separate streams:
+// conv1 of all siblings (*took_tc = 1 when the tensor-core kernel ran), then Net::forward_trunk(first_conv = *took_tc)
+int conv1_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
+                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s, int* took_tc);
 bool conv1_tc_enabled();
 void set_conv1_tc_enabled(int on);     // -1: back to the CARTPOLEPP_CONV1 environment default
 // conv1 weight/bias gradients of n sibling networks whose backward passes were run with defer_conv1 (tensor cores,
