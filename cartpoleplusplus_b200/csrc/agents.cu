@@ -3,6 +3,7 @@
 // Every step is "backward" (forward + loss + gradients into the flat gradient buffer) followed by
 // "apply" (global-norm clip + optimiser); a data-parallel host all-reduces the flat buffer in between.
 #include <algorithm>
+#include <stdlib.h>
 #include "agents.cuh"
 
 namespace cpp {
@@ -44,6 +45,9 @@ void DDPG::carve(void* ws, bool assign) {
   void* ts1 = cv.take<char>((size_t)trunk_group_scratch_bytes(2, actor));
   void* ts2 = cv.take<char>((size_t)trunk_group_scratch_bytes(2, actor));
   void* wgs = cv.take<char>((size_t)std::max(conv1_wgrad_group_scratch_bytes(1, actor), conv1_wgrad_group_scratch_bytes(2, actor)));
+  void* wgs2 = cv.take<char>((size_t)std::max(conv1_wgrad_group_scratch_bytes(1, actor), conv1_wgrad_group_scratch_bytes(2, actor)));
+  void* ts3 = cv.take<char>((size_t)trunk_group_scratch_bytes(2, actor));
+  void* ts4 = cv.take<char>((size_t)trunk_group_scratch_bytes(2, actor));
   float* mu_ = cv.take<float>((size_t)B * A); float* dqda_ = cv.take<float>((size_t)B * A); float* neg_ = cv.take<float>((size_t)B * A);
   float* mu2_ = cv.take<float>((size_t)B * A);
   float* q_ = cv.take<float>(B); float* q2_ = cv.take<float>(B); float* td_ = cv.take<float>(B); float* dq_ = cv.take<float>(B);
@@ -53,7 +57,8 @@ void DDPG::carve(void* ws, bool assign) {
   float* sc = cv.take<float>(4);
   ws_bytes = cv.off;
   if (assign) {
-    ws_actor = wa; ws_critic = wc; ws_target = wt; ws_target2 = wt2; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; mu = mu_; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
+    ws_actor = wa; ws_critic = wc; ws_target = wt; ws_target2 = wt2; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; mu = mu_;
+    tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts2; tcs[3] = ts4; this->wgs[0] = wgs; this->wgs[1] = wgs2; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
     ones = ones_; mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
   }
 }
@@ -67,6 +72,7 @@ int DDPG::bind(const cpp_ddpg_buffers& b) {
   buf = b; bound = true;
   carve(b.workspace, true);
   ones_ready = false; pinned1 = pinned2 = nullptr;
+  for (auto& g : graph) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = 0; }
   return CPP_OK;
 }
 
@@ -157,38 +163,138 @@ int DDPG::critic_backward(const void* s1, const float* action, const float* rewa
   return CPP_OK;
 }
 
+static int g_use_streams = -1, g_use_graphs = -1;     // -1: environment default (CARTPOLEPP_STREAMS / CARTPOLEPP_GRAPHS, on unless "0")
+void set_step_options(int streams, int graphs) { if (streams >= -1) g_use_streams = streams; if (graphs >= -1) g_use_graphs = graphs; }
+static bool env_flag(const char* name) { const char* e = getenv(name); return !(e && e[0] == '0'); }
+static bool use_streams() { static const bool d = env_flag("CARTPOLEPP_STREAMS"); return g_use_streams < 0 ? d : g_use_streams != 0; }
+static bool use_graphs() { static const bool d = env_flag("CARTPOLEPP_GRAPHS"); return g_use_graphs < 0 ? d : g_use_graphs != 0; }
+
+DDPG::~DDPG() {
+  for (auto& g : graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (streams_ready) {
+    for (auto& st : side) if (st) cudaStreamDestroy(st);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+  }
+}
+
+int DDPG::ensure_streams() {
+  if (streams_ready) return CPP_OK;
+  for (auto& st : side) CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  for (auto& e : ev) CPP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  streams_ready = true;
+  return CPP_OK;
+}
+
+int DDPG::step_body(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                    int B, int B_global, bool with_apply, bool multi, cudaStream_t s0) {
+  const int A = critic.action_dim, ca = critic.concat_at;
+  cudaStream_t sc = multi ? side[0] : s0, sta = multi ? side[1] : s0, stc = multi ? side[2] : s0;
+  enum { E_FORK = 0, E_MU, E_DQDA, E_MU2, E_Q2, E_CB, E_TA };
+  auto record = [&](int e, cudaStream_t st) -> int { if (multi) CPP_CHECK_CUDA(cudaEventRecord(ev[e], st)); return CPP_OK; };
+  auto wait = [&](cudaStream_t st, int e) -> int { if (multi) CPP_CHECK_CUDA(cudaStreamWaitEvent(st, ev[e], 0)); return CPP_OK; };
+  struct CapGuard { ~CapGuard() { g_cta_cap = kNumSMs; } } cap_guard;
+  const float* P = buf.params; const float* T = buf.target_params;
+
+  // ---- shared passes over the pixels: whitening statistics and conv1 of {actor, critic}(s1), {targets}(s2); whole GPU
+  const float *m1, *m2;
+  CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s0));
+  CPP_TRY(stats_for(s2, is_f16, B, mi2, pinned2, &m2, s0));
+  cur_m1 = m1;
+  const Net* g2[2] = {&actor, &critic};
+  int tc1 = 0, tc2 = 0;
+  {
+    const float* pp[2] = {P, P + off_c}; char* wss[2] = {ws_actor, ws_critic};
+    CPP_TRY(conv1_forward_group(2, g2, pp, wss, s1, is_f16, m1, B, tcs[0], s0, &tc1));
+    const float* pt[2] = {T, T + off_c}; char* wst[2] = {ws_target, ws_target2};
+    CPP_TRY(conv1_forward_group(2, g2, pt, wst, s2, is_f16, m2, B, tcs[2], s0, &tc2));
+  }
+  if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s0)); ones_ready = true; }
+  CPP_TRY(record(E_FORK, s0));
+  CPP_TRY(wait(sc, E_FORK)); CPP_TRY(wait(sta, E_FORK)); CPP_TRY(wait(stc, E_FORK));
+  if (multi) g_cta_cap = kNumSMs / 4;
+  // ---- actor chain (s0): trunk tail, FC stack -> mu                       ddpg_cartpole.py:90-100
+  CPP_TRY(actor.forward_trunk(P, s1, is_f16, m1, B, ws_actor, s0, tc1, tc1 ? tcs[0] : nullptr));
+  CPP_TRY(actor.forward_fc(P, nullptr, B, ws_actor, mu, s0));
+  CPP_TRY(record(E_MU, s0));
+  // ---- critic chain (sc): trunk tail, FC below the action concat, then Q(s1, mu(s1)) and dQ/da      :161-184,220-222
+  CPP_TRY(critic.forward_trunk(P + off_c, s1, is_f16, m1, B, ws_critic, sc, tc1, tc1 ? tcs[1] : nullptr));
+  if (ca > 0) CPP_TRY(critic.forward_fc(P + off_c, nullptr, B, ws_critic, nullptr, sc, 0, ca));
+  CPP_TRY(wait(sc, E_MU));
+  CPP_TRY(critic.forward_fc(P + off_c, mu, B, ws_critic, nullptr, sc, ca > 0 ? ca : 0));
+  CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, sc));
+  CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, sc));                       // tf.neg(...), :113
+  CPP_TRY(record(E_DQDA, sc));
+  // ---- target actor chain (sta) -> mu2, target critic chain (stc) -> q2                            :198-202
+  CPP_TRY(actor.forward_trunk(T, s2, is_f16, m2, B, ws_target, sta, tc2, tc2 ? tcs[2] : nullptr));
+  CPP_TRY(actor.forward_fc(T, nullptr, B, ws_target, mu2, sta));
+  CPP_TRY(record(E_MU2, sta));
+  CPP_TRY(critic.forward_trunk(T + off_c, s2, is_f16, m2, B, ws_target2, stc, tc2, tc2 ? tcs[3] : nullptr));
+  if (ca > 0) CPP_TRY(critic.forward_fc(T + off_c, nullptr, B, ws_target2, nullptr, stc, 0, ca));
+  CPP_TRY(wait(stc, E_MU2));
+  CPP_TRY(critic.forward_fc(T + off_c, mu2, B, ws_target2, q2, stc, ca > 0 ? ca : 0));
+  CPP_TRY(record(E_Q2, stc));
+  // ---- backward chains: actor on s0, critic on sc
+  if (multi) g_cta_cap = kNumSMs / 2;
+  CPP_TRY(wait(s0, E_DQDA));
+  CPP_TRY(actor.backward(P, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s0, 1, wgs[0], tcs[0]));
+  CPP_TRY(wait(sc, E_Q2));
+  CPP_TRY(critic.forward_fc(P + off_c, action, B, ws_critic, q, sc, ca > 0 ? ca : 0));   // Q(s1, a_batch): only the layers above the concat
+  CPP_TRY(launch_td_mse(q, q2, reward, mask, cfg.discount, B, B_global, td, dq, buf.grads + off_loss, sc));
+  CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, sc, 1, wgs[1], tcs[1]));
+  CPP_TRY(record(E_CB, sc));
+  CPP_TRY(wait(s0, E_CB));
+  g_cta_cap = kNumSMs;
+  // ---- conv1 weight gradients of both networks in one pass over state_1; whole GPU
+  {
+    char* wss[2] = {ws_actor, ws_critic}; float* gr[2] = {buf.grads, buf.grads + off_c};
+    CPP_TRY(conv1_wgrad_group(2, g2, wss, gr, s1, is_f16, m1, B, wgs[0], s0));
+  }
+  if (with_apply) { CPP_TRY(actor_apply(s0)); CPP_TRY(critic_apply(s0)); }
+  return CPP_OK;
+}
+
+int DDPG::step(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+               int B, int B_global, bool with_apply, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  critic_trunk_valid = false;
+  const bool multi = use_streams();
+  if (multi || use_graphs()) CPP_TRY(ensure_streams());
+  if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
+  GraphSlot& G = graph[with_apply ? 1 : 0];
+  const void* key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, s};
+  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, conv1_tc_enabled() ? 1 : 0};
+  bool same = G.seen > 0;
+  for (int i = 0; i < 8 && same; ++i) same = G.key[i] == key[i];
+  for (int i = 0; i < 5 && same; ++i) same = G.ikey[i] == ikey[i];
+  if (same && G.exec != nullptr) { CPP_CHECK_CUDA(cudaGraphLaunch(G.exec, s)); g_launch_count += G.launches; return CPP_OK; }
+  if (!same) {                      // new argument set: run it eagerly once (validates, configures kernels), capture on the next call
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    for (int i = 0; i < 8; ++i) G.key[i] = key[i];
+    for (int i = 0; i < 5; ++i) G.ikey[i] = ikey[i];
+    G.seen = 1;
+    return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
+  }
+  // second call with the same arguments: capture the fork/join structure once, replay from now on
+  CPP_CHECK_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+  const long long launches_before = g_launch_count;
+  const int st = step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, cap_stream);
+  cudaGraph_t gr = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(cap_stream, &gr);
+  if (st != CPP_OK) { if (gr) cudaGraphDestroy(gr); G.seen = 0; return st; }
+  if (ce != cudaSuccess) { G.seen = 0; set_error("graph capture failed: %s", cudaGetErrorString(ce)); return CPP_ERR_CUDA; }
+  G.launches = (int)(g_launch_count - launches_before);
+  const cudaError_t ie = cudaGraphInstantiate(&G.exec, gr, 0);
+  cudaGraphDestroy(gr);
+  if (ie != cudaSuccess) { G.exec = nullptr; G.seen = 0; set_error("graph instantiate failed: %s", cudaGetErrorString(ie)); return CPP_ERR_CUDA; }
+  CPP_CHECK_CUDA(cudaGraphLaunch(G.exec, s));
+  return CPP_OK;
+}
+
 int DDPG::step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
                         int is_f16, int B, int B_global, cudaStream_t s) {
-  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
-  const int A = critic.action_dim;
-  const float* m1;
-  CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
-  cur_m1 = m1;
-  {
-    const Net* g[2] = {&actor, &critic};
-    const float* pp[2] = {buf.params, buf.params + off_c};
-    char* wss[2] = {ws_actor, ws_critic};
-    CPP_TRY(trunk_forward_group(2, g, pp, wss, s1, is_f16, m1, B, tc_scr1, s));
-  }
-  // ---- actor.train(state_1): ddpg_cartpole.py:102-119,140-145
-  CPP_TRY(actor.forward_fc(buf.params, nullptr, B, ws_actor, mu, s));
-  CPP_TRY(critic.forward_fc(buf.params + off_c, mu, B, ws_critic, nullptr, s));
-  if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s)); ones_ready = true; }
-  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, s));
-  CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, s));
-  CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s, 1, wg_scr, tc_scr1));
-  // ---- critic.train(batch): :186-218,230-237.  The critic trunk on state_1 is the one computed above (the critic's
-  // parameters have not changed); only the layers from the action concat upwards are re-evaluated at the batch actions.
-  critic_trunk_valid = true; trunk_B = B;
-  CPP_TRY(critic_forward_td(s1, action, reward, mask, s2, is_f16, B, B_global, true, td, dq, buf.grads + off_loss, s));
-  CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s, 1, wg_scr, tc_scr1));
-  // ---- conv1 weight gradients of both networks in one pass over state_1
-  {
-    const Net* g[2] = {&actor, &critic}; char* wss[2] = {ws_actor, ws_critic}; float* gr[2] = {buf.grads, buf.grads + off_c};
-    CPP_TRY(conv1_wgrad_group(2, g, wss, gr, s1, is_f16, m1, B, wg_scr, s));
-  }
-  critic_trunk_valid = false;
-  return CPP_OK;
+  return step(s1, action, reward, mask, s2, is_f16, B, B_global, false, s);
 }
 
 int DDPG::critic_apply(cudaStream_t s) {

@@ -4,6 +4,8 @@
 
 namespace cpp {
 
+void set_step_options(int streams, int graphs);   // -1 = environment default, -2 = leave unchanged
+
 struct DDPG {
   cpp_ddpg_config cfg;
   Net actor, critic;
@@ -37,6 +39,29 @@ struct DDPG {
   // depend on the actor update, so actor.train(s1); critic.train(batch) can share every pass over state_1
   int step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
                     int B, int B_global, cudaStream_t s);
+  // with_apply: clip + SGD of both networks appended (single-GPU train step in ONE graph launch)
+  int step(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+           int B, int B_global, bool with_apply, cudaStream_t s);
+  // the enqueue-only body of a step: four independent chains (actor, critic, target actor, target critic) forked onto
+  // side streams between the shared conv1 passes; captured into a CUDA graph after one eager run
+  int step_body(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                int B, int B_global, bool with_apply, bool multi, cudaStream_t s);
+  int ensure_streams();
+  ~DDPG();
+  // streams / graph state
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t cap_stream = nullptr;                      // origin stream of the graph capture (the caller's may be the legacy default stream)
+  cudaEvent_t ev[8] = {};
+  bool streams_ready = false;
+  void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};   // packed-weight scratch per chain (actor, critic, target actor, target critic)
+  void* wgs[2] = {nullptr, nullptr};                      // weight-gradient partials per backward chain
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    const void* key[8] = {};
+    int ikey[5] = {};
+    int seen = 0;
+    int launches = 0;                                     // kernels inside the captured step (for cpp_launch_count)
+  } graph[2];                                             // [0] backward only, [1] backward + apply
   int check_loss(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
                  float* loss, float* td_out, float* q_out, cudaStream_t s);
   int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);

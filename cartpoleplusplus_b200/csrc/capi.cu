@@ -43,6 +43,8 @@ int cpp_set_option(const char* name, int32_t value) {
   API_BEGIN
   NEED(name);
   if (strcmp(name, "conv1_tc") == 0) { set_conv1_tc_enabled(value); return CPP_OK; }
+  if (strcmp(name, "streams") == 0) { set_step_options(value, -2); return CPP_OK; }
+  if (strcmp(name, "graphs") == 0) { set_step_options(-2, value); return CPP_OK; }
   set_error("unknown option `%s`", name);
   return CPP_ERR_INVALID;
   API_END
@@ -283,6 +285,13 @@ int cpp_ddpg_step_backward(cpp_ddpg* a, const void* s1, const float* action, con
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
   CPP_REQUIRE(B_global >= B, "B_global %d < B %d", B_global, B);
   return a->a.step_backward(s1, action, reward, mask, s2, is_f16, B, B_global, ST(stream));
+  API_END
+}
+int cpp_ddpg_train_step(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask,
+                        const void* s2, int32_t is_f16, int32_t B, void* stream) {
+  API_BEGIN
+  NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
+  return a->a.step(s1, action, reward, mask, s2, is_f16, B, B, true, ST(stream));
   API_END
 }
 int cpp_ddpg_step_apply(cpp_ddpg* a, void* stream) {

@@ -269,6 +269,12 @@ class DDPGEngine(EngineBase):
     if moments is not None:
       _lib.check(self.lib.cpp_ddpg_set_moments(self.handle, _lib.ptr(moments[0]), _lib.ptr(moments[1])))
     Bg = B * self.world_size
+    if self.dp is None and self.world_size == 1:
+      _lib.check(self.lib.cpp_ddpg_train_step(self.handle, _lib.ptr(s1), _lib.ptr(a), _lib.ptr(r), _lib.ptr(m), _lib.ptr(s2),
+                                              state_flag(s1), B, st))
+      if moments is not None:
+        _lib.check(self.lib.cpp_ddpg_set_moments(self.handle, None, None))
+      return
     _lib.check(self.lib.cpp_ddpg_step_backward(self.handle, _lib.ptr(s1), _lib.ptr(a), _lib.ptr(r), _lib.ptr(m), _lib.ptr(s2),
                                                state_flag(s1), B, Bg, st))
     if self.dp is not None:

@@ -43,7 +43,9 @@ const char* cpp_last_error(void);
 int64_t cpp_launch_count(void);
 
 /* runtime switches (tests and A/B timing): "conv1_tc" = 1 routes conv1 forward / weight gradient of fp16 states through the
- * tensor-core kernels (default, also CARTPOLEPP_CONV1=tc), 0 through the exact-fp32 CUDA-core kernels, -1 = environment default */
+ * tensor-core kernels (default, also CARTPOLEPP_CONV1=tc), 0 through the exact-fp32 CUDA-core kernels, -1 = environment default;
+ * "streams" = 1 forks the independent chains of a fused DDPG step onto side streams (CARTPOLEPP_STREAMS), "graphs" = 1
+ * replays a fused step as one CUDA graph (CARTPOLEPP_GRAPHS); both default on */
 int cpp_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------ a1: index sampling (host)
@@ -225,6 +227,10 @@ int cpp_ddpg_critic_train(cpp_ddpg* a, const void* s1, const float* action, cons
 int cpp_ddpg_step_backward(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask,
                            const void* s2, int32_t is_f16, int32_t B, int32_t B_global, void* stream);
 int cpp_ddpg_step_apply(cpp_ddpg* a, void* stream);
+/* both of the above in one call (single replica): after one eager run per argument set the whole step - four chains on
+ * forked streams between the shared conv1 passes - is replayed as ONE CUDA graph launch */
+int cpp_ddpg_train_step(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask,
+                        const void* s2, int32_t is_f16, int32_t B, void* stream);
 /* out: loss f32[1], td f32[B], q f32[B] (dev) */
 int cpp_ddpg_check_loss(cpp_ddpg* a, const void* s1, const float* action, const float* reward,
                         const float* mask, const void* s2, int32_t is_f16, int32_t B,

@@ -290,3 +290,34 @@ def test_step_is_deterministic():
       nets["actor"].train(b.state_1); nets["critic"].train(b)
     outs.append(eng.buffers["params"].cpu().numpy())
   assert np.array_equal(outs[0], outs[1])
+
+
+def _set_opt(name, v):
+  from cartpoleplusplus_b200 import _lib
+  _lib.check(_lib.lib().cpp_set_option(name.encode(), int(v)))
+
+
+def test_ddpg_fused_step_streams_and_graph_replay():
+  """the fused train step on forked streams + CUDA-graph replay (eager, capture, replay, replay) gives the results of
+  the single-stream eager path, and is bit-reproducible"""
+  shape, B = (32, 32, 3, 1, 3), 32
+  P, batch = _oracle_ddpg(shape, True, B, 21)
+  values = {k: v.numpy() for k, v in P.items()}
+  dev_batch = U.Batch(*[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in batch])
+  outs = []
+  try:
+    for streams, graphs in ((0, 0), (1, 1), (1, 1), (0, 1), (1, 0)):
+      _set_opt("streams", streams); _set_opt("graphs", graphs)
+      nets, eng, o = U.make_ddpg(shape, True, values, batch_size=B)
+      for i in range(5):
+        eng.train_step(dev_batch)
+        if i == 2:
+          eng.update_targets()
+      torch.cuda.synchronize()
+      outs.append(torch.cat([eng.buffers["params"], eng.buffers["target_params"], eng.buffers["grads"]]).cpu().numpy())
+  finally:
+    _set_opt("streams", -1); _set_opt("graphs", -1)
+  assert np.array_equal(outs[1], outs[2])                                  # same mode twice: identical bits
+  for k in (1, 3, 4):
+    U.assert_close(outs[k][:-4], outs[0][:-4], tol=2e-6, what="mode %d vs single-stream eager" % k)
+    U.assert_close(outs[k][-4], outs[0][-4], tol=2e-6, what="loss")
