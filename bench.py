@@ -226,14 +226,16 @@ def run_native(args):
 
     def e2e_step(i):
       b = host[i % len(host)]
-      eng.train_step(b)                      # == actor.train(b.state_1); critic.train(b): stages the host batch (H2D)
+      eng.train_step(b)                      # == actor.train(b.state_1); critic.train(b): H2D of this batch unless prefetched
+      eng.prefetch(host[(i + 1) % len(host)])   # the next batch's H2D copy overlaps this step's kernels (copy stream)
       if (i + 1) % BATCHES_PER_STEP == 0:
         eng.update_targets()
       losses.append(eng.last_loss())         # D2H read of the step's loss (syncs, like Session.run returning)
 
     ems, _, _ = timed(e2e_step, args.steps, W)
     e2e = dict(value=G * args.steps / (ems / 1e3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
-               ms_per_step=ems / args.steps, api="DDPGEngine.train_step(Batch of pinned host tensors) + last_loss()")
+               ms_per_step=ems / args.steps, api="DDPGEngine.train_step(Batch of pinned host tensors) + prefetch(next batch) + last_loss(); every batch is "
+                   "copied host->device inside the timed region, overlapped with the previous step")
 
   # ---- roofline of the dominant tensor-core kernel: conv1 forward of actor+critic on state_1 in one tcgen05 pass
   # (5x5, 9 -> 2x10 ch, 64x64, B=256), timed alone with CUDA events on the launching stream, L2 flushed in between

@@ -92,7 +92,13 @@ class EngineBase(object):
     _require_cuda()
     self.lib = _lib.lib()
     self.device = torch.device("cuda", torch.cuda.current_device())
-    self.stage = DeviceStager(self.device)
+    # two staging slots: while a step computes out of one, prefetch() fills the other on a copy stream
+    self._stagers = [DeviceStager(self.device), DeviceStager(self.device)]
+    self._slot = 0
+    self.stage = self._stagers[0]
+    self._copy_stream = None
+    self._slot_free = [None, None]       # event: the compute stream is done reading this slot
+    self._prefetched = None              # (batch object, staged tensors, copy-done event, slot)
     self.parts = {}           # part name -> (buffer name, offset, size)
     self.buffers = {}
 
@@ -106,3 +112,41 @@ class EngineBase(object):
   @staticmethod
   def _f(x):
     return C.c_float(float(x))
+
+
+  # ---- double-buffered input staging ---------------------------------------------------------------------------------
+  def prefetch(self, batch):
+    """start the host->device copy of `batch` (a Batch of host arrays / pinned tensors) on a copy stream so that it overlaps
+    the step that is computing now; the next train_step(batch) called with this very object uses the staged copy"""
+    if self._copy_stream is None:
+      self._copy_stream = torch.cuda.Stream(device=self.device)
+    slot = 1 - self._slot
+    st = self._stagers[slot]
+    cs = self._copy_stream
+    if self._slot_free[slot] is not None:
+      cs.wait_event(self._slot_free[slot])          # a step that read this slot must have finished with it
+    with torch.cuda.stream(cs):
+      staged = (st("s1", batch.state_1), st("a", batch.action, torch.float32), st("r", batch.reward, torch.float32),
+                st("m", batch.terminal_mask, torch.float32), st("s2", batch.state_2))
+      done = torch.cuda.Event()
+      done.record(cs)
+    self._prefetched = (batch, staged, done, slot)
+
+  def _staged(self, batch):
+    """-> (s1, a, r, m, s2) device tensors of `batch`: the prefetched copy when there is one, else staged now"""
+    pf, self._prefetched = self._prefetched, None
+    if pf is not None and pf[0] is batch:
+      torch.cuda.current_stream().wait_event(pf[2])
+      self._slot = pf[3]
+      self.stage = self._stagers[self._slot]
+      return pf[1]
+    st = self.stage
+    return (st("s1", batch.state_1), st("a", batch.action, torch.float32), st("r", batch.reward, torch.float32),
+            st("m", batch.terminal_mask, torch.float32), st("s2", batch.state_2))
+
+  def _release_slot(self):
+    """call after the step's work is enqueued: marks when the current staging slot may be overwritten"""
+    ev = self._slot_free[self._slot]
+    if ev is None:
+      ev = self._slot_free[self._slot] = torch.cuda.Event()
+    ev.record()

@@ -72,7 +72,7 @@ int DDPG::bind(const cpp_ddpg_buffers& b) {
   buf = b; bound = true;
   carve(b.workspace, true);
   ones_ready = false; pinned1 = pinned2 = nullptr;
-  for (auto& g : graph) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = 0; }
+  for (auto& gm : graph) for (auto& g : gm) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = 0; }
   return CPP_OK;
 }
 
@@ -170,7 +170,7 @@ static bool use_streams() { static const bool d = env_flag("CARTPOLEPP_STREAMS")
 static bool use_graphs() { static const bool d = env_flag("CARTPOLEPP_GRAPHS"); return g_use_graphs < 0 ? d : g_use_graphs != 0; }
 
 DDPG::~DDPG() {
-  for (auto& g : graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& gm : graph) for (auto& g : gm) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (streams_ready) {
     for (auto& st : side) if (st) cudaStreamDestroy(st);
     if (cap_stream) cudaStreamDestroy(cap_stream);
@@ -262,12 +262,22 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   const bool multi = use_streams();
   if (multi || use_graphs()) CPP_TRY(ensure_streams());
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
-  GraphSlot& G = graph[with_apply ? 1 : 0];
-  const void* key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, s};
+  const void* key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
   const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, conv1_tc_enabled() ? 1 : 0};
-  bool same = G.seen > 0;
-  for (int i = 0; i < 8 && same; ++i) same = G.key[i] == key[i];
-  for (int i = 0; i < 5 && same; ++i) same = G.ikey[i] == ikey[i];
+  // a few argument sets are kept (double-buffered staging alternates between two input buffer sets); least recently used goes
+  GraphSlot* slots = graph[with_apply ? 1 : 0];
+  GraphSlot* hit = nullptr; GraphSlot* lru = &slots[0];
+  for (int k = 0; k < 4; ++k) {
+    GraphSlot& c = slots[k];
+    bool eq = c.seen > 0;
+    for (int i = 0; i < 8 && eq; ++i) eq = c.key[i] == key[i];
+    for (int i = 0; i < 5 && eq; ++i) eq = c.ikey[i] == ikey[i];
+    if (eq) { hit = &c; break; }
+    if (c.used < lru->used) lru = &c;
+  }
+  const bool same = hit != nullptr;
+  GraphSlot& G = same ? *hit : *lru;
+  G.used = ++graph_clock;
   if (same && G.exec != nullptr) { CPP_CHECK_CUDA(cudaGraphLaunch(G.exec, s)); g_launch_count += G.launches; return CPP_OK; }
   if (!same) {                      // new argument set: run it eagerly once (validates, configures kernels), capture on the next call
     if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }

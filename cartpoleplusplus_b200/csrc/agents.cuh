@@ -59,9 +59,10 @@ struct DDPG {
     cudaGraphExec_t exec = nullptr;
     const void* key[8] = {};
     int ikey[5] = {};
-    int seen = 0;
+    int seen = 0, used = 0;
     int launches = 0;                                     // kernels inside the captured step (for cpp_launch_count)
-  } graph[2];                                             // [0] backward only, [1] backward + apply
+  } graph[2][4];                                          // [0] backward only, [1] backward + apply; a few argument sets each
+  int graph_clock = 0;
   int check_loss(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
                  float* loss, float* td_out, float* q_out, cudaStream_t s);
   int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) wgrad_absmax_kernel(const __grid_constant
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < 8; ++i) m = fmaxf(m, sh[i]);
-    atomicMax(reinterpret_cast<int*>(P.gmax + net), __float_as_int(m));      // non-negative floats order like ints
+    atomicMax(reinterpret_cast<int*>(P.gmax_own + net), __float_as_int(m));      // non-negative floats order like ints
   }
 }
 
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
 
   __shared__ float s_scale[kMaxNets];
   __shared__ int s_pk[8][8];                    // packed planes: entry (j, e) -> kx | channel << 8 (kx = 255: unused entry)
-  if (tid < kMaxNets) s_scale[tid] = tid < nets ? scale_for(P.gmax[tid]) : 1.f;
+  if (tid < kMaxNets) s_scale[tid] = tid < nets ? scale_for(P.gmax[tid][0]) : 1.f;
   if (tid < 64) {
     const int E = tid, kx = P.R > 0 ? E / P.R : 255;
     s_pk[tid >> 3][tid & 7] = (P.R > 0 && kx < KS) ? (kx | ((8 * P.G8 + E - kx * P.R) << 8)) : 255;
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const __grid_consta
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.nets * (nw + CO)) return;
   const int net = i / (nw + CO), j = i - net * (nw + CO);
-  const float inv_scale = 1.f / scale_for(P.gmax[net]);
+  const float inv_scale = 1.f / scale_for(P.gmax[net][0]);
   if (j >= nw) {                                                          // bias gradient: constant-one channel, centre tap
     const int o = j - nw, row = row_of(P, P.PAD, P.PAD, P.C);
     const float s = g_at(P, row, net * 2 * CO + o) + g_at(P, row, (net * 2 + 1) * CO + o);
@@ -502,7 +502,7 @@ static int launch_nt(const Plan& P, cudaStream_t s) {
 
 int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int nets, const float* const* d_pooled,
                           const uint8_t* const* amax, int B, int H, int W, int C, int KS, float* const* dw, float* const* db,
-                          void* scratch, cudaStream_t s) {
+                          void* scratch, cudaStream_t s, const float* const* gmax_pre) {
   if (B <= 0) return CPP_OK;
   Plan P{};
   CPP_TRY(build_plan(nets, B, H, W, C, KS, &P));
@@ -514,11 +514,12 @@ int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int
     P.g[n] = d_pooled[n]; P.amax[n] = amax[n]; P.dw[n] = dw[n]; P.db[n] = db[n];
   }
   char* sc = reinterpret_cast<char*>(scratch);
-  P.gmax = reinterpret_cast<float*>(sc); sc += al256(16);
+  P.gmax_own = reinterpret_cast<float*>(sc); sc += al256(16);
+  for (int n = 0; n < nets; ++n) P.gmax[n] = gmax_pre ? gmax_pre[n] : P.gmax_own + n;
   P.partials = reinterpret_cast<float*>(sc); sc += al256((size_t)2 * kNumSMs * P.part_floats * 4);
   P.gsum = reinterpret_cast<float*>(sc);
-  CPP_CHECK_CUDA(cudaMemsetAsync(P.gmax, 0, 16, s));
-  {
+  if (gmax_pre == nullptr) {
+    CPP_CHECK_CUDA(cudaMemsetAsync(P.gmax_own, 0, 16, s));
     const int64_t n = (int64_t)B * P.PH * P.PW * CO;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, ceil_div(n, 256 * 8)));
     wgrad_absmax_kernel<<<dim3(blocks, nets), 256, 0, s>>>(P);

@@ -26,7 +26,8 @@ struct Plan {
   const uint8_t* amax[kMaxNets];   // argmax side band of the forward pass
   float* dw[kMaxNets];             // HWIO [KS][KS][Cout_in][10]
   float* db[kMaxNets];             // [10]
-  float* gmax;                     // [nets] max |g| (device scratch, filled by the absmax kernel)
+  const float* gmax[kMaxNets];     // max |g| per network (device; filled by the absmax kernel here or handed in by the caller)
+  float* gmax_own;                 // [nets] scratch the absmax kernel writes when the caller has no precomputed maxima
   float* partials;                 // [grid][part_floats] per-CTA partial sums, thread-native order
   float* gsum;                     // [part_floats] reduced over CTAs
   int B, H, W, C, KS, PAD, PH, PW, nets;
@@ -49,7 +50,7 @@ int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS);
 // dw_n, db_n of the layer for every sibling network; x fp16 (exact pixels, or hi|lo pieces when dup); scratch 256-byte aligned
 int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int nets, const float* const* d_pooled,
                           const uint8_t* const* amax, int B, int H, int W, int C, int KS, float* const* dw, float* const* db,
-                          void* scratch, cudaStream_t s);
+                          void* scratch, cudaStream_t s, const float* const* gmax_pre = nullptr);
 
 }  // namespace wg
 }  // namespace cpp

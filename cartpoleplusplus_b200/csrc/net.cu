@@ -300,23 +300,27 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     else { x = ws + L.pooled[i - 1]; xf16 = 0; mi = nullptr; }
     const uint8_t* amax = reinterpret_cast<const uint8_t*>(ws + L.amax[i]);
     if (i == 0 && defer_conv1) break;                       // gp == ws + L.dpool[1]: picked up by conv1_wgrad_group
+    // tensor-core route for conv3/conv2: the un-pool + split pass also yields max|gp|, shared by wgrad and dgrad
+    const bool tc_dg = i > 0 && tc_scratch != nullptr && tc_route(is_f16);
+    float* gsc = reinterpret_cast<float*>(ws + L.gsc);
+    if (tc_dg)
+      CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, reinterpret_cast<__half*>(ws + L.dyp), s));
     if (i > 0 && wg_scratch != nullptr && tc_route(is_f16) &&
         wg::conv_wgrad_mma_supported(1, conv[i].H, conv[i].W, 2 * kConvCout, conv[i].KS)) {
       const float* g1[1] = {gp}; const uint8_t* a1[1] = {amax};
       float* dw[1] = {grads + off_conv_w[i]}; float* db[1] = {grads + off_conv_b[i]};
+      const float* gm[1] = {gsc};
       CPP_TRY(wg::launch_conv_wgrad_mma(ws + L.hl[i - 1], nullptr, 1, 1, g1, a1, B, conv[i].H, conv[i].W, 2 * kConvCout, conv[i].KS,
-                                        dw, db, wg_scratch, s));
+                                        dw, db, wg_scratch, s, tc_dg ? gm : nullptr));
     } else {
       CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, gp, amax, B, grads + off_conv_w[i], grads + off_conv_b[i],
                                 reinterpret_cast<float*>(ws + L.wgrad), s));
     }
     if (i > 0) {
       float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
-      if (tc_scratch != nullptr && tc_route(is_f16)) {
-        float* gsc = reinterpret_cast<float*>(ws + L.gsc);
-        __half* dyp = reinterpret_cast<__half*>(ws + L.dyp);
-        CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, dyp, s));
-        CPP_TRY(tc::launch_conv_dgrad_tc(dyp, gsc + 1, params + off_conv_w[i], B, conv[i].H, conv[i].W, conv[i].KS, dx, tc_scratch, s));
+      if (tc_dg) {
+        CPP_TRY(tc::launch_conv_dgrad_tc(reinterpret_cast<__half*>(ws + L.dyp), gsc + 1, params + off_conv_w[i], B, conv[i].H, conv[i].W,
+                                         conv[i].KS, dx, tc_scratch, s));
       } else {
         CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));
       }

@@ -217,11 +217,7 @@ class DDPGEngine(EngineBase):
     self.world_size, self.rank = dp.world_size, dp.rank
 
   def _batch_args(self, batch):
-    s1 = self.stage("s1", batch.state_1)
-    s2 = self.stage("s2", batch.state_2)
-    a = self.stage("a", batch.action, torch.float32)
-    r = self.stage("r", batch.reward, torch.float32)
-    m = self.stage("m", batch.terminal_mask, torch.float32)
+    s1, a, r, m, s2 = self._staged(batch)
     B = int(s1.shape[0])
     if state_flag(s1) != state_flag(s2):
       raise TypeError("state_1 and state_2 must share a dtype")
@@ -274,12 +270,14 @@ class DDPGEngine(EngineBase):
                                               state_flag(s1), B, st))
       if moments is not None:
         _lib.check(self.lib.cpp_ddpg_set_moments(self.handle, None, None))
+      self._release_slot()
       return
     _lib.check(self.lib.cpp_ddpg_step_backward(self.handle, _lib.ptr(s1), _lib.ptr(a), _lib.ptr(r), _lib.ptr(m), _lib.ptr(s2),
                                                state_flag(s1), B, Bg, st))
     if self.dp is not None:
       self.dp.all_reduce_sum(self.buffers["grads"])        # the single gradient all-reduce of the step
     _lib.check(self.lib.cpp_ddpg_step_apply(self.handle, st))
+    self._release_slot()
     if moments is not None:
       _lib.check(self.lib.cpp_ddpg_set_moments(self.handle, None, None))
 
