@@ -148,9 +148,11 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
     if (valid) {
       const int net = n / (kPieces * CO), piece = (n / CO) % kPieces, o = n % CO;
       const float inv = A.mean_inv ? A.mean_inv[C + ch] : 1.f;
-      const int chw = ch < Cw ? ch : ch - Cw;
-      const float wv = P.dgrad ? A.w[net][(((KS - 1 - ky) * KS + (KS - 1 - kx)) * CO + o) * CO + chw]      // flipped taps, in/out swapped
-                               : A.w[net][((ky * KS + kx) * Cw + chw) * CO + o];
+      const int chw = P.in_layout == 2 ? c24_weight_channel(ch) : (ch < Cw ? ch : ch - Cw);
+      float wv = 0.f;
+      if (chw >= 0)
+        wv = P.dgrad ? A.w[net][(((KS - 1 - ky) * KS + (KS - 1 - kx)) * CO + o) * CO + chw]      // flipped taps, in/out swapped
+                     : A.w[net][((ky * KS + kx) * Cw + chw) * CO + o];
       v = wv * inv * scale;
       const __half hi = __float2half_rn(v);
       out = (piece == 0) ? hi : __float2half_rn(v - __half2float(hi));
@@ -363,15 +365,20 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
               const uint16_t pk = (uint16_t)((best[o] > 0.f ? arg[o] : 4) | ((best[o + 1] > 0.f ? arg[o + 1] : 4) << 8));
               *reinterpret_cast<uint16_t*>(ap + o) = pk;
             }
-            if (P.pooled_hl[net] != nullptr) {                     // the same values as fp16 pieces for the next layer's MMAs
-              __half2* hp = reinterpret_cast<__half2*>(P.pooled_hl[net] + 2 * base);
+            if (P.pooled_hl[net] != nullptr) {                     // the same values as fp16 pieces (24-channel layout) for the next layer
+              uint32_t hi[CO / 2], lo[CO / 2];
 #pragma unroll
               for (int o = 0; o < CO; o += 2) {
                 const float v0 = fmaxf(best[o], 0.f), v1 = fmaxf(best[o + 1], 0.f);
                 const __half h0 = __float2half_rn(fminf(v0, 65504.f)), h1 = __float2half_rn(fminf(v1, 65504.f));
-                hp[o >> 1] = __halves2half2(h0, h1);
-                hp[(CO + o) >> 1] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+                const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+                hi[o >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                lo[o >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
               }
+              uint4* hp = reinterpret_cast<uint4*>(P.pooled_hl[net] + (base / CO) * kC24);
+              hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              hp[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              hp[2] = make_uint4(hi[4], lo[4], 0x00003C00u, 0u);   // hi8 hi9 | lo8 lo9 | 1.0 0 | 0 0
             }
           }
         }
@@ -666,8 +673,9 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   if (B <= 0) return CPP_OK;
   FwdPlan P{};
   CPP_TRY(build_plan(nets, B, H, W, C, KS, &P));
-  CPP_REQUIRE(!x_is_pieces || (C % 2 == 0 && mean_inv == nullptr), "conv_tc: piece input needs an even channel count and no whitening");
-  P.Cw = x_is_pieces ? C / 2 : C;
+  CPP_REQUIRE(x_is_pieces == 0 || (mean_inv == nullptr && C == (x_is_pieces == 2 ? kC24 : 2 * CO)), "conv_tc: piece input has 20 or 24 channels and no whitening");
+  P.Cw = x_is_pieces ? CO : C;
+  P.in_layout = x_is_pieces;
   CPP_REQUIRE(((uintptr_t)x_f16 & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
   P.x = reinterpret_cast<const __half*>(x_f16); P.rows = rows;
   P.bpack = reinterpret_cast<const __half*>(scratch);
@@ -699,7 +707,7 @@ int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const fl
   FwdPlan P{};
   CPP_TRY(build_plan(1, B, H, W, 2 * CO, KS, &P, 1));
   CPP_REQUIRE(((uintptr_t)dy_pieces & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
-  P.Cw = CO;
+  P.Cw = CO; P.in_layout = 1;
   P.x = reinterpret_cast<const __half*>(dy_pieces); P.rows = nullptr;
   P.bpack = reinterpret_cast<const __half*>(scratch);
   P.corr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(scratch) + bpack_bytes(P));

@@ -9,6 +9,13 @@ namespace tc {
 constexpr int kMaxNets = 3;     // sibling networks that read the same input (actor+critic; NAF value/mu/l)
 constexpr int kMaxPairs = 64;   // K16 MMAs per accumulator
 constexpr int kPieces = 2;      // fp16 pieces per fp32 weight (hi + lo): 22 mantissa bits
+// 24-channel piece layout of a 10-channel fp32 activation: [hi0..7 | lo0..7 | hi8 hi9 lo8 lo9 1.0 0 0 0] - every 8-channel
+// group is one aligned 16-byte vector, and the constant-one channel the weight-gradient kernel needs is already in place
+constexpr int kC24 = 24;
+__host__ __device__ inline int c24_weight_channel(int ch) { return ch < 8 ? ch : ch < 16 ? ch - 8 : ch < 18 ? ch - 8 : ch < 20 ? ch - 10 : -1; }
+__host__ __device__ inline int c24_hi(int c) { return c < 8 ? c : 8 + c; }
+__host__ __device__ inline int c24_lo(int c) { return c < 8 ? 8 + c : 10 + c; }
+constexpr int kC24One = 20;
 
 // one K8 slab of the implicit GEMM: 8 consecutive K entries that sit in ONE 16-byte shared-memory row
 struct Slab {
@@ -25,9 +32,10 @@ struct FwdPlan {
   const float* corr;        // [(2*PAD+1)^2][nets][10] bias - border-aware mean term, then [1] = 2^-S
   float* pooled[kMaxNets];
   uint8_t* amax[kMaxNets];
-  __half* pooled_hl[kMaxNets];   // optional: the pooled output again as fp16 pieces [B][PH][PW][hi(10) | lo(10)] for the next layer
+  __half* pooled_hl[kMaxNets];   // optional: the pooled output again as fp16 pieces in the 24-channel layout below, for the next layer
   int B, H, W, C, PH, PW, Pq, KS, PAD;
-  int Cw;                   // weight input channels: C, or C/2 when x holds [hi | lo] pieces of an fp32 activation
+  int Cw;                   // weight input channels: C, or 10 when x holds fp16 pieces of an fp32 activation
+  int in_layout;            // 0: plain channels; 1: [hi(10) | lo(10)]; 2: kPieceLayout24 (three aligned 16-byte vectors per pixel)
   int dgrad;                // 1: input-gradient mode - x = un-pooled output gradient pieces, taps flipped and channels transposed,
                             //    no bias / ReLU / pool: every conv position is written to the dense fp32 output pooled[n] [B][H][W][10]
   const float* out_scale;   // dgrad: device scalar the result is multiplied with (undoes the power-of-two scaling of the pieces)
@@ -54,8 +62,9 @@ struct PrepArgs {
 int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS);
 bool conv_tc_supported(int nets, int H, int W, int C, int KS);
 // y_n = maxpool2x2(relu(conv_same(whiten(x), w_n) + b_n)) for n < nets sibling networks in ONE pass over x.
-// x_is_pieces: x holds [hi(C/2) | lo(C/2)] fp16 pieces of an fp32 activation (conv2/conv3), w has C/2 input channels,
-// mean_inv must be NULL.  pooled_hl (optional, may be NULL or hold NULLs): fp16 piece copy of the output.
+// x_is_pieces: 1 = x holds [hi(10) | lo(10)] fp16 pieces of an fp32 activation, 2 = the 24-channel piece layout above
+// (conv2/conv3); w has 10 input channels, mean_inv must be NULL.  pooled_hl (optional, may be NULL or hold NULLs): piece
+// copy of the output in the 24-channel layout.
 int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int nets,
                        const float* const* w, const float* const* bias, int B, int H, int W, int C, int KS,
                        float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s,

@@ -173,13 +173,32 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     ylo = max(0, y0 - PAD); yhi = min(H, y0 + BR + PAD);
   };
   // (1) global -> shared / registers, asynchronous
-  auto issue_loads = [&](int band) {
+  auto issue_loads = [&](int band, int buf) {
     int b, y0, ylo, yhi;
     band_rows_of(band, b, y0, ylo, yhi);
     const __half* src = P.x + ((size_t)b * H + ylo) * rowC;
     const int n_bytes = (yhi - ylo) * rowC * 2;
     const uint32_t dst = smem_u + L.raw;
-    if (raw_mode == 16) {
+    if (P.dup == 2) {
+      // 24-channel piece layout: every plane vector is one aligned 16-byte global vector; the zero padding is a zero-size copy
+      const int nwarps = nthr >> 5;
+      const uint32_t pl = smem_u + (uint32_t)buf * L.buf_stride + L.planes;
+      for (int lr = warp; lr < rows_in; lr += nwarps) {
+        const int y = y0 - PAD + lr;
+        const bool yok = y >= 0 && y < H;
+        const __half* rowg = P.x + ((size_t)b * H + (yok ? y : 0)) * rowC;
+        for (int lc = lane; lc < pitch; lc += 32) {
+          const int xin = lc - PAD;
+          const bool ok = yok && xin >= 0 && xin < W;
+          const __half* g = rowg + (ok ? xin : 0) * tc::kC24;
+          const uint32_t d = pl + (uint32_t)((lr * pitch + lc) * 16);
+          const int nbytes = ok ? 16 : 0;
+#pragma unroll
+          for (int v = 0; v < 3; ++v)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + (uint32_t)(v * P.plane_bytes)), "l"(g + 8 * v), "r"(nbytes) : "memory");
+        }
+      }
+    } else if (raw_mode == 16) {
       for (int i = tid * 16; i < n_bytes; i += nthr * 16)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i), "l"(reinterpret_cast<const char*>(src) + i) : "memory");
     } else if (raw_mode == 4) {
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   auto stage_dy = [&](int band, int buf) {
     int b, y0, ylo, yhi;
     band_rows_of(band, b, y0, ylo, yhi);
-    if (raw_mode == 0) {
+    if (raw_mode == 0 && P.dup != 2) {
       unsigned short* d = reinterpret_cast<unsigned short*>(smem + L.raw);
       const unsigned short* s2 = reinterpret_cast<const unsigned short*>(P.x + ((size_t)b * H + ylo) * rowC);
       for (int i = tid; i < (yhi - ylo) * rowC; i += nthr) d[i] = s2[i];
@@ -297,17 +316,17 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   const int band1 = (int)((long long)P.total_bands * (blockIdx.x + 1) / gridDim.x);
   __syncthreads();                                                         // s_scale, zeroed dY buffers
   if (band0 < band1) {
-    issue_loads(band0);
+    issue_loads(band0, 0);
     stage_dy(band0, 0);
     __syncthreads();
-    stage_planes(band0, 0);
+    if (P.dup != 2) stage_planes(band0, 0);
   }
   __syncthreads();
   int since_flush = 0;
   for (int band = band0; band < band1; ++band) {
     const int buf = (band - band0) & 1;
     const bool has_next = band + 1 < band1;
-    if (has_next) issue_loads(band + 1);
+    if (has_next) issue_loads(band + 1, buf ^ 1);
     // ---- MMAs: K runs over the band's output pixels, 16 per step
     {
       const int y0 = (band % P.bands_per_image) * BR;
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     if (has_next) {
       stage_dy(band + 1, buf ^ 1);                                         // buffer buf^1 was last read one iteration ago
       __syncthreads();                                                     // raw rows of band+1 are complete in shared memory
-      stage_planes(band + 1, buf ^ 1);
+      if (P.dup != 2) stage_planes(band + 1, buf ^ 1);
     }
     __syncthreads();                                                       // band+1 staged; every warp is done reading `buf` and raw
     if (++since_flush >= P.flush_every) { flush(); since_flush = 0; }
@@ -370,25 +389,27 @@ __device__ __forceinline__ float g_at(const Plan& P, int row, int n) {
   return P.gsum[idx];
 }
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const __grid_constant__ Plan P) {
-  const int KS = P.KS, Cr = P.dup ? P.C / 2 : P.C;
+  const int KS = P.KS, Cr = P.dup == 2 ? CO : (P.dup ? P.C / 2 : P.C);
+  const int one_ch = P.dup == 2 ? tc::kC24One : P.C;
   const int nw = KS * KS * Cr * CO;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.nets * (nw + CO)) return;
   const int net = i / (nw + CO), j = i - net * (nw + CO);
   const float inv_scale = 1.f / scale_for(P.gmax[net][0]);
   if (j >= nw) {                                                          // bias gradient: constant-one channel, centre tap
-    const int o = j - nw, row = row_of(P, P.PAD, P.PAD, P.C);
+    const int o = j - nw, row = row_of(P, P.PAD, P.PAD, one_ch);
     const float s = g_at(P, row, net * 2 * CO + o) + g_at(P, row, (net * 2 + 1) * CO + o);
     P.db[net][o] = s * inv_scale;
     return;
   }
   const int o = j % CO, c = (j / CO) % Cr, kx = (j / (CO * Cr)) % KS, ky = j / (CO * Cr * KS);
   const int n0 = net * 2 * CO + o, n1 = n0 + CO;
-  float gsum = g_at(P, row_of(P, ky, kx, c), n0) + g_at(P, row_of(P, ky, kx, c), n1);
-  if (P.dup) gsum += g_at(P, row_of(P, ky, kx, c + Cr), n0) + g_at(P, row_of(P, ky, kx, c + Cr), n1);
+  const int c_hi = P.dup == 2 ? tc::c24_hi(c) : c, c_lo = P.dup == 2 ? tc::c24_lo(c) : c + Cr;
+  float gsum = g_at(P, row_of(P, ky, kx, c_hi), n0) + g_at(P, row_of(P, ky, kx, c_hi), n1);
+  if (P.dup) gsum += g_at(P, row_of(P, ky, kx, c_lo), n0) + g_at(P, row_of(P, ky, kx, c_lo), n1);
   float v = gsum * inv_scale;
   if (P.mean_inv) {
-    const int rs = row_of(P, ky, kx, P.C);
+    const int rs = row_of(P, ky, kx, one_ch);
     const float ssum = (g_at(P, rs, n0) + g_at(P, rs, n1)) * inv_scale;
     v = P.mean_inv[P.C + c] * (v - P.mean_inv[c] * ssum);
   }
@@ -396,12 +417,14 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
+static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int dup = 0) {
   CPP_REQUIRE(KS == 5 || KS == 3, "wgrad_mma: kernel size %d", KS);
   CPP_REQUIRE(nets >= 1 && nets <= kMaxNets, "wgrad_mma: %d sibling networks", nets);
   CPP_REQUIRE(H >= 2 && W >= 2 && C >= 1, "wgrad_mma: input %dx%dx%d", H, W, C);
   P->B = B; P->H = H; P->W = W; P->C = C; P->KS = KS; P->PAD = KS / 2; P->PH = H / 2; P->PW = W / 2; P->nets = nets;
-  P->CE = C + 1;
+  P->dup = dup;
+  CPP_REQUIRE(dup != 2 || C == tc::kC24, "wgrad_mma: the aligned piece layout has %d channels", tc::kC24);
+  P->CE = dup == 2 ? C : C + 1;               // the 24-channel layout already carries its constant-one channel
   P->G8 = P->CE / 8; P->R = P->CE % 8;
   P->nR = (KS * P->R + 7) / 8;
   if (P->R > 0 && P->nR >= KS) { P->G8 += 1; P->R = 0; P->nR = 0; }          // packing along kx would not save slabs
@@ -437,7 +460,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
   if (P->NT == 4) P->NT = 5;                                                  // instantiated widths: 3, 5, 8
   if (P->NT == 6 || P->NT == 7) P->NT = 8;
   P->NTp = P->NT | 1;
-  P->raw_bytes = (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
+  P->raw_bytes = dup == 2 ? 0 : (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
   P->smem_bytes = (int)smem_layout(*P).total;
   if (P->smem_bytes > 220 * 1024) {        // wide images: two-row bands keep both staging buffers inside one SM's shared memory
     P->band_rows = 2;
@@ -448,7 +471,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
       P->slab_off[i] = sl.kind == 0 ? sl.set * P->plane_bytes + (sl.ky * P->pitch + sl.kx) * 16
                                     : (P->G8 + sl.set) * P->plane_bytes + (sl.ky * P->pitch) * 16;
     }
-    P->raw_bytes = (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
+    P->raw_bytes = dup == 2 ? 0 : (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
     P->smem_bytes = (int)smem_layout(*P).total;
   }
   CPP_REQUIRE(P->smem_bytes <= 220 * 1024, "wgrad_mma: %dx%dx%d does not fit shared memory", H, W, C);
@@ -467,14 +490,14 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P) {
 
 static inline size_t al256(size_t b) { return (size_t)round_up((int64_t)b, 256); }
 
-bool conv_wgrad_mma_supported(int nets, int H, int W, int C, int KS) {
+bool conv_wgrad_mma_supported(int nets, int H, int W, int C, int KS, int dup) {
   Plan P{};
-  return build_plan(nets, 1, H, W, C, KS, &P) == CPP_OK;
+  return build_plan(nets, 1, H, W, C, KS, &P, dup) == CPP_OK;
 }
 
-int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS) {
+int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS, int dup) {
   Plan P{};
-  if (build_plan(nets, 1, H, W, C, KS, &P) != CPP_OK) return -1;
+  if (build_plan(nets, 1, H, W, C, KS, &P, dup) != CPP_OK) return -1;
   return (int64_t)(al256(16) + al256((size_t)2 * kNumSMs * P.part_floats * 4) + al256((size_t)P.part_floats * 4));
 }
 
@@ -505,8 +528,9 @@ int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int
                           void* scratch, cudaStream_t s, const float* const* gmax_pre) {
   if (B <= 0) return CPP_OK;
   Plan P{};
-  CPP_TRY(build_plan(nets, B, H, W, C, KS, &P));
+  CPP_TRY(build_plan(nets, B, H, W, C, KS, &P, dup));
   CPP_REQUIRE(!dup || (C % 2 == 0 && mean_inv == nullptr), "wgrad_mma: piece input needs an even channel count and no whitening");
+  CPP_REQUIRE(dup != 2 || ((uintptr_t)x_f16 & 15) == 0, "wgrad_mma: unaligned piece input");
   CPP_REQUIRE(((uintptr_t)scratch & 255) == 0, "wgrad_mma: unaligned scratch");
   P.x = reinterpret_cast<const __half*>(x_f16); P.mean_inv = mean_inv; P.dup = dup;
   for (int n = 0; n < nets; ++n) {
@@ -536,7 +560,7 @@ int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int
   CPP_TRY(st);
   wgrad_reduce_kernel<<<(unsigned)ceil_div(P.part_floats, 32), dim3(32, 8), 0, s>>>(P, P.grid);
   CPP_CHECK_LAUNCH();
-  const int Cr = dup ? C / 2 : C;
+  const int Cr = dup == 2 ? CO : (dup ? C / 2 : C);
   const int total = nets * (KS * KS * Cr * CO + CO);
   wgrad_finalize_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(P);
   CPP_CHECK_LAUNCH();

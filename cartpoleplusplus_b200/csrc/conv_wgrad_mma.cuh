@@ -3,6 +3,7 @@
 // See conv_wgrad_mma.cu for the design.
 #pragma once
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace cpp {
 namespace wg {
@@ -32,6 +33,8 @@ struct Plan {
   float* gsum;                     // [part_floats] reduced over CTAs
   int B, H, W, C, KS, PAD, PH, PW, nets;
   int dup;                         // 1: x holds [hi(C/2) | lo(C/2)] fp16 pieces of an fp32 activation: dw[c] = G[c] + G[c + C/2]
+                                   // 2: x is in the 24-channel piece layout of conv_tc.cuh (aligned vectors, constant-one channel
+                                   //    included): rows go global -> shared planes with cp.async, no re-layout at all
   // ---- geometry
   int CE;                          // channels incl. the constant-one channel appended at index C
   int G8, R, nR, nvec;             // full 8-channel groups, remainder channels, packed slabs per ky, smem vectors per pixel
@@ -45,8 +48,8 @@ struct Plan {
   int32_t slab_off[kMaxSlabs];     // byte offset of the slab's row (band row 0, output column 0) inside the x planes
 };
 
-bool conv_wgrad_mma_supported(int nets, int H, int W, int C, int KS);
-int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS);
+bool conv_wgrad_mma_supported(int nets, int H, int W, int C, int KS, int dup = 0);
+int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS, int dup = 0);
 // dw_n, db_n of the layer for every sibling network; x fp16 (exact pixels, or hi|lo pieces when dup); scratch 256-byte aligned
 int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int nets, const float* const* d_pooled,
                           const uint8_t* const* amax, int B, int H, int W, int C, int KS, float* const* dw, float* const* db,

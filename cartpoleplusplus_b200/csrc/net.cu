@@ -66,7 +66,7 @@ Net::Layout Net::layout(int B) const {
       const size_t n = (size_t)B * conv[i].PH() * conv[i].PW() * kConvCout;
       L.pooled[i] = take(n * sizeof(float));
       L.amax[i] = take(n);
-      if (i < 2) L.hl[i] = take(n * 2 * sizeof(__half));       // [hi(10) | lo(10)] fp16 pieces of pooled[i]
+      if (i < 2) L.hl[i] = take(n / kConvCout * tc::kC24 * sizeof(__half));   // fp16 pieces of pooled[i], 24-channel layout (conv_tc.cuh)
     }
     // gradients wrt pooled2 / pooled1 (dense, the size of conv3 / conv2 inputs)
     L.dpool[0] = take((size_t)B * conv[2].H * conv[2].W * kConvCout * sizeof(float));
@@ -103,8 +103,8 @@ const float* Net::fc_input(const Layout& L, char* ws, int i, int* ld) const {
 
 bool Net::tc_route(int is_f16) const {
   return pixels && is_f16 && conv1_tc_enabled() && tc::conv_tc_supported(1, conv[0].H, conv[0].W, conv[0].Cin, conv[0].KS) &&
-         tc::conv_tc_supported(1, conv[1].H, conv[1].W, 2 * kConvCout, conv[1].KS) &&
-         tc::conv_tc_supported(1, conv[2].H, conv[2].W, 2 * kConvCout, conv[2].KS);
+         tc::conv_tc_supported(1, conv[1].H, conv[1].W, tc::kC24, conv[1].KS) &&
+         tc::conv_tc_supported(1, conv[2].H, conv[2].W, tc::kC24, conv[2].KS);
 }
 
 int Net::forward_trunk(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
@@ -124,8 +124,8 @@ int Net::forward_trunk(const float* params, const void* state, int is_f16, const
         const float* w[1] = {params + off_conv_w[i]}; const float* b[1] = {params + off_conv_b[i]};
         float* po[1] = {pooled}; uint8_t* am[1] = {amax};
         __half* hl[1] = {i < 2 ? reinterpret_cast<__half*>(ws + L.hl[i]) : nullptr};
-        CPP_TRY(tc::launch_conv_fwd_tc(ws + L.hl[i - 1], nullptr, nullptr, 1, w, b, B, conv[i].H, conv[i].W, 2 * kConvCout, conv[i].KS,
-                                       po, am, tc_scratch, s, 1, hl));
+        CPP_TRY(tc::launch_conv_fwd_tc(ws + L.hl[i - 1], nullptr, nullptr, 1, w, b, B, conv[i].H, conv[i].W, tc::kC24, conv[i].KS,
+                                       po, am, tc_scratch, s, 2, hl));
       } else {
         CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
       }
@@ -180,7 +180,7 @@ bool conv1_tc_enabled() {
 int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net) {
   if (!net.pixels) return 0;
   int64_t b = wg::conv_wgrad_mma_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
-  for (int i = 1; i < 3; ++i) b = std::max(b, wg::conv_wgrad_mma_scratch_bytes(1, net.conv[i].H, net.conv[i].W, 2 * kConvCout, net.conv[i].KS));
+  for (int i = 1; i < 3; ++i) b = std::max(b, wg::conv_wgrad_mma_scratch_bytes(1, net.conv[i].H, net.conv[i].W, tc::kC24, net.conv[i].KS, 2));
   return b > 0 ? b : 0;
 }
 
@@ -209,7 +209,7 @@ int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* con
 int64_t trunk_group_scratch_bytes(int n, const Net& net) {
   if (!net.pixels) return 0;
   int64_t b = tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
-  for (int i = 1; i < 3; ++i) b = std::max(b, tc::conv_tc_scratch_bytes(1, net.conv[i].H, net.conv[i].W, 2 * kConvCout, net.conv[i].KS));
+  for (int i = 1; i < 3; ++i) b = std::max(b, tc::conv_tc_scratch_bytes(1, net.conv[i].H, net.conv[i].W, tc::kC24, net.conv[i].KS));
   return b > 0 ? b : 0;
 }
 
@@ -306,11 +306,11 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     if (tc_dg)
       CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, reinterpret_cast<__half*>(ws + L.dyp), s));
     if (i > 0 && wg_scratch != nullptr && tc_route(is_f16) &&
-        wg::conv_wgrad_mma_supported(1, conv[i].H, conv[i].W, 2 * kConvCout, conv[i].KS)) {
+        wg::conv_wgrad_mma_supported(1, conv[i].H, conv[i].W, tc::kC24, conv[i].KS, 2)) {
       const float* g1[1] = {gp}; const uint8_t* a1[1] = {amax};
       float* dw[1] = {grads + off_conv_w[i]}; float* db[1] = {grads + off_conv_b[i]};
       const float* gm[1] = {gsc};
-      CPP_TRY(wg::launch_conv_wgrad_mma(ws + L.hl[i - 1], nullptr, 1, 1, g1, a1, B, conv[i].H, conv[i].W, 2 * kConvCout, conv[i].KS,
+      CPP_TRY(wg::launch_conv_wgrad_mma(ws + L.hl[i - 1], nullptr, 2, 1, g1, a1, B, conv[i].H, conv[i].W, tc::kC24, conv[i].KS,
                                         dw, db, wg_scratch, s, tc_dg ? gm : nullptr));
     } else {
       CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, gp, amax, B, grads + off_conv_w[i], grads + off_conv_b[i],

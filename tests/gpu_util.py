@@ -165,3 +165,23 @@ def assert_flat_grads_close(got_flat, want_flat, cpu32_flat, nets, tc_route, wha
     assert frac_ok >= 0.7 and e_gpu <= 5e-2, "%s %s: rel err %.3e, only %.0f %% of the entries within tolerance" % (what, n, e_gpu, 100 * frac_ok)
     worst = max(worst, e_gpu)
   return worst
+
+
+def to_c24(x32):
+  """fp32 activation (..., 10) -> the 24-channel fp16 piece layout of csrc/conv_tc.cuh:
+  [hi0..7 | lo0..7 | hi8 hi9 lo8 lo9 1.0 0 0 0]; returns (pieces fp16 (..., 24), exact fp64 value hi + lo)"""
+  x32 = np.asarray(x32, dtype=np.float32)
+  assert x32.shape[-1] == 10
+  hi = x32.astype(np.float16); lo = (x32 - hi.astype(np.float32)).astype(np.float16)
+  out = np.zeros(x32.shape[:-1] + (24,), dtype=np.float16)
+  out[..., 0:8] = hi[..., 0:8]; out[..., 8:16] = lo[..., 0:8]
+  out[..., 16:18] = hi[..., 8:10]; out[..., 18:20] = lo[..., 8:10]
+  out[..., 20] = 1.0
+  return out, hi.astype(np.float64) + lo.astype(np.float64)
+
+
+def from_c24(p):
+  """(hi, lo) fp64 (..., 10) of a 24-channel piece tensor, plus the constant channel and the padding"""
+  p = np.asarray(p).astype(np.float64)
+  hi = np.concatenate([p[..., 0:8], p[..., 16:18]], axis=-1); lo = np.concatenate([p[..., 8:16], p[..., 18:20]], axis=-1)
+  return hi, lo, p[..., 20], p[..., 21:24]

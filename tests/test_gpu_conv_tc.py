@@ -118,28 +118,28 @@ def test_conv_tc_full_batch_c3():
 
 
 def run_tc_pieces(B, H, W, KS, seed):
-  """conv2 / conv3 on the tensor cores: the input is an fp32 activation handed over as [hi | lo] fp16 pieces, the output
-  comes back as fp32 + arg-max + its own fp16 piece copy for the next layer"""
+  """conv2 / conv3 on the tensor cores: the input is an fp32 activation handed over as fp16 pieces (24-channel layout), the
+  output comes back as fp32 + arg-max + its own piece copy for the next layer"""
   L, lib = _lib()
   rs = np.random.RandomState(seed)
   dev = "cuda"
   Cin = 10
   x32 = (np.maximum(rs.randn(B, H, W, Cin), 0) * 10.0 ** rs.uniform(-2, 1)).astype(np.float32)
-  hi = x32.astype(np.float16); lo = (x32 - hi.astype(np.float32)).astype(np.float16)
-  x = torch.from_numpy(np.concatenate([hi, lo], axis=-1)).to(dev)
-  x64 = torch.from_numpy(hi.astype(np.float64) + lo.astype(np.float64)).permute(0, 3, 1, 2).contiguous()
+  x_h, x_exact = U.to_c24(x32)
+  x = torch.from_numpy(x_h).to(dev)
+  x64 = torch.from_numpy(x_exact).permute(0, 3, 1, 2).contiguous()
   lim = np.sqrt(6.0 / (KS * KS * (Cin + 10)))
   w_h = rs.uniform(-lim, lim, (KS, KS, Cin, 10)).astype(np.float32); b_h = rs.uniform(-0.1, 0.1, 10).astype(np.float32)
   w, b = torch.from_numpy(w_h).to(dev), torch.from_numpy(b_h).to(dev)
   PH, PW = H // 2, W // 2
   pooled = torch.full((B, PH, PW, 10), -7.0, dtype=torch.float32, device=dev)
   amax = torch.full((B, PH, PW, 10), 9, dtype=torch.uint8, device=dev)
-  hl = torch.full((B, PH, PW, 20), -7.0, dtype=torch.float16, device=dev)
-  nb = int(lib.cpp_conv_tc_scratch_bytes(1, H, W, 2 * Cin, KS))
+  hl = torch.full((B, PH, PW, 24), -7.0, dtype=torch.float16, device=dev)
+  nb = int(lib.cpp_conv_tc_scratch_bytes(1, H, W, 24, KS))
   assert nb > 0
   scr = torch.zeros(nb, dtype=torch.uint8, device=dev)
-  L.check(lib.cpp_conv_forward_tc(L.ptr(x), None, None, 1, L.ptr_array([w]), L.ptr_array([b]), B, H, W, 2 * Cin, KS,
-                                  L.ptr_array([pooled]), L.ptr_array([amax]), L.ptr(scr), L.stream_ptr(), 1, L.ptr_array([hl])))
+  L.check(lib.cpp_conv_forward_tc(L.ptr(x), None, None, 1, L.ptr_array([w]), L.ptr_array([b]), B, H, W, 24, KS,
+                                  L.ptr_array([pooled]), L.ptr_array([amax]), L.ptr(scr), L.stream_ptr(), 2, L.ptr_array([hl])))
   torch.cuda.synchronize()
   y = F.conv2d(x64, torch.from_numpy(w_h.astype(np.float64)).permute(3, 2, 0, 1).contiguous(), torch.from_numpy(b_h.astype(np.float64)),
                padding=KS // 2)
@@ -153,10 +153,10 @@ def run_tc_pieces(B, H, W, KS, seed):
   picked = np.take_along_axis(yw, np.minimum(a, 3)[..., None], axis=-1)[..., 0]
   scale = np.abs(yw).max()
   assert np.all(np.abs(picked - yw.max(-1))[~closed] <= 1e-5 * scale)
-  h = hl.cpu().numpy().astype(np.float64)
-  rec = h[..., :10] + h[..., 10:]
-  assert np.array_equal(h[..., :10].astype(np.float16), got.astype(np.float16))          # hi = round-to-nearest fp16 of the fp32 value
-  assert np.abs(rec - got).max() <= 2.0 ** -20 * max(np.abs(got).max(), 1e-30)
+  hi_o, lo_o, one_o, pad_o = U.from_c24(hl.cpu().numpy())
+  assert np.array_equal(hi_o.astype(np.float16), got.astype(np.float16))                 # hi = round-to-nearest fp16 of the fp32 value
+  assert np.abs(hi_o + lo_o - got).max() <= 2.0 ** -20 * max(np.abs(got).max(), 1e-30)
+  assert np.all(one_o == 1.0) and np.all(pad_o == 0.0)
   # the exact-fp32 CUDA-core kernel on the fp32 activation
   p2 = torch.zeros((B, PH, PW, 10), dtype=torch.float32, device=dev); a2 = torch.zeros((B, PH, PW, 10), dtype=torch.uint8, device=dev)
   x32d = torch.from_numpy(x32).to(dev)

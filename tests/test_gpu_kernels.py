@@ -145,7 +145,10 @@ def run_wgrad_mma(B, H, W, Cin, KS, nets, seed, sparse=False, pieces=False):
   if pieces:
     x32 = np.maximum(rs.randn(B, H, W, Cin), 0).astype(np.float32)
     hi = x32.astype(np.float16); lo = (x32 - hi.astype(np.float32)).astype(np.float16)
-    x_h = np.concatenate([hi, lo], axis=-1)
+    if pieces == 2:
+      x_h, _ = U.to_c24(x32)                                # aligned 24-channel layout (what conv_tc's epilogue writes)
+    else:
+      x_h = np.concatenate([hi, lo], axis=-1)
     x_ref32 = torch.from_numpy(x32).to(dev)
     mi = None
     x64 = torch.from_numpy(hi.astype(np.float64) + lo.astype(np.float64))
@@ -187,11 +190,11 @@ def run_wgrad_mma(B, H, W, Cin, KS, nets, seed, sparse=False, pieces=False):
     refs.append((gw64.permute(2, 3, 1, 0).numpy(), gb64.numpy()))
     gps.append(torch.from_numpy(gp_h).to(dev)); amaxs.append(torch.from_numpy(a.astype(np.uint8)).to(dev))
     dws.append(torch.full((KS, KS, Cin, 10), 7.0, dtype=torch.float32, device=dev)); dbs.append(torch.full((10,), 7.0, dtype=torch.float32, device=dev))
-  Cmem = 2 * Cin if pieces else Cin
+  Cmem = 24 if pieces == 2 else (2 * Cin if pieces else Cin)
   nb = int(lib.cpp_conv_wgrad_mma_scratch_bytes(nets, H, W, Cmem, KS))
   assert nb > 0
   scr = torch.zeros(nb, dtype=torch.uint8, device=dev)
-  L.check(lib.cpp_conv_wgrad_mma(L.ptr(x), L.ptr(mi), 1 if pieces else 0, nets, L.ptr_array(gps), L.ptr_array(amaxs), B, H, W, Cmem, KS,
+  L.check(lib.cpp_conv_wgrad_mma(L.ptr(x), L.ptr(mi), int(pieces), nets, L.ptr_array(gps), L.ptr_array(amaxs), B, H, W, Cmem, KS,
                                  L.ptr_array(dws), L.ptr_array(dbs), L.ptr(scr), L.stream_ptr()))
   torch.cuda.synchronize()
   errs = []
@@ -218,8 +221,12 @@ WGRAD = [
     (3, 50, 50, 6, 5, 2, False),      # reference default render: 50 -> Wp 64, 6+1 channels
     (3, 33, 31, 9, 5, 2, False),      # odd sizes: VALID pooling drops the last row/column, partial last band
     (2, 22, 18, 15, 5, 1, False),     # 15+1 channels: exactly two groups
-    (8, 32, 32, 10, 5, 1, True),      # conv2 from activation pieces
-    (8, 16, 16, 10, 3, 1, True),      # conv3 from activation pieces
+    (8, 32, 32, 10, 5, 1, 1),         # conv2 from [hi | lo] activation pieces
+    (8, 16, 16, 10, 3, 1, 1),         # conv3 from [hi | lo] activation pieces
+    (8, 32, 32, 10, 5, 1, 2),         # conv2 from the aligned 24-channel piece layout (cp.async straight into the planes)
+    (8, 16, 16, 10, 3, 1, 2),         # conv3, same
+    (3, 25, 25, 10, 5, 1, 2),         # odd size
+    (256, 32, 32, 10, 5, 1, 2),       # c3 conv2 at full batch
     (5, 8, 8, 3, 5, 1, False),        # smallest legal image
 ]
 
