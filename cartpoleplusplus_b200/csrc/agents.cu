@@ -4,6 +4,9 @@
 // "apply" (global-norm clip + optimiser); a data-parallel host all-reduces the flat buffer in between.
 #include <algorithm>
 #include <stdlib.h>
+#include <string>
+#include <utility>
+#include <vector>
 #include "agents.cuh"
 
 namespace cpp {
@@ -169,6 +172,33 @@ static bool env_flag(const char* name) { const char* e = getenv(name); return !(
 static bool use_streams() { static const bool d = env_flag("CARTPOLEPP_STREAMS"); return g_use_streams < 0 ? d : g_use_streams != 0; }
 static bool use_graphs() { static const bool d = env_flag("CARTPOLEPP_GRAPHS"); return g_use_graphs < 0 ? d : g_use_graphs != 0; }
 
+// CARTPOLEPP_TRACE=1: eager steps record a timing event at every chain milestone and print the timeline (us since the
+// start of the step) to stderr - the poor man's nsys for the fork/join schedule
+struct Tracer {
+  bool on = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> pts;
+  void mark(const char* label, cudaStream_t st) {
+    if (!on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    pts.emplace_back(label, e);
+  }
+  void dump() {
+    if (!on || pts.empty()) return;
+    cudaDeviceSynchronize();
+    fprintf(stderr, "---- step timeline (us)\n");
+    for (auto& p : pts) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pts[0].second, p.second);
+      fprintf(stderr, "%9.1f  %s\n", ms * 1e3f, p.first.c_str());
+    }
+    for (auto& p : pts) cudaEventDestroy(p.second);
+    pts.clear();
+  }
+};
+static bool trace_enabled() { static const bool t = [] { const char* e = getenv("CARTPOLEPP_TRACE"); return e && e[0] == '1'; }(); return t; }
+
 DDPG::~DDPG() {
   for (auto& gm : graph) for (auto& g : gm) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (streams_ready) {
@@ -195,6 +225,8 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   auto record = [&](int e, cudaStream_t st) -> int { if (multi) CPP_CHECK_CUDA(cudaEventRecord(ev[e], st)); return CPP_OK; };
   auto wait = [&](cudaStream_t st, int e) -> int { if (multi) CPP_CHECK_CUDA(cudaStreamWaitEvent(st, ev[e], 0)); return CPP_OK; };
   struct CapGuard { ~CapGuard() { g_cta_cap = kNumSMs; } } cap_guard;
+  Tracer tr; tr.on = trace_enabled() && !use_graphs();
+  tr.mark("start", s0);
   const float* P = buf.params; const float* T = buf.target_params;
 
   // ---- shared passes over the pixels: whitening statistics and conv1 of {actor, critic}(s1), {targets}(s2); whole GPU
@@ -203,12 +235,15 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   CPP_TRY(stats_for(s2, is_f16, B, mi2, pinned2, &m2, s0));
   cur_m1 = m1;
   const Net* g2[2] = {&actor, &critic};
+  tr.mark("s0 moments done", s0);
   int tc1 = 0, tc2 = 0;
   {
     const float* pp[2] = {P, P + off_c}; char* wss[2] = {ws_actor, ws_critic};
     CPP_TRY(conv1_forward_group(2, g2, pp, wss, s1, is_f16, m1, B, tcs[0], s0, &tc1));
+    tr.mark("s0 conv1 fwd {actor,critic}(s1) done", s0);
     const float* pt[2] = {T, T + off_c}; char* wst[2] = {ws_target, ws_target2};
     CPP_TRY(conv1_forward_group(2, g2, pt, wst, s2, is_f16, m2, B, tcs[2], s0, &tc2));
+    tr.mark("s0 conv1 fwd {targets}(s2) done", s0);
   }
   if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s0)); ones_ready = true; }
   CPP_TRY(record(E_FORK, s0));
@@ -216,33 +251,42 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   if (multi) g_cta_cap = kNumSMs / 4;
   // ---- actor chain (s0): trunk tail, FC stack -> mu                       ddpg_cartpole.py:90-100
   CPP_TRY(actor.forward_trunk(P, s1, is_f16, m1, B, ws_actor, s0, tc1, tc1 ? tcs[0] : nullptr));
+  tr.mark("s0 actor conv2/3 fwd done", s0);
   CPP_TRY(actor.forward_fc(P, nullptr, B, ws_actor, mu, s0));
+  tr.mark("s0 actor FC fwd done (mu)", s0);
   CPP_TRY(record(E_MU, s0));
   // ---- critic chain (sc): trunk tail, FC below the action concat, then Q(s1, mu(s1)) and dQ/da      :161-184,220-222
   CPP_TRY(critic.forward_trunk(P + off_c, s1, is_f16, m1, B, ws_critic, sc, tc1, tc1 ? tcs[1] : nullptr));
+  tr.mark("sc critic conv2/3 fwd done", sc);
   if (ca > 0) CPP_TRY(critic.forward_fc(P + off_c, nullptr, B, ws_critic, nullptr, sc, 0, ca));
   CPP_TRY(wait(sc, E_MU));
   CPP_TRY(critic.forward_fc(P + off_c, mu, B, ws_critic, nullptr, sc, ca > 0 ? ca : 0));
   CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, sc));
   CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, sc));                       // tf.neg(...), :113
+  tr.mark("sc critic FC fwd @mu + dQ/da done", sc);
   CPP_TRY(record(E_DQDA, sc));
   // ---- target actor chain (sta) -> mu2, target critic chain (stc) -> q2                            :198-202
   CPP_TRY(actor.forward_trunk(T, s2, is_f16, m2, B, ws_target, sta, tc2, tc2 ? tcs[2] : nullptr));
   CPP_TRY(actor.forward_fc(T, nullptr, B, ws_target, mu2, sta));
+  tr.mark("sta target actor done (mu2)", sta);
   CPP_TRY(record(E_MU2, sta));
   CPP_TRY(critic.forward_trunk(T + off_c, s2, is_f16, m2, B, ws_target2, stc, tc2, tc2 ? tcs[3] : nullptr));
   if (ca > 0) CPP_TRY(critic.forward_fc(T + off_c, nullptr, B, ws_target2, nullptr, stc, 0, ca));
   CPP_TRY(wait(stc, E_MU2));
   CPP_TRY(critic.forward_fc(T + off_c, mu2, B, ws_target2, q2, stc, ca > 0 ? ca : 0));
+  tr.mark("stc target critic done (q2)", stc);
   CPP_TRY(record(E_Q2, stc));
   // ---- backward chains: actor on s0, critic on sc
   if (multi) g_cta_cap = kNumSMs / 2;
   CPP_TRY(wait(s0, E_DQDA));
   CPP_TRY(actor.backward(P, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s0, 1, wgs[0], tcs[0]));
+  tr.mark("s0 actor backward (FC, conv3, conv2) done", s0);
   CPP_TRY(wait(sc, E_Q2));
   CPP_TRY(critic.forward_fc(P + off_c, action, B, ws_critic, q, sc, ca > 0 ? ca : 0));   // Q(s1, a_batch): only the layers above the concat
   CPP_TRY(launch_td_mse(q, q2, reward, mask, cfg.discount, B, B_global, td, dq, buf.grads + off_loss, sc));
+  tr.mark("sc critic FC @a + TD done", sc);
   CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, sc, 1, wgs[1], tcs[1]));
+  tr.mark("sc critic backward (FC, conv3, conv2) done", sc);
   CPP_TRY(record(E_CB, sc));
   CPP_TRY(wait(s0, E_CB));
   g_cta_cap = kNumSMs;
@@ -251,7 +295,10 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
     char* wss[2] = {ws_actor, ws_critic}; float* gr[2] = {buf.grads, buf.grads + off_c};
     CPP_TRY(conv1_wgrad_group(2, g2, wss, gr, s1, is_f16, m1, B, wgs[0], s0));
   }
+  tr.mark("s0 conv1 wgrad {actor,critic} done", s0);
   if (with_apply) { CPP_TRY(actor_apply(s0)); CPP_TRY(critic_apply(s0)); }
+  tr.mark("s0 apply done", s0);
+  tr.dump();
   return CPP_OK;
 }
 
