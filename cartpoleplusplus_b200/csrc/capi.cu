@@ -174,9 +174,9 @@ int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mea
 }
 
 int64_t cpp_conv_dgrad_tc_scratch_bytes(int32_t B, int32_t H, int32_t W, int32_t KS) {
-  const int64_t pk = tc::conv_tc_scratch_bytes(1, H, W, 2 * kConvCout, KS);
+  const int64_t pk = tc::conv_tc_scratch_bytes(1, H, W, tc::kC24, KS);
   if (pk < 0 || B < 1) return -1;
-  return 256 + round_up((int64_t)B * H * W * 2 * kConvCout * 2, 256) + pk;
+  return 256 + round_up((int64_t)B * H * W * tc::kC24 * 2, 256) + pk;
 }
 int cpp_conv_dgrad_tc(const float* d_pooled, const uint8_t* amax, const float* w, int32_t B, int32_t H, int32_t W, int32_t KS,
                       float* dx, void* scratch, void* stream) {
@@ -186,7 +186,7 @@ int cpp_conv_dgrad_tc(const float* d_pooled, const uint8_t* amax, const float* w
   char* sc = reinterpret_cast<char*>(scratch);
   float* gsc = reinterpret_cast<float*>(sc);
   __half* dyp = reinterpret_cast<__half*>(sc + 256);
-  void* pk = sc + 256 + round_up((int64_t)B * H * W * 2 * kConvCout * 2, 256);
+  void* pk = sc + 256 + round_up((int64_t)B * H * W * tc::kC24 * 2, 256);
   CPP_TRY(tc::launch_unpool_split(d_pooled, amax, B, H, W, gsc, gsc + 1, dyp, ST(stream)));
   return tc::launch_conv_dgrad_tc(dyp, gsc + 1, w, B, H, W, KS, dx, pk, ST(stream));
   API_END

@@ -402,6 +402,41 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
       mbar_wait(&bars[BAR_EMPTY_PL + buf], ((it >> 1) & 1) ^ 1);   // the MMAs that read this buffer two units ago are done
       uint8_t* planes = planes_base + (size_t)buf * P.unit_bytes;
 
+      if (P.in_layout == 2) {
+        // aligned 24-channel pieces: every plane vector is ONE 16-byte global vector -> cp.async straight into the parity
+        // planes (zero-size copy = zero padding); no staging ring, no re-layout, one round trip per unit
+        const uint32_t pl = smem_u32(planes);
+        const int fw = ftid >> 5, nfw = kFillWarps;
+        for (int rho = fw; rho < P.rows_alloc; rho += nfw) {
+          const int yh = yh0 + rho;
+          for (int kap = lane; kap < Pq; kap += 32) {
+            const int xh = kap - 1;
+            const uint32_t d0 = pl + (uint32_t)((rho * Pq + kap) * 16);
+#pragma unroll
+            for (int yp = 0; yp < 2; ++yp) {
+              const int y = 2 * yh + yp;
+#pragma unroll
+              for (int xp = 0; xp < 2; ++xp) {
+                const int x = 2 * xh + xp;
+                const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+                const __half* g = img + ((size_t)(ok ? y : 0) * W + (ok ? x : 0)) * kC24;
+                const int nbytes = ok ? 16 : 0;
+#pragma unroll
+                for (int gq = 0; gq < 3; ++gq)
+                  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                               ::"r"(d0 + (uint32_t)((gq * 4 + yp * 2 + xp) * P.plane_bytes)), "l"(g + 8 * gq), "r"(nbytes) : "memory");
+              }
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async();                                       // plane writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BAR_FULL_PL + buf]);
+        continue;
+      }
+
       auto group_rows = [&](int g, int& rho0, int& rho1, int& yc0, int& yc1) {
         rho0 = g * P.crh; rho1 = min(rho0 + P.crh, P.rows_alloc);
         yc0 = max(0, 2 * (yh0 + rho0)); yc1 = min(H, 2 * (yh0 + rho1));
@@ -705,9 +740,9 @@ int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const fl
                          void* scratch, cudaStream_t s) {
   if (B <= 0) return CPP_OK;
   FwdPlan P{};
-  CPP_TRY(build_plan(1, B, H, W, 2 * CO, KS, &P, 1));
+  CPP_TRY(build_plan(1, B, H, W, kC24, KS, &P, 1));
   CPP_REQUIRE(((uintptr_t)dy_pieces & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
-  P.Cw = CO; P.in_layout = 1;
+  P.Cw = CO; P.in_layout = 2;
   P.x = reinterpret_cast<const __half*>(dy_pieces); P.rows = nullptr;
   P.bpack = reinterpret_cast<const __half*>(scratch);
   P.corr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(scratch) + bpack_bytes(P));
@@ -749,14 +784,19 @@ __global__ void __launch_bounds__(256) unpool_split_kernel(const float* __restri
   for (int pa = 0; pa < 4; ++pa) {
     const int y = 2 * py + (pa >> 1), x = 2 * px + (pa & 1);
     if (y >= H || x >= W) continue;
-    __half2* d = reinterpret_cast<__half2*>(out + (((size_t)b * H + y) * W + x) * 2 * CO);
+    uint32_t hi[CO / 2], lo[CO / 2];
 #pragma unroll
     for (int o = 0; o < CO; o += 2) {
       const float v0 = a[o] == pa ? gv[o] : 0.f, v1 = a[o + 1] == pa ? gv[o + 1] : 0.f;
       const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-      d[o >> 1] = __halves2half2(h0, h1);
-      d[(CO + o) >> 1] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+      const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+      hi[o >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lo[o >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
+    uint4* d = reinterpret_cast<uint4*>(out + (((size_t)b * H + y) * W + x) * kC24);      // 24-channel piece layout, constant channel 0
+    d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    d[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    d[2] = make_uint4(hi[4], lo[4], 0u, 0u);
   }
 }
 

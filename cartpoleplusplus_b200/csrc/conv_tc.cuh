@@ -70,11 +70,12 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
                        float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s,
                        int x_is_pieces = 0, __half* const* pooled_hl = nullptr);
 // gradient wrt the input of a 10 -> 10 channel layer (conv2 / conv3): dx = conv_same(dY, flip(w)^T) on the tensor cores.
-// dy_pieces fp16 [B][H][W][hi(10) | lo(10)] = the un-pooled output gradient times *inv_scale^-1 (launch_unpool_split);
+// dy_pieces fp16 [B][H][W][24] (piece layout above, constant channel 0) = the un-pooled output gradient times *inv_scale^-1
+// (launch_unpool_split);
 // dx fp32 [B][H][W][10].
 int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
                          void* scratch, cudaStream_t s);
-// un-pool + split: d_pooled fp32 [B][H/2][W/2][10] and the arg-max side band -> dy_pieces fp16 [B][H][W][hi | lo], scaled by
+// un-pool + split: d_pooled fp32 [B][H/2][W/2][10] and the arg-max side band -> dy_pieces fp16 [B][H][W][24], scaled by
 // a power of two from max|d_pooled| (gmax: device float, zeroed and filled here); inv_scale receives 1/scale
 int launch_unpool_split(const float* d_pooled, const uint8_t* amax, int B, int H, int W, float* gmax, float* inv_scale,
                         __half* dy_pieces, cudaStream_t s);

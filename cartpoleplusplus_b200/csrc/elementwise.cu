@@ -135,12 +135,15 @@ __global__ void __launch_bounds__(256) moments_partial_kernel(const void* __rest
   }
 }
 
-__global__ void moments_finalize_kernel(const double* __restrict__ partial, int nparts, int C, double n_per_channel,
-                                        float* __restrict__ mean_inv) {
-  const int c = threadIdx.x;
+// one warp per channel: lanes split the per-block partials (fp64), fixed-order shuffle reduction
+__global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __restrict__ partial, int nparts, int C, double n_per_channel,
+                                                               float* __restrict__ mean_inv) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < nparts; ++k) { s1 += partial[(size_t)k * 2 * C + c]; s2 += partial[(size_t)k * 2 * C + C + c]; }
+  for (int k = lane; k < nparts; k += 32) { s1 += partial[(size_t)k * 2 * C + c]; s2 += partial[(size_t)k * 2 * C + C + c]; }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane != 0) return;
   const double mean = s1 / n_per_channel;
   double var = s2 / n_per_channel - mean * mean;      // population variance (tf.nn.moments)
   if (var < 0.0) var = 0.0;
@@ -164,7 +167,7 @@ int launch_channel_moments(const void* x, int is_f16, int64_t n_pix_total, int C
   if (is_f16) moments_partial_kernel<true><<<blocks, 256, 256 * 16 * sizeof(double), s>>>(x, n, C, st, scratch);
   else moments_partial_kernel<false><<<blocks, 256, 256 * 16 * sizeof(double), s>>>(x, n, C, st, scratch);
   CPP_CHECK_LAUNCH();
-  moments_finalize_kernel<<<1, (unsigned)round_up(C, 32), 0, s>>>(scratch, blocks, C, (double)n_pix_total, mean_inv);
+  moments_finalize_kernel<<<(unsigned)ceil_div(C, 8), 256, 0, s>>>(scratch, blocks, C, (double)n_pix_total, mean_inv);
   CPP_CHECK_LAUNCH();
   return CPP_OK;
 }

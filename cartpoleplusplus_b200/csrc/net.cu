@@ -74,7 +74,7 @@ Net::Layout Net::layout(int B) const {
     int64_t wg = 0;
     for (int i = 0; i < 3; ++i) { const int64_t w = conv_wgrad_scratch_floats(conv[i]); if (w > wg) wg = w; }
     L.wgrad = take((size_t)wg * sizeof(float));
-    L.dyp = take((size_t)B * conv[1].H * conv[1].W * 2 * kConvCout * sizeof(__half));   // un-pooled gradient pieces (dgrad on tensor cores)
+    L.dyp = take((size_t)B * conv[1].H * conv[1].W * tc::kC24 * sizeof(__half));   // un-pooled gradient pieces (dgrad on tensor cores)
     L.gsc = take(4 * sizeof(float));
   } else {
     L.x0 = take((size_t)B * in_dim[0] * sizeof(float));
