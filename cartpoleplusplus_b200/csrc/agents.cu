@@ -172,33 +172,6 @@ static bool env_flag(const char* name) { const char* e = getenv(name); return !(
 static bool use_streams() { static const bool d = env_flag("CARTPOLEPP_STREAMS"); return g_use_streams < 0 ? d : g_use_streams != 0; }
 static bool use_graphs() { static const bool d = env_flag("CARTPOLEPP_GRAPHS"); return g_use_graphs < 0 ? d : g_use_graphs != 0; }
 
-// CARTPOLEPP_TRACE=1: eager steps record a timing event at every chain milestone and print the timeline (us since the
-// start of the step) to stderr - the poor man's nsys for the fork/join schedule
-struct Tracer {
-  bool on = false;
-  std::vector<std::pair<std::string, cudaEvent_t>> pts;
-  void mark(const char* label, cudaStream_t st) {
-    if (!on) return;
-    cudaEvent_t e;
-    if (cudaEventCreate(&e) != cudaSuccess) return;
-    cudaEventRecord(e, st);
-    pts.emplace_back(label, e);
-  }
-  void dump() {
-    if (!on || pts.empty()) return;
-    cudaDeviceSynchronize();
-    fprintf(stderr, "---- step timeline (us)\n");
-    for (auto& p : pts) {
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, pts[0].second, p.second);
-      fprintf(stderr, "%9.1f  %s\n", ms * 1e3f, p.first.c_str());
-    }
-    for (auto& p : pts) cudaEventDestroy(p.second);
-    pts.clear();
-  }
-};
-static bool trace_enabled() { static const bool t = [] { const char* e = getenv("CARTPOLEPP_TRACE"); return e && e[0] == '1'; }(); return t; }
-
 DDPG::~DDPG() {
   for (auto& gm : graph) for (auto& g : gm) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (streams_ready) {
@@ -225,7 +198,9 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   auto record = [&](int e, cudaStream_t st) -> int { if (multi) CPP_CHECK_CUDA(cudaEventRecord(ev[e], st)); return CPP_OK; };
   auto wait = [&](cudaStream_t st, int e) -> int { if (multi) CPP_CHECK_CUDA(cudaStreamWaitEvent(st, ev[e], 0)); return CPP_OK; };
   struct CapGuard { ~CapGuard() { g_cta_cap = kNumSMs; } } cap_guard;
-  Tracer tr; tr.on = trace_enabled() && !use_graphs();
+  struct Tr { bool on; void mark(const char* l, cudaStream_t st) { if (on) trace_mark(l, st); } void dump() { if (on) trace_dump(); } } tr;
+  tr.on = trace_enabled() && !use_graphs();
+  if (tr.on) trace_begin();
   tr.mark("start", s0);
   const float* P = buf.params; const float* T = buf.target_params;
 

@@ -1,6 +1,10 @@
 // extern "C" surface of libcartpolepp.so (include/cartpolepp.h).  Thin: argument checks, object
 // lifetime, exception firewall.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string>
+#include <utility>
+#include <vector>
 #include <new>
 #include "agents.cuh"
 #include "conv_tc.cuh"
@@ -18,6 +22,32 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static bool g_trace_active = false;
+static std::vector<std::pair<std::string, cudaEvent_t>> g_trace_pts;
+bool trace_enabled() { static const bool t = [] { const char* e = getenv("CARTPOLEPP_TRACE"); return e && e[0] == '1'; }(); return t; }
+void trace_begin() { g_trace_active = true; }
+void trace_mark(const char* label, cudaStream_t st) {
+  if (!g_trace_active) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_trace_pts.emplace_back(label, e);
+}
+void trace_dump() {
+  if (!g_trace_active) return;
+  g_trace_active = false;
+  if (g_trace_pts.empty()) return;
+  cudaDeviceSynchronize();
+  fprintf(stderr, "---- step timeline (us)\n");
+  for (auto& p : g_trace_pts) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_trace_pts[0].second, p.second);
+    fprintf(stderr, "%9.1f  %s\n", ms * 1e3f, p.first.c_str());
+  }
+  for (auto& p : g_trace_pts) cudaEventDestroy(p.second);
+  g_trace_pts.clear();
+}
 }  // namespace cpp
 
 using namespace cpp;

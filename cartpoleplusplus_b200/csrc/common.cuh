@@ -41,6 +41,13 @@ static inline int sm_budget() { return g_cta_cap < 1 ? 1 : (g_cta_cap > 148 ? 14
     if (_s != CPP_OK) return _s; \
   } while (0)
 
+// CARTPOLEPP_TRACE=1: eager steps record a timing event at every chain milestone and print the timeline (us since the
+// start of the step) to stderr - the poor man's nsys for the fork/join schedule (capi.cu)
+bool trace_enabled();
+void trace_begin();
+void trace_mark(const char* label, cudaStream_t st);     // no-op unless trace_begin() was called
+void trace_dump();
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -130,6 +130,7 @@ int Net::forward_trunk(const float* params, const void* state, int is_f16, const
         CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
       }
       x = pooled; xf16 = 0; mi = nullptr;
+      trace_mark(i == 1 ? "   . conv2 fwd" : (i == 2 ? "   . conv3 fwd" : "   . conv1 fwd"), s);
     }
   } else {
     CPP_TRY(launch_state_to_f32(state, is_f16, B, feat, reinterpret_cast<float*>(ws + L.x0), in_dim[0], s));
@@ -291,6 +292,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     dld = in_dim[i];
   }
   if (!pixels || grads == nullptr) return CPP_OK;
+  trace_mark("   . FC backward", s);
 
   // conv trunk: dcur = d(pooled3) as (B, F); base_network.py:103-123 backwards
   const float* gp = dcur;
@@ -303,8 +305,10 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     // tensor-core route for conv3/conv2: the un-pool + split pass also yields max|gp|, shared by wgrad and dgrad
     const bool tc_dg = i > 0 && tc_scratch != nullptr && tc_route(is_f16);
     float* gsc = reinterpret_cast<float*>(ws + L.gsc);
-    if (tc_dg)
+    if (tc_dg) {
       CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, reinterpret_cast<__half*>(ws + L.dyp), s));
+      trace_mark(i == 2 ? "   . conv3 un-pool/split" : "   . conv2 un-pool/split", s);
+    }
     if (i > 0 && wg_scratch != nullptr && tc_route(is_f16) &&
         wg::conv_wgrad_mma_supported(1, conv[i].H, conv[i].W, tc::kC24, conv[i].KS, 2)) {
       const float* g1[1] = {gp}; const uint8_t* a1[1] = {amax};
@@ -316,6 +320,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
       CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, gp, amax, B, grads + off_conv_w[i], grads + off_conv_b[i],
                                 reinterpret_cast<float*>(ws + L.wgrad), s));
     }
+    trace_mark(i == 2 ? "   . conv3 wgrad" : (i == 1 ? "   . conv2 wgrad" : "   . conv1 wgrad"), s);
     if (i > 0) {
       float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
       if (tc_dg) {
@@ -325,6 +330,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
         CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));
       }
       gp = dx;
+      trace_mark(i == 2 ? "   . conv3 dgrad" : "   . conv2 dgrad", s);
     }
   }
   return CPP_OK;

@@ -1,6 +1,11 @@
 #!/usr/bin/env python
-"""Kernel-level timings (CUDA events, L2 flushed between launches) of the conv layers at the BASELINE shapes:
-exact-fp32 CUDA-core kernels vs the tcgen05 path.  usage: python scripts/bench_kernels.py [c3|c4|c5]"""
+"""Kernel-level timings (CUDA events on the launching stream, L2 flushed between launches) of the conv kernels at the
+BASELINE config 3 layer shapes, each through its C-ABI entry point on the whole GPU.
+
+  python scripts/bench_kernels.py                 all kernels, one JSON line each
+  python scripts/bench_kernels.py --only NAME     one kernel (for `ncu -k regex:... python scripts/bench_kernels.py --only NAME`)
+"""
+import argparse
 import ctypes as C
 import json
 import os
@@ -11,8 +16,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cartpoleplusplus_b200 import _lib as L   # noqa: E402
+from tests import gpu_util as U               # noqa: E402
 
-CFG = dict(c3=(256, 64, 64, 9, 2), c4=(128, 64, 64, 18, 3), c5=(128, 128, 128, 24, 2))
+B, H, W, CIN, NETS = 256, 64, 64, 9, 2
 
 
 def timeit(fn, flush, n=10):
@@ -28,36 +34,89 @@ def timeit(fn, flush, n=10):
 
 
 def main():
-  name = sys.argv[1] if len(sys.argv) > 1 else "c3"
-  B, H, W, Cin, nets = CFG[name]
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--only", default=None)
+  ap.add_argument("--reps", type=int, default=10)
+  args = ap.parse_args()
   lib = L.lib()
   dev = "cuda"
   g = torch.Generator(device=dev); g.manual_seed(0)
-  x = (torch.randint(0, 256, (B, H, W, Cin), device=dev, generator=g).to(torch.float16) / 255).contiguous()
-  scratch = torch.zeros(int(lib.cpp_moments_scratch_doubles(Cin)), dtype=torch.float64, device=dev)
-  mi = torch.zeros(2 * Cin, dtype=torch.float32, device=dev)
-  L.check(lib.cpp_channel_moments(L.ptr(x), 1, C.c_int64(B * H * W), Cin, L.ptr(scratch), L.ptr(mi), L.stream_ptr()))
-  ws = [torch.randn(5, 5, Cin, 10, device=dev) * 0.05 for _ in range(nets)]
-  bs = [torch.randn(10, device=dev) * 0.1 for _ in range(nets)]
-  pooled = [torch.zeros(B, H // 2, W // 2, 10, device=dev) for _ in range(nets)]
-  amax = [torch.zeros(B, H // 2, W // 2, 10, dtype=torch.uint8, device=dev) for _ in range(nets)]
+  rs = np.random.RandomState(0)
   flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-  scr = torch.zeros(int(lib.cpp_conv_tc_scratch_bytes(nets, H, W, Cin, 5)), dtype=torch.uint8, device=dev)
-  wa, ba, pa, aa = L.ptr_array(ws), L.ptr_array(bs), L.ptr_array(pooled), L.ptr_array(amax)
+  st = L.stream_ptr
 
-  def ffma():
-    for n in range(nets):
-      L.check(lib.cpp_conv_forward(L.ptr(x), 1, L.ptr(mi), L.ptr(ws[n]), L.ptr(bs[n]), B, H, W, Cin, 5, L.ptr(pooled[n]), L.ptr(amax[n]), L.stream_ptr()))
+  # ---- conv1 (fp16 pixels, whitening folded), actor + critic
+  x = (torch.randint(0, 256, (B, H, W, CIN), device=dev, generator=g).to(torch.float16) / 255).contiguous()
+  scratch = torch.zeros(int(lib.cpp_moments_scratch_doubles(CIN)), dtype=torch.float64, device=dev)
+  mi = torch.zeros(2 * CIN, dtype=torch.float32, device=dev)
+  L.check(lib.cpp_channel_moments(L.ptr(x), 1, C.c_int64(B * H * W), CIN, L.ptr(scratch), L.ptr(mi), st()))
+  w1 = [torch.randn(5, 5, CIN, 10, device=dev) * 0.05 for _ in range(NETS)]
+  b1 = [torch.randn(10, device=dev) * 0.1 for _ in range(NETS)]
+  p1 = [torch.zeros(B, 32, 32, 10, device=dev) for _ in range(NETS)]
+  a1 = [torch.zeros(B, 32, 32, 10, dtype=torch.uint8, device=dev) for _ in range(NETS)]
+  hl1 = [torch.zeros(B, 32, 32, 24, dtype=torch.float16, device=dev) for _ in range(NETS)]
+  scr1 = torch.zeros(int(lib.cpp_conv_tc_scratch_bytes(NETS, H, W, CIN, 5)), dtype=torch.uint8, device=dev)
+  pw1, pb1, pp1, pa1, ph1 = L.ptr_array(w1), L.ptr_array(b1), L.ptr_array(p1), L.ptr_array(a1), L.ptr_array(hl1)
+  g1 = [torch.randn(B, 32, 32, 10, device=dev) * 1e-3 for _ in range(NETS)]
+  dw1 = [torch.zeros(5, 5, CIN, 10, device=dev) for _ in range(NETS)]
+  db1 = [torch.zeros(10, device=dev) for _ in range(NETS)]
+  wscr1 = torch.zeros(int(lib.cpp_conv_wgrad_mma_scratch_bytes(NETS, H, W, CIN, 5)), dtype=torch.uint8, device=dev)
+  pg1, pdw1, pdb1 = L.ptr_array(g1), L.ptr_array(dw1), L.ptr_array(db1)
 
-  def tc():
-    L.check(lib.cpp_conv_forward_tc(L.ptr(x), None, L.ptr(mi), nets, wa, ba, B, H, W, Cin, 5, pa, aa, L.ptr(scr), L.stream_ptr()))
+  def conv1_fwd_tc():
+    L.check(lib.cpp_conv_forward_tc(L.ptr(x), None, L.ptr(mi), NETS, pw1, pb1, B, H, W, CIN, 5, pp1, pa1, L.ptr(scr1), st(), 0, ph1))
 
-  flops = 2.0 * B * H * W * 10 * 25 * Cin * nets
-  out = dict(config=name, B=B, H=H, W=W, Cin=Cin, nets=nets, useful_gflop=flops / 1e9)
-  for nm, fn in (("ffma", ffma), ("tcgen05", tc)):
-    med, mn = timeit(fn, flush)
-    out[nm] = dict(us_median=med, us_min=mn, useful_tflops=flops / (med * 1e-6) / 1e12)
-  print(json.dumps(out))
+  def conv1_wgrad_mma():
+    L.check(lib.cpp_conv_wgrad_mma(L.ptr(x), L.ptr(mi), 0, NETS, pg1, pa1, B, H, W, CIN, 5, pdw1, pdb1, L.ptr(wscr1), st()))
+
+  # ---- conv2 / conv3 (one network; input = 24-channel fp16 pieces of the layer below)
+  def layer(Hh, KS):
+    act = np.maximum(rs.randn(B, Hh, Hh, 10), 0).astype(np.float32)
+    xin = torch.from_numpy(U.to_c24(act)[0]).to(dev)
+    w = torch.randn(KS, KS, 10, 10, device=dev) * 0.05; b = torch.randn(10, device=dev) * 0.1
+    po = torch.zeros(B, Hh // 2, Hh // 2, 10, device=dev); am = torch.zeros(B, Hh // 2, Hh // 2, 10, dtype=torch.uint8, device=dev)
+    hl = torch.zeros(B, Hh // 2, Hh // 2, 24, dtype=torch.float16, device=dev)
+    scr = torch.zeros(int(lib.cpp_conv_tc_scratch_bytes(1, Hh, Hh, 24, KS)), dtype=torch.uint8, device=dev)
+    gp = torch.randn(B, Hh // 2, Hh // 2, 10, device=dev) * 1e-3
+    dx = torch.zeros(B, Hh, Hh, 10, device=dev)
+    dscr = torch.zeros(int(lib.cpp_conv_dgrad_tc_scratch_bytes(B, Hh, Hh, KS)), dtype=torch.uint8, device=dev)
+    dw = torch.zeros(KS, KS, 10, 10, device=dev); db = torch.zeros(10, device=dev)
+    wscr = torch.zeros(int(lib.cpp_conv_wgrad_mma_scratch_bytes(1, Hh, Hh, 24, KS)), dtype=torch.uint8, device=dev)
+    pw, pb, pp, pa, ph = L.ptr_array([w]), L.ptr_array([b]), L.ptr_array([po]), L.ptr_array([am]), L.ptr_array([hl])
+    pg, pdw, pdb = L.ptr_array([gp]), L.ptr_array([dw]), L.ptr_array([db])
+
+    def fwd():
+      L.check(lib.cpp_conv_forward_tc(L.ptr(xin), None, None, 1, pw, pb, B, Hh, Hh, 24, KS, pp, pa, L.ptr(scr), st(), 2, ph))
+
+    def dgrad():
+      L.check(lib.cpp_conv_dgrad_tc(L.ptr(gp), L.ptr(am), L.ptr(w), B, Hh, Hh, KS, L.ptr(dx), L.ptr(dscr), st()))
+
+    def wgrad():
+      L.check(lib.cpp_conv_wgrad_mma(L.ptr(xin), None, 2, 1, pg, pa, B, Hh, Hh, 24, KS, pdw, pdb, L.ptr(wscr), st()))
+    keep = (xin, w, b, po, am, hl, scr, gp, dx, dscr, dw, db, wscr, pw, pb, pp, pa, ph, pg, pdw, pdb)
+    return fwd, dgrad, wgrad, keep
+
+  c2 = layer(32, 5)
+  c3 = layer(16, 3)
+  conv1_fwd_tc()          # fills the arg-max side band the wgrad reads
+  c2[0](); c3[0]()
+  mac1 = B * H * W * 10 * 25 * CIN * NETS
+  kernels = [
+      ("conv1_fwd_tc", conv1_fwd_tc, 2.0 * mac1, "conv1 5x5 9->10 fwd, actor+critic, incl. weight prep"),
+      ("conv1_wgrad_mma", conv1_wgrad_mma, 2.0 * mac1, "conv1 weight gradient, actor+critic, incl. absmax/reduce/finalize"),
+      ("conv2_fwd_tc", c2[0], 2.0 * B * 32 * 32 * 10 * 25 * 10, "conv2 5x5 10->10 fwd, one network, incl. weight prep"),
+      ("conv2_dgrad_tc", c2[1], 2.0 * B * 32 * 32 * 10 * 25 * 10, "conv2 input gradient, incl. un-pool/split + prep"),
+      ("conv2_wgrad_mma", c2[2], 2.0 * B * 32 * 32 * 10 * 25 * 10, "conv2 weight gradient, one network"),
+      ("conv3_fwd_tc", c3[0], 2.0 * B * 16 * 16 * 10 * 9 * 10, "conv3 3x3 10->10 fwd"),
+      ("conv3_dgrad_tc", c3[1], 2.0 * B * 16 * 16 * 10 * 9 * 10, "conv3 input gradient"),
+      ("conv3_wgrad_mma", c3[2], 2.0 * B * 16 * 16 * 10 * 9 * 10, "conv3 weight gradient"),
+  ]
+  for name, fn, flops, what in kernels:
+    if args.only and args.only != name:
+      continue
+    med, mn = timeit(fn, flush, args.reps)
+    print(json.dumps(dict(kernel=name, what=what, us_median=med, us_min=mn, useful_gflop=flops / 1e9,
+                          useful_tflops=flops / (med * 1e-6) / 1e12)))
 
 
 if __name__ == "__main__":
