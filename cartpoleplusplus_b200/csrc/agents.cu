@@ -177,6 +177,11 @@ DDPG::~DDPG() {
   if (streams_ready) {
     for (auto& st : side) if (st) cudaStreamDestroy(st);
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    for (auto& a : aux) {
+      if (a.stream) cudaStreamDestroy(a.stream);
+      for (auto& e : a.ready) if (e) cudaEventDestroy(e);
+      if (a.done) cudaEventDestroy(a.done);
+    }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
 }
@@ -185,6 +190,11 @@ int DDPG::ensure_streams() {
   if (streams_ready) return CPP_OK;
   for (auto& st : side) CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  for (auto& a : aux) {
+    CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    for (auto& e : a.ready) CPP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CPP_CHECK_CUDA(cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming));
+  }
   for (auto& e : ev) CPP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   streams_ready = true;
   return CPP_OK;
@@ -254,16 +264,19 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   // ---- backward chains: actor on s0, critic on sc
   if (multi) g_cta_cap = kNumSMs / 2;
   CPP_TRY(wait(s0, E_DQDA));
-  CPP_TRY(actor.backward(P, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s0, 1, wgs[0], tcs[0]));
+  aux[0].used = aux[1].used = false;
+  aux[0].cta_cap = aux[1].cta_cap = kNumSMs / 2;
+  CPP_TRY(actor.backward(P, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s0, 1, wgs[0], tcs[0], multi ? &aux[0] : nullptr));
   tr.mark("s0 actor backward (FC, conv3, conv2) done", s0);
   CPP_TRY(wait(sc, E_Q2));
   CPP_TRY(critic.forward_fc(P + off_c, action, B, ws_critic, q, sc, ca > 0 ? ca : 0));   // Q(s1, a_batch): only the layers above the concat
   CPP_TRY(launch_td_mse(q, q2, reward, mask, cfg.discount, B, B_global, td, dq, buf.grads + off_loss, sc));
   tr.mark("sc critic FC @a + TD done", sc);
-  CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, sc, 1, wgs[1], tcs[1]));
+  CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, sc, 1, wgs[1], tcs[1], multi ? &aux[1] : nullptr));
   tr.mark("sc critic backward (FC, conv3, conv2) done", sc);
   CPP_TRY(record(E_CB, sc));
   CPP_TRY(wait(s0, E_CB));
+  if (multi) for (auto& a : aux) if (a.used) CPP_CHECK_CUDA(cudaStreamWaitEvent(s0, a.done, 0));     // join the weight-gradient side streams
   g_cta_cap = kNumSMs;
   // ---- conv1 weight gradients of both networks in one pass over state_1; whole GPU
   {

@@ -640,8 +640,12 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, 
     P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
     return (int)smem_layout(*P).total;
   };
+  // pipelining needs several units per CTA (fill of unit u+1 overlaps the MMAs of unit u): with few tiles per CTA, small
+  // units beat the halo rows they re-stage
+  const int64_t tiles_per_cta = ceil_div((int64_t)B * P->tiles_per_image, sm_budget());
+  const int want_tpu = (int)std::max<int64_t>(1, std::min<int64_t>(8, tiles_per_cta / 6));
   int best_tpu = 0;
-  for (int tpu = std::min(P->tiles_per_image, 8); tpu >= 1; --tpu)
+  for (int tpu = std::min(P->tiles_per_image, want_tpu); tpu >= 1; --tpu)
     if (size_unit(tpu) <= kSmemLimit) { best_tpu = tpu; break; }
   CPP_REQUIRE(best_tpu > 0, "conv_tc: %dx%dx%d does not fit shared memory", H, W, C);
   P->units_per_image = (int)ceil_div(P->tiles_per_image, best_tpu);

@@ -75,18 +75,15 @@ Net::Layout Net::layout(int B) const {
     for (int i = 0; i < 3; ++i) { const int64_t w = conv_wgrad_scratch_floats(conv[i]); if (w > wg) wg = w; }
     L.wgrad = take((size_t)wg * sizeof(float));
     L.dyp = take((size_t)B * conv[1].H * conv[1].W * tc::kC24 * sizeof(__half));   // un-pooled gradient pieces (dgrad on tensor cores)
-    L.gsc = take(4 * sizeof(float));
+    L.gsc = take(8 * sizeof(float));                                                      // {max|g|, 1/scale} per conv layer
   } else {
     L.x0 = take((size_t)B * in_dim[0] * sizeof(float));
   }
-  int maxw = feat;
-  for (int i = 0; i < n_fc; ++i) {
-    L.h[i] = take((size_t)B * out_ld[i] * sizeof(float));
-    if (in_dim[i] > maxw) maxw = in_dim[i];
-    if (out_dim[i] > maxw) maxw = out_dim[i];
-  }
-  L.dA = take((size_t)B * maxw * sizeof(float));
-  L.dB = take((size_t)B * maxw * sizeof(float));
+  for (int i = 0; i < n_fc; ++i) L.h[i] = take((size_t)B * out_ld[i] * sizeof(float));
+  // gradients: one buffer per FC layer input (a weight gradient running on a side stream may still read the gradient of
+  // layer i after the main chain has moved on) and the gradient wrt the last pre-activation
+  for (int i = 0; i < n_fc; ++i) L.dX[i] = take((size_t)B * in_dim[i] * sizeof(float));
+  L.dTop = take((size_t)B * out_dim[n_fc - 1] * sizeof(float));
   L.total = off;
   return L;
 }
@@ -251,15 +248,24 @@ int trunk_forward_group(int n, const Net* const* nets, const float* const* param
 
 int Net::backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
                   const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1, void* wg_scratch,
-                  void* tc_scratch) const {
+                  void* tc_scratch, BackwardAux* aux) const {
   CPP_REQUIRE(B >= 1, "batch %d", B);
   CPP_REQUIRE(d_action == nullptr || concat_at >= 0, "d_action requested from a network without action input");
   char* ws = reinterpret_cast<char*>(ws_);
   const Layout L = layout(B);
-  float* dcur = reinterpret_cast<float*>(ws + L.dA);
-  float* dnext = reinterpret_cast<float*>(ws + L.dB);
   const int last = n_fc - 1;
+  const bool fork = aux != nullptr && aux->stream != nullptr && grads != nullptr;
+  cudaStream_t sw = fork ? aux->stream : s;              // weight / bias gradients
+  int ev = 0;
+  auto ready = [&]() -> int {                            // the gradient produced last on `s` may now be consumed on `sw`
+    if (!fork) return CPP_OK;
+    CPP_CHECK_CUDA(cudaEventRecord(aux->ready[ev], s));
+    CPP_CHECK_CUDA(cudaStreamWaitEvent(sw, aux->ready[ev], 0));
+    ++ev; aux->used = true;
+    return CPP_OK;
+  };
   // gradient wrt the last pre-activation
+  float* dcur = reinterpret_cast<float*>(ws + L.dTop);
   CPP_TRY(launch_act_grad(d_out, out_dim[last], reinterpret_cast<const float*>(ws + L.h[last]), out_ld[last], act[last], B,
                           out_dim[last], dcur, out_dim[last], s));
   int dld = out_dim[last];
@@ -268,16 +274,18 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     int xld;
     const float* x = fc_input(L, ws, i, &xld);
     if (grads != nullptr) {
+      CPP_TRY(ready());
       GemmArgs g{};                                        // dW = x^T . dPre
       g.A = x; g.lda = xld; g.transA = 1;
       g.B = dcur; g.ldb = dld; g.transB = 0;
       g.C = grads + off_fc_w[i]; g.ldc = out_dim[i];
       g.M = in_dim[i]; g.N = out_dim[i]; g.K = B; g.epi = EPI_NONE;
-      CPP_TRY(launch_gemm(g, s));
-      CPP_TRY(launch_colsum(dcur, dld, B, out_dim[i], grads + off_fc_b[i], s));
+      CPP_TRY(launch_gemm(g, sw));
+      CPP_TRY(launch_colsum(dcur, dld, B, out_dim[i], grads + off_fc_b[i], sw));
     }
     const bool need_dx = (i > stop_at) || (i == 0 && pixels && grads != nullptr) || (concat_at == i && d_action != nullptr);
     if (!need_dx) break;
+    float* dnext = reinterpret_cast<float*>(ws + L.dX[i]);
     GemmArgs g{};                                          // dX = dPre . W^T, masked by the ReLU of the layer below
     g.A = dcur; g.lda = dld; g.transA = 0;
     g.B = params + off_fc_w[i]; g.ldb = out_dim[i]; g.transB = 1;
@@ -288,11 +296,16 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     CPP_TRY(launch_gemm(g, s));
     if (concat_at == i && d_action != nullptr)
       CPP_TRY(launch_copy_cols(dnext + (in_dim[i] - action_dim), in_dim[i], B, action_dim, d_action, action_dim, 0, s));
-    float* t = dcur; dcur = dnext; dnext = t;
+    dcur = dnext;
     dld = in_dim[i];
   }
-  if (!pixels || grads == nullptr) return CPP_OK;
-  trace_mark("   . FC backward", s);
+  auto finish = [&]() -> int {                            // mark the end of the side stream's work for the caller's join
+    if (fork && aux->used) CPP_CHECK_CUDA(cudaEventRecord(aux->done, sw));
+    return CPP_OK;
+  };
+  if (!pixels || grads == nullptr) return finish();
+  trace_mark("   . FC input gradients", s);
+
 
   // conv trunk: dcur = d(pooled3) as (B, F); base_network.py:103-123 backwards
   const float* gp = dcur;
@@ -304,23 +317,28 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     if (i == 0 && defer_conv1) break;                       // gp == ws + L.dpool[1]: picked up by conv1_wgrad_group
     // tensor-core route for conv3/conv2: the un-pool + split pass also yields max|gp|, shared by wgrad and dgrad
     const bool tc_dg = i > 0 && tc_scratch != nullptr && tc_route(is_f16);
-    float* gsc = reinterpret_cast<float*>(ws + L.gsc);
+    float* gsc = reinterpret_cast<float*>(ws + L.gsc) + 2 * i;
     if (tc_dg) {
       CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, reinterpret_cast<__half*>(ws + L.dyp), s));
       trace_mark(i == 2 ? "   . conv3 un-pool/split" : "   . conv2 un-pool/split", s);
     }
+    CPP_TRY(ready());                                      // gp (and its max) are complete on the main stream
+    const int cap_saved = g_cta_cap;
+    if (fork && aux->cta_cap > 0) g_cta_cap = aux->cta_cap;
+    struct CapRestore { int v; ~CapRestore() { g_cta_cap = v; } } cap_restore{cap_saved};
     if (i > 0 && wg_scratch != nullptr && tc_route(is_f16) &&
         wg::conv_wgrad_mma_supported(1, conv[i].H, conv[i].W, tc::kC24, conv[i].KS, 2)) {
       const float* g1[1] = {gp}; const uint8_t* a1[1] = {amax};
       float* dw[1] = {grads + off_conv_w[i]}; float* db[1] = {grads + off_conv_b[i]};
       const float* gm[1] = {gsc};
       CPP_TRY(wg::launch_conv_wgrad_mma(ws + L.hl[i - 1], nullptr, 2, 1, g1, a1, B, conv[i].H, conv[i].W, tc::kC24, conv[i].KS,
-                                        dw, db, wg_scratch, s, tc_dg ? gm : nullptr));
+                                        dw, db, wg_scratch, sw, tc_dg ? gm : nullptr));
     } else {
       CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, gp, amax, B, grads + off_conv_w[i], grads + off_conv_b[i],
-                                reinterpret_cast<float*>(ws + L.wgrad), s));
+                                reinterpret_cast<float*>(ws + L.wgrad), sw));
     }
-    trace_mark(i == 2 ? "   . conv3 wgrad" : (i == 1 ? "   . conv2 wgrad" : "   . conv1 wgrad"), s);
+    g_cta_cap = cap_saved;
+    trace_mark(i == 2 ? "   . conv3 wgrad (side)" : (i == 1 ? "   . conv2 wgrad (side)" : "   . conv1 wgrad"), sw);
     if (i > 0) {
       float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
       if (tc_dg) {
@@ -333,7 +351,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
       trace_mark(i == 2 ? "   . conv3 dgrad" : "   . conv2 dgrad", s);
     }
   }
-  return CPP_OK;
+  return finish();
 }
 
 }  // namespace cpp

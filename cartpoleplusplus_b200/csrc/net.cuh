@@ -7,6 +7,16 @@ namespace cpp {
 
 struct VarInfo { int64_t offset; int ndim; int64_t shape[4]; };
 
+// Side stream for the work of a backward pass that nothing downstream in the same pass waits for (every weight / bias
+// gradient): the chain of input gradients stays short on the main stream, the caller joins `done` before it reads grads.
+struct BackwardAux {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready[CPP_MAX_FC + 3] = {};   // "the gradient this weight gradient consumes is ready", one per layer
+  cudaEvent_t done = nullptr;               // recorded on `stream` after the last weight gradient
+  bool used = false;
+  int cta_cap = 0;                          // SM budget of the persistent kernels launched on the side stream (0: unchanged)
+};
+
 struct Net {
   cpp_net_spec spec;
   bool pixels = false;
@@ -20,7 +30,7 @@ struct Net {
   std::vector<VarInfo> vars;
 
   struct Layout {
-    size_t pooled[3], amax[3], hl[2], x0, h[CPP_MAX_FC], dA, dB, dpool[2], wgrad, dyp, gsc, total;
+    size_t pooled[3], amax[3], hl[2], x0, h[CPP_MAX_FC], dX[CPP_MAX_FC], dTop, dpool[2], wgrad, dyp, gsc, total;
   };
 
   int init(const cpp_net_spec& s);
@@ -52,7 +62,7 @@ struct Net {
   // tc_scratch != NULL: conv3/conv2 input gradients through the tcgen05 kernel in dgrad mode (conv_tc.cu).
   int backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
                const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1 = 0,
-               void* wg_scratch = nullptr, void* tc_scratch = nullptr) const;
+               void* wg_scratch = nullptr, void* tc_scratch = nullptr, BackwardAux* aux = nullptr) const;
 };
 
 // Conv trunks of n (<= 3) sibling networks that read the SAME state (actor+critic on state_1, the two targets on
