@@ -163,9 +163,10 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     first_flush = false;
   };
 
-  // ---- staging pieces.  dY item = (output row r of the band, window column, network): the two pixels (x even / odd) of one
-  // window row; its 10 pooled gradients and arg-max bytes are prefetched into registers one band ahead.
-  const int wp2 = Wp / 2, dy_items = BR * wp2 * nets;
+  // ---- staging pieces.  dY item = (window row of the band, window column, network): the 10 pooled gradients and arg-max
+  // bytes of one 2x2 window, prefetched into registers one band ahead, converted to fp16 pieces once and scattered to the
+  // window's four pixels.
+  const int wp2 = Wp / 2, hp = BR / 2, dy_items = hp * wp2 * nets;
   float2 gq[kDyItems][5];
   unsigned short aq[kDyItems][5];
   auto band_rows_of = [&](int band, int& b, int& y0, int& ylo, int& yhi) {
@@ -212,8 +213,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
 #pragma unroll
       for (int v = 0; v < 5; ++v) { gq[k][v] = make_float2(0.f, 0.f); aq[k][v] = 0x0404; }
       if (it < dy_items) {
-        const int net = it % nets, t2 = it / nets, pxl = t2 % wp2, r = t2 / wp2;
-        const int py = (y0 + r) >> 1;
+        const int net = it % nets, t2 = it / nets, pxl = t2 % wp2, pyl = t2 / wp2;
+        const int py = (y0 >> 1) + pyl;
         if (py < PH && pxl < PW) {
           const size_t idx = (((size_t)b * PH + py) * PW + pxl) * CO;
           const float2* gp = reinterpret_cast<const float2*>(P.g[net] + idx);
@@ -238,26 +239,30 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     for (int k = 0; k < kDyItems; ++k) {
       const int it = tid + k * nthr;
       if (it < dy_items) {
-        const int net = it % nets, t2 = it / nets, pxl = t2 % wp2, r = t2 / wp2;
+        const int net = it % nets, t2 = it / nets, pxl = t2 % wp2, pyl = t2 / wp2;
         const float sc = s_scale[net];
-        const uint32_t pa0 = (uint32_t)(((y0 + r) & 1) << 1);            // window positions of this row: pa0 (x even), pa0 + 1 (x odd)
-        uint32_t w0[10], w1[10];                                         // [hi(10) | lo(10)] halves of the two pixels, as half2 words
+        uint32_t hi2[5], lo2[5], a0[5], a1[5];                         // 10 filters as 5 half2 words + their arg-max bytes
 #pragma unroll
         for (int v = 0; v < 5; ++v) {
           const float g0 = gq[k][v].x * sc, g1 = gq[k][v].y * sc;
           const __half h0 = __float2half_rn(g0), h1 = __float2half_rn(g1);
           const __half l0 = __float2half_rn(g0 - __half2float(h0)), l1 = __float2half_rn(g1 - __half2float(h1));
-          const uint32_t hi2 = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          const uint32_t lo2 = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-          const uint32_t a0 = aq[k][v] & 0xffu, a1 = aq[k][v] >> 8;
-          const uint32_t m0 = (a0 == pa0 ? 0x0000ffffu : 0u) | (a1 == pa0 ? 0xffff0000u : 0u);
-          const uint32_t m1 = (a0 == pa0 + 1 ? 0x0000ffffu : 0u) | (a1 == pa0 + 1 ? 0xffff0000u : 0u);
-          w0[v] = hi2 & m0; w0[5 + v] = lo2 & m0; w1[v] = hi2 & m1; w1[5 + v] = lo2 & m1;
+          hi2[v] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          lo2[v] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          a0[v] = aq[k][v] & 0xffu; a1[v] = aq[k][v] >> 8;
         }
-        uint2* d0 = reinterpret_cast<uint2*>(dys + ((size_t)(r * Wp + 2 * pxl) * NTp) * 8 + net * 2 * CO);
-        uint2* d1 = reinterpret_cast<uint2*>(dys + ((size_t)(r * Wp + 2 * pxl + 1) * NTp) * 8 + net * 2 * CO);
 #pragma unroll
-        for (int v = 0; v < 5; ++v) { d0[v] = make_uint2(w0[2 * v], w0[2 * v + 1]); d1[v] = make_uint2(w1[2 * v], w1[2 * v + 1]); }
+        for (int pa = 0; pa < 4; ++pa) {
+          uint32_t w[10];                                              // [hi(10) | lo(10)] halves of this pixel and network
+#pragma unroll
+          for (int v = 0; v < 5; ++v) {
+            const uint32_t m = (a0[v] == (uint32_t)pa ? 0x0000ffffu : 0u) | (a1[v] == (uint32_t)pa ? 0xffff0000u : 0u);
+            w[v] = hi2[v] & m; w[5 + v] = lo2[v] & m;
+          }
+          uint2* d = reinterpret_cast<uint2*>(dys + ((size_t)((2 * pyl + (pa >> 1)) * Wp + 2 * pxl + (pa & 1)) * NTp) * 8 + net * 2 * CO);
+#pragma unroll
+          for (int v = 0; v < 5; ++v) d[v] = make_uint2(w[2 * v], w[2 * v + 1]);
+        }
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -270,6 +275,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     uint8_t* planes = smem + buf * L.buf_stride + L.planes;
     const uint32_t ONE = 0x3C00u;                                          // fp16 1.0
     const int nwarps = nthr >> 5;
+    const bool fast_r2 = P.R == 2 && KS == 5 && C == 8 * P.G8 + 1;          // c3: 9 pixels channels + 1
     for (int item = warp; item < P.nvec * rows_in; item += nwarps) {
       const int v = item / rows_in, lr = item - v * rows_in;
       const int y = y0 - PAD + lr;
@@ -292,6 +298,22 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
             }
           }
           dst[lc] = val;
+        }
+      } else if (fast_r2) {
+        // one real remainder channel + the constant-one channel: entry pair kx = (pixel[x + kx - PAD][8 G8], inside ? 1 : 0);
+        // both packed planes of this row in one pass (plane G8: kx 0..3, plane G8 + 1: kx 4)
+        if (v != P.G8) continue;
+        uint4* dst1 = reinterpret_cast<uint4*>(planes + (size_t)(v + 1) * P.plane_bytes + (size_t)lr * pitch * 16);
+        const unsigned short* rp = rowp + 8 * P.G8;
+        for (int lc = lane; lc < pitch; lc += 32) {
+          uint32_t w[5];
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const int xin = lc + kx - PAD;
+            w[kx] = (xin >= 0 && xin < W && lc < Wp) ? ((uint32_t)rp[xin * C] | (ONE << 16)) : 0u;
+          }
+          dst[lc] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst1[lc] = make_uint4(w[4], 0u, 0u, 0u);
         }
       } else {
         const int j = v - P.G8;                                            // packed: entry e <-> (kx, channel) from the table
@@ -477,7 +499,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
   CPP_REQUIRE(P->smem_bytes <= 220 * 1024, "wgrad_mma: %dx%dx%d does not fit shared memory", H, W, C);
   P->bands_per_image = (int)ceil_div(H, P->band_rows);
   P->total_bands = B * P->bands_per_image;
-  CPP_REQUIRE(P->band_rows * (P->Wp / 2) * nets <= kDyItems * 32 * P->NW, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
+  CPP_REQUIRE((P->band_rows / 2) * (P->Wp / 2) * nets <= kDyItems * 32 * P->NW, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
   CPP_REQUIRE(P->nR <= 8, "wgrad_mma: too many packed planes");
   const int occ = (P->MT * P->NT <= 16 && P->smem_bytes <= 110 * 1024) ? 2 : 1;
   P->grid = std::max(1, std::min(P->total_bands, sm_budget() * occ));
