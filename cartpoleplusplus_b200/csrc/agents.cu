@@ -112,7 +112,7 @@ int DDPG::actor_backward(const void* s1, int is_f16, int B, int B_global, cudaSt
   CPP_TRY(actor.backward(buf.params, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s, 1, wg_scr, tc_scr1));
   {
     const Net* g[1] = {&actor}; char* wss[1] = {ws_actor}; float* gr[1] = {buf.grads};
-    CPP_TRY(conv1_wgrad_group(1, g, wss, gr, s1, is_f16, m1, B, wg_scr, s));
+    CPP_TRY(conv1_wgrad_group(1, g, wss, gr, s1, is_f16, m1, B, wg_scr, s, 1));
   }
   critic_trunk_valid = true; trunk_B = B;
   return CPP_OK;
@@ -160,7 +160,7 @@ int DDPG::critic_backward(const void* s1, const float* action, const float* rewa
   CPP_TRY(critic.backward(buf.params + off_c, s1, is_f16, cur_m1, B, ws_critic, dq, buf.grads + off_c, nullptr, s, 1, wg_scr, tc_scr1));
   {
     const Net* g[1] = {&critic}; char* wss[1] = {ws_critic}; float* gr[1] = {buf.grads + off_c};
-    CPP_TRY(conv1_wgrad_group(1, g, wss, gr, s1, is_f16, cur_m1, B, wg_scr, s));
+    CPP_TRY(conv1_wgrad_group(1, g, wss, gr, s1, is_f16, cur_m1, B, wg_scr, s, 1));
   }
   critic_trunk_valid = false;
   return CPP_OK;
@@ -281,7 +281,7 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   // ---- conv1 weight gradients of both networks in one pass over state_1; whole GPU
   {
     char* wss[2] = {ws_actor, ws_critic}; float* gr[2] = {buf.grads, buf.grads + off_c};
-    CPP_TRY(conv1_wgrad_group(2, g2, wss, gr, s1, is_f16, m1, B, wgs[0], s0));
+    CPP_TRY(conv1_wgrad_group(2, g2, wss, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
   }
   tr.mark("s0 conv1 wgrad {actor,critic} done", s0);
   if (with_apply) { CPP_TRY(actor_apply(s0)); CPP_TRY(critic_apply(s0)); }
@@ -471,7 +471,7 @@ int NAF::backward(const void* s1, const float* action, const float* reward, cons
   {  // conv1 weight gradients of the three networks in one pass over state_1
     const Net* g[3] = {&value, &mu, &l}; char* wss[3] = {ws_v, ws_m, ws_l};
     float* gr[3] = {buf.grads, buf.grads + off_m, buf.grads + off_l};
-    CPP_TRY(conv1_wgrad_group(3, g, wss, gr, s1, is_f16, cur_m1, B, wg_scr, s));
+    CPP_TRY(conv1_wgrad_group(3, g, wss, gr, s1, is_f16, cur_m1, B, wg_scr, s, 1));
   }
   return CPP_OK;
 }

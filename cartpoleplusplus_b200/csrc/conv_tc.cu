@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
         if (P.dgrad) {
           // input-gradient mode: no bias / ReLU / pool, the four window positions are four output pixels
           const float osc = scale_inv * P.out_scale[0];
+          float amx = 0.f;
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             uint32_t r[20];
@@ -322,10 +323,18 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
             if (valid && y < H && x < W) {
               float* op = P.pooled[0] + (((size_t)b * H + y) * W + x) * CO;
 #pragma unroll
-              for (int o = 0; o < CO; o += 2)
-                *reinterpret_cast<float2*>(op + o) = make_float2((__uint_as_float(r[o]) + __uint_as_float(r[CO + o])) * osc,
-                                                                 (__uint_as_float(r[o + 1]) + __uint_as_float(r[CO + o + 1])) * osc);
+              for (int o = 0; o < CO; o += 2) {
+                const float v0 = (__uint_as_float(r[o]) + __uint_as_float(r[CO + o])) * osc;
+                const float v1 = (__uint_as_float(r[o + 1]) + __uint_as_float(r[CO + o + 1])) * osc;
+                *reinterpret_cast<float2*>(op + o) = make_float2(v0, v1);
+                amx = fmaxf(amx, fmaxf(fabsf(v0), fabsf(v1)));
+              }
             }
+          }
+          if (P.out_absmax != nullptr) {               // max is order independent: an atomic keeps the result deterministic
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, sft));
+            if (lane == 0 && amx > 0.f) atomicMax(reinterpret_cast<int*>(P.out_absmax), __float_as_int(amx));
           }
           tc_fence_before();
           __syncwarp();
@@ -741,10 +750,12 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
 }
 
 int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
-                         void* scratch, cudaStream_t s) {
+                         void* scratch, cudaStream_t s, float* out_absmax) {
   if (B <= 0) return CPP_OK;
   FwdPlan P{};
   CPP_TRY(build_plan(1, B, H, W, kC24, KS, &P, 1));
+  P.out_absmax = out_absmax;
+  if (out_absmax != nullptr) CPP_CHECK_CUDA(cudaMemsetAsync(out_absmax, 0, sizeof(float), s));
   CPP_REQUIRE(((uintptr_t)dy_pieces & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
   P.Cw = CO; P.in_layout = 2;
   P.x = reinterpret_cast<const __half*>(dy_pieces); P.rows = nullptr;

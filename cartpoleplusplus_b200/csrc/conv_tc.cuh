@@ -39,6 +39,7 @@ struct FwdPlan {
   int dgrad;                // 1: input-gradient mode - x = un-pooled output gradient pieces, taps flipped and channels transposed,
                             //    no bias / ReLU / pool: every conv position is written to the dense fp32 output pooled[n] [B][H][W][10]
   const float* out_scale;   // dgrad: device scalar the result is multiplied with (undoes the power-of-two scaling of the pieces)
+  float* out_absmax;        // dgrad, optional: max |dx| is atomically max-ed into this device float (the next weight gradient's scale)
   int nets, N;              // MMA N = round_up(nets * kPieces * 10, 16)
   // ---- shared-memory geometry
   int G8, R, nR;            // full 8-channel groups, remainder channels, packed slabs per ky
@@ -74,7 +75,7 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
 // (launch_unpool_split);
 // dx fp32 [B][H][W][10].
 int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
-                         void* scratch, cudaStream_t s);
+                         void* scratch, cudaStream_t s, float* out_absmax = nullptr);
 // un-pool + split: d_pooled fp32 [B][H/2][W/2][10] and the arg-max side band -> dy_pieces fp16 [B][H][W][24], scaled by
 // a power of two from max|d_pooled| (gmax: device float, zeroed and filled here); inv_scale receives 1/scale
 int launch_unpool_split(const float* d_pooled, const uint8_t* amax, int B, int H, int W, float* gmax, float* inv_scale,

@@ -151,15 +151,23 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   bool first_flush = true;
   auto flush = [&]() {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+    for (int mt = 0; mt < MT; ++mt) {
+      float* p = part + ((size_t)((warp * MT + mt) * NT) * 4) * 32 + lane;
+      float old[NT][4];
+      if (!first_flush) {                              // all loads of this M tile in flight together, then add + store
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) old[nt][r] = __ldcg(p + (nt * 4 + r) * 32);
+      }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          float* p = part + ((size_t)((warp * MT + mt) * NT + nt) * 4 + r) * 32 + lane;
-          *p = first_flush ? acc[mt][nt][r] : (*p + acc[mt][nt][r]);
+          __stcg(p + (nt * 4 + r) * 32, first_flush ? acc[mt][nt][r] : old[nt][r] + acc[mt][nt][r]);
           acc[mt][nt][r] = 0.f;
         }
+    }
     first_flush = false;
   };
 
@@ -169,8 +177,20 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   const int wp2 = Wp / 2, hp = BR / 2, dy_items = hp * wp2 * nets;
   float2 gq[kDyItems][5];
   unsigned short aq[kDyItems][5];
+  int it_net[kDyItems], it_pxl[kDyItems], it_pyl[kDyItems];            // this thread's items: the same for every band
+#pragma unroll
+  for (int k = 0; k < kDyItems; ++k) {
+    const int it = tid + k * nthr;
+    it_net[k] = it % nets; it_pxl[k] = (it / nets) % wp2; it_pyl[k] = it / (nets * wp2);
+  }
+  int cur_b = 0, cur_bi = 0, nxt_b = 0, nxt_bi = 0;                    // (image, band-in-image) of the band being multiplied / staged
+  int cur_band = -1, nxt_band = -1;
   auto band_rows_of = [&](int band, int& b, int& y0, int& ylo, int& yhi) {
-    b = band / P.bands_per_image; y0 = (band - b * P.bands_per_image) * BR;
+    int bb, bi;
+    if (band == cur_band) { bb = cur_b; bi = cur_bi; }
+    else if (band == nxt_band) { bb = nxt_b; bi = nxt_bi; }
+    else { bb = band / P.bands_per_image; bi = band - bb * P.bands_per_image; nxt_band = band; nxt_b = bb; nxt_bi = bi; }
+    b = bb; y0 = bi * BR;
     ylo = max(0, y0 - PAD); yhi = min(H, y0 + BR + PAD);
   };
   // (1) global -> shared / registers, asynchronous
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
 #pragma unroll
       for (int v = 0; v < 5; ++v) { gq[k][v] = make_float2(0.f, 0.f); aq[k][v] = 0x0404; }
       if (it < dy_items) {
-        const int net = it % nets, t2 = it / nets, pxl = t2 % wp2, pyl = t2 / wp2;
+        const int net = it_net[k], pxl = it_pxl[k], pyl = it_pyl[k];
         const int py = (y0 >> 1) + pyl;
         if (py < PH && pxl < PW) {
           const size_t idx = (((size_t)b * PH + py) * PW + pxl) * CO;
@@ -239,7 +259,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     for (int k = 0; k < kDyItems; ++k) {
       const int it = tid + k * nthr;
       if (it < dy_items) {
-        const int net = it % nets, t2 = it / nets, pxl = t2 % wp2, pyl = t2 / wp2;
+        const int net = it_net[k], pxl = it_pxl[k], pyl = it_pyl[k];
         const float sc = s_scale[net];
         uint32_t hi2[5], lo2[5], a0[5], a1[5];                         // 10 filters as 5 half2 words + their arg-max bytes
 #pragma unroll
@@ -276,8 +296,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     const uint32_t ONE = 0x3C00u;                                          // fp16 1.0
     const int nwarps = nthr >> 5;
     const bool fast_r2 = P.R == 2 && KS == 5 && C == 8 * P.G8 + 1;          // c3: 9 pixels channels + 1
-    for (int item = warp; item < P.nvec * rows_in; item += nwarps) {
-      const int v = item / rows_in, lr = item - v * rows_in;
+    for (int v = 0; v < P.nvec; ++v)
+    for (int lr = warp; lr < rows_in; lr += nwarps) {
       const int y = y0 - PAD + lr;
       uint4* dst = reinterpret_cast<uint4*>(planes + (size_t)v * P.plane_bytes + (size_t)lr * pitch * 16);
       if (y < ylo || y >= yhi) {
@@ -348,10 +368,16 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   for (int band = band0; band < band1; ++band) {
     const int buf = (band - band0) & 1;
     const bool has_next = band + 1 < band1;
+    if (band == nxt_band) { cur_band = band; cur_b = nxt_b; cur_bi = nxt_bi; }
+    else { cur_band = band; cur_b = band / P.bands_per_image; cur_bi = band - cur_b * P.bands_per_image; }
+    if (has_next) {                                                        // next band without a division
+      nxt_band = band + 1; nxt_b = cur_b; nxt_bi = cur_bi + 1;
+      if (nxt_bi == P.bands_per_image) { nxt_bi = 0; ++nxt_b; }
+    }
     if (has_next) issue_loads(band + 1, buf ^ 1);
     // ---- MMAs: K runs over the band's output pixels, 16 per step
     {
-      const int y0 = (band % P.bands_per_image) * BR;
+      const int y0 = cur_bi * BR;
       const int ly_end = min(BR, H - y0);
       const uint32_t boff = (uint32_t)buf * L.buf_stride;
       for (int ly = 0; ly < ly_end; ++ly)

@@ -183,20 +183,23 @@ int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net) {
 }
 
 int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* const* grads, const void* state, int is_f16,
-                      const float* mean_inv, int B, void* scratch, cudaStream_t s) {
+                      const float* mean_inv, int B, void* scratch, cudaStream_t s, int gmax_from_dgrad) {
   const Net& n0 = *nets[0];
   if (!n0.pixels) return CPP_OK;
   CPP_REQUIRE(n >= 1 && n <= wg::kMaxNets, "conv1 wgrad group of %d networks", n);
   const ConvLayer& c1 = n0.conv[0];
   const float* gp[wg::kMaxNets]; const uint8_t* am[wg::kMaxNets]; float* dw[wg::kMaxNets]; float* db[wg::kMaxNets];
+  const float* gm[wg::kMaxNets];
   for (int i = 0; i < n; ++i) {
     const Net::Layout L = nets[i]->layout(B);
+    gm[i] = reinterpret_cast<const float*>(ws[i] + L.gsc) + 6;
     gp[i] = reinterpret_cast<const float*>(ws[i] + L.dpool[1]);
     am[i] = reinterpret_cast<const uint8_t*>(ws[i] + L.amax[0]);
     dw[i] = grads[i] + nets[i]->off_conv_w[0]; db[i] = grads[i] + nets[i]->off_conv_b[0];
   }
   if (scratch != nullptr && n0.tc_route(is_f16) && wg::conv_wgrad_mma_supported(n, c1.H, c1.W, c1.Cin, c1.KS))
-    return wg::launch_conv_wgrad_mma(state, mean_inv, 0, n, gp, am, B, c1.H, c1.W, c1.Cin, c1.KS, dw, db, scratch, s);
+    return wg::launch_conv_wgrad_mma(state, mean_inv, 0, n, gp, am, B, c1.H, c1.W, c1.Cin, c1.KS, dw, db, scratch, s,
+                                     gmax_from_dgrad ? gm : nullptr);
   for (int i = 0; i < n; ++i) {
     const Net::Layout L = nets[i]->layout(B);
     CPP_TRY(launch_conv_wgrad(c1, state, is_f16, mean_inv, gp[i], am[i], B, dw[i], db[i], reinterpret_cast<float*>(ws[i] + L.wgrad), s));
@@ -343,7 +346,8 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
       float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
       if (tc_dg) {
         CPP_TRY(tc::launch_conv_dgrad_tc(reinterpret_cast<__half*>(ws + L.dyp), gsc + 1, params + off_conv_w[i], B, conv[i].H, conv[i].W,
-                                         conv[i].KS, dx, tc_scratch, s));
+                                         conv[i].KS, dx, tc_scratch, s,
+                                         i == 1 ? reinterpret_cast<float*>(ws + L.gsc) + 6 : nullptr));   // max|d(pooled1)| for conv1's wgrad
       } else {
         CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));
       }

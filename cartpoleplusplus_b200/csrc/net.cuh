@@ -81,8 +81,10 @@ void set_conv1_tc_enabled(int on);     // -1: back to the CARTPOLEPP_CONV1 envir
 // conv1 weight/bias gradients of n sibling networks whose backward passes were run with defer_conv1 (tensor cores,
 // conv_wgrad_mma.cu, when the state is fp16 and scratch is given; the exact-fp32 CUDA-core kernel otherwise)
 int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net);
+// gmax_from_dgrad: the backward passes ran conv2's input gradient on the tensor cores (tc_scratch given), which left
+// max|d(pooled1)| of every network in its workspace - no separate max pass is needed
 int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* const* grads, const void* state, int is_f16,
-                      const float* mean_inv, int B, void* scratch, cudaStream_t s);
+                      const float* mean_inv, int B, void* scratch, cudaStream_t s, int gmax_from_dgrad = 0);
 
 // elementwise.cu
 int64_t moments_scratch_doubles(int C);
