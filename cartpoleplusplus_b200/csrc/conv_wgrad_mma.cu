@@ -97,7 +97,7 @@ __host__ __device__ inline Smem smem_layout(const Plan& P) {
   return L;
 }
 
-constexpr int kDyItems = 2;        // (2x2 window, network) items a thread may own per band
+constexpr int kDyItems = 1;        // (2x2 window, network) items a thread owns per band (the plan shrinks the band if there are more)
 
 template <int MT, int NT>
 __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_wgrad_mma_kernel(const __grid_constant__ Plan P) {
@@ -151,23 +151,18 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   bool first_flush = true;
   auto flush = [&]() {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      float* p = part + ((size_t)((warp * MT + mt) * NT) * 4) * 32 + lane;
-      float old[NT][4];
-      if (!first_flush) {                              // all loads of this M tile in flight together, then add + store
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
+      for (int nt = 0; nt < NT; ++nt) {
+        float* p = part + ((size_t)((warp * MT + mt) * NT + nt) * 4) * 32 + lane;
+        float old[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!first_flush) {                              // four independent loads in flight, then add + store
 #pragma unroll
-          for (int r = 0; r < 4; ++r) old[nt][r] = __ldcg(p + (nt * 4 + r) * 32);
-      }
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          __stcg(p + (nt * 4 + r) * 32, first_flush ? acc[mt][nt][r] : old[nt][r] + acc[mt][nt][r]);
-          acc[mt][nt][r] = 0.f;
+          for (int r = 0; r < 4; ++r) old[r] = __ldcg(p + r * 32);
         }
-    }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { __stcg(p + r * 32, old[r] + acc[mt][nt][r]); acc[mt][nt][r] = 0.f; }
+      }
     first_flush = false;
   };
 
@@ -177,26 +172,23 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   const int wp2 = Wp / 2, hp = BR / 2, dy_items = hp * wp2 * nets;
   float2 gq[kDyItems][5];
   unsigned short aq[kDyItems][5];
-  int it_net[kDyItems], it_pxl[kDyItems], it_pyl[kDyItems];            // this thread's items: the same for every band
+  int it_pack[kDyItems];                                               // this thread's items (net | window col << 4 | window row << 20): the same for every band
 #pragma unroll
   for (int k = 0; k < kDyItems; ++k) {
     const int it = tid + k * nthr;
-    it_net[k] = it % nets; it_pxl[k] = (it / nets) % wp2; it_pyl[k] = it / (nets * wp2);
+    it_pack[k] = (it % nets) | (((it / nets) % wp2) << 4) | ((it / (nets * wp2)) << 20);
   }
-  int cur_b = 0, cur_bi = 0, nxt_b = 0, nxt_bi = 0;                    // (image, band-in-image) of the band being multiplied / staged
-  int cur_band = -1, nxt_band = -1;
-  auto band_rows_of = [&](int band, int& b, int& y0, int& ylo, int& yhi) {
-    int bb, bi;
-    if (band == cur_band) { bb = cur_b; bi = cur_bi; }
-    else if (band == nxt_band) { bb = nxt_b; bi = nxt_bi; }
-    else { bb = band / P.bands_per_image; bi = band - bb * P.bands_per_image; nxt_band = band; nxt_b = bb; nxt_bi = bi; }
+  int cur_b = 0, cur_bi = 0;                                            // (image, band-in-image) of the band being multiplied
+  auto band_rows_of = [&](bool next, int& b, int& y0, int& ylo, int& yhi) {   // next: the band after the current one (no division)
+    int bb = cur_b, bi = cur_bi;
+    if (next && ++bi == P.bands_per_image) { bi = 0; ++bb; }
     b = bb; y0 = bi * BR;
     ylo = max(0, y0 - PAD); yhi = min(H, y0 + BR + PAD);
   };
   // (1) global -> shared / registers, asynchronous
-  auto issue_loads = [&](int band, int buf) {
+  auto issue_loads = [&](bool next, int buf) {
     int b, y0, ylo, yhi;
-    band_rows_of(band, b, y0, ylo, yhi);
+    band_rows_of(next, b, y0, ylo, yhi);
     const __half* src = P.x + ((size_t)b * H + ylo) * rowC;
     const int n_bytes = (yhi - ylo) * rowC * 2;
     const uint32_t dst = smem_u + L.raw;
@@ -233,7 +225,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
 #pragma unroll
       for (int v = 0; v < 5; ++v) { gq[k][v] = make_float2(0.f, 0.f); aq[k][v] = 0x0404; }
       if (it < dy_items) {
-        const int net = it_net[k], pxl = it_pxl[k], pyl = it_pyl[k];
+        const int net = it_pack[k] & 15, pxl = (it_pack[k] >> 4) & 0xffff, pyl = it_pack[k] >> 20;
         const int py = (y0 >> 1) + pyl;
         if (py < PH && pxl < PW) {
           const size_t idx = (((size_t)b * PH + py) * PW + pxl) * CO;
@@ -246,9 +238,9 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     }
   };
   // (2) registers -> dY pieces of buffer `buf`; raw rows that cp.async cannot move (2-byte granular) are copied here
-  auto stage_dy = [&](int band, int buf) {
+  auto stage_dy = [&](bool next, int buf) {
     int b, y0, ylo, yhi;
-    band_rows_of(band, b, y0, ylo, yhi);
+    band_rows_of(next, b, y0, ylo, yhi);
     if (raw_mode == 0 && P.dup != 2) {
       unsigned short* d = reinterpret_cast<unsigned short*>(smem + L.raw);
       const unsigned short* s2 = reinterpret_cast<const unsigned short*>(P.x + ((size_t)b * H + ylo) * rowC);
@@ -259,7 +251,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     for (int k = 0; k < kDyItems; ++k) {
       const int it = tid + k * nthr;
       if (it < dy_items) {
-        const int net = it_net[k], pxl = it_pxl[k], pyl = it_pyl[k];
+        const int net = it_pack[k] & 15, pxl = (it_pack[k] >> 4) & 0xffff, pyl = it_pack[k] >> 20;
         const float sc = s_scale[net];
         uint32_t hi2[5], lo2[5], a0[5], a1[5];                         // 10 filters as 5 half2 words + their arg-max bytes
 #pragma unroll
@@ -289,15 +281,15 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   };
   // (3) raw rows -> planes of buffer `buf`: 16-byte channel-group vectors per pixel (zero padding; constant-one channel at C).
   // One warp per (plane, input row), lanes along the columns: no per-vector index arithmetic.
-  auto stage_planes = [&](int band, int buf) {
+  auto stage_planes = [&](bool next, int buf) {
     int b, y0, ylo, yhi;
-    band_rows_of(band, b, y0, ylo, yhi);
+    band_rows_of(next, b, y0, ylo, yhi);
     uint8_t* planes = smem + buf * L.buf_stride + L.planes;
     const uint32_t ONE = 0x3C00u;                                          // fp16 1.0
     const int nwarps = nthr >> 5;
     const bool fast_r2 = P.R == 2 && KS == 5 && C == 8 * P.G8 + 1;          // c3: 9 pixels channels + 1
-    for (int v = 0; v < P.nvec; ++v)
-    for (int lr = warp; lr < rows_in; lr += nwarps) {
+    for (int item = warp; item < P.nvec * rows_in; item += nwarps) {
+      const int v = item / rows_in, lr = item - v * rows_in;
       const int y = y0 - PAD + lr;
       uint4* dst = reinterpret_cast<uint4*>(planes + (size_t)v * P.plane_bytes + (size_t)lr * pitch * 16);
       if (y < ylo || y >= yhi) {
@@ -358,23 +350,18 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   const int band1 = (int)((long long)P.total_bands * (blockIdx.x + 1) / gridDim.x);
   __syncthreads();                                                         // s_scale, zeroed dY buffers
   if (band0 < band1) {
-    issue_loads(band0, 0);
-    stage_dy(band0, 0);
+    cur_b = band0 / P.bands_per_image; cur_bi = band0 - cur_b * P.bands_per_image;
+    issue_loads(false, 0);
+    stage_dy(false, 0);
     __syncthreads();
-    if (P.dup != 2) stage_planes(band0, 0);
+    if (P.dup != 2) stage_planes(false, 0);
   }
   __syncthreads();
   int since_flush = 0;
   for (int band = band0; band < band1; ++band) {
     const int buf = (band - band0) & 1;
     const bool has_next = band + 1 < band1;
-    if (band == nxt_band) { cur_band = band; cur_b = nxt_b; cur_bi = nxt_bi; }
-    else { cur_band = band; cur_b = band / P.bands_per_image; cur_bi = band - cur_b * P.bands_per_image; }
-    if (has_next) {                                                        // next band without a division
-      nxt_band = band + 1; nxt_b = cur_b; nxt_bi = cur_bi + 1;
-      if (nxt_bi == P.bands_per_image) { nxt_bi = 0; ++nxt_b; }
-    }
-    if (has_next) issue_loads(band + 1, buf ^ 1);
+    if (has_next) issue_loads(true, buf ^ 1);
     // ---- MMAs: K runs over the band's output pixels, 16 per step
     {
       const int y0 = cur_bi * BR;
@@ -397,12 +384,13 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
         }
     }
     if (has_next) {
-      stage_dy(band + 1, buf ^ 1);                                         // buffer buf^1 was last read one iteration ago
+      stage_dy(true, buf ^ 1);                                         // buffer buf^1 was last read one iteration ago
       __syncthreads();                                                     // raw rows of band+1 are complete in shared memory
-      if (P.dup != 2) stage_planes(band + 1, buf ^ 1);
+      if (P.dup != 2) stage_planes(true, buf ^ 1);
     }
     __syncthreads();                                                       // band+1 staged; every warp is done reading `buf` and raw
     if (++since_flush >= P.flush_every) { flush(); since_flush = 0; }
+    if (++cur_bi == P.bands_per_image) { cur_bi = 0; ++cur_b; }             // advance to the next band
   }
   if (since_flush > 0 || first_flush) flush();
 }
@@ -510,7 +498,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
   P->NTp = P->NT | 1;
   P->raw_bytes = dup == 2 ? 0 : (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
   P->smem_bytes = (int)smem_layout(*P).total;
-  if (P->smem_bytes > 220 * 1024) {        // wide images: two-row bands keep both staging buffers inside one SM's shared memory
+  if (P->smem_bytes > 220 * 1024 || (P->band_rows / 2) * (P->Wp / 2) * nets > kDyItems * 32 * P->NW) {        // wide images: two-row bands keep both staging buffers inside one SM's shared memory
     P->band_rows = 2;
     P->rows_in = P->band_rows + 2 * P->PAD;
     P->plane_bytes = P->rows_in * P->pitch * 16;
@@ -527,6 +515,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
   P->total_bands = B * P->bands_per_image;
   CPP_REQUIRE((P->band_rows / 2) * (P->Wp / 2) * nets <= kDyItems * 32 * P->NW, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
   CPP_REQUIRE(P->nR <= 8, "wgrad_mma: too many packed planes");
+
   const int occ = (P->MT * P->NT <= 16 && P->smem_bytes <= 110 * 1024) ? 2 : 1;
   P->grid = std::max(1, std::min(P->total_bands, sm_budget() * occ));
   // bound the tensor-core accumulation chains to ~128 MMA steps between fp32 flushes
