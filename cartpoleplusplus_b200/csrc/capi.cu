@@ -73,6 +73,7 @@ int cpp_set_option(const char* name, int32_t value) {
   API_BEGIN
   NEED(name);
   if (strcmp(name, "conv1_tc") == 0) { set_conv1_tc_enabled(value); return CPP_OK; }
+  if (strcmp(name, "fused_mlp") == 0) { set_fused_mlp(value); return CPP_OK; }
   if (strcmp(name, "streams") == 0) { set_step_options(value, -2); return CPP_OK; }
   if (strcmp(name, "graphs") == 0) { set_step_options(-2, value); return CPP_OK; }
   set_error("unknown option `%s`", name);

@@ -1,0 +1,260 @@
+// Fused fully connected stacks (slim.fully_connected chains, base_network.py:58-71; ddpg_cartpole.py:95-100,168-184;
+// naf_cartpole.py:105-109,156-184).  The layers are tiny (K <= 2560, N <= 200, batch 256): one GEMM launch per layer is
+// pure launch / dependency latency on the critical path of a step, so
+//   mlp_forward_kernel   runs layers [first, end) of one network for 8 batch rows per CTA, activations in shared memory,
+//   mlp_dgrad_kernel     runs the chain of input gradients dX_i = (dPre_i . W_i^T) * relu'(h_{i-1}) from the top down,
+// both writing every intermediate (activations h_i, gradients dPre_i) to the workspace, because the weight gradients
+// (x^T . dPre, the plain GEMM of fc.cu on a side stream) need them.  Exact fp32 FFMA with a fixed summation order.
+#include "net.cuh"
+
+namespace cpp {
+
+constexpr int kRows = 8;          // batch rows per CTA
+constexpr int kMlpThreads = 256;
+
+struct MlpLayer {
+  const float* W; const float* b;   // [in][out], [out]
+  float* h;                         // activation output in the workspace [B][h_ld]
+  float* dX;                        // backward: gradient wrt this layer's input [B][in]
+  int in, out, act, h_ld;
+  int action_in;                    // 1: the last action_dim inputs of this layer are the action (tf.concat, ddpg_cartpole.py:170,175)
+};
+
+struct MlpArgs {
+  MlpLayer L[CPP_MAX_FC];
+  int first, end;                   // forward: layers [first, end);  backward: layers end-1 down to first
+  int B, action_dim;
+  const float* x; int x_ld, x_cols; // forward: input of layer `first` without the action columns
+  float* x_tail;                    // forward: where the action columns of that input live in the workspace (or NULL)
+  const float* action;              // forward: [B][action_dim] or NULL
+  // backward
+  const float* d_out;               // [B][out(end-1)] gradient wrt the post-activation output of layer end-1
+  float* dTop;                      // [B][out(end-1)] gradient wrt its pre-activation (kept for the weight gradient)
+  float* d_action;                  // [B][action_dim] or NULL
+  int need_dx_first;                // 1: also produce dX of layer `first`
+  int maxw;
+};
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? tanhf(v) : v);
+}
+
+// ------------------------------------------------------------------------------------------ forward
+// shared: xa / xb [maxw][kRows] (k-major so that one k is two float4 loads for all 8 rows), red [kMlpThreads][kRows]
+__global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_constant__ MlpArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  float* xa = sm;
+  float* xb = sm + (size_t)A.maxw * kRows;
+  float* red = xb + (size_t)A.maxw * kRows;
+  const int tid = threadIdx.x, row0 = blockIdx.x * kRows;
+  const int nrow = min(kRows, A.B - row0);
+  // input of the first layer (coalesced along k), then its action columns
+  for (int r = 0; r < kRows; ++r)
+    for (int k = tid; k < A.x_cols; k += kMlpThreads) xa[k * kRows + r] = r < nrow ? A.x[(size_t)(row0 + r) * A.x_ld + k] : 0.f;
+  if (A.L[A.first].action_in) {
+    for (int i = tid; i < kRows * A.action_dim; i += kMlpThreads) {
+      const int r = i / A.action_dim, j = i - r * A.action_dim;
+      const float v = r < nrow ? A.action[(size_t)(row0 + r) * A.action_dim + j] : 0.f;
+      xa[(A.x_cols + j) * kRows + r] = v;
+      if (r < nrow && A.x_tail) A.x_tail[(size_t)(row0 + r) * A.x_ld + j] = v;
+    }
+  }
+  __syncthreads();
+  for (int l = A.first; l < A.end; ++l) {
+    const MlpLayer& Ly = A.L[l];
+    const int N = Ly.out, K = Ly.in;
+    const int npad = (N + 31) & ~31;
+    const int ks = max(1, min(8, kMlpThreads / npad));          // K slices: threads beyond one column set split the reduction
+    const int slice = tid / npad, n = tid - slice * npad;
+    float acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+    if (slice < ks && n < N) {
+      const float* w = Ly.W + n;
+#pragma unroll 4
+      for (int k = slice; k < K; k += ks) {
+        const float wv = __ldg(w + (size_t)k * N);
+        const float4 x0 = *reinterpret_cast<const float4*>(xa + k * kRows), x1 = *reinterpret_cast<const float4*>(xa + k * kRows + 4);
+        acc[0] = fmaf(x0.x, wv, acc[0]); acc[1] = fmaf(x0.y, wv, acc[1]); acc[2] = fmaf(x0.z, wv, acc[2]); acc[3] = fmaf(x0.w, wv, acc[3]);
+        acc[4] = fmaf(x1.x, wv, acc[4]); acc[5] = fmaf(x1.y, wv, acc[5]); acc[6] = fmaf(x1.z, wv, acc[6]); acc[7] = fmaf(x1.w, wv, acc[7]);
+      }
+    }
+    if (ks > 1) {                                                // fixed-order reduction over the K slices
+      if (slice > 0 && slice < ks && n < N) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) red[(size_t)tid * kRows + r] = acc[r];
+      }
+      __syncthreads();
+      if (slice == 0 && n < N)
+        for (int s2 = 1; s2 < ks; ++s2)
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) acc[r] += red[(size_t)(s2 * npad + n) * kRows + r];
+    }
+    const bool more = l + 1 < A.end;
+    if (slice == 0 && n < N) {
+      const float bv = Ly.b[n];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const float v = act_fwd(acc[r] + bv, Ly.act);
+        if (more) xb[n * kRows + r] = v;
+        if (r < nrow) Ly.h[(size_t)(row0 + r) * Ly.h_ld + n] = v;
+      }
+    }
+    if (more && A.L[l + 1].action_in) {                          // the next layer reads [h | action]
+      for (int i = tid; i < kRows * A.action_dim; i += kMlpThreads) {
+        const int r = i / A.action_dim, j = i - r * A.action_dim;
+        const float v = r < nrow ? A.action[(size_t)(row0 + r) * A.action_dim + j] : 0.f;
+        xb[(N + j) * kRows + r] = v;
+        if (r < nrow) Ly.h[(size_t)(row0 + r) * Ly.h_ld + N + j] = v;
+      }
+    }
+    __syncthreads();
+    float* t = xa; xa = xb; xb = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ input-gradient chain
+// One warp per input column k, lanes over the output columns n (coalesced reads of W[k][:]), shuffle reduction.
+// shared: da / db [maxw][kRows]
+__global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_constant__ MlpArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  float* da = sm;
+  float* db = sm + (size_t)A.maxw * kRows;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = blockIdx.x * kRows;
+  const int nrow = min(kRows, A.B - row0);
+  const int last = A.end - 1;
+  {   // gradient wrt the last pre-activation: d_out * act'(out)
+    const MlpLayer& Ly = A.L[last];
+    for (int i = tid; i < kRows * Ly.out; i += kMlpThreads) {
+      const int r = i / Ly.out, n = i - r * Ly.out;
+      float g = 0.f;
+      if (r < nrow) {
+        g = A.d_out[(size_t)(row0 + r) * Ly.out + n];
+        const float y = Ly.h[(size_t)(row0 + r) * Ly.h_ld + n];
+        if (Ly.act == 1) g = y > 0.f ? g : 0.f;
+        else if (Ly.act == 2) g = g * (1.f - y * y);
+        A.dTop[(size_t)(row0 + r) * Ly.out + n] = g;
+      }
+      da[n * kRows + r] = g;
+    }
+  }
+  __syncthreads();
+  for (int l = last; l >= A.first; --l) {
+    if (l == A.first && !A.need_dx_first) break;
+    const MlpLayer& Ly = A.L[l];
+    const int N = Ly.out, K = Ly.in;
+    const int relu_cols = l > 0 ? A.L[l - 1].out : 0;               // the first relu_cols inputs are the ReLU output of layer l-1
+    const float* hprev = l > 0 ? A.L[l - 1].h : nullptr;
+    const int hprev_ld = l > 0 ? A.L[l - 1].h_ld : 0;
+    for (int k = warp; k < K; k += kMlpThreads / 32) {
+      float acc[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+      const float* w = Ly.W + (size_t)k * N;
+      for (int n = lane; n < N; n += 32) {
+        const float wv = __ldg(w + n);
+        const float4 d0 = *reinterpret_cast<const float4*>(da + n * kRows), d1 = *reinterpret_cast<const float4*>(da + n * kRows + 4);
+        acc[0] = fmaf(d0.x, wv, acc[0]); acc[1] = fmaf(d0.y, wv, acc[1]); acc[2] = fmaf(d0.z, wv, acc[2]); acc[3] = fmaf(d0.w, wv, acc[3]);
+        acc[4] = fmaf(d1.x, wv, acc[4]); acc[5] = fmaf(d1.y, wv, acc[5]); acc[6] = fmaf(d1.z, wv, acc[6]); acc[7] = fmaf(d1.w, wv, acc[7]);
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
+      if (lane < kRows) {                                            // lane r finishes row r
+        float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) if (lane == r) v = acc[r];
+        const int r = lane;
+        if (k < relu_cols && r < nrow && !(hprev[(size_t)(row0 + r) * hprev_ld + k] > 0.f)) v = 0.f;
+        if (r >= nrow) v = 0.f;
+        db[k * kRows + r] = v;
+        if (r < nrow) {
+          Ly.dX[(size_t)(row0 + r) * K + k] = v;
+          if (Ly.action_in && A.d_action && k >= K - A.action_dim) A.d_action[(size_t)(row0 + r) * A.action_dim + (k - (K - A.action_dim))] = v;
+        }
+      }
+    }
+    __syncthreads();
+    float* t = da; da = db; db = t;
+  }
+}
+
+static int g_use_fused_mlp = -1;
+void set_fused_mlp(int on) { g_use_fused_mlp = on; }
+bool fused_mlp_enabled() {
+  static const bool d = [] { const char* e = getenv("CARTPOLEPP_FUSED_MLP"); return !(e && e[0] == '0'); }();
+  return g_use_fused_mlp < 0 ? d : g_use_fused_mlp != 0;
+}
+
+static void fill_layers(const Net& net, const float* params, char* ws, const Net::Layout& L, MlpArgs* A) {
+  int maxw = net.feat + net.action_dim;
+  for (int i = 0; i < net.n_fc; ++i) {
+    MlpLayer& y = A->L[i];
+    y.W = params + net.off_fc_w[i]; y.b = params + net.off_fc_b[i];
+    y.h = reinterpret_cast<float*>(ws + L.h[i]); y.dX = reinterpret_cast<float*>(ws + L.dX[i]);
+    y.in = net.in_dim[i]; y.out = net.out_dim[i]; y.act = net.act[i]; y.h_ld = net.out_ld[i];
+    y.action_in = net.concat_at == i ? 1 : 0;
+    maxw = std::max(maxw, std::max(y.in, y.out + net.action_dim));
+  }
+  A->maxw = maxw;
+  A->action_dim = net.action_dim;
+}
+
+bool mlp_fits(const Net& net) {
+  int maxw = net.feat + net.action_dim;
+  for (int i = 0; i < net.n_fc; ++i) maxw = std::max(maxw, std::max(net.in_dim[i], net.out_dim[i] + net.action_dim));
+  return (size_t)(2 * maxw + kMlpThreads) * kRows * sizeof(float) <= 200 * 1024;
+}
+
+int launch_mlp_forward(const Net& net, const float* params, const float* action, int B, void* ws_, float* out, cudaStream_t s,
+                       int first_fc, int end_fc) {
+  char* ws = reinterpret_cast<char*>(ws_);
+  const Net::Layout L = net.layout(B);
+  if (end_fc < 0 || end_fc > net.n_fc) end_fc = net.n_fc;
+  if (first_fc >= end_fc) return CPP_OK;
+  MlpArgs A{};
+  fill_layers(net, params, ws, L, &A);
+  A.first = first_fc; A.end = end_fc; A.B = B; A.action = action;
+  int ld;
+  const float* x = net.fc_input(L, ws, first_fc, &ld);
+  A.x = x; A.x_ld = ld;
+  A.x_cols = net.in_dim[first_fc] - (net.concat_at == first_fc ? net.action_dim : 0);
+  A.x_tail = net.concat_at == first_fc ? const_cast<float*>(x) + A.x_cols : nullptr;
+  const size_t smem = (size_t)(2 * A.maxw + kMlpThreads) * kRows * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CPP_CHECK_CUDA(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  mlp_forward_kernel<<<(unsigned)ceil_div(B, kRows), kMlpThreads, smem, s>>>(A);
+  CPP_CHECK_LAUNCH();
+  if (out != nullptr && end_fc == net.n_fc) {
+    const int n = net.out_dim[net.n_fc - 1];
+    CPP_CHECK_CUDA(cudaMemcpyAsync(out, ws + L.h[net.n_fc - 1], (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return CPP_OK;
+}
+
+// gradients wrt the inputs of layers last .. stop_at (dTop and every dX[i] land in the workspace); d_action optional
+int launch_mlp_dgrad(const Net& net, const float* params, int B, void* ws_, const float* d_out, int stop_at, int need_dx_first,
+                     float* d_action, cudaStream_t s) {
+  char* ws = reinterpret_cast<char*>(ws_);
+  const Net::Layout L = net.layout(B);
+  MlpArgs A{};
+  fill_layers(net, params, ws, L, &A);
+  A.first = stop_at; A.end = net.n_fc; A.B = B;
+  A.d_out = d_out; A.dTop = reinterpret_cast<float*>(ws + L.dTop); A.d_action = d_action; A.need_dx_first = need_dx_first;
+  const size_t smem = (size_t)2 * A.maxw * kRows * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CPP_CHECK_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  mlp_dgrad_kernel<<<(unsigned)ceil_div(B, kRows), kMlpThreads, smem, s>>>(A);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
+}  // namespace cpp

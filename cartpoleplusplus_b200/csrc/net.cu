@@ -140,6 +140,7 @@ int Net::forward_fc(const float* params, const float* action, int B, void* ws_, 
   CPP_REQUIRE(B >= 1, "batch %d", B);
   if (end_fc < 0 || end_fc > n_fc) end_fc = n_fc;
   CPP_REQUIRE(concat_at < 0 || concat_at < first_fc || concat_at >= end_fc || action != nullptr, "this network needs an action input");
+  if (fused_mlp_enabled() && mlp_fits(*this)) return launch_mlp_forward(*this, params, action, B, ws_, out, s, first_fc, end_fc);
   char* ws = reinterpret_cast<char*>(ws_);
   const Layout L = layout(B);
   for (int i = first_fc; i < end_fc; ++i) {
@@ -267,13 +268,38 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     ++ev; aux->used = true;
     return CPP_OK;
   };
+  const bool fused = fused_mlp_enabled() && mlp_fits(*this);
+  const int stop_at_f = (grads == nullptr) ? concat_at : 0;
+  if (fused) {
+    // one launch for the whole chain of input gradients; every weight / bias gradient afterwards (side stream if given)
+    const bool need_first = (stop_at_f == 0 && pixels && grads != nullptr) || (concat_at == stop_at_f && d_action != nullptr);
+    CPP_TRY(launch_mlp_dgrad(*this, params, B, ws, d_out, stop_at_f, need_first ? 1 : 0, d_action, s));
+    if (grads != nullptr) {
+      CPP_TRY(ready());
+      for (int i = last; i >= 0; --i) {
+        int xld;
+        const float* x = fc_input(L, ws, i, &xld);
+        const float* dpre = i == last ? reinterpret_cast<const float*>(ws + L.dTop) : reinterpret_cast<const float*>(ws + L.dX[i + 1]);
+        const int dld = i == last ? out_dim[last] : in_dim[i + 1];
+        GemmArgs g{};                                        // dW = x^T . dPre
+        g.A = x; g.lda = xld; g.transA = 1;
+        g.B = dpre; g.ldb = dld; g.transB = 0;
+        g.C = grads + off_fc_w[i]; g.ldc = out_dim[i];
+        g.M = in_dim[i]; g.N = out_dim[i]; g.K = B; g.epi = EPI_NONE;
+        CPP_TRY(launch_gemm(g, sw));
+        CPP_TRY(launch_colsum(dpre, dld, B, out_dim[i], grads + off_fc_b[i], sw));
+      }
+    }
+  }
   // gradient wrt the last pre-activation
   float* dcur = reinterpret_cast<float*>(ws + L.dTop);
+  if (!fused)
   CPP_TRY(launch_act_grad(d_out, out_dim[last], reinterpret_cast<const float*>(ws + L.h[last]), out_ld[last], act[last], B,
                           out_dim[last], dcur, out_dim[last], s));
   int dld = out_dim[last];
   const int stop_at = (grads == nullptr) ? concat_at : 0;   // only d_action wanted: stop once it is known
-  for (int i = last; i >= stop_at; --i) {
+  if (fused) dcur = reinterpret_cast<float*>(ws + L.dX[0]);
+  for (int i = last; i >= stop_at && !fused; --i) {
     int xld;
     const float* x = fc_input(L, ws, i, &xld);
     if (grads != nullptr) {

@@ -86,6 +86,15 @@ int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net);
 int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* const* grads, const void* state, int is_f16,
                       const float* mean_inv, int B, void* scratch, cudaStream_t s, int gmax_from_dgrad = 0);
 
+// mlp.cu: fused FC stacks (one launch per network and direction instead of one GEMM per layer)
+bool fused_mlp_enabled();
+void set_fused_mlp(int on);           // -1: CARTPOLEPP_FUSED_MLP environment default (on)
+bool mlp_fits(const Net& net);
+int launch_mlp_forward(const Net& net, const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s,
+                       int first_fc, int end_fc);
+int launch_mlp_dgrad(const Net& net, const float* params, int B, void* ws, const float* d_out, int stop_at, int need_dx_first,
+                     float* d_action, cudaStream_t s);
+
 // elementwise.cu
 int64_t moments_scratch_doubles(int C);
 int launch_channel_moments(const void* x, int is_f16, int64_t n_pix_total, int C, double* scratch, float* mean_inv, cudaStream_t s);

@@ -45,7 +45,8 @@ int64_t cpp_launch_count(void);
 /* runtime switches (tests and A/B timing): "conv1_tc" = 1 routes conv1 forward / weight gradient of fp16 states through the
  * tensor-core kernels (default, also CARTPOLEPP_CONV1=tc), 0 through the exact-fp32 CUDA-core kernels, -1 = environment default;
  * "streams" = 1 forks the independent chains of a fused DDPG step onto side streams (CARTPOLEPP_STREAMS), "graphs" = 1
- * replays a fused step as one CUDA graph (CARTPOLEPP_GRAPHS); both default on */
+ * replays a fused step as one CUDA graph (CARTPOLEPP_GRAPHS); "fused_mlp" = 1 runs every FC stack as one forward and one
+ * input-gradient launch instead of one GEMM per layer (CARTPOLEPP_FUSED_MLP); all default on */
 int cpp_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------ a1: index sampling (host)
