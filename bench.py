@@ -264,11 +264,19 @@ def run_native(args):
     kms = float(np.mean(ts))
     flops = 2.0 * 2 * BATCH * 64 * 64 * 10 * 25 * 9         # conv1 MACs/sample = H*W*10*25*Cin, two sibling nets
     ach = flops / (kms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):                       # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+      tj = json.load(open(tp))
+      traffic, traffic_src = int(tj["dram_read_bytes"]) + int(tj["dram_write_bytes"]), tj["source"]
     roof = dict(kernel="conv_fwd_tc_kernel<5,1> + weight prep (conv1 5x5 fwd of actor+critic, whitening fold, bias, ReLU, 2x2 maxpool; "
                        "tcgen05.mma kind::f16, fp32 weights as 2 fp16 pieces)", bound="tensor",
-                achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=None,
+                achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=traffic,
+                traffic_unit="bytes of DRAM traffic per launch", traffic_source=traffic_src,
                 peak_source=peaks["source"] + " bf16 dense (burst)", kernel_ms=kms, algorithmic_flops_per_launch=flops,
-                note="algorithmic (useful) FLOPs: N = 20 real filters of 48 issued columns, K = 225 of 256 issued")
+                algorithmic_bytes_per_launch=BATCH * 64 * 64 * 9 * 2,
+                note="algorithmic (useful) FLOPs: N = 20 real filters of 48 issued columns, K = 225 of 256 issued; the kernel is bound "
+                     "by the shared-memory read of the A operand (4 KB per tcgen05.mma), not by the math rate")
 
   cpu = None
   if dp.rank == 0 and not args.skip_cpu_baseline:

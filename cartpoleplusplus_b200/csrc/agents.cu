@@ -57,8 +57,10 @@ void DDPG::carve(void* ws, bool assign) {
   float* ones_ = cv.take<float>(B);
   float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
   double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(norm_scratch_doubles());
+  double* msc2 = cv.take<double>(moments_scratch_doubles(C));
   float* sc = cv.take<float>(4);
   ws_bytes = cv.off;
+  if (assign) mom_scratch2 = msc2;
   if (assign) {
     ws_actor = wa; ws_critic = wc; ws_target = wt; ws_target2 = wt2; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; mu = mu_;
     tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts2; tcs[3] = ts4; this->wgs[0] = wgs; this->wgs[1] = wgs2; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
@@ -214,25 +216,37 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   tr.mark("start", s0);
   const float* P = buf.params; const float* T = buf.target_params;
 
-  // ---- shared passes over the pixels: whitening statistics and conv1 of {actor, critic}(s1), {targets}(s2); whole GPU
-  const float *m1, *m2;
-  CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s0));
-  CPP_TRY(stats_for(s2, is_f16, B, mi2, pinned2, &m2, s0));
-  cur_m1 = m1;
+  // ---- shared passes over the pixels: whitening statistics and conv1 of {actor, critic}(s1) on s0, of {targets}(s2) on
+  // sta, each on half of the GPU
+  enum { E_START = 7 };
+  const float *m1 = nullptr, *m2 = nullptr;
   const Net* g2[2] = {&actor, &critic};
-  tr.mark("s0 moments done", s0);
   int tc1 = 0, tc2 = 0;
+  if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s0)); ones_ready = true; }
+  CPP_TRY(record(E_START, s0));
+  CPP_TRY(wait(sta, E_START));
+  if (multi) g_cta_cap = kNumSMs / 2;
   {
+    CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s0));
+    cur_m1 = m1;
     const float* pp[2] = {P, P + off_c}; char* wss[2] = {ws_actor, ws_critic};
     CPP_TRY(conv1_forward_group(2, g2, pp, wss, s1, is_f16, m1, B, tcs[0], s0, &tc1));
     tr.mark("s0 conv1 fwd {actor,critic}(s1) done", s0);
-    const float* pt[2] = {T, T + off_c}; char* wst[2] = {ws_target, ws_target2};
-    CPP_TRY(conv1_forward_group(2, g2, pt, wst, s2, is_f16, m2, B, tcs[2], s0, &tc2));
-    tr.mark("s0 conv1 fwd {targets}(s2) done", s0);
   }
-  if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s0)); ones_ready = true; }
-  CPP_TRY(record(E_FORK, s0));
-  CPP_TRY(wait(sc, E_FORK)); CPP_TRY(wait(sta, E_FORK)); CPP_TRY(wait(stc, E_FORK));
+  {
+    double* keep = mom_scratch;
+    if (multi) mom_scratch = mom_scratch2;                       // the two statistics passes run concurrently
+    const int st = stats_for(s2, is_f16, B, mi2, pinned2, &m2, sta);
+    mom_scratch = keep;
+    CPP_TRY(st);
+    const float* pt[2] = {T, T + off_c}; char* wst[2] = {ws_target, ws_target2};
+    CPP_TRY(conv1_forward_group(2, g2, pt, wst, s2, is_f16, m2, B, tcs[2], sta, &tc2));
+    tr.mark("sta conv1 fwd {targets}(s2) done", sta);
+  }
+  CPP_TRY(record(E_FORK, s0));                                   // conv1(s1) done: the critic chain may start
+  CPP_TRY(wait(sc, E_FORK));
+  CPP_TRY(record(E_TA, sta));                                    // conv1(s2) done: the target critic chain may start
+  CPP_TRY(wait(stc, E_TA));
   if (multi) g_cta_cap = kNumSMs / 4;
   // ---- actor chain (s0): trunk tail, FC stack -> mu                       ddpg_cartpole.py:90-100
   CPP_TRY(actor.forward_trunk(P, s1, is_f16, m1, B, ws_actor, s0, tc1, tc1 ? tcs[0] : nullptr));

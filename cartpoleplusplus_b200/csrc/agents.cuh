@@ -19,7 +19,7 @@ struct DDPG {
   void* wg_scr = nullptr;                          // conv1 weight-gradient partials (conv_wgrad_mma.cu)
   float *mu = nullptr, *dqda = nullptr, *neg = nullptr, *mu2 = nullptr, *q = nullptr, *q2 = nullptr, *td = nullptr, *dq = nullptr;
   float *ones = nullptr, *mi1 = nullptr, *mi2 = nullptr, *scale2 = nullptr;
-  double *mom_scratch = nullptr, *norm_scratch = nullptr;
+  double *mom_scratch = nullptr, *mom_scratch2 = nullptr, *norm_scratch = nullptr;
   const float *pinned1 = nullptr, *pinned2 = nullptr, *cur_m1 = nullptr;
   bool ones_ready = false, critic_trunk_valid = false;
   int trunk_B = 0;

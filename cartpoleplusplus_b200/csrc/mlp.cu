@@ -39,16 +39,55 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
   return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? tanhf(v) : v);
 }
 
+// ------------------------------------------------------------------------------------------ weight streaming
+// The weight matrix of a layer is streamed global -> shared in tiles of KT input rows x N outputs through a 3-stage
+// cp.async ring, so that the L2 latency of ~hundreds of rows is paid once, not per row (one CTA alone cannot keep enough
+// plain loads in flight).  W tiles are contiguous in memory (row-major [in][out]).
+constexpr int kStages = 3;
+constexpr int kTileFloats = 3072;          // 12 KB per stage
+
+__device__ __forceinline__ int tile_rows(int K, int N) {
+  int kt = (kTileFloats / N) & ~3;
+  if (kt < 4) kt = 4;
+  return kt < K ? kt : K;
+}
+// issue the copy of tile t (rows [t*KT, min(K, (t+1)*KT))) into `dst`; every thread commits exactly one group
+__device__ __forceinline__ void issue_tile(const float* __restrict__ W, int K, int N, int KT, int t, float* dst, int tid, bool vec4) {
+  const int k0 = t * KT;
+  if (k0 < K) {
+    const int rows = min(KT, K - k0), n_el = rows * N;
+    const float* src = W + (size_t)k0 * N;
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    if (vec4) {
+      for (int i = tid * 4; i < n_el; i += kMlpThreads * 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+    } else {
+      for (int i = tid; i < n_el; i += kMlpThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------ forward
-// shared: xa / xb [maxw][kRows] (k-major so that one k is two float4 loads for all 8 rows), red [kMlpThreads][kRows]
+// shared: xa / xb [maxw][kRows] (k-major so that one k is two float4 loads for all 8 rows), red [kMlpThreads][kRows],
+// wt [kStages][kTileFloats]
 __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_constant__ MlpArgs A) {
   extern __shared__ __align__(16) float sm[];
   float* xa = sm;
   float* xb = sm + (size_t)A.maxw * kRows;
   float* red = xb + (size_t)A.maxw * kRows;
+  float* wt = red + (size_t)kMlpThreads * kRows;
   const int tid = threadIdx.x, row0 = blockIdx.x * kRows;
   const int nrow = min(kRows, A.B - row0);
-  // input of the first layer (coalesced along k), then its action columns
+  // start streaming the first layer's weights, then fetch its input (coalesced along k) and its action columns
+  {
+    const MlpLayer& L0 = A.L[A.first];
+    const bool vec4 = ((reinterpret_cast<uintptr_t>(L0.W) & 15) == 0) && (L0.out % 4 == 0);
+    const int KT = tile_rows(L0.in, L0.out);
+    issue_tile(L0.W, L0.in, L0.out, KT, 0, wt, tid, vec4);
+    issue_tile(L0.W, L0.in, L0.out, KT, 1, wt + kTileFloats, tid, vec4);
+  }
   for (int r = 0; r < kRows; ++r)
     for (int k = tid; k < A.x_cols; k += kMlpThreads) xa[k * kRows + r] = r < nrow ? A.x[(size_t)(row0 + r) * A.x_ld + k] : 0.f;
   if (A.L[A.first].action_in) {
@@ -59,28 +98,47 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
       if (r < nrow && A.x_tail) A.x_tail[(size_t)(row0 + r) * A.x_ld + j] = v;
     }
   }
-  __syncthreads();
   for (int l = A.first; l < A.end; ++l) {
     const MlpLayer& Ly = A.L[l];
     const int N = Ly.out, K = Ly.in;
+    const bool vec4 = ((reinterpret_cast<uintptr_t>(Ly.W) & 15) == 0) && (N % 4 == 0);
+    const int KT = tile_rows(K, N), ntiles = (K + KT - 1) / KT;
     const int npad = (N + 31) & ~31;
     const int ks = max(1, min(8, kMlpThreads / npad));          // K slices: threads beyond one column set split the reduction
     const int slice = tid / npad, n = tid - slice * npad;
+    const bool active = slice < ks && n < N;
     float acc[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
-    if (slice < ks && n < N) {
-      const float* w = Ly.W + n;
+    for (int t = 0; t < ntiles; ++t) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");        // tile t has landed (one younger group may be in flight)
+      __syncthreads();                                           // ... for every thread; stage (t+2)%3 is free again; xa is complete
+      issue_tile(Ly.W, K, N, KT, t + 2, wt + ((t + 2) % kStages) * kTileFloats, tid, vec4);
+      if (active) {
+        const float* w = wt + (t % kStages) * kTileFloats + n;
+        const int k0 = t * KT, rows = min(KT, K - k0);
 #pragma unroll 4
-      for (int k = slice; k < K; k += ks) {
-        const float wv = __ldg(w + (size_t)k * N);
-        const float4 x0 = *reinterpret_cast<const float4*>(xa + k * kRows), x1 = *reinterpret_cast<const float4*>(xa + k * kRows + 4);
-        acc[0] = fmaf(x0.x, wv, acc[0]); acc[1] = fmaf(x0.y, wv, acc[1]); acc[2] = fmaf(x0.z, wv, acc[2]); acc[3] = fmaf(x0.w, wv, acc[3]);
-        acc[4] = fmaf(x1.x, wv, acc[4]); acc[5] = fmaf(x1.y, wv, acc[5]); acc[6] = fmaf(x1.z, wv, acc[6]); acc[7] = fmaf(x1.w, wv, acc[7]);
+        for (int kk = slice; kk < rows; kk += ks) {
+          const float wv = w[kk * N];
+          const float* xp = xa + (k0 + kk) * kRows;
+          const float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
+          acc[0] = fmaf(x0.x, wv, acc[0]); acc[1] = fmaf(x0.y, wv, acc[1]); acc[2] = fmaf(x0.z, wv, acc[2]); acc[3] = fmaf(x0.w, wv, acc[3]);
+          acc[4] = fmaf(x1.x, wv, acc[4]); acc[5] = fmaf(x1.y, wv, acc[5]); acc[6] = fmaf(x1.z, wv, acc[6]); acc[7] = fmaf(x1.w, wv, acc[7]);
+        }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                             // all weight stages idle: the next layer may start streaming
+    const bool more = l + 1 < A.end;
+    if (more) {
+      const MlpLayer& Ln = A.L[l + 1];
+      const bool v4 = ((reinterpret_cast<uintptr_t>(Ln.W) & 15) == 0) && (Ln.out % 4 == 0);
+      const int KTn = tile_rows(Ln.in, Ln.out);
+      issue_tile(Ln.W, Ln.in, Ln.out, KTn, 0, wt, tid, v4);
+      issue_tile(Ln.W, Ln.in, Ln.out, KTn, 1, wt + kTileFloats, tid, v4);
+    }
     if (ks > 1) {                                                // fixed-order reduction over the K slices
-      if (slice > 0 && slice < ks && n < N) {
+      if (slice > 0 && active) {
 #pragma unroll
         for (int r = 0; r < kRows; ++r) red[(size_t)tid * kRows + r] = acc[r];
       }
@@ -90,7 +148,6 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
 #pragma unroll
           for (int r = 0; r < kRows; ++r) acc[r] += red[(size_t)(s2 * npad + n) * kRows + r];
     }
-    const bool more = l + 1 < A.end;
     if (slice == 0 && n < N) {
       const float bv = Ly.b[n];
 #pragma unroll
@@ -108,21 +165,29 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
         if (r < nrow) Ly.h[(size_t)(row0 + r) * Ly.h_ld + N + j] = v;
       }
     }
-    __syncthreads();
-    float* t = xa; xa = xb; xb = t;
+    float* tsw = xa; xa = xb; xb = tsw;                          // the first sync of the next layer's tile loop publishes xb
   }
 }
 
 // ------------------------------------------------------------------------------------------ input-gradient chain
-// One warp per input column k, lanes over the output columns n (coalesced reads of W[k][:]), shuffle reduction.
-// shared: da / db [maxw][kRows]
+// One warp per input column k of the current weight tile, lanes over the output columns n, shuffle reduction.
+// shared: da / db [maxw][kRows], wt [kStages][kTileFloats]
 __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_constant__ MlpArgs A) {
   extern __shared__ __align__(16) float sm[];
   float* da = sm;
   float* db = sm + (size_t)A.maxw * kRows;
+  float* wt = db + (size_t)A.maxw * kRows;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = blockIdx.x * kRows;
   const int nrow = min(kRows, A.B - row0);
   const int last = A.end - 1;
+  const int lowest = A.need_dx_first ? A.first : A.first + 1;      // lowest layer whose input gradient is produced
+  if (last >= lowest) {
+    const MlpLayer& L0 = A.L[last];
+    const bool vec4 = ((reinterpret_cast<uintptr_t>(L0.W) & 15) == 0) && (L0.out % 4 == 0);
+    const int KT = tile_rows(L0.in, L0.out);
+    issue_tile(L0.W, L0.in, L0.out, KT, 0, wt, tid, vec4);
+    issue_tile(L0.W, L0.in, L0.out, KT, 1, wt + kTileFloats, tid, vec4);
+  }
   {   // gradient wrt the last pre-activation: d_out * act'(out)
     const MlpLayer& Ly = A.L[last];
     for (int i = tid; i < kRows * Ly.out; i += kMlpThreads) {
@@ -138,46 +203,62 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
       da[n * kRows + r] = g;
     }
   }
-  __syncthreads();
-  for (int l = last; l >= A.first; --l) {
-    if (l == A.first && !A.need_dx_first) break;
+  for (int l = last; l >= lowest; --l) {
     const MlpLayer& Ly = A.L[l];
     const int N = Ly.out, K = Ly.in;
+    const bool vec4 = ((reinterpret_cast<uintptr_t>(Ly.W) & 15) == 0) && (N % 4 == 0);
+    const int KT = tile_rows(K, N), ntiles = (K + KT - 1) / KT;
     const int relu_cols = l > 0 ? A.L[l - 1].out : 0;               // the first relu_cols inputs are the ReLU output of layer l-1
     const float* hprev = l > 0 ? A.L[l - 1].h : nullptr;
     const int hprev_ld = l > 0 ? A.L[l - 1].h_ld : 0;
-    for (int k = warp; k < K; k += kMlpThreads / 32) {
-      float acc[kRows];
+    for (int t = 0; t < ntiles; ++t) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncthreads();                                             // tile t visible to all; da complete; stage (t+2)%3 free
+      issue_tile(Ly.W, K, N, KT, t + 2, wt + ((t + 2) % kStages) * kTileFloats, tid, vec4);
+      const float* wtile = wt + (t % kStages) * kTileFloats;
+      const int k0 = t * KT, rows = min(KT, K - k0);
+      for (int kk = warp; kk < rows; kk += kMlpThreads / 32) {
+        const int k = k0 + kk;
+        float acc[kRows];
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
-      const float* w = Ly.W + (size_t)k * N;
-      for (int n = lane; n < N; n += 32) {
-        const float wv = __ldg(w + n);
-        const float4 d0 = *reinterpret_cast<const float4*>(da + n * kRows), d1 = *reinterpret_cast<const float4*>(da + n * kRows + 4);
-        acc[0] = fmaf(d0.x, wv, acc[0]); acc[1] = fmaf(d0.y, wv, acc[1]); acc[2] = fmaf(d0.z, wv, acc[2]); acc[3] = fmaf(d0.w, wv, acc[3]);
-        acc[4] = fmaf(d1.x, wv, acc[4]); acc[5] = fmaf(d1.y, wv, acc[5]); acc[6] = fmaf(d1.z, wv, acc[6]); acc[7] = fmaf(d1.w, wv, acc[7]);
-      }
+        for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+        const float* w = wtile + kk * N;
+        for (int n = lane; n < N; n += 32) {
+          const float wv = w[n];
+          const float4 d0 = *reinterpret_cast<const float4*>(da + n * kRows), d1 = *reinterpret_cast<const float4*>(da + n * kRows + 4);
+          acc[0] = fmaf(d0.x, wv, acc[0]); acc[1] = fmaf(d0.y, wv, acc[1]); acc[2] = fmaf(d0.z, wv, acc[2]); acc[3] = fmaf(d0.w, wv, acc[3]);
+          acc[4] = fmaf(d1.x, wv, acc[4]); acc[5] = fmaf(d1.y, wv, acc[5]); acc[6] = fmaf(d1.z, wv, acc[6]); acc[7] = fmaf(d1.w, wv, acc[7]);
+        }
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
+        for (int r = 0; r < kRows; ++r) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-      }
-      if (lane < kRows) {                                            // lane r finishes row r
-        float v = 0.f;
+          for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        }
+        if (lane < kRows) {                                          // lane r finishes row r
+          float v = 0.f;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) if (lane == r) v = acc[r];
-        const int r = lane;
-        if (k < relu_cols && r < nrow && !(hprev[(size_t)(row0 + r) * hprev_ld + k] > 0.f)) v = 0.f;
-        if (r >= nrow) v = 0.f;
-        db[k * kRows + r] = v;
-        if (r < nrow) {
-          Ly.dX[(size_t)(row0 + r) * K + k] = v;
-          if (Ly.action_in && A.d_action && k >= K - A.action_dim) A.d_action[(size_t)(row0 + r) * A.action_dim + (k - (K - A.action_dim))] = v;
+          for (int r = 0; r < kRows; ++r) if (lane == r) v = acc[r];
+          const int r = lane;
+          if (k < relu_cols && r < nrow && !(hprev[(size_t)(row0 + r) * hprev_ld + k] > 0.f)) v = 0.f;
+          if (r >= nrow) v = 0.f;
+          db[k * kRows + r] = v;
+          if (r < nrow) {
+            Ly.dX[(size_t)(row0 + r) * K + k] = v;
+            if (Ly.action_in && A.d_action && k >= K - A.action_dim) A.d_action[(size_t)(row0 + r) * A.action_dim + (k - (K - A.action_dim))] = v;
+          }
         }
       }
     }
-    __syncthreads();
-    float* t = da; da = db; db = t;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                               // all stages idle, db complete
+    if (l - 1 >= lowest) {
+      const MlpLayer& Ln = A.L[l - 1];
+      const bool v4 = ((reinterpret_cast<uintptr_t>(Ln.W) & 15) == 0) && (Ln.out % 4 == 0);
+      const int KTn = tile_rows(Ln.in, Ln.out);
+      issue_tile(Ln.W, Ln.in, Ln.out, KTn, 0, wt, tid, v4);
+      issue_tile(Ln.W, Ln.in, Ln.out, KTn, 1, wt + kTileFloats, tid, v4);
+    }
+    float* tsw = da; da = db; db = tsw;
   }
 }
 
@@ -205,7 +286,7 @@ static void fill_layers(const Net& net, const float* params, char* ws, const Net
 bool mlp_fits(const Net& net) {
   int maxw = net.feat + net.action_dim;
   for (int i = 0; i < net.n_fc; ++i) maxw = std::max(maxw, std::max(net.in_dim[i], net.out_dim[i] + net.action_dim));
-  return (size_t)(2 * maxw + kMlpThreads) * kRows * sizeof(float) <= 200 * 1024;
+  return (size_t)(2 * maxw + kMlpThreads) * kRows * sizeof(float) + (size_t)kStages * kTileFloats * sizeof(float) <= 200 * 1024;
 }
 
 int launch_mlp_forward(const Net& net, const float* params, const float* action, int B, void* ws_, float* out, cudaStream_t s,
@@ -222,7 +303,7 @@ int launch_mlp_forward(const Net& net, const float* params, const float* action,
   A.x = x; A.x_ld = ld;
   A.x_cols = net.in_dim[first_fc] - (net.concat_at == first_fc ? net.action_dim : 0);
   A.x_tail = net.concat_at == first_fc ? const_cast<float*>(x) + A.x_cols : nullptr;
-  const size_t smem = (size_t)(2 * A.maxw + kMlpThreads) * kRows * sizeof(float);
+  const size_t smem = (size_t)(2 * A.maxw + kMlpThreads) * kRows * sizeof(float) + (size_t)kStages * kTileFloats * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     CPP_CHECK_CUDA(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -246,7 +327,7 @@ int launch_mlp_dgrad(const Net& net, const float* params, int B, void* ws_, cons
   fill_layers(net, params, ws, L, &A);
   A.first = stop_at; A.end = net.n_fc; A.B = B;
   A.d_out = d_out; A.dTop = reinterpret_cast<float*>(ws + L.dTop); A.d_action = d_action; A.need_dx_first = need_dx_first;
-  const size_t smem = (size_t)2 * A.maxw * kRows * sizeof(float);
+  const size_t smem = (size_t)2 * A.maxw * kRows * sizeof(float) + (size_t)kStages * kTileFloats * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     CPP_CHECK_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
