@@ -40,11 +40,11 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
 }
 
 // ------------------------------------------------------------------------------------------ weight streaming
-// The weight matrix of a layer is streamed global -> shared in tiles of KT input rows x N outputs through a 3-stage
+// The weight matrix of a layer is streamed global -> shared in tiles of KT input rows x N outputs through a 4-stage
 // cp.async ring, so that the L2 latency of ~hundreds of rows is paid once, not per row (one CTA alone cannot keep enough
 // plain loads in flight).  W tiles are contiguous in memory (row-major [in][out]).
-constexpr int kStages = 3;
-constexpr int kTileFloats = 3072;          // 12 KB per stage
+constexpr int kStages = 4;
+constexpr int kTileFloats = 8192;          // 32 KB per stage: ~100 KB of weights in flight per CTA hide the L2 latency
 
 __device__ __forceinline__ int tile_rows(int K, int N) {
   int kt = (kTileFloats / N) & ~3;
@@ -85,11 +85,15 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
     const MlpLayer& L0 = A.L[A.first];
     const bool vec4 = ((reinterpret_cast<uintptr_t>(L0.W) & 15) == 0) && (L0.out % 4 == 0);
     const int KT = tile_rows(L0.in, L0.out);
-    issue_tile(L0.W, L0.in, L0.out, KT, 0, wt, tid, vec4);
-    issue_tile(L0.W, L0.in, L0.out, KT, 1, wt + kTileFloats, tid, vec4);
+    for (int t = 0; t < kStages - 1; ++t) issue_tile(L0.W, L0.in, L0.out, KT, t, wt + t * kTileFloats, tid, vec4);
   }
-  for (int r = 0; r < kRows; ++r)
-    for (int k = tid; k < A.x_cols; k += kMlpThreads) xa[k * kRows + r] = r < nrow ? A.x[(size_t)(row0 + r) * A.x_ld + k] : 0.f;
+  for (int k = tid; k < A.x_cols; k += kMlpThreads) {
+    float v[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) v[r] = r < nrow ? __ldg(A.x + (size_t)(row0 + r) * A.x_ld + k) : 0.f;
+    *reinterpret_cast<float4*>(xa + k * kRows) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(xa + k * kRows + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
   if (A.L[A.first].action_in) {
     for (int i = tid; i < kRows * A.action_dim; i += kMlpThreads) {
       const int r = i / A.action_dim, j = i - r * A.action_dim;
@@ -111,9 +115,9 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
     for (int t = 0; t < ntiles; ++t) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");        // tile t has landed (one younger group may be in flight)
-      __syncthreads();                                           // ... for every thread; stage (t+2)%3 is free again; xa is complete
-      issue_tile(Ly.W, K, N, KT, t + 2, wt + ((t + 2) % kStages) * kTileFloats, tid, vec4);
+      asm volatile("cp.async.wait_group 2;" ::: "memory");        // tile t has landed (kStages - 2 younger groups may be in flight)
+      __syncthreads();                                           // ... for every thread; the stage of tile t-1 is free again; xa is complete
+      issue_tile(Ly.W, K, N, KT, t + kStages - 1, wt + ((t + kStages - 1) % kStages) * kTileFloats, tid, vec4);
       if (active) {
         const float* w = wt + (t % kStages) * kTileFloats + n;
         const int k0 = t * KT, rows = min(KT, K - k0);
@@ -134,8 +138,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
       const MlpLayer& Ln = A.L[l + 1];
       const bool v4 = ((reinterpret_cast<uintptr_t>(Ln.W) & 15) == 0) && (Ln.out % 4 == 0);
       const int KTn = tile_rows(Ln.in, Ln.out);
-      issue_tile(Ln.W, Ln.in, Ln.out, KTn, 0, wt, tid, v4);
-      issue_tile(Ln.W, Ln.in, Ln.out, KTn, 1, wt + kTileFloats, tid, v4);
+      for (int t = 0; t < kStages - 1; ++t) issue_tile(Ln.W, Ln.in, Ln.out, KTn, t, wt + t * kTileFloats, tid, v4);
     }
     if (ks > 1) {                                                // fixed-order reduction over the K slices
       if (slice > 0 && active) {
@@ -185,8 +188,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
     const MlpLayer& L0 = A.L[last];
     const bool vec4 = ((reinterpret_cast<uintptr_t>(L0.W) & 15) == 0) && (L0.out % 4 == 0);
     const int KT = tile_rows(L0.in, L0.out);
-    issue_tile(L0.W, L0.in, L0.out, KT, 0, wt, tid, vec4);
-    issue_tile(L0.W, L0.in, L0.out, KT, 1, wt + kTileFloats, tid, vec4);
+    for (int t = 0; t < kStages - 1; ++t) issue_tile(L0.W, L0.in, L0.out, KT, t, wt + t * kTileFloats, tid, vec4);
   }
   {   // gradient wrt the last pre-activation: d_out * act'(out)
     const MlpLayer& Ly = A.L[last];
@@ -212,9 +214,9 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
     const float* hprev = l > 0 ? A.L[l - 1].h : nullptr;
     const int hprev_ld = l > 0 ? A.L[l - 1].h_ld : 0;
     for (int t = 0; t < ntiles; ++t) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-      __syncthreads();                                             // tile t visible to all; da complete; stage (t+2)%3 free
-      issue_tile(Ly.W, K, N, KT, t + 2, wt + ((t + 2) % kStages) * kTileFloats, tid, vec4);
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      __syncthreads();                                             // tile t visible to all; da complete; the stage of tile t-1 is free
+      issue_tile(Ly.W, K, N, KT, t + kStages - 1, wt + ((t + kStages - 1) % kStages) * kTileFloats, tid, vec4);
       const float* wtile = wt + (t % kStages) * kTileFloats;
       const int k0 = t * KT, rows = min(KT, K - k0);
       for (int kk = warp; kk < rows; kk += kMlpThreads / 32) {
@@ -255,8 +257,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
       const MlpLayer& Ln = A.L[l - 1];
       const bool v4 = ((reinterpret_cast<uintptr_t>(Ln.W) & 15) == 0) && (Ln.out % 4 == 0);
       const int KTn = tile_rows(Ln.in, Ln.out);
-      issue_tile(Ln.W, Ln.in, Ln.out, KTn, 0, wt, tid, v4);
-      issue_tile(Ln.W, Ln.in, Ln.out, KTn, 1, wt + kTileFloats, tid, v4);
+      for (int t = 0; t < kStages - 1; ++t) issue_tile(Ln.W, Ln.in, Ln.out, KTn, t, wt + t * kTileFloats, tid, v4);
     }
     float* tsw = da; da = db; db = tsw;
   }
