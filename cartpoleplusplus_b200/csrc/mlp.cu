@@ -213,6 +213,15 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
     const int relu_cols = l > 0 ? A.L[l - 1].out : 0;               // the first relu_cols inputs are the ReLU output of layer l-1
     const float* hprev = l > 0 ? A.L[l - 1].h : nullptr;
     const int hprev_ld = l > 0 ? A.L[l - 1].h_ld : 0;
+    // ReLU mask of the layer below: its activations go into db up front (coalesced, all loads in flight); the epilogue of
+    // column k reads db[k][r] and overwrites it with the gradient - no global load on the per-column critical path
+    for (int k = tid; k < relu_cols; k += kMlpThreads) {
+      float v[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) v[r] = r < nrow ? __ldg(hprev + (size_t)(row0 + r) * hprev_ld + k) : 0.f;
+      *reinterpret_cast<float4*>(db + k * kRows) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(db + k * kRows + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
     for (int t = 0; t < ntiles; ++t) {
       asm volatile("cp.async.wait_group 2;" ::: "memory");
       __syncthreads();                                             // tile t visible to all; da complete; the stage of tile t-1 is free
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
 #pragma unroll
           for (int r = 0; r < kRows; ++r) if (lane == r) v = acc[r];
           const int r = lane;
-          if (k < relu_cols && r < nrow && !(hprev[(size_t)(row0 + r) * hprev_ld + k] > 0.f)) v = 0.f;
+          if (k < relu_cols && !(db[k * kRows + r] > 0.f)) v = 0.f;
           if (r >= nrow) v = 0.f;
           db[k * kRows + r] = v;
           if (r < nrow) {
