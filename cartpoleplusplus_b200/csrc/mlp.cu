@@ -272,12 +272,14 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
   }
 }
 
+// 0: one GEMM per layer; 1: fused forward stacks only; 2: fused forward and fused input-gradient chain
 static int g_use_fused_mlp = -1;
 void set_fused_mlp(int on) { g_use_fused_mlp = on; }
-bool fused_mlp_enabled() {
-  static const bool d = [] { const char* e = getenv("CARTPOLEPP_FUSED_MLP"); return !(e && e[0] == '0'); }();
-  return g_use_fused_mlp < 0 ? d : g_use_fused_mlp != 0;
+int fused_mlp_level() {
+  static const int d = [] { const char* e = getenv("CARTPOLEPP_FUSED_MLP"); return e ? atoi(e) : 1; }();
+  return g_use_fused_mlp < 0 ? d : g_use_fused_mlp;
 }
+bool fused_mlp_enabled() { return fused_mlp_level() >= 1; }
 
 static void fill_layers(const Net& net, const float* params, char* ws, const Net::Layout& L, MlpArgs* A) {
   int maxw = net.feat + net.action_dim;

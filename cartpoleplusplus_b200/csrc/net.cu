@@ -268,7 +268,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     ++ev; aux->used = true;
     return CPP_OK;
   };
-  const bool fused = fused_mlp_enabled() && mlp_fits(*this);
+  const bool fused = fused_mlp_level() >= 2 && mlp_fits(*this);
   const int stop_at_f = (grads == nullptr) ? concat_at : 0;
   if (fused) {
     // one launch for the whole chain of input gradients; every weight / bias gradient afterwards (side stream if given)

@@ -88,7 +88,8 @@ int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* con
 
 // mlp.cu: fused FC stacks (one launch per network and direction instead of one GEMM per layer)
 bool fused_mlp_enabled();
-void set_fused_mlp(int on);           // -1: CARTPOLEPP_FUSED_MLP environment default (on)
+int fused_mlp_level();                // 0: GEMM per layer, 1: fused forward stacks, 2: + fused input-gradient chain
+void set_fused_mlp(int on);           // -1: CARTPOLEPP_FUSED_MLP environment default
 bool mlp_fits(const Net& net);
 int launch_mlp_forward(const Net& net, const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s,
                        int first_fc, int end_fc);
