@@ -77,7 +77,7 @@ int DDPG::bind(const cpp_ddpg_buffers& b) {
   buf = b; bound = true;
   carve(b.workspace, true);
   ones_ready = false; pinned1 = pinned2 = nullptr;
-  for (auto& gm : graph) for (auto& g : gm) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = 0; }
+  for (auto& gc : graph) gc.clear();
   return CPP_OK;
 }
 
@@ -171,11 +171,18 @@ int DDPG::critic_backward(const void* s1, const float* action, const float* rewa
 static int g_use_streams = -1, g_use_graphs = -1;     // -1: environment default (CARTPOLEPP_STREAMS / CARTPOLEPP_GRAPHS, on unless "0")
 void set_step_options(int streams, int graphs) { if (streams >= -1) g_use_streams = streams; if (graphs >= -1) g_use_graphs = graphs; }
 static bool env_flag(const char* name) { const char* e = getenv(name); return !(e && e[0] == '0'); }
+bool step_streams_enabled();
 static bool use_streams() { static const bool d = env_flag("CARTPOLEPP_STREAMS"); return g_use_streams < 0 ? d : g_use_streams != 0; }
 static bool use_graphs() { static const bool d = env_flag("CARTPOLEPP_GRAPHS"); return g_use_graphs < 0 ? d : g_use_graphs != 0; }
 
+void GraphCache::clear() {
+  for (auto& g : slots) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = 0; }
+}
+bool step_streams_enabled() { return use_streams(); }
+bool step_graphs_enabled() { return use_graphs(); }
+
 DDPG::~DDPG() {
-  for (auto& gm : graph) for (auto& g : gm) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& gc : graph) gc.clear();
   if (streams_ready) {
     for (auto& st : side) if (st) cudaStreamDestroy(st);
     if (cap_stream) cudaStreamDestroy(cap_stream);
@@ -311,44 +318,11 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   const bool multi = use_streams();
   if (multi || use_graphs()) CPP_TRY(ensure_streams());
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
-  const void* key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
-  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, conv1_tc_enabled() ? 1 : 0};
-  // a few argument sets are kept (double-buffered staging alternates between two input buffer sets); least recently used goes
-  GraphSlot* slots = graph[with_apply ? 1 : 0];
-  GraphSlot* hit = nullptr; GraphSlot* lru = &slots[0];
-  for (int k = 0; k < 4; ++k) {
-    GraphSlot& c = slots[k];
-    bool eq = c.seen > 0;
-    for (int i = 0; i < 8 && eq; ++i) eq = c.key[i] == key[i];
-    for (int i = 0; i < 5 && eq; ++i) eq = c.ikey[i] == ikey[i];
-    if (eq) { hit = &c; break; }
-    if (c.used < lru->used) lru = &c;
-  }
-  const bool same = hit != nullptr;
-  GraphSlot& G = same ? *hit : *lru;
-  G.used = ++graph_clock;
-  if (same && G.exec != nullptr) { CPP_CHECK_CUDA(cudaGraphLaunch(G.exec, s)); g_launch_count += G.launches; return CPP_OK; }
-  if (!same) {                      // new argument set: run it eagerly once (validates, configures kernels), capture on the next call
-    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
-    for (int i = 0; i < 8; ++i) G.key[i] = key[i];
-    for (int i = 0; i < 5; ++i) G.ikey[i] = ikey[i];
-    G.seen = 1;
-    return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
-  }
-  // second call with the same arguments: capture the fork/join structure once, replay from now on
-  CPP_CHECK_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-  const long long launches_before = g_launch_count;
-  const int st = step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, cap_stream);
-  cudaGraph_t gr = nullptr;
-  const cudaError_t ce = cudaStreamEndCapture(cap_stream, &gr);
-  if (st != CPP_OK) { if (gr) cudaGraphDestroy(gr); G.seen = 0; return st; }
-  if (ce != cudaSuccess) { G.seen = 0; set_error("graph capture failed: %s", cudaGetErrorString(ce)); return CPP_ERR_CUDA; }
-  G.launches = (int)(g_launch_count - launches_before);
-  const cudaError_t ie = cudaGraphInstantiate(&G.exec, gr, 0);
-  cudaGraphDestroy(gr);
-  if (ie != cudaSuccess) { G.exec = nullptr; G.seen = 0; set_error("graph instantiate failed: %s", cudaGetErrorString(ie)); return CPP_ERR_CUDA; }
-  CPP_CHECK_CUDA(cudaGraphLaunch(G.exec, s));
-  return CPP_OK;
+  const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
+  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1)};
+  return run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
+    return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, st);
+  });
 }
 
 int DDPG::step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
@@ -415,6 +389,11 @@ void NAF::carve(void* ws, bool assign) {
   void* ts1 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
   void* ts2 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
   void* wgs = cv.take<char>((size_t)conv1_wgrad_group_scratch_bytes(3, value));
+  void* wgs1 = cv.take<char>((size_t)conv1_wgrad_group_scratch_bytes(3, value));
+  void* wgs2 = cv.take<char>((size_t)conv1_wgrad_group_scratch_bytes(3, value));
+  void* ts3 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
+  void* ts4 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
+  double* msc2 = cv.take<double>(moments_scratch_doubles(value.pixels ? value.spec.Cin : 1));
   float* V_ = cv.take<float>(B); float* V2_ = cv.take<float>(B); float* mu_ = cv.take<float>((size_t)B * A); float* lv_ = cv.take<float>((size_t)B * NL);
   float* dV_ = cv.take<float>(B); float* dmu_ = cv.take<float>((size_t)B * A); float* dl_ = cv.take<float>((size_t)B * NL);
   float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
@@ -422,7 +401,8 @@ void NAF::carve(void* ws, bool assign) {
   float* sc = cv.take<float>(4);
   ws_bytes = cv.off;
   if (assign) {
-    ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; V = V_; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
+    ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; V = V_;
+    tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts4; tcs[3] = ts2; this->wgs[0] = wgs; this->wgs[1] = wgs1; this->wgs[2] = wgs2; mom_scratch2 = msc2; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
     mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
   }
 }
@@ -436,6 +416,95 @@ int NAF::bind(const cpp_naf_buffers& b) {
   buf = b; bound = true;
   carve(b.workspace, true);
   pinned1 = pinned2 = nullptr;
+  graph.clear();
+  return CPP_OK;
+}
+
+NAF::~NAF() {
+  graph.clear();
+  if (streams_ready) {
+    for (auto& st : side) if (st) cudaStreamDestroy(st);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+  }
+}
+
+int NAF::ensure_streams() {
+  if (streams_ready) return CPP_OK;
+  for (auto& st : side) CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  for (auto& e : ev) CPP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  streams_ready = true;
+  return CPP_OK;
+}
+
+// naf.train(batch) up to the gradients (naf_cartpole.py:147-239): conv1 of {value, mu, l}(s1) in one tensor-core pass on s0
+// while the target value network runs on state_2 on its own stream; then the three chains fork (trunk tail + FC), join at
+// the L.L^T head, fork again for their backward passes and join for the shared conv1 weight gradient.
+int NAF::backward_body(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
+                       int B, int B_global, bool multi, cudaStream_t s0) {
+  cudaStream_t sm = multi ? side[0] : s0, sl = multi ? side[1] : s0, st = multi ? side[2] : s0;
+  enum { E_START = 0, E_C1, E_MU, E_L, E_V2, E_HEAD, E_BM, E_BL };
+  auto record = [&](int e, cudaStream_t x) -> int { if (multi) CPP_CHECK_CUDA(cudaEventRecord(ev[e], x)); return CPP_OK; };
+  auto wait = [&](cudaStream_t x, int e) -> int { if (multi) CPP_CHECK_CUDA(cudaStreamWaitEvent(x, ev[e], 0)); return CPP_OK; };
+  struct CapGuard { ~CapGuard() { g_cta_cap = kNumSMs; } } cap_guard;
+  const float* P = buf.params;
+  const float *m1 = nullptr, *m2 = nullptr;
+  CPP_TRY(record(E_START, s0));
+  CPP_TRY(wait(st, E_START));
+  // ---- target value network on state_2 (its own stream, a quarter of the GPU)
+  if (multi) g_cta_cap = kNumSMs / 4;
+  {
+    double* keep = mom_scratch;
+    if (multi) mom_scratch = mom_scratch2;
+    const int rc = stats_for(s2, is_f16, B, mi2, pinned2, &m2, st);
+    mom_scratch = keep;
+    CPP_TRY(rc);
+    const Net* g[1] = {&value}; const float* pp[1] = {buf.target_params}; char* wss[1] = {ws_t};
+    CPP_TRY(trunk_forward_group(1, g, pp, wss, s2, is_f16, m2, B, tcs[3], st));
+    CPP_TRY(value.forward_fc(buf.target_params, nullptr, B, ws_t, V2, st));
+    CPP_TRY(record(E_V2, st));
+  }
+  // ---- conv1 of the three networks on state_1 in one pass
+  if (multi) g_cta_cap = kNumSMs - kNumSMs / 4;
+  CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s0));
+  cur_m1 = m1;
+  const Net* g3[3] = {&value, &mu, &l};
+  const float* pp3[3] = {P, P + off_m, P + off_l};
+  char* ws3[3] = {ws_v, ws_m, ws_l};
+  int tc1 = 0;
+  CPP_TRY(conv1_forward_group(3, g3, pp3, ws3, s1, is_f16, m1, B, tcs[0], s0, &tc1));
+  CPP_TRY(record(E_C1, s0));
+  CPP_TRY(wait(sm, E_C1)); CPP_TRY(wait(sl, E_C1));
+  // ---- three forward chains
+  if (multi) g_cta_cap = kNumSMs / 4;
+  CPP_TRY(value.forward_trunk(P, s1, is_f16, m1, B, ws_v, s0, tc1, tc1 ? tcs[0] : nullptr));
+  CPP_TRY(value.forward_fc(P, nullptr, B, ws_v, V, s0));
+  CPP_TRY(mu.forward_trunk(P + off_m, s1, is_f16, m1, B, ws_m, sm, tc1, tc1 ? tcs[1] : nullptr));
+  CPP_TRY(mu.forward_fc(P + off_m, nullptr, B, ws_m, muo, sm));
+  CPP_TRY(record(E_MU, sm));
+  CPP_TRY(l.forward_trunk(P + off_l, s1, is_f16, m1, B, ws_l, sl, tc1, tc1 ? tcs[2] : nullptr));
+  CPP_TRY(l.forward_fc(P + off_l, nullptr, B, ws_l, lv, sl));
+  CPP_TRY(record(E_L, sl));
+  // ---- head: Q = V + A, TD target, loss, gradients wrt V / mu / l                          naf_cartpole.py:186-230
+  CPP_TRY(wait(s0, E_MU)); CPP_TRY(wait(s0, E_L)); CPP_TRY(wait(s0, E_V2));
+  CPP_TRY(launch_naf_head(V, muo, lv, action, reward, mask, V2, cfg.discount, B, A, B_global, dV, dmu, dl, nullptr,
+                          buf.grads + off_loss, s0));
+  CPP_TRY(record(E_HEAD, s0));
+  CPP_TRY(wait(sm, E_HEAD)); CPP_TRY(wait(sl, E_HEAD));
+  // ---- three backward chains (conv1 weight gradients deferred)
+  if (multi) g_cta_cap = kNumSMs / 3;
+  CPP_TRY(value.backward(P, s1, is_f16, m1, B, ws_v, dV, buf.grads, nullptr, s0, 1, wgs[0], tcs[0]));
+  CPP_TRY(mu.backward(P + off_m, s1, is_f16, m1, B, ws_m, dmu, buf.grads + off_m, nullptr, sm, 1, wgs[1], tcs[1]));
+  CPP_TRY(record(E_BM, sm));
+  CPP_TRY(l.backward(P + off_l, s1, is_f16, m1, B, ws_l, dl, buf.grads + off_l, nullptr, sl, 1, wgs[2], tcs[2]));
+  CPP_TRY(record(E_BL, sl));
+  CPP_TRY(wait(s0, E_BM)); CPP_TRY(wait(s0, E_BL));
+  g_cta_cap = kNumSMs;
+  {
+    float* gr[3] = {buf.grads, buf.grads + off_m, buf.grads + off_l};
+    CPP_TRY(conv1_wgrad_group(3, g3, ws3, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
+  }
   return CPP_OK;
 }
 
@@ -478,16 +547,14 @@ int NAF::forward_all(const void* s1, const float* action, const float* reward, c
 int NAF::backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
                   int B, int B_global, cudaStream_t s) {
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
-  CPP_TRY(forward_all(s1, action, reward, mask, s2, is_f16, B, B_global, true, nullptr, buf.grads + off_loss, s));
-  CPP_TRY(value.backward(buf.params, s1, is_f16, cur_m1, B, ws_v, dV, buf.grads, nullptr, s, 1, wg_scr, tc_scr1));
-  CPP_TRY(mu.backward(buf.params + off_m, s1, is_f16, cur_m1, B, ws_m, dmu, buf.grads + off_m, nullptr, s, 1, wg_scr, tc_scr1));
-  CPP_TRY(l.backward(buf.params + off_l, s1, is_f16, cur_m1, B, ws_l, dl, buf.grads + off_l, nullptr, s, 1, wg_scr, tc_scr1));
-  {  // conv1 weight gradients of the three networks in one pass over state_1
-    const Net* g[3] = {&value, &mu, &l}; char* wss[3] = {ws_v, ws_m, ws_l};
-    float* gr[3] = {buf.grads, buf.grads + off_m, buf.grads + off_l};
-    CPP_TRY(conv1_wgrad_group(3, g, wss, gr, s1, is_f16, cur_m1, B, wg_scr, s, 1));
-  }
-  return CPP_OK;
+  const bool multi = step_streams_enabled(), graphs = step_graphs_enabled();
+  if (multi || graphs) CPP_TRY(ensure_streams());
+  if (!graphs) return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, s);
+  const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
+  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1)};
+  return run_graphed(graph, key, ikey, s, cap_stream, [&](cudaStream_t x) {
+    return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, x);
+  });
 }
 
 int NAF::apply(int check, float* loss_host, cudaStream_t s) {

@@ -6,6 +6,61 @@ namespace cpp {
 
 void set_step_options(int streams, int graphs);   // -1 = environment default, -2 = leave unchanged
 
+// One captured step per argument set: a few sets are kept (double-buffered staging alternates between two input buffer
+// sets), least recently used goes.  First call with a new set runs eagerly (validates, configures kernels), the second
+// captures the fork/join structure on `cap_stream`, later calls replay it with one cudaGraphLaunch.
+struct GraphSlot {
+  cudaGraphExec_t exec = nullptr;
+  const void* key[8] = {};
+  int ikey[5] = {};
+  int seen = 0, used = 0;
+  int launches = 0;                                     // kernels inside the captured step (for cpp_launch_count)
+};
+struct GraphCache {
+  GraphSlot slots[4];
+  int clock = 0;
+  void clear();
+  ~GraphCache() { clear(); }
+};
+// body(stream) enqueues the step; returns a cpp_status
+template <typename Body>
+int run_graphed(GraphCache& gc, const void* const (&key)[8], const int (&ikey)[5], cudaStream_t s, cudaStream_t cap_stream, Body body) {
+  GraphSlot* hit = nullptr; GraphSlot* lru = &gc.slots[0];
+  for (auto& c : gc.slots) {
+    bool eq = c.seen > 0;
+    for (int i = 0; i < 8 && eq; ++i) eq = c.key[i] == key[i];
+    for (int i = 0; i < 5 && eq; ++i) eq = c.ikey[i] == ikey[i];
+    if (eq) { hit = &c; break; }
+    if (c.used < lru->used) lru = &c;
+  }
+  const bool same = hit != nullptr;
+  GraphSlot& G = same ? *hit : *lru;
+  G.used = ++gc.clock;
+  if (same && G.exec != nullptr) { CPP_CHECK_CUDA(cudaGraphLaunch(G.exec, s)); g_launch_count += G.launches; return CPP_OK; }
+  if (!same) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    for (int i = 0; i < 8; ++i) G.key[i] = key[i];
+    for (int i = 0; i < 5; ++i) G.ikey[i] = ikey[i];
+    G.seen = 1;
+    return body(s);
+  }
+  CPP_CHECK_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+  const long long launches_before = g_launch_count;
+  const int st = body(cap_stream);
+  cudaGraph_t gr = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(cap_stream, &gr);
+  if (st != CPP_OK) { if (gr) cudaGraphDestroy(gr); G.seen = 0; return st; }
+  if (ce != cudaSuccess) { G.seen = 0; set_error("graph capture failed: %s", cudaGetErrorString(ce)); return CPP_ERR_CUDA; }
+  G.launches = (int)(g_launch_count - launches_before);
+  const cudaError_t ie = cudaGraphInstantiate(&G.exec, gr, 0);
+  cudaGraphDestroy(gr);
+  if (ie != cudaSuccess) { G.exec = nullptr; G.seen = 0; set_error("graph instantiate failed: %s", cudaGetErrorString(ie)); return CPP_ERR_CUDA; }
+  CPP_CHECK_CUDA(cudaGraphLaunch(G.exec, s));
+  return CPP_OK;
+}
+bool step_streams_enabled();
+bool step_graphs_enabled();
+
 struct DDPG {
   cpp_ddpg_config cfg;
   Net actor, critic;
@@ -56,14 +111,7 @@ struct DDPG {
   bool streams_ready = false;
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};   // packed-weight scratch per chain (actor, critic, target actor, target critic)
   void* wgs[2] = {nullptr, nullptr};                      // weight-gradient partials per backward chain
-  struct GraphSlot {
-    cudaGraphExec_t exec = nullptr;
-    const void* key[8] = {};
-    int ikey[5] = {};
-    int seen = 0, used = 0;
-    int launches = 0;                                     // kernels inside the captured step (for cpp_launch_count)
-  } graph[2][4];                                          // [0] backward only, [1] backward + apply; a few argument sets each
-  int graph_clock = 0;
+  GraphCache graph[2];                                    // [0] backward only, [1] backward + apply
   int check_loss(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
                  float* loss, float* td_out, float* q_out, cudaStream_t s);
   int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
@@ -99,6 +147,19 @@ struct NAF {
   int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
   int value_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
   int update_targets(float coeff, cudaStream_t s);
+  // fused backward: value / mu / l chains and the target value chain on forked streams, one CUDA graph per argument set
+  int backward_body(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
+                    int B_global, bool multi, cudaStream_t s);
+  int ensure_streams();
+  ~NAF();
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // mu chain, l chain, target value chain
+  cudaStream_t cap_stream = nullptr;
+  cudaEvent_t ev[10] = {};
+  bool streams_ready = false;
+  void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};    // packed-weight scratch per chain (value, mu, l, target value)
+  void* wgs[3] = {nullptr, nullptr, nullptr};
+  double* mom_scratch2 = nullptr;
+  GraphCache graph;
 };
 
 struct LRPG {
