@@ -154,14 +154,16 @@ def assert_flat_grads_close(got_flat, want_flat, cpu32_flat, nets, tc_route, wha
     den = max(np.abs(a64).max(), 1e-30)
     diff = np.abs(g - a64) / den
     e_gpu, e_cpu = float(diff.max()), float(np.abs(a32 - a64).max() / den)
-    if e_gpu <= max(TOL, 4.0 * e_cpu):
+    # ill-conditioned quantities (cancelling sums, e.g. the bias gradient of the 1e-3-weight tanh head) are bounded by the
+    # fp32 CPU path's own error; the tensor-core route carries ~1e-6 instead of ~1.2e-7 relative forward error, hence 8x
+    if e_gpu <= max(TOL, 8.0 * e_cpu):
       worst = max(worst, e_gpu)
       continue
     # Only a conv variable may exceed the arithmetic tolerance, and only in the way a flipped gate does it: the golden
     # batches are tiny (one gate is ~1/500 of a conv1 filter's gradient terms), a flipped conv-k gate touches ONE output
     # channel (<= 10 % + of the entries) of the conv layers at or below k, everything else stays within 1e-5.
     assert "/conv" in n, "%s %s: GPU rel err %.3e vs fp64 (fp32 CPU path: %.3e)" % (what, n, e_gpu, e_cpu)
-    frac_ok = float((diff <= max(TOL, 4.0 * e_cpu)).mean())
+    frac_ok = float((diff <= max(TOL, 8.0 * e_cpu)).mean())
     assert frac_ok >= 0.7 and e_gpu <= 5e-2, "%s %s: rel err %.3e, only %.0f %% of the entries within tolerance" % (what, n, e_gpu, 100 * frac_ok)
     worst = max(worst, e_gpu)
   return worst
