@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
 // tile t+1 overlap the epilogue of tile t), all handed over through mbarriers.
 constexpr int kEpiWarps = 4, kFillWarps = 8;
 constexpr int kThreads2 = 32 * (kEpiWarps + kFillWarps + 1);
-enum { BAR_FULL_PL = 0, BAR_EMPTY_PL = 2, BAR_FULL_ACC = 4, BAR_EMPTY_ACC = 6, BAR_STAGE = 8, BAR_COUNT = 10 };
+constexpr int kMaxStageSlots = 4;
+enum { BAR_FULL_PL = 0, BAR_EMPTY_PL = 2, BAR_FULL_ACC = 4, BAR_EMPTY_ACC = 6, BAR_STAGE = 8, BAR_COUNT = 8 + kMaxStageSlots };
 
 struct SmemLayout { uint32_t planes, bsm, stage, corr, bars, tmem, total; };
 
@@ -198,7 +199,7 @@ __host__ __device__ inline SmemLayout smem_layout(const FwdPlan& P) {
   uint32_t off = 0;
   L.planes = off; off += 2u * (uint32_t)P.unit_bytes;
   L.bsm = off; off += (uint32_t)P.n_pairs * 2 * P.N * 16;
-  L.stage = off; off += 2u * (uint32_t)P.stage_bytes;
+  L.stage = off; off += (uint32_t)P.stage_slots * (uint32_t)P.stage_bytes;
   const int ncls = 2 * P.PAD + 1;
   L.corr = off; off += (uint32_t)((ncls * ncls * P.nets * CO + 4) * 4);
   off = (off + 15) & ~15u;
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[BAR_FULL_PL + i], kFillWarps); mbar_init(&bars[BAR_EMPTY_PL + i], 1);
       mbar_init(&bars[BAR_FULL_ACC + i], 1); mbar_init(&bars[BAR_EMPTY_ACC + i], kEpiWarps);
-      mbar_init(&bars[BAR_STAGE + i], 1);
     }
+    for (int i = 0; i < kMaxStageSlots; ++i) mbar_init(&bars[BAR_STAGE + i], 1);
     fence_mbar_init();
   }
   if (warp == kEpiWarps + kFillWarps) tmem_alloc(tmem_slot, 512);
@@ -403,6 +404,31 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
     const int n_groups = (P.rows_alloc + P.crh - 1) / P.crh;
     const int rowC = W * C;
     uint32_t it = 0, icnt = 0, wcnt = 0;                           // units done; staging copies issued / consumed
+    // producer cursor (fill thread 0): raw rows are requested up to stage_slots groups ahead of the re-layout, across
+    // unit boundaries, so the TMA latency is off the fill warps' critical path
+    const uint32_t NS = (uint32_t)P.stage_slots;
+    UnitIter pui(P);
+    bool p_ok = pui.next();
+    int p_g = 0;
+    auto issue_next = [&]() {                                      // thread ftid == 0 only
+      while (p_ok) {
+        const int pyh0 = (128 * pui.t0) / Pq - 1;
+        const int rho0 = p_g * P.crh, rho1 = min(rho0 + P.crh, P.rows_alloc);
+        const int yc0 = max(0, 2 * (pyh0 + rho0)), yc1 = min(H, 2 * (pyh0 + rho1));
+        const __half* pimg = P.x + (size_t)(P.rows ? P.rows[pui.b] : pui.b) * img_elems;
+        if (++p_g >= n_groups) { p_g = 0; p_ok = pui.next(); }
+        if (yc1 > yc0) {
+          const uint32_t sb = icnt % NS, bytes = (uint32_t)(yc1 - yc0) * rowC * 2;
+          fence_proxy_async();                                     // the buffer was read through the generic proxy before
+          mbar_expect_tx(&bars[BAR_STAGE + sb], bytes);
+          bulk_g2s(stage_base + (size_t)sb * P.stage_bytes, pimg + (size_t)yc0 * rowC, bytes, &bars[BAR_STAGE + sb]);
+          ++icnt;
+          return;
+        }
+      }
+    };
+    if (P.use_bulk && P.in_layout != 2 && ftid == 0)
+      for (uint32_t i = 0; i < NS; ++i) issue_next();
     for (UnitIter ui(P); ui.next(); ++it) {
       const int b = ui.b;
       const int py_first = (128 * ui.t0) / Pq, yh0 = py_first - 1;
@@ -450,28 +476,15 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
         rho0 = g * P.crh; rho1 = min(rho0 + P.crh, P.rows_alloc);
         yc0 = max(0, 2 * (yh0 + rho0)); yc1 = min(H, 2 * (yh0 + rho1));
       };
-      auto issue = [&](int g) {                                    // thread ftid == 0 only
-        int rho0, rho1, yc0, yc1;
-        group_rows(g, rho0, rho1, yc0, yc1);
-        if (yc1 > yc0) {
-          const uint32_t sb = icnt & 1, bytes = (uint32_t)(yc1 - yc0) * rowC * 2;
-          fence_proxy_async();                                     // the buffer was read through the generic proxy before
-          mbar_expect_tx(&bars[BAR_STAGE + sb], bytes);
-          bulk_g2s(stage_base + (size_t)sb * P.stage_bytes, img + (size_t)yc0 * rowC, bytes, &bars[BAR_STAGE + sb]);
-          ++icnt;
-        }
-      };
-      if (P.use_bulk && ftid == 0) issue(0);
       for (int g = 0; g < n_groups; ++g) {
         int rho0, rho1, yc0, yc1;
         group_rows(g, rho0, rho1, yc0, yc1);
         const bool have = yc1 > yc0;
         const unsigned short* stage = nullptr;
         if (P.use_bulk) {
-          if (ftid == 0 && g + 1 < n_groups) issue(g + 1);         // prefetch: its buffer was released by the barrier below
           if (have) {
-            const uint32_t sb = wcnt & 1;
-            mbar_wait(&bars[BAR_STAGE + sb], (wcnt >> 1) & 1);
+            const uint32_t sb = wcnt % NS;
+            mbar_wait(&bars[BAR_STAGE + sb], (wcnt / NS) & 1);
             stage = reinterpret_cast<const unsigned short*>(stage_base + (size_t)sb * P.stage_bytes);
             ++wcnt;
           }
@@ -532,6 +545,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
           }
         }
         named_bar_sync(1, nfill);                                  // every fill thread is done with this staging buffer
+        if (P.use_bulk && have && ftid == 0) issue_next();         // ... which the producer cursor refills right away
       }
       fence_proxy_async();                                         // generic-proxy plane writes -> visible to the tensor core
       __syncwarp();
@@ -654,8 +668,11 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, 
   const int64_t tiles_per_cta = ceil_div((int64_t)B * P->tiles_per_image, sm_budget());
   const int want_tpu = (int)std::max<int64_t>(1, std::min<int64_t>(8, tiles_per_cta / 6));
   int best_tpu = 0;
-  for (int tpu = std::min(P->tiles_per_image, want_tpu); tpu >= 1; --tpu)
-    if (size_unit(tpu) <= kSmemLimit) { best_tpu = tpu; break; }
+  for (int ns = kMaxStageSlots; ns >= 2 && best_tpu == 0; ns -= 2) {      // deepest staging ring that leaves room for a unit
+    P->stage_slots = ns;
+    for (int tpu = std::min(P->tiles_per_image, want_tpu); tpu >= 1; --tpu)
+      if (size_unit(tpu) <= kSmemLimit) { best_tpu = tpu; break; }
+  }
   CPP_REQUIRE(best_tpu > 0, "conv_tc: %dx%dx%d does not fit shared memory", H, W, C);
   P->units_per_image = (int)ceil_div(P->tiles_per_image, best_tpu);
   P->smem_bytes = size_unit(best_tpu);

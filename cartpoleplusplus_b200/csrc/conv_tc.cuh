@@ -45,6 +45,7 @@ struct FwdPlan {
   int G8, R, nR;            // full 8-channel groups, remainder channels, packed slabs per ky
   int n_planes, rows_alloc, plane_bytes, unit_bytes;
   int crh, stage_bytes, use_bulk;   // parity rows per staging group, staging buffer bytes, TMA bulk copy usable
+  int stage_slots;                  // staging ring depth: raw rows are fetched this many groups ahead, across units
   int tiles_per_image, tiles_per_unit, units_per_image, n_units;
   int n_pairs;
   int smem_bytes;

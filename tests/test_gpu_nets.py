@@ -85,7 +85,8 @@ def _oracle_ddpg(shape, pixels, B, seed, dtype=torch.float64):
   return P, batch
 
 
-@pytest.mark.parametrize("shape,B", [((64, 64, 3, 1, 3), 256), ((50, 50, 3, 1, 2), 128)], ids=["c3", "default50"])
+@pytest.mark.parametrize("shape,B", [((64, 64, 3, 1, 3), 256), ((50, 50, 3, 1, 2), 128), ((128, 128, 3, 2, 4), 12)],
+                         ids=["c3", "default50", "c5shape"])
 def test_ddpg_full_size_vs_live_oracle(shape, B):
   """BASELINE config 3 (64x64, R=3, C=1, batch 256) and the reference's default 50x50 render: forward observables
   within 1e-5 of the fp64 oracle; gradients per variable within 1e-5 or the fp32 CPU path's own error (flips)"""
