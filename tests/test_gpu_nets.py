@@ -114,7 +114,9 @@ def test_ddpg_full_size_vs_live_oracle(shape, B):
   eng.critic_apply()
   for k in ("actor", "critic"):
     want = np.concatenate([orc.P[n].numpy().reshape(-1) for n in U.names_of(nets[k])])
-    e["P_" + k] = U.assert_close(U.flat_of(nets[k]), want, what="params " + k)
+    # with a dozen samples one flipped max-pool gate (see gpu_util.assert_grads_close) is a visible share of a conv filter's
+    # gradient and moves its parameters by lr * clip * that share; at full batch sizes the plain 1e-5 holds
+    e["P_" + k] = U.assert_close(U.flat_of(nets[k]), want, tol=U.TOL if B >= 64 else 5e-5, what="params " + k)
   print("full-size errors vs fp64 oracle:", json.dumps(e))
   print("per-variable gradient errors (gpu vs fp64, cpu-fp32 vs fp64):", json.dumps({k: ["%.2e" % v[0], "%.2e" % v[1]] for k, v in rep.items()}))
 
