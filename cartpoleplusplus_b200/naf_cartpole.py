@@ -195,9 +195,7 @@ class NAFEngine(EngineBase):
     self.world_size, self.rank = dp.world_size, dp.rank
 
   def _batch_args(self, batch):
-    s1 = self.stage("s1", batch.state_1); s2 = self.stage("s2", batch.state_2)
-    a = self.stage("a", batch.action, torch.float32); r = self.stage("r", batch.reward, torch.float32)
-    m = self.stage("m", batch.terminal_mask, torch.float32)
+    s1, a, r, m, s2 = self._staged(batch)
     return s1, a, r, m, s2, int(s1.shape[0])
 
   def backward(self, batch):
@@ -212,11 +210,19 @@ class NAFEngine(EngineBase):
     _lib.check(self.lib.cpp_naf_apply(self.handle, 1 if check else 0, C.byref(loss), self._stream()))
     return float(loss.value)
 
-  def train(self, batch):
+  def train(self, batch, moments=None):
+    """naf.train(batch) (naf_cartpole.py:264-272).  moments: optional (mean_inv_s1, mean_inv_s2) device tensors with the
+    whitening statistics of the GLOBAL batch (data parallel: every rank trains on a slice of it)"""
+    if moments is not None:
+      _lib.check(self.lib.cpp_naf_set_moments(self.handle, _lib.ptr(moments[0]), _lib.ptr(moments[1])))
     self.backward(batch)
+    if moments is not None:
+      _lib.check(self.lib.cpp_naf_set_moments(self.handle, None, None))
     if self.dp is not None:
-      self.dp.all_reduce_sum(self.buffers["grads"])
-    return self.apply(True)
+      self.dp.all_reduce_sum(self.buffers["grads"])        # the single gradient all-reduce of the step (SURVEY.md 8e)
+    loss = self.apply(True)
+    self._release_slot()
+    return loss
 
   def debug_values(self, batch):
     s1, a, r, m, s2, B = self._batch_args(batch)
