@@ -40,22 +40,6 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok, spins = 0;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (!ok && ++spins > (1u << 24)) __trap();   // a lost arrival must fail loudly, never hang the GPU
-  } while (!ok);
-}
-
 // up to 8 halfs (zero padded) from a 2-byte aligned shared-memory address
 __device__ __forceinline__ uint4 load8h(const unsigned short* p, int nch) {
   if (nch >= 8) {
@@ -109,22 +93,19 @@ __host__ __device__ inline Smem smem_layout(const Plan& P) {
   const uint32_t planes_b = (uint32_t)P.nvec * P.plane_bytes, dy_b = (uint32_t)P.band_rows * P.Wp * P.NTp * 16;
   L.planes = 0; L.dy = planes_b; L.buf_stride = planes_b + dy_b;
   L.raw = 2 * L.buf_stride;
-  L.total = L.raw + 2u * (uint32_t)P.raw_bytes + 16;     // two raw-row buffers; + 16: the B-fragment load of an odd tile count reads one vector past the end
+  L.total = L.raw + (uint32_t)P.raw_bytes + 16;          // + 16: the B-fragment load of an odd tile count reads one vector past the end
   return L;
 }
 
-constexpr int kDyItems = 3;        // (2x2 window, network) items a staging thread may own per band
-constexpr int kProdWarps = 2;      // staging warps (the other NW warps only issue ldmatrix + mma.sync)
+constexpr int kDyItems = 1;        // (2x2 window, network) items a thread owns per band (the plan shrinks the band if there are more)
 
 template <int MT, int NT>
-__global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT * NT <= 16) ? 128 : 200) conv_wgrad_mma_kernel(const __grid_constant__ Plan P) {
+__global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_wgrad_mma_kernel(const __grid_constant__ Plan P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const Smem L = smem_layout(P);
+  const unsigned short* raw = reinterpret_cast<const unsigned short*>(smem + L.raw);
 
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  // warp roles: warps [0, NW) multiply, warps [NW, NW + kProdWarps) stage the next band (global -> shared, re-layout, dY pieces)
-  const bool producer = warp >= P.NW;
-  const int stid = tid - 32 * P.NW, snthr = 32 * kProdWarps, swarp = warp - P.NW;
   const int H = P.H, W = P.W, C = P.C, KS = P.KS, PAD = P.PAD, PH = P.PH, PW = P.PW;
   const int Wp = P.Wp, pitch = P.pitch, rows_in = P.rows_in, NTp = P.NTp, nets = P.nets, BR = P.band_rows;
   const int rowC = W * C;
@@ -194,8 +175,8 @@ __global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT
   int it_pack[kDyItems];                                               // this thread's items (net | window col << 4 | window row << 20): the same for every band
 #pragma unroll
   for (int k = 0; k < kDyItems; ++k) {
-    const int it = stid + k * snthr;
-    it_pack[k] = producer ? ((it % nets) | (((it / nets) % wp2) << 4) | ((it / (nets * wp2)) << 20)) : 0;
+    const int it = tid + k * nthr;
+    it_pack[k] = (it % nets) | (((it / nets) % wp2) << 4) | ((it / (nets * wp2)) << 20);
   }
   int cur_b = 0, cur_bi = 0;                                            // (image, band-in-image) of the band being multiplied
   auto band_rows_of = [&](bool next, int& b, int& y0, int& ylo, int& yhi) {   // next: the band after the current one (no division)
@@ -210,12 +191,12 @@ __global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT
     band_rows_of(next, b, y0, ylo, yhi);
     const __half* src = P.x + ((size_t)b * H + ylo) * rowC;
     const int n_bytes = (yhi - ylo) * rowC * 2;
-    const uint32_t dst = smem_u + L.raw + (uint32_t)buf * P.raw_bytes;
+    const uint32_t dst = smem_u + L.raw;
     if (P.dup == 2) {
       // 24-channel piece layout: every plane vector is one aligned 16-byte global vector; the zero padding is a zero-size copy
-      const int nwarps = kProdWarps;
+      const int nwarps = nthr >> 5;
       const uint32_t pl = smem_u + (uint32_t)buf * L.buf_stride + L.planes;
-      for (int lr = swarp; lr < rows_in; lr += nwarps) {
+      for (int lr = warp; lr < rows_in; lr += nwarps) {
         const int y = y0 - PAD + lr;
         const bool yok = y >= 0 && y < H;
         const __half* rowg = P.x + ((size_t)b * H + (yok ? y : 0)) * rowC;
@@ -231,16 +212,16 @@ __global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT
         }
       }
     } else if (raw_mode == 16) {
-      for (int i = stid * 16; i < n_bytes; i += snthr * 16)
+      for (int i = tid * 16; i < n_bytes; i += nthr * 16)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i), "l"(reinterpret_cast<const char*>(src) + i) : "memory");
     } else if (raw_mode == 4) {
-      for (int i = stid * 4; i < n_bytes; i += snthr * 4)
+      for (int i = tid * 4; i < n_bytes; i += nthr * 4)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i), "l"(reinterpret_cast<const char*>(src) + i) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
     for (int k = 0; k < kDyItems; ++k) {
-      const int it = stid + k * snthr;
+      const int it = tid + k * nthr;
 #pragma unroll
       for (int v = 0; v < 5; ++v) { gq[k][v] = make_float2(0.f, 0.f); aq[k][v] = 0x0404; }
       if (it < dy_items) {
@@ -261,14 +242,14 @@ __global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT
     int b, y0, ylo, yhi;
     band_rows_of(next, b, y0, ylo, yhi);
     if (raw_mode == 0 && P.dup != 2) {
-      unsigned short* d = reinterpret_cast<unsigned short*>(smem + L.raw + (size_t)buf * P.raw_bytes);
+      unsigned short* d = reinterpret_cast<unsigned short*>(smem + L.raw);
       const unsigned short* s2 = reinterpret_cast<const unsigned short*>(P.x + ((size_t)b * H + ylo) * rowC);
-      for (int i = stid; i < (yhi - ylo) * rowC; i += snthr) d[i] = s2[i];
+      for (int i = tid; i < (yhi - ylo) * rowC; i += nthr) d[i] = s2[i];
     }
     __half* dys = reinterpret_cast<__half*>(smem + buf * L.buf_stride + L.dy);
 #pragma unroll
     for (int k = 0; k < kDyItems; ++k) {
-      const int it = stid + k * snthr;
+      const int it = tid + k * nthr;
       if (it < dy_items) {
         const int net = it_pack[k] & 15, pxl = (it_pack[k] >> 4) & 0xffff, pyl = it_pack[k] >> 20;
         const float sc = s_scale[net];
@@ -304,11 +285,10 @@ __global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT
     int b, y0, ylo, yhi;
     band_rows_of(next, b, y0, ylo, yhi);
     uint8_t* planes = smem + buf * L.buf_stride + L.planes;
-    const unsigned short* raw = reinterpret_cast<const unsigned short*>(smem + L.raw + (size_t)buf * P.raw_bytes);
     const uint32_t ONE = 0x3C00u;                                          // fp16 1.0
-    const int nwarps = kProdWarps;
+    const int nwarps = nthr >> 5;
     const bool fast_r2 = P.R == 2 && KS == 5 && C == 8 * P.G8 + 1;          // c3: 9 pixels channels + 1
-    for (int item = swarp; item < P.nvec * rows_in; item += nwarps) {
+    for (int item = warp; item < P.nvec * rows_in; item += nwarps) {
       const int v = item / rows_in, lr = item - v * rows_in;
       const int y = y0 - PAD + lr;
       uint4* dst = reinterpret_cast<uint4*>(planes + (size_t)v * P.plane_bytes + (size_t)lr * pitch * 16);
@@ -368,42 +348,21 @@ __global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT
 
   const int band0 = (int)((long long)P.total_bands * blockIdx.x / gridDim.x);
   const int band1 = (int)((long long)P.total_bands * (blockIdx.x + 1) / gridDim.x);
-  const int nb = band1 - band0;
-  __shared__ uint64_t bars[4];                                             // full[2] (staged band ready), empty[2] (band consumed)
-  if (tid == 0) {
-    mbar_init(&bars[0], kProdWarps); mbar_init(&bars[1], kProdWarps);
-    mbar_init(&bars[2], P.NW); mbar_init(&bars[3], P.NW);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();                                                         // s_scale, s_pk, zeroed dY buffers, barriers - the last CTA-wide sync
-  if (nb <= 0) { if (!producer) flush(); return; }
-  cur_b = band0 / P.bands_per_image; cur_bi = band0 - cur_b * P.bands_per_image;
-
-  if (producer) {
-    // ===================================================================== staging warps
+  __syncthreads();                                                         // s_scale, zeroed dY buffers
+  if (band0 < band1) {
+    cur_b = band0 / P.bands_per_image; cur_bi = band0 - cur_b * P.bands_per_image;
     issue_loads(false, 0);
-    for (int j = 0; j < nb; ++j) {
-      const int buf = j & 1;
-      if (j >= 2) mbar_wait(&bars[2 + buf], ((j >> 1) - 1) & 1);           // the multiply warps are done with band j-2 (same buffers)
-      stage_dy(false, buf);                                                // also waits for this thread's cp.async of band j
-      asm volatile("bar.sync 1, %0;" ::"r"(32 * kProdWarps) : "memory");    // band j has landed for every staging thread, and
-                                                                           // all of them are done re-laying band j-1 (raw buffer free)
-      if (j + 1 < nb) {
-        if (P.dup == 2 && j >= 1) mbar_wait(&bars[2 + (buf ^ 1)], (((j + 1) >> 1) - 1) & 1);   // cp.async lands in the planes of band j-1
-        issue_loads(true, buf ^ 1);                                        // in flight while band j is re-laid and band j+1 waits its turn
-      }
-      if (P.dup != 2) stage_planes(false, buf);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[buf]);                              // release: band j is staged
-      if (++cur_bi == P.bands_per_image) { cur_bi = 0; ++cur_b; }
-    }
-    return;
+    stage_dy(false, 0);
+    __syncthreads();
+    if (P.dup != 2) stage_planes(false, 0);
   }
-  // ======================================================================= multiply warps
+  __syncthreads();
   int since_flush = 0;
-  for (int j = 0; j < nb; ++j) {
-    const int buf = j & 1;
-    mbar_wait(&bars[buf], (j >> 1) & 1);
+  for (int band = band0; band < band1; ++band) {
+    const int buf = (band - band0) & 1;
+    const bool has_next = band + 1 < band1;
+    if (has_next) issue_loads(true, buf ^ 1);
+    // ---- MMAs: K runs over the band's output pixels, 16 per step
     {
       const int y0 = cur_bi * BR;
       const int ly_end = min(BR, H - y0);
@@ -413,7 +372,7 @@ __global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT
           uint32_t bf[(NT + 1) / 2][4];
           const uint32_t b_addr = b_lane + boff + (uint32_t)((ly * Wp + x0) * NTp * 16);
 #pragma unroll
-          for (int jj = 0; jj < (NT + 1) / 2; ++jj) ldsm_x4_t(b_addr + (uint32_t)(jj * 32), bf[jj]);
+          for (int j = 0; j < (NT + 1) / 2; ++j) ldsm_x4_t(b_addr + (uint32_t)(j * 32), bf[j]);
           const uint32_t a_off = boff + (uint32_t)((ly * pitch + x0) * 16);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -424,10 +383,14 @@ __global__ void __launch_bounds__(32 * (kMaxWarps + kProdWarps)) __maxnreg__((MT
           }
         }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[2 + buf]);                            // this warp is done reading band j's buffers
+    if (has_next) {
+      stage_dy(true, buf ^ 1);                                         // buffer buf^1 was last read one iteration ago
+      __syncthreads();                                                     // raw rows of band+1 are complete in shared memory
+      if (P.dup != 2) stage_planes(true, buf ^ 1);
+    }
+    __syncthreads();                                                       // band+1 staged; every warp is done reading `buf` and raw
     if (++since_flush >= P.flush_every) { flush(); since_flush = 0; }
-    if (++cur_bi == P.bands_per_image) { cur_bi = 0; ++cur_b; }
+    if (++cur_bi == P.bands_per_image) { cur_bi = 0; ++cur_b; }             // advance to the next band
   }
   if (since_flush > 0 || first_flush) flush();
 }
@@ -535,7 +498,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
   P->NTp = P->NT | 1;
   P->raw_bytes = dup == 2 ? 0 : (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
   P->smem_bytes = (int)smem_layout(*P).total;
-  if (P->smem_bytes > 220 * 1024 || (P->band_rows / 2) * (P->Wp / 2) * nets > kDyItems * 32 * kProdWarps) {        // wide images: two-row bands keep both staging buffers inside one SM's shared memory
+  if (P->smem_bytes > 220 * 1024 || (P->band_rows / 2) * (P->Wp / 2) * nets > kDyItems * 32 * P->NW) {        // wide images: two-row bands keep both staging buffers inside one SM's shared memory
     P->band_rows = 2;
     P->rows_in = P->band_rows + 2 * P->PAD;
     P->plane_bytes = P->rows_in * P->pitch * 16;
@@ -550,7 +513,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
   CPP_REQUIRE(P->smem_bytes <= 220 * 1024, "wgrad_mma: %dx%dx%d does not fit shared memory", H, W, C);
   P->bands_per_image = (int)ceil_div(H, P->band_rows);
   P->total_bands = B * P->bands_per_image;
-  CPP_REQUIRE((P->band_rows / 2) * (P->Wp / 2) * nets <= kDyItems * 32 * kProdWarps, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
+  CPP_REQUIRE((P->band_rows / 2) * (P->Wp / 2) * nets <= kDyItems * 32 * P->NW, "wgrad_mma: image too wide for the dY staging (W=%d)", W);
   CPP_REQUIRE(P->nR <= 8, "wgrad_mma: too many packed planes");
 
   const int occ = (P->MT * P->NT <= 16 && P->smem_bytes <= 110 * 1024) ? 2 : 1;
@@ -583,7 +546,7 @@ static int launch_main(const Plan& P, cudaStream_t s) {
     CPP_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured = true;
   }
-  k<<<P.grid, 32 * (P.NW + kProdWarps), P.smem_bytes, s>>>(P);
+  k<<<P.grid, 32 * P.NW, P.smem_bytes, s>>>(P);
   CPP_CHECK_LAUNCH();
   return CPP_OK;
 }
