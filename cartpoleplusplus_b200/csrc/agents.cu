@@ -59,10 +59,8 @@ void DDPG::carve(void* ws, bool assign) {
   double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(norm_scratch_doubles());
   double* msc2 = cv.take<double>(moments_scratch_doubles(C));
   float* sc = cv.take<float>(4);
-  const size_t xpb = actor.pixels ? (size_t)prelay_elems(B, actor.spec.H, actor.spec.W, actor.spec.Cin, actor.conv[0].KS) * sizeof(__half) : 0;
-  void* xpa = cv.take<char>(xpb); void* xpb2 = cv.take<char>(xpb);
   ws_bytes = cv.off;
-  if (assign) { mom_scratch2 = msc2; xp1 = xpa; xp2 = xpb2; }
+  if (assign) mom_scratch2 = msc2;
   if (assign) {
     ws_actor = wa; ws_critic = wc; ws_target = wt; ws_target2 = wt2; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; mu = mu_;
     tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts2; tcs[3] = ts4; this->wgs[0] = wgs; this->wgs[1] = wgs2; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
@@ -231,7 +229,6 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   const float *m1 = nullptr, *m2 = nullptr;
   const Net* g2[2] = {&actor, &critic};
   int tc1 = 0, tc2 = 0;
-  const bool use_pre = prelay_enabled() && actor.tc_route(is_f16);       // pixel states are re-laid once for both conv1 kernels
   if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s0)); ones_ready = true; }
   CPP_TRY(record(E_START, s0));
   CPP_TRY(wait(sta, E_START));
@@ -240,8 +237,7 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
     CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s0));
     cur_m1 = m1;
     const float* pp[2] = {P, P + off_c}; char* wss[2] = {ws_actor, ws_critic};
-    if (use_pre) CPP_TRY(launch_prelay(s1, B, actor.spec.H, actor.spec.W, actor.spec.Cin, actor.conv[0].KS, xp1, s0));
-    CPP_TRY(conv1_forward_group(2, g2, pp, wss, s1, is_f16, m1, B, tcs[0], s0, &tc1, use_pre ? xp1 : nullptr));
+    CPP_TRY(conv1_forward_group(2, g2, pp, wss, s1, is_f16, m1, B, tcs[0], s0, &tc1));
     tr.mark("s0 conv1 fwd {actor,critic}(s1) done", s0);
   }
   {
@@ -251,8 +247,7 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
     mom_scratch = keep;
     CPP_TRY(st);
     const float* pt[2] = {T, T + off_c}; char* wst[2] = {ws_target, ws_target2};
-    if (use_pre) CPP_TRY(launch_prelay(s2, B, actor.spec.H, actor.spec.W, actor.spec.Cin, actor.conv[0].KS, xp2, sta));
-    CPP_TRY(conv1_forward_group(2, g2, pt, wst, s2, is_f16, m2, B, tcs[2], sta, &tc2, use_pre ? xp2 : nullptr));
+    CPP_TRY(conv1_forward_group(2, g2, pt, wst, s2, is_f16, m2, B, tcs[2], sta, &tc2));
     tr.mark("sta conv1 fwd {targets}(s2) done", sta);
   }
   CPP_TRY(record(E_FORK, s0));                                   // conv1(s1) done: the critic chain may start
@@ -307,7 +302,7 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   // ---- conv1 weight gradients of both networks in one pass over state_1; whole GPU
   {
     char* wss[2] = {ws_actor, ws_critic}; float* gr[2] = {buf.grads, buf.grads + off_c};
-    CPP_TRY(conv1_wgrad_group(2, g2, wss, gr, s1, is_f16, m1, B, wgs[0], s0, 1, use_pre ? xp1 : nullptr));
+    CPP_TRY(conv1_wgrad_group(2, g2, wss, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
   }
   tr.mark("s0 conv1 wgrad {actor,critic} done", s0);
   if (with_apply) { CPP_TRY(actor_apply(s0)); CPP_TRY(critic_apply(s0)); }
@@ -324,7 +319,7 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   if (multi || use_graphs()) CPP_TRY(ensure_streams());
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
-  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (prelay_enabled() ? 8 : 0)};
+  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1)};
   return run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
     return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, st);
   });
@@ -399,7 +394,6 @@ void NAF::carve(void* ws, bool assign) {
   void* ts3 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
   void* ts4 = cv.take<char>((size_t)trunk_group_scratch_bytes(3, value));
   double* msc2 = cv.take<double>(moments_scratch_doubles(value.pixels ? value.spec.Cin : 1));
-  void* xpa = cv.take<char>(value.pixels ? (size_t)prelay_elems(B, value.spec.H, value.spec.W, value.spec.Cin, value.conv[0].KS) * sizeof(__half) : 0);
   float* V_ = cv.take<float>(B); float* V2_ = cv.take<float>(B); float* mu_ = cv.take<float>((size_t)B * A); float* lv_ = cv.take<float>((size_t)B * NL);
   float* dV_ = cv.take<float>(B); float* dmu_ = cv.take<float>((size_t)B * A); float* dl_ = cv.take<float>((size_t)B * NL);
   float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
@@ -408,7 +402,7 @@ void NAF::carve(void* ws, bool assign) {
   ws_bytes = cv.off;
   if (assign) {
     ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; V = V_;
-    tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts4; tcs[3] = ts2; this->wgs[0] = wgs; this->wgs[1] = wgs1; this->wgs[2] = wgs2; mom_scratch2 = msc2; xp1 = xpa; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
+    tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts4; tcs[3] = ts2; this->wgs[0] = wgs; this->wgs[1] = wgs1; this->wgs[2] = wgs2; mom_scratch2 = msc2; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
     mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
   }
 }
@@ -479,9 +473,7 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
   const float* pp3[3] = {P, P + off_m, P + off_l};
   char* ws3[3] = {ws_v, ws_m, ws_l};
   int tc1 = 0;
-  const bool use_pre = prelay_enabled() && value.tc_route(is_f16);
-  if (use_pre) CPP_TRY(launch_prelay(s1, B, value.spec.H, value.spec.W, value.spec.Cin, value.conv[0].KS, xp1, s0));
-  CPP_TRY(conv1_forward_group(3, g3, pp3, ws3, s1, is_f16, m1, B, tcs[0], s0, &tc1, use_pre ? xp1 : nullptr));
+  CPP_TRY(conv1_forward_group(3, g3, pp3, ws3, s1, is_f16, m1, B, tcs[0], s0, &tc1));
   CPP_TRY(record(E_C1, s0));
   CPP_TRY(wait(sm, E_C1)); CPP_TRY(wait(sl, E_C1));
   // ---- three forward chains
@@ -511,7 +503,7 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
   g_cta_cap = kNumSMs;
   {
     float* gr[3] = {buf.grads, buf.grads + off_m, buf.grads + off_l};
-    CPP_TRY(conv1_wgrad_group(3, g3, ws3, gr, s1, is_f16, m1, B, wgs[0], s0, 1, use_pre ? xp1 : nullptr));
+    CPP_TRY(conv1_wgrad_group(3, g3, ws3, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
   }
   return CPP_OK;
 }
@@ -559,7 +551,7 @@ int NAF::backward(const void* s1, const float* action, const float* reward, cons
   if (multi || graphs) CPP_TRY(ensure_streams());
   if (!graphs) return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
-  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (prelay_enabled() ? 8 : 0)};
+  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1)};
   return run_graphed(graph, key, ikey, s, cap_stream, [&](cudaStream_t x) {
     return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, x);
   });

@@ -107,7 +107,6 @@ struct DDPG {
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;                      // origin stream of the graph capture (the caller's may be the legacy default stream)
   cudaEvent_t ev[8] = {};
-  void *xp1 = nullptr, *xp2 = nullptr;                    // pre-laid copies of state_1 / state_2 (launch_prelay)
   BackwardAux aux[2];                                     // side streams of the actor / critic backward chains (weight gradients)
   bool streams_ready = false;
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};   // packed-weight scratch per chain (actor, critic, target actor, target critic)
@@ -160,7 +159,6 @@ struct NAF {
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};    // packed-weight scratch per chain (value, mu, l, target value)
   void* wgs[3] = {nullptr, nullptr, nullptr};
   double* mom_scratch2 = nullptr;
-  void* xp1 = nullptr;                                    // pre-laid copy of state_1
   GraphCache graph;
 };
 

@@ -1,7 +1,6 @@
 // extern "C" surface of libcartpolepp.so (include/cartpolepp.h).  Thin: argument checks, object
 // lifetime, exception firewall.
 #include <stdarg.h>
-#include <algorithm>
 #include <stdlib.h>
 #include <string>
 #include <utility>
@@ -74,7 +73,6 @@ int cpp_set_option(const char* name, int32_t value) {
   API_BEGIN
   NEED(name);
   if (strcmp(name, "conv1_tc") == 0) { set_conv1_tc_enabled(value); return CPP_OK; }
-  if (strcmp(name, "prelay") == 0) { set_prelay(value); return CPP_OK; }
   if (strcmp(name, "fused_mlp") == 0) { set_fused_mlp(value); return CPP_OK; }
   if (strcmp(name, "streams") == 0) { set_step_options(value, -2); return CPP_OK; }
   if (strcmp(name, "graphs") == 0) { set_step_options(-2, value); return CPP_OK; }
@@ -193,14 +191,7 @@ int cpp_conv_wgrad(const void* x, int32_t x_is_f16, const float* mean_inv, const
 }
 
 int64_t cpp_conv_tc_scratch_bytes(int32_t nets, int32_t H, int32_t W, int32_t Cin, int32_t KS) {
-  return std::max(tc::conv_tc_scratch_bytes(nets, H, W, Cin, KS, 0), tc::conv_tc_scratch_bytes(nets, H, W, Cin, KS, 1));   // either input layout
-}
-int64_t cpp_prelay_elems(int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS) { return prelay_elems(B, H, W, Cin, KS); }
-int cpp_prelay(const void* x_f16, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS, void* out, void* stream) {
-  API_BEGIN
-  NEED(x_f16); NEED(out);
-  return launch_prelay(x_f16, B, H, W, Cin, KS, out, ST(stream));
-  API_END
+  return tc::conv_tc_scratch_bytes(nets, H, W, Cin, KS);
 }
 int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int32_t nets, const float* const* w,
                         const float* const* bias, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS,

@@ -54,26 +54,7 @@ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 constexpr int kNumSMs = 148;      // B200
 constexpr int kConvCout = 10;     // every conv of the reference trunk has 10 filters (base_network.py:103,111,119)
 
-// How the CE = C + 1 channels of a conv1 input (the pixels plus one constant-one channel) are cut into 16-byte vectors:
-// G8 full groups of 8 channels, and the R = CE % 8 remainder channels packed along kx - entry E = kx * R + r of a
-// remainder vector holds channel 8 G8 + r of the pixel kx - KS/2 columns away - into nR = ceil(KS R / 8) vectors, unless
-// that would not save any K slab.  Shared by the weight-gradient kernel, the tcgen05 forward kernel and the pre-layout pass.
-struct ChannelPack { int G8, R, nR, nvec; };
-static inline ChannelPack channel_pack(int CE, int KS) {
-  ChannelPack p;
-  p.G8 = CE / 8; p.R = CE % 8; p.nR = (KS * p.R + 7) / 8;
-  if (p.R > 0 && p.nR >= KS) { p.G8 += 1; p.R = 0; p.nR = 0; }
-  p.nvec = p.G8 + p.nR;
-  return p;
-}
-
 // ---- kernels launched from more than one translation unit (declared here, defined in the .cu named)
-
-// elementwise.cu: pre-layout of a batch of fp16 NHWC states for the conv1 tensor-core kernels: [B][H][W][nvec][8] fp16 in
-// the ChannelPack order above (zero padding and the constant-one channel resolved), so that both kernels stage their
-// shared-memory planes with plain 16-byte cp.async instead of re-laying 18-byte pixels in every CTA
-int64_t prelay_elems(int B, int H, int W, int C, int KS);
-int launch_prelay(const void* x_f16, int B, int H, int W, int C, int KS, void* out, cudaStream_t s);
 
 // elementwise.cu
 int launch_state_to_f32(const void* state, int is_f16, int B, int dim, float* dst, int ld, cudaStream_t s);

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
     int ky = sl.ky, kx = sl.kx, ch = 0;
     if (valid) {
       if (sl.kind == 0) { ch = 8 * sl.set + e; valid = ch < C; }
-      else { const int E = 8 * sl.set + e; valid = E < KS * P.R; kx = E / P.R; ch = 8 * P.G8 + E % P.R; valid = valid && ch < C; }
+      else { const int E = 8 * sl.set + e; valid = E < KS * P.R; kx = E / P.R; ch = 8 * P.G8 + E % P.R; }
     }
     __half out = __float2half_rn(0.f);
     if (valid) {
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
   } else if (warp < kEpiWarps + kFillWarps) {
     // =========================================================================== fill warps
     const int ftid = tid - 32 * kEpiWarps, nfill = 32 * kFillWarps;
-    const size_t img_elems = P.in_layout == 3 ? (size_t)H * W * (P.G8 + P.nR) * 8 : (size_t)H * W * C;
+    const size_t img_elems = (size_t)H * W * C;
     const int n_groups = (P.rows_alloc + P.crh - 1) / P.crh;
     const int rowC = W * C;
     uint32_t it = 0, icnt = 0, wcnt = 0;                           // units done; staging copies issued / consumed
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
         }
       }
     };
-    if (P.use_bulk && P.in_layout < 2 && ftid == 0)
+    if (P.use_bulk && P.in_layout != 2 && ftid == 0)
       for (uint32_t i = 0; i < NS; ++i) issue_next();
     for (UnitIter ui(P); ui.next(); ++it) {
       const int b = ui.b;
@@ -437,12 +437,11 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
       mbar_wait(&bars[BAR_EMPTY_PL + buf], ((it >> 1) & 1) ^ 1);   // the MMAs that read this buffer two units ago are done
       uint8_t* planes = planes_base + (size_t)buf * P.unit_bytes;
 
-      if (P.in_layout >= 2) {
+      if (P.in_layout == 2) {
         // aligned 24-channel pieces: every plane vector is ONE 16-byte global vector -> cp.async straight into the parity
         // planes (zero-size copy = zero padding); no staging ring, no re-layout, one round trip per unit
         const uint32_t pl = smem_u32(planes);
         const int fw = ftid >> 5, nfw = kFillWarps;
-        const int nvec_in = P.G8 + P.nR;
         for (int rho = fw; rho < P.rows_alloc; rho += nfw) {
           const int yh = yh0 + rho;
           for (int kap = lane; kap < Pq; kap += 32) {
@@ -455,9 +454,10 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
               for (int xp = 0; xp < 2; ++xp) {
                 const int x = 2 * xh + xp;
                 const bool ok = y >= 0 && y < H && x >= 0 && x < W;
-                const __half* g = img + ((size_t)(ok ? y : 0) * W + (ok ? x : 0)) * (nvec_in * 8);
+                const __half* g = img + ((size_t)(ok ? y : 0) * W + (ok ? x : 0)) * kC24;
                 const int nbytes = ok ? 16 : 0;
-                for (int gq = 0; gq < nvec_in; ++gq)           // 3 vectors per pixel (pieces) or G8 + nR (pre-laid state)
+#pragma unroll
+                for (int gq = 0; gq < 3; ++gq)
                   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
                                ::"r"(d0 + (uint32_t)((gq * 4 + yp * 2 + xp) * P.plane_bytes)), "l"(g + 8 * gq), "r"(nbytes) : "memory");
               }
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------ host: plan
-static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, int dgrad = 0, int prelaid = 0) {
+static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, int dgrad = 0) {
   CPP_REQUIRE(KS == 5 || KS == 3, "conv_tc: kernel size %d", KS);
   CPP_REQUIRE(nets >= 1 && nets <= kMaxNets, "conv_tc: %d sibling networks", nets);
   const int PAD = KS / 2;
@@ -602,10 +602,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, 
   P->nets = nets; P->N = (int)round_up(nets * kPieces * CO, 16);
   CPP_REQUIRE(8 * P->N <= 512, "conv_tc: N=%d does not fit two sets of TMEM accumulators", P->N);
   const int rem = C % 8;
-  if (prelaid) {               // the input was pre-laid with the constant-one channel appended (launch_prelay): its packing rule
-    const ChannelPack cpk = channel_pack(C + 1, KS);
-    P->G8 = cpk.G8; P->R = cpk.R; P->nR = cpk.nR;
-  } else if (rem == 1 || rem == 2) { P->G8 = C / 8; P->R = rem; P->nR = (KS * rem + 7) / 8; }
+  if (rem == 1 || rem == 2) { P->G8 = C / 8; P->R = rem; P->nR = (KS * rem + 7) / 8; }
   else { P->G8 = (C + 7) / 8; P->R = 0; P->nR = 0; }
   P->n_planes = 4 * (P->G8 + P->nR);
 
@@ -708,15 +705,15 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, 
 
 static inline size_t bpack_bytes(const FwdPlan& P) { return (size_t)round_up((int64_t)P.n_pairs * 2 * P.N * 16, 256); }
 
-bool conv_tc_supported(int nets, int H, int W, int C, int KS, int prelaid) {
+bool conv_tc_supported(int nets, int H, int W, int C, int KS) {
   FwdPlan P{};
-  const bool ok = build_plan(nets, 1, H, W, C, KS, &P, 0, prelaid) == CPP_OK;
+  const bool ok = build_plan(nets, 1, H, W, C, KS, &P) == CPP_OK;
   return ok;
 }
 
-int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS, int prelaid) {
+int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS) {
   FwdPlan P{};
-  if (build_plan(nets, 1, H, W, C, KS, &P, 0, prelaid) != CPP_OK) return -1;
+  if (build_plan(nets, 1, H, W, C, KS, &P) != CPP_OK) return -1;
   const int ncls = 2 * P.PAD + 1;
   return (int64_t)bpack_bytes(P) + (int64_t)round_up((int64_t)(ncls * ncls * nets * CO + 4) * 4, 256);
 }
@@ -740,10 +737,9 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
                        int x_is_pieces, __half* const* pooled_hl) {
   if (B <= 0) return CPP_OK;
   FwdPlan P{};
-  CPP_TRY(build_plan(nets, B, H, W, C, KS, &P, 0, x_is_pieces == 3));
-  CPP_REQUIRE(x_is_pieces == 0 || x_is_pieces == 3 || (mean_inv == nullptr && C == (x_is_pieces == 2 ? kC24 : 2 * CO)),
-              "conv_tc: piece input has 20 or 24 channels and no whitening");
-  P.Cw = (x_is_pieces == 1 || x_is_pieces == 2) ? CO : C;
+  CPP_TRY(build_plan(nets, B, H, W, C, KS, &P));
+  CPP_REQUIRE(x_is_pieces == 0 || (mean_inv == nullptr && C == (x_is_pieces == 2 ? kC24 : 2 * CO)), "conv_tc: piece input has 20 or 24 channels and no whitening");
+  P.Cw = x_is_pieces ? CO : C;
   P.in_layout = x_is_pieces;
   CPP_REQUIRE(((uintptr_t)x_f16 & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
   P.x = reinterpret_cast<const __half*>(x_f16); P.rows = rows;
@@ -760,7 +756,6 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
   CPP_CHECK_LAUNCH();
   const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, sm_budget());   // persistent: one CTA per SM (it owns all 512 TMEM columns)
-  if (P.in_layout >= 2) return KS == 5 ? launch_main<5, 0>(P, grid, s) : launch_main<3, 0>(P, grid, s);   // direct fill: no packing code
   if (KS == 5) {
     if (P.R == 0) return launch_main<5, 0>(P, grid, s);
     if (P.R == 1) return launch_main<5, 1>(P, grid, s);

@@ -35,8 +35,7 @@ struct FwdPlan {
   __half* pooled_hl[kMaxNets];   // optional: the pooled output again as fp16 pieces in the 24-channel layout below, for the next layer
   int B, H, W, C, PH, PW, Pq, KS, PAD;
   int Cw;                   // weight input channels: C, or 10 when x holds fp16 pieces of an fp32 activation
-  int in_layout;            // 0: plain channels; 1: [hi(10) | lo(10)]; 2: kPieceLayout24 (three aligned 16-byte vectors per pixel);
-                            // 3: pre-laid state [H][W][G8 + nR][8] (launch_prelay)
+  int in_layout;            // 0: plain channels; 1: [hi(10) | lo(10)]; 2: kPieceLayout24 (three aligned 16-byte vectors per pixel)
   int dgrad;                // 1: input-gradient mode - x = un-pooled output gradient pieces, taps flipped and channels transposed,
                             //    no bias / ReLU / pool: every conv position is written to the dense fp32 output pooled[n] [B][H][W][10]
   const float* out_scale;   // dgrad: device scalar the result is multiplied with (undoes the power-of-two scaling of the pieces)
@@ -62,12 +61,11 @@ struct PrepArgs {
   float* corr;
 };
 
-int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS, int prelaid = 0);
-bool conv_tc_supported(int nets, int H, int W, int C, int KS, int prelaid = 0);
+int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS);
+bool conv_tc_supported(int nets, int H, int W, int C, int KS);
 // y_n = maxpool2x2(relu(conv_same(whiten(x), w_n) + b_n)) for n < nets sibling networks in ONE pass over x.
 // x_is_pieces: 1 = x holds [hi(10) | lo(10)] fp16 pieces of an fp32 activation, 2 = the 24-channel piece layout above
-// (conv2/conv3); w has 10 input channels, mean_inv must be NULL; 3 = x is the pre-laid copy of a C-channel fp16 state
-// (launch_prelay), w has C input channels, whitening folded as for 0.  pooled_hl (optional, may be NULL or hold NULLs): piece
+// (conv2/conv3); w has 10 input channels, mean_inv must be NULL.  pooled_hl (optional, may be NULL or hold NULLs): piece
 // copy of the output in the 24-channel layout.
 int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int nets,
                        const float* const* w, const float* const* bias, int B, int H, int W, int C, int KS,

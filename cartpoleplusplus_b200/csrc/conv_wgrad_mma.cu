@@ -192,30 +192,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     const __half* src = P.x + ((size_t)b * H + ylo) * rowC;
     const int n_bytes = (yhi - ylo) * rowC * 2;
     const uint32_t dst = smem_u + L.raw;
-    if (P.dup == 3) {
-      // pre-laid input (launch_prelay): [B][H][W][nvec][8]; main planes are indexed by the input column, packed planes by the
-      // output column; padding = zero-size copy
-      const int nwarps = nthr >> 5;
-      const uint32_t pl = smem_u + (uint32_t)buf * L.buf_stride + L.planes;
-      const int nvec = P.nvec;
-      for (int lr = warp; lr < rows_in; lr += nwarps) {
-        const int y = y0 - PAD + lr;
-        const bool yok = y >= 0 && y < H;
-        const __half* rowg = P.x + ((size_t)b * H + (yok ? y : 0)) * W * nvec * 8;
-        for (int lc = lane; lc < pitch; lc += 32) {
-          const uint32_t d = pl + (uint32_t)((lr * pitch + lc) * 16);
-          const int xm = lc - PAD;
-          const bool okm = yok && xm >= 0 && xm < W, okp = yok && lc < W;
-          for (int v = 0; v < nvec; ++v) {
-            const bool main_v = v < P.G8;
-            const bool ok = main_v ? okm : okp;
-            const __half* g = rowg + ((size_t)(ok ? (main_v ? xm : lc) : 0) * nvec + v) * 8;
-            const int nbytes = ok ? 16 : 0;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + (uint32_t)(v * P.plane_bytes)), "l"(g), "r"(nbytes) : "memory");
-          }
-        }
-      }
-    } else if (P.dup == 2) {
+    if (P.dup == 2) {
       // 24-channel piece layout: every plane vector is one aligned 16-byte global vector; the zero padding is a zero-size copy
       const int nwarps = nthr >> 5;
       const uint32_t pl = smem_u + (uint32_t)buf * L.buf_stride + L.planes;
@@ -264,7 +241,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
   auto stage_dy = [&](bool next, int buf) {
     int b, y0, ylo, yhi;
     band_rows_of(next, b, y0, ylo, yhi);
-    if (raw_mode == 0 && P.dup < 2) {
+    if (raw_mode == 0 && P.dup != 2) {
       unsigned short* d = reinterpret_cast<unsigned short*>(smem + L.raw);
       const unsigned short* s2 = reinterpret_cast<const unsigned short*>(P.x + ((size_t)b * H + ylo) * rowC);
       for (int i = tid; i < (yhi - ylo) * rowC; i += nthr) d[i] = s2[i];
@@ -377,7 +354,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     issue_loads(false, 0);
     stage_dy(false, 0);
     __syncthreads();
-    if (P.dup < 2) stage_planes(false, 0);
+    if (P.dup != 2) stage_planes(false, 0);
   }
   __syncthreads();
   int since_flush = 0;
@@ -409,7 +386,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, (MT * NT <= 16) ? 2 : 1) conv_
     if (has_next) {
       stage_dy(true, buf ^ 1);                                         // buffer buf^1 was last read one iteration ago
       __syncthreads();                                                     // raw rows of band+1 are complete in shared memory
-      if (P.dup < 2) stage_planes(true, buf ^ 1);
+      if (P.dup != 2) stage_planes(true, buf ^ 1);
     }
     __syncthreads();                                                       // band+1 staged; every warp is done reading `buf` and raw
     if (++since_flush >= P.flush_every) { flush(); since_flush = 0; }
@@ -448,7 +425,7 @@ __device__ __forceinline__ float g_at(const Plan& P, int row, int n) {
   return P.gsum[idx];
 }
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const __grid_constant__ Plan P) {
-  const int KS = P.KS, Cr = P.dup == 2 ? CO : (P.dup == 1 ? P.C / 2 : P.C);
+  const int KS = P.KS, Cr = P.dup == 2 ? CO : (P.dup ? P.C / 2 : P.C);
   const int one_ch = P.dup == 2 ? tc::kC24One : P.C;
   const int nw = KS * KS * Cr * CO;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -465,7 +442,7 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const __grid_consta
   const int n0 = net * 2 * CO + o, n1 = n0 + CO;
   const int c_hi = P.dup == 2 ? tc::c24_hi(c) : c, c_lo = P.dup == 2 ? tc::c24_lo(c) : c + Cr;
   float gsum = g_at(P, row_of(P, ky, kx, c_hi), n0) + g_at(P, row_of(P, ky, kx, c_hi), n1);
-  if (P.dup == 1 || P.dup == 2) gsum += g_at(P, row_of(P, ky, kx, c_lo), n0) + g_at(P, row_of(P, ky, kx, c_lo), n1);
+  if (P.dup) gsum += g_at(P, row_of(P, ky, kx, c_lo), n0) + g_at(P, row_of(P, ky, kx, c_lo), n1);
   float v = gsum * inv_scale;
   if (P.mean_inv) {
     const int rs = row_of(P, ky, kx, one_ch);
@@ -484,10 +461,10 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
   P->dup = dup;
   CPP_REQUIRE(dup != 2 || C == tc::kC24, "wgrad_mma: the aligned piece layout has %d channels", tc::kC24);
   P->CE = dup == 2 ? C : C + 1;               // the 24-channel layout already carries its constant-one channel
-  {
-    const ChannelPack cpk = channel_pack(P->CE, KS);
-    P->G8 = cpk.G8; P->R = cpk.R; P->nR = cpk.nR; P->nvec = cpk.nvec;
-  }
+  P->G8 = P->CE / 8; P->R = P->CE % 8;
+  P->nR = (KS * P->R + 7) / 8;
+  if (P->R > 0 && P->nR >= KS) { P->G8 += 1; P->R = 0; P->nR = 0; }          // packing along kx would not save slabs
+  P->nvec = P->G8 + P->nR;
   P->Wp = (int)round_up(W, 16);
   P->pitch = P->Wp + 2 * P->PAD;
   P->band_rows = kBandRows;
@@ -519,7 +496,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
   if (P->NT == 4) P->NT = 5;                                                  // instantiated widths: 3, 5, 8
   if (P->NT == 6 || P->NT == 7) P->NT = 8;
   P->NTp = P->NT | 1;
-  P->raw_bytes = dup >= 2 ? 0 : (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
+  P->raw_bytes = dup == 2 ? 0 : (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
   P->smem_bytes = (int)smem_layout(*P).total;
   if (P->smem_bytes > 220 * 1024 || (P->band_rows / 2) * (P->Wp / 2) * nets > kDyItems * 32 * P->NW) {        // wide images: two-row bands keep both staging buffers inside one SM's shared memory
     P->band_rows = 2;
@@ -530,7 +507,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
       P->slab_off[i] = sl.kind == 0 ? sl.set * P->plane_bytes + (sl.ky * P->pitch + sl.kx) * 16
                                     : (P->G8 + sl.set) * P->plane_bytes + (sl.ky * P->pitch) * 16;
     }
-    P->raw_bytes = dup >= 2 ? 0 : (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
+    P->raw_bytes = dup == 2 ? 0 : (int)round_up((int64_t)P->rows_in * W * C * 2, 16);
     P->smem_bytes = (int)smem_layout(*P).total;
   }
   CPP_REQUIRE(P->smem_bytes <= 220 * 1024, "wgrad_mma: %dx%dx%d does not fit shared memory", H, W, C);
@@ -589,8 +566,7 @@ int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int
   if (B <= 0) return CPP_OK;
   Plan P{};
   CPP_TRY(build_plan(nets, B, H, W, C, KS, &P, dup));
-  CPP_REQUIRE(dup == 0 || dup == 3 || (C % 2 == 0 && mean_inv == nullptr), "wgrad_mma: piece input needs an even channel count and no whitening");
-  CPP_REQUIRE(dup != 3 || ((uintptr_t)x_f16 & 15) == 0, "wgrad_mma: unaligned pre-laid input");
+  CPP_REQUIRE(!dup || (C % 2 == 0 && mean_inv == nullptr), "wgrad_mma: piece input needs an even channel count and no whitening");
   CPP_REQUIRE(dup != 2 || ((uintptr_t)x_f16 & 15) == 0, "wgrad_mma: unaligned piece input");
   CPP_REQUIRE(((uintptr_t)scratch & 255) == 0, "wgrad_mma: unaligned scratch");
   P.x = reinterpret_cast<const __half*>(x_f16); P.mean_inv = mean_inv; P.dup = dup;
@@ -621,7 +597,7 @@ int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int
   CPP_TRY(st);
   wgrad_reduce_kernel<<<(unsigned)ceil_div(P.part_floats, 32), dim3(32, 8), 0, s>>>(P, P.grid);
   CPP_CHECK_LAUNCH();
-  const int Cr = dup == 2 ? CO : (dup == 1 ? C / 2 : C);
+  const int Cr = dup == 2 ? CO : (dup ? C / 2 : C);
   const int total = nets * (KS * KS * Cr * CO + CO);
   wgrad_finalize_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(P);
   CPP_CHECK_LAUNCH();

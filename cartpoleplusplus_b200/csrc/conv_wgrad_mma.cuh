@@ -35,8 +35,6 @@ struct Plan {
   int dup;                         // 1: x holds [hi(C/2) | lo(C/2)] fp16 pieces of an fp32 activation: dw[c] = G[c] + G[c + C/2]
                                    // 2: x is in the 24-channel piece layout of conv_tc.cuh (aligned vectors, constant-one channel
                                    //    included): rows go global -> shared planes with cp.async, no re-layout at all
-                                   // 3: x is the pre-laid copy of a C-channel fp16 state (launch_prelay: ChannelPack vectors, zero
-                                   //    padding and constant-one channel resolved); same result as 0, staging by cp.async only
   // ---- geometry
   int CE;                          // channels incl. the constant-one channel appended at index C
   int G8, R, nR, nvec;             // full 8-channel groups, remainder channels, packed slabs per ky, smem vectors per pixel

@@ -576,49 +576,6 @@ int launch_soft_update(float* target, const float* source, float coeff, int64_t 
   return CPP_OK;
 }
 
-// ---------------------------------------------------------------------------- conv1 pre-layout
-// one thread per (pixel, vector): main vectors are 8 consecutive channels (pixels, then the constant one, then zeros), packed
-// vectors gather the remainder channels of the KS horizontal neighbours
-__global__ void __launch_bounds__(256) prelay_kernel(const __half* __restrict__ x, int64_t n_pix, int H, int W, int C, int KS,
-                                                     ChannelPack cp, uint4* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pix * cp.nvec) return;
-  const int v = (int)(i % cp.nvec);
-  const int64_t pix = i / cp.nvec;
-  const int xq = (int)(pix % W);
-  const unsigned short* row = reinterpret_cast<const unsigned short*>(x) + (pix - xq) * C;      // start of this image row
-  const uint32_t ONE = 0x3C00u;
-  uint32_t h[8];
-  if (v < cp.G8) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ch = 8 * v + e;
-      h[e] = ch < C ? (uint32_t)row[xq * C + ch] : (ch == C ? ONE : 0u);
-    }
-  } else {
-    const int j = v - cp.G8, PAD = KS / 2;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int E = 8 * j + e, kx = E / cp.R, ch = 8 * cp.G8 + E - kx * cp.R;
-      const int xin = xq + kx - PAD;
-      const bool ok = kx < KS && xin >= 0 && xin < W;
-      h[e] = !ok ? 0u : (ch < C ? (uint32_t)row[xin * C + ch] : (ch == C ? ONE : 0u));
-    }
-  }
-  out[i] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-}
-int64_t prelay_elems(int B, int H, int W, int C, int KS) { return (int64_t)B * H * W * channel_pack(C + 1, KS).nvec * 8; }
-int launch_prelay(const void* x_f16, int B, int H, int W, int C, int KS, void* out, cudaStream_t s) {
-  if (B <= 0) return CPP_OK;
-  CPP_REQUIRE(((uintptr_t)out & 15) == 0, "prelay: unaligned output");
-  const ChannelPack cp = channel_pack(C + 1, KS);
-  const int64_t n_pix = (int64_t)B * H * W, n = n_pix * cp.nvec;
-  prelay_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(x_f16), n_pix, H, W, C, KS, cp,
-                                                         reinterpret_cast<uint4*>(out));
-  CPP_CHECK_LAUNCH();
-  return CPP_OK;
-}
-
 int launch_gather(const void* slab, const int32_t* s1_idx, const int32_t* s2_idx, const float* action, const float* reward,
                   const float* mask, const int64_t* idxs, int B, int64_t row_elems, int A, void* o1, void* o2, float* oa,
                   float* orw, float* om, cudaStream_t s) {

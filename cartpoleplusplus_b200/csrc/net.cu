@@ -169,12 +169,6 @@ int Net::forward(const float* params, const void* state, int is_f16, const float
   return forward_fc(params, action, B, ws, out, s, first_fc);
 }
 
-static int g_prelay = -1;
-void set_prelay(int on) { g_prelay = on; }
-bool prelay_enabled() {
-  static const bool d = [] { const char* e = getenv("CARTPOLEPP_PRELAY"); return !(e && e[0] == '0'); }();
-  return g_prelay < 0 ? d : g_prelay != 0;
-}
 static int g_conv1_tc_override = -1;
 void set_conv1_tc_enabled(int on) { g_conv1_tc_override = on; }
 bool conv1_tc_enabled() {
@@ -190,7 +184,7 @@ int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net) {
 }
 
 int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* const* grads, const void* state, int is_f16,
-                      const float* mean_inv, int B, void* scratch, cudaStream_t s, int gmax_from_dgrad, const void* prelaid) {
+                      const float* mean_inv, int B, void* scratch, cudaStream_t s, int gmax_from_dgrad) {
   const Net& n0 = *nets[0];
   if (!n0.pixels) return CPP_OK;
   CPP_REQUIRE(n >= 1 && n <= wg::kMaxNets, "conv1 wgrad group of %d networks", n);
@@ -205,8 +199,8 @@ int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* con
     dw[i] = grads[i] + nets[i]->off_conv_w[0]; db[i] = grads[i] + nets[i]->off_conv_b[0];
   }
   if (scratch != nullptr && n0.tc_route(is_f16) && wg::conv_wgrad_mma_supported(n, c1.H, c1.W, c1.Cin, c1.KS))
-    return wg::launch_conv_wgrad_mma(prelaid ? prelaid : state, mean_inv, prelaid ? 3 : 0, n, gp, am, B, c1.H, c1.W, c1.Cin, c1.KS, dw, db,
-                                     scratch, s, gmax_from_dgrad ? gm : nullptr);
+    return wg::launch_conv_wgrad_mma(state, mean_inv, 0, n, gp, am, B, c1.H, c1.W, c1.Cin, c1.KS, dw, db, scratch, s,
+                                     gmax_from_dgrad ? gm : nullptr);
   for (int i = 0; i < n; ++i) {
     const Net::Layout L = nets[i]->layout(B);
     CPP_TRY(launch_conv_wgrad(c1, state, is_f16, mean_inv, gp[i], am[i], B, dw[i], db[i], reinterpret_cast<float*>(ws[i] + L.wgrad), s));
@@ -216,15 +210,13 @@ int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* con
 
 int64_t trunk_group_scratch_bytes(int n, const Net& net) {
   if (!net.pixels) return 0;
-  int64_t b = std::max(tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS, 0),
-                       tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS, 1));
+  int64_t b = tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
   for (int i = 1; i < 3; ++i) b = std::max(b, tc::conv_tc_scratch_bytes(1, net.conv[i].H, net.conv[i].W, tc::kC24, net.conv[i].KS));
   return b > 0 ? b : 0;
 }
 
 int conv1_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
-                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s, int* took_tc,
-                        const void* prelaid) {
+                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s, int* took_tc) {
   CPP_REQUIRE(n >= 1 && n <= tc::kMaxNets, "trunk group of %d networks", n);
   const Net& n0 = *nets[0];
   *took_tc = 0;
@@ -243,8 +235,8 @@ int conv1_forward_group(int n, const Net* const* nets, const float* const* param
     pooled[i] = reinterpret_cast<float*>(ws[i] + L.pooled[0]); amax[i] = reinterpret_cast<uint8_t*>(ws[i] + L.amax[0]);
     hl[i] = reinterpret_cast<__half*>(ws[i] + L.hl[0]);
   }
-  CPP_TRY(tc::launch_conv_fwd_tc(prelaid ? prelaid : state, nullptr, mean_inv, n, w, b, B, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin,
-                                 n0.conv[0].KS, pooled, amax, tc_scratch, s, prelaid ? 3 : 0, hl));
+  CPP_TRY(tc::launch_conv_fwd_tc(state, nullptr, mean_inv, n, w, b, B, n0.conv[0].H, n0.conv[0].W, n0.conv[0].Cin,
+                                 n0.conv[0].KS, pooled, amax, tc_scratch, s, 0, hl));
   *took_tc = 1;
   return CPP_OK;
 }

@@ -74,12 +74,8 @@ int trunk_forward_group(int n, const Net* const* nets, const float* const* param
                         int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s);
 // the two halves of trunk_forward_group, for callers that run the per-network tails on separate streams:
 // conv1 of all siblings (*took_tc = 1 when the tensor-core kernel ran), then Net::forward_trunk(first_conv = *took_tc)
-// prelaid (optional): launch_prelay's copy of `state` - the tensor-core kernel then stages it with cp.async only
 int conv1_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
-                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s, int* took_tc,
-                        const void* prelaid = nullptr);
-bool prelay_enabled();
-void set_prelay(int on);              // -1: CARTPOLEPP_PRELAY environment default (on)
+                        int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s, int* took_tc);
 bool conv1_tc_enabled();
 void set_conv1_tc_enabled(int on);     // -1: back to the CARTPOLEPP_CONV1 environment default
 // conv1 weight/bias gradients of n sibling networks whose backward passes were run with defer_conv1 (tensor cores,
@@ -88,8 +84,7 @@ int64_t conv1_wgrad_group_scratch_bytes(int n, const Net& net);
 // gmax_from_dgrad: the backward passes ran conv2's input gradient on the tensor cores (tc_scratch given), which left
 // max|d(pooled1)| of every network in its workspace - no separate max pass is needed
 int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* const* grads, const void* state, int is_f16,
-                      const float* mean_inv, int B, void* scratch, cudaStream_t s, int gmax_from_dgrad = 0,
-                      const void* prelaid = nullptr);
+                      const float* mean_inv, int B, void* scratch, cudaStream_t s, int gmax_from_dgrad = 0);
 
 // mlp.cu: fused FC stacks (one launch per network and direction instead of one GEMM per layer)
 bool fused_mlp_enabled();

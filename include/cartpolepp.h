@@ -45,8 +45,7 @@ int64_t cpp_launch_count(void);
 /* runtime switches (tests and A/B timing): "conv1_tc" = 1 routes conv1 forward / weight gradient of fp16 states through the
  * tensor-core kernels (default, also CARTPOLEPP_CONV1=tc), 0 through the exact-fp32 CUDA-core kernels, -1 = environment default;
  * "streams" = 1 forks the independent chains of a fused DDPG step onto side streams (CARTPOLEPP_STREAMS), "graphs" = 1
- * replays a fused step as one CUDA graph (CARTPOLEPP_GRAPHS); "prelay" = 1 pre-lays the pixel states once per step for
- * the conv1 kernels (CARTPOLEPP_PRELAY); "fused_mlp" = 1 runs every FC stack as one forward and one
+ * replays a fused step as one CUDA graph (CARTPOLEPP_GRAPHS); "fused_mlp" = 1 runs every FC stack as one forward and one
  * input-gradient launch instead of one GEMM per layer (CARTPOLEPP_FUSED_MLP); all default on */
 int cpp_set_option(const char* name, int32_t value);
 
@@ -159,13 +158,6 @@ int cpp_conv_forward_tc(const void* x_f16, const int32_t* rows, const float* mea
 int64_t cpp_conv_dgrad_tc_scratch_bytes(int32_t B, int32_t H, int32_t W, int32_t KS);
 int cpp_conv_dgrad_tc(const float* d_pooled, const uint8_t* amax, const float* w, int32_t B, int32_t H, int32_t W, int32_t KS,
                       float* dx, void* scratch, void* stream);
-/* pre-layout of a batch of fp16 NHWC states for the conv1 tensor-core kernels (x_is_pieces = 3 of cpp_conv_forward_tc /
- * cpp_conv_wgrad_mma): out fp16 [B][H][W][nvec][8], nvec = cpp_prelay_elems / (B*H*W*8); channels are cut into aligned
- * 16-byte vectors, the constant-one channel of the weight-gradient fold and the zero padding of the packed remainder
- * vectors are resolved once here instead of in every CTA of both kernels.  The weight gradient is bit-identical to
- * x_is_pieces = 0, the forward pass agrees to fp32 rounding (its K slabs are cut differently). */
-int64_t cpp_prelay_elems(int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS);
-int cpp_prelay(const void* x_f16, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS, void* out, void* stream);
 /* weight and bias gradients of the same layer for `nets` (<= 3) sibling networks in ONE pass over x on the tensor cores
  * (mma.sync m16n8k16, fp16 x fp16 -> fp32): tf.gradients of the conv1 variables in ddpg_cartpole.py:111,213 /
  * naf_cartpole.py:233.  x fp16 NHWC (exact replay pixels); d_pooled/amax/dw/db: HOST arrays of `nets` device pointers;

@@ -27,7 +27,7 @@ def make_input(rs, B, H, W, Cin, sparse):
   return (k.astype(np.float16) / np.float16(255))
 
 
-def run_tc(B, H, W, Cin, KS, nets, seed, sparse=False, gather=False, prelaid=False):
+def run_tc(B, H, W, Cin, KS, nets, seed, sparse=False, gather=False):
   L, lib = _lib()
   rs = np.random.RandomState(seed)
   dev = "cuda"
@@ -63,13 +63,8 @@ def run_tc(B, H, W, Cin, KS, nets, seed, sparse=False, gather=False, prelaid=Fal
   assert nb > 0
   scr = torch.zeros(nb, dtype=torch.uint8, device=dev)
   src = slab if gather else x
-  mode = 0
-  if prelaid:      # the state re-laid once (cpp_prelay): aligned vectors, constant-one channel, resolved padding
-    xp = torch.zeros(int(lib.cpp_prelay_elems(B, H, W, Cin, KS)), dtype=torch.float16, device=dev)
-    L.check(lib.cpp_prelay(L.ptr(x), B, H, W, Cin, KS, L.ptr(xp), L.stream_ptr()))
-    src, mode = xp, 3
   L.check(lib.cpp_conv_forward_tc(L.ptr(src), L.ptr(rows), L.ptr(mi), nets, L.ptr_array(ws), L.ptr_array(bs), B, H, W, Cin, KS,
-                                  L.ptr_array(pooled), L.ptr_array(amax), L.ptr(scr), L.stream_ptr(), mode, None))
+                                  L.ptr_array(pooled), L.ptr_array(amax), L.ptr(scr), L.stream_ptr(), 0, None))
   torch.cuda.synchronize()
   errs = []
   for n in range(nets):
@@ -213,10 +208,3 @@ def run_dgrad_tc(B, H, W, KS, seed):
                                       (256, 16, 16, 3), (1, 4, 4, 3)])
 def test_conv_dgrad_tc(B, H, W, KS):
   print("dgrad_tc B%d %dx%d k%d: rel err vs fp64 %.2e" % (B, H, W, KS, run_dgrad_tc(B, H, W, KS, seed=B + H + KS)))
-
-
-@pytest.mark.parametrize("B,H,W,Cin,KS,nets", [(8, 64, 64, 9, 5, 2), (4, 64, 64, 18, 5, 3), (2, 128, 128, 24, 5, 2), (2, 50, 50, 6, 5, 2),
-                                               (3, 33, 31, 9, 5, 2), (2, 22, 18, 15, 5, 1), (256, 64, 64, 9, 5, 2)])
-def test_conv_tc_forward_prelaid(B, H, W, Cin, KS, nets):
-  errs = run_tc(B, H, W, Cin, KS, nets, seed=B * 1000 + H + Cin, prelaid=True)
-  print("tc conv fwd (pre-laid state) B%d %dx%dx%d nets%d: rel err vs fp64" % (B, H, W, Cin, nets), ["%.2e" % e for e in errs])

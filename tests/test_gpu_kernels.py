@@ -209,16 +209,6 @@ def run_wgrad_mma(B, H, W, Cin, KS, nets, seed, sparse=False, pieces=False):
     L.check(lib.cpp_conv_wgrad(L.ptr(xx), 0 if pieces else 1, L.ptr(mi), L.ptr(gps[n]), L.ptr(amaxs[n]), B, H, W, Cin, KS,
                                L.ptr(dw2), L.ptr(db2), L.ptr(scr2), L.stream_ptr()))
     U.assert_close(dws[n].cpu().numpy(), dw2.cpu().numpy(), what="wgrad_mma vs fp32 kernel")
-  if not pieces:
-    # the same kernel fed from the pre-laid copy of the state (cp.async staging only): identical bits
-    xp = torch.zeros(int(lib.cpp_prelay_elems(B, H, W, Cin, KS)), dtype=torch.float16, device=dev)
-    L.check(lib.cpp_prelay(L.ptr(x), B, H, W, Cin, KS, L.ptr(xp), L.stream_ptr()))
-    dws3 = [torch.zeros_like(d) for d in dws]; dbs3 = [torch.zeros_like(d) for d in dbs]
-    L.check(lib.cpp_conv_wgrad_mma(L.ptr(xp), L.ptr(mi), 3, nets, L.ptr_array(gps), L.ptr_array(amaxs), B, H, W, Cin, KS,
-                                   L.ptr_array(dws3), L.ptr_array(dbs3), L.ptr(scr), L.stream_ptr()))
-    torch.cuda.synchronize()
-    for n in range(nets):
-      assert torch.equal(dws3[n], dws[n]) and torch.equal(dbs3[n], dbs[n]), "pre-laid wgrad differs from the raw-state path"
   return errs
 
 
