@@ -161,7 +161,31 @@ class ReplayMemory(object):
     return s2_idx
 
   def reset_from_event_log(self, log_file):
-    raise NotImplementedError("event-log prefill is SURVEY.md 8f row 3 (out of scope this round)")
+    """replay_memory.py:40-61: prefill from a recorded event log until the memory is full"""
+    import sys
+    import time
+    from . import event_log
+    elr = event_log.EventLogReader(log_file)
+    num_episodes = num_events = 0
+    start = time.time()
+    for episode in elr.entries():
+      initial_state = None
+      action_reward_state_sequence = []
+      for event_id, event in enumerate(episode.event):
+        if event_id == 0:
+          assert len(event.action) == 0
+          assert not event.HasField("reward")
+          initial_state = event_log.read_state_from_event(event)
+        else:
+          action_reward_state_sequence.append((np.asarray(event.action, dtype=np.float32), event.reward,
+                                               event_log.read_state_from_event(event)))
+        num_events += 1
+      num_episodes += 1
+      self.add_episode(initial_state, action_reward_state_sequence)
+      if self.full:
+        break
+    sys.stderr.write("reset_from_event_log \"%s\" num_episodes=%d num_events=%d took %s sec\n"
+                     % (log_file, num_episodes, num_events, time.time() - start))
 
   # ---- sample path --------------------------------------------------------------------------------
   def size(self):
