@@ -56,7 +56,7 @@ void DDPG::carve(void* ws, bool assign) {
   float* q_ = cv.take<float>(B); float* q2_ = cv.take<float>(B); float* td_ = cv.take<float>(B); float* dq_ = cv.take<float>(B);
   float* ones_ = cv.take<float>(B);
   float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
-  double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(norm_scratch_doubles());
+  double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(2 * norm_scratch_doubles());
   double* msc2 = cv.take<double>(moments_scratch_doubles(C));
   float* sc = cv.take<float>(4);
   ws_bytes = cv.off;
@@ -305,7 +305,7 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
     CPP_TRY(conv1_wgrad_group(2, g2, wss, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
   }
   tr.mark("s0 conv1 wgrad {actor,critic} done", s0);
-  if (with_apply) { CPP_TRY(actor_apply(s0)); CPP_TRY(critic_apply(s0)); }
+  if (with_apply) CPP_TRY(apply_both(s0));
   tr.mark("s0 apply done", s0);
   tr.dump();
   return CPP_OK;
@@ -328,6 +328,13 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
 int DDPG::step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
                         int is_f16, int B, int B_global, cudaStream_t s) {
   return step(s1, action, reward, mask, s2, is_f16, B, B_global, false, s);
+}
+
+int DDPG::apply_both(cudaStream_t s) {
+  CPP_NEED_BOUND();
+  critic_trunk_valid = false;
+  return launch_clip_sgd_dual(buf.params, buf.grads, pad4(n_a), cfg.actor_lr, buf.params + off_c, buf.grads + off_c, pad4(n_c),
+                              cfg.critic_lr, cfg.gradient_clip, norm_scratch, scale2, s);
 }
 
 int DDPG::critic_apply(cudaStream_t s) {

@@ -90,6 +90,7 @@ struct DDPG {
   int critic_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
                       int B, int B_global, int reuse, cudaStream_t s);
   int critic_apply(cudaStream_t s);
+  int apply_both(cudaStream_t s);     // actor_apply; critic_apply in three launches
   // one whole grad-step (ddpg_cartpole.py:332-334) as backward-of-both then apply-of-both: the critic gradient does not
   // depend on the actor update, so actor.train(s1); critic.train(batch) can share every pass over state_1
   int step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,

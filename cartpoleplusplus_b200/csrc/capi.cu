@@ -328,8 +328,7 @@ int cpp_ddpg_train_step(cpp_ddpg* a, const void* s1, const float* action, const 
 int cpp_ddpg_step_apply(cpp_ddpg* a, void* stream) {
   API_BEGIN
   NEED(a);
-  CPP_TRY(a->a.actor_apply(ST(stream)));
-  return a->a.critic_apply(ST(stream));
+  return a->a.apply_both(ST(stream));
   API_END
 }
 int cpp_ddpg_check_loss(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask, const void* s2,

@@ -789,11 +789,12 @@ int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const fl
   return KS == 5 ? launch_main<5, 0>(P, grid, s) : launch_main<3, 0>(P, grid, s);
 }
 
-// one thread per 2x2 window (and per odd-edge pixel): 4 pixels x [hi(10) | lo(10)]
+// one thread per (pixel, 16-byte vector of the 24-channel piece layout): coalesced stores; the window's gradient and
+// arg-max bytes are re-read by its 4 pixels x 3 vectors from L1
 __global__ void __launch_bounds__(256) unpool_split_kernel(const float* __restrict__ g, const uint8_t* __restrict__ amax, int B, int H, int W,
                                                            const float* __restrict__ gmax, float* __restrict__ inv_scale,
-                                                           __half* __restrict__ out) {
-  const int PH = H / 2, PW = W / 2, PHc = (H + 1) / 2, PWc = (W + 1) / 2;
+                                                           uint4* __restrict__ out) {
+  const int PH = H / 2, PW = W / 2;
   float scale = 1.f;
   {
     const float mx = gmax[0];
@@ -801,35 +802,28 @@ __global__ void __launch_bounds__(256) unpool_split_kernel(const float* __restri
   }
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) inv_scale[0] = 1.f / scale;
-  if (i >= (int64_t)B * PHc * PWc) return;
-  const int px = (int)(i % PWc), py = (int)((i / PWc) % PHc), b = (int)(i / ((int64_t)PWc * PHc));
-  float gv[CO]; int a[CO];
-  const bool inside = py < PH && px < PW;
-#pragma unroll
-  for (int o = 0; o < CO; ++o) { gv[o] = 0.f; a[o] = 4; }
-  if (inside) {
+  if (i >= (int64_t)B * H * W * 3) return;
+  const int v = (int)(i % 3);
+  const int64_t pix = i / 3;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
+  const int py = y >> 1, px = x >> 1, pa = ((y & 1) << 1) | (x & 1);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (py < PH && px < PW) {
     const size_t idx = (((size_t)b * PH + py) * PW + px) * CO;
+    auto piece = [&](int o, bool lo) -> uint32_t {
+      const float val = amax[idx + o] == pa ? g[idx + o] * scale : 0.f;
+      const __half h = __float2half_rn(val);
+      return (uint32_t)__half_as_ushort(lo ? __float2half_rn(val - __half2float(h)) : h);
+    };
+    if (v < 2) {
 #pragma unroll
-    for (int o = 0; o < CO; ++o) { gv[o] = g[idx + o] * scale; a[o] = amax[idx + o]; }
-  }
-#pragma unroll
-  for (int pa = 0; pa < 4; ++pa) {
-    const int y = 2 * py + (pa >> 1), x = 2 * px + (pa & 1);
-    if (y >= H || x >= W) continue;
-    uint32_t hi[CO / 2], lo[CO / 2];
-#pragma unroll
-    for (int o = 0; o < CO; o += 2) {
-      const float v0 = a[o] == pa ? gv[o] : 0.f, v1 = a[o + 1] == pa ? gv[o + 1] : 0.f;
-      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-      const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
-      hi[o >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      lo[o >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      for (int k = 0; k < 4; ++k) w[k] = piece(2 * k, v == 1) | (piece(2 * k + 1, v == 1) << 16);
+    } else {
+      w[0] = piece(8, false) | (piece(9, false) << 16);
+      w[1] = piece(8, true) | (piece(9, true) << 16);
     }
-    uint4* d = reinterpret_cast<uint4*>(out + (((size_t)b * H + y) * W + x) * kC24);      // 24-channel piece layout, constant channel 0
-    d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    d[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    d[2] = make_uint4(hi[4], lo[4], 0u, 0u);
   }
+  out[i] = make_uint4(w[0], w[1], w[2], w[3]);                          // constant channel and padding stay 0 in a gradient
 }
 
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
@@ -847,17 +841,20 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ g
 }
 
 int launch_unpool_split(const float* d_pooled, const uint8_t* amax, int B, int H, int W, float* gmax, float* inv_scale,
-                        __half* dy_pieces, cudaStream_t s) {
+                        __half* dy_pieces, cudaStream_t s, int gmax_ready) {
   if (B <= 0) return CPP_OK;
   const int64_t n = (int64_t)B * (H / 2) * (W / 2) * CO;
-  CPP_CHECK_CUDA(cudaMemsetAsync(gmax, 0, sizeof(float), s));
-  if (n > 0) {
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, ceil_div(n, 256 * 8)));
-    absmax_kernel<<<blocks, 256, 0, s>>>(d_pooled, n, gmax);
-    CPP_CHECK_LAUNCH();
+  if (!gmax_ready) {
+    CPP_CHECK_CUDA(cudaMemsetAsync(gmax, 0, sizeof(float), s));
+    if (n > 0) {
+      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, ceil_div(n, 256 * 8)));
+      absmax_kernel<<<blocks, 256, 0, s>>>(d_pooled, n, gmax);
+      CPP_CHECK_LAUNCH();
+    }
   }
-  const int64_t items = (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2);
-  unpool_split_kernel<<<(unsigned)ceil_div(items, 256), 256, 0, s>>>(d_pooled, amax, B, H, W, gmax, inv_scale, dy_pieces);
+  const int64_t items = (int64_t)B * H * W * 3;
+  unpool_split_kernel<<<(unsigned)ceil_div(items, 256), 256, 0, s>>>(d_pooled, amax, B, H, W, gmax, inv_scale,
+                                                                    reinterpret_cast<uint4*>(dy_pieces));
   CPP_CHECK_LAUNCH();
   return CPP_OK;
 }

@@ -79,8 +79,9 @@ int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const fl
                          void* scratch, cudaStream_t s, float* out_absmax = nullptr);
 // un-pool + split: d_pooled fp32 [B][H/2][W/2][10] and the arg-max side band -> dy_pieces fp16 [B][H][W][24], scaled by
 // a power of two from max|d_pooled| (gmax: device float, zeroed and filled here); inv_scale receives 1/scale
+// gmax_ready: *gmax already holds max|d_pooled| (left there by the kernel that produced d_pooled)
 int launch_unpool_split(const float* d_pooled, const uint8_t* amax, int B, int H, int W, float* gmax, float* inv_scale,
-                        __half* dy_pieces, cudaStream_t s);
+                        __half* dy_pieces, cudaStream_t s, int gmax_ready = 0);
 
 }  // namespace tc
 }  // namespace cpp

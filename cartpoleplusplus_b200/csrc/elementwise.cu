@@ -486,6 +486,64 @@ int launch_global_norm_scale(const float* grads, int64_t n, float clip, double* 
   return CPP_OK;
 }
 
+// DDPG applies two independent (clip, SGD) pairs - actor and critic (ddpg_cartpole.py:116-119,213-218) - back to back:
+// the same three kernels handle both segments in one launch each (blockIdx.y = segment), same arithmetic and order
+struct DualSeg { const float* g[2]; float* p[2]; int64_t n[2]; float lr[2]; };
+__global__ void __launch_bounds__(256) sumsq_partial_dual_kernel(DualSeg d, double* __restrict__ partial /*[2][kNormBlocks]*/) {
+  __shared__ double sh[32];
+  const int seg = blockIdx.y;
+  const float* g = d.g[seg];
+  const int64_t n = d.n[seg], n4 = n / 4;
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  if (blockIdx.x == 0) for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) s += (double)g[i] * g[i];
+  const double tot = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[seg * kNormBlocks + blockIdx.x] = tot;
+}
+__global__ void norm_finalize_dual_kernel(const double* __restrict__ partial, int nparts, float clip, float* __restrict__ out4) {
+  const int seg = threadIdx.x;
+  if (seg >= 2) return;
+  double s = 0.0;
+  for (int i = 0; i < nparts; ++i) s += partial[seg * kNormBlocks + i];
+  const float norm = (float)sqrt(s);
+  float scale = 1.f;
+  if (clip > 0.f) scale = clip * fminf(1.f / norm, 1.f / clip);
+  out4[2 * seg] = scale; out4[2 * seg + 1] = norm;
+}
+__global__ void __launch_bounds__(256) sgd_dual_kernel(DualSeg d, const float* __restrict__ scale4) {
+  const int seg = blockIdx.y;
+  const int64_t n = d.n[seg], n4 = n / 4;
+  const float scale = scale4[2 * seg], lr = d.lr[seg];
+  float* p = d.p[seg]; const float* g = d.g[seg];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    pv.x -= lr * (gv.x * scale); pv.y -= lr * (gv.y * scale); pv.z -= lr * (gv.z * scale); pv.w -= lr * (gv.w * scale);
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+  if (i == 0) for (int64_t e = n4 * 4; e < n; ++e) p[e] -= lr * (g[e] * scale);
+}
+int launch_clip_sgd_dual(float* p0, const float* g0, int64_t n0, float lr0, float* p1, const float* g1, int64_t n1, float lr1,
+                         float clip, double* scratch /*[2 * norm_scratch_doubles()]*/, float* out4, cudaStream_t s) {
+  DualSeg d;
+  d.g[0] = g0; d.g[1] = g1; d.p[0] = p0; d.p[1] = p1; d.n[0] = n0; d.n[1] = n1; d.lr[0] = lr0; d.lr[1] = lr1;
+  const int64_t nmax = n0 > n1 ? n0 : n1;
+  int blocks = (int)ceil_div(ceil_div(nmax, 4), 256);
+  if (blocks > kNormBlocks) blocks = kNormBlocks;
+  if (blocks < 1) blocks = 1;
+  sumsq_partial_dual_kernel<<<dim3(blocks, 2), 256, 0, s>>>(d, scratch);
+  CPP_CHECK_LAUNCH();
+  norm_finalize_dual_kernel<<<1, 32, 0, s>>>(scratch, blocks, clip, out4);
+  CPP_CHECK_LAUNCH();
+  sgd_dual_kernel<<<dim3((unsigned)ceil_div(ceil_div(nmax, 4) + 1, 256), 2), 256, 0, s>>>(d, out4);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
 // ---------------------------------------------------------------------------- a12: optimisers
 // kind 0: p -= lr*g ; 1: acc = m*acc + g, p -= lr*acc ; 2: Adam with epsilon-hat (SURVEY A-9)
 template <int KIND>

@@ -348,7 +348,9 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     const bool tc_dg = i > 0 && tc_scratch != nullptr && tc_route(is_f16);
     float* gsc = reinterpret_cast<float*>(ws + L.gsc) + 2 * i;
     if (tc_dg) {
-      CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, reinterpret_cast<__half*>(ws + L.dyp), s));
+      // i == 1: conv3's input-gradient kernel has already left max|gp| in gsc[0] (its epilogue), no separate max pass
+      CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, reinterpret_cast<__half*>(ws + L.dyp), s,
+                                      i == 1 ? 1 : 0));
       trace_mark(i == 2 ? "   . conv3 un-pool/split" : "   . conv2 un-pool/split", s);
     }
     CPP_TRY(ready());                                      // gp (and its max) are complete on the main stream
@@ -373,7 +375,8 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
       if (tc_dg) {
         CPP_TRY(tc::launch_conv_dgrad_tc(reinterpret_cast<__half*>(ws + L.dyp), gsc + 1, params + off_conv_w[i], B, conv[i].H, conv[i].W,
                                          conv[i].KS, dx, tc_scratch, s,
-                                         i == 1 ? reinterpret_cast<float*>(ws + L.gsc) + 6 : nullptr));   // max|d(pooled1)| for conv1's wgrad
+                                         // max|dx| for the next consumer: conv1's wgrad (i == 1), conv2's un-pool/split (i == 2)
+                                         reinterpret_cast<float*>(ws + L.gsc) + (i == 1 ? 6 : 2)));
       } else {
         CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));
       }

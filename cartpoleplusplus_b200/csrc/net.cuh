@@ -110,6 +110,8 @@ int launch_global_norm_scale(const float* grads, int64_t n, float clip, double* 
 int launch_optimiser(int kind, float* params, const float* grads, const float* scale, int64_t n, float lr, float momentum,
                      float beta1, float beta2, float eps, float* slots, float* opt_state, const float* skip, cudaStream_t s);
 int launch_soft_update(float* target, const float* source, float coeff, int64_t n, cudaStream_t s);
+int launch_clip_sgd_dual(float* p0, const float* g0, int64_t n0, float lr0, float* p1, const float* g1, int64_t n1, float lr1,
+                         float clip, double* scratch, float* out4, cudaStream_t s);
 int launch_gather(const void* slab, const int32_t* s1_idx, const int32_t* s2_idx, const float* action, const float* reward,
                   const float* mask, const int64_t* idxs, int B, int64_t row_elems, int A, void* o1, void* o2, float* oa,
                   float* orw, float* om, cudaStream_t s);
