@@ -218,7 +218,7 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   auto wait = [&](cudaStream_t st, int e) -> int { if (multi) CPP_CHECK_CUDA(cudaStreamWaitEvent(st, ev[e], 0)); return CPP_OK; };
   struct CapGuard { ~CapGuard() { g_cta_cap = kNumSMs; } } cap_guard;
   struct Tr { bool on; void mark(const char* l, cudaStream_t st) { if (on) trace_mark(l, st); } void dump() { if (on) trace_dump(); } } tr;
-  tr.on = trace_enabled() && !use_graphs();
+  tr.on = trace_enabled() && (!use_graphs() || trace_level() >= 2);
   if (tr.on) trace_begin();
   tr.mark("start", s0);
   const float* P = buf.params; const float* T = buf.target_params;
@@ -320,9 +320,11 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
   const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1)};
-  return run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
+  const int rc = run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
     return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, st);
   });
+  if (rc == CPP_OK && trace_level() >= 2) trace_dump_graph();
+  return rc;
 }
 
 int DDPG::step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2,

@@ -24,30 +24,45 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 static bool g_trace_active = false;
-static std::vector<std::pair<std::string, cudaEvent_t>> g_trace_pts;
-bool trace_enabled() { static const bool t = [] { const char* e = getenv("CARTPOLEPP_TRACE"); return e && e[0] == '1'; }(); return t; }
+static std::vector<std::pair<std::string, cudaEvent_t>> g_trace_pts;      // eager step: recreated every step
+static std::vector<std::pair<std::string, cudaEvent_t>> g_graph_pts;      // captured step: event-record nodes inside the graph
+int trace_level() { static const int t = [] { const char* e = getenv("CARTPOLEPP_TRACE"); return e ? atoi(e) : 0; }(); return t; }
+bool trace_enabled() { return trace_level() >= 1; }
 void trace_begin() { g_trace_active = true; }
 void trace_mark(const char* label, cudaStream_t st) {
   if (!g_trace_active) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;
-  cudaEventRecord(e, st);
-  g_trace_pts.emplace_back(label, e);
+  if (cs == cudaStreamCaptureStatusActive) {
+    // inside a capture a plain record is only a dependency edge; the external flag makes it a timed event-record node
+    if (cudaEventRecordWithFlags(e, st, cudaEventRecordExternal) != cudaSuccess) { cudaEventDestroy(e); return; }
+    g_graph_pts.emplace_back(label, e);
+  } else {
+    cudaEventRecord(e, st);
+    g_trace_pts.emplace_back(label, e);
+  }
+}
+static void dump_list(std::vector<std::pair<std::string, cudaEvent_t>>& pts, const char* title) {
+  if (pts.empty()) return;
+  cudaDeviceSynchronize();
+  fprintf(stderr, "---- %s (us)\n", title);
+  for (auto& p : pts) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pts[0].second, p.second) == cudaSuccess) fprintf(stderr, "%9.1f  %s\n", ms * 1e3f, p.first.c_str());
+  }
 }
 void trace_dump() {
   if (!g_trace_active) return;
   g_trace_active = false;
-  if (g_trace_pts.empty()) return;
-  cudaDeviceSynchronize();
-  fprintf(stderr, "---- step timeline (us)\n");
-  for (auto& p : g_trace_pts) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, g_trace_pts[0].second, p.second);
-    fprintf(stderr, "%9.1f  %s\n", ms * 1e3f, p.first.c_str());
+  if (!g_trace_pts.empty()) {
+    dump_list(g_trace_pts, "step timeline");
+    for (auto& p : g_trace_pts) cudaEventDestroy(p.second);
+    g_trace_pts.clear();
   }
-  for (auto& p : g_trace_pts) cudaEventDestroy(p.second);
-  g_trace_pts.clear();
 }
+void trace_dump_graph() { dump_list(g_graph_pts, "step timeline inside the CUDA graph"); }
 }  // namespace cpp
 
 using namespace cpp;

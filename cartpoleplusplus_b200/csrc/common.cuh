@@ -44,6 +44,8 @@ static inline int sm_budget() { return g_cta_cap < 1 ? 1 : (g_cta_cap > 148 ? 14
 // CARTPOLEPP_TRACE=1: eager steps record a timing event at every chain milestone and print the timeline (us since the
 // start of the step) to stderr - the poor man's nsys for the fork/join schedule (capi.cu)
 bool trace_enabled();
+int trace_level();                  // CARTPOLEPP_TRACE: 1 = eager steps, 2 = also the timeline inside the captured graph
+void trace_dump_graph();            // after a graph replay: prints the event-record nodes captured with the step
 void trace_begin();
 void trace_mark(const char* label, cudaStream_t st);     // no-op unless trace_begin() was called
 void trace_dump();

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Prints the fork/join timeline of fused DDPG steps at c3 (eager multi-stream mode, CARTPOLEPP_TRACE=1, graphs off)."""
 import os, sys
-os.environ["CARTPOLEPP_TRACE"] = "1"; os.environ["CARTPOLEPP_GRAPHS"] = "0"
+mode = os.environ.get("TRACE_MODE", "eager")       # eager | graph
+os.environ["CARTPOLEPP_TRACE"] = "2" if mode == "graph" else "1"; os.environ["CARTPOLEPP_GRAPHS"] = "1" if mode == "graph" else "0"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tests import gpu_util as U
