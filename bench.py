@@ -284,7 +284,8 @@ def run_native(args):
 
   if dp.rank == 0:
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=G, steps=args.steps, warmup=W, ms_per_step=ms / args.steps,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32 (conv MMAs: fp16 hi+lo operand pieces, fp32 accumulate; FC / elementwise fp32)", data="synthetic",
                 config=dict(workload=WORKLOAD, global_batch=BATCH * G, replay=N_REPLAY, batches_per_step=BATCHES_PER_STEP,
                             parallelism="dp%d" % G,
                             l2="inputs larger than L2: each step gathers 37.7 MB of random rows from a 453 MB fp16 replay slab"),
