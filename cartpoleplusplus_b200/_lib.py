@@ -39,7 +39,8 @@ class NAFConfig(C.Structure):
               ("discount", C.c_float), ("gradient_clip", C.c_float), ("target_update_rate", C.c_float),
               ("optimiser", C.c_int32),
               ("lr", C.c_float), ("momentum", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-              ("max_batch", C.c_int32), ("action_dim", C.c_int32), ("world_size", C.c_int32), ("rank", C.c_int32)]
+              ("max_batch", C.c_int32), ("action_dim", C.c_int32), ("world_size", C.c_int32), ("rank", C.c_int32),
+              ("share_input_state_representation", C.c_int32)]
 
 
 class NAFBuffers(C.Structure):

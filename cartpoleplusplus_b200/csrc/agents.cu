@@ -382,7 +382,15 @@ int NAF::init(const cpp_naf_config& c) {
   A = c.action_dim;
   CPP_REQUIRE(A >= 1 && A <= 8, "action_dim=%d unsupported", A);
   CPP_REQUIRE(value.out_width() == 1 && mu.out_width() == A && l.out_width() == A * (A + 1) / 2, "NAF head widths do not match action_dim");
-  CPP_REQUIRE(value.pixels == mu.pixels && mu.pixels == l.pixels, "NAF nets read the same state");
+  share = c.share_input_state_representation != 0;
+  rep_dim = value.in_dim[value.n_fc - 1];
+  if (share) {
+    CPP_REQUIRE(!mu.pixels && !l.pixels && mu.n_fc == 1 && l.n_fc == 1 && mu.feat == rep_dim && l.feat == rep_dim,
+                "shared input state representation: mu / l must be single layers on the %d-wide representation", rep_dim);
+    CPP_REQUIRE(value.n_fc == 1 || value.out_ld[value.n_fc - 2] == rep_dim, "representation must be contiguous");
+  } else {
+    CPP_REQUIRE(value.pixels == mu.pixels && mu.pixels == l.pixels, "NAF nets read the same state");
+  }
   CPP_REQUIRE(c.optimiser >= 0 && c.optimiser <= 2, "optimiser kind %d", c.optimiser);
   n_v = value.nparams; n_m = mu.nparams; n_l = l.nparams;
   off_m = pad4(n_v); off_l = off_m + pad4(n_m); off_loss = off_l + pad4(n_l); total = off_loss + 4;
@@ -408,8 +416,10 @@ void NAF::carve(void* ws, bool assign) {
   float* mi1_ = cv.take<float>(2 * C); float* mi2_ = cv.take<float>(2 * C);
   double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(norm_scratch_doubles());
   float* sc = cv.take<float>(4);
+  float* drep = cv.take<float>((size_t)B * rep_dim);
   ws_bytes = cv.off;
   if (assign) {
+    d_rep = drep;
     ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; V = V_;
     tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts4; tcs[3] = ts2; this->wgs[0] = wgs; this->wgs[1] = wgs1; this->wgs[2] = wgs2; mom_scratch2 = msc2; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
     mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
@@ -459,6 +469,7 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
   struct CapGuard { ~CapGuard() { g_cta_cap = kNumSMs; } } cap_guard;
   const float* P = buf.params;
   const float *m1 = nullptr, *m2 = nullptr;
+  const int NL = A * (A + 1) / 2;
   CPP_TRY(record(E_START, s0));
   CPP_TRY(wait(st, E_START));
   // ---- target value network on state_2 (its own stream, a quarter of the GPU)
@@ -478,6 +489,29 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
   if (multi) g_cta_cap = kNumSMs - kNumSMs / 4;
   CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s0));
   cur_m1 = m1;
+  if (share) {
+    // one trunk: value network, then V / mu / l as three heads on its representation          naf_cartpole.py:151-154,176-179
+    const Net* g1[1] = {&value}; const float* pp1[1] = {P}; char* ws1[1] = {ws_v};
+    int tc1 = 0;
+    CPP_TRY(conv1_forward_group(1, g1, pp1, ws1, s1, is_f16, m1, B, tcs[0], s0, &tc1));
+    CPP_TRY(value.forward_trunk(P, s1, is_f16, m1, B, ws_v, s0, tc1, tc1 ? tcs[0] : nullptr));
+    CPP_TRY(value.forward_fc(P, nullptr, B, ws_v, V, s0));
+    CPP_TRY(heads_forward(P, ws_v, B, muo, lv, s0));
+    CPP_TRY(wait(s0, E_V2));
+    CPP_TRY(launch_naf_head(V, muo, lv, action, reward, mask, V2, cfg.discount, B, A, B_global, dV, dmu, dl, nullptr,
+                            buf.grads + off_loss, s0));
+    const float* rep = shared_rep(ws_v, B);
+    CPP_TRY(mu.backward(P + off_m, rep, 0, nullptr, B, ws_m, dmu, buf.grads + off_m, nullptr, s0));
+    CPP_TRY(l.backward(P + off_l, rep, 0, nullptr, B, ws_l, dl, buf.grads + off_l, nullptr, s0));
+    CPP_TRY(launch_heads_dgrad(reinterpret_cast<const float*>(ws_m + mu.layout(B).dTop), P + off_m + mu.off_fc_w[0], A,
+                               reinterpret_cast<const float*>(ws_l + l.layout(B).dTop), P + off_l + l.off_fc_w[0], NL, B, rep_dim,
+                               d_rep, s0));
+    CPP_TRY(value.backward(P, s1, is_f16, m1, B, ws_v, dV, buf.grads, nullptr, s0, 1, wgs[0], tcs[0], nullptr, d_rep));
+    g_cta_cap = kNumSMs;
+    float* gr[1] = {buf.grads};
+    CPP_TRY(conv1_wgrad_group(1, g1, ws1, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
+    return CPP_OK;
+  }
   const Net* g3[3] = {&value, &mu, &l};
   const float* pp3[3] = {P, P + off_m, P + off_l};
   char* ws3[3] = {ws_v, ws_m, ws_l};
@@ -532,15 +566,22 @@ int NAF::forward_all(const void* s1, const float* action, const float* reward, c
   CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s));
   CPP_TRY(stats_for(s2, is_f16, B, mi2, pinned2, &m2, s));
   cur_m1 = m1;
-  {  // value / mu / l trunks read the same whitened state_1 (naf_cartpole.py:104,150,175)
-    const Net* g[3] = {&value, &mu, &l};
-    const float* pp[3] = {buf.params, buf.params + off_m, buf.params + off_l};
-    char* wss[3] = {ws_v, ws_m, ws_l};
-    CPP_TRY(trunk_forward_group(3, g, pp, wss, s1, is_f16, m1, B, tc_scr1, s));
+  if (share) {
+    const Net* g[1] = {&value}; const float* pp[1] = {buf.params}; char* wss[1] = {ws_v};
+    CPP_TRY(trunk_forward_group(1, g, pp, wss, s1, is_f16, m1, B, tc_scr1, s));
+    CPP_TRY(value.forward_fc(buf.params, nullptr, B, ws_v, V, s));
+    CPP_TRY(heads_forward(buf.params, ws_v, B, muo, lv, s));
+  } else {
+    {  // value / mu / l trunks read the same whitened state_1 (naf_cartpole.py:104,150,175)
+      const Net* g[3] = {&value, &mu, &l};
+      const float* pp[3] = {buf.params, buf.params + off_m, buf.params + off_l};
+      char* wss[3] = {ws_v, ws_m, ws_l};
+      CPP_TRY(trunk_forward_group(3, g, pp, wss, s1, is_f16, m1, B, tc_scr1, s));
+    }
+    CPP_TRY(value.forward_fc(buf.params, nullptr, B, ws_v, V, s));
+    CPP_TRY(mu.forward_fc(buf.params + off_m, nullptr, B, ws_m, muo, s));
+    CPP_TRY(l.forward_fc(buf.params + off_l, nullptr, B, ws_l, lv, s));
   }
-  CPP_TRY(value.forward_fc(buf.params, nullptr, B, ws_v, V, s));
-  CPP_TRY(mu.forward_fc(buf.params + off_m, nullptr, B, ws_m, muo, s));
-  CPP_TRY(l.forward_fc(buf.params + off_l, nullptr, B, ws_l, lv, s));
   {  // target_value_net on state_2, naf_cartpole.py:225-227
     const Net* g[1] = {&value};
     const float* pp[1] = {buf.target_params};
@@ -601,6 +642,12 @@ int NAF::action_given(const void* state, int is_f16, int B, float* out, cudaStre
   CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
   const float* m;
   CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));
+  if (share) {    // value trunk and hidden layers, then the mu head
+    const Net* g[1] = {&value}; const float* pp[1] = {buf.params}; char* wss[1] = {ws_t};
+    CPP_TRY(trunk_forward_group(1, g, pp, wss, state, is_f16, m, B, tc_scr2, s));
+    if (value.n_fc > 1) CPP_TRY(value.forward_fc(buf.params, nullptr, B, ws_t, nullptr, s, 0, value.n_fc - 1));
+    return mu.forward(buf.params + off_m, shared_rep(ws_t, B), 0, nullptr, nullptr, B, ws_m, out, s);
+  }
   const Net* g[1] = {&mu};
   const float* pp[1] = {buf.params + off_m};
   char* wss[1] = {ws_t};
@@ -617,6 +664,17 @@ int NAF::value_given(const void* state, int is_f16, int B, float* out, cudaStrea
   char* wss[1] = {ws_t};
   CPP_TRY(trunk_forward_group(1, g, pp, wss, state, is_f16, m, B, tc_scr2, s));
   return value.forward_fc(buf.params, nullptr, B, ws_t, out, s);
+}
+
+const float* NAF::shared_rep(char* wsv, int B) const {
+  int ld;
+  return value.fc_input(value.layout(B), wsv, value.n_fc - 1, &ld);
+}
+
+int NAF::heads_forward(const float* P, char* wsv, int B, float* mu_out, float* l_out, cudaStream_t s) {
+  const float* rep = shared_rep(wsv, B);
+  CPP_TRY(mu.forward(P + off_m, rep, 0, nullptr, nullptr, B, ws_m, mu_out, s));
+  return l.forward(P + off_l, rep, 0, nullptr, nullptr, B, ws_l, l_out, s);
 }
 
 int NAF::update_targets(float coeff, cudaStream_t s) {

@@ -123,6 +123,9 @@ struct NAF {
   cpp_naf_config cfg;
   Net value, mu, l;
   int A = 2;
+  bool share = false;                 // --share-input-state-representation: mu / l are heads on value's last hidden layer
+  int rep_dim = 0;
+  float* d_rep = nullptr;             // [B][rep_dim] gradient the two heads send into the shared representation
   int64_t n_v = 0, n_m = 0, n_l = 0, off_m = 0, off_l = 0, off_loss = 0, total = 0;
   cpp_naf_buffers buf{};
   bool bound = false;
@@ -148,6 +151,9 @@ struct NAF {
   int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
   int value_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
   int update_targets(float coeff, cudaStream_t s);
+  // share mode: mu and l heads on the representation the value network left in `wsv`
+  const float* shared_rep(char* wsv, int B) const;
+  int heads_forward(const float* P, char* wsv, int B, float* mu_out, float* l_out, cudaStream_t s);
   // fused backward: value / mu / l chains and the target value chain on forked streams, one CUDA graph per argument set
   int backward_body(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
                     int B_global, bool multi, cudaStream_t s);

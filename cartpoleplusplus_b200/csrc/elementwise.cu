@@ -278,6 +278,41 @@ int launch_act_grad(const float* d_out, int d_ld, const float* out, int out_ld, 
   return CPP_OK;
 }
 
+// NAF --share-input-state-representation: input gradients of the single-layer mu and l heads, summed
+//   out[b][j] = sum_k dmu_pre[b][k] * Wmu[j][k] + sum_k dl_pre[b][k] * Wl[j][k]          (W stored [in][out])
+__global__ void heads_dgrad_kernel(const float* __restrict__ dmu, const float* __restrict__ Wmu, int A, const float* __restrict__ dl,
+                                   const float* __restrict__ Wl, int NL, int B, int D, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, j = i - b * D;
+  float s = 0.f;
+  for (int k = 0; k < A; ++k) s = fmaf(dmu[b * A + k], Wmu[j * A + k], s);
+  float t = 0.f;
+  for (int k = 0; k < NL; ++k) t = fmaf(dl[b * NL + k], Wl[j * NL + k], t);
+  out[i] = s + t;
+}
+int launch_heads_dgrad(const float* dmu_pre, const float* Wmu, int A, const float* dl_pre, const float* Wl, int NL, int B, int D,
+                       float* out, cudaStream_t s) {
+  heads_dgrad_kernel<<<(unsigned)ceil_div(B * D, 256), 256, 0, s>>>(dmu_pre, Wmu, A, dl_pre, Wl, NL, B, D, out);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
+// d[b][j] += extra[b][j], gated by the ReLU below (x = that layer's output; NULL: no gate)
+__global__ void add_gated_kernel(float* __restrict__ d, int d_ld, const float* __restrict__ extra, const float* __restrict__ x, int x_ld,
+                                 int B, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n) return;
+  const int b = i / n, j = i - b * n;
+  const bool open = x == nullptr || x[(size_t)b * x_ld + j] > 0.f;
+  if (open) d[(size_t)b * d_ld + j] += extra[i];
+}
+int launch_add_gated(float* d, int d_ld, const float* extra, const float* x, int x_ld, int B, int n, cudaStream_t s) {
+  add_gated_kernel<<<(unsigned)ceil_div(B * n, 256), 256, 0, s>>>(d, d_ld, extra, x, x_ld, B, n);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
 // bias gradient: out[c] = sum_b x[b][c]; one warp per column, fixed order
 __global__ void colsum_kernel(const float* __restrict__ x, int ld, int B, int n, float* __restrict__ out) {
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;

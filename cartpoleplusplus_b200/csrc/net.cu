@@ -252,7 +252,7 @@ int trunk_forward_group(int n, const Net* const* nets, const float* const* param
 
 int Net::backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
                   const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1, void* wg_scratch,
-                  void* tc_scratch, BackwardAux* aux) const {
+                  void* tc_scratch, BackwardAux* aux, const float* d_rep_extra) const {
   CPP_REQUIRE(B >= 1, "batch %d", B);
   CPP_REQUIRE(d_action == nullptr || concat_at >= 0, "d_action requested from a network without action input");
   char* ws = reinterpret_cast<char*>(ws_);
@@ -268,7 +268,8 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     ++ev; aux->used = true;
     return CPP_OK;
   };
-  const bool fused = fused_mlp_level() >= 2 && mlp_fits(*this);
+  CPP_REQUIRE(d_rep_extra == nullptr || (grads != nullptr && concat_at < 0), "d_rep_extra needs a full backward pass of a network without action input");
+  const bool fused = fused_mlp_level() >= 2 && mlp_fits(*this) && d_rep_extra == nullptr;
   const int stop_at_f = (grads == nullptr) ? concat_at : 0;
   if (fused) {
     // one launch for the whole chain of input gradients; every weight / bias gradient afterwards (side stream if given)
@@ -313,7 +314,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
       CPP_TRY(launch_colsum(dcur, dld, B, out_dim[i], grads + off_fc_b[i], sw));
     }
     const bool need_dx = (i > stop_at) || (i == 0 && pixels && grads != nullptr) || (concat_at == i && d_action != nullptr);
-    if (!need_dx) break;
+    if (!need_dx) break;     // (a low-dim network without hidden layers: the representation is the state, nothing to send)
     float* dnext = reinterpret_cast<float*>(ws + L.dX[i]);
     GemmArgs g{};                                          // dX = dPre . W^T, masked by the ReLU of the layer below
     g.A = dcur; g.lda = dld; g.transA = 0;
@@ -323,6 +324,8 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     if (i > 0) { g.epi = EPI_RELU_MASK; g.aux = x; g.aux_ld = xld; g.mask_cols = out_dim[i - 1]; }
     else g.epi = EPI_NONE;
     CPP_TRY(launch_gemm(g, s));
+    if (i == last && d_rep_extra != nullptr)
+      CPP_TRY(launch_add_gated(dnext, in_dim[i], d_rep_extra, i > 0 ? x : nullptr, xld, B, in_dim[i], s));
     if (concat_at == i && d_action != nullptr)
       CPP_TRY(launch_copy_cols(dnext + (in_dim[i] - action_dim), in_dim[i], B, action_dim, d_action, action_dim, 0, s));
     dcur = dnext;

@@ -58,11 +58,14 @@ struct Net {
                  int end_fc = -1) const;
   // grads == nullptr: only d_action is produced (stops at the concat layer).  defer_conv1: stop in front of conv1's
   // weight gradient (its input gradient d(pooled1) stays in ws) so that conv1_wgrad_group can do it for all siblings.
+  // d_rep_extra [B][in_dim[last]]: gradient that other heads sharing the input of the LAST FC layer send into it (NAF's
+  // --share-input-state-representation); added to this network's own before the ReLU gate of the layer below.
   // wg_scratch != NULL on the tensor-core route: conv2/conv3 weight gradients from the fp16 piece copies (conv_wgrad_mma.cu);
   // tc_scratch != NULL: conv3/conv2 input gradients through the tcgen05 kernel in dgrad mode (conv_tc.cu).
   int backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws,
                const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1 = 0,
-               void* wg_scratch = nullptr, void* tc_scratch = nullptr, BackwardAux* aux = nullptr) const;
+               void* wg_scratch = nullptr, void* tc_scratch = nullptr, BackwardAux* aux = nullptr,
+               const float* d_rep_extra = nullptr) const;
 };
 
 // Conv trunks of n (<= 3) sibling networks that read the SAME state (actor+critic on state_1, the two targets on

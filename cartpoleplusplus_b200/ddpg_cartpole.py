@@ -413,11 +413,17 @@ def main(argv=None):
   for net in (agent.actor, agent.critic, agent.target_actor, agent.target_critic):
     for v in net._variables():
       sys.stderr.write("%s %s\n" % (v.name, util.shape_and_product_of(v.shape)))
+  # setup saver util and either load latest ckpt or keep the initialised variables (ddpg_cartpole.py:419-422)
+  saver_util = None
+  if opts.ckpt_dir is not None:
+    saver_util = util.SaverUtil(agent.actor._engine, opts.ckpt_dir, opts.ckpt_freq)
   agent.post_var_init_setup()
   if opts.num_eval > 0:
     agent.run_eval(opts.num_eval, opts.eval_action_noise)
   else:
-    agent.run_training(opts.max_num_actions, opts.max_run_time, opts.batch_size, opts.batches_per_step, None)
+    agent.run_training(opts.max_num_actions, opts.max_run_time, opts.batch_size, opts.batches_per_step, saver_util)
+    if saver_util is not None:
+      saver_util.force_save()
   env.reset()
 
 

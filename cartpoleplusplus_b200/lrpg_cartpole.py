@@ -124,6 +124,8 @@ class LikelihoodRatioPolicyGradientAgent(base_network.Network):
       stats["loss"] = loss
       print("STATS %s\t%s" % (datetime.datetime.now().strftime('%Y-%m-%d %H:%M:%S'), json.dumps(stats)))
       sys.stdout.flush()
+      if saver_util is not None:
+        saver_util.save_if_required()
       n += 1
       if max_num_actions > 0 and num_actions_taken > max_num_actions:
         break
@@ -202,11 +204,16 @@ def main(argv=None):
   sys.stderr.write("%s\n" % opts)
   env = synthetic_env.SyntheticCartpole(opts=opts, discrete_actions=True)
   agent = LikelihoodRatioPolicyGradientAgent(env=env)
+  saver_util = None
+  if opts.ckpt_dir is not None:     # lrpg_cartpole.py:278-281
+    saver_util = util.SaverUtil(agent._engine, opts.ckpt_dir, opts.ckpt_freq)
   agent.post_var_init_setup()
   if opts.num_eval > 0:
     agent.run_eval(opts.num_eval)
   else:
-    agent.run_training(opts.max_num_actions, opts.max_run_time, opts.rollouts_per_batch, None)
+    agent.run_training(opts.max_num_actions, opts.max_run_time, opts.rollouts_per_batch, saver_util)
+    if saver_util is not None:
+      saver_util.force_save()
 
 
 if __name__ == "__main__":

@@ -89,20 +89,40 @@ class _SubNet(base_network.Network):
     return self.initial_values(rng, small_uniform=("fc",) if self._small else ())
 
 
+class _HeadNet(base_network.Network):
+  """--share-input-state-representation (naf_cartpole.py:151-154,176-179): the sub-network is only its `fc` layer, on top of
+  value_net.input_state_representation; the gradient it sends into the representation reaches the value/* variables"""
+
+  def __init__(self, namespace, representation, num_outputs, activation, small):
+    super(_HeadNet, self).__init__(namespace)
+    rep_dim = representation.fc[-1][1] if representation.fc else int(np.prod(representation.feature_shape()))
+    src = base_network.Placeholder((rep_dim,), "input_state_representation")
+    self._finalise(base_network.fully_connected(src, num_outputs, scope='fc', activation=activation))
+    self._small = small
+
+  def initial_flat(self, rng):
+    return self.initial_values(rng, small_uniform=("fc",) if self._small else ())
+
+
 class NafNetwork(base_network.Network):
 
   def __init__(self, namespace, input_state, input_state_2, value_net, target_value_net, action_dim):
     super(NafNetwork, self).__init__(namespace)
-    if opts.share_input_state_representation:
-      raise NotImplementedError("--share-input-state-representation is SURVEY.md 8f row 4 (not built yet)")
     self.exploration_noise = util.OrnsteinUhlenbeckNoise(action_dim, opts.action_noise_theta, opts.action_noise_sigma)
     self.value_net, self.target_value_net = value_net, target_value_net
     self.input_state, self.input_state_2 = input_state, input_state_2
     self.action_dim = action_dim
     # mu (output_action): its own input_state_network + tanh head with U(+-1e-3) weights (:150-161)
-    self.mu_net = _SubNet(namespace + "/output_action", input_state, action_dim, "tanh", True)
-    # l_values: lower-triangular entries, diagonal exponentiated in the head kernel (:172-207)
-    self.l_net = _SubNet(namespace + "/l_values", input_state, (action_dim * (action_dim + 1)) // 2, None, False)
+    num_l_values = (action_dim * (action_dim + 1)) // 2
+    self.share = bool(getattr(opts, "share_input_state_representation", False))
+    if self.share:
+      rep = value_net.input_state_representation
+      self.mu_net = _HeadNet(namespace + "/output_action", rep, action_dim, "tanh", True)
+      self.l_net = _HeadNet(namespace + "/l_values", rep, num_l_values, None, False)
+    else:
+      self.mu_net = _SubNet(namespace + "/output_action", input_state, action_dim, "tanh", True)
+      # l_values: lower-triangular entries, diagonal exponentiated in the head kernel (:172-207)
+      self.l_net = _SubNet(namespace + "/l_values", input_state, num_l_values, None, False)
     self.optimiser = util.construct_optimiser(opts)
     NAFEngine(self, opts)
 
@@ -150,6 +170,7 @@ class NAFEngine(EngineBase):
     cfg.lr, cfg.momentum, cfg.beta1, cfg.beta2, cfg.eps = (self.hp[k] for k in ("lr", "momentum", "beta1", "beta2", "eps"))
     cfg.max_batch, cfg.action_dim = max_batch, self.naf.action_dim
     cfg.world_size, cfg.rank = self.world_size, self.rank
+    cfg.share_input_state_representation = 1 if self.naf.share else 0
     return cfg
 
   def _layout(self):
@@ -300,6 +321,8 @@ class NormalizedAdvantageFunctionAgent(object):
       stats["replay_memory_stats"] = self.replay_memory.current_stats()
       print("STATS %s\t%s" % (datetime.datetime.now().strftime('%Y-%m-%d %H:%M:%S'), json.dumps(stats)))
       sys.stdout.flush()
+      if saver_util is not None:
+        saver_util.save_if_required()
       n += 1
       if VERBOSE_DEBUG or n % 10 == 0:
         self.run_eval(1)
@@ -331,11 +354,17 @@ def main(argv=None):
   sys.stderr.write("%s\n" % opts)
   env = synthetic_env.SyntheticCartpole(opts=opts, discrete_actions=False)
   agent = NormalizedAdvantageFunctionAgent(env=env)
+  # setup saver util and either load latest ckpt or keep the initialised variables (naf_cartpole.py:467-470)
+  saver_util = None
+  if opts.ckpt_dir is not None:
+    saver_util = util.SaverUtil(agent.naf._engine, opts.ckpt_dir, opts.ckpt_freq)
   agent.post_var_init_setup()
   if opts.num_eval > 0:
     agent.run_eval(opts.num_eval, opts.eval_action_noise)
   else:
-    agent.run_training(opts.max_num_actions, opts.max_run_time, opts.batch_size, opts.batches_per_step, None)
+    agent.run_training(opts.max_num_actions, opts.max_run_time, opts.batch_size, opts.batches_per_step, saver_util)
+    if saver_util is not None:
+      saver_util.force_save()
   env.reset()
 
 

@@ -1,9 +1,12 @@
 """Mirror of the reference's util.py for the pieces the hot path and its callers need
 (/root/reference/util.py): flags :10-20, StopWatch :22-26, collapsed_successive_ranges :60-71,
 construct_optimiser :73-76 (returns the optimiser *description* the CUDA step consumes),
-OrnsteinUhlenbeckNoise :134-156 (host side, including the rotated np.clip arguments, Appendix C-6).
-SaverUtil / PNG helpers are out of scope."""
+OrnsteinUhlenbeckNoise :134-156 (host side, including the rotated np.clip arguments, Appendix C-6),
+SaverUtil :88-131 (checkpoint save / restore of the device-resident variables)."""
+import datetime
 import json
+import os
+import sys
 import time
 import numpy as np
 
@@ -52,6 +55,111 @@ def shape_and_product_of(shape):
     if d is not None:
       n *= int(d)
   return "%s #%s" % (tuple(shape), n)
+
+
+class SaverUtil(object):
+  """util.py:88-131.  The reference hands `tf.train.Saver` every variable except the replay memory; here the variables
+  are the engine's flat device buffers: each network's variables go into one `.npz` under their reference names
+  (`actor/conv1/weights` ...), optimiser slots and the Adam power accumulators under `__slots__` / `__opt_state__`.
+  Like the Saver, a text file `checkpoint` in the directory names the latest save (`model_checkpoint_path: "ckpt.<ts>"`);
+  restore copies into the bound buffers in place, so captured CUDA graphs stay valid."""
+
+  def __init__(self, engine, ckpt_dir="/tmp", save_freq=60):
+    self.engine = engine
+    self.ckpt_dir = ckpt_dir
+    if not os.path.exists(self.ckpt_dir):
+      os.makedirs(self.ckpt_dir)
+    assert save_freq > 0
+    self.save_freq = save_freq
+    self.load_latest_ckpt_or_init_if_none()
+
+  def _networks(self):
+    e = self.engine
+    nets = getattr(e, "nets", None)
+    return list(nets.items()) if nets is not None else [("model", e.agent)]
+
+  def _latest(self):
+    ckpt_info_file = "%s/checkpoint" % self.ckpt_dir
+    if not os.path.isfile(ckpt_info_file):
+      return None
+    for line in open(ckpt_info_file, "r"):
+      key, _, value = line.partition(":")
+      if key.strip() == "model_checkpoint_path":
+        return value.strip().strip('"')
+    raise AssertionError("no model_checkpoint_path in %s" % ckpt_info_file)
+
+  def load_latest_ckpt_or_init_if_none(self):
+    """loads latest ckpt from dir; if there is none the (already initialised) variables are saved straight away"""
+    latest = self._latest()
+    if latest is None:
+      sys.stderr.write("no latest ckpt in %s, just initing vars...\n" % self.ckpt_dir)
+      self.force_save()
+      return
+    most_recent_ckpt = "%s/%s" % (self.ckpt_dir, latest)
+    sys.stderr.write("loading ckpt %s\n" % most_recent_ckpt)
+    self.restore(most_recent_ckpt)
+    self.next_scheduled_save_time = time.time() + self.save_freq
+
+  def restore(self, path):
+    import torch
+    e = self.engine
+    with np.load(path if path.endswith(".npz") else path + ".npz") as z:
+      for part, net in self._networks():
+        values = {}
+        for v in net._variables():
+          if v.name not in z.files:
+            raise KeyError("checkpoint %s has no variable %s" % (path, v.name))
+          if tuple(z[v.name].shape) != tuple(v.shape):
+            raise ValueError("checkpoint %s: %s has shape %s, the model wants %s" % (path, v.name, z[v.name].shape, v.shape))
+          values[v.name] = z[v.name]
+        net.set_variables(values)
+      for key, buf in (("__slots__", "slots"), ("__opt_state__", "opt_state")):
+        if buf in e.buffers:
+          if key not in z.files or z[key].size != e.buffers[buf].numel():
+            raise ValueError("checkpoint %s does not hold this optimiser's %s" % (path, buf))
+          e.buffers[buf].copy_(torch.from_numpy(np.ascontiguousarray(z[key], dtype=np.float32)))
+    if e.buffers["params"].is_cuda:
+      torch.cuda.current_stream().synchronize()
+
+  def force_save(self):
+    """force a save now."""
+    dts = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
+    name = "ckpt.%s" % dts
+    n = 1
+    while os.path.exists("%s/%s.npz" % (self.ckpt_dir, name)):      # two saves within one second
+      name = "ckpt.%s_%d" % (dts, n)
+      n += 1
+    new_ckpt = "%s/%s" % (self.ckpt_dir, name)
+    sys.stderr.write("saving ckpt %s\n" % new_ckpt)
+    start_time = time.time()
+    e = self.engine
+    arrays = {}
+    for part, net in self._networks():
+      flat = e.part_view(part).detach().cpu().numpy()
+      for v in net._variables():
+        arrays[v.name] = flat[v.offset:v.offset + v.size].reshape(v.shape)
+    for key, buf in (("__slots__", "slots"), ("__opt_state__", "opt_state")):
+      if buf in e.buffers:
+        arrays[key] = e.buffers[buf].detach().cpu().numpy()
+    tmp = "%s/.%s.tmp.npz" % (self.ckpt_dir, name)
+    np.savez(tmp, **arrays)
+    os.replace(tmp, new_ckpt + ".npz")
+    history = []
+    info = "%s/checkpoint" % self.ckpt_dir
+    if os.path.isfile(info):
+      history = [l for l in open(info) if l.startswith("all_model_checkpoint_paths")]
+    with open(info + ".tmp", "w") as f:
+      f.write('model_checkpoint_path: "%s"\n' % name)
+      f.writelines(history)
+      f.write('all_model_checkpoint_paths: "%s"\n' % name)
+    os.replace(info + ".tmp", info)
+    print("save_took", time.time() - start_time)
+    self.next_scheduled_save_time = time.time() + self.save_freq
+
+  def save_if_required(self):
+    """check if save is required based on time and if so, save."""
+    if time.time() >= self.next_scheduled_save_time:
+      self.force_save()
 
 
 class OrnsteinUhlenbeckNoise(object):

@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define CPP_ABI_VERSION 2
+#define CPP_ABI_VERSION 3
 #define CPP_MAX_FC 8
 
 typedef enum {
@@ -249,6 +249,9 @@ typedef struct {
   float lr, momentum, beta1, beta2, eps;
   int32_t max_batch, action_dim;
   int32_t world_size, rank;
+  /* --share-input-state-representation (naf_cartpole.py:151-154,176-179): `mu` and `l` are then single-layer networks
+   * (pixels = 0, input_dim = width of value's last hidden layer) on top of the value network's representation */
+  int32_t share_input_state_representation;
 } cpp_naf_config;
 
 typedef struct {

@@ -199,10 +199,12 @@ def golden_ddpg(name, shape, pixels, B, seed, sparse=False):
   print("nets_%s" % name)
 
 
-def golden_naf(name, shape, pixels, B, seed, optimiser, optimiser_args):
+def golden_naf(name, shape, pixels, B, seed, optimiser, optimiser_args, share=False):
   rs = np.random.RandomState(seed)
   P = {}
-  defs = [no.naf_value("value", shape, pixels), no.naf_mu(shape, pixels), no.naf_l(shape, pixels)]
+  value = no.naf_value("value", shape, pixels)
+  heads = no.naf_shared_heads(value.fc[-2].out) if share else (no.naf_mu(shape, pixels), no.naf_l(shape, pixels))
+  defs = [value] + list(heads)
   for d in defs:
     P.update(no.init_params(d, rs))
   for k in list(P):
@@ -214,10 +216,11 @@ def golden_naf(name, shape, pixels, B, seed, optimiser, optimiser_args):
   for k in T:
     T[k] = torch.tensor((T[k].numpy() + rs.uniform(-0.02, 0.02, tuple(T[k].shape))).astype(np.float32), dtype=torch.float64)
   P.update(T)
-  out = {"meta": json.dumps(dict(state_shape=shape, pixels=pixels, B=B, seed=seed, optimiser=optimiser, optimiser_args=optimiser_args))}
+  out = {"meta": json.dumps(dict(state_shape=shape, pixels=pixels, B=B, seed=seed, optimiser=optimiser, optimiser_args=optimiser_args,
+                                 share=bool(share)))}
   for k, v in P.items():
     out["P0/" + k] = v.numpy().astype(np.float32)
-  o = no.NAFOracle(shape, pixels, P, optimiser=optimiser, optimiser_args=optimiser_args)
+  o = no.NAFOracle(shape, pixels, P, optimiser=optimiser, optimiser_args=optimiser_args, share=share)
   for step in range(3):
     batch = _batch(rs, B, shape)
     for f, v in zip(("s1", "a", "r", "m", "s2"), batch):
@@ -276,7 +279,16 @@ def main():
   golden_ddpg("ddpg_lowdim", (2, 2, 7), False, 16, 23)
   golden_naf("naf_pixel", (16, 16, 3, 2, 1), True, 8, 24, "Adam", {"learning_rate": 0.01})
   golden_naf("naf_lowdim", (3, 2, 7), False, 16, 25, "Momentum", {"learning_rate": 0.01, "momentum": 0.9})
+  golden_naf_shared()
   golden_lrpg()
+
+
+def golden_naf_shared():
+  """--share-input-state-representation (naf_cartpole.py:151-154,176-179)"""
+  # (plain SGD here: Adam's g / (|g| + 1e-8) update is ill-conditioned wherever the summed three-head gradient nearly cancels,
+  # which says nothing about the shared graph; Adam itself is pinned by naf_pixel)
+  golden_naf("naf_pixel_shared", (16, 16, 3, 2, 1), True, 8, 26, "GradientDescent", {"learning_rate": 0.01}, share=True)
+  golden_naf("naf_lowdim_shared", (3, 2, 7), False, 16, 27, "Momentum", {"learning_rate": 0.01, "momentum": 0.9}, share=True)
 
 
 if __name__ == "__main__":

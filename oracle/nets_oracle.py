@@ -100,6 +100,13 @@ def naf_l(state_shape, pixels, hidden="100,50", action_dim=2):
                 _hidden(hidden) + [FC("fc", action_dim * (action_dim + 1) // 2, None)])
 
 
+def naf_shared_heads(rep_dim, action_dim=2):
+  """--share-input-state-representation, naf_cartpole.py:151-154,176-179: output_action / l_values are only their `fc` layer,
+  fed by value_net.input_state_representation (width rep_dim)"""
+  return (NetDef("naf/output_action", (rep_dim,), False, [FC("fc", action_dim, "tanh")]),
+          NetDef("naf/l_values", (rep_dim,), False, [FC("fc", action_dim * (action_dim + 1) // 2, None)]))
+
+
 def lrpg_model(state_shape, hidden="100,50", num_actions=5):
   """lrpg_cartpole.py:80-88"""
   return NetDef("model", state_shape, False, _hidden(hidden) + [FC("fully_connected", num_actions, None)])
@@ -160,7 +167,7 @@ def conv_trunk(nd, P, state):
   return x.permute(0, 2, 3, 1)
 
 
-def forward(nd, P, state, action=None, dtype=None, return_hidden=False):
+def forward(nd, P, state, action=None, dtype=None, return_hidden=False, end_fc=None):
   dtype = dtype or next(iter(P.values())).dtype
   state = torch.as_tensor(np.asarray(state)) if not torch.is_tensor(state) else state
   x = state.to(dtype)                                  # fp16 replay states are cast by the feed
@@ -170,6 +177,8 @@ def forward(nd, P, state, action=None, dtype=None, return_hidden=False):
   else:
     x = x.reshape(B, -1)
   for i, l in enumerate(nd.fc):
+    if end_fc is not None and i >= end_fc:            # stop in front of FC layer end_fc (the shared representation)
+      break
     if nd.concat_at == i:
       x = torch.cat([x, action.to(dtype)], dim=1)     # ddpg_cartpole.py:170,175
     x = x @ P["%s/%s/weights" % (nd.ns, l.scope)] + P["%s/%s/biases" % (nd.ns, l.scope)]
@@ -320,12 +329,17 @@ class DDPGOracle(object):
 
 # ----------------------------------------------------------------------------- NAF
 
-def naf_quantities(value, mu_net, l_net, P, s1, action, action_dim):
+def naf_quantities(value, mu_net, l_net, P, s1, action, action_dim, share=False):
   """naf_cartpole.py:147-221 -> (l_values, L, V, mu, A, Q)"""
   dt = next(iter(P.values())).dtype
   V = forward(value, P, s1)
-  mu = forward(mu_net, P, s1)
-  l = forward(l_net, P, s1)
+  if share:      # the same graph nodes feed all three heads, so their gradients add up in value/* (:151-154,176-179)
+    rep = forward(value, P, s1, end_fc=len(value.fc) - 1)
+    mu = forward(mu_net, P, rep)
+    l = forward(l_net, P, rep)
+  else:
+    mu = forward(mu_net, P, s1)
+    l = forward(l_net, P, s1)
   B = l.shape[0]
   rows = []
   for r in range(action_dim):                               # naf_cartpole.py:195-203
@@ -345,11 +359,15 @@ class NAFOracle(object):
   """naf_cartpole.py:367-373 body: naf.train(batch) then (every batches_per_step) target update."""
 
   def __init__(self, state_shape, pixels, P, hidden="100,50", action_dim=2, discount=0.99, clip=5.0,
-               tau=1e-4, optimiser="GradientDescent", optimiser_args=None):
+               tau=1e-4, optimiser="GradientDescent", optimiser_args=None, share=False):
     self.value = naf_value("value", state_shape, pixels, hidden)
     self.tvalue = naf_value("target_value", state_shape, pixels, hidden)
-    self.mu = naf_mu(state_shape, pixels, hidden, action_dim)
-    self.l = naf_l(state_shape, pixels, hidden, action_dim)
+    self.share = bool(share)
+    if self.share:
+      self.mu, self.l = naf_shared_heads(self.value.fc[-2].out if len(self.value.fc) > 1 else self.value.feat, action_dim)
+    else:
+      self.mu = naf_mu(state_shape, pixels, hidden, action_dim)
+      self.l = naf_l(state_shape, pixels, hidden, action_dim)
     self.P, self.A, self.discount, self.clip, self.tau = P, action_dim, discount, clip, tau
     self.opt = Optimiser(optimiser, **(optimiser_args or {"learning_rate": 1e-3}))
     self.train_names = _names(self.value) + _names(self.mu) + _names(self.l)
@@ -357,7 +375,7 @@ class NAFOracle(object):
   def _loss(self, batch):
     s1, a, r, mask, s2 = batch
     dt = next(iter(self.P.values())).dtype
-    l, L, V, mu, A, Q = naf_quantities(self.value, self.mu, self.l, self.P, s1, a, self.A)
+    l, L, V, mu, A, Q = naf_quantities(self.value, self.mu, self.l, self.P, s1, a, self.A, self.share)
     with torch.no_grad():
       V2 = forward(self.tvalue, self.P, s2)
       y = torch.as_tensor(r).to(dt) + torch.as_tensor(mask).to(dt) * self.discount * V2   # :225-227
@@ -389,7 +407,10 @@ class NAFOracle(object):
 
   def action_given(self, state):
     with torch.no_grad():
-      return forward(self.mu, self.P, torch.as_tensor(np.asarray(state))[None])
+      x = torch.as_tensor(np.asarray(state))[None]
+      if self.share:
+        x = forward(self.value, self.P, x, end_fc=len(self.value.fc) - 1)
+      return forward(self.mu, self.P, x)
 
 
 # ----------------------------------------------------------------------------- LRPG

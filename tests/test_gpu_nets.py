@@ -173,22 +173,27 @@ def test_target_update_properties():
 
 # ------------------------------------------------------------------------------------------ NAF
 @pytest.mark.parametrize("tc", [False, True], ids=["cudacore", "tensorcore"])
-@pytest.mark.parametrize("name", ["naf_pixel", "naf_lowdim"])
+@pytest.mark.parametrize("name", ["naf_pixel", "naf_lowdim", "naf_pixel_shared", "naf_lowdim_shared"])
 def test_naf_golden(golden_dir, name, tc):
   U.set_route(tc)
   g, meta = U.load_golden(golden_dir, name)
-  shape, pixels = tuple(meta["state_shape"]), meta["pixels"]
+  shape, pixels, share = tuple(meta["state_shape"]), meta["pixels"], bool(meta.get("share", False))
   naf, nets, eng, o = U.make_naf(shape, pixels, U.golden_values(g), batch_size=meta["B"],
-                                 optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"])
+                                 optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"],
+                                 extra=["--share-input-state-representation"] if share else [])
   # the fp32 CPU path run alongside, for the conditioning of the Adam / Momentum parameter updates
   orc32 = no.NAFOracle(shape, pixels, {k: torch.tensor(v, dtype=torch.float32) for k, v in U.golden_values(g).items()},
-                       optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"])
+                       optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"], share=share)
   worst = {}
   for step in range(3):
     batch = U.golden_batch(g, step)
     dv = naf.debug_values(batch)
-    for f, v in zip(("l_values", "dbg_loss", "V", "A", "V2"), dv):
-      worst[f] = max(worst.get(f, 0), U.assert_close(v, g["step%d/%s" % (step, f)], what=f))
+    # after an Adam / Momentum update the parameters themselves are only as close to fp64 as fp32 arithmetic allows (see the
+    # final parameter check below); from step 1 on the forward values inherit that and are bounded by the fp32 CPU path's own error
+    dv32 = orc32.debug_values(tuple(batch))
+    for f, v, v32 in zip(("l_values", "dbg_loss", "V", "A", "V2"), dv, dv32):
+      worst[f] = max(worst.get(f, 0), U.assert_close(v, g["step%d/%s" % (step, f)], what="step %d %s" % (step, f),
+                                                     cpu32=v32 if step > 0 else None))
     eng.backward(batch)
     r32 = orc32.train(tuple(batch))
     gr = eng.buffers["grads"].cpu().numpy()

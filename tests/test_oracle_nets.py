@@ -134,3 +134,59 @@ def test_oracle_reproduces_committed_golden(golden_dir, name):
     o.update_targets(0.05)
   for k, v in o.P.items():
     np.testing.assert_allclose(v.numpy(), g["Pfinal/" + k], rtol=1e-9, atol=1e-13)
+
+
+def test_naf_shared_representation_sums_head_gradients():
+  """--share-input-state-representation (naf_cartpole.py:151-154,176-179): V, mu and l are three `fc` heads on ONE
+  representation, so d loss / d value/* carries all three heads.  Checked against central differences in fp64, and
+  against the un-shared graph to make sure the flag changes the variable set the way the reference does."""
+  rs = np.random.RandomState(3)
+  shape, B = (3, 2, 7), 6
+  value = no.naf_value("value", shape, False)
+  mu, l = no.naf_shared_heads(value.fc[-2].out)
+  assert [n for n, _ in mu.var_shapes()] == ["naf/output_action/fc/weights", "naf/output_action/fc/biases"]
+  assert dict(l.var_shapes())["naf/l_values/fc/weights"] == (50, 3)
+  P = {}
+  for d in (value, mu, l):
+    P.update(no.init_params(d, rs))
+  P["naf/output_action/fc/weights"] = torch.tensor(rs.uniform(-0.3, 0.3, (50, 2)))
+  P.update(no.retarget({k: v for k, v in P.items() if k.startswith("value/")}, "value", "target_value"))
+  batch = (rs.uniform(-1, 1, (B,) + shape).astype(np.float32), rs.uniform(-1, 1, (B, 2)).astype(np.float32),
+           np.ones((B, 1), np.float32), np.ones((B, 1), np.float32), rs.uniform(-1, 1, (B,) + shape).astype(np.float32))
+  o = no.NAFOracle(shape, False, {k: v.clone() for k, v in P.items()}, share=True, optimiser_args={"learning_rate": 0.0})
+  assert len(o.train_names) == 6 + 2 + 2
+  r = o.train(batch)
+  grads = dict(zip(o.train_names, r["grads"]))
+
+  def loss_at(name, idx, eps):
+    Q = {k: v.clone() for k, v in P.items()}
+    Q[name].view(-1)[idx] += eps
+    with torch.no_grad():
+      return float(no.NAFOracle(shape, False, Q, share=True)._loss(batch)[0])
+  for name in ("value/h0/weights", "value/h1/biases", "naf/l_values/fc/weights", "naf/output_action/fc/biases"):
+    for idx in (0, P[name].numel() - 1):
+      fd = (loss_at(name, idx, 1e-6) - loss_at(name, idx, -1e-6)) / 2e-6
+      assert abs(fd - float(grads[name].reshape(-1)[idx])) <= 1e-7 * max(1.0, abs(fd)), (name, idx, fd)
+  # with the heads cut off (their weights zeroed -> mu = 0, l = const) the hidden layers only see V's gradient: different
+  Z = {k: v.clone() for k, v in P.items()}
+  Z["naf/output_action/fc/weights"].zero_(); Z["naf/l_values/fc/weights"].zero_()
+  r0 = no.NAFOracle(shape, False, Z, share=True, optimiser_args={"learning_rate": 0.0}).train(batch)
+  assert not np.allclose(r0["grads"][0].numpy(), r["grads"][0].numpy())
+
+
+@pytest.mark.parametrize("name", ["naf_pixel_shared", "naf_lowdim_shared"])
+def test_oracle_reproduces_committed_shared_naf_golden(golden_dir, name):
+  g = np.load(os.path.join(golden_dir, "nets_%s.npz" % name))
+  meta = json.loads(str(g["meta"]))
+  assert meta["share"] is True
+  P = {k[3:]: torch.tensor(g[k].astype(np.float64)) for k in g.files if k.startswith("P0/")}
+  assert not any(k.startswith("naf/output_action/h") or k.startswith("naf/l_values/conv") for k in P)
+  o = no.NAFOracle(tuple(meta["state_shape"]), meta["pixels"], P, optimiser=meta["optimiser"],
+                   optimiser_args=meta["optimiser_args"], share=True)
+  for step in range(3):
+    batch = tuple(g["step%d/%s" % (step, f)] for f in ("s1", "a", "r", "m", "s2"))
+    r = o.train(batch)
+    np.testing.assert_allclose(torch.cat([x.reshape(-1) for x in r["grads"]]).numpy(), g["step%d/grads" % step], rtol=1e-9, atol=1e-13)
+    o.update_targets(0.05)
+  for k, v in o.P.items():
+    np.testing.assert_allclose(v.numpy(), g["Pfinal/" + k], rtol=1e-9, atol=1e-13)
