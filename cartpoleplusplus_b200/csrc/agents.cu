@@ -232,7 +232,21 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s0)); ones_ready = true; }
   CPP_TRY(record(E_START, s0));
   CPP_TRY(wait(sta, E_START));
-  if (multi) g_cta_cap = kNumSMs / 2;
+  // ---- weight preparation of every conv2 / conv3 pass of the step (fp16 weight pieces, 12 small kernels) on the critic
+  // chain's stream, which idles until conv1 is done: off the critical path of the four chains
+  struct PrepGuard { ~PrepGuard() { g_tc_prepped = 0; } } prep_guard;
+  enum { E_PREP = 8 };
+  if (multi && g_prep_hoist && actor.pixels && actor.tc_route(is_f16)) {
+    CPP_TRY(wait(sc, E_START));
+    CPP_TRY(actor.prep_trunk_tc(P, B, tcs[0], true, sc));
+    CPP_TRY(critic.prep_trunk_tc(P + off_c, B, tcs[1], true, sc));
+    CPP_TRY(actor.prep_trunk_tc(T, B, tcs[2], false, sc));
+    CPP_TRY(critic.prep_trunk_tc(T + off_c, B, tcs[3], false, sc));
+    CPP_TRY(record(E_PREP, sc));
+    g_tc_prepped = 1;
+  }
+  cudaStream_t sx = g_conv1_split ? sta : s0;                    // stream of the conv1 pass over state_2
+  if (multi) g_cta_cap = g_conv1_split ? kNumSMs / 2 : kNumSMs;
   {
     CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s0));
     cur_m1 = m1;
@@ -246,14 +260,17 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
     const int st = stats_for(s2, is_f16, B, mi2, pinned2, &m2, sta);
     mom_scratch = keep;
     CPP_TRY(st);
+    if (sx != sta) { CPP_TRY(record(E_TA, sta)); CPP_TRY(wait(sx, E_TA)); }
     const float* pt[2] = {T, T + off_c}; char* wst[2] = {ws_target, ws_target2};
-    CPP_TRY(conv1_forward_group(2, g2, pt, wst, s2, is_f16, m2, B, tcs[2], sta, &tc2));
-    tr.mark("sta conv1 fwd {targets}(s2) done", sta);
+    CPP_TRY(record(E_FORK, s0));                                 // conv1(s1) done: the critic chain may start
+    CPP_TRY(wait(sc, E_FORK));
+    CPP_TRY(conv1_forward_group(2, g2, pt, wst, s2, is_f16, m2, B, tcs[2], sx, &tc2));
+    tr.mark("sta conv1 fwd {targets}(s2) done", sx);
   }
-  CPP_TRY(record(E_FORK, s0));                                   // conv1(s1) done: the critic chain may start
-  CPP_TRY(wait(sc, E_FORK));
-  CPP_TRY(record(E_TA, sta));                                    // conv1(s2) done: the target critic chain may start
+  CPP_TRY(record(E_TA, sx));                                     // conv1(s2) done: the target chains may start
   CPP_TRY(wait(stc, E_TA));
+  if (sx != sta) CPP_TRY(wait(sta, E_TA));
+  if (g_tc_prepped) { CPP_TRY(wait(s0, E_PREP)); CPP_TRY(wait(sta, E_PREP)); CPP_TRY(wait(stc, E_PREP)); }
   if (multi) g_cta_cap = kNumSMs / 4;
   // ---- actor chain (s0): trunk tail, FC stack -> mu                       ddpg_cartpole.py:90-100
   CPP_TRY(actor.forward_trunk(P, s1, is_f16, m1, B, ws_actor, s0, tc1, tc1 ? tcs[0] : nullptr));
@@ -319,7 +336,7 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   if (multi || use_graphs()) CPP_TRY(ensure_streams());
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
-  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1)};
+  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | (g_conv1_split << 5)};
   const int rc = run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
     return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, st);
   });

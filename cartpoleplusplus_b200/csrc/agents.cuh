@@ -107,7 +107,7 @@ struct DDPG {
   // streams / graph state
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;                      // origin stream of the graph capture (the caller's may be the legacy default stream)
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};
   BackwardAux aux[2];                                     // side streams of the actor / critic backward chains (weight gradients)
   bool streams_ready = false;
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};   // packed-weight scratch per chain (actor, critic, target actor, target critic)

@@ -182,12 +182,13 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const __grid_constant
 
 // ------------------------------------------------------------------------------------------ main kernel
 // Warp-specialised, persistent (one CTA per SM):
-//   warps 0-3  epilogue : TMEM -> registers (tcgen05.ld), pieces summed, scale, border-aware bias, ReLU, 2x2 max-pool
-//   warps 4-7  fill     : TMA bulk copies of raw image rows into a staging ring, re-laid into the parity planes
-//   warp  8    MMA      : one elected lane issues the tcgen05.mma stream
+//   warps 0-7   epilogue : TMEM -> registers (tcgen05.ld), pieces summed, scale, border-aware bias, ReLU, 2x2 max-pool;
+//                          two groups of four (one warp per TMEM lane quarter), group e drains accumulator set e
+//   warps 8-19  fill     : TMA bulk copies of raw image rows into a staging ring, re-laid into the parity planes
+//   warp  20    MMA      : one elected lane issues the tcgen05.mma stream
 // Two plane buffers (fill of unit u+1 overlaps the MMAs of unit u) and two sets of TMEM accumulators (MMAs of
 // tile t+1 overlap the epilogue of tile t), all handed over through mbarriers.
-constexpr int kEpiWarps = 4, kFillWarps = 8;
+constexpr int kEpiWarps = 8, kEpiPerAcc = 4, kFillWarps = 12;
 constexpr int kThreads2 = 32 * (kEpiWarps + kFillWarps + 1);
 constexpr int kMaxStageSlots = 4;
 enum { BAR_FULL_PL = 0, BAR_EMPTY_PL = 2, BAR_FULL_ACC = 4, BAR_EMPTY_ACC = 6, BAR_STAGE = 8, BAR_COUNT = 8 + kMaxStageSlots };
@@ -237,6 +238,17 @@ __device__ __forceinline__ uint4 load8h(const unsigned short* p, int nch) {
   return make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
 }
 
+// 8 halfs from a 2-byte aligned shared-memory address, branch free: five aligned words, funnel-shifted by the misalignment
+// (reads up to 4 bytes past the 8th half: callers keep that inside the shared-memory allocation and mask what they use)
+__device__ __forceinline__ uint4 load8h_any(const unsigned short* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t sh = ((uint32_t)a & 2u) << 3;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+constexpr int kMaxG8 = 3;       // 8-channel groups of the input (C <= 24)
+
 // Work distribution: the tiles of the whole batch (image-major) are split into one contiguous range per CTA
 // (near-perfect balance); a CTA walks its range in units of <= tiles_per_unit tiles that never cross an image.
 struct UnitIter {
@@ -256,9 +268,28 @@ struct UnitIter {
   }
 };
 
+// Pipeline diagnosis build (nvcc -DCONV_TC_PROF, scripts/prof_conv_tc.py): per CTA, the cycles each role spends waiting on
+// each hand-over barrier.  Slots: 0 prologue, 1 MMA total, 2 MMA waits FULL_PL, 3 MMA waits EMPTY_ACC, 4 fill total,
+// 5 fill waits EMPTY_PL, 6 fill waits STAGE, 7 epilogue total, 8 epilogue waits FULL_ACC, 9 whole kernel, 10 tiles, 11 units
+#ifdef CONV_TC_PROF
+__device__ unsigned long long g_prof[160][12];
+__device__ int g_dbg_skip;     // timing experiments only (results are wrong): 1 no MMAs, 2 no re-layout, 4 no epilogue math
+#define PROF_DECL unsigned long long pf_t = 0, pf_w0 = 0, pf_w1 = 0; const long long pf_start = clock64();
+#define PROF_WAIT(acc, stmt) { const long long pf_a = clock64(); stmt; acc += (unsigned long long)(clock64() - pf_a); }
+#define PROF_PUT(slot, v) { if (lane == 0) g_prof[blockIdx.x][slot] = (unsigned long long)(v); }
+#else
+#define PROF_DECL
+#define PROF_WAIT(acc, stmt) { stmt; }
+#define PROF_PUT(slot, v)
+#endif
+
 template <int KS, int R>
 __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_constant__ FwdPlan P) {
   extern __shared__ __align__(128) uint8_t smem[];
+#ifdef CONV_TC_PROF
+  const long long pf_k0 = clock64();
+  const int pf_dbg = g_dbg_skip;
+#endif
   const SmemLayout L = smem_layout(P);
   uint8_t* planes_base = smem + L.planes;
   uint8_t* bsm = smem + L.bsm;
@@ -277,7 +308,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[BAR_FULL_PL + i], kFillWarps); mbar_init(&bars[BAR_EMPTY_PL + i], 1);
-      mbar_init(&bars[BAR_FULL_ACC + i], 1); mbar_init(&bars[BAR_EMPTY_ACC + i], kEpiWarps);
+      mbar_init(&bars[BAR_FULL_ACC + i], 1); mbar_init(&bars[BAR_EMPTY_ACC + i], kEpiPerAcc);
     }
     for (int i = 0; i < kMaxStageSlots; ++i) mbar_init(&bars[BAR_STAGE + i], 1);
     fence_mbar_init();
@@ -294,17 +325,23 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PROF_DECL
+#ifdef CONV_TC_PROF
+  if (tid == 0) g_prof[blockIdx.x][0] = (unsigned long long)(pf_start - pf_k0);
+#endif
 
   if (warp < kEpiWarps) {
     // =========================================================================== epilogue warps
     const float scale_inv = corr_s[ncorr];
-    const int quarter = warp;                                      // TMEM lanes 32*quarter .. +31
+    const int quarter = warp & 3;                                  // TMEM lanes 32*quarter .. +31
+    const uint32_t egroup = (uint32_t)warp >> 2;                   // this group of four drains accumulator set `egroup`
     uint32_t tc = 0;
     for (UnitIter ui(P); ui.next();) {
       const int b = ui.b;
       for (int t = ui.t0; t < ui.t1; ++t, ++tc) {
         const uint32_t ab = tc & 1;
-        mbar_wait(&bars[BAR_FULL_ACC + ab], (tc >> 1) & 1);
+        if (ab != egroup) continue;
+        PROF_WAIT(pf_w0, mbar_wait(&bars[BAR_FULL_ACC + ab], (tc >> 1) & 1));
         tc_fence_after();
         const int q = 128 * t + 32 * quarter + lane;
         const int py = q / Pq, px = q - py * Pq;
@@ -343,6 +380,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
           continue;
         }
         for (int net = 0; net < P.nets; ++net) {
+#ifdef CONV_TC_PROF
+          if (pf_dbg & 4) break;
+#endif
           float best[CO];
           int arg[CO];
 #pragma unroll
@@ -397,12 +437,24 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
         if (lane == 0) mbar_arrive(&bars[BAR_EMPTY_ACC + ab]);     // this warp's quarter of the accumulators is drained
       }
     }
+#ifdef CONV_TC_PROF
+    if (warp == 0) { PROF_PUT(7, clock64() - pf_start); PROF_PUT(8, pf_w0); PROF_PUT(10, tc); }
+#endif
   } else if (warp < kEpiWarps + kFillWarps) {
     // =========================================================================== fill warps
     const int ftid = tid - 32 * kEpiWarps, nfill = 32 * kFillWarps;
     const size_t img_elems = (size_t)H * W * C;
     const int n_groups = (P.rows_alloc + P.crh - 1) / P.crh;
     const int rowC = W * C;
+    // channels of the last 8-group that exist (a zero-padded group when C is not 8*G8 + R)
+    const int nch_last = P.R > 0 ? 8 : C - 8 * (P.G8 - 1);
+    uint4 last_mask;
+    {
+      uint32_t m[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) m[e] = nch_last >= 2 * e + 2 ? 0xffffffffu : (nch_last == 2 * e + 1 ? 0x0000ffffu : 0u);
+      last_mask = make_uint4(m[0], m[1], m[2], m[3]);
+    }
     uint32_t it = 0, icnt = 0, wcnt = 0;                           // units done; staging copies issued / consumed
     // producer cursor (fill thread 0): raw rows are requested up to stage_slots groups ahead of the re-layout, across
     // unit boundaries, so the TMA latency is off the fill warps' critical path
@@ -434,7 +486,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
       const int py_first = (128 * ui.t0) / Pq, yh0 = py_first - 1;
       const __half* img = P.x + (size_t)(P.rows ? P.rows[b] : b) * img_elems;
       const uint32_t buf = it & 1;
-      mbar_wait(&bars[BAR_EMPTY_PL + buf], ((it >> 1) & 1) ^ 1);   // the MMAs that read this buffer two units ago are done
+      PROF_WAIT(pf_w0, mbar_wait(&bars[BAR_EMPTY_PL + buf], ((it >> 1) & 1) ^ 1));   // the MMAs that read this buffer two units ago are done
       uint8_t* planes = planes_base + (size_t)buf * P.unit_bytes;
 
       if (P.in_layout == 2) {
@@ -480,11 +532,11 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
         int rho0, rho1, yc0, yc1;
         group_rows(g, rho0, rho1, yc0, yc1);
         const bool have = yc1 > yc0;
-        const unsigned short* stage = nullptr;
+        const unsigned short* stage = reinterpret_cast<const unsigned short*>(stage_base);   // (never read when !have, but addressed)
         if (P.use_bulk) {
           if (have) {
             const uint32_t sb = wcnt % NS;
-            mbar_wait(&bars[BAR_STAGE + sb], (wcnt / NS) & 1);
+            PROF_WAIT(pf_w1, mbar_wait(&bars[BAR_STAGE + sb], (wcnt / NS) & 1));
             stage = reinterpret_cast<const unsigned short*>(stage_base + (size_t)sb * P.stage_bytes);
             ++wcnt;
           }
@@ -495,39 +547,62 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
           named_bar_sync(1, nfill);
           stage = st;
         }
-        const int npos = (rho1 - rho0) * Pq;
-        for (int pos = ftid; pos < npos; pos += nfill) {
+        // one work item = one plane position x one row parity (short items: the re-layout is latency bound, not issue bound)
+        int npos = (rho1 - rho0) * Pq;
+#ifdef CONV_TC_PROF
+        if (pf_dbg & 2) npos = 0;
+#endif
+        for (int item = ftid; item < 2 * npos; item += nfill) {
+          const int yp = item >= npos ? 1 : 0;
+          const int pos = item - yp * npos;
           const int rl = pos / Pq, kap = pos - rl * Pq;
           const int rho = rho0 + rl, yh = yh0 + rho, xh = kap - 1;
           uint8_t* dst = planes + ((size_t)rho * Pq + kap) * 16;
-#pragma unroll
-          for (int yp = 0; yp < 2; ++yp) {
+          {
+            // all shared-memory loads of the item first (branch free, clamped addresses), then the selects, then all stores:
+            // stores into the planes may alias the staging rows as far as the compiler knows, so interleaving them with the
+            // loads would serialise every load behind the previous store
             const int y = 2 * yh + yp;
             const bool yok = have && y >= yc0 && y < yc1;
             const unsigned short* rowp = stage + (yok ? (y - yc0) : 0) * rowC;
+            uint4 v[2][kMaxG8];
+            const bool ok0 = yok && xh >= 0 && 2 * xh < W, ok1 = yok && xh >= 0 && 2 * xh + 1 < W;
+            const unsigned short* px0 = rowp + (ok0 ? 2 * xh : 0) * C;
+            const unsigned short* px1 = rowp + (ok1 ? 2 * xh + 1 : 0) * C;
 #pragma unroll
-            for (int xp = 0; xp < 2; ++xp) {
-              const int x = 2 * xh + xp;
-              const bool ok = yok && x >= 0 && x < W;
-              for (int gq = 0; gq < P.G8; ++gq) {
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (ok) v = load8h(rowp + x * C + 8 * gq, C - 8 * gq);
-                *reinterpret_cast<uint4*>(dst + (size_t)(gq * 4 + yp * 2 + xp) * P.plane_bytes) = v;
+            for (int gq = 0; gq < kMaxG8; ++gq)
+              if (gq < P.G8) {                                     // (uniform)
+                uint4 t0 = load8h_any(px0 + 8 * gq), t1 = load8h_any(px1 + 8 * gq);
+                if (gq == P.G8 - 1) {
+                  t0.x &= last_mask.x; t0.y &= last_mask.y; t0.z &= last_mask.z; t0.w &= last_mask.w;
+                  t1.x &= last_mask.x; t1.y &= last_mask.y; t1.z &= last_mask.z; t1.w &= last_mask.w;
+                }
+                v[0][gq] = ok0 ? t0 : make_uint4(0, 0, 0, 0);
+                v[1][gq] = ok1 ? t1 : make_uint4(0, 0, 0, 0);
               }
-            }
+            constexpr int NPIX = KS + 1, NE = KS * R, NJ = (NE + 7) / 8;
+            uint32_t pix[NPIX][R > 0 ? R : 1];
             if constexpr (R > 0) {
               // remainder channels: the KS taps along x of the R channels share 16-byte rows, one per output column.
               // Output columns 2*xh (dx = 0) and 2*xh + 1 (dx = 1) read pixels 2*xh - PAD .. 2*xh + 1 + PAD.
-              constexpr int NPIX = KS + 1, NE = KS * R, NJ = (NE + 7) / 8;
-              uint32_t pix[NPIX][R > 0 ? R : 1];
               const bool cok = yok && xh >= 0 && xh < PW;
 #pragma unroll
               for (int i = 0; i < NPIX; ++i) {
                 const int x = 2 * xh - PAD + i;
                 const bool ok = cok && x >= 0 && x < W;
 #pragma unroll
-                for (int c = 0; c < R; ++c) pix[i][c] = ok ? (uint32_t)rowp[x * C + 8 * P.G8 + c] : 0u;
+                for (int c = 0; c < R; ++c) {
+                  const uint32_t t = (uint32_t)rowp[(ok ? x : 0) * C + 8 * P.G8 + c];
+                  pix[i][c] = ok ? t : 0u;
+                }
               }
+            }
+#pragma unroll
+            for (int xp = 0; xp < 2; ++xp)
+#pragma unroll
+              for (int gq = 0; gq < kMaxG8; ++gq)
+                if (gq < P.G8) *reinterpret_cast<uint4*>(dst + (size_t)(gq * 4 + yp * 2 + xp) * P.plane_bytes) = v[xp][gq];
+            if constexpr (R > 0) {
 #pragma unroll
               for (int dx = 0; dx < 2; ++dx)
 #pragma unroll
@@ -551,6 +626,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_FULL_PL + buf]);
     }
+#ifdef CONV_TC_PROF
+    if (warp == kEpiWarps) { PROF_PUT(4, clock64() - pf_start); PROF_PUT(5, pf_w0); PROF_PUT(6, pf_w1); PROF_PUT(11, it); }
+#endif
   } else {
     // =========================================================================== MMA warp (one elected lane issues)
     const uint32_t idesc = make_idesc(N);
@@ -561,19 +639,25 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
       const int t0 = ui.t0, t1 = ui.t1;
       const int py_first = (128 * t0) / Pq;
       const uint32_t buf = it & 1;
-      mbar_wait(&bars[BAR_FULL_PL + buf], (it >> 1) & 1);
+      PROF_WAIT(pf_w0, mbar_wait(&bars[BAR_FULL_PL + buf], (it >> 1) & 1));
       tc_fence_after();
       const uint32_t pl16 = (smem_u32(planes_base + (size_t)buf * P.unit_bytes) & 0x3FFFFu) >> 4;
       for (int t = t0; t < t1; ++t, ++tc) {
         const uint32_t ab = tc & 1;
-        mbar_wait(&bars[BAR_EMPTY_ACC + ab], ((tc >> 1) & 1) ^ 1); // the epilogue drained these accumulators
+        PROF_WAIT(pf_w1, mbar_wait(&bars[BAR_EMPTY_ACC + ab], ((tc >> 1) & 1) ^ 1)); // the epilogue drained these accumulators
         tc_fence_after();
         const uint32_t a_add = pl16 + (uint32_t)(128 * t - py_first * Pq);
-        for (int a = 0; a < 4; ++a) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)((ab * 4 + a) * N);
-          for (int i = 0; i < P.n_pairs; ++i) {
+        // K step outermost, the four pool positions (independent accumulators) innermost: back-to-back MMAs into the SAME
+        // accumulator serialise on its read-modify-write latency (scripts/micro/umma_rate.cu: nacc = 1 vs 4)
+        for (int i = 0; i < P.n_pairs; ++i) {
+          const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(i * 2 * N));
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((ab * 4 + a) * N);
             const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(P.adesc_lo[a][i] + a_add);
-            const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(i * 2 * N));
+#ifdef CONV_TC_PROF
+            if (pf_dbg & 1) continue;
+#endif
             if (elect_one()) umma_f16(d_tmem, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
           }
         }
@@ -583,11 +667,24 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
       if (elect_one()) umma_commit(&bars[BAR_EMPTY_PL + buf]);     // all MMAs that read this plane buffer have completed
       __syncwarp();
     }
+    PROF_PUT(1, clock64() - pf_start); PROF_PUT(2, pf_w0); PROF_PUT(3, pf_w1);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == kEpiWarps + kFillWarps) tmem_dealloc(tmem_base, 512);
+#ifdef CONV_TC_PROF
+  if (tid == 0) g_prof[blockIdx.x][9] = (unsigned long long)(clock64() - pf_k0);
+#endif
 }
+
+#ifdef CONV_TC_PROF
+extern "C" __attribute__((visibility("default"))) int cpp_debug_conv_tc_skip(int mask) {
+  return (int)cudaMemcpyToSymbol(g_dbg_skip, &mask, sizeof(int));
+}
+extern "C" __attribute__((visibility("default"))) int cpp_debug_conv_tc_prof(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * 160 * 12);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------ host: plan
 static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, int dgrad = 0) {
@@ -604,6 +701,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, 
   const int rem = C % 8;
   if (rem == 1 || rem == 2) { P->G8 = C / 8; P->R = rem; P->nR = (KS * rem + 7) / 8; }
   else { P->G8 = (C + 7) / 8; P->R = 0; P->nR = 0; }
+  CPP_REQUIRE(P->G8 <= kMaxG8, "conv_tc: %d input channels (at most %d groups of 8)", C, kMaxG8);
   P->n_planes = 4 * (P->G8 + P->nR);
 
   // slab pairs: both K8 halves of an instruction live in the same plane set with the second at a higher address
@@ -654,12 +752,14 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, 
   P->use_bulk = (row_bytes % 16 == 0) && (((size_t)H * W * C * 2) % 16 == 0);
   // shared-memory budget: two staging buffers of up to 16 KB first (few, long TMA copies), then the largest unit
   // (fewer halo rows re-staged per tile) whose two plane buffers still fit
+  int stage_budget = 16384;
   auto size_unit = [&](int tpu) {
     P->tiles_per_unit = tpu;
     P->rows_alloc = (P->Pq - 1 + 128 * tpu - 1 + 2 * P->Pq + 2) / P->Pq + 1;
     P->plane_bytes = P->rows_alloc * P->Pq * 16;
     P->unit_bytes = P->n_planes * P->plane_bytes;
-    P->crh = std::max(1, std::min(P->rows_alloc, 16384 / (2 * row_bytes)));
+    P->crh = std::max(1, std::min(P->rows_alloc, stage_budget / (2 * row_bytes)));
+    P->crh = (int)ceil_div(P->rows_alloc, ceil_div(P->rows_alloc, P->crh));      // equal groups
     P->stage_bytes = (int)round_up((int64_t)2 * P->crh * row_bytes, 16);
     return (int)smem_layout(*P).total;
   };
@@ -672,6 +772,18 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, FwdPlan* P, 
     P->stage_slots = ns;
     for (int tpu = std::min(P->tiles_per_image, want_tpu); tpu >= 1; --tpu)
       if (size_unit(tpu) <= kSmemLimit) { best_tpu = tpu; break; }
+  }
+  if (best_tpu > 0 && P->crh < P->rows_alloc) {
+    // room left: stage a whole unit's rows per TMA copy, so the re-layout of a unit is ONE pass of the fill warps with one
+    // barrier (it is latency bound: 2 passes of half the rows cost twice as much as one pass of all of them)
+    const int ns_keep = P->stage_slots;
+    stage_budget = 2 * P->rows_alloc * row_bytes;
+    bool fits = false;
+    for (int ns = ns_keep; ns >= 2 && !fits; ns -= 2) {
+      P->stage_slots = ns;
+      fits = size_unit(best_tpu) <= kSmemLimit;
+    }
+    if (!fits) { stage_budget = 16384; P->stage_slots = ns_keep; }
   }
   CPP_REQUIRE(best_tpu > 0, "conv_tc: %dx%dx%d does not fit shared memory", H, W, C);
   P->units_per_image = (int)ceil_div(P->tiles_per_image, best_tpu);
@@ -734,7 +846,7 @@ static int launch_main(const FwdPlan& P, int grid, cudaStream_t s) {
 int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int nets,
                        const float* const* w, const float* const* bias, int B, int H, int W, int C, int KS,
                        float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s,
-                       int x_is_pieces, __half* const* pooled_hl) {
+                       int x_is_pieces, __half* const* pooled_hl, int phase) {
   if (B <= 0) return CPP_OK;
   FwdPlan P{};
   CPP_TRY(build_plan(nets, B, H, W, C, KS, &P));
@@ -742,19 +854,23 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
   P.Cw = x_is_pieces ? CO : C;
   P.in_layout = x_is_pieces;
   CPP_REQUIRE(((uintptr_t)x_f16 & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
+  const bool prep_only = phase == kPhasePrep;
   P.x = reinterpret_cast<const __half*>(x_f16); P.rows = rows;
   P.bpack = reinterpret_cast<const __half*>(scratch);
   P.corr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(scratch) + bpack_bytes(P));
   PrepArgs A{};
   for (int n = 0; n < nets; ++n) {
-    CPP_REQUIRE(w[n] && bias[n] && pooled[n] && amax[n], "conv_tc: null pointer for network %d", n);
-    A.w[n] = w[n]; A.bias[n] = bias[n]; P.pooled[n] = pooled[n]; P.amax[n] = amax[n];
-    P.pooled_hl[n] = pooled_hl ? pooled_hl[n] : nullptr;
+    CPP_REQUIRE(w[n] && bias[n] && (prep_only || (pooled[n] && amax[n])), "conv_tc: null pointer for network %d", n);
+    A.w[n] = w[n]; A.bias[n] = bias[n];
+    if (!prep_only) { P.pooled[n] = pooled[n]; P.amax[n] = amax[n]; P.pooled_hl[n] = pooled_hl ? pooled_hl[n] : nullptr; }
   }
   A.mean_inv = mean_inv;
   A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);
-  conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
-  CPP_CHECK_LAUNCH();
+  if (phase != kPhaseMain) {
+    conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
+    CPP_CHECK_LAUNCH();
+  }
+  if (prep_only) return CPP_OK;
   const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, sm_budget());   // persistent: one CTA per SM (it owns all 512 TMEM columns)
   if (KS == 5) {
     if (P.R == 0) return launch_main<5, 0>(P, grid, s);
@@ -767,12 +883,12 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
 }
 
 int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
-                         void* scratch, cudaStream_t s, float* out_absmax) {
+                         void* scratch, cudaStream_t s, float* out_absmax, int phase) {
   if (B <= 0) return CPP_OK;
   FwdPlan P{};
   CPP_TRY(build_plan(1, B, H, W, kC24, KS, &P, 1));
   P.out_absmax = out_absmax;
-  if (out_absmax != nullptr) CPP_CHECK_CUDA(cudaMemsetAsync(out_absmax, 0, sizeof(float), s));
+  if (out_absmax != nullptr && phase != kPhasePrep) CPP_CHECK_CUDA(cudaMemsetAsync(out_absmax, 0, sizeof(float), s));
   CPP_REQUIRE(((uintptr_t)dy_pieces & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
   P.Cw = CO; P.in_layout = 2;
   P.x = reinterpret_cast<const __half*>(dy_pieces); P.rows = nullptr;
@@ -783,8 +899,11 @@ int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const fl
   PrepArgs A{};
   A.w[0] = w; A.bias[0] = nullptr; A.mean_inv = nullptr;
   A.bpack = const_cast<__half*>(P.bpack); A.corr = const_cast<float*>(P.corr);
-  conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
-  CPP_CHECK_LAUNCH();
+  if (phase != kPhaseMain) {
+    conv_tc_prep_kernel<<<64, 256, 0, s>>>(P, A);
+    CPP_CHECK_LAUNCH();
+  }
+  if (phase == kPhasePrep) return CPP_OK;
   const int grid = (int)std::min<int64_t>((int64_t)B * P.tiles_per_image, sm_budget());
   return KS == 5 ? launch_main<5, 0>(P, grid, s) : launch_main<3, 0>(P, grid, s);
 }

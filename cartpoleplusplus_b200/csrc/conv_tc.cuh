@@ -67,16 +67,20 @@ bool conv_tc_supported(int nets, int H, int W, int C, int KS);
 // x_is_pieces: 1 = x holds [hi(10) | lo(10)] fp16 pieces of an fp32 activation, 2 = the 24-channel piece layout above
 // (conv2/conv3); w has 10 input channels, mean_inv must be NULL.  pooled_hl (optional, may be NULL or hold NULLs): piece
 // copy of the output in the 24-channel layout.
+// phase: the launch is a weight-prep kernel (fp16 weight pieces + border table into `scratch`; needs only w, bias, mean_inv)
+// followed by the main kernel.  kPhasePrep / kPhaseMain launch one of the two, so that a caller can prepare the weights
+// of many layers on a side stream at the start of a step (the activations pointers may be NULL for kPhasePrep).
+enum { kPhaseBoth = 0, kPhasePrep = 1, kPhaseMain = 2 };
 int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean_inv, int nets,
                        const float* const* w, const float* const* bias, int B, int H, int W, int C, int KS,
                        float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s,
-                       int x_is_pieces = 0, __half* const* pooled_hl = nullptr);
+                       int x_is_pieces = 0, __half* const* pooled_hl = nullptr, int phase = kPhaseBoth);
 // gradient wrt the input of a 10 -> 10 channel layer (conv2 / conv3): dx = conv_same(dY, flip(w)^T) on the tensor cores.
 // dy_pieces fp16 [B][H][W][24] (piece layout above, constant channel 0) = the un-pooled output gradient times *inv_scale^-1
 // (launch_unpool_split);
 // dx fp32 [B][H][W][10].
 int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
-                         void* scratch, cudaStream_t s, float* out_absmax = nullptr);
+                         void* scratch, cudaStream_t s, float* out_absmax = nullptr, int phase = kPhaseBoth);
 // un-pool + split: d_pooled fp32 [B][H/2][W/2][10] and the arg-max side band -> dy_pieces fp16 [B][H][W][24], scaled by
 // a power of two from max|d_pooled| (gmax: device float, zeroed and filled here); inv_scale receives 1/scale
 // gmax_ready: *gmax already holds max|d_pooled| (left there by the kernel that produced d_pooled)

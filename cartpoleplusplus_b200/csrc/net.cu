@@ -122,7 +122,8 @@ int Net::forward_trunk(const float* params, const void* state, int is_f16, const
         float* po[1] = {pooled}; uint8_t* am[1] = {amax};
         __half* hl[1] = {i < 2 ? reinterpret_cast<__half*>(ws + L.hl[i]) : nullptr};
         CPP_TRY(tc::launch_conv_fwd_tc(ws + L.hl[i - 1], nullptr, nullptr, 1, w, b, B, conv[i].H, conv[i].W, tc::kC24, conv[i].KS,
-                                       po, am, tc_scratch, s, 2, hl));
+                                       po, am, reinterpret_cast<char*>(tc_scratch) + i * trunk_slot_bytes(*this), s, 2, hl,
+                                       g_tc_prepped ? tc::kPhaseMain : tc::kPhaseBoth));
       } else {
         CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
       }
@@ -208,11 +209,28 @@ int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* con
   return CPP_OK;
 }
 
-int64_t trunk_group_scratch_bytes(int n, const Net& net) {
+int64_t trunk_slot_bytes(const Net& net) {
   if (!net.pixels) return 0;
-  int64_t b = tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS);
+  int64_t b = 0;
+  for (int n = 1; n <= tc::kMaxNets; ++n) b = std::max(b, tc::conv_tc_scratch_bytes(n, net.conv[0].H, net.conv[0].W, net.conv[0].Cin, net.conv[0].KS));
   for (int i = 1; i < 3; ++i) b = std::max(b, tc::conv_tc_scratch_bytes(1, net.conv[i].H, net.conv[i].W, tc::kC24, net.conv[i].KS));
-  return b > 0 ? b : 0;
+  return b > 0 ? (int64_t)round_up(b, 256) : 0;
+}
+
+int64_t trunk_group_scratch_bytes(int, const Net& net) { return kTcSlots * trunk_slot_bytes(net); }
+
+int Net::prep_trunk_tc(const float* params, int B, void* tc_scratch, bool with_dgrad, cudaStream_t s) const {
+  char* base = reinterpret_cast<char*>(tc_scratch);
+  const int64_t slot = trunk_slot_bytes(*this);
+  for (int i = 1; i < 3; ++i) {
+    const float* w[1] = {params + off_conv_w[i]}; const float* b[1] = {params + off_conv_b[i]};
+    CPP_TRY(tc::launch_conv_fwd_tc(base, nullptr, nullptr, 1, w, b, B, conv[i].H, conv[i].W, tc::kC24, conv[i].KS, nullptr, nullptr,
+                                   base + i * slot, s, 2, nullptr, tc::kPhasePrep));
+    if (with_dgrad)
+      CPP_TRY(tc::launch_conv_dgrad_tc(base, nullptr, params + off_conv_w[i], B, conv[i].H, conv[i].W, conv[i].KS, nullptr,
+                                       base + (i == 2 ? 3 : 4) * slot, s, nullptr, tc::kPhasePrep));
+  }
+  return CPP_OK;
 }
 
 int conv1_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
@@ -377,9 +395,10 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
       float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
       if (tc_dg) {
         CPP_TRY(tc::launch_conv_dgrad_tc(reinterpret_cast<__half*>(ws + L.dyp), gsc + 1, params + off_conv_w[i], B, conv[i].H, conv[i].W,
-                                         conv[i].KS, dx, tc_scratch, s,
+                                         conv[i].KS, dx, reinterpret_cast<char*>(tc_scratch) + (i == 2 ? 3 : 4) * trunk_slot_bytes(*this), s,
                                          // max|dx| for the next consumer: conv1's wgrad (i == 1), conv2's un-pool/split (i == 2)
-                                         reinterpret_cast<float*>(ws + L.gsc) + (i == 1 ? 6 : 2)));
+                                         reinterpret_cast<float*>(ws + L.gsc) + (i == 1 ? 6 : 2),
+                                         g_tc_prepped ? tc::kPhaseMain : tc::kPhaseBoth));
       } else {
         CPP_TRY(launch_conv_dgrad(conv[i], gp, amax, params + off_conv_w[i], B, dx, s));
       }

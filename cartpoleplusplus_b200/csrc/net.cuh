@@ -53,6 +53,10 @@ struct Net {
                     cudaStream_t s, int first_conv = 0, void* tc_scratch = nullptr) const;
   // does this network take the tensor-core route for a state of this dtype (same answer in forward and backward)
   bool tc_route(int is_f16) const;
+  // weight-prep kernels of conv2 / conv3 forward (and, with_dgrad, of their input-gradient passes) into their slots of
+  // tc_scratch; forward_trunk / backward then launch main kernels only while g_tc_prepped is set.  The weights must not change
+  // in between (they do not inside one step: the optimiser runs last).
+  int prep_trunk_tc(const float* params, int B, void* tc_scratch, bool with_dgrad, cudaStream_t s) const;
   // layers [first_fc, end_fc) (end_fc < 0: to the last one; `out` is only written when the last layer is included)
   int forward_fc(const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s, int first_fc = 0,
                  int end_fc = -1) const;
@@ -72,6 +76,9 @@ struct Net {
 // state_2, ddpg_cartpole.py:270-273; NAF's value/mu/l, naf_cartpole.py:104,150,175): conv1 of all of them in one
 // tcgen05 pass over the pixels (conv_tc.cu) when the state is fp16 and tc_scratch is given, conv2/conv3 per net.
 // Falls back to the exact-fp32 CUDA-core conv1 for fp32 states (action_given from the env) or CARTPOLEPP_CONV1=ffma.
+// tc_scratch = kTcSlots slots of trunk_slot_bytes(net): 0 conv1 (all siblings), 1 conv2 fwd, 2 conv3 fwd, 3 conv3 dgrad, 4 conv2 dgrad
+constexpr int kTcSlots = 5;
+int64_t trunk_slot_bytes(const Net& net);
 int64_t trunk_group_scratch_bytes(int n, const Net& net);
 int trunk_forward_group(int n, const Net* const* nets, const float* const* params, char* const* ws, const void* state,
                         int is_f16, const float* mean_inv, int B, void* tc_scratch, cudaStream_t s);

@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""A/B timing of a cpp_set_option switch on ONE box, interleaved so that clock / box differences cancel:
+  python scripts/ab_option.py prep_hoist [c3|c5] [rounds]
+prints the median ms/step of the fused DDPG step (device-resident batch, CUDA events) for value 0 and 1."""
+import json
+import os
+import sys
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import gpu_util as U                     # noqa: E402
+from oracle.make_golden import _batch               # noqa: E402
+from cartpoleplusplus_b200 import _lib as L         # noqa: E402
+
+
+def main():
+  name = sys.argv[1]
+  cfg = sys.argv[2] if len(sys.argv) > 2 else "c3"
+  rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 7
+  shape, B = {"c3": ((64, 64, 3, 1, 3), 256), "c5": ((128, 128, 3, 2, 4), 128)}[cfg]
+  rs = np.random.RandomState(0)
+  nets, eng, o = U.make_ddpg(shape, True, None, batch_size=B)
+  b = U.Batch(*[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in _batch(rs, B, shape)])
+  res = {0: [], 1: []}
+  for r in range(rounds):
+    for v in (0, 1):
+      L.check(L.lib().cpp_set_option(name.encode(), v))
+      for _ in range(5):
+        eng.train_step(b)
+      torch.cuda.synchronize()
+      a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      for _ in range(40):
+        eng.train_step(b)
+      e.record(); torch.cuda.synchronize()
+      res[v].append(a.elapsed_time(e) / 40)
+  print(json.dumps({"option": name, "config": cfg, "ms_per_step_0": float(np.median(res[0])), "ms_per_step_1": float(np.median(res[1])),
+                    "all_0": [round(x, 4) for x in res[0]], "all_1": [round(x, 4) for x in res[1]]}))
+
+
+if __name__ == "__main__":
+  main()

@@ -14,7 +14,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   d |= (uint64_t)layout << 61;
   return d;
 }
-__global__ void __launch_bounds__(128, 1) k(int M, int N, int iters, int layout, int sbo_sw, int a_shift, int a_step, int n_acc, long long* out) {
+__global__ void __launch_bounds__(128, 1) k(int M, int N, int iters, int layout, int sbo_sw, int a_shift, int a_step, int n_acc, long long* out, int lbo = 2064) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128, 1) k(int M, int N, int iters, int layout,
   if (warp == 0) {
     const uint32_t a_base = smem_u32(smem) + a_shift, b_base = smem_u32(smem) + 128 * 1024;
     const uint32_t hi_a = layout == 0 ? ((128u >> 4) | (1u << 14)) : ((uint32_t)(sbo_sw >> 4) | (1u << 14) | ((uint32_t)layout << 29));
-    const uint32_t lo_a0 = layout == 0 ? (((a_base & 0x3FFFF) >> 4) | (((2048u + 16u) >> 4) << 16)) : (((a_base & 0x3FFFF) >> 4) | (1u << 16));
+    const uint32_t lo_a0 = layout == 0 ? (((a_base & 0x3FFFF) >> 4) | (((uint32_t)lbo >> 4) << 16)) : (((a_base & 0x3FFFF) >> 4) | (1u << 16));
     const uint32_t lo_b = layout == 0 ? (((b_base & 0x3FFFF) >> 4) | ((uint32_t)N << 16)) : (((b_base & 0x3FFFF) >> 4) | (1u << 16));
     t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -67,6 +67,18 @@ int main() {
   long long* out; cudaMalloc(&out, 148 * sizeof(long long));
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 4096;
+  auto run_lbo = [&](int N, int lbo, int step) {
+    k<<<148, 128, 200 * 1024>>>(128, N, iters, 0, 0, 0, step, 4, out, lbo);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, out, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("M=128 N=%3d no-swizzle LBO=%5d window step=%4d : %7.1f cyc/mma  (%s)\n", N, lbo, step, (double)mx / iters, cudaGetErrorString(e));
+  };
+  printf("-- A operand: distance between the two K8 halves (LBO) - shared-memory bank overlap of the halves\n");
+  for (int lbo : {16, 32, 48, 64, 128, 256, 512, 528, 1024, 2048, 2064, 5280, 5296, 10560})
+    run_lbo(48, lbo, 0);
+  for (int lbo : {16, 128, 528, 5280}) run_lbo(48, lbo, 528);
+  for (int lbo : {16, 128, 528, 5280}) run_lbo(32, lbo, 16);
   auto run = [&](int M, int N, int layout, int sbo_sw, int shift, int step, int nacc, int grid) {
     if (nacc * N > 512) nacc = 512 / N;
     int p2 = 1; while (p2 * 2 <= nacc) p2 *= 2; nacc = p2;
@@ -77,6 +89,9 @@ int main() {
     printf("M=%3d N=%3d layout=%d sbo=%4d shift=%4d step=%5d nacc=%d grid=%3d : %7.1f cyc/mma  (%s)\n", M, N, layout, sbo_sw, shift, step, nacc, grid, (double)mx / iters, cudaGetErrorString(e));
   };
   const int Ns[] = {16, 32, 48, 64, 96, 128, 256};
+  printf("-- accumulator dependency: consecutive MMAs into the SAME accumulator (nacc=1) vs rotating over 2 / 4\n");
+  for (int N : {32, 48, 64, 128, 256})
+    for (int nacc : {1, 2, 4}) run(128, N, 0, 0, 0, 0, nacc, 148);
   printf("-- no swizzle, K-major, dense (SBO=128, LBO=2064)\n");
   for (int N : Ns) run(128, N, 0, 0, 0, 0, 4, 148);
   printf("-- no swizzle, unaligned start (+16), moving window\n");
