@@ -283,9 +283,14 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   tr.mark("sc critic conv2/3 fwd done", sc);
   if (ca > 0) CPP_TRY(critic.forward_fc(P + off_c, nullptr, B, ws_critic, nullptr, sc, 0, ca));
   CPP_TRY(wait(sc, E_MU));
-  CPP_TRY(critic.forward_fc(P + off_c, mu, B, ws_critic, nullptr, sc, ca > 0 ? ca : 0));
-  CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, sc));
-  CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, sc));                       // tf.neg(...), :113
+  const bool tail = critic_tail_ok(critic);
+  if (tail) {
+    CPP_TRY(launch_critic_tail_fwd(critic, P + off_c, mu, B, ws_critic, nullptr, dqda, neg, sc));   // Q(s1, mu), dQ/da and tf.neg in one launch
+  } else {
+    CPP_TRY(critic.forward_fc(P + off_c, mu, B, ws_critic, nullptr, sc, ca > 0 ? ca : 0));
+    CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, ones, nullptr, dqda, sc));
+    CPP_TRY(launch_scale_copy(dqda, -1.f, (int64_t)B * A, neg, sc));                     // tf.neg(...), :113
+  }
   tr.mark("sc critic FC fwd @mu + dQ/da done", sc);
   CPP_TRY(record(E_DQDA, sc));
   // ---- target actor chain (sta) -> mu2, target critic chain (stc) -> q2                            :198-202
@@ -307,7 +312,8 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   CPP_TRY(actor.backward(P, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s0, 1, wgs[0], tcs[0], multi ? &aux[0] : nullptr));
   tr.mark("s0 actor backward (FC, conv3, conv2) done", s0);
   CPP_TRY(wait(sc, E_Q2));
-  CPP_TRY(critic.forward_fc(P + off_c, action, B, ws_critic, q, sc, ca > 0 ? ca : 0));   // Q(s1, a_batch): only the layers above the concat
+  if (tail) CPP_TRY(launch_critic_tail_fwd(critic, P + off_c, action, B, ws_critic, q, nullptr, nullptr, sc));
+  else CPP_TRY(critic.forward_fc(P + off_c, action, B, ws_critic, q, sc, ca > 0 ? ca : 0));   // Q(s1, a_batch): only the layers above the concat
   CPP_TRY(launch_td_mse(q, q2, reward, mask, cfg.discount, B, B_global, td, dq, buf.grads + off_loss, sc));
   tr.mark("sc critic FC @a + TD done", sc);
   CPP_TRY(critic.backward(P + off_c, s1, is_f16, m1, B, ws_critic, dq, buf.grads + off_c, nullptr, sc, 1, wgs[1], tcs[1], multi ? &aux[1] : nullptr));
@@ -336,7 +342,7 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   if (multi || use_graphs()) CPP_TRY(ensure_streams());
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
-  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | (g_conv1_split << 5)};
+  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | (g_conv1_split << 5) | (g_critic_tail << 6)};
   const int rc = run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
     return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, st);
   });

@@ -16,6 +16,7 @@ long long g_launch_count = 0;
 int g_cta_cap = 148;
 int g_tc_prepped = 0;
 int g_conv1_split = 1;     // the two conv1 passes of the DDPG step side by side on half of the SMs each (1) or one after the other on all (0)
+int g_critic_tail = 1;     // the pixel critic's [hidden2, action] -> hidden3 -> q head as one kernel per evaluation / backward (mlp.cu)
 int g_prep_hoist = 1;      // cpp_set_option("prep_hoist", 0): weight prep kernels stay in front of their main kernels (A/B timing)
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
@@ -96,6 +97,7 @@ int cpp_set_option(const char* name, int32_t value) {
   if (strcmp(name, "graphs") == 0) { set_step_options(-2, value); return CPP_OK; }
   if (strcmp(name, "prep_hoist") == 0) { g_prep_hoist = value != 0; return CPP_OK; }
   if (strcmp(name, "conv1_split") == 0) { g_conv1_split = value != 0; return CPP_OK; }
+  if (strcmp(name, "critic_tail") == 0) { g_critic_tail = value != 0; return CPP_OK; }
   set_error("unknown option `%s`", name);
   return CPP_ERR_INVALID;
   API_END

@@ -350,4 +350,163 @@ int launch_mlp_dgrad(const Net& net, const float* params, int B, void* ws_, cons
   return CPP_OK;
 }
 
+// ------------------------------------------------------------------------------------------ critic tail
+// The top of the pixel critic, hidden3 = relu([hidden2, action] . W3 + b3), q = hidden3 . wq + bq (ddpg_cartpole.py:168-171,
+// 180-184), is evaluated twice per step (at mu(s1) for dQ/da, at the batch action for the TD error) and sits on the step's
+// critical path between the actor's output and both backward chains.  As per-layer launches it is 4-8 dependent tiny kernels;
+// here ONE kernel does a whole evaluation (one warp per batch row, W3 in shared memory):
+//   forward : writes the action columns of the concat buffer, hidden3, q into the workspace (the weight gradients read them),
+//             q_out, and optionally dQ/da = W3[action rows] . (wq * relu'(hidden3)) and its negation (tf.neg, :113)
+//   backward: from dq, dTop = dq, dPre3 = dq * wq * relu'(hidden3), dXcat = (dPre3 . W3^T) * relu'(hidden2) in one launch
+constexpr int kTailThreads = 256;
+constexpr int kTailMaxH = 128, kTailMaxIn = 256;
+
+struct TailArgs {
+  float* xcat; int x_ld;            // [B][x_ld]: columns [0, D) = hidden2 output, [D, D + A) = action
+  const float* action;              // forward: [B][A] copied into xcat (NULL: already there)
+  const float* W3; const float* b3; // [D + A][H], [H]
+  const float* wq; const float* bq; // [H][1], [1]
+  float* h3; int h3_ld;             // [B][h3_ld] relu output
+  float* hq;                        // [B] q in the workspace
+  float* q_out; float* dqda; float* neg_dqda;   // optional
+  // backward
+  const float* dq;                  // [B]
+  float* dTop; float* dPre3; float* dXcat;      // [B], [B][H], [B][D + A]
+  int B, D, A, H;
+};
+
+__global__ void __launch_bounds__(kTailThreads) critic_tail_fwd_kernel(const __grid_constant__ TailArgs T) {
+  extern __shared__ float tsm[];
+  const int In = T.D + T.A, H = T.H, Hp = H | 1;
+  float* W = tsm;                                   // [In][Hp]
+  float* xs = W + (size_t)In * Hp;                  // [warps][In]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kTailThreads >> 5;
+  for (int i = tid; i < In * H; i += kTailThreads) W[(i / H) * Hp + (i % H)] = __ldg(T.W3 + i);
+  __syncthreads();
+  for (int b = blockIdx.x * nwarp + warp; b < T.B; b += gridDim.x * nwarp) {
+    float* x = xs + warp * In;
+    for (int i = lane; i < In; i += 32) {
+      float v;
+      if (i >= T.D && T.action != nullptr) { v = T.action[(size_t)b * T.A + (i - T.D)]; T.xcat[(size_t)b * T.x_ld + i] = v; }
+      else v = T.xcat[(size_t)b * T.x_ld + i];
+      x[i] = v;
+    }
+    __syncwarp();
+    float qacc = 0.f, da[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) da[k] = 0.f;
+    for (int j = lane; j < H; j += 32) {
+      float z = __ldg(T.b3 + j);
+      for (int i = 0; i < In; ++i) z = fmaf(x[i], W[i * Hp + j], z);
+      const float h = fmaxf(z, 0.f), wq = __ldg(T.wq + j);
+      T.h3[(size_t)b * T.h3_ld + j] = h;
+      qacc = fmaf(h, wq, qacc);
+      if (T.dqda != nullptr && z > 0.f) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (k < T.A) da[k] = fmaf(W[(T.D + k) * Hp + j], wq, da[k]);
+      }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      qacc += __shfl_xor_sync(0xffffffffu, qacc, sft);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (k < T.A) da[k] += __shfl_xor_sync(0xffffffffu, da[k], sft);
+    }
+    if (lane == 0) {
+      const float q = qacc + __ldg(T.bq);
+      T.hq[b] = q;
+      if (T.q_out != nullptr) T.q_out[b] = q;
+    }
+    if (T.dqda != nullptr && lane < T.A) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (k == lane) v = da[k];
+      T.dqda[(size_t)b * T.A + lane] = v;
+      if (T.neg_dqda != nullptr) T.neg_dqda[(size_t)b * T.A + lane] = -v;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kTailThreads) critic_tail_bwd_kernel(const __grid_constant__ TailArgs T) {
+  extern __shared__ float tsm[];
+  const int In = T.D + T.A, H = T.H, Hp = H | 1;
+  float* W = tsm;                                   // [In][Hp]
+  float* ds = W + (size_t)In * Hp;                  // [warps][H]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kTailThreads >> 5;
+  for (int i = tid; i < In * H; i += kTailThreads) W[(i / H) * Hp + (i % H)] = __ldg(T.W3 + i);
+  __syncthreads();
+  for (int b = blockIdx.x * nwarp + warp; b < T.B; b += gridDim.x * nwarp) {
+    float* d3 = ds + warp * H;
+    const float dq = T.dq[b];
+    if (lane == 0) T.dTop[b] = dq;                                   // q is linear
+    for (int j = lane; j < H; j += 32) {
+      const float g = T.h3[(size_t)b * T.h3_ld + j] > 0.f ? dq * __ldg(T.wq + j) : 0.f;
+      d3[j] = g;
+      T.dPre3[(size_t)b * H + j] = g;
+    }
+    __syncwarp();
+    for (int i = lane; i < In; i += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < H; ++j) acc = fmaf(d3[j], W[i * Hp + j], acc);
+      if (i < T.D && !(T.xcat[(size_t)b * T.x_ld + i] > 0.f)) acc = 0.f;      // ReLU of hidden2; the action columns pass
+      T.dXcat[(size_t)b * In + i] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+bool critic_tail_ok(const Net& net) {
+  const int ca = net.concat_at, last = net.n_fc - 1;
+  return g_critic_tail && fused_mlp_enabled() && ca >= 1 && last == ca + 1 && net.act[ca] == 1 && net.act[last] == 0 && net.out_dim[last] == 1 &&
+         net.act[ca - 1] == 1 && net.out_dim[ca] <= kTailMaxH && net.in_dim[ca] <= kTailMaxIn && net.action_dim <= 8;
+}
+
+static void tail_common(const Net& net, const float* params, int B, char* ws, const Net::Layout& L, TailArgs* T) {
+  const int ca = net.concat_at, last = net.n_fc - 1;
+  int ld;
+  T->xcat = const_cast<float*>(net.fc_input(L, ws, ca, &ld)); T->x_ld = ld;
+  T->W3 = params + net.off_fc_w[ca]; T->b3 = params + net.off_fc_b[ca];
+  T->wq = params + net.off_fc_w[last]; T->bq = params + net.off_fc_b[last];
+  T->h3 = reinterpret_cast<float*>(ws + L.h[ca]); T->h3_ld = net.out_ld[ca];
+  T->hq = reinterpret_cast<float*>(ws + L.h[last]);
+  T->B = B; T->D = net.in_dim[ca] - net.action_dim; T->A = net.action_dim; T->H = net.out_dim[ca];
+}
+
+static int tail_grid(int B) { return (int)std::min<int64_t>(ceil_div(B, kTailThreads / 32), 4 * sm_budget()); }
+
+int launch_critic_tail_fwd(const Net& net, const float* params, const float* action, int B, void* ws_, float* q_out, float* dqda,
+                           float* neg_dqda, cudaStream_t s) {
+  CPP_REQUIRE(critic_tail_ok(net), "critic tail kernel: unsupported head");
+  char* ws = reinterpret_cast<char*>(ws_);
+  const Net::Layout L = net.layout(B);
+  TailArgs T{};
+  tail_common(net, params, B, ws, L, &T);
+  T.action = action; T.q_out = q_out; T.dqda = dqda; T.neg_dqda = neg_dqda;
+  const size_t smem = ((size_t)(T.D + T.A) * (T.H | 1) + (size_t)(kTailThreads / 32) * (T.D + T.A)) * sizeof(float);
+  static bool configured = false;
+  if (!configured) { CPP_CHECK_CUDA(cudaFuncSetAttribute(critic_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); configured = true; }
+  critic_tail_fwd_kernel<<<tail_grid(B), kTailThreads, smem, s>>>(T);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
+int launch_critic_tail_bwd(const Net& net, const float* params, const float* dq, int B, void* ws_, cudaStream_t s) {
+  CPP_REQUIRE(critic_tail_ok(net), "critic tail kernel: unsupported head");
+  char* ws = reinterpret_cast<char*>(ws_);
+  const Net::Layout L = net.layout(B);
+  const int ca = net.concat_at, last = net.n_fc - 1;
+  TailArgs T{};
+  tail_common(net, params, B, ws, L, &T);
+  T.dq = dq;
+  T.dTop = reinterpret_cast<float*>(ws + L.dTop); T.dPre3 = reinterpret_cast<float*>(ws + L.dX[last]);
+  T.dXcat = reinterpret_cast<float*>(ws + L.dX[ca]);
+  const size_t smem = ((size_t)(T.D + T.A) * (T.H | 1) + (size_t)(kTailThreads / 32) * T.H) * sizeof(float);
+  static bool configured = false;
+  if (!configured) { CPP_CHECK_CUDA(cudaFuncSetAttribute(critic_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); configured = true; }
+  critic_tail_bwd_kernel<<<tail_grid(B), kTailThreads, smem, s>>>(T);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
 }  // namespace cpp

@@ -312,13 +312,38 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
   }
   // gradient wrt the last pre-activation
   float* dcur = reinterpret_cast<float*>(ws + L.dTop);
-  if (!fused)
-  CPP_TRY(launch_act_grad(d_out, out_dim[last], reinterpret_cast<const float*>(ws + L.h[last]), out_ld[last], act[last], B,
-                          out_dim[last], dcur, out_dim[last], s));
   int dld = out_dim[last];
+  int i_first = last;
+  const bool tail = !fused && grads != nullptr && d_rep_extra == nullptr && critic_tail_ok(*this);
+  if (tail) {
+    // pixel critic: q and hidden3 backwards in one launch (dTop, dX[last], dX[concat_at]); their weight gradients follow
+    CPP_TRY(launch_critic_tail_bwd(*this, params, d_out, B, ws, s));
+    CPP_TRY(ready());
+    for (int i = last; i >= concat_at; --i) {
+      int xld;
+      const float* x = fc_input(L, ws, i, &xld);
+      const float* dpre = i == last ? reinterpret_cast<const float*>(ws + L.dTop) : reinterpret_cast<const float*>(ws + L.dX[last]);
+      const int pld = i == last ? out_dim[last] : in_dim[last];
+      GemmArgs g{};                                        // dW = x^T . dPre
+      g.A = x; g.lda = xld; g.transA = 1;
+      g.B = dpre; g.ldb = pld; g.transB = 0;
+      g.C = grads + off_fc_w[i]; g.ldc = out_dim[i];
+      g.M = in_dim[i]; g.N = out_dim[i]; g.K = B; g.epi = EPI_NONE;
+      CPP_TRY(launch_gemm(g, sw));
+      CPP_TRY(launch_colsum(dpre, pld, B, out_dim[i], grads + off_fc_b[i], sw));
+    }
+    dcur = reinterpret_cast<float*>(ws + L.dX[concat_at]);
+    dld = in_dim[concat_at];
+    if (d_action != nullptr)
+      CPP_TRY(launch_copy_cols(dcur + (dld - action_dim), dld, B, action_dim, d_action, action_dim, 0, s));
+    i_first = concat_at - 1;
+  } else if (!fused) {
+    CPP_TRY(launch_act_grad(d_out, out_dim[last], reinterpret_cast<const float*>(ws + L.h[last]), out_ld[last], act[last], B,
+                            out_dim[last], dcur, out_dim[last], s));
+  }
   const int stop_at = (grads == nullptr) ? concat_at : 0;   // only d_action wanted: stop once it is known
   if (fused) dcur = reinterpret_cast<float*>(ws + L.dX[0]);
-  for (int i = last; i >= stop_at && !fused; --i) {
+  for (int i = i_first; i >= stop_at && !fused; --i) {
     int xld;
     const float* x = fc_input(L, ws, i, &xld);
     if (grads != nullptr) {

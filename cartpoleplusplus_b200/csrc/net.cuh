@@ -106,6 +106,13 @@ int launch_mlp_forward(const Net& net, const float* params, const float* action,
 int launch_mlp_dgrad(const Net& net, const float* params, int B, void* ws, const float* d_out, int stop_at, int need_dx_first,
                      float* d_action, cudaStream_t s);
 
+// critic tail (mlp.cu): [hidden2, action] -> hidden3 -> q of the pixel critic in one launch per evaluation / per backward
+bool critic_tail_ok(const Net& net);
+int launch_critic_tail_fwd(const Net& net, const float* params, const float* action, int B, void* ws, float* q_out, float* dqda,
+                           float* neg_dqda, cudaStream_t s);
+// needs d_out [B] (= dq); leaves dTop, dX[last], dX[concat_at] in the workspace exactly like the per-layer path
+int launch_critic_tail_bwd(const Net& net, const float* params, const float* dq, int B, void* ws, cudaStream_t s);
+
 // elementwise.cu
 int64_t moments_scratch_doubles(int C);
 int launch_channel_moments(const void* x, int is_f16, int64_t n_pix_total, int C, double* scratch, float* mean_inv, cudaStream_t s);
