@@ -169,29 +169,51 @@ def run_native(args):
   rm.sampler.seed(0)                                   # np.random.seed(0) stream, identical on every rank
 
   G = dp.world_size
-  idx_pin = torch.empty(BATCH * G, dtype=torch.int64, pin_memory=True)
-  d_idx = torch.empty(BATCH * G, dtype=torch.int64, device=dev)
-  out = Batch(torch.empty((BATCH,) + SHAPE, dtype=torch.float16, device=dev), torch.empty((BATCH, 2), device=dev),
-              torch.empty((BATCH, 1), device=dev), torch.empty((BATCH, 1), device=dev),
-              torch.empty((BATCH,) + SHAPE, dtype=torch.float16, device=dev))
-  m1 = torch.empty(18, dtype=torch.float32, device=dev); m2 = torch.empty(18, dtype=torch.float32, device=dev)
-  copied = torch.cuda.Event()
+  # Two sets of batch buffers: the replay gather of step i+1 (a1, a2 and the whitening statistics) is enqueued on a second
+  # stream right after the training step i was launched and runs next to it; every step still does exactly one gather and
+  # one training step, in index-stream order.
+  gs = torch.cuda.Stream(device=dev)
+  idx_pin = [torch.empty(BATCH * G, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+  d_idx = [torch.empty(BATCH * G, dtype=torch.int64, device=dev) for _ in range(2)]
+  outs = [Batch(torch.empty((BATCH,) + SHAPE, dtype=torch.float16, device=dev), torch.empty((BATCH, 2), device=dev),
+                torch.empty((BATCH, 1), device=dev), torch.empty((BATCH, 1), device=dev),
+                torch.empty((BATCH,) + SHAPE, dtype=torch.float16, device=dev)) for _ in range(2)]
+  moms = [(torch.empty(18, dtype=torch.float32, device=dev), torch.empty(18, dtype=torch.float32, device=dev)) for _ in range(2)]
+  copied = [torch.cuda.Event() for _ in range(2)]      # the index vector left its pinned buffer
+  ready = [torch.cuda.Event() for _ in range(2)]       # gather + statistics of this buffer set are complete
+  free = [torch.cuda.Event() for _ in range(2)]        # the training step that read this buffer set is complete
+  pending = {}
+
+  def issue_gather(i):
+    k = i % 2
+    idxs = rm.random_indexes(BATCH * G)                                    # a1: host MT19937, bit exact
+    if i >= 2:
+      copied[k].synchronize()
+    idx_pin[k].copy_(torch.from_numpy(idxs))
+    with torch.cuda.stream(gs):
+      if i >= 2:
+        gs.wait_event(free[k])
+      d_idx[k].copy_(idx_pin[k], non_blocking=True)
+      copied[k].record(gs)
+      mine = d_idx[k][dp.rank * BATCH:(dp.rank + 1) * BATCH]
+      batch = rm.batch_at(idxs[dp.rank * BATCH:(dp.rank + 1) * BATCH], d_idxs=mine, out=outs[k])   # a2: gather kernel
+      rm.batch_moments(d_idx[k], 1, out=moms[k][0]); rm.batch_moments(d_idx[k], 2, out=moms[k][1])  # global-batch whitening statistics
+      ready[k].record(gs)
+    pending[i] = batch
 
   def step(i):
-    idxs = rm.random_indexes(BATCH * G)                                    # a1: host MT19937, bit exact
-    if i > 0:
-      copied.synchronize()
-    idx_pin.copy_(torch.from_numpy(idxs))
-    d_idx.copy_(idx_pin, non_blocking=True)
-    copied.record()
-    mine = d_idx[dp.rank * BATCH:(dp.rank + 1) * BATCH]
-    batch = rm.batch_at(idxs[dp.rank * BATCH:(dp.rank + 1) * BATCH], d_idxs=mine, out=out)      # a2: gather kernel
-    rm.batch_moments(d_idx, 1, out=m1); rm.batch_moments(d_idx, 2, out=m2)  # global-batch whitening statistics
-    eng.train_step(batch, moments=(m1, m2))                                # a3-a12
+    k = i % 2
+    if i not in pending:
+      issue_gather(i)
+    batch = pending.pop(i)
+    torch.cuda.current_stream().wait_event(ready[k])
+    eng.train_step(batch, moments=moms[k])                                 # a3-a12
+    free[k].record()
+    issue_gather(i + 1)
     if (i + 1) % BATCHES_PER_STEP == 0:
       eng.update_targets()                                                 # a13
 
-  def timed(fn, steps, warmup, clocks=None):
+  def timed(fn, steps, warmup, clocks=None, drain=None):
     for i in range(warmup):
       fn(i)
     if clocks:
@@ -202,6 +224,8 @@ def run_native(args):
     e0.record()
     for i in range(steps):
       fn(warmup + i)
+    if drain is not None:
+      drain()                               # work the steps put on other streams belongs to the timed region
     e1.record()
     torch.cuda.synchronize(); dp.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -209,8 +233,28 @@ def run_native(args):
     return float(ms.item()), lib.cpp_launch_count() - l0, (clocks.stop() if clocks else None)
 
   W = max(3, args.warmup)
+  if os.environ.get("BENCH_HOST_PROFILE"):
+    # diagnosis, not a bench value: is the loop host bound?  host clock before / after the final synchronize + cProfile
+    import cProfile, pstats
+    for i in range(10):
+      step(i)
+    torch.cuda.synchronize()
+    n = 300
+    t0 = time.perf_counter()
+    for i in range(n):
+      step(10 + i)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    sys.stderr.write("enqueue %.1f us/step, until the GPU is done %.1f us/step\n" % ((t1 - t0) / n * 1e6, (t2 - t0) / n * 1e6))
+    pr = cProfile.Profile(); pr.enable()
+    for i in range(n):
+      step(1000 + i)
+    pr.disable(); torch.cuda.synchronize()
+    pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
+    pending.clear()
   clocks = ClockSampler(dp.local_rank) if dp.rank == 0 else None
-  ms, launches, clk = timed(step, args.steps, W, clocks)
+  ms, launches, clk = timed(step, args.steps, W, clocks, drain=lambda: torch.cuda.current_stream().wait_stream(gs))
   value = G * args.steps / (ms / 1e3)
 
   # ---- e2e: host (pinned) batches through the reference-facing API, H2D + loss D2H inside the timed region
@@ -242,7 +286,8 @@ def run_native(args):
   roof = None
   if dp.rank == 0 and not args.skip_roofline:
     peaks = measured_peaks()
-    x = out.state_1
+    x = outs[0].state_1
+    m1 = moms[0][0]
     ws_ = [actor.get_variable("actor/conv1/weights"), critic.get_variable("critic/conv1/weights")]
     bs_ = [actor.get_variable("actor/conv1/biases"), critic.get_variable("critic/conv1/biases")]
     pooled = [torch.empty((BATCH, 32, 32, 10), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -288,7 +333,9 @@ def run_native(args):
                 dtype="f32 (conv MMAs: fp16 hi+lo operand pieces, fp32 accumulate; FC / elementwise fp32)", data="synthetic",
                 config=dict(workload=WORKLOAD, global_batch=BATCH * G, replay=N_REPLAY, batches_per_step=BATCHES_PER_STEP,
                             parallelism="dp%d" % G,
-                            l2="inputs larger than L2: each step gathers 37.7 MB of random rows from a 453 MB fp16 replay slab"),
+                            l2="inputs larger than L2: each step gathers 37.7 MB of random rows from a 453 MB fp16 replay slab",
+                            pipeline="the replay gather of step i+1 runs on a second stream next to training step i (two batch buffer sets); "
+                                     "each timed step = one gather + one training step"),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line))
   dp.close()

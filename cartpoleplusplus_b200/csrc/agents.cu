@@ -232,17 +232,18 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   if (!ones_ready) { CPP_TRY(launch_fill(ones, 1.f, cfg.max_batch, s0)); ones_ready = true; }
   CPP_TRY(record(E_START, s0));
   CPP_TRY(wait(sta, E_START));
-  // ---- weight preparation of every conv2 / conv3 pass of the step (fp16 weight pieces, 12 small kernels) on the critic
-  // chain's stream, which idles until conv1 is done: off the critical path of the four chains
+  // ---- weight preparation of every conv2 / conv3 pass of the step (fp16 weight pieces, 12 small kernels) on the two
+  // streams that idle until conv1 is done (critic and target critic chains): off the critical path of the four chains.
+  // (Next to the persistent conv1 CTAs a prep kernel only gets left-over issue slots, ~10 us each: two streams, six each.)
   struct PrepGuard { ~PrepGuard() { g_tc_prepped = 0; } } prep_guard;
-  enum { E_PREP = 8 };
+  enum { E_PREP = 8, E_PREP2 = 9 };
   if (multi && g_prep_hoist && actor.pixels && actor.tc_route(is_f16)) {
-    CPP_TRY(wait(sc, E_START));
+    CPP_TRY(wait(sc, E_START)); CPP_TRY(wait(stc, E_START));
     CPP_TRY(actor.prep_trunk_tc(P, B, tcs[0], true, sc));
-    CPP_TRY(critic.prep_trunk_tc(P + off_c, B, tcs[1], true, sc));
+    CPP_TRY(critic.prep_trunk_tc(P + off_c, B, tcs[1], true, stc));
     CPP_TRY(actor.prep_trunk_tc(T, B, tcs[2], false, sc));
-    CPP_TRY(critic.prep_trunk_tc(T + off_c, B, tcs[3], false, sc));
-    CPP_TRY(record(E_PREP, sc));
+    CPP_TRY(critic.prep_trunk_tc(T + off_c, B, tcs[3], false, stc));
+    CPP_TRY(record(E_PREP, sc)); CPP_TRY(record(E_PREP2, stc));
     g_tc_prepped = 1;
   }
   cudaStream_t sx = g_conv1_split ? sta : s0;                    // stream of the conv1 pass over state_2
@@ -270,7 +271,10 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   CPP_TRY(record(E_TA, sx));                                     // conv1(s2) done: the target chains may start
   CPP_TRY(wait(stc, E_TA));
   if (sx != sta) CPP_TRY(wait(sta, E_TA));
-  if (g_tc_prepped) { CPP_TRY(wait(s0, E_PREP)); CPP_TRY(wait(sta, E_PREP)); CPP_TRY(wait(stc, E_PREP)); }
+  if (g_tc_prepped) {
+    CPP_TRY(wait(s0, E_PREP)); CPP_TRY(wait(sta, E_PREP)); CPP_TRY(wait(stc, E_PREP));
+    CPP_TRY(wait(s0, E_PREP2)); CPP_TRY(wait(sta, E_PREP2)); CPP_TRY(wait(sc, E_PREP2));
+  }
   if (multi) g_cta_cap = kNumSMs / 4;
   // ---- actor chain (s0): trunk tail, FC stack -> mu                       ddpg_cartpole.py:90-100
   CPP_TRY(actor.forward_trunk(P, s1, is_f16, m1, B, ws_actor, s0, tc1, tc1 ? tcs[0] : nullptr));

@@ -22,17 +22,30 @@ def main():
   rs = np.random.RandomState(0)
   nets, eng, o = U.make_ddpg(shape, True, None, batch_size=B)
   b = U.Batch(*[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in _batch(rs, B, shape)])
+  moments = None
+  if len(sys.argv) > 4 and sys.argv[4] == "pinned":        # whitening statistics handed in, as bench.py does (per-slot sums)
+    import ctypes as C
+    lib = L.lib()
+    cin = int(np.prod(shape[2:]))
+    ms = []
+    for x in (b.state_1, b.state_2):
+      scratch = torch.zeros(int(lib.cpp_moments_scratch_doubles(cin)), dtype=torch.float64, device="cuda")
+      mi = torch.zeros(2 * cin, dtype=torch.float32, device="cuda")
+      L.check(lib.cpp_channel_moments(L.ptr(x), 1, C.c_int64(B * shape[0] * shape[1]), cin, L.ptr(scratch), L.ptr(mi), L.stream_ptr()))
+      ms.append(mi)
+    moments = tuple(ms)
+  step = (lambda: eng.train_step(b, moments=moments)) if moments is not None else (lambda: eng.train_step(b))
   res = {0: [], 1: []}
   for r in range(rounds):
     for v in (0, 1):
       L.check(L.lib().cpp_set_option(name.encode(), v))
       for _ in range(5):
-        eng.train_step(b)
+        step()
       torch.cuda.synchronize()
       a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       a.record()
       for _ in range(40):
-        eng.train_step(b)
+        step()
       e.record(); torch.cuda.synchronize()
       res[v].append(a.elapsed_time(e) / 40)
   print(json.dumps({"option": name, "config": cfg, "ms_per_step_0": float(np.median(res[0])), "ms_per_step_1": float(np.median(res[1])),
