@@ -275,7 +275,8 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
     CPP_TRY(wait(s0, E_PREP)); CPP_TRY(wait(sta, E_PREP)); CPP_TRY(wait(stc, E_PREP));
     CPP_TRY(wait(s0, E_PREP2)); CPP_TRY(wait(sta, E_PREP2)); CPP_TRY(wait(sc, E_PREP2));
   }
-  if (multi) g_cta_cap = kNumSMs / 4;
+  const int cap_fa = g_fwd_actor_sms, cap_fo = (kNumSMs - g_fwd_actor_sms) / 3;
+  if (multi) g_cta_cap = cap_fa;
   // ---- actor chain (s0): trunk tail, FC stack -> mu                       ddpg_cartpole.py:90-100
   CPP_TRY(actor.forward_trunk(P, s1, is_f16, m1, B, ws_actor, s0, tc1, tc1 ? tcs[0] : nullptr));
   tr.mark("s0 actor conv2/3 fwd done", s0);
@@ -283,6 +284,7 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   tr.mark("s0 actor FC fwd done (mu)", s0);
   CPP_TRY(record(E_MU, s0));
   // ---- critic chain (sc): trunk tail, FC below the action concat, then Q(s1, mu(s1)) and dQ/da      :161-184,220-222
+  if (multi) g_cta_cap = cap_fo;
   CPP_TRY(critic.forward_trunk(P + off_c, s1, is_f16, m1, B, ws_critic, sc, tc1, tc1 ? tcs[1] : nullptr));
   tr.mark("sc critic conv2/3 fwd done", sc);
   if (ca > 0) CPP_TRY(critic.forward_fc(P + off_c, nullptr, B, ws_critic, nullptr, sc, 0, ca));
@@ -309,13 +311,15 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   tr.mark("stc target critic done (q2)", stc);
   CPP_TRY(record(E_Q2, stc));
   // ---- backward chains: actor on s0, critic on sc
-  if (multi) g_cta_cap = kNumSMs / 2;
+  const int cap_critic = g_bwd_critic_sms, cap_actor = kNumSMs - g_bwd_critic_sms;
+  if (multi) g_cta_cap = cap_actor;
   CPP_TRY(wait(s0, E_DQDA));
   aux[0].used = aux[1].used = false;
-  aux[0].cta_cap = aux[1].cta_cap = kNumSMs / 2;
+  aux[0].cta_cap = cap_actor; aux[1].cta_cap = cap_critic;
   CPP_TRY(actor.backward(P, s1, is_f16, m1, B, ws_actor, neg, buf.grads, nullptr, s0, 1, wgs[0], tcs[0], multi ? &aux[0] : nullptr));
   tr.mark("s0 actor backward (FC, conv3, conv2) done", s0);
   CPP_TRY(wait(sc, E_Q2));
+  if (multi) g_cta_cap = cap_critic;
   if (tail) CPP_TRY(launch_critic_tail_fwd(critic, P + off_c, action, B, ws_critic, q, nullptr, nullptr, sc));
   else CPP_TRY(critic.forward_fc(P + off_c, action, B, ws_critic, q, sc, ca > 0 ? ca : 0));   // Q(s1, a_batch): only the layers above the concat
   CPP_TRY(launch_td_mse(q, q2, reward, mask, cfg.discount, B, B_global, td, dq, buf.grads + off_loss, sc));
@@ -346,7 +350,7 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   if (multi || use_graphs()) CPP_TRY(ensure_streams());
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, nullptr};
-  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | (g_conv1_split << 5) | (g_critic_tail << 6)};
+  const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | (g_conv1_split << 5) | (g_critic_tail << 6) | (g_bwd_critic_sms << 8) | (g_fwd_actor_sms << 16)};
   const int rc = run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
     return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, st);
   });

@@ -26,6 +26,8 @@ extern long long g_launch_count;    // kernels launched by this library (capi.cu
 extern int g_tc_prepped;           // 1 while the agent has already run Net::prep_trunk_tc for this step (the trunk launches skip their weight prep)
 extern int g_prep_hoist;
 extern int g_critic_tail;
+extern int g_bwd_critic_sms;
+extern int g_fwd_actor_sms;
 extern int g_conv1_split;
 extern int g_cta_cap;               // SMs a persistent kernel may occupy (agents lower it while independent chains share the GPU)
 static inline int sm_budget() { return g_cta_cap < 1 ? 1 : (g_cta_cap > 148 ? 148 : g_cta_cap); }

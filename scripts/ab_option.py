@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """A/B timing of a cpp_set_option switch on ONE box, interleaved so that clock / box differences cancel:
-  python scripts/ab_option.py prep_hoist [c3|c5] [rounds]
-prints the median ms/step of the fused DDPG step (device-resident batch, CUDA events) for value 0 and 1."""
+  python scripts/ab_option.py prep_hoist [c3|c5] [rounds] [pinned|computed] [values ...]
+prints the median ms/step of the fused DDPG step (device-resident batch, CUDA events) per option value (default 0 and 1);
+`pinned`: whitening statistics handed in, as bench.py does."""
 import json
 import os
 import sys
@@ -35,9 +36,10 @@ def main():
       ms.append(mi)
     moments = tuple(ms)
   step = (lambda: eng.train_step(b, moments=moments)) if moments is not None else (lambda: eng.train_step(b))
-  res = {0: [], 1: []}
+  values = [int(v) for v in sys.argv[5:]] or [0, 1]
+  res = {v: [] for v in values}
   for r in range(rounds):
-    for v in (0, 1):
+    for v in values:
       L.check(L.lib().cpp_set_option(name.encode(), v))
       for _ in range(5):
         step()
@@ -48,8 +50,8 @@ def main():
         step()
       e.record(); torch.cuda.synchronize()
       res[v].append(a.elapsed_time(e) / 40)
-  print(json.dumps({"option": name, "config": cfg, "ms_per_step_0": float(np.median(res[0])), "ms_per_step_1": float(np.median(res[1])),
-                    "all_0": [round(x, 4) for x in res[0]], "all_1": [round(x, 4) for x in res[1]]}))
+  print(json.dumps({"option": name, "config": cfg, "median_ms_per_step": {str(v): round(float(np.median(res[v])), 4) for v in values},
+                    "all": {str(v): [round(x, 4) for x in res[v]] for v in values}}))
 
 
 if __name__ == "__main__":

@@ -329,3 +329,33 @@ def test_ddpg_fused_step_streams_and_graph_replay():
   for k in (1, 3, 4, 5, 6):                                                # 5, 6: one GEMM per FC layer instead of the fused stacks
     U.assert_close(outs[k][:-4], outs[0][:-4], tol=2e-6, what="mode %d vs single-stream eager" % k)
     U.assert_close(outs[k][-4], outs[0][-4], tol=2e-6, what="loss")
+
+
+def test_ddpg_schedule_switches_do_not_change_results():
+  """cpp_set_option switches of the fused step's schedule (weight-prep hoisting, conv1 passes side by side or in sequence, the
+  fused critic tail, SM budgets of the chains) change WHEN and WHERE work runs, not what is computed"""
+  shape, B = (32, 32, 3, 1, 3), 32
+  P, batch = _oracle_ddpg(shape, True, B, 22)
+  values = {k: v.numpy() for k, v in P.items()}
+  dev_batch = U.Batch(*[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in batch])
+  defaults = dict(prep_hoist=1, conv1_split=1, critic_tail=1, bwd_critic_sms=74, fwd_actor_sms=37)
+  variants = [dict(), dict(prep_hoist=0), dict(conv1_split=0), dict(critic_tail=0), dict(bwd_critic_sms=100, fwd_actor_sms=60),
+              dict(prep_hoist=0, conv1_split=0, critic_tail=0)]
+  outs = []
+  try:
+    for var in variants:
+      for k, v in dict(defaults, **var).items():
+        _set_opt(k, v)
+      nets, eng, o = U.make_ddpg(shape, True, values, batch_size=B)
+      for i in range(4):
+        eng.train_step(dev_batch)
+        if i == 1:
+          eng.update_targets()
+      torch.cuda.synchronize()
+      outs.append(torch.cat([eng.buffers["params"], eng.buffers["target_params"], eng.buffers["grads"]]).cpu().numpy())
+  finally:
+    for k, v in defaults.items():
+      _set_opt(k, v)
+  for k in range(1, len(variants)):
+    U.assert_close(outs[k][:-4], outs[0][:-4], tol=2e-6, what="variant %s vs default" % variants[k])
+    U.assert_close(outs[k][-4], outs[0][-4], tol=2e-6, what="loss")
