@@ -1,5 +1,6 @@
 """Agent-level engines: own the flat device buffers (torch tensors as containers) and drive the step
 functions of libcartpolepp.  One engine per agent; the Network objects of base_network.py are views."""
+import os
 import ctypes as C
 import numpy as np
 import torch
@@ -97,6 +98,7 @@ class EngineBase(object):
     self._slot = 0
     self.stage = self._stagers[0]
     self._copy_stream = None
+    self._copy_stream2 = None
     self._slot_free = [None, None]       # event: the compute stream is done reading this slot
     self._prefetched = None              # (batch object, staged tensors, copy-done event, slot)
     self.parts = {}           # part name -> (buffer name, offset, size)
@@ -120,14 +122,29 @@ class EngineBase(object):
     the step that is computing now; the next train_step(batch) called with this very object uses the staged copy"""
     if self._copy_stream is None:
       self._copy_stream = torch.cuda.Stream(device=self.device)
+      # CARTPOLEPP_COPY_STREAMS=2: state_2 travels on a second copy stream (two DMA engines share the link)
+      self._copy_stream2 = torch.cuda.Stream(device=self.device) if int(os.environ.get("CARTPOLEPP_COPY_STREAMS", "1")) >= 2 else None
     slot = 1 - self._slot
     st = self._stagers[slot]
-    cs = self._copy_stream
+    cs, cs2 = self._copy_stream, self._copy_stream2
     if self._slot_free[slot] is not None:
       cs.wait_event(self._slot_free[slot])          # a step that read this slot must have finished with it
+      if cs2 is not None:
+        cs2.wait_event(self._slot_free[slot])
+    s2 = None
+    if cs2 is not None:
+      with torch.cuda.stream(cs2):
+        s2 = st("s2", batch.state_2)
+        done2 = torch.cuda.Event()
+        done2.record(cs2)
     with torch.cuda.stream(cs):
-      staged = (st("s1", batch.state_1), st("a", batch.action, torch.float32), st("r", batch.reward, torch.float32),
-                st("m", batch.terminal_mask, torch.float32), st("s2", batch.state_2))
+      s1 = st("s1", batch.state_1)
+      if s2 is None:
+        s2 = st("s2", batch.state_2)
+      small = (st("a", batch.action, torch.float32), st("r", batch.reward, torch.float32), st("m", batch.terminal_mask, torch.float32))
+      if cs2 is not None:
+        cs.wait_event(done2)
+      staged = (s1,) + small + (s2,)
       done = torch.cuda.Event()
       done.record(cs)
     self._prefetched = (batch, staged, done, slot)
