@@ -152,13 +152,18 @@ def _np(x):
 
 def ddpg_params(rs, shape, pixels, perturb_targets=True, **kw):
   P = {}
-  a = no.ddpg_actor("actor", shape, pixels, kw.get("actor_hidden", "100,100,50"))
-  c = no.ddpg_critic("critic", shape, pixels, kw.get("critic_hidden", "100,100,50"))
+  bn = bool(kw.get("batch_norm", False))
+  a = no.ddpg_actor("actor", shape, pixels, kw.get("actor_hidden", "100,100,50"), batch_norm=bn)
+  c = no.ddpg_critic("critic", shape, pixels, kw.get("critic_hidden", "100,100,50"), batch_norm=bn)
   for d in (a, c):
     P.update(no.init_params(d, rs))
   # realistic non-zero biases / bigger action head so every gradient path is exercised
   for k in list(P):
-    if k.endswith("biases"):
+    if k.endswith("/moving_mean"):       # the reference never moves them off 0 / 1; off-default values pin that inference reads them
+      P[k] = torch.tensor(rs.uniform(-0.05, 0.05, tuple(P[k].shape)).astype(np.float32), dtype=torch.float64)
+    if k.endswith("/moving_variance"):
+      P[k] = torch.tensor(rs.uniform(0.8, 1.2, tuple(P[k].shape)).astype(np.float32), dtype=torch.float64)
+    if k.endswith("biases") or k.endswith("/beta"):
       P[k] = torch.tensor(rs.uniform(-0.1, 0.1, tuple(P[k].shape)).astype(np.float32), dtype=torch.float64)
     if k == "actor/output_action/weights":
       P[k] = torch.tensor(rs.uniform(-0.3, 0.3, tuple(P[k].shape)).astype(np.float32), dtype=torch.float64)
@@ -171,13 +176,13 @@ def ddpg_params(rs, shape, pixels, perturb_targets=True, **kw):
   return P
 
 
-def golden_ddpg(name, shape, pixels, B, seed, sparse=False):
+def golden_ddpg(name, shape, pixels, B, seed, sparse=False, batch_norm=False):
   rs = np.random.RandomState(seed)
-  P = ddpg_params(rs, shape, pixels)
-  out = {"meta": json.dumps(dict(state_shape=shape, pixels=pixels, B=B, seed=seed, sparse=sparse))}
+  P = ddpg_params(rs, shape, pixels, batch_norm=batch_norm)
+  out = {"meta": json.dumps(dict(state_shape=shape, pixels=pixels, B=B, seed=seed, sparse=sparse, batch_norm=bool(batch_norm)))}
   for k, v in P.items():
     out["P0/" + k] = v.numpy().astype(np.float32)
-  o = no.DDPGOracle(shape, pixels, P)
+  o = no.DDPGOracle(shape, pixels, P, batch_norm=batch_norm)
   for step in range(2):
     batch = _batch(rs, B, shape, sparse)
     for f, v in zip(("s1", "a", "r", "m", "s2"), batch):
@@ -280,7 +285,13 @@ def main():
   golden_naf("naf_pixel", (16, 16, 3, 2, 1), True, 8, 24, "Adam", {"learning_rate": 0.01})
   golden_naf("naf_lowdim", (3, 2, 7), False, 16, 25, "Momentum", {"learning_rate": 0.01, "momentum": 0.9})
   golden_naf_shared()
+  golden_batch_norm()
   golden_lrpg()
+
+
+def golden_batch_norm():
+  """--use-batch-norm (base_network.py:74-79): oracle-side vectors for the round that builds the kernels"""
+  golden_ddpg("ddpg_pixel_bn", (16, 16, 3, 1, 2), True, 8, 28, batch_norm=True)
 
 
 def golden_naf_shared():

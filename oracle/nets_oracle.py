@@ -9,6 +9,10 @@ fp64 = truth; fp32 = the "reference CPU path" that bench.py times.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
+Optional graph variants restated here: --share-input-state-representation (naf_cartpole.py:151-154,176-179) and
+--use-batch-norm (base_network.py:74-79 + slim.batch_norm defaults, Appendix A-5: batch statistics under the global
+IS_TRAINING flag in every network of a train op, never-updated moving statistics in inference).
+
 Reference defects at HEAD are resolved as SURVEY.md Appendix C fixes them (C-1: opts=None means
 no dropout; C-2: the pixel critic flattens the conv trunk before hidden1).
 """
@@ -26,8 +30,9 @@ FC = collections.namedtuple("FC", "scope out act")          # act in {'relu','ta
 class NetDef(object):
   """One reference network: optional conv trunk -> flatten -> FC stack (optional action concat)."""
 
-  def __init__(self, ns, state_shape, pixels, fc, concat_at=None, action_dim=0):
+  def __init__(self, ns, state_shape, pixels, fc, concat_at=None, action_dim=0, batch_norm=False):
     self.ns, self.state_shape, self.pixels = ns, tuple(state_shape), bool(pixels)
+    self.batch_norm = bool(batch_norm) and bool(pixels)      # --use-batch-norm only touches the conv layers, base_network.py:74-79
     self.fc, self.concat_at, self.action_dim = list(fc), concat_at, action_dim
     if pixels:
       H, W = state_shape[0], state_shape[1]
@@ -48,7 +53,14 @@ class NetDef(object):
       cin = self.cin
       for name, k in (("conv1", 5), ("conv2", 5), ("conv3", 3)):   # base_network.py:103-123
         out.append(("%s/%s/weights" % (self.ns, name), (k, k, cin, 10)))
-        out.append(("%s/%s/biases" % (self.ns, name), (10,)))
+        if self.batch_norm:
+          # slim.conv2d with a normalizer_fn creates no bias; slim.batch_norm (center=True, scale=False) creates beta and the
+          # two moving statistics, in this order (Appendix A-4, A-5)
+          out.append(("%s/%s/BatchNorm/beta" % (self.ns, name), (10,)))
+          out.append(("%s/%s/BatchNorm/moving_mean" % (self.ns, name), (10,)))
+          out.append(("%s/%s/BatchNorm/moving_variance" % (self.ns, name), (10,)))
+        else:
+          out.append(("%s/%s/biases" % (self.ns, name), (10,)))
         cin = 10
     d = self.feat
     for i, l in enumerate(self.fc):
@@ -62,6 +74,11 @@ class NetDef(object):
   def num_params(self):
     return sum(int(np.prod(s)) for _, s in self.var_shapes())
 
+  def trainable_names(self):
+    """tf.trainable_variables of the namespace: the moving statistics are variables (the target update copies them,
+    base_network.py:25-26) but not trainable"""
+    return [n for n, _ in self.var_shapes() if "/moving_" not in n]
+
 
 def _hidden(sizes):
   if isinstance(sizes, str):
@@ -69,35 +86,35 @@ def _hidden(sizes):
   return [FC("h%d" % i, s, "relu") for i, s in enumerate(sizes)]   # base_network.py:63-68
 
 
-def ddpg_actor(ns, state_shape, pixels, hidden="100,100,50", action_dim=2):
+def ddpg_actor(ns, state_shape, pixels, hidden="100,100,50", action_dim=2, batch_norm=False):
   """ddpg_cartpole.py:90-100"""
-  return NetDef(ns, state_shape, pixels, _hidden(hidden) + [FC("output_action", action_dim, "tanh")])
+  return NetDef(ns, state_shape, pixels, _hidden(hidden) + [FC("output_action", action_dim, "tanh")], batch_norm=batch_norm)
 
 
-def ddpg_critic(ns, state_shape, pixels, hidden="100,100,50", action_dim=2):
+def ddpg_critic(ns, state_shape, pixels, hidden="100,100,50", action_dim=2, batch_norm=False):
   """ddpg_cartpole.py:161-184 (pixel branch repaired per Appendix C-2)"""
   if pixels:
     fc = [FC("hidden1", 200, "relu"), FC("hidden2", 50, "relu"), FC("hidden3", 50, "relu"),
           FC("q_value", 1, None)]
-    return NetDef(ns, state_shape, True, fc, concat_at=2, action_dim=action_dim)
+    return NetDef(ns, state_shape, True, fc, concat_at=2, action_dim=action_dim, batch_norm=batch_norm)
   return NetDef(ns, state_shape, False, _hidden(hidden) + [FC("q_value", 1, None)],
                 concat_at=0, action_dim=action_dim)
 
 
-def naf_value(ns, state_shape, pixels, hidden="100,50"):
+def naf_value(ns, state_shape, pixels, hidden="100,50", batch_norm=False):
   """naf_cartpole.py:96-109"""
-  return NetDef(ns, state_shape, pixels, _hidden(hidden) + [FC("fc", 1, None)])
+  return NetDef(ns, state_shape, pixels, _hidden(hidden) + [FC("fc", 1, None)], batch_norm=batch_norm)
 
 
-def naf_mu(state_shape, pixels, hidden="100,50", action_dim=2):
+def naf_mu(state_shape, pixels, hidden="100,50", action_dim=2, batch_norm=False):
   """naf_cartpole.py:147-161"""
-  return NetDef("naf/output_action", state_shape, pixels, _hidden(hidden) + [FC("fc", action_dim, "tanh")])
+  return NetDef("naf/output_action", state_shape, pixels, _hidden(hidden) + [FC("fc", action_dim, "tanh")], batch_norm=batch_norm)
 
 
-def naf_l(state_shape, pixels, hidden="100,50", action_dim=2):
+def naf_l(state_shape, pixels, hidden="100,50", action_dim=2, batch_norm=False):
   """naf_cartpole.py:172-184"""
   return NetDef("naf/l_values", state_shape, pixels,
-                _hidden(hidden) + [FC("fc", action_dim * (action_dim + 1) // 2, None)])
+                _hidden(hidden) + [FC("fc", action_dim * (action_dim + 1) // 2, None)], batch_norm=batch_norm)
 
 
 def naf_shared_heads(rep_dim, action_dim=2):
@@ -118,8 +135,10 @@ def init_params(netdef, rs, dtype=torch.float64):
   parity tests always inject weights; this is only a generator of plausible values."""
   P = collections.OrderedDict()
   for name, shape in netdef.var_shapes():
-    if name.endswith("biases"):
-      v = np.zeros(shape)
+    if name.endswith("biases") or name.endswith("/beta") or name.endswith("/moving_mean"):
+      v = np.zeros(shape)                       # zeros_initializer (slim defaults)
+    elif name.endswith("/moving_variance"):
+      v = np.ones(shape)                        # ones_initializer
     elif len(shape) == 4:
       kh, kw, ci, co = shape
       lim = math.sqrt(6.0 / (kh * kw * ci + kh * kw * co))
@@ -154,6 +173,42 @@ def whiten(x):
   return x * inv - mean * inv
 
 
+# base_network.py:11: ONE global placeholder fed to every Session.run - True in the train ops, False in action_given /
+# check_loss / debug_values.  It reaches slim.batch_norm of EVERY network evaluated by that run, the target networks too.
+IS_TRAINING = True
+
+
+class is_training(object):
+  """with is_training(False): ... - the feed_dict={IS_TRAINING: ...} of one Session.run"""
+
+  def __init__(self, value):
+    self.value = bool(value)
+
+  def __enter__(self):
+    global IS_TRAINING
+    self.saved, IS_TRAINING = IS_TRAINING, self.value
+
+  def __exit__(self, *exc):
+    global IS_TRAINING
+    IS_TRAINING = self.saved
+
+
+BN_EPSILON = 1e-3      # slim.batch_norm default epsilon; decay 0.999 is irrelevant: UPDATE_OPS never run (Appendix A-5)
+
+
+def batch_norm(x, beta, moving_mean, moving_variance):
+  """slim.batch_norm(center=True, scale=False, epsilon=1e-3) on an NCHW tensor (Appendix A-5).  Training: per-channel batch
+  mean and POPULATION variance over (B, H, W), gradients flow through both.  Inference: the moving statistics, which the
+  reference never updates (it never runs the UPDATE_OPS collection), i.e. their initial 0 / 1 or whatever a target copy put there."""
+  if IS_TRAINING:
+    mean = x.mean(dim=(0, 2, 3))
+    var = ((x - mean[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))
+  else:
+    mean, var = moving_mean, moving_variance
+  inv = torch.rsqrt(var + BN_EPSILON)
+  return (x - mean[None, :, None, None]) * inv[None, :, None, None] + beta[None, :, None, None]
+
+
 def conv_trunk(nd, P, state):
   """base_network.py:73-127 -> (B, h, w, 10) NHWC"""
   B = state.shape[0]
@@ -161,8 +216,13 @@ def conv_trunk(nd, P, state):
   x = whiten(x).permute(0, 3, 1, 2)
   for name, k in (("conv1", 5), ("conv2", 5), ("conv3", 3)):
     W = P["%s/%s/weights" % (nd.ns, name)].permute(3, 2, 0, 1)   # HWIO -> OIHW
-    b = P["%s/%s/biases" % (nd.ns, name)]
-    x = F.relu(F.conv2d(x, W, b, stride=1, padding=k // 2))       # SAME, cross-correlation
+    if nd.batch_norm:                                             # no bias; BN in front of the ReLU (Appendix A-4)
+      pre = "%s/%s/BatchNorm/" % (nd.ns, name)
+      x = F.conv2d(x, W, None, stride=1, padding=k // 2)
+      x = F.relu(batch_norm(x, P[pre + "beta"], P[pre + "moving_mean"], P[pre + "moving_variance"]))
+    else:
+      b = P["%s/%s/biases" % (nd.ns, name)]
+      x = F.relu(F.conv2d(x, W, b, stride=1, padding=k // 2))     # SAME, cross-correlation
     x = F.max_pool2d(x, 2)                                        # stride 2, VALID (floor)
   return x.permute(0, 2, 3, 1)
 
@@ -191,6 +251,10 @@ def forward(nd, P, state, action=None, dtype=None, return_hidden=False, end_fc=N
 
 def _names(nd):
   return [n for n, _ in nd.var_shapes()]
+
+
+def _trainable(nd):
+  return nd.trainable_names()
 
 
 def _leaf(P, names):
@@ -251,7 +315,7 @@ def soft_update(target, source, coeff):
 
 def ddpg_actor_grads(actor, critic, P, s1):
   """ddpg_cartpole.py:102-119,220-222: grads = d mu/d theta . (-dQ(s1,mu(s1))/da), batch SUM."""
-  names = _names(actor)
+  names = _trainable(actor)
   leaves = _leaf(P, names)
   mu = forward(actor, P, s1)
   a_in = mu.detach().clone().requires_grad_(True)        # stop_gradient(actor.output_action) :162
@@ -277,7 +341,7 @@ def ddpg_critic_loss(critic, tactor, tcritic, P, batch, discount):
 
 
 def ddpg_critic_grads(critic, tactor, tcritic, P, batch, discount):
-  names = _names(critic)
+  names = _trainable(critic)
   leaves = _leaf(P, names)
   loss, td, q = ddpg_critic_loss(critic, tactor, tcritic, P, batch, discount)
   grads = torch.autograd.grad(loss, leaves)
@@ -290,30 +354,30 @@ class DDPGOracle(object):
   """The reference DDPG inner loop body (ddpg_cartpole.py:331-337) on explicit weights."""
 
   def __init__(self, state_shape, pixels, P, actor_hidden="100,100,50", critic_hidden="100,100,50",
-               action_dim=2, actor_lr=1e-3, critic_lr=1e-2, discount=0.99, clip=5.0, tau=1e-4):
-    self.actor = ddpg_actor("actor", state_shape, pixels, actor_hidden, action_dim)
-    self.critic = ddpg_critic("critic", state_shape, pixels, critic_hidden, action_dim)
-    self.tactor = ddpg_actor("target_actor", state_shape, pixels, actor_hidden, action_dim)
-    self.tcritic = ddpg_critic("target_critic", state_shape, pixels, critic_hidden, action_dim)
+               action_dim=2, actor_lr=1e-3, critic_lr=1e-2, discount=0.99, clip=5.0, tau=1e-4, batch_norm=False):
+    self.actor = ddpg_actor("actor", state_shape, pixels, actor_hidden, action_dim, batch_norm)
+    self.critic = ddpg_critic("critic", state_shape, pixels, critic_hidden, action_dim, batch_norm)
+    self.tactor = ddpg_actor("target_actor", state_shape, pixels, actor_hidden, action_dim, batch_norm)
+    self.tcritic = ddpg_critic("target_critic", state_shape, pixels, critic_hidden, action_dim, batch_norm)
     self.P = P
     self.actor_lr, self.critic_lr, self.discount, self.clip, self.tau = actor_lr, critic_lr, discount, clip, tau
 
   def actor_train(self, s1):
     g, mu, q, dqda = ddpg_actor_grads(self.actor, self.critic, self.P, s1)
     gc, norm = clip_by_global_norm(g, self.clip)
-    for n, gi in zip(_names(self.actor), gc):
+    for n, gi in zip(_trainable(self.actor), gc):
       self.P[n] = self.P[n] - self.actor_lr * gi
     return dict(grads=g, clipped=gc, norm=norm, mu=mu, q=q, dqda=dqda)
 
   def critic_train(self, batch):
     g, loss, td, q = ddpg_critic_grads(self.critic, self.tactor, self.tcritic, self.P, batch, self.discount)
     gc, norm = clip_by_global_norm(g, self.clip)
-    for n, gi in zip(_names(self.critic), gc):
+    for n, gi in zip(_trainable(self.critic), gc):
       self.P[n] = self.P[n] - self.critic_lr * gi
     return dict(grads=g, clipped=gc, norm=norm, loss=loss, td=td, q=q)
 
   def check_loss(self, batch):
-    with torch.no_grad():
+    with torch.no_grad(), is_training(False):                                          # ddpg_cartpole.py:239-248
       return ddpg_critic_loss(self.critic, self.tactor, self.tcritic, self.P, batch, self.discount)
 
   def update_targets(self, coeff=None):
@@ -323,7 +387,7 @@ class DDPGOracle(object):
         self.P[nd_] = soft_update(self.P[nd_], self.P[ns_], c)
 
   def action_given(self, state):
-    with torch.no_grad():
+    with torch.no_grad(), is_training(False):                                          # ddpg_cartpole.py:121-138
       return forward(self.actor, self.P, torch.as_tensor(np.asarray(state))[None])
 
 
@@ -359,18 +423,18 @@ class NAFOracle(object):
   """naf_cartpole.py:367-373 body: naf.train(batch) then (every batches_per_step) target update."""
 
   def __init__(self, state_shape, pixels, P, hidden="100,50", action_dim=2, discount=0.99, clip=5.0,
-               tau=1e-4, optimiser="GradientDescent", optimiser_args=None, share=False):
-    self.value = naf_value("value", state_shape, pixels, hidden)
-    self.tvalue = naf_value("target_value", state_shape, pixels, hidden)
+               tau=1e-4, optimiser="GradientDescent", optimiser_args=None, share=False, batch_norm=False):
+    self.value = naf_value("value", state_shape, pixels, hidden, batch_norm)
+    self.tvalue = naf_value("target_value", state_shape, pixels, hidden, batch_norm)
     self.share = bool(share)
     if self.share:
       self.mu, self.l = naf_shared_heads(self.value.fc[-2].out if len(self.value.fc) > 1 else self.value.feat, action_dim)
     else:
-      self.mu = naf_mu(state_shape, pixels, hidden, action_dim)
-      self.l = naf_l(state_shape, pixels, hidden, action_dim)
+      self.mu = naf_mu(state_shape, pixels, hidden, action_dim, batch_norm)
+      self.l = naf_l(state_shape, pixels, hidden, action_dim, batch_norm)
     self.P, self.A, self.discount, self.clip, self.tau = P, action_dim, discount, clip, tau
     self.opt = Optimiser(optimiser, **(optimiser_args or {"learning_rate": 1e-3}))
-    self.train_names = _names(self.value) + _names(self.mu) + _names(self.l)
+    self.train_names = _trainable(self.value) + _trainable(self.mu) + _trainable(self.l)
 
   def _loss(self, batch):
     s1, a, r, mask, s2 = batch
@@ -396,7 +460,7 @@ class NAFOracle(object):
     return dict(loss=loss.detach(), grads=grads, clipped=gc, norm=norm)
 
   def debug_values(self, batch):
-    with torch.no_grad():
+    with torch.no_grad(), is_training(False):                                          # naf_cartpole.py:274-284
       loss, l, L, V, A, V2 = self._loss(batch)
     return [np.squeeze(v.numpy()) for v in (l, loss, V, A, V2)]                         # :274-284
 
@@ -406,7 +470,7 @@ class NAFOracle(object):
       self.P[nd_] = soft_update(self.P[nd_], self.P[ns_], c)
 
   def action_given(self, state):
-    with torch.no_grad():
+    with torch.no_grad(), is_training(False):                                          # naf_cartpole.py:247-262
       x = torch.as_tensor(np.asarray(state))[None]
       if self.share:
         x = forward(self.value, self.P, x, end_fc=len(self.value.fc) - 1)

@@ -190,3 +190,114 @@ def test_oracle_reproduces_committed_shared_naf_golden(golden_dir, name):
     o.update_targets(0.05)
   for k, v in o.P.items():
     np.testing.assert_allclose(v.numpy(), g["Pfinal/" + k], rtol=1e-9, atol=1e-13)
+
+
+# ------------------------------------------------------------------ --use-batch-norm (oracle side)
+
+def _bn_net(rs, shape=(8, 8, 3, 1, 1)):
+  nd = no.ddpg_actor("actor", shape, True, "8,4", batch_norm=True)
+  P = no.init_params(nd, rs)
+  for k in list(P):
+    if k.endswith("/beta"):
+      P[k] = torch.tensor(rs.uniform(-0.2, 0.2, tuple(P[k].shape)))
+    if k.endswith("/moving_mean"):
+      P[k] = torch.tensor(rs.uniform(-0.1, 0.1, tuple(P[k].shape)))
+    if k.endswith("/moving_variance"):
+      P[k] = torch.tensor(rs.uniform(0.5, 1.5, tuple(P[k].shape)))
+  return nd, P
+
+
+def test_batch_norm_variables_and_trainables():
+  nd = no.ddpg_critic("critic", (16, 16, 3, 1, 2), True, batch_norm=True)
+  names = [n for n, _ in nd.var_shapes()]
+  assert names[:4] == ["critic/conv1/weights", "critic/conv1/BatchNorm/beta", "critic/conv1/BatchNorm/moving_mean",
+                       "critic/conv1/BatchNorm/moving_variance"]
+  assert not any(n.endswith("conv1/biases") or n.endswith("conv3/biases") for n in names)      # slim.conv2d drops the bias
+  assert "critic/hidden1/biases" in names                                                      # FC layers are untouched
+  tr = nd.trainable_names()
+  assert "critic/conv2/BatchNorm/beta" in tr and not any("/moving_" in n for n in tr)
+  assert len(names) - len(tr) == 6
+  # the flag does nothing for a low-dimensional state (no conv layers)
+  with_flag = [n for n, _ in no.ddpg_actor("a", (2, 2, 7), False, batch_norm=True).var_shapes()]
+  assert with_flag == [n for n, _ in no.ddpg_actor("a", (2, 2, 7), False).var_shapes()]
+
+
+def test_batch_norm_training_and_inference_formulas():
+  rs = np.random.RandomState(5)
+  x = torch.tensor(rs.randn(6, 10, 5, 4))
+  beta = torch.tensor(rs.randn(10)); mm = torch.tensor(rs.randn(10) * 0.1); mv = torch.tensor(rs.uniform(0.5, 2, 10))
+  xn = x.numpy()
+  y = no.batch_norm(x, beta, mm, mv).numpy()                       # IS_TRAINING defaults to True, like the train ops
+  mean = xn.mean(axis=(0, 2, 3)); var = xn.var(axis=(0, 2, 3))     # population variance
+  want = (xn - mean[None, :, None, None]) / np.sqrt(var + 1e-3)[None, :, None, None] + beta.numpy()[None, :, None, None]
+  np.testing.assert_allclose(y, want, rtol=1e-12, atol=1e-12)
+  with no.is_training(False):
+    y = no.batch_norm(x, beta, mm, mv).numpy()
+  want = (xn - mm.numpy()[None, :, None, None]) / np.sqrt(mv.numpy() + 1e-3)[None, :, None, None] + beta.numpy()[None, :, None, None]
+  np.testing.assert_allclose(y, want, rtol=1e-12, atol=1e-12)
+  assert no.IS_TRAINING is True                                    # the context manager restores the flag
+
+
+def test_batch_norm_gradients_flow_through_the_batch_statistics():
+  """central differences through whiten -> conv -> BN(batch stats) -> ReLU -> pool x3 -> FC, for a weight, a beta and (zero
+  gradient) a moving statistic"""
+  rs = np.random.RandomState(6)
+  nd, P = _bn_net(rs)
+  s = torch.tensor(rs.uniform(0, 1, (5,) + nd.state_shape))
+  co = torch.tensor(rs.randn(5, 2))
+
+  def f(Q):
+    return float((no.forward(nd, Q, s) * co).sum())
+  leaves = no._leaf(P, nd.trainable_names())
+  g = dict(zip(nd.trainable_names(), torch.autograd.grad((no.forward(nd, P, s) * co).sum(), leaves)))
+  for name, idx in (("actor/conv1/weights", 7), ("actor/conv2/weights", 123), ("actor/conv2/BatchNorm/beta", 3), ("actor/conv3/BatchNorm/beta", 0)):
+    Qp = {k: v.detach().clone() for k, v in P.items()}; Qm = {k: v.detach().clone() for k, v in P.items()}
+    Qp[name].view(-1)[idx] += 1e-6; Qm[name].view(-1)[idx] -= 1e-6
+    fd = (f(Qp) - f(Qm)) / 2e-6
+    assert abs(fd - float(g[name].reshape(-1)[idx])) <= 2e-6 * max(1.0, abs(fd)), (name, fd, float(g[name].reshape(-1)[idx]))
+  Qp = {k: v.detach().clone() for k, v in P.items()}
+  Qp["actor/conv1/BatchNorm/moving_mean"] += 1.0
+  assert f(Qp) == f({k: v.detach() for k, v in P.items()})        # training mode never reads the moving statistics
+
+
+def test_batch_norm_train_step_semantics():
+  """Appendix A-5: the moving statistics are never updated by training, are copied by the target update, and inference
+  (check_loss) reads them while the train ops - target networks included - use batch statistics"""
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nets_ddpg_pixel_bn.npz"))
+  meta = json.loads(str(g["meta"]))
+  assert meta["batch_norm"] is True
+  P = {k[3:]: torch.tensor(g[k].astype(np.float64)) for k in g.files if k.startswith("P0/")}
+  o = no.DDPGOracle(tuple(meta["state_shape"]), True, P, batch_norm=True)
+  batch = tuple(g["step0/%s" % f] for f in ("s1", "a", "r", "m", "s2"))
+  mm0 = o.P["critic/conv1/BatchNorm/moving_mean"].clone(); tm0 = o.P["target_critic/conv1/BatchNorm/moving_mean"].clone()
+  loss_inf, _, _ = o.check_loss(batch)
+  o.actor_train(batch[0]); rc = o.critic_train(batch)
+  assert torch.equal(o.P["critic/conv1/BatchNorm/moving_mean"], mm0)                     # UPDATE_OPS never run
+  assert abs(float(rc["loss"]) - float(loss_inf)) > 1e-6                                  # batch statistics != moving statistics
+  o.update_targets(0.25)
+  np.testing.assert_allclose(o.P["target_critic/conv1/BatchNorm/moving_mean"].numpy(), (tm0 - 0.25 * (tm0 - mm0)).numpy(), rtol=1e-15)
+  # the TD target inside critic_train used batch statistics in the TARGET networks: recompute it by hand in training mode
+  P2 = {k[3:]: torch.tensor(g[k].astype(np.float64)) for k in g.files if k.startswith("P0/")}
+  o2 = no.DDPGOracle(tuple(meta["state_shape"]), True, P2, batch_norm=True)
+  o2.actor_train(batch[0])
+  with torch.no_grad():
+    loss_train, _, _ = no.ddpg_critic_loss(o2.critic, o2.tactor, o2.tcritic, o2.P, batch, o2.discount)
+  np.testing.assert_allclose(float(loss_train), float(rc["loss"]), rtol=1e-12)
+
+
+def test_oracle_reproduces_committed_batch_norm_golden(golden_dir):
+  g = np.load(os.path.join(golden_dir, "nets_ddpg_pixel_bn.npz"))
+  meta = json.loads(str(g["meta"]))
+  P = {k[3:]: torch.tensor(g[k].astype(np.float64)) for k in g.files if k.startswith("P0/")}
+  o = no.DDPGOracle(tuple(meta["state_shape"]), meta["pixels"], P, batch_norm=True)
+  for step in range(2):
+    batch = tuple(g["step%d/%s" % (step, f)] for f in ("s1", "a", "r", "m", "s2"))
+    loss0, _, _ = o.check_loss(batch)
+    np.testing.assert_allclose(float(loss0), float(g["step%d/check_loss" % step]), rtol=1e-10)
+    ra = o.actor_train(batch[0])
+    np.testing.assert_allclose(torch.cat([x.reshape(-1) for x in ra["grads"]]).numpy(), g["step%d/actor_grads" % step], rtol=1e-9, atol=1e-13)
+    rc = o.critic_train(batch)
+    np.testing.assert_allclose(float(rc["loss"]), float(g["step%d/loss" % step]), rtol=1e-10)
+    o.update_targets(0.05)
+  for k, v in o.P.items():
+    np.testing.assert_allclose(v.numpy(), g["Pfinal/" + k], rtol=1e-9, atol=1e-13)
