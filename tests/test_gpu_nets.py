@@ -212,21 +212,28 @@ def test_naf_golden(golden_dir, name, tc):
   print(name, json.dumps(worst))
 
 
-def test_naf_full_size_c4_shard_vs_live_oracle():
-  """BASELINE config 4 (64x64, R=3, C=2 -> 18 channels): one 128-sample shard of the 512 batch"""
+@pytest.mark.parametrize("share", [False, True], ids=["three_trunks", "shared_representation"])
+def test_naf_full_size_c4_shard_vs_live_oracle(share):
+  """BASELINE config 4 (64x64, R=3, C=2 -> 18 channels): one 128-sample shard of the 512 batch; also with
+  --share-input-state-representation (one trunk, three heads)"""
   from oracle.make_golden import _batch
   shape, B = (64, 64, 3, 2, 3), 128
   rs = np.random.RandomState(91)
   P = {}
-  for d in (no.naf_value("value", shape, True), no.naf_mu(shape, True), no.naf_l(shape, True)):
+  value = no.naf_value("value", shape, True)
+  heads = no.naf_shared_heads(value.fc[-2].out) if share else (no.naf_mu(shape, True), no.naf_l(shape, True))
+  for d in (value,) + tuple(heads):
     P.update(no.init_params(d, rs))
+  if share:     # the reference's U(+-1e-3) action head would hide the heads' share of the trunk gradient
+    P["naf/output_action/fc/weights"] = torch.tensor(rs.uniform(-0.3, 0.3, (50, 2)).astype(np.float32), dtype=torch.float64)
   P.update(no.retarget({k: v for k, v in P.items() if k.startswith("value/")}, "value", "target_value"))
   batch = _batch(rs, B, shape)
   naf, nets, eng, o = U.make_naf(shape, True, {k: v.numpy() for k, v in P.items()}, batch_size=B,
-                                 optimiser="Momentum", optimiser_args={"learning_rate": 0.01, "momentum": 0.9})
-  orc = no.NAFOracle(shape, True, P, optimiser="Momentum", optimiser_args={"learning_rate": 0.01, "momentum": 0.9})
+                                 optimiser="Momentum", optimiser_args={"learning_rate": 0.01, "momentum": 0.9},
+                                 extra=["--share-input-state-representation"] if share else [])
+  orc = no.NAFOracle(shape, True, P, optimiser="Momentum", optimiser_args={"learning_rate": 0.01, "momentum": 0.9}, share=share)
   orc32 = no.NAFOracle(shape, True, {k: v.to(torch.float32) for k, v in P.items()}, optimiser="Momentum",
-                       optimiser_args={"learning_rate": 0.01, "momentum": 0.9})
+                       optimiser_args={"learning_rate": 0.01, "momentum": 0.9}, share=share)
   r, r32 = orc.train(batch), orc32.train(batch)
   eng.backward(U.Batch(*batch))
   gr = eng.buffers["grads"].cpu().numpy()
