@@ -204,16 +204,21 @@ def golden_ddpg(name, shape, pixels, B, seed, sparse=False, batch_norm=False):
   print("nets_%s" % name)
 
 
-def golden_naf(name, shape, pixels, B, seed, optimiser, optimiser_args, share=False):
+def golden_naf(name, shape, pixels, B, seed, optimiser, optimiser_args, share=False, batch_norm=False):
   rs = np.random.RandomState(seed)
   P = {}
-  value = no.naf_value("value", shape, pixels)
-  heads = no.naf_shared_heads(value.fc[-2].out) if share else (no.naf_mu(shape, pixels), no.naf_l(shape, pixels))
+  value = no.naf_value("value", shape, pixels, batch_norm=batch_norm)
+  heads = no.naf_shared_heads(value.fc[-2].out) if share else (no.naf_mu(shape, pixels, batch_norm=batch_norm),
+                                                               no.naf_l(shape, pixels, batch_norm=batch_norm))
   defs = [value] + list(heads)
   for d in defs:
     P.update(no.init_params(d, rs))
   for k in list(P):
-    if k.endswith("biases"):
+    if k.endswith("/moving_mean"):
+      P[k] = torch.tensor(rs.uniform(-0.05, 0.05, tuple(P[k].shape)).astype(np.float32), dtype=torch.float64)
+    if k.endswith("/moving_variance"):
+      P[k] = torch.tensor(rs.uniform(0.8, 1.2, tuple(P[k].shape)).astype(np.float32), dtype=torch.float64)
+    if k.endswith("biases") or k.endswith("/beta"):
       P[k] = torch.tensor(rs.uniform(-0.1, 0.1, tuple(P[k].shape)).astype(np.float32), dtype=torch.float64)
     if k == "naf/output_action/fc/weights":
       P[k] = torch.tensor(rs.uniform(-0.3, 0.3, tuple(P[k].shape)).astype(np.float32), dtype=torch.float64)
@@ -222,10 +227,10 @@ def golden_naf(name, shape, pixels, B, seed, optimiser, optimiser_args, share=Fa
     T[k] = torch.tensor((T[k].numpy() + rs.uniform(-0.02, 0.02, tuple(T[k].shape))).astype(np.float32), dtype=torch.float64)
   P.update(T)
   out = {"meta": json.dumps(dict(state_shape=shape, pixels=pixels, B=B, seed=seed, optimiser=optimiser, optimiser_args=optimiser_args,
-                                 share=bool(share)))}
+                                 share=bool(share), batch_norm=bool(batch_norm)))}
   for k, v in P.items():
     out["P0/" + k] = v.numpy().astype(np.float32)
-  o = no.NAFOracle(shape, pixels, P, optimiser=optimiser, optimiser_args=optimiser_args, share=share)
+  o = no.NAFOracle(shape, pixels, P, optimiser=optimiser, optimiser_args=optimiser_args, share=share, batch_norm=batch_norm)
   for step in range(3):
     batch = _batch(rs, B, shape)
     for f, v in zip(("s1", "a", "r", "m", "s2"), batch):
@@ -292,6 +297,10 @@ def main():
 def golden_batch_norm():
   """--use-batch-norm (base_network.py:74-79): oracle-side vectors for the round that builds the kernels"""
   golden_ddpg("ddpg_pixel_bn", (16, 16, 3, 1, 2), True, 8, 28, batch_norm=True)
+  # NAF with Momentum + batch norm as in exps/run_84.sh:11-15, here combined with the shared representation so that both graph
+  # variants meet (three heads on one batch-normalised trunk)
+  golden_naf("naf_pixel_bn_shared", (16, 16, 3, 2, 1), True, 8, 29, "Momentum", {"learning_rate": 0.01, "momentum": 0.9},
+             share=True, batch_norm=True)
 
 
 def golden_naf_shared():

@@ -301,3 +301,25 @@ def test_oracle_reproduces_committed_batch_norm_golden(golden_dir):
     o.update_targets(0.05)
   for k, v in o.P.items():
     np.testing.assert_allclose(v.numpy(), g["Pfinal/" + k], rtol=1e-9, atol=1e-13)
+
+
+def test_oracle_reproduces_committed_naf_batch_norm_shared_golden(golden_dir):
+  g = np.load(os.path.join(golden_dir, "nets_naf_pixel_bn_shared.npz"))
+  meta = json.loads(str(g["meta"]))
+  assert meta["batch_norm"] is True and meta["share"] is True
+  P = {k[3:]: torch.tensor(g[k].astype(np.float64)) for k in g.files if k.startswith("P0/")}
+  assert "value/conv1/BatchNorm/beta" in P and "value/conv1/biases" not in P and "target_value/conv3/BatchNorm/moving_variance" in P
+  o = no.NAFOracle(tuple(meta["state_shape"]), True, P, optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"],
+                   share=True, batch_norm=True)
+  assert not any("/moving_" in n for n in o.train_names)
+  for step in range(3):
+    batch = tuple(g["step%d/%s" % (step, f)] for f in ("s1", "a", "r", "m", "s2"))
+    dv = o.debug_values(batch)                                      # inference mode: moving statistics
+    np.testing.assert_allclose(dv[1], g["step%d/dbg_loss" % step], rtol=1e-10)
+    r = o.train(batch)                                              # training mode: batch statistics, target network included
+    np.testing.assert_allclose(float(r["loss"]), float(g["step%d/loss" % step]), rtol=1e-10)
+    assert abs(float(r["loss"]) - float(dv[1])) > 1e-9
+    np.testing.assert_allclose(torch.cat([x.reshape(-1) for x in r["grads"]]).numpy(), g["step%d/grads" % step], rtol=1e-9, atol=1e-13)
+    o.update_targets(0.05)
+  for k, v in o.P.items():
+    np.testing.assert_allclose(v.numpy(), g["Pfinal/" + k], rtol=1e-9, atol=1e-13)
