@@ -46,7 +46,13 @@ int64_t cpp_launch_count(void);
  * tensor-core kernels (default, also CARTPOLEPP_CONV1=tc), 0 through the exact-fp32 CUDA-core kernels, -1 = environment default;
  * "streams" = 1 forks the independent chains of a fused DDPG step onto side streams (CARTPOLEPP_STREAMS), "graphs" = 1
  * replays a fused step as one CUDA graph (CARTPOLEPP_GRAPHS); "fused_mlp" = 1 runs every FC stack as one forward and one
- * input-gradient launch instead of one GEMM per layer (CARTPOLEPP_FUSED_MLP); all default on */
+ * input-gradient launch instead of one GEMM per layer (CARTPOLEPP_FUSED_MLP; 1 = forward stacks (default), 2 = also the
+ * input-gradient chain); schedule of the fused DDPG step, all for A/B timing, results are unchanged up to summation order:
+ * "prep_hoist" = 1 (default) runs the conv2/conv3 weight-prep kernels of the whole step at its start on idle streams,
+ * "conv1_split" = 1 (default) runs the two conv1 passes side by side on half of the SMs each, "critic_tail" = 1 (default) evaluates
+ * the pixel critic's [hidden2, action] -> hidden3 -> q head (incl. dQ/da) as one kernel, "bwd_critic_sms" (default 74) and
+ * "fwd_actor_sms" (default 37) set the SM budgets of the critic's backward and the actor's forward chain.
+ * Process-wide state: set options from the (single) caller thread, between steps. */
 int cpp_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------ a1: index sampling (host)
