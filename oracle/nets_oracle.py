@@ -9,8 +9,8 @@ fp64 = truth; fp32 = the "reference CPU path" that bench.py times.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
-Optional graph variants restated here: --share-input-state-representation (naf_cartpole.py:151-154,176-179) and
---use-batch-norm (base_network.py:74-79 + slim.batch_norm defaults, Appendix A-5: batch statistics under the global
+Optional graph variants restated here: --share-input-state-representation (naf_cartpole.py:151-154,176-179),
+--use-dropout (base_network.py:69-70; masks are inputs, see `dropout`) and --use-batch-norm (base_network.py:74-79 + slim.batch_norm defaults, Appendix A-5: batch statistics under the global
 IS_TRAINING flag in every network of a train op, never-updated moving statistics in inference).
 
 Reference defects at HEAD are resolved as SURVEY.md Appendix C fixes them (C-1: opts=None means
@@ -227,6 +227,43 @@ def conv_trunk(nd, P, state):
   return x.permute(0, 2, 3, 1)
 
 
+# --use-dropout (base_network.py:69-70): slim.dropout(keep_prob=0.5, is_training=IS_TRAINING) after every layer that
+# hidden_layers_starting_at creates (scopes h0, h1, ...; NOT the pixel critic's hidden1-3, ddpg_cartpole.py:168-171, and not the
+# heads).  TF's random stream cannot be reproduced, so the masks are INPUTS here: {(namespace, scope): 0/1 tensor [B][out]},
+# one per graph node and Session.run - a node that feeds several consumers (the shared NAF representation) has ONE mask.
+DROPOUT_KEEP_PROB = 0.5
+DROPOUT_MASKS = None
+
+
+class dropout(object):
+  """with dropout(masks): ... - the masks the dropout ops of one Session.run draw (None: --use-dropout is off)"""
+
+  def __init__(self, masks):
+    self.masks = masks
+
+  def __enter__(self):
+    global DROPOUT_MASKS
+    self.saved, DROPOUT_MASKS = DROPOUT_MASKS, self.masks
+
+  def __exit__(self, *exc):
+    global DROPOUT_MASKS
+    DROPOUT_MASKS = self.saved
+
+
+def has_dropout(scope):
+  return len(scope) >= 2 and scope[0] == "h" and scope[1:].isdigit()
+
+
+def draw_dropout_masks(rs, nets, B, dtype=torch.float64):
+  """Bernoulli(keep_prob) masks for every dropout node of `nets` (a stand-in for TF's stream in tests and golden vectors)"""
+  out = {}
+  for nd in nets:
+    for l in nd.fc:
+      if has_dropout(l.scope):
+        out[(nd.ns, l.scope)] = torch.tensor((rs.rand(B, l.out) < DROPOUT_KEEP_PROB).astype(np.float64), dtype=dtype)
+  return out
+
+
 def forward(nd, P, state, action=None, dtype=None, return_hidden=False, end_fc=None):
   dtype = dtype or next(iter(P.values())).dtype
   state = torch.as_tensor(np.asarray(state)) if not torch.is_tensor(state) else state
@@ -246,6 +283,8 @@ def forward(nd, P, state, action=None, dtype=None, return_hidden=False, end_fc=N
       x = F.relu(x)
     elif l.act == "tanh":
       x = torch.tanh(x)
+    if DROPOUT_MASKS is not None and IS_TRAINING and has_dropout(l.scope):
+      x = x * DROPOUT_MASKS[(nd.ns, l.scope)].to(dtype) / DROPOUT_KEEP_PROB      # inverted dropout: kept units scaled by 1/keep_prob
   return x
 
 

@@ -323,3 +323,67 @@ def test_oracle_reproduces_committed_naf_batch_norm_shared_golden(golden_dir):
     o.update_targets(0.05)
   for k, v in o.P.items():
     np.testing.assert_allclose(v.numpy(), g["Pfinal/" + k], rtol=1e-9, atol=1e-13)
+
+
+# ------------------------------------------------------------------ --use-dropout (oracle side: masks are inputs)
+
+def test_dropout_nodes_masks_and_modes():
+  rs = np.random.RandomState(11)
+  shape, B = (2, 2, 7), 12
+  actor = no.ddpg_actor("actor", shape, False)
+  pix_critic = no.ddpg_critic("critic", (16, 16, 3, 1, 1), True)
+  masks = no.draw_dropout_masks(rs, [actor, pix_critic], B)
+  assert sorted(masks) == [("actor", "h0"), ("actor", "h1"), ("actor", "h2")]          # heads and the pixel critic's hidden1-3 have none
+  assert masks[("actor", "h2")].shape == (B, 50) and set(np.unique(masks[("actor", "h0")].numpy())) <= {0.0, 1.0}
+  P = no.init_params(actor, rs)
+  P["actor/output_action/weights"] = torch.tensor(rs.uniform(-0.3, 0.3, (50, 2)))
+  s = rs.uniform(-1, 1, (B,) + shape)
+  plain = no.forward(actor, P, s)
+  with no.dropout(masks):
+    dropped = no.forward(actor, P, s)
+    with no.is_training(False):
+      inference = no.forward(actor, P, s)
+  assert not torch.allclose(dropped, plain) and torch.equal(inference, plain)          # IS_TRAINING=False: identity
+  assert no.DROPOUT_MASKS is None
+  # explicit restatement of one layer chain: relu(xW+b) * mask / 0.5
+  x = torch.tensor(s).reshape(B, -1)
+  for i, sc in enumerate(("h0", "h1", "h2")):
+    x = torch.relu(x @ P["actor/%s/weights" % sc] + P["actor/%s/biases" % sc]) * masks[("actor", sc)] * 2.0
+  want = torch.tanh(x @ P["actor/output_action/weights"] + P["actor/output_action/biases"])
+  np.testing.assert_allclose(dropped.numpy(), want.numpy(), rtol=1e-13, atol=1e-15)
+  # all-ones masks with keep_prob 0.5 double every hidden activation; the mean over many masks is the plain activation
+  h0 = torch.relu(torch.tensor(s).reshape(B, -1) @ P["actor/h0/weights"] + P["actor/h0/biases"])
+  acc = torch.zeros_like(h0)
+  for _ in range(400):
+    acc += h0 * no.draw_dropout_masks(rs, [actor], B)[("actor", "h0")] / no.DROPOUT_KEEP_PROB
+  assert float((acc / 400 - h0).abs().max()) < 0.25 * float(h0.abs().max())
+
+
+def test_dropout_gradient_passes_only_through_kept_units():
+  rs = np.random.RandomState(12)
+  shape, B = (2, 2, 7), 5
+  critic = no.ddpg_critic("critic", shape, False)
+  P = no.init_params(critic, rs)
+  masks = no.draw_dropout_masks(rs, [critic], B)
+  s, a = rs.uniform(-1, 1, (B,) + shape), torch.tensor(rs.uniform(-1, 1, (B, 2)))
+  leaves = no._leaf(P, ["critic/h2/weights", "critic/q_value/weights"])
+  with no.dropout(masks):
+    q = no.forward(critic, P, s, a)
+    g_h2, g_q = torch.autograd.grad(q.sum(), leaves)
+  # a unit of h2 dropped for EVERY sample receives no gradient; the others do
+  dead = (masks[("critic", "h2")].sum(dim=0) == 0)
+  if bool(dead.any()):
+    assert float(g_h2[:, dead].abs().max()) == 0.0
+  assert float(g_h2[:, ~dead].abs().max()) > 0.0
+  # central difference on one weight of h1 under the same masks
+  name, idx = "critic/h1/weights", 17
+  def f(eps):
+    Q = {k: v.detach().clone() for k, v in P.items()}
+    Q[name].view(-1)[idx] += eps
+    with no.dropout(masks):
+      return float(no.forward(critic, Q, s, a).sum())
+  leaves = no._leaf(P, [name])
+  with no.dropout(masks):
+    g, = torch.autograd.grad(no.forward(critic, P, s, a).sum(), leaves)
+  fd = (f(1e-6) - f(-1e-6)) / 2e-6
+  assert abs(fd - float(g.reshape(-1)[idx])) <= 1e-6 * max(1.0, abs(fd))
