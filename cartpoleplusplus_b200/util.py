@@ -121,8 +121,22 @@ class SaverUtil(object):
     if e.buffers["params"].is_cuda:
       torch.cuda.current_stream().synchronize()
 
+  @staticmethod
+  def _is_writer():
+    """data parallel: replicas are bit-identical, so rank 0 alone writes; every rank restores"""
+    try:
+      import torch.distributed as dist
+      if dist.is_available() and dist.is_initialized():
+        return dist.get_rank() == 0
+    except ImportError:
+      pass
+    return int(os.environ.get("RANK", "0")) == 0
+
   def force_save(self):
     """force a save now."""
+    if not self._is_writer():
+      self.next_scheduled_save_time = time.time() + self.save_freq
+      return
     dts = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
     name = "ckpt.%s" % dts
     n = 1

@@ -171,3 +171,14 @@ def test_ddpg_restore_in_place_under_graph_replay(tmp_path):
   assert ptrs == {k: eng.buffers[k].data_ptr() for k in ptrs}
   b2 = [eng.train_step(b) for b in batches[1:]]
   assert a == b2 and torch.equal(end, eng.buffers["params"])
+
+
+def test_only_rank_zero_writes(tmp_path, monkeypatch):
+  monkeypatch.setenv("RANK", "1")
+  s = util.SaverUtil(_HostEngine(1), str(tmp_path), save_freq=3600)      # nothing to load, and a non-zero rank does not save
+  assert os.listdir(str(tmp_path)) == []
+  s.force_save()
+  assert os.listdir(str(tmp_path)) == []
+  monkeypatch.setenv("RANK", "0")
+  s.force_save()
+  assert "checkpoint" in os.listdir(str(tmp_path))
