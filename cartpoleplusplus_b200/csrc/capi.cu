@@ -19,6 +19,7 @@ int g_conv1_split = 1;     // the two conv1 passes of the DDPG step side by side
 int g_fwd_actor_sms = 37;  // SM budget of the actor's forward chain (mu is needed first); the other three chains share the rest
 int g_bwd_critic_sms = 74; // SM budget of the critic's backward chain in the fused DDPG step (the actor's gets the rest of the 148)
 int g_critic_tail = 1;     // the pixel critic's [hidden2, action] -> hidden3 -> q head as one kernel per evaluation / backward (mlp.cu)
+int g_wgrad_flush_steps = 32;     // the tensor-core accumulator truncates: 128-step chains cost 1.3e-5 on the conv1 weight gradient, 32 keep it at 5e-6 (profiles/r3/wgrad_flush.md)
 int g_prep_hoist = 1;      // cpp_set_option("prep_hoist", 0): weight prep kernels stay in front of their main kernels (A/B timing)
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
@@ -98,6 +99,7 @@ int cpp_set_option(const char* name, int32_t value) {
   if (strcmp(name, "streams") == 0) { set_step_options(value, -2); return CPP_OK; }
   if (strcmp(name, "graphs") == 0) { set_step_options(-2, value); return CPP_OK; }
   if (strcmp(name, "prep_hoist") == 0) { g_prep_hoist = value != 0; return CPP_OK; }
+  if (strcmp(name, "wgrad_flush_steps") == 0) { g_wgrad_flush_steps = value < 16 ? 16 : (value > 1024 ? 1024 : value); return CPP_OK; }
   if (strcmp(name, "conv1_split") == 0) { g_conv1_split = value != 0; return CPP_OK; }
   if (strcmp(name, "critic_tail") == 0) { g_critic_tail = value != 0; return CPP_OK; }
   if (strcmp(name, "fwd_actor_sms") == 0) { g_fwd_actor_sms = value < 16 ? 16 : (value > 100 ? 100 : value); return CPP_OK; }
@@ -369,7 +371,47 @@ int cpp_ddpg_action_given(cpp_ddpg* a, const void* state, int32_t is_f16, int32_
 }
 int cpp_ddpg_update_targets(cpp_ddpg* a, float coeff, void* stream) { API_BEGIN NEED(a); return a->a.update_targets(coeff, ST(stream)); API_END }
 
+static int debug_view(const Net& net, const char* ws_part, const void* ws_base, int kind, int index, int B, int64_t* out4) {
+  CPP_REQUIRE(ws_part != nullptr && ws_base != nullptr, "debug_view: buffers not bound");
+  CPP_REQUIRE(B >= 1, "debug_view: batch %d", B);
+  const Net::Layout L = net.layout(B);
+  size_t off = 0; int64_t per = 0, valid = 0;
+  if (kind == 0 || kind == 1) {
+    CPP_REQUIRE(net.pixels && index >= 0 && index < 3, "debug_view: conv layer %d of a %s network", index, net.pixels ? "pixel" : "low-dim");
+    off = kind == 0 ? L.amax[index] : L.pooled[index];
+    per = valid = (int64_t)net.conv[index].PH() * net.conv[index].PW() * kConvCout;
+  } else if (kind == 2) {
+    CPP_REQUIRE(index >= 0 && index < net.n_fc, "debug_view: FC layer %d", index);
+    off = L.h[index]; per = net.out_ld[index]; valid = net.out_dim[index];
+  } else {
+    set_error("debug_view: kind %d", kind);
+    return CPP_ERR_INVALID;
+  }
+  out4[0] = (int64_t)((ws_part - reinterpret_cast<const char*>(ws_base)) + (ptrdiff_t)off);
+  out4[1] = B; out4[2] = per; out4[3] = valid;
+  return CPP_OK;
+}
+int cpp_ddpg_debug_view(const cpp_ddpg* a, int32_t part, int32_t kind, int32_t index, int32_t B, int64_t* out4) {
+  API_BEGIN
+  NEED(a); NEED(out4);
+  CPP_REQUIRE(part >= 0 && part < 4, "debug_view: part %d", part);
+  const DDPG& d = a->a;
+  const char* ws[4] = {d.ws_actor, d.ws_critic, d.ws_target, d.ws_target2};
+  return debug_view((part & 1) ? d.critic : d.actor, ws[part], d.buf.workspace, kind, index, B, out4);
+  API_END
+}
+
 // ---------------------------------------------------------------- NAF
+int cpp_naf_debug_view(const cpp_naf* a, int32_t part, int32_t kind, int32_t index, int32_t B, int64_t* out4) {
+  API_BEGIN
+  NEED(a); NEED(out4);
+  CPP_REQUIRE(part >= 0 && part < 4, "debug_view: part %d", part);
+  const NAF& d = a->a;
+  const char* ws[4] = {d.ws_v, d.ws_m, d.ws_l, d.ws_t};
+  const Net* nets[4] = {&d.value, &d.mu, &d.l, &d.value};
+  return debug_view(*nets[part], ws[part], d.buf.workspace, kind, index, B, out4);
+  API_END
+}
 int cpp_naf_create(const cpp_naf_config* cfg, cpp_naf** out) {
   API_BEGIN
   NEED(cfg); NEED(out);

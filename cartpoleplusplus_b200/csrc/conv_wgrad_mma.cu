@@ -520,7 +520,7 @@ static int build_plan(int nets, int B, int H, int W, int C, int KS, Plan* P, int
   P->grid = std::max(1, std::min(P->total_bands, sm_budget() * occ));
   // bound the tensor-core accumulation chains to ~128 MMA steps between fp32 flushes
   const int steps_per_band = P->band_rows * (P->Wp / 16);
-  P->flush_every = std::max(1, 128 / steps_per_band);
+  P->flush_every = std::max(1, g_wgrad_flush_steps / steps_per_band);
   P->part_floats = P->NW * P->MT * P->NT * 128;
   return CPP_OK;
 }

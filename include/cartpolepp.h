@@ -244,6 +244,13 @@ int cpp_ddpg_check_loss(cpp_ddpg* a, const void* s1, const float* action, const 
                         float* loss, float* td, float* q, void* stream);
 int cpp_ddpg_action_given(cpp_ddpg* a, const void* state, int32_t is_f16, int32_t B, float* out_action, void* stream);
 int cpp_ddpg_update_targets(cpp_ddpg* a, float coeff, void* stream);
+/* parity instrumentation (tests/test_gpu_step_pinned.py): where one intermediate of the LAST step lives inside the bound
+ * workspace, so that the fp64 oracle can be evaluated with the routing (2x2 max-pool winners, ReLU gates) the GPU took.
+ * part: 0 actor, 1 critic, 2 target actor, 3 target critic.
+ * kind 0: routing bytes of conv layer `index` - u8 [B][PH][PW][10], 0..3 = winner of the window (dy*2+dx), 4 = ReLU closed;
+ * kind 1: pooled output of conv layer `index` - f32 [B][PH][PW][10];  kind 2: output of FC layer `index` - f32 [B][ld].
+ * out4 = {byte offset inside the workspace, B, elements per batch row, valid leading elements per row}. */
+int cpp_ddpg_debug_view(const cpp_ddpg* a, int32_t part, int32_t kind, int32_t index, int32_t B, int64_t* out4);
 
 /* ------------------------------------------------------------------ a10: NAF agent
  * NafNetwork.train naf_cartpole.py:264-272, debug_values :274-284, action_given :247-262,
@@ -290,6 +297,8 @@ int cpp_naf_debug_values(cpp_naf* a, const void* s1, const float* action, const 
 int cpp_naf_action_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_action, void* stream);
 int cpp_naf_value_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_value, void* stream);
 int cpp_naf_update_targets(cpp_naf* a, float coeff, void* stream);
+/* as cpp_ddpg_debug_view; part: 0 value, 1 naf/output_action, 2 naf/l_values, 3 target value */
+int cpp_naf_debug_view(const cpp_naf* a, int32_t part, int32_t kind, int32_t index, int32_t B, int64_t* out4);
 
 /* ------------------------------------------------------------------ a14: LRPG
  * LikelihoodRatioPolicyGradientAgent graph lrpg_cartpole.py:80-130, train :165-182, util.standardise util.py:37-43 */

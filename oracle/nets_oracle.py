@@ -209,6 +209,56 @@ def batch_norm(x, beta, moving_mean, moving_variance):
   return (x - mean[None, :, None, None]) * inv[None, :, None, None] + beta[None, :, None, None]
 
 
+# Routing pinned from outside (parity tests only): relu + max_pool2d is a piecewise-linear map whose pieces are selected by
+# discrete decisions (which of the four window positions wins, whether the ReLU is open).  A decision that sits within
+# rounding of a tie may legitimately be taken differently by an fp32 / tensor-core forward pass and by this fp64 graph; the
+# gradient behind it then differs by a whole term, not by rounding.  `with gates({(ns, "conv1"): u8 [B][PH][PW][10], ...})`
+# evaluates relu(max_pool(.)) of those layers with the GIVEN decisions (0..3 = dy*2+dx of the winner, 4 = ReLU closed) and
+# records in GATE_STATS how many decisions differ from the ones this graph would have taken and how far each of those is
+# from a tie - so that a test can assert "same function, and every disagreement is a tie within rounding".
+GATES = None
+GATE_STATS = None
+
+
+class gates(object):
+  """with gates(routing) as stats: ... - stats[(ns, layer)] = dict(n, mismatched, worst_gap_rel)"""
+
+  def __init__(self, routing):
+    self.routing = routing
+
+  def __enter__(self):
+    global GATES, GATE_STATS
+    self.saved = (GATES, GATE_STATS)
+    GATES, GATE_STATS = self.routing, {}
+    return GATE_STATS
+
+  def __exit__(self, *exc):
+    global GATES, GATE_STATS
+    GATES, GATE_STATS = self.saved
+
+
+def _relu_pool_pinned(x, amax, key):
+  """x (B, C, H, W) pre-activation, amax u8 (B, H//2, W//2, C) -> (B, C, H//2, W//2) with the routing of `amax`"""
+  B, C, H, W = x.shape
+  ph, pw = H // 2, W // 2
+  win = x[:, :, :2 * ph, :2 * pw].reshape(B, C, ph, 2, pw, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, ph, pw, 4)
+  a = torch.as_tensor(np.asarray(amax)).to(torch.int64).reshape(B, ph, pw, C).permute(0, 3, 1, 2)
+  is_open = (a < 4).to(x.dtype)
+  picked = torch.gather(win, 4, a.clamp(max=3).unsqueeze(-1)).squeeze(-1)
+  out = picked * is_open
+  with torch.no_grad():
+    best, arg = win.max(dim=4)
+    own = torch.where(best > 0, arg, torch.full_like(arg, 4))
+    diff = own != a
+    # distance of a disagreeing decision from the tie: |value the pinned routing passes on - value this graph passes on|
+    gap = (out - F.relu(best)).abs()
+    scale = float(x.abs().max())
+    st = GATE_STATS.setdefault(key, dict(n=0, mismatched=0, worst_gap_rel=0.0))
+    st["n"] += int(diff.numel()); st["mismatched"] += int(diff.sum())
+    st["worst_gap_rel"] = max(st["worst_gap_rel"], float(gap.max()) / max(scale, 1e-30))
+  return out
+
+
 def conv_trunk(nd, P, state):
   """base_network.py:73-127 -> (B, h, w, 10) NHWC"""
   B = state.shape[0]
@@ -219,11 +269,14 @@ def conv_trunk(nd, P, state):
     if nd.batch_norm:                                             # no bias; BN in front of the ReLU (Appendix A-4)
       pre = "%s/%s/BatchNorm/" % (nd.ns, name)
       x = F.conv2d(x, W, None, stride=1, padding=k // 2)
-      x = F.relu(batch_norm(x, P[pre + "beta"], P[pre + "moving_mean"], P[pre + "moving_variance"]))
+      x = batch_norm(x, P[pre + "beta"], P[pre + "moving_mean"], P[pre + "moving_variance"])
     else:
       b = P["%s/%s/biases" % (nd.ns, name)]
-      x = F.relu(F.conv2d(x, W, b, stride=1, padding=k // 2))     # SAME, cross-correlation
-    x = F.max_pool2d(x, 2)                                        # stride 2, VALID (floor)
+      x = F.conv2d(x, W, b, stride=1, padding=k // 2)             # SAME, cross-correlation
+    if GATES is not None and (nd.ns, name) in GATES:
+      x = _relu_pool_pinned(x, GATES[(nd.ns, name)], (nd.ns, name))
+    else:
+      x = F.max_pool2d(F.relu(x), 2)                              # relu, then stride 2, VALID (floor)
   return x.permute(0, 2, 3, 1)
 
 

@@ -29,37 +29,72 @@ def assert_close(got, want, tol=TOL, what="", cpu32=None, slack=4.0):
   return e
 
 
-FLIP = 3e-4    # allowance for max-pool argmax / ReLU gate decisions that differ between fp32 and fp64 (see below)
+# ---- routing-pinned gradient parity ---------------------------------------------------------------------------------
+# relu + 2x2 max-pool is piecewise linear; which piece applies is a discrete decision per window (winner, ReLU open or
+# closed).  A decision within rounding of a tie may be taken differently by the GPU forward pass and by the fp64 oracle;
+# the gradient behind it then differs by a whole term.  Instead of allowing for that, the tests read the GPU's decisions
+# back (cpp_*_debug_view) and evaluate the fp64 oracle with THOSE (oracle.nets_oracle.gates): both sides then compute
+# the same smooth function and every gradient tensor must meet the plain tolerance.  The decisions that differ from the
+# oracle's own are counted and each must sit within rounding of a tie.
+TIE = 1e-5             # a differing decision must be this close to a tie (relative to max|pre-activation| of the layer)
+MAX_MISMATCH = 2e-4    # ... and differing decisions must be rare (fraction of a layer's decisions), at least allow one
 
 
-def assert_grads_close(got_flat, want64, want32, names, tol=TOL, slack=4.0, flip=FLIP, what="grads"):
-  """Per-variable gradient parity of a whole training step at FULL size.
+def debug_view(eng, part, kind, index, B):
+  """intermediate `kind` (0 routing bytes, 1 pooled conv output, 2 FC output) of layer `index` of network `part` after the
+  last step, read from the engine's workspace through cpp_{ddpg,naf}_debug_view"""
+  import ctypes as C
+  from cartpoleplusplus_b200 import _lib
+  fn = _lib.lib().cpp_ddpg_debug_view if "actor" in eng.nets else _lib.lib().cpp_naf_debug_view
+  out = (C.c_int64 * 4)()
+  _lib.check(fn(eng.handle, part, kind, index, B, out))
+  off, rows, per, valid = [int(v) for v in out]
+  ws = eng.buffers["workspace"]
+  if kind == 0:
+    return ws[off:off + rows * per].view(rows, per).cpu().numpy()
+  return ws[off:off + rows * per * 4].view(torch.float32).view(rows, per)[:, :valid].cpu().numpy()
 
-  Among the ~3.4 M gates (2x2 max-pool winners, ReLUs) of one c3 forward pass a handful sit within fp32 rounding of
-  a tie; an fp32 run and the fp64 oracle then route one gradient term differently.  That is a discrete change, not
-  a rounding error: it shows up as 1e-5..4e-4 (relative to the variable's own max) in whichever variables lie
-  upstream of the flipped gate, and the reference's own fp32 CPU path shows exactly the same thing against fp64
-  (SURVEY.md 7.2 'Parity definition'; e.g. actor/conv1/weights 4.4e-4 at seed 77).  The arithmetic itself is
-  held to 1e-5 at full size by tests/test_gpu_kernels.py, which pins the routing, and by the small golden cases,
-  which have too few gates to flip.  Here each variable must be within `tol` of fp64, or within `slack` x the fp32
-  CPU path's own error, or within the flip allowance.  Returns {name: (gpu_err, cpu32_err)}."""
+
+def conv_routing(eng, parts, shape, B):
+  """{(namespace, 'conv1'|'conv2'|'conv3'): u8 [B][PH][PW][10]} for parts = [(part index, namespace), ...]"""
+  out = {}
+  for part, ns in parts:
+    H, W = shape[0], shape[1]
+    for i, name in enumerate(("conv1", "conv2", "conv3")):
+      H, W = H // 2, W // 2
+      out[(ns, name)] = debug_view(eng, part, 0, i, B).reshape(B, H, W, 10)
+  return out
+
+
+def check_gate_stats(stats, report=None):
+  """every routing decision that differs from the fp64 graph's own is a tie within rounding, and there are few; -> #differing"""
+  total = 0
+  for key, st in sorted(stats.items()):
+    total += st["mismatched"]
+    if report is not None:
+      report["gates %s/%s" % key] = "%d of %d differ, worst gap %.1e" % (st["mismatched"], st["n"], st["worst_gap_rel"])
+    assert st["mismatched"] <= max(1, MAX_MISMATCH * st["n"]), "%s: %d of %d routing decisions differ from the fp64 graph" % (key, st["mismatched"], st["n"])
+    assert st["worst_gap_rel"] <= TIE, "%s: a differing decision is %.2e away from a tie - not a rounding tie" % (key, st["worst_gap_rel"])
+  return total
+
+
+def per_variable_errors(names, got_flat, want_list):
+  """{variable: max|got - want| / max|want|} over the flat gradient (or parameter) vector of one network"""
   got_flat = np.asarray(got_flat, dtype=np.float64).reshape(-1)
   off, rep = 0, {}
-  for n, w64, w32 in zip(names, want64, want32):
-    w64 = np.asarray(w64, dtype=np.float64).reshape(-1); w32 = np.asarray(w32, dtype=np.float64).reshape(-1)
-    g = got_flat[off:off + w64.size]; off += w64.size
-    den = max(np.abs(w64).max(), 1e-30)
-    e_gpu, e_cpu = float(np.abs(g - w64).max() / den), float(np.abs(w32 - w64).max() / den)
-    rep[n] = (e_gpu, e_cpu)
-    if e_gpu <= max(tol, slack * e_cpu, flip):
-      continue
-    # a flipped conv gate with an unusually large gradient behind it: allowed for conv variables only, and only when the
-    # bulk of the variable's entries still meets the arithmetic tolerance (a systematic error would touch all of them)
-    frac_ok = float((np.abs(g - w64) / den <= max(tol, slack * e_cpu)).mean())
-    assert "/conv" in n and frac_ok >= 0.7 and e_gpu <= 5e-2, \
-        "%s %s: GPU rel err %.3e vs fp64 (fp32 CPU path: %.3e), %.0f %% of entries within tolerance" % (what, n, e_gpu, e_cpu, 100 * frac_ok)
-  assert off == got_flat.size
+  for n, w in zip(names, want_list):
+    w = np.asarray(w, dtype=np.float64).reshape(-1)
+    rep[n] = rel_err(got_flat[off:off + w.size], w)
+    off += w.size
+  assert off == got_flat.size, (off, got_flat.size)
   return rep
+
+
+def assert_all_within(rep, what, tol=TOL, cpu32=None, slack=4.0):
+  """every tensor of `rep` within tol (or, for ill-conditioned quantities, slack x the fp32 CPU path's own error cpu32[name])"""
+  bad = {k: "%.2e" % v for k, v in rep.items() if not v <= (tol if cpu32 is None else max(tol, slack * cpu32.get(k, 0.0)))}
+  assert not bad, "%s: tensors outside %.0e of the fp64 oracle (routing pinned): %s" % (what, tol, json.dumps(bad))
+  return max(rep.values()) if rep else 0.0
 
 
 def load_golden(golden_dir, name):
@@ -130,43 +165,6 @@ def set_route(tc):
   """pin conv1 to the tensor-core kernels (True) or the exact-fp32 CUDA-core kernels (False); None = default"""
   from cartpoleplusplus_b200 import _lib
   _lib.check(_lib.lib().cpp_set_option(b"conv1_tc", -1 if tc is None else int(bool(tc))))
-
-
-def assert_flat_grads_close(got_flat, want_flat, cpu32_flat, nets, tc_route, what="grads"):
-  """golden-vector gradient check.  CUDA-core route: the whole vector within 1e-5 (or the fp32 CPU path's own error).
-  Tensor-core route: conv1 outputs carry ~1e-6 relative error instead of ~1e-7, which makes a max-pool / ReLU gate that
-  sits within rounding of a tie ten times more likely to route differently from the fp64 oracle even in the small golden
-  cases; there the per-variable flip-aware criterion of assert_grads_close applies."""
-  got_flat = np.asarray(got_flat, dtype=np.float64).reshape(-1)
-  want_flat = np.asarray(want_flat, dtype=np.float64).reshape(-1); cpu32_flat = np.asarray(cpu32_flat, dtype=np.float64).reshape(-1)
-  if not tc_route:
-    return assert_close(got_flat, want_flat, what=what, cpu32=cpu32_flat)
-  names, w64, w32, off = [], [], [], 0
-  for net in nets:
-    for v in net._variables():
-      n = int(np.prod(v.shape))
-      names.append(v.name); w64.append(want_flat[off:off + n]); w32.append(cpu32_flat[off:off + n]); off += n
-  assert off == want_flat.size, (off, want_flat.size)
-  worst = 0.0
-  off = 0
-  for n, a64, a32 in zip(names, w64, w32):
-    g = got_flat[off:off + a64.size]; off += a64.size
-    den = max(np.abs(a64).max(), 1e-30)
-    diff = np.abs(g - a64) / den
-    e_gpu, e_cpu = float(diff.max()), float(np.abs(a32 - a64).max() / den)
-    # ill-conditioned quantities (cancelling sums, e.g. the bias gradient of the 1e-3-weight tanh head) are bounded by the
-    # fp32 CPU path's own error; the tensor-core route carries ~1e-6 instead of ~1.2e-7 relative forward error, hence 8x
-    if e_gpu <= max(TOL, 8.0 * e_cpu):
-      worst = max(worst, e_gpu)
-      continue
-    # Only a conv variable may exceed the arithmetic tolerance, and only in the way a flipped gate does it: the golden
-    # batches are tiny (one gate is ~1/500 of a conv1 filter's gradient terms), a flipped conv-k gate touches ONE output
-    # channel (<= 10 % + of the entries) of the conv layers at or below k, everything else stays within 1e-5.
-    assert "/conv" in n, "%s %s: GPU rel err %.3e vs fp64 (fp32 CPU path: %.3e)" % (what, n, e_gpu, e_cpu)
-    frac_ok = float((diff <= max(TOL, 8.0 * e_cpu)).mean())
-    assert frac_ok >= 0.7 and e_gpu <= 5e-2, "%s %s: rel err %.3e, only %.0f %% of the entries within tolerance" % (what, n, e_gpu, 100 * frac_ok)
-    worst = max(worst, e_gpu)
-  return worst
 
 
 def to_c24(x32):

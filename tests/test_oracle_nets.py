@@ -387,3 +387,37 @@ def test_dropout_gradient_passes_only_through_kept_units():
     g, = torch.autograd.grad(no.forward(critic, P, s, a).sum(), leaves)
   fd = (f(1e-6) - f(-1e-6)) / 2e-6
   assert abs(fd - float(g.reshape(-1)[idx])) <= 1e-6 * max(1.0, abs(fd))
+
+
+def test_pinned_routing_reproduces_the_graph_and_reports_disagreements():
+  """oracle.gates: evaluating relu + max_pool with the routing the graph itself takes changes nothing (values, gradients);
+  a routing that differs is counted and its distance from a tie reported (tests/test_gpu_step_pinned.py relies on both)"""
+  import torch.nn.functional as F
+  rs = np.random.RandomState(0)
+  shape = (16, 16, 3, 1, 2)
+  nd = no.ddpg_actor("actor", shape, True)
+  P = no.init_params(nd, rs)
+  s = torch.tensor(rs.rand(4, *shape))
+  leaves = no._leaf(P, no._trainable(nd))
+  out = no.forward(nd, P, s)
+  g0 = torch.autograd.grad(out.sum(), leaves)
+  routing = {}
+  x = no.whiten(s.reshape(4, 16, 16, 6)).permute(0, 3, 1, 2)
+  with torch.no_grad():
+    for name, k in (("conv1", 5), ("conv2", 5), ("conv3", 3)):
+      x = F.conv2d(x, P["actor/%s/weights" % name].permute(3, 2, 0, 1), P["actor/%s/biases" % name], padding=k // 2)
+      B, Cc, H, W = x.shape
+      win = x.reshape(B, Cc, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, Cc, H // 2, W // 2, 4)
+      best, arg = win.max(dim=4)
+      routing[("actor", name)] = torch.where(best > 0, arg, torch.full_like(arg, 4)).permute(0, 2, 3, 1).to(torch.uint8).numpy()
+      x = F.max_pool2d(F.relu(x), 2)
+  with no.gates(routing) as stats:
+    out1 = no.forward(nd, P, s)
+    g1 = torch.autograd.grad(out1.sum(), leaves)
+  assert all(st["mismatched"] == 0 and st["worst_gap_rel"] == 0.0 for st in stats.values()) and len(stats) == 3
+  assert float((out - out1).abs().max()) < 1e-14 and max(float((a - b).abs().max()) for a, b in zip(g0, g1)) < 1e-12
+  routing[("actor", "conv1")][0, 0, 0, 0] = (routing[("actor", "conv1")][0, 0, 0, 0] + 1) % 4
+  with no.gates(routing) as stats:
+    no.forward(nd, P, s)
+  assert stats[("actor", "conv1")]["mismatched"] == 1 and stats[("actor", "conv1")]["worst_gap_rel"] > 1e-3
+  assert no.GATES is None
