@@ -103,6 +103,33 @@ class EngineBase(object):
     self._prefetched = None              # (batch object, staged tensors, copy-done event, slot)
     self.parts = {}           # part name -> (buffer name, offset, size)
     self.buffers = {}
+    self.dp, self.lib_comm, self._comm_uid = None, False, None
+    self.world_size, self.rank = 1, 0
+
+  # ---- data parallel -----------------------------------------------------------------------------------
+  def set_data_parallel(self, dp, lib_comm=True):
+    """make this engine one replica of `dp.world_size`: rank 0's parameters, targets and optimiser state are broadcast (replicas
+    must start from identical bits: only gradients are exchanged afterwards), and - on GPUs - the library creates its own
+    NCCL communicator so that the gradient all-reduce runs inside the step (captured in its CUDA graph) instead of from here."""
+    self.dp = dp
+    self.world_size, self.rank = dp.world_size, dp.rank
+    self.lib_comm = False
+    if not dp.enabled:
+      return
+    for name in ("params", "target_params", "slots", "opt_state"):
+      if name in self.buffers:
+        dp.broadcast(self.buffers[name], 0)
+    import torch.distributed as dist
+    if lib_comm and dist.get_backend() == "nccl":
+      uid = dp.nccl_unique_id()
+      _lib.check(self._comm_init(self.handle, dp.rank, dp.world_size, uid))
+      self._comm_uid = uid
+      self.lib_comm = True
+
+  def _need_global_moments(self, moments, pixels):
+    if self.dp is not None and self.dp.enabled and pixels and moments is None:
+      raise ValueError("data parallel on pixel states: pass moments=(mean_inv_s1, mean_inv_s2) of the GLOBAL batch "
+                       "(ReplayMemory.batch_moments); a shard's own statistics would whiten every replica differently")
 
   def part_view(self, part):
     bufname, off, n = self.parts[part]

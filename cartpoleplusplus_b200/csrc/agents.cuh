@@ -1,6 +1,7 @@
 // Agent-level step objects behind the C ABI (see include/cartpolepp.h).
 #pragma once
 #include "net.cuh"
+#include "comm.cuh"
 
 namespace cpp {
 
@@ -107,7 +108,13 @@ struct DDPG {
   // streams / graph state
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;                      // origin stream of the graph capture (the caller's may be the legacy default stream)
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[12] = {};
+  // data parallel: the gradient all-reduce runs inside the step (comm.cu) - everything but the conv1 gradients on comm_stream
+  // next to conv1's weight-gradient kernel, the two small conv1 ranges afterwards on the main stream
+  Comm comm;
+  cudaStream_t comm_stream = nullptr;
+  int all_reduce_early(cudaStream_t s);
+  int all_reduce_late(cudaStream_t s);
   BackwardAux aux[2];                                     // side streams of the actor / critic backward chains (weight gradients)
   bool streams_ready = false;
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};   // packed-weight scratch per chain (actor, critic, target actor, target critic)
@@ -161,7 +168,11 @@ struct NAF {
   ~NAF();
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // mu chain, l chain, target value chain
   cudaStream_t cap_stream = nullptr;
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[12] = {};
+  Comm comm;                                              // data parallel, as in DDPG
+  cudaStream_t comm_stream = nullptr;
+  int all_reduce_early(cudaStream_t s);
+  int all_reduce_late(cudaStream_t s);
   bool streams_ready = false;
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};    // packed-weight scratch per chain (value, mu, l, target value)
   void* wgs[3] = {nullptr, nullptr, nullptr};

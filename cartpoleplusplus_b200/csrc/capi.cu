@@ -284,6 +284,24 @@ int cpp_soft_update(float* target, const float* source, float coeff, int64_t n, 
   API_END
 }
 
+// ---------------------------------------------------------------- data parallel (8e)
+int cpp_nccl_unique_id(void* out128) { API_BEGIN NEED(out128); return comm_unique_id(out128); API_END }
+int cpp_nccl_version(int32_t* out) { API_BEGIN NEED(out); int v = 0; CPP_TRY(comm_version(&v)); *out = v; return CPP_OK; API_END }
+int cpp_ddpg_comm_init(cpp_ddpg* a, int32_t rank, int32_t world, const void* id128) {
+  API_BEGIN
+  NEED(a);
+  for (auto& gc : a->a.graph) gc.clear();
+  return a->a.comm.init(rank, world, id128);
+  API_END
+}
+int cpp_naf_comm_init(cpp_naf* a, int32_t rank, int32_t world, const void* id128) {
+  API_BEGIN
+  NEED(a);
+  a->a.graph.clear();
+  return a->a.comm.init(rank, world, id128);
+  API_END
+}
+
 // ---------------------------------------------------------------- DDPG
 int cpp_ddpg_create(const cpp_ddpg_config* cfg, cpp_ddpg** out) {
   API_BEGIN
@@ -350,7 +368,7 @@ int cpp_ddpg_train_step(cpp_ddpg* a, const void* s1, const float* action, const 
                         const void* s2, int32_t is_f16, int32_t B, void* stream) {
   API_BEGIN
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
-  return a->a.step(s1, action, reward, mask, s2, is_f16, B, B, true, ST(stream));
+  return a->a.step(s1, action, reward, mask, s2, is_f16, B, B * a->a.comm.world, true, ST(stream));
   API_END
 }
 int cpp_ddpg_step_apply(cpp_ddpg* a, void* stream) {

@@ -95,6 +95,8 @@ class ActorNetwork(base_network.Network):
     self._critic = critic
 
   def action_given(self, state, add_noise=False):
+    if self._part != "actor":      # the engine entry point reads the online parameters; the reference loops never ask the target actor
+      raise NotImplementedError("action_given on %s: only the online actor is evaluated on this path" % self.namespace)
     actions = self._need_engine().action_given(np.asarray(state)[None])
     # NOTE: noise is added _outside_ the device graph, as in the reference (:127-134)
     if add_noise:
@@ -157,8 +159,7 @@ class DDPGEngine(EngineBase):
     self.o = o
     self.max_batch = 0
     self.handle = None
-    self.world_size, self.rank = 1, 0
-    self.dp = None
+    self._comm_init = self.lib.cpp_ddpg_comm_init
     self._layout()
     rng = np.random.RandomState(seed)
     for part, net in self.nets.items():
@@ -206,15 +207,13 @@ class DDPGEngine(EngineBase):
     b.workspace, b.workspace_bytes = self.buffers["workspace"].data_ptr(), nbytes
     _lib.check(self.lib.cpp_ddpg_bind(h, C.byref(b)))
     self.handle, self.max_batch = h, B
+    if self.lib_comm:                                 # a re-created agent joins the communicator group again (all ranks grow together)
+      self._comm_uid = self.dp.nccl_unique_id()
+      _lib.check(self._comm_init(self.handle, self.rank, self.world_size, self._comm_uid))
     self.out_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
     self.out_td = torch.zeros(B, dtype=torch.float32, device=self.device)
     self.out_q = torch.zeros(B, dtype=torch.float32, device=self.device)
     self.out_action = torch.zeros(B * self.nets["actor"].action_dim, dtype=torch.float32, device=self.device)
-
-  # ---- data parallel: grads are summed over ranks between backward and apply
-  def set_data_parallel(self, dp):
-    self.dp = dp
-    self.world_size, self.rank = dp.world_size, dp.rank
 
   def _batch_args(self, batch):
     s1, a, r, m, s2 = self._staged(batch)
@@ -261,11 +260,13 @@ class DDPGEngine(EngineBase):
     device tensors with the whitening statistics of the GLOBAL batch (data parallel / replay-resident path)."""
     s1, a, r, m, s2, B = self._batch_args(batch)
     self._ensure(B)
+    self._need_global_moments(moments, self.nets["actor"]._spec.pixels)
     st = self._stream()
     if moments is not None:
       _lib.check(self.lib.cpp_ddpg_set_moments(self.handle, _lib.ptr(moments[0]), _lib.ptr(moments[1])))
     Bg = B * self.world_size
-    if self.dp is None and self.world_size == 1:
+    if (self.dp is None and self.world_size == 1) or self.lib_comm:
+      # one call, one graph: backward of both networks, (data parallel: the in-library all-reduce,) clip + SGD of both
       _lib.check(self.lib.cpp_ddpg_train_step(self.handle, _lib.ptr(s1), _lib.ptr(a), _lib.ptr(r), _lib.ptr(m), _lib.ptr(s2),
                                               state_flag(s1), B, st))
       if moments is not None:

@@ -32,6 +32,26 @@ class DataParallel(object):
     assert len(idxs) == per_rank * self.world_size
     return idxs[self.rank * per_rank:(self.rank + 1) * per_rank]
 
+  def broadcast(self, t, src=0):
+    """replicas start (and resume) from rank `src`'s bits: parameters, targets, optimiser slots"""
+    if self.enabled:
+      dist.broadcast(t, src=src)
+    return t
+
+  def nccl_unique_id(self):
+    """ncclGetUniqueId on rank 0, handed to every rank: the library creates its OWN communicator from it (csrc/comm.cu),
+    torch.distributed is only the rendezvous"""
+    import ctypes as C
+    from . import _lib
+    buf = (C.c_uint8 * 128)()
+    if self.rank == 0:
+      _lib.check(_lib.lib().cpp_nccl_unique_id(buf))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    out = (C.c_uint8 * 128)(*t.cpu().tolist())
+    return out
+
   def all_reduce_sum(self, flat):
     if self.enabled:
       dist.all_reduce(flat, op=dist.ReduceOp.SUM)

@@ -111,22 +111,30 @@ class LikelihoodRatioPolicyGradientAgent(base_network.Network):
         batch_actions += actions
         batch_advantages += [sum(rewards)] * len(rewards)       # lrpg_cartpole.py:209
         total_rewards.append(sum(rewards))
-      if min(total_rewards) == max(total_rewards):               # :213-216
-        print("skipping training; all rollouts gave the same reward")
-        loss = float("nan")
+      losses = []
+      if min(total_rewards) == max(total_rewards):               # :213-216: standardising equal advantages would divide by zero
+        sys.stderr.write("converged? standardisation of advantaged will barf here....\n")
+        loss = 0
       else:
         loss = self.train(batch_observations, batch_actions, batch_advantages)
-      num_actions_taken += len(batch_actions)
+        losses.append(loss)
+      # the reference's STATS keys and accounting (:221-250): mean over the (zero or one) losses of this iteration - NaN
+      # when training was skipped, exactly like np.mean([]) there -, the episode length of the LAST rollout, and
+      # num_actions_taken advanced by that last rollout only
       stats = collections.OrderedDict()
       stats["time"] = time.time()
       stats["n"] = n
-      stats["mean_total_reward"] = float(np.mean(total_rewards))
-      stats["loss"] = loss
+      stats["mean_losses"] = float(np.mean(losses)) if losses else float("nan")
+      stats["total_reward"] = float(np.sum(total_rewards))
+      stats["episode_len"] = len(rewards)
       print("STATS %s\t%s" % (datetime.datetime.now().strftime('%Y-%m-%d %H:%M:%S'), json.dumps(stats)))
       sys.stdout.flush()
+      n += 1
       if saver_util is not None:
         saver_util.save_if_required()
-      n += 1
+      if VERBOSE_DEBUG or n % 10 == 0:                           # :239-240 occasional eval
+        self.run_eval(1)
+      num_actions_taken += len(rewards)
       if max_num_actions > 0 and num_actions_taken > max_num_actions:
         break
       if max_run_time > 0 and time.time() > start_time + max_run_time:

@@ -73,6 +73,8 @@ class ValueNetwork(base_network.Network):
     return self.initial_values(rng)
 
   def value_given(self, state):
+    if self._part != "value":      # the engine entry point reads the online parameters; the reference loops never ask a target net
+      raise NotImplementedError("value_given on %s: only the online value network is evaluated on this path" % self.namespace)
     return self._need_engine().value_given(state)
 
 
@@ -150,8 +152,8 @@ class NAFEngine(EngineBase):
     self.nets = collections.OrderedDict([("value", naf.value_net), ("mu", naf.mu_net), ("l", naf.l_net),
                                          ("target_value", naf.target_value_net)])
     self.kind, self.hp = naf.optimiser
-    self.max_batch, self.handle, self.dp = 0, None, None
-    self.world_size, self.rank = 1, 0
+    self.max_batch, self.handle = 0, None
+    self._comm_init = self.lib.cpp_naf_comm_init
     self._layout()
     rng = np.random.RandomState(seed)
     for part, net in self.nets.items():
@@ -205,15 +207,14 @@ class NAFEngine(EngineBase):
     b.workspace, b.workspace_bytes = self.buffers["workspace"].data_ptr(), nbytes
     _lib.check(self.lib.cpp_naf_bind(h, C.byref(b)))
     self.handle, self.max_batch = h, B
+    if self.lib_comm:
+      self._comm_uid = self.dp.nccl_unique_id()
+      _lib.check(self._comm_init(self.handle, self.rank, self.world_size, self._comm_uid))
     A = self.naf.action_dim
     dev = self.device
     self.out = dict(l=torch.zeros(B * (A * (A + 1)) // 2, dtype=torch.float32, device=dev), loss=torch.zeros(1, dtype=torch.float32, device=dev),
                     V=torch.zeros(B, dtype=torch.float32, device=dev), A=torch.zeros(B, dtype=torch.float32, device=dev),
                     V2=torch.zeros(B, dtype=torch.float32, device=dev), act=torch.zeros(B * A, dtype=torch.float32, device=dev))
-
-  def set_data_parallel(self, dp):
-    self.dp = dp
-    self.world_size, self.rank = dp.world_size, dp.rank
 
   def _batch_args(self, batch):
     s1, a, r, m, s2 = self._staged(batch)
@@ -231,17 +232,30 @@ class NAFEngine(EngineBase):
     _lib.check(self.lib.cpp_naf_apply(self.handle, 1 if check else 0, C.byref(loss), self._stream()))
     return float(loss.value)
 
-  def train(self, batch, moments=None):
+  def apply_async(self):
+    """clip + optimiser without the host read-back of the loss: the update is skipped on the device when l_values / L / loss
+    were non-finite and the error surfaces at the next last_loss() (steady-state loops, bench.py)"""
+    _lib.check(self.lib.cpp_naf_apply(self.handle, 2, None, self._stream()))
+    return None
+
+  def last_loss(self):
+    lf = self.buffers["grads"][self.off_loss:self.off_loss + 2].cpu().numpy()
+    if lf[1] != 0 or not np.isfinite(lf[0]):
+      raise _lib.CppError(-4, "check_numerics: non-finite l_values / L / loss (naf_cartpole.py:242-245)")
+    return float(lf[0])
+
+  def train(self, batch, moments=None, sync=True):
     """naf.train(batch) (naf_cartpole.py:264-272).  moments: optional (mean_inv_s1, mean_inv_s2) device tensors with the
     whitening statistics of the GLOBAL batch (data parallel: every rank trains on a slice of it)"""
+    self._need_global_moments(moments, self.nets["value"]._spec.pixels)
     if moments is not None:
       _lib.check(self.lib.cpp_naf_set_moments(self.handle, _lib.ptr(moments[0]), _lib.ptr(moments[1])))
-    self.backward(batch)
+    self.backward(batch)                                   # data parallel with lib_comm: the all-reduce ran inside
     if moments is not None:
       _lib.check(self.lib.cpp_naf_set_moments(self.handle, None, None))
-    if self.dp is not None:
+    if self.dp is not None and not self.lib_comm:
       self.dp.all_reduce_sum(self.buffers["grads"])        # the single gradient all-reduce of the step (SURVEY.md 8e)
-    loss = self.apply(True)
+    loss = self.apply(True) if sync else self.apply_async()
     self._release_slot()
     return loss
 

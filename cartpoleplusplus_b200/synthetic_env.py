@@ -57,6 +57,12 @@ class SyntheticCartpole(object):
     self.rs = np.random.RandomState(0)
     self.steps = 0
     self.done = True
+    # --event-log-out (bullet_cartpole.py:90-94,221-222,283-285): every episode is appended in the reference's framed
+    # protobuf + PNG format, which ReplayMemory.reset_from_event_log (--event-log-in) reads back
+    self.event_log = None
+    if getattr(opts, "event_log_out", None):
+      from . import event_log
+      self.event_log = event_log.EventLog(opts.event_log_out, opts.use_raw_pixels)
 
   def _render(self, cam):
     H, W = self.render_height, self.render_width
@@ -84,6 +90,9 @@ class SyntheticCartpole(object):
     self.omega = self.rs.uniform(-0.3, 0.3, 2)
     for r in range(self.repeats):
       self._fill(r)
+    if self.event_log:
+      self.event_log.reset()
+      self.event_log.add_just_state(self.state)
     return np.copy(self.state)
 
   def step(self, action):
@@ -103,4 +112,6 @@ class SyntheticCartpole(object):
     self.steps += 1
     if np.any(np.abs(self.theta) > 0.35) or np.any(np.abs(self.pos) > 1.0) or self.steps >= self.max_episode_len:
       self.done = True
+    if self.event_log:
+      self.event_log.add(self.state, int(action) if self.discrete_actions else np.asarray(action, dtype=np.float32).reshape(1, -1), 1.0)
     return np.copy(self.state), 1.0, self.done, {}

@@ -1,6 +1,5 @@
 """Mirror of the reference's util.py for the pieces the hot path and its callers need
-(/root/reference/util.py): flags :10-20, StopWatch :22-26, collapsed_successive_ranges :60-71,
-construct_optimiser :73-76 (returns the optimiser *description* the CUDA step consumes),
+(/root/reference/util.py): flags :10-20, construct_optimiser :73-76 (returns the optimiser *description* the CUDA step consumes),
 OrnsteinUhlenbeckNoise :134-156 (host side, including the rotated np.clip arguments, Appendix C-6),
 SaverUtil :88-131 (checkpoint save / restore of the device-resident variables)."""
 import datetime
@@ -20,28 +19,6 @@ def add_opts(parser):
   parser.add_argument('--optimiser-args', type=str, default="{\"learning_rate\": 0.001}",
                       help="json serialised args for optimiser constructor")
   parser.add_argument('--use-dropout', action='store_true', help="include a dropout layers after each fully connected layer")
-
-
-class StopWatch:
-  def reset(self):
-    self.start = time.time()
-
-  def time(self):
-    return time.time() - self.start
-
-
-def collapsed_successive_ranges(values):
-  """reduce an array, e.g. [2,3,4,5,13,14,15], to its successive ranges [2-5, 13-15]"""
-  last, start, out = None, None, []
-  for value in values:
-    if start is None:
-      start = value
-    elif value != last + 1:
-      out.append("%d-%d" % (start, last))
-      start = value
-    last = value
-  out.append("%d-%d" % (start, last))
-  return ", ".join(out)
 
 
 def construct_optimiser(opts):
@@ -89,18 +66,41 @@ class SaverUtil(object):
     raise AssertionError("no model_checkpoint_path in %s" % ckpt_info_file)
 
   def load_latest_ckpt_or_init_if_none(self):
-    """loads latest ckpt from dir; if there is none the (already initialised) variables are saved straight away"""
-    latest = self._latest()
-    if latest is None:
-      sys.stderr.write("no latest ckpt in %s, just initing vars...\n" % self.ckpt_dir)
-      self.force_save()
-      return
-    most_recent_ckpt = "%s/%s" % (self.ckpt_dir, latest)
-    sys.stderr.write("loading ckpt %s\n" % most_recent_ckpt)
-    self.restore(most_recent_ckpt)
+    """loads latest ckpt from dir; if there is none the (already initialised) variables are saved straight away.
+    Data parallel: rank 0 alone reads the directory and restores (or keeps its initialisation); its variables, targets and
+    optimiser state are then broadcast, so every replica starts from the same bits whether or not the file system is shared."""
+    if self._is_writer():
+      latest = self._latest()
+      if latest is None:
+        sys.stderr.write("no latest ckpt in %s, just initing vars...\n" % self.ckpt_dir)
+        self.force_save()
+      else:
+        most_recent_ckpt = "%s/%s" % (self.ckpt_dir, latest)
+        sys.stderr.write("loading ckpt %s\n" % most_recent_ckpt)
+        self._restore_local(most_recent_ckpt)
+    self._sync_replicas()
     self.next_scheduled_save_time = time.time() + self.save_freq
 
+  def _sync_replicas(self):
+    """rank 0's buffers -> every rank (a no-op without an initialised process group), then a barrier"""
+    try:
+      import torch.distributed as dist
+    except ImportError:
+      return
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+      return
+    for name in ("params", "target_params", "slots", "opt_state"):
+      if name in self.engine.buffers:
+        dist.broadcast(self.engine.buffers[name], src=0)
+    dist.barrier()
+
   def restore(self, path):
+    """restore `path` into the bound buffers in place; data parallel: rank 0 reads, everyone receives its bits"""
+    if self._is_writer():
+      self._restore_local(path)
+    self._sync_replicas()
+
+  def _restore_local(self, path):
     import torch
     e = self.engine
     with np.load(path if path.endswith(".npz") else path + ".npz") as z:
@@ -123,18 +123,22 @@ class SaverUtil(object):
 
   @staticmethod
   def _is_writer():
-    """data parallel: replicas are bit-identical, so rank 0 alone writes; every rank restores"""
+    """data parallel: replicas are bit-identical (set_data_parallel / _sync_replicas broadcast rank 0's bits, only summed
+    gradients are exchanged afterwards), so rank 0 alone writes.  A process is a non-writer only inside an initialised
+    process group, or when the launcher's environment says so (WORLD_SIZE > 1 and RANK != 0): a stray RANK variable in the
+    environment of a single-process run must not silence its checkpoints."""
     try:
       import torch.distributed as dist
       if dist.is_available() and dist.is_initialized():
         return dist.get_rank() == 0
     except ImportError:
       pass
-    return int(os.environ.get("RANK", "0")) == 0
+    return not (int(os.environ.get("WORLD_SIZE", "1")) > 1 and int(os.environ.get("RANK", "0")) != 0)
 
   def force_save(self):
     """force a save now."""
     if not self._is_writer():
+      sys.stderr.write("rank != 0: checkpoint left to rank 0\n")
       self.next_scheduled_save_time = time.time() + self.save_freq
       return
     dts = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')

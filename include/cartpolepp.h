@@ -252,6 +252,19 @@ int cpp_ddpg_update_targets(cpp_ddpg* a, float coeff, void* stream);
  * out4 = {byte offset inside the workspace, B, elements per batch row, valid leading elements per row}. */
 int cpp_ddpg_debug_view(const cpp_ddpg* a, int32_t part, int32_t kind, int32_t index, int32_t B, int64_t* out4);
 
+/* ------------------------------------------------------------------ 8e: data parallel, the gradient all-reduce inside the step
+ * The reference is a single replica; SURVEY.md 8e shards the minibatch over one process per GPU with ONE NCCL sum all-reduce of
+ * the flat gradient buffer per grad-step.  cpp_nccl_unique_id (rank 0) -> the host broadcasts the 128 bytes (torch.distributed
+ * is only the rendezvous) -> every rank calls cpp_*_comm_init on its bound agent.  From then on cpp_ddpg_train_step /
+ * cpp_ddpg_step_backward / cpp_naf_backward sum the gradients over the replicas inside the step: everything but the conv1
+ * gradients on a communication stream next to conv1's weight-gradient kernel, the two small conv1 ranges afterwards, all
+ * captured into the step's CUDA graph; the loss and critic/NAF gradients are scaled by 1 / (B * world).  world = 1 (or
+ * never calling comm_init) is the single-replica behaviour.  NCCL is bound at run time (the libnccl.so.2 the process already
+ * loaded, else the system one); CPP_ERR_NCCL when it is missing or a call fails. */
+int cpp_nccl_unique_id(void* out_host_128_bytes);
+int cpp_nccl_version(int32_t* out);
+int cpp_ddpg_comm_init(cpp_ddpg* a, int32_t rank, int32_t world_size, const void* unique_id_128_bytes);
+
 /* ------------------------------------------------------------------ a10: NAF agent
  * NafNetwork.train naf_cartpole.py:264-272, debug_values :274-284, action_given :247-262,
  * ValueNetwork.value_given :111-114, target update :373. */
@@ -286,7 +299,8 @@ int cpp_naf_bind(cpp_naf* a, const cpp_naf_buffers* b);
 int cpp_naf_set_moments(cpp_naf* a, const float* mean_inv_s1, const float* mean_inv_s2);
 int cpp_naf_backward(cpp_naf* a, const void* s1, const float* action, const float* reward, const float* mask,
                      const void* s2, int32_t is_f16, int32_t B, int32_t B_global, void* stream);
-/* returns CPP_ERR_NUMERICS (after a stream sync) when check=1 and l_values/L/loss were non-finite */
+/* returns CPP_ERR_NUMERICS (after a stream sync) when check=1 and l_values/L/loss were non-finite; check=2 skips the update
+ * on the device in that case without synchronising (loss_host must be NULL; the caller reads grads[offset_loss .. +1] later) */
 int cpp_naf_apply(cpp_naf* a, int32_t check, float* loss_host, void* stream);
 int cpp_naf_train(cpp_naf* a, const void* s1, const float* action, const float* reward, const float* mask,
                   const void* s2, int32_t is_f16, int32_t B, float* loss_host, void* stream);
@@ -297,6 +311,7 @@ int cpp_naf_debug_values(cpp_naf* a, const void* s1, const float* action, const 
 int cpp_naf_action_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_action, void* stream);
 int cpp_naf_value_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_value, void* stream);
 int cpp_naf_update_targets(cpp_naf* a, float coeff, void* stream);
+int cpp_naf_comm_init(cpp_naf* a, int32_t rank, int32_t world_size, const void* unique_id_128_bytes);
 /* as cpp_ddpg_debug_view; part: 0 value, 1 naf/output_action, 2 naf/l_values, 3 target value */
 int cpp_naf_debug_view(const cpp_naf* a, int32_t part, int32_t kind, int32_t index, int32_t B, int64_t* out4);
 

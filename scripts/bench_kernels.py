@@ -33,11 +33,9 @@ def timeit(fn, flush, n=10):
   return float(np.median(ts)), float(np.min(ts))
 
 
-def main():
-  ap = argparse.ArgumentParser()
-  ap.add_argument("--only", default=None)
-  ap.add_argument("--reps", type=int, default=10)
-  args = ap.parse_args()
+def kernel_table(only=None, reps=10, rm=None):
+  """[{kernel, what, launches_per_step, us_median, us_min, useful_gflop | bytes, ...}] at the c3 layer shapes; rm: a filled
+  ReplayMemory for the gather line (bench.py passes its own)"""
   lib = L.lib()
   dev = "cuda"
   g = torch.Generator(device=dev); g.manual_seed(0)
@@ -100,23 +98,85 @@ def main():
   c3 = layer(16, 3)
   conv1_fwd_tc()          # fills the arg-max side band the wgrad reads
   c2[0](); c3[0]()
+
+  # ---- FC stacks (a4): the actor's 640 -> 100 -> 100 -> 50 -> 2 and the critic's 640 -> 200 -> 50 (+2) -> 50 -> 1 through
+  # cpp_net_forward / cpp_net_backward of a low-dim network fed with the flattened trunk output
+  def fc_net(sizes, acts, concat_at=-1):
+    spec = L.NetSpec()
+    spec.pixels, spec.input_dim, spec.n_fc, spec.concat_at, spec.action_dim = 0, 640, len(sizes), concat_at, 2 if concat_at >= 0 else 0
+    for i, (n_, a_) in enumerate(zip(sizes, acts)):
+      spec.fc_out[i], spec.fc_act[i] = n_, a_
+    h = C.c_void_p()
+    L.check(lib.cpp_net_create(C.byref(spec), C.byref(h)))
+    n_par = int(lib.cpp_net_num_params(h))
+    P_ = (torch.randn(n_par, device=dev) * 0.05).contiguous()
+    G_ = torch.zeros(n_par, device=dev)
+    ws = torch.zeros(int(lib.cpp_net_workspace_bytes(h, B)), dtype=torch.uint8, device=dev)
+    xin = torch.relu(torch.randn(B, 640, device=dev)).contiguous()
+    act = torch.randn(B, 2, device=dev) if concat_at >= 0 else None
+    out = torch.zeros(B, sizes[-1], device=dev); dout = torch.randn(B, sizes[-1], device=dev)
+    dact = torch.zeros(B, 2, device=dev) if concat_at >= 0 else None
+
+    def fwd():
+      L.check(lib.cpp_net_forward(h, L.ptr(P_), L.ptr(xin), 0, None, L.ptr(act), B, L.ptr(ws), L.ptr(out), st()))
+
+    def bwd():
+      L.check(lib.cpp_net_backward(h, L.ptr(P_), L.ptr(xin), 0, None, B, L.ptr(ws), L.ptr(dout), L.ptr(G_), L.ptr(dact), st()))
+    macs = 0
+    d = 640
+    for i, n_ in enumerate(sizes):
+      macs += (d + (2 if concat_at == i else 0)) * n_
+      d = n_
+    return fwd, bwd, macs, (h, P_, G_, ws, xin, act, out, dout, dact)
+
+  fa = fc_net([100, 100, 50, 2], [1, 1, 1, 2])
+  fcr = fc_net([200, 50, 50, 1], [1, 1, 1, 0], concat_at=2)
+  fa[0](); fcr[0]()
+
   mac1 = B * H * W * 10 * 25 * CIN * NETS
+  mac2, mac3 = B * 32 * 32 * 10 * 25 * 10, B * 16 * 16 * 10 * 9 * 10
+  # launches per DDPG grad-step at c3 (csrc/agents.cu DDPG::step_body): conv1 fwd {actor,critic}(s1) + {targets}(s2); conv2/3
+  # fwd of the 4 networks; conv2/3 dgrad + wgrad of the 2 trained ones; one conv1 wgrad; FC fwd of 4 networks (the critic's
+  # tail twice), FC bwd of 2
   kernels = [
-      ("conv1_fwd_tc", conv1_fwd_tc, 2.0 * mac1, "conv1 5x5 9->10 fwd, actor+critic, incl. weight prep"),
-      ("conv1_wgrad_mma", conv1_wgrad_mma, 2.0 * mac1, "conv1 weight gradient, actor+critic, incl. absmax/reduce/finalize"),
-      ("conv2_fwd_tc", c2[0], 2.0 * B * 32 * 32 * 10 * 25 * 10, "conv2 5x5 10->10 fwd, one network, incl. weight prep"),
-      ("conv2_dgrad_tc", c2[1], 2.0 * B * 32 * 32 * 10 * 25 * 10, "conv2 input gradient, incl. un-pool/split + prep"),
-      ("conv2_wgrad_mma", c2[2], 2.0 * B * 32 * 32 * 10 * 25 * 10, "conv2 weight gradient, one network"),
-      ("conv3_fwd_tc", c3[0], 2.0 * B * 16 * 16 * 10 * 9 * 10, "conv3 3x3 10->10 fwd"),
-      ("conv3_dgrad_tc", c3[1], 2.0 * B * 16 * 16 * 10 * 9 * 10, "conv3 input gradient"),
-      ("conv3_wgrad_mma", c3[2], 2.0 * B * 16 * 16 * 10 * 9 * 10, "conv3 weight gradient"),
+      ("conv1_fwd_tc", conv1_fwd_tc, 2.0 * mac1, 2, "conv1 5x5 9->10 fwd, 2 sibling nets in one pass, incl. weight prep"),
+      ("conv1_wgrad_mma", conv1_wgrad_mma, 2.0 * mac1, 1, "conv1 weight gradient, actor+critic, incl. absmax/reduce/finalize"),
+      ("conv2_fwd_tc", c2[0], 2.0 * mac2, 4, "conv2 5x5 10->10 fwd, one network, incl. weight prep"),
+      ("conv2_dgrad_tc", c2[1], 2.0 * mac2, 2, "conv2 input gradient, incl. un-pool/split + prep"),
+      ("conv2_wgrad_mma", c2[2], 2.0 * mac2, 2, "conv2 weight gradient, one network"),
+      ("conv3_fwd_tc", c3[0], 2.0 * mac3, 4, "conv3 3x3 10->10 fwd"),
+      ("conv3_dgrad_tc", c3[1], 2.0 * mac3, 2, "conv3 input gradient"),
+      ("conv3_wgrad_mma", c3[2], 2.0 * mac3, 2, "conv3 weight gradient"),
+      ("fc_actor_fwd", fa[0], 2.0 * B * fa[2], 2, "actor FC stack 640-100-100-50-2 forward (actor, target actor)"),
+      ("fc_actor_bwd", fa[1], 4.0 * B * fa[2], 1, "actor FC stack backward: input gradients + weight / bias gradients"),
+      ("fc_critic_fwd", fcr[0], 2.0 * B * fcr[2], 2, "critic FC stack 640-200-50(+2)-50-1 forward (critic, target critic)"),
+      ("fc_critic_bwd", fcr[1], 4.0 * B * fcr[2], 1, "critic FC stack backward"),
   ]
-  for name, fn, flops, what in kernels:
-    if args.only and args.only != name:
+  rows = []
+  for name, fn, flops, per_step, what in kernels:
+    if only and only != name:
       continue
-    med, mn = timeit(fn, flush, args.reps)
-    print(json.dumps(dict(kernel=name, what=what, us_median=med, us_min=mn, useful_gflop=flops / 1e9,
-                          useful_tflops=flops / (med * 1e-6) / 1e12)))
+    med, mn = timeit(fn, flush, reps)
+    rows.append(dict(kernel=name, what=what, launches_per_step=per_step, us_median=med, us_min=mn, useful_gflop=flops / 1e9,
+                     useful_tflops=flops / (med * 1e-6) / 1e12))
+  if rm is not None and (not only or only == "replay_gather"):
+    idx = torch.randint(0, rm.buffer_size, (B,), device=dev, dtype=torch.int64)
+    idx_h = idx.cpu().numpy()
+    out = rm.batch_at(idx_h, d_idxs=idx)
+    med, mn = timeit(lambda: rm.batch_at(idx_h, d_idxs=idx, out=out), flush, reps)
+    nbytes = 2 * 2 * B * rm.row_elems * 2                 # s1 + s2 rows, read + written, fp16
+    rows.append(dict(kernel="replay_gather", what="ReplayMemory.batch gather of state_1 / state_2 rows + action/reward/mask",
+                     launches_per_step=1, us_median=med, us_min=mn, bytes=nbytes, gb_per_s=nbytes / (med * 1e-6) / 1e9))
+  return rows
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--only", default=None)
+  ap.add_argument("--reps", type=int, default=10)
+  args = ap.parse_args()
+  for r in kernel_table(args.only, args.reps):
+    print(json.dumps(r))
 
 
 if __name__ == "__main__":

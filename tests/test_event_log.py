@@ -112,3 +112,26 @@ def test_reset_from_event_log_equals_add_episode(tmp_path, pixels):
   np.random.seed(0); bb = b_mem.batch(16)
   for x, y in zip(ba, bb):
     assert torch.equal(x, y)
+
+
+def test_synthetic_env_writes_an_event_log_the_reader_understands(tmp_path):
+  """--event-log-out (bullet_cartpole.py:90-94,221-222,283-285): episodes land in the reference's framed format"""
+  import argparse
+  from cartpoleplusplus_b200 import synthetic_env
+  p = argparse.ArgumentParser()
+  synthetic_env.add_opts(p)
+  path = str(tmp_path / "events.log")
+  o = p.parse_args(["--event-log-out", path, "--max-episode-len", "4", "--action-repeats", "2"])
+  env = synthetic_env.SyntheticCartpole(o, discrete_actions=False)
+  for _ in range(2):
+    env.reset()
+    done = False
+    while not done:
+      _, _, done, _ = env.step(np.array([[0.25, -0.5]], dtype=np.float32))
+  env.reset()                                       # flushes the second episode, as in the reference
+  episodes = list(el.EventLogReader(path).entries())
+  assert len(episodes) == 2
+  for ep in episodes:
+    assert len(ep.event) >= 2 and len(ep.event[0].action) == 0
+    assert list(ep.event[1].action) == [0.25, -0.5] and ep.event[1].reward == 1.0
+    assert el.read_state_from_event(ep.event[1]).shape == (2, 2, 7)

@@ -29,7 +29,7 @@ def _moments(batch_states, C_):
   return out
 
 
-def _run(kind, world, rank, dp, steps=3):
+def _run(kind, world, rank, dp, steps=3, lib_comm=True):
   from tests import gpu_util as U
   from oracle import nets_oracle as no
   from oracle.make_golden import ddpg_params, _batch
@@ -47,8 +47,7 @@ def _run(kind, world, rank, dp, steps=3):
     naf, nets, eng, o = U.make_naf(shape, True, {k: v.numpy() for k, v in P.items()}, batch_size=Bg, optimiser="Momentum",
                                    optimiser_args={"learning_rate": 0.01, "momentum": 0.9})
   if dp is not None:
-    eng.set_data_parallel(dp)
-    eng.max_batch = 0; eng._ensure(Bg)
+    eng.set_data_parallel(dp, lib_comm=lib_comm)
   per = Bg // world
   for step in range(steps):
     batch = _batch(np.random.RandomState(100 + step), Bg, shape)
@@ -73,11 +72,12 @@ def _worker(rank, world, port, q):
   dp = dpmod.DataParallel(backend="nccl")
   out = {}
   for kind in ("ddpg", "naf"):
-    mine = _run(kind, world, rank, dp)
-    gathered = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    assert all(torch.equal(g, gathered[0]) for g in gathered), "%s: replicas diverged" % kind
-    out[kind] = mine.cpu().numpy()
+    for lib_comm in (True, False):       # the all-reduce inside the step's graph (csrc/comm.cu), and issued from the host
+      mine = _run(kind, world, rank, dp, lib_comm=lib_comm)
+      gathered = [torch.zeros_like(mine) for _ in range(world)]
+      dist.all_gather(gathered, mine)
+      assert all(torch.equal(g, gathered[0]) for g in gathered), "%s: replicas diverged (lib_comm=%s)" % (kind, lib_comm)
+      out[(kind, lib_comm)] = mine.cpu().numpy()
   dp.barrier()
   if rank == 0:
     q.put(out)
@@ -103,4 +103,6 @@ def test_two_rank_nccl_replicas_identical_and_match_single_gpu():
     assert p.exitcode == 0
   for kind in ("ddpg", "naf"):
     single = _run(kind, 1, 0, None).cpu().numpy()
-    U.assert_close(out[kind], single, tol=2e-6, what="%s: 2-rank data parallel vs one GPU on the whole batch" % kind)
+    for lib_comm in (True, False):
+      U.assert_close(out[(kind, lib_comm)], single, tol=2e-6,
+                     what="%s: 2-rank data parallel (lib_comm=%s) vs one GPU on the whole batch" % (kind, lib_comm))

@@ -174,11 +174,18 @@ def test_ddpg_restore_in_place_under_graph_replay(tmp_path):
 
 
 def test_only_rank_zero_writes(tmp_path, monkeypatch):
-  monkeypatch.setenv("RANK", "1")
+  monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2")
   s = util.SaverUtil(_HostEngine(1), str(tmp_path), save_freq=3600)      # nothing to load, and a non-zero rank does not save
   assert os.listdir(str(tmp_path)) == []
   s.force_save()
   assert os.listdir(str(tmp_path)) == []
   monkeypatch.setenv("RANK", "0")
   s.force_save()
+  assert "checkpoint" in os.listdir(str(tmp_path))
+
+
+def test_a_stray_rank_variable_does_not_silence_checkpoints(tmp_path, monkeypatch):
+  """single-process run with a leftover RANK (old torchrun / MPI / scheduler environment): it IS the writer"""
+  monkeypatch.setenv("RANK", "3"); monkeypatch.delenv("WORLD_SIZE", raising=False)
+  util.SaverUtil(_HostEngine(1), str(tmp_path), save_freq=3600)
   assert "checkpoint" in os.listdir(str(tmp_path))
