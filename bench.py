@@ -58,6 +58,7 @@ def parse_args():
   ap.add_argument("--skip-e2e", action="store_true")
   ap.add_argument("--skip-roofline", action="store_true")
   ap.add_argument("--host-allreduce", action="store_true", help="A/B: the round-1 all-reduce issued from the host between two C-ABI calls")
+  ap.add_argument("--no-allreduce", action="store_true", help="diagnosis only (replicas diverge): N independent replicas, what N processes cost without any exchange")
   return ap.parse_args()
 
 
@@ -225,8 +226,8 @@ def run_native(args):
   G = dp.world_size
 
   eng, o, nets = build_agent(cfg, BATCH)
-  if dp.enabled:
-    eng.set_data_parallel(dp, lib_comm=not args.host_allreduce)     # rank 0's weights broadcast; NCCL communicator inside the library
+  if dp.enabled and not args.no_allreduce:
+    eng.set_data_parallel(dp, lib_comm=not args.host_allreduce)     # rank 0's weights broadcast; the all-reduce moves inside the library
 
   rm = ReplayMemory(N_REPLAY, SHAPE, 2)
   fill_replay(rm)
@@ -319,7 +320,7 @@ def run_native(args):
 
   # ---- data parallel: the replicas must hold identical bits after all these steps
   replicas_identical = None
-  if dp.enabled:
+  if dp.enabled and not args.no_allreduce:
     mine = torch.cat([eng.buffers["params"], eng.buffers["target_params"]])
     ref = mine.clone()
     dp.broadcast(ref, 0)
@@ -413,8 +414,9 @@ def run_native(args):
                            pipeline="the replay gather of step i+1 runs on a second stream next to training step i (two batch buffer "
                                     "sets); each timed step = one gather + one training step",
                            optimiser_steps_per_s=steps_per_s,
-                           all_reduce=None if not dp.enabled else ("host-issued torch.distributed" if args.host_allreduce else
-                                                                   "inside the step's CUDA graph (csrc/comm.cu)")),
+                           all_reduce=None if not dp.enabled else ("NONE (diagnosis: independent replicas)" if args.no_allreduce else
+                                                                   "host-issued torch.distributed" if args.host_allreduce else
+                                                                   "inside the step's CUDA graph (csrc/comm.cu), transport %s" % eng.transport)),
                 clocks=clk, sustained=sustained, replicas_identical=replicas_identical, e2e=e2e, gpu_launches=int(launches),
                 roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line))

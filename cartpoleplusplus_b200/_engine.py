@@ -107,13 +107,14 @@ class EngineBase(object):
     self.world_size, self.rank = 1, 0
 
   # ---- data parallel -----------------------------------------------------------------------------------
-  def set_data_parallel(self, dp, lib_comm=True):
+  def set_data_parallel(self, dp, lib_comm=True, transport=None):
     """make this engine one replica of `dp.world_size`: rank 0's parameters, targets and optimiser state are broadcast (replicas
-    must start from identical bits: only gradients are exchanged afterwards), and - on GPUs - the library creates its own
-    NCCL communicator so that the gradient all-reduce runs inside the step (captured in its CUDA graph) instead of from here."""
+    must start from identical bits: only gradients are exchanged afterwards), and - on GPUs - the gradient all-reduce moves
+    inside the step (captured in its CUDA graph) instead of being issued from here.  transport: "p2p" (default; our own
+    all-reduce over NVLink peer memory, csrc/comm.cu; CARTPOLEPP_COMM overrides) or "nccl"."""
     self.dp = dp
     self.world_size, self.rank = dp.world_size, dp.rank
-    self.lib_comm = False
+    self.lib_comm, self.transport = False, None
     if not dp.enabled:
       return
     for name in ("params", "target_params", "slots", "opt_state"):
@@ -121,10 +122,22 @@ class EngineBase(object):
         dp.broadcast(self.buffers[name], 0)
     import torch.distributed as dist
     if lib_comm and dist.get_backend() == "nccl":
-      uid = dp.nccl_unique_id()
-      _lib.check(self._comm_init(self.handle, dp.rank, dp.world_size, uid))
-      self._comm_uid = uid
+      self.transport = transport or os.environ.get("CARTPOLEPP_COMM", "p2p")
+      if self.transport not in ("p2p", "nccl"):
+        raise ValueError("transport %r (p2p | nccl)" % self.transport)
       self.lib_comm = True
+      self._connect()
+
+  def _connect(self):
+    """(re-)join the replica group with the agent object the engine currently holds; collective over all ranks"""
+    dp = self.dp
+    if self.transport == "nccl":
+      _lib.check(self._comm_init(self.handle, dp.rank, dp.world_size, dp.nccl_unique_id()))
+    else:
+      handle = (C.c_uint8 * 64)()
+      _lib.check(self._p2p_prepare(self.handle, dp.rank, dp.world_size, handle))
+      _lib.check(self._p2p_connect(self.handle, dp.all_gather_bytes(handle)))
+    dp.barrier()
 
   def _need_global_moments(self, moments, pixels):
     if self.dp is not None and self.dp.enabled and pixels and moments is None:

@@ -186,7 +186,6 @@ DDPG::~DDPG() {
   if (streams_ready) {
     for (auto& st : side) if (st) cudaStreamDestroy(st);
     if (cap_stream) cudaStreamDestroy(cap_stream);
-    if (comm_stream) cudaStreamDestroy(comm_stream);
     for (auto& a : aux) {
       if (a.stream) cudaStreamDestroy(a.stream);
       for (auto& e : a.ready) if (e) cudaEventDestroy(e);
@@ -200,7 +199,6 @@ int DDPG::ensure_streams() {
   if (streams_ready) return CPP_OK;
   for (auto& st : side) CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
-  CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
   for (auto& a : aux) {
     CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
     for (auto& e : a.ready) CPP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -332,26 +330,15 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   CPP_TRY(wait(s0, E_CB));
   if (multi) for (auto& a : aux) if (a.used) CPP_CHECK_CUDA(cudaStreamWaitEvent(s0, a.done, 0));     // join the weight-gradient side streams
   g_cta_cap = kNumSMs;
-  // ---- data parallel: every gradient except conv1's is complete -> summed over the replicas on the comm stream while
-  // conv1's weight gradient (the longest kernel of the step) runs
-  enum { E_JOIN = 10, E_AR = 11 };
-  if (comm.active()) {
-    cudaStream_t sa = multi ? comm_stream : s0;
-    CPP_TRY(record(E_JOIN, s0)); CPP_TRY(wait(sa, E_JOIN));
-    CPP_TRY(all_reduce_early(sa));
-    CPP_TRY(record(E_AR, sa));
-    tr.mark("comm all-reduce (all but conv1) done", sa);
-  }
   // ---- conv1 weight gradients of both networks in one pass over state_1; whole GPU
   {
     char* wss[2] = {ws_actor, ws_critic}; float* gr[2] = {buf.grads, buf.grads + off_c};
     CPP_TRY(conv1_wgrad_group(2, g2, wss, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
   }
   tr.mark("s0 conv1 wgrad {actor,critic} done", s0);
-  if (comm.active()) {
-    CPP_TRY(wait(s0, E_AR));
-    CPP_TRY(all_reduce_late(s0));
-    tr.mark("s0 all-reduce (conv1) done", s0);
+  if (comm.active()) {                      // data parallel: the flat gradient buffer summed over the replicas (comm.cu)
+    CPP_TRY(comm.all_reduce(buf.grads, total, s0));
+    tr.mark("s0 all-reduce done", s0);
   }
   if (with_apply) CPP_TRY(apply_both(s0));
   tr.mark("s0 apply done", s0);
@@ -366,29 +353,13 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   const bool multi = use_streams();
   if (multi || use_graphs()) CPP_TRY(ensure_streams());
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
-  const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, comm.comm};
+  const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, comm.key()};
   const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | (g_conv1_split << 5) | (g_critic_tail << 6) | (g_bwd_critic_sms << 8) | (g_fwd_actor_sms << 16) | ((g_wgrad_flush_steps / 16) << 24)};
   const int rc = run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
     return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, st);
   });
   if (rc == CPP_OK && trace_level() >= 2) trace_dump_graph();
   return rc;
-}
-
-// the flat gradient buffer in two exchanges: [everything behind conv1 of the actor | everything behind conv1 of the critic,
-// the loss and the non-finite flag], then [conv1 of the actor | conv1 of the critic]
-int DDPG::all_reduce_early(cudaStream_t s) {
-  const int64_t ca = actor.pixels ? actor.off_conv_w[1] : 0, cc = critic.pixels ? critic.off_conv_w[1] : 0;
-  float* p[2] = {buf.grads + ca, buf.grads + off_c + cc};
-  const int64_t n[2] = {off_c - ca, total - off_c - cc};
-  return comm.all_reduce_sum(p, n, 2, s);
-}
-int DDPG::all_reduce_late(cudaStream_t s) {
-  const int64_t ca = actor.pixels ? actor.off_conv_w[1] : 0, cc = critic.pixels ? critic.off_conv_w[1] : 0;
-  float* p[2] = {buf.grads, buf.grads + off_c};
-  const int64_t n[2] = {ca, cc};
-  if (ca + cc == 0) return CPP_OK;
-  return comm.all_reduce_sum(p, n, 2, s);
 }
 
 int DDPG::step_backward(const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
@@ -508,7 +479,6 @@ NAF::~NAF() {
   if (streams_ready) {
     for (auto& st : side) if (st) cudaStreamDestroy(st);
     if (cap_stream) cudaStreamDestroy(cap_stream);
-    if (comm_stream) cudaStreamDestroy(comm_stream);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
 }
@@ -517,7 +487,6 @@ int NAF::ensure_streams() {
   if (streams_ready) return CPP_OK;
   for (auto& st : side) CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
-  CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
   for (auto& e : ev) CPP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   streams_ready = true;
   return CPP_OK;
@@ -529,7 +498,7 @@ int NAF::ensure_streams() {
 int NAF::backward_body(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16,
                        int B, int B_global, bool multi, cudaStream_t s0) {
   cudaStream_t sm = multi ? side[0] : s0, sl = multi ? side[1] : s0, st = multi ? side[2] : s0;
-  enum { E_START = 0, E_C1, E_MU, E_L, E_V2, E_HEAD, E_BM, E_BL, E_JOIN, E_AR };
+  enum { E_START = 0, E_C1, E_MU, E_L, E_V2, E_HEAD, E_BM, E_BL };
   auto record = [&](int e, cudaStream_t x) -> int { if (multi) CPP_CHECK_CUDA(cudaEventRecord(ev[e], x)); return CPP_OK; };
   auto wait = [&](cudaStream_t x, int e) -> int { if (multi) CPP_CHECK_CUDA(cudaStreamWaitEvent(x, ev[e], 0)); return CPP_OK; };
   struct CapGuard { ~CapGuard() { g_cta_cap = kNumSMs; } } cap_guard;
@@ -574,16 +543,9 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
                                d_rep, s0));
     CPP_TRY(value.backward(P, s1, is_f16, m1, B, ws_v, dV, buf.grads, nullptr, s0, 1, wgs[0], tcs[0], nullptr, d_rep));
     g_cta_cap = kNumSMs;
-    if (comm.active()) {
-      cudaStream_t sa = multi ? comm_stream : s0;
-      CPP_TRY(record(E_JOIN, s0)); CPP_TRY(wait(sa, E_JOIN));
-      CPP_TRY(all_reduce_early(sa));
-      CPP_TRY(record(E_AR, sa));
-    }
     float* gr[1] = {buf.grads};
     CPP_TRY(conv1_wgrad_group(1, g1, ws1, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
-    if (comm.active()) { CPP_TRY(wait(s0, E_AR)); CPP_TRY(all_reduce_late(s0)); }
-    return CPP_OK;
+    return comm.all_reduce(buf.grads, total, s0);
   }
   const Net* g3[3] = {&value, &mu, &l};
   const float* pp3[3] = {P, P + off_m, P + off_l};
@@ -617,37 +579,11 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
   CPP_TRY(record(E_BL, sl));
   CPP_TRY(wait(s0, E_BM)); CPP_TRY(wait(s0, E_BL));
   g_cta_cap = kNumSMs;
-  if (comm.active()) {         // all gradients but conv1's: summed over the replicas next to the conv1 weight-gradient kernel
-    cudaStream_t sa = multi ? comm_stream : s0;
-    CPP_TRY(record(E_JOIN, s0)); CPP_TRY(wait(sa, E_JOIN));
-    CPP_TRY(all_reduce_early(sa));
-    CPP_TRY(record(E_AR, sa));
-  }
   {
     float* gr[3] = {buf.grads, buf.grads + off_m, buf.grads + off_l};
     CPP_TRY(conv1_wgrad_group(3, g3, ws3, gr, s1, is_f16, m1, B, wgs[0], s0, 1));
   }
-  if (comm.active()) { CPP_TRY(wait(s0, E_AR)); CPP_TRY(all_reduce_late(s0)); }
-  return CPP_OK;
-}
-
-int NAF::all_reduce_early(cudaStream_t s) {
-  const Net* nets[3] = {&value, &mu, &l};
-  const int64_t off[4] = {0, off_m, off_l, off_loss + 4};
-  float* p[3]; int64_t n[3];
-  for (int i = 0; i < 3; ++i) {
-    const int64_t c1 = nets[i]->pixels ? nets[i]->off_conv_w[1] : 0;
-    p[i] = buf.grads + off[i] + c1; n[i] = off[i + 1] - off[i] - c1;
-  }
-  return comm.all_reduce_sum(p, n, 3, s);
-}
-int NAF::all_reduce_late(cudaStream_t s) {
-  const Net* nets[3] = {&value, &mu, &l};
-  const int64_t off[3] = {0, off_m, off_l};
-  float* p[3]; int64_t n[3]; int64_t tot = 0;
-  for (int i = 0; i < 3; ++i) { p[i] = buf.grads + off[i]; n[i] = nets[i]->pixels ? nets[i]->off_conv_w[1] : 0; tot += n[i]; }
-  if (tot == 0) return CPP_OK;
-  return comm.all_reduce_sum(p, n, 3, s);
+  return comm.all_reduce(buf.grads, total, s0);      // data parallel: summed over the replicas (comm.cu); no-op for one replica
 }
 
 int NAF::stats_for(const void* x, int is_f16, int B, float* dst, const float* pinned, const float** out, cudaStream_t s) {
@@ -699,7 +635,7 @@ int NAF::backward(const void* s1, const float* action, const float* reward, cons
   const bool multi = step_streams_enabled(), graphs = step_graphs_enabled();
   if (multi || graphs) CPP_TRY(ensure_streams());
   if (!graphs) return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, s);
-  const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, comm.comm};
+  const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, comm.key()};
   const int ikey[5] = {is_f16, B, B_global, multi ? 1 : 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | ((g_wgrad_flush_steps / 16) << 24)};
   return run_graphed(graph, key, ikey, s, cap_stream, [&](cudaStream_t x) {
     return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, x);

@@ -108,13 +108,8 @@ struct DDPG {
   // streams / graph state
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;                      // origin stream of the graph capture (the caller's may be the legacy default stream)
-  cudaEvent_t ev[12] = {};
-  // data parallel: the gradient all-reduce runs inside the step (comm.cu) - everything but the conv1 gradients on comm_stream
-  // next to conv1's weight-gradient kernel, the two small conv1 ranges afterwards on the main stream
-  Comm comm;
-  cudaStream_t comm_stream = nullptr;
-  int all_reduce_early(cudaStream_t s);
-  int all_reduce_late(cudaStream_t s);
+  cudaEvent_t ev[10] = {};
+  Comm comm;                                              // data parallel: the gradient all-reduce runs inside the step (comm.cu)
   BackwardAux aux[2];                                     // side streams of the actor / critic backward chains (weight gradients)
   bool streams_ready = false;
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};   // packed-weight scratch per chain (actor, critic, target actor, target critic)
@@ -168,11 +163,8 @@ struct NAF {
   ~NAF();
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};     // mu chain, l chain, target value chain
   cudaStream_t cap_stream = nullptr;
-  cudaEvent_t ev[12] = {};
+  cudaEvent_t ev[10] = {};
   Comm comm;                                              // data parallel, as in DDPG
-  cudaStream_t comm_stream = nullptr;
-  int all_reduce_early(cudaStream_t s);
-  int all_reduce_late(cudaStream_t s);
   bool streams_ready = false;
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};    // packed-weight scratch per chain (value, mu, l, target value)
   void* wgs[3] = {nullptr, nullptr, nullptr};

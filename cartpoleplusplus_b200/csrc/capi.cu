@@ -301,6 +301,36 @@ int cpp_naf_comm_init(cpp_naf* a, int32_t rank, int32_t world, const void* id128
   return a->a.comm.init(rank, world, id128);
   API_END
 }
+int cpp_ddpg_p2p_prepare(cpp_ddpg* a, int32_t rank, int32_t world, void* handle_out64) {
+  API_BEGIN
+  NEED(a); NEED(handle_out64);
+  for (auto& gc : a->a.graph) gc.clear();
+  return a->a.comm.p2p_prepare(rank, world, a->a.total, handle_out64);
+  API_END
+}
+int cpp_ddpg_all_reduce_grads(cpp_ddpg* a, void* stream) {
+  API_BEGIN
+  NEED(a);
+  CPP_REQUIRE(a->a.bound, "agent buffers not bound");
+  return a->a.comm.all_reduce(a->a.buf.grads, a->a.total, ST(stream));
+  API_END
+}
+int cpp_naf_all_reduce_grads(cpp_naf* a, void* stream) {
+  API_BEGIN
+  NEED(a);
+  CPP_REQUIRE(a->a.bound, "agent buffers not bound");
+  return a->a.comm.all_reduce(a->a.buf.grads, a->a.total, ST(stream));
+  API_END
+}
+int cpp_ddpg_p2p_connect(cpp_ddpg* a, const void* handles) { API_BEGIN NEED(a); NEED(handles); return a->a.comm.p2p_connect(handles); API_END }
+int cpp_naf_p2p_prepare(cpp_naf* a, int32_t rank, int32_t world, void* handle_out64) {
+  API_BEGIN
+  NEED(a); NEED(handle_out64);
+  a->a.graph.clear();
+  return a->a.comm.p2p_prepare(rank, world, a->a.total, handle_out64);
+  API_END
+}
+int cpp_naf_p2p_connect(cpp_naf* a, const void* handles) { API_BEGIN NEED(a); NEED(handles); return a->a.comm.p2p_connect(handles); API_END }
 
 // ---------------------------------------------------------------- DDPG
 int cpp_ddpg_create(const cpp_ddpg_config* cfg, cpp_ddpg** out) {

@@ -159,7 +159,7 @@ class DDPGEngine(EngineBase):
     self.o = o
     self.max_batch = 0
     self.handle = None
-    self._comm_init = self.lib.cpp_ddpg_comm_init
+    self._comm_init, self._p2p_prepare, self._p2p_connect = self.lib.cpp_ddpg_comm_init, self.lib.cpp_ddpg_p2p_prepare, self.lib.cpp_ddpg_p2p_connect
     self._layout()
     rng = np.random.RandomState(seed)
     for part, net in self.nets.items():
@@ -208,8 +208,7 @@ class DDPGEngine(EngineBase):
     _lib.check(self.lib.cpp_ddpg_bind(h, C.byref(b)))
     self.handle, self.max_batch = h, B
     if self.lib_comm:                                 # a re-created agent joins the communicator group again (all ranks grow together)
-      self._comm_uid = self.dp.nccl_unique_id()
-      _lib.check(self._comm_init(self.handle, self.rank, self.world_size, self._comm_uid))
+      self._connect()
     self.out_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
     self.out_td = torch.zeros(B, dtype=torch.float32, device=self.device)
     self.out_q = torch.zeros(B, dtype=torch.float32, device=self.device)

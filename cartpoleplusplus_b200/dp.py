@@ -52,6 +52,17 @@ class DataParallel(object):
     out = (C.c_uint8 * 128)(*t.cpu().tolist())
     return out
 
+  def all_gather_bytes(self, buf):
+    """every rank's `buf` (ctypes uint8 array of one fixed size) -> one ctypes array, rank-major (CUDA IPC handles)"""
+    import ctypes as C
+    n = len(buf)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    out = [torch.zeros(n, dtype=torch.uint8, device=dev) for _ in range(self.world_size)]
+    dist.all_gather(out, mine)
+    flat = torch.cat(out).cpu().tolist()
+    return (C.c_uint8 * len(flat))(*flat)
+
   def all_reduce_sum(self, flat):
     if self.enabled:
       dist.all_reduce(flat, op=dist.ReduceOp.SUM)

@@ -153,7 +153,7 @@ class NAFEngine(EngineBase):
                                          ("target_value", naf.target_value_net)])
     self.kind, self.hp = naf.optimiser
     self.max_batch, self.handle = 0, None
-    self._comm_init = self.lib.cpp_naf_comm_init
+    self._comm_init, self._p2p_prepare, self._p2p_connect = self.lib.cpp_naf_comm_init, self.lib.cpp_naf_p2p_prepare, self.lib.cpp_naf_p2p_connect
     self._layout()
     rng = np.random.RandomState(seed)
     for part, net in self.nets.items():
@@ -208,8 +208,7 @@ class NAFEngine(EngineBase):
     _lib.check(self.lib.cpp_naf_bind(h, C.byref(b)))
     self.handle, self.max_batch = h, B
     if self.lib_comm:
-      self._comm_uid = self.dp.nccl_unique_id()
-      _lib.check(self._comm_init(self.handle, self.rank, self.world_size, self._comm_uid))
+      self._connect()
     A = self.naf.action_dim
     dev = self.device
     self.out = dict(l=torch.zeros(B * (A * (A + 1)) // 2, dtype=torch.float32, device=dev), loss=torch.zeros(1, dtype=torch.float32, device=dev),

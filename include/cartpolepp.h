@@ -256,11 +256,21 @@ int cpp_ddpg_debug_view(const cpp_ddpg* a, int32_t part, int32_t kind, int32_t i
  * The reference is a single replica; SURVEY.md 8e shards the minibatch over one process per GPU with ONE NCCL sum all-reduce of
  * the flat gradient buffer per grad-step.  cpp_nccl_unique_id (rank 0) -> the host broadcasts the 128 bytes (torch.distributed
  * is only the rendezvous) -> every rank calls cpp_*_comm_init on its bound agent.  From then on cpp_ddpg_train_step /
- * cpp_ddpg_step_backward / cpp_naf_backward sum the gradients over the replicas inside the step: everything but the conv1
- * gradients on a communication stream next to conv1's weight-gradient kernel, the two small conv1 ranges afterwards, all
- * captured into the step's CUDA graph; the loss and critic/NAF gradients are scaled by 1 / (B * world).  world = 1 (or
+ * cpp_ddpg_step_backward / cpp_naf_backward sum the gradients over the replicas inside the step, after its last gradient kernel
+ * and captured into the step's CUDA graph; the loss and critic/NAF gradients are scaled by 1 / (B * world).  world = 1 (or
  * never calling comm_init) is the single-replica behaviour.  NCCL is bound at run time (the libnccl.so.2 the process already
- * loaded, else the system one); CPP_ERR_NCCL when it is missing or a call fails. */
+ * loaded, else the system one); CPP_ERR_NCCL when it is missing or a call fails.
+ *
+ * Transport 1 (default, one NVSwitch box, <= 8 ranks): our own all-reduce over NVLink peer memory.  cpp_*_p2p_prepare allocates
+ * this rank's exchange block and returns its 64-byte CUDA IPC handle; the host all-gathers the handles; cpp_*_p2p_connect maps
+ * the peers' blocks.  Per step ONE kernel after the last gradient kernel: 128-bit peer stores of this rank's buffer into its slot
+ * in every peer's block, release flags, acquire of the peers' flags, local sum of the slots in rank order (csrc/comm.cu).
+ * Transport 2: NCCL (cpp_nccl_unique_id + cpp_*_comm_init), one ncclAllReduce at the same place. */
+int cpp_ddpg_p2p_prepare(cpp_ddpg* a, int32_t rank, int32_t world_size, void* out_host_handle_64_bytes);
+int cpp_ddpg_p2p_connect(cpp_ddpg* a, const void* handles_world_x_64_bytes);
+/* the exchange alone: the bound gradient buffer summed in place over the replicas (what the step does after its last gradient
+ * kernel); for callers that run actor.train / critic.train as separate calls, tests and scripts/bench_allreduce.py */
+int cpp_ddpg_all_reduce_grads(cpp_ddpg* a, void* stream);
 int cpp_nccl_unique_id(void* out_host_128_bytes);
 int cpp_nccl_version(int32_t* out);
 int cpp_ddpg_comm_init(cpp_ddpg* a, int32_t rank, int32_t world_size, const void* unique_id_128_bytes);
@@ -312,6 +322,9 @@ int cpp_naf_action_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t 
 int cpp_naf_value_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_value, void* stream);
 int cpp_naf_update_targets(cpp_naf* a, float coeff, void* stream);
 int cpp_naf_comm_init(cpp_naf* a, int32_t rank, int32_t world_size, const void* unique_id_128_bytes);
+int cpp_naf_p2p_prepare(cpp_naf* a, int32_t rank, int32_t world_size, void* out_host_handle_64_bytes);
+int cpp_naf_p2p_connect(cpp_naf* a, const void* handles_world_x_64_bytes);
+int cpp_naf_all_reduce_grads(cpp_naf* a, void* stream);
 /* as cpp_ddpg_debug_view; part: 0 value, 1 naf/output_action, 2 naf/l_values, 3 target value */
 int cpp_naf_debug_view(const cpp_naf* a, int32_t part, int32_t kind, int32_t index, int32_t B, int64_t* out4);
 

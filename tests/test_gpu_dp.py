@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+MODES = ("p2p", "nccl", "host")
+
+
 def _free_port():
   s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
   return p
@@ -29,7 +32,7 @@ def _moments(batch_states, C_):
   return out
 
 
-def _run(kind, world, rank, dp, steps=3, lib_comm=True):
+def _run(kind, world, rank, dp, steps=3, lib_comm=True, transport=None):
   from tests import gpu_util as U
   from oracle import nets_oracle as no
   from oracle.make_golden import ddpg_params, _batch
@@ -47,7 +50,7 @@ def _run(kind, world, rank, dp, steps=3, lib_comm=True):
     naf, nets, eng, o = U.make_naf(shape, True, {k: v.numpy() for k, v in P.items()}, batch_size=Bg, optimiser="Momentum",
                                    optimiser_args={"learning_rate": 0.01, "momentum": 0.9})
   if dp is not None:
-    eng.set_data_parallel(dp, lib_comm=lib_comm)
+    eng.set_data_parallel(dp, lib_comm=lib_comm, transport=transport)
   per = Bg // world
   for step in range(steps):
     batch = _batch(np.random.RandomState(100 + step), Bg, shape)
@@ -72,12 +75,13 @@ def _worker(rank, world, port, q):
   dp = dpmod.DataParallel(backend="nccl")
   out = {}
   for kind in ("ddpg", "naf"):
-    for lib_comm in (True, False):       # the all-reduce inside the step's graph (csrc/comm.cu), and issued from the host
-      mine = _run(kind, world, rank, dp, lib_comm=lib_comm)
+    # the all-reduce inside the step's graph (csrc/comm.cu) over NVLink peer memory / through NCCL, and issued from the host
+    for mode in MODES:
+      mine = _run(kind, world, rank, dp, steps=5, lib_comm=mode != "host", transport=None if mode == "host" else mode)
       gathered = [torch.zeros_like(mine) for _ in range(world)]
       dist.all_gather(gathered, mine)
-      assert all(torch.equal(g, gathered[0]) for g in gathered), "%s: replicas diverged (lib_comm=%s)" % (kind, lib_comm)
-      out[(kind, lib_comm)] = mine.cpu().numpy()
+      assert all(torch.equal(g, gathered[0]) for g in gathered), "%s: replicas diverged (%s)" % (kind, mode)
+      out[(kind, mode)] = mine.cpu().numpy()
   dp.barrier()
   if rank == 0:
     q.put(out)
@@ -102,7 +106,6 @@ def test_two_rank_nccl_replicas_identical_and_match_single_gpu():
     p.join(timeout=60)
     assert p.exitcode == 0
   for kind in ("ddpg", "naf"):
-    single = _run(kind, 1, 0, None).cpu().numpy()
-    for lib_comm in (True, False):
-      U.assert_close(out[(kind, lib_comm)], single, tol=2e-6,
-                     what="%s: 2-rank data parallel (lib_comm=%s) vs one GPU on the whole batch" % (kind, lib_comm))
+    single = _run(kind, 1, 0, None, steps=5).cpu().numpy()
+    for mode in MODES:
+      U.assert_close(out[(kind, mode)], single, tol=5e-6, what="%s: 2-rank data parallel (%s) vs one GPU on the whole batch" % (kind, mode))
