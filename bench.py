@@ -204,7 +204,7 @@ def build_agent(cfg, per_gpu_batch):
     for net in (value, naf.mu_net, naf.l_net):
       net.flat_params().copy_(torch.from_numpy(net.initial_flat(rng)))
     tvalue.set_as_target_network_for(value, o.target_update_rate)
-    nets = dict(value=value)
+    nets = dict(value=value, naf=naf)
   return eng, o, nets
 
 
@@ -400,6 +400,23 @@ def run_native(args):
     else:
       roof.update(kernel="whole step (per-kernel table only for c3)", achieved=step_tf, frac=step_tf / peaks["bf16_tflops"], traffic=None)
 
+  # ---- rollout latency (8f row 2): actor.action_given(state) / naf.action_given(state) at B = 1, host fp32 state in, host
+  # action out, as bullet_cartpole's env loop calls it once per step (ddpg_cartpole.py:317, naf_cartpole.py:349)
+  latency = None
+  if dp.rank == 0 and not args.skip_e2e:
+    rs_ = np.random.RandomState(5)
+    states = [(rs_.randint(0, 256, SHAPE).astype(np.float16) / np.float16(255)).astype(np.float32) for _ in range(8)]
+    net = nets["actor"] if is_ddpg else nets["naf"]
+    call = (lambda s_: net.action_given(s_)) if is_ddpg else (lambda s_: net.action_given(s_, add_noise=False))
+    for i in range(20):
+      call(states[i % 8])
+    ts = []
+    for i in range(200):
+      t0 = time.perf_counter(); call(states[i % 8]); ts.append((time.perf_counter() - t0) * 1e6)
+    latency = dict(call="%s.action_given(state fp32 %s), B=1, host in / host out" % ("ActorNetwork" if is_ddpg else "NafNetwork", list(SHAPE)),
+                   us_median=float(np.median(ts)), us_p10=float(np.percentile(ts, 10)), us_p90=float(np.percentile(ts, 90)), calls=200,
+                   h2d_bytes=int(states[0].nbytes), d2h_bytes=12,
+                   path="fp32 -> exact fp16 copy on the device, tensor-core trunk, FC stack; one CUDA graph replay per call")
   cpu = None
   if dp.rank == 0 and not args.skip_cpu_baseline:
     cpu = cpu_reference(args, steps=3, warmup=1)
@@ -418,7 +435,7 @@ def run_native(args):
                                                                    "host-issued torch.distributed" if args.host_allreduce else
                                                                    "inside the step's CUDA graph (csrc/comm.cu), transport %s" % eng.transport)),
                 clocks=clk, sustained=sustained, replicas_identical=replicas_identical, e2e=e2e, gpu_launches=int(launches),
-                roofline=roof, cpu_baseline=cpu)
+                action_latency=latency, roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line))
   dp.close()
 

@@ -144,6 +144,29 @@ class EngineBase(object):
       raise ValueError("data parallel on pixel states: pass moments=(mean_inv_s1, mean_inv_s2) of the GLOBAL batch "
                        "(ReplayMemory.batch_moments); a shard's own statistics would whiten every replica differently")
 
+  # ---- rollout path (8f row 2) ------------------------------------------------------------------------------------------
+  def _action_given(self, fast_fn, exact_fn, states, A):
+    """B states -> (B, A) actions through the graph-replayed fast path (tensor-core trunk on an exact fp16 copy of an fp32
+    state); a state that is not made of fp16 numbers is re-run through the exact fp32 route.  One pinned read-back."""
+    s = self.stage("s_act", states)
+    B = int(s.shape[0])
+    self._ensure(B)
+    n = B * A
+    if getattr(self, "_act_dev", None) is None or self._act_dev.numel() < n + 1:
+      self._act_dev = torch.zeros(n + 1, dtype=torch.float32, device=self.device)
+      self._act_pin = torch.zeros(n + 1, dtype=torch.float32, pin_memory=True)
+      self._act_ev = torch.cuda.Event()
+    _lib.check(fast_fn(self.handle, _lib.ptr(s), state_flag(s), B, _lib.ptr(self._act_dev), self._stream()))
+    self._act_pin[:n + 1].copy_(self._act_dev[:n + 1], non_blocking=True)
+    self._act_ev.record()
+    self._act_ev.synchronize()
+    if self._act_pin[n] != 0:                       # not the env's fp16-valued pixels: keep fp32 exact
+      _lib.check(exact_fn(self.handle, _lib.ptr(s), state_flag(s), B, _lib.ptr(self._act_dev), self._stream()))
+      self._act_pin[:n].copy_(self._act_dev[:n], non_blocking=True)
+      self._act_ev.record()
+      self._act_ev.synchronize()
+    return self._act_pin[:n].numpy().reshape(B, A).copy()
+
   def part_view(self, part):
     bufname, off, n = self.parts[part]
     return self.buffers[bufname][off:off + n]

@@ -72,7 +72,7 @@ cpp_net_workspace_bytes cpp_net_forward cpp_net_backward
 cpp_norm_scratch_doubles cpp_global_norm_scale cpp_optimiser_apply cpp_soft_update
 cpp_ddpg_create cpp_ddpg_destroy cpp_ddpg_workspace_bytes cpp_ddpg_layout cpp_ddpg_bind cpp_ddpg_set_moments
 cpp_ddpg_actor_backward cpp_ddpg_actor_apply cpp_ddpg_actor_train cpp_ddpg_critic_backward cpp_ddpg_critic_apply
-cpp_ddpg_critic_train cpp_ddpg_check_loss cpp_ddpg_action_given cpp_ddpg_update_targets cpp_ddpg_debug_view cpp_nccl_unique_id cpp_nccl_version cpp_ddpg_comm_init cpp_naf_comm_init cpp_ddpg_p2p_prepare cpp_ddpg_p2p_connect cpp_naf_p2p_prepare cpp_naf_p2p_connect cpp_ddpg_all_reduce_grads cpp_naf_all_reduce_grads
+cpp_ddpg_critic_train cpp_ddpg_check_loss cpp_ddpg_action_given cpp_ddpg_update_targets cpp_ddpg_debug_view cpp_nccl_unique_id cpp_nccl_version cpp_ddpg_comm_init cpp_naf_comm_init cpp_ddpg_p2p_prepare cpp_ddpg_p2p_connect cpp_naf_p2p_prepare cpp_naf_p2p_connect cpp_ddpg_all_reduce_grads cpp_naf_all_reduce_grads cpp_ddpg_action_given_fast cpp_naf_action_given_fast
 cpp_naf_create cpp_naf_destroy cpp_naf_workspace_bytes cpp_naf_layout cpp_naf_bind cpp_naf_set_moments
 cpp_naf_backward cpp_naf_apply cpp_naf_train cpp_naf_debug_values cpp_naf_action_given cpp_naf_value_given
 cpp_naf_update_targets cpp_naf_debug_view

@@ -59,8 +59,10 @@ void DDPG::carve(void* ws, bool assign) {
   double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(2 * norm_scratch_doubles());
   double* msc2 = cv.take<double>(moments_scratch_doubles(C));
   float* sc = cv.take<float>(4);
+  __half* af = cv.take<__half>(actor.pixels ? (size_t)B * actor.spec.H * actor.spec.W * actor.spec.Cin : 8);
   ws_bytes = cv.off;
   if (assign) mom_scratch2 = msc2;
+  if (assign) act_f16 = af;
   if (assign) {
     ws_actor = wa; ws_critic = wc; ws_target = wt; ws_target2 = wt2; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; mu = mu_;
     tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts2; tcs[3] = ts4; this->wgs[0] = wgs; this->wgs[1] = wgs2; dqda = dqda_; neg = neg_; mu2 = mu2_; q = q_; q2 = q2_; td = td_; dq = dq_;
@@ -78,6 +80,7 @@ int DDPG::bind(const cpp_ddpg_buffers& b) {
   carve(b.workspace, true);
   ones_ready = false; pinned1 = pinned2 = nullptr;
   for (auto& gc : graph) gc.clear();
+  graph_act.clear();
   return CPP_OK;
 }
 
@@ -392,8 +395,14 @@ int DDPG::check_loss(const void* s1, const float* action, const float* reward, c
   return CPP_OK;
 }
 
-int DDPG::action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
-  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+int DDPG::action_body(const void* state, int is_f16, int B, float* out, bool fast, cudaStream_t s) {
+  if (fast && !is_f16 && actor.pixels) {
+    CPP_TRY(launch_f32_to_f16_exact(reinterpret_cast<const float*>(state), (int64_t)B * actor.spec.H * actor.spec.W * actor.spec.Cin,
+                                    act_f16, out + (size_t)B * critic.action_dim, s));
+    state = act_f16; is_f16 = 1;
+  } else if (fast) {
+    CPP_CHECK_CUDA(cudaMemsetAsync(out + (size_t)B * critic.action_dim, 0, sizeof(float), s));
+  }
   const float* m;
   CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));     // statistics of the fed batch itself (B=1 in rollouts)
   const Net* g[1] = {&actor};
@@ -402,6 +411,20 @@ int DDPG::action_given(const void* state, int is_f16, int B, float* out, cudaStr
   CPP_TRY(trunk_forward_group(1, g, pp, wss, state, is_f16, m, B, tc_scr2, s));
   CPP_TRY(actor.forward_fc(buf.params, nullptr, B, ws_target, out, s));
   return CPP_OK;
+}
+
+int DDPG::action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  return action_body(state, is_f16, B, out, false, s);
+}
+
+int DDPG::action_given_fast(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  if (!use_graphs()) return action_body(state, is_f16, B, out, true, s);
+  CPP_TRY(ensure_streams());
+  const void* const key[8] = {state, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const int ikey[5] = {is_f16, B, 0, 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1)};
+  return run_graphed(graph_act, key, ikey, s, cap_stream, [&](cudaStream_t st) { return action_body(state, is_f16, B, out, true, st); });
 }
 
 int DDPG::update_targets(float coeff, cudaStream_t s) {
@@ -452,9 +475,10 @@ void NAF::carve(void* ws, bool assign) {
   double* msc = cv.take<double>(moments_scratch_doubles(C)); double* nsc = cv.take<double>(norm_scratch_doubles());
   float* sc = cv.take<float>(4);
   float* drep = cv.take<float>((size_t)B * rep_dim);
+  __half* af = cv.take<__half>(value.pixels ? (size_t)B * value.spec.H * value.spec.W * value.spec.Cin : 8);
   ws_bytes = cv.off;
   if (assign) {
-    d_rep = drep;
+    d_rep = drep; act_f16 = af;
     ws_v = wv; ws_m = wm; ws_l = wl; ws_t = wt; tc_scr1 = ts1; tc_scr2 = ts2; wg_scr = wgs; V = V_;
     tcs[0] = ts1; tcs[1] = ts3; tcs[2] = ts4; tcs[3] = ts2; this->wgs[0] = wgs; this->wgs[1] = wgs1; this->wgs[2] = wgs2; mom_scratch2 = msc2; V2 = V2_; muo = mu_; lv = lv_; dV = dV_; dmu = dmu_; dl = dl_;
     mi1 = mi1_; mi2 = mi2_; mom_scratch = msc; norm_scratch = nsc; scale2 = sc;
@@ -470,7 +494,7 @@ int NAF::bind(const cpp_naf_buffers& b) {
   buf = b; bound = true;
   carve(b.workspace, true);
   pinned1 = pinned2 = nullptr;
-  graph.clear();
+  graph.clear(); graph_act.clear();
   return CPP_OK;
 }
 
@@ -673,8 +697,14 @@ int NAF::debug_values(const void* s1, const float* action, const float* reward, 
   return CPP_OK;
 }
 
-int NAF::action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
-  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+int NAF::action_body(const void* state, int is_f16, int B, float* out, bool fast, cudaStream_t s) {
+  if (fast && !is_f16 && value.pixels) {
+    CPP_TRY(launch_f32_to_f16_exact(reinterpret_cast<const float*>(state), (int64_t)B * value.spec.H * value.spec.W * value.spec.Cin,
+                                    act_f16, out + (size_t)B * A, s));
+    state = act_f16; is_f16 = 1;
+  } else if (fast) {
+    CPP_CHECK_CUDA(cudaMemsetAsync(out + (size_t)B * A, 0, sizeof(float), s));
+  }
   const float* m;
   CPP_TRY(stats_for(state, is_f16, B, mi2, nullptr, &m, s));
   if (share) {    // value trunk and hidden layers, then the mu head
@@ -688,6 +718,20 @@ int NAF::action_given(const void* state, int is_f16, int B, float* out, cudaStre
   char* wss[1] = {ws_t};
   CPP_TRY(trunk_forward_group(1, g, pp, wss, state, is_f16, m, B, tc_scr2, s));
   return mu.forward_fc(buf.params + off_m, nullptr, B, ws_t, out, s);
+}
+
+int NAF::action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  return action_body(state, is_f16, B, out, false, s);
+}
+
+int NAF::action_given_fast(const void* state, int is_f16, int B, float* out, cudaStream_t s) {
+  CPP_NEED_BOUND(); CPP_NEED_BATCH(B);
+  if (!step_graphs_enabled()) return action_body(state, is_f16, B, out, true, s);
+  CPP_TRY(ensure_streams());
+  const void* const key[8] = {state, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const int ikey[5] = {is_f16, B, 0, 0, (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1)};
+  return run_graphed(graph_act, key, ikey, s, cap_stream, [&](cudaStream_t st) { return action_body(state, is_f16, B, out, true, st); });
 }
 
 int NAF::value_given(const void* state, int is_f16, int B, float* out, cudaStream_t s) {

@@ -118,6 +118,13 @@ struct DDPG {
   int check_loss(const void* s1, const float* action, const float* reward, const float* mask, const void* s2, int is_f16, int B,
                  float* loss, float* td_out, float* q_out, cudaStream_t s);
   int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
+  // the rollout path (B = 1 per env step): an fp32 state is copied to fp16 on the device (exact for the env's k/255 pixels), runs
+  // the tensor-core trunk, and the whole chain replays as one CUDA graph.  out [B*A + 1]: actions, then 1.0 if some element of the
+  // state was NOT an fp16 number (the caller must then use action_given, which keeps fp32 states exact)
+  int action_given_fast(const void* state, int is_f16, int B, float* out, cudaStream_t s);
+  int action_body(const void* state, int is_f16, int B, float* out, bool fast, cudaStream_t s);
+  __half* act_f16 = nullptr;                              // fp16 copy of a fed fp32 state (action_given_fast)
+  GraphCache graph_act;
   int update_targets(float coeff, cudaStream_t s);
 };
 
@@ -152,6 +159,10 @@ struct NAF {
                    float* l_out, float* loss, float* V_out, float* A_out, float* V2_out, cudaStream_t s);
   int action_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
   int value_given(const void* state, int is_f16, int B, float* out, cudaStream_t s);
+  int action_given_fast(const void* state, int is_f16, int B, float* out, cudaStream_t s);     // as DDPG::action_given_fast
+  int action_body(const void* state, int is_f16, int B, float* out, bool fast, cudaStream_t s);
+  __half* act_f16 = nullptr;
+  GraphCache graph_act;
   int update_targets(float coeff, cudaStream_t s);
   // share mode: mu and l heads on the representation the value network left in `wsv`
   const float* shared_rep(char* wsv, int B) const;

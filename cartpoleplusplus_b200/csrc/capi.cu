@@ -417,6 +417,9 @@ int cpp_ddpg_check_loss(cpp_ddpg* a, const void* s1, const float* action, const 
 int cpp_ddpg_action_given(cpp_ddpg* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
   API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.action_given(state, is_f16, B, out, ST(stream)); API_END
 }
+int cpp_ddpg_action_given_fast(cpp_ddpg* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
+  API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.action_given_fast(state, is_f16, B, out, ST(stream)); API_END
+}
 int cpp_ddpg_update_targets(cpp_ddpg* a, float coeff, void* stream) { API_BEGIN NEED(a); return a->a.update_targets(coeff, ST(stream)); API_END }
 
 static int debug_view(const Net& net, const char* ws_part, const void* ws_base, int kind, int index, int B, int64_t* out4) {
@@ -509,6 +512,9 @@ int cpp_naf_debug_values(cpp_naf* a, const void* s1, const float* action, const 
 }
 int cpp_naf_action_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
   API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.action_given(state, is_f16, B, out, ST(stream)); API_END
+}
+int cpp_naf_action_given_fast(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
+  API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.action_given_fast(state, is_f16, B, out, ST(stream)); API_END
 }
 int cpp_naf_value_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
   API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.value_given(state, is_f16, B, out, ST(stream)); API_END

@@ -67,6 +67,7 @@ constexpr int kConvCout = 10;     // every conv of the reference trunk has 10 fi
 
 // elementwise.cu
 int launch_state_to_f32(const void* state, int is_f16, int B, int dim, float* dst, int ld, cudaStream_t s);
+int launch_f32_to_f16_exact(const float* src, int64_t n, __half* dst, float* inexact, cudaStream_t s);
 int launch_copy_cols(const float* src, int src_ld, int B, int cols, float* dst, int dst_ld, int dst_col0, cudaStream_t s);
 int launch_act_grad(const float* d_out, int d_ld, const float* out, int out_ld, int act, int B, int n, float* d_pre, int p_ld, cudaStream_t s);
 int launch_heads_dgrad(const float* dmu_pre, const float* Wmu, int A, const float* dl_pre, const float* Wl, int NL, int B, int D,

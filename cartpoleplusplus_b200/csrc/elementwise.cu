@@ -246,6 +246,24 @@ int launch_state_to_f32(const void* state, int is_f16, int B, int dim, float* ds
   return CPP_OK;
 }
 
+// fp32 -> fp16 copy of an environment state whose values are fp16 numbers stored as fp32 (bullet_cartpole.py:239-242 renders
+// fp16(k) / 255 in fp16 into a float32 array); *inexact is set to 1 when an element does not survive the round trip
+__global__ void f32_to_f16_exact_kernel(const float* __restrict__ src, int64_t n, __half* __restrict__ dst, float* __restrict__ inexact) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  const __half h = __float2half_rn(v);
+  dst[i] = h;
+  if (!(__half2float(h) == v)) *inexact = 1.f;     // (NaN lands here too); racing writers all store the same value
+}
+int launch_f32_to_f16_exact(const float* src, int64_t n, __half* dst, float* inexact, cudaStream_t s) {
+  if (n == 0) return CPP_OK;
+  CPP_CHECK_CUDA(cudaMemsetAsync(inexact, 0, sizeof(float), s));
+  f32_to_f16_exact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, n, dst, inexact);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
 __global__ void copy_cols_kernel(const float* __restrict__ src, int src_ld, int B, int cols, float* __restrict__ dst, int dst_ld, int c0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * cols) return;

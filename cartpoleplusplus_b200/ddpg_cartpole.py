@@ -299,12 +299,7 @@ class DDPGEngine(EngineBase):
             self.out_q[:B].cpu().numpy().reshape(B, 1))
 
   def action_given(self, states):
-    s = self.stage("s_act", states)
-    B = int(s.shape[0])
-    self._ensure(B)
-    A = self.nets["actor"].action_dim
-    _lib.check(self.lib.cpp_ddpg_action_given(self.handle, _lib.ptr(s), state_flag(s), B, _lib.ptr(self.out_action), self._stream()))
-    return self.out_action[:B * A].cpu().numpy().reshape(B, A)
+    return self._action_given(self.lib.cpp_ddpg_action_given_fast, self.lib.cpp_ddpg_action_given, states, self.nets["actor"].action_dim)
 
 
 class DeepDeterministicPolicyGradientAgent(object):

@@ -272,11 +272,7 @@ class NAFEngine(EngineBase):
     return [np.squeeze(v) for v in vals]
 
   def action_given(self, states):
-    s = self.stage("s_act", states)
-    B = int(s.shape[0]); self._ensure(B)
-    A = self.naf.action_dim
-    _lib.check(self.lib.cpp_naf_action_given(self.handle, _lib.ptr(s), state_flag(s), B, _lib.ptr(self.out["act"]), self._stream()))
-    return self.out["act"][:B * A].cpu().numpy().reshape(B, A)
+    return self._action_given(self.lib.cpp_naf_action_given_fast, self.lib.cpp_naf_action_given, states, self.naf.action_dim)
 
   def value_given(self, states):
     s = self.stage("s_act", states)

@@ -243,6 +243,13 @@ int cpp_ddpg_check_loss(cpp_ddpg* a, const void* s1, const float* action, const 
                         const float* mask, const void* s2, int32_t is_f16, int32_t B,
                         float* loss, float* td, float* q, void* stream);
 int cpp_ddpg_action_given(cpp_ddpg* a, const void* state, int32_t is_f16, int32_t B, float* out_action, void* stream);
+/* 8f row 2, the rollout latency path of ActorNetwork.action_given (ddpg_cartpole.py:121-138), called once per env step with
+ * B = 1: an fp32 state is copied to fp16 on the device - exact for what the env produces, fp16(k)/255 stored in a float32 array,
+ * bullet_cartpole.py:239-242 - so that it takes the tensor-core trunk, and the whole chain (copy, statistics, conv1-3, FC stack)
+ * replays as ONE CUDA graph per (state buffer, output buffer).  out_action_and_flag (dev) holds B*A actions followed by one
+ * float that is 1.0 when some element of the state was NOT an fp16 number: the caller must then use cpp_ddpg_action_given,
+ * which keeps fp32 states exact (CUDA-core route). */
+int cpp_ddpg_action_given_fast(cpp_ddpg* a, const void* state, int32_t is_f16, int32_t B, float* out_action_and_flag, void* stream);
 int cpp_ddpg_update_targets(cpp_ddpg* a, float coeff, void* stream);
 /* parity instrumentation (tests/test_gpu_step_pinned.py): where one intermediate of the LAST step lives inside the bound
  * workspace, so that the fp64 oracle can be evaluated with the routing (2x2 max-pool winners, ReLU gates) the GPU took.
@@ -319,6 +326,8 @@ int cpp_naf_debug_values(cpp_naf* a, const void* s1, const float* action, const 
                          const void* s2, int32_t is_f16, int32_t B,
                          float* l_values, float* loss, float* V, float* Aout, float* V2, void* stream);
 int cpp_naf_action_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_action, void* stream);
+/* as cpp_ddpg_action_given_fast (naf_cartpole.py:247-262) */
+int cpp_naf_action_given_fast(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_action_and_flag, void* stream);
 int cpp_naf_value_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out_value, void* stream);
 int cpp_naf_update_targets(cpp_naf* a, float coeff, void* stream);
 int cpp_naf_comm_init(cpp_naf* a, int32_t rank, int32_t world_size, const void* unique_id_128_bytes);

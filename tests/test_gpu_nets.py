@@ -415,3 +415,56 @@ def test_ddpg_schedule_switches_do_not_change_results():
   for k in range(1, len(variants)):
     U.assert_close(outs[k][:-4], outs[0][:-4], tol=2e-6, what="variant %s vs default" % variants[k])
     U.assert_close(outs[k][-4], outs[0][-4], tol=2e-6, what="loss")
+
+
+# ------------------------------------------------------------------------------------------ rollout path (8f row 2)
+@pytest.mark.parametrize("agent", ["ddpg", "naf", "naf_shared"])
+def test_action_given_fast_path(agent):
+  """ActorNetwork.action_given / NafNetwork.action_given at B = 1 (ddpg_cartpole.py:121-138, naf_cartpole.py:247-262): an fp32
+  environment state made of fp16 numbers (bullet_cartpole.py:239-242) takes the tensor-core trunk through an exact fp16 copy
+  and replays as one CUDA graph - same bits as feeding the fp16 array, within 1e-5 of the fp64 oracle on every replay; an fp32
+  state that is NOT made of fp16 numbers is detected on the device and answered by the exact fp32 route"""
+  shape = (64, 64, 3, 1, 3)
+  rs = np.random.RandomState(3)
+  if agent == "ddpg":
+    from oracle.make_golden import ddpg_params
+    P = ddpg_params(rs, shape, True)
+    nets, eng, o = U.make_ddpg(shape, True, {k: v.numpy() for k, v in P.items()}, batch_size=4)
+    orc = no.DDPGOracle(shape, True, P)
+    act = nets["actor"].action_given
+  else:
+    share = agent == "naf_shared"
+    value = no.naf_value("value", shape, True)
+    heads = no.naf_shared_heads(value.fc[-2].out) if share else (no.naf_mu(shape, True), no.naf_l(shape, True))
+    P = {}
+    for d in (value,) + tuple(heads):
+      P.update(no.init_params(d, rs))
+    P["naf/output_action/fc/weights"] = torch.tensor(rs.uniform(-0.3, 0.3, tuple(P["naf/output_action/fc/weights"].shape)).astype(np.float32), dtype=torch.float64)
+    P.update(no.retarget({k: v for k, v in P.items() if k.startswith("value/")}, "value", "target_value"))
+    naf, nets, eng, o = U.make_naf(shape, True, {k: v.numpy() for k, v in P.items()}, batch_size=4,
+                                   extra=["--share-input-state-representation"] if share else [])
+    orc = no.NAFOracle(shape, True, P, share=share)
+    act = lambda s: naf.action_given(s, add_noise=False)
+  from cartpoleplusplus_b200 import _lib
+  launches = []
+  for trial in range(4):                                    # eager, capture, replay, replay - a new state every time
+    k = rs.randint(0, 256, shape)
+    s16 = (k.astype(np.float16) / np.float16(255)).astype(np.float16)
+    s32 = s16.astype(np.float32)                            # what the env hands over: fp16 numbers in a float32 array
+    want = orc.action_given(s16).numpy()
+    l0 = _lib.lib().cpp_launch_count()
+    got32 = act(s32)
+    launches.append(_lib.lib().cpp_launch_count() - l0)
+    assert got32.shape == (1, 2)
+    U.assert_close(got32, want, what="%s action_given(fp32 env state), call %d" % (agent, trial))
+    assert np.array_equal(got32, act(s16)), "fp32 env state and its fp16 copy must give the same bits"
+  # an arbitrary fp32 state: flagged on the device, answered by the exact fp32 route
+  s_any = rs.uniform(0, 1, shape).astype(np.float32)
+  got = act(s_any)
+  U.assert_close(got, orc.action_given(s_any).numpy(), what="%s action_given(arbitrary fp32 state)" % agent)
+  exact = np.zeros((1, 2), np.float32)
+  dev_s = torch.from_numpy(s_any[None]).cuda(); dev_o = torch.zeros(2, device="cuda")
+  fn = _lib.lib().cpp_ddpg_action_given if agent == "ddpg" else _lib.lib().cpp_naf_action_given
+  _lib.check(fn(eng.handle, _lib.ptr(dev_s), 0, 1, _lib.ptr(dev_o), _lib.stream_ptr()))
+  assert np.array_equal(got.reshape(-1), dev_o.cpu().numpy())
+  print(agent, "kernels per action_given call (eager, capture, replay, replay):", launches)
