@@ -30,6 +30,7 @@ extern int g_bwd_critic_sms;
 extern int g_fwd_actor_sms;
 extern int g_conv1_split;
 extern int g_wgrad_flush_steps;   // mma.sync weight gradient: MMA K-steps accumulated on the tensor cores between two fp32 flushes
+extern int g_wgrad_tc;            // 1: conv1 weight gradient on tcgen05 (conv_wgrad_tc.cu) where supported, 0: always mma.sync
 extern int g_cta_cap;               // SMs a persistent kernel may occupy (agents lower it while independent chains share the GPU)
 static inline int sm_budget() { return g_cta_cap < 1 ? 1 : (g_cta_cap > 148 ? 148 : g_cta_cap); }
 #define CPP_CHECK_LAUNCH() do { ++cpp::g_launch_count; CPP_CHECK_CUDA(cudaGetLastError()); } while (0)

@@ -22,6 +22,7 @@
 //    few bands, which also bounds the length of the tensor-core accumulation chains); partials are reduced in fixed order.
 #include <algorithm>
 #include "conv_wgrad_mma.cuh"
+#include "conv_wgrad_tc.cuh"
 
 namespace cpp {
 namespace wg {
@@ -535,7 +536,9 @@ bool conv_wgrad_mma_supported(int nets, int H, int W, int C, int KS, int dup) {
 int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS, int dup) {
   Plan P{};
   if (build_plan(nets, 1, H, W, C, KS, &P, dup) != CPP_OK) return -1;
-  return (int64_t)(al256(16) + al256((size_t)2 * kNumSMs * P.part_floats * 4) + al256((size_t)P.part_floats * 4));
+  const int64_t own = (int64_t)(al256(16) + al256((size_t)2 * kNumSMs * P.part_floats * 4) + al256((size_t)P.part_floats * 4));
+  const int64_t tcb = dup == 0 ? (int64_t)al256(16) + wgtc::scratch_bytes(nets, H, W, C, KS) : 0;     // the tcgen05 route shares the scratch
+  return std::max(own, tcb);
 }
 
 template <int MT, int NT>
@@ -586,6 +589,8 @@ int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int
     wgrad_absmax_kernel<<<dim3(blocks, nets), 256, 0, s>>>(P);
     CPP_CHECK_LAUNCH();
   }
+  if (dup == 0 && g_wgrad_tc && wgtc::supported(nets, H, W, C, KS))       // tcgen05 route (conv_wgrad_tc.cu): conv1 of c3-class inputs
+    return wgtc::launch(x_f16, mean_inv, nets, d_pooled, amax, B, H, W, C, KS, dw, db, P.gmax, reinterpret_cast<char*>(scratch) + al256(16), s);
   int st;
   switch (P.MT) {
     case 1: st = launch_nt<1>(P, s); break;

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Where does a conv_wgrad_tc CTA spend its cycles?  Needs the diagnosis build:
+  CARTPOLEPP_NVCC_EXTRA=-DWGTC_PROF python -c "import __graft_entry__ as g; g.build(force=True)"
+prints per-role wait cycles (mean / min / max over the CTAs of the LAST launch).  Numbers under this build are not bench values."""
+import ctypes as C
+import os
+import sys
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+NAMES = ["kernel", "mma loop", "mma waits FULL (fill-bound)", "mma waits EMPTY_ACC (epilogue-bound)", "fill loop",
+         "fill waits FREE (mma-bound)", "fill waits STAGE (TMA latency)", "epi loop", "epi waits FULL_ACC", "producer waits FULL",
+         "steps", "-"]
+
+
+def main():
+  from cartpoleplusplus_b200 import _lib as L
+  import torch
+  lib = L.lib()
+  import scripts.bench_kernels as bk
+  sys.argv = ["bench_kernels.py", "--only", "conv1_wgrad_mma", "--reps", "3"]
+  bk.main()
+  torch.cuda.synchronize()
+  buf = (C.c_ulonglong * (160 * 12))()
+  assert lib.cpp_debug_wgrad_tc_prof(buf) == 0
+  a = np.frombuffer(buf, dtype=np.uint64).reshape(160, 12).astype(np.float64)
+  a = a[a[:, 0] > 0]
+  print("== conv_wgrad_tc: %d CTAs" % a.shape[0])
+  for i, n in enumerate(NAMES):
+    print("  %-42s mean %9.0f   min %9.0f   max %9.0f" % (n, a[:, i].mean(), a[:, i].min(), a[:, i].max()))
+
+
+if __name__ == "__main__":
+  main()

@@ -228,12 +228,27 @@ WGRAD = [
     (3, 25, 25, 10, 5, 1, 2),         # odd size
     (256, 32, 32, 10, 5, 1, 2),       # c3 conv2 at full batch
     (5, 8, 8, 3, 5, 1, False),        # smallest legal image
+    (3, 32, 32, 9, 5, 2, False),      # tcgen05 route (conv_wgrad_tc.cu): narrower rows, two K-steps per row
+    (2, 40, 48, 6, 5, 1, False),      # tcgen05 route: 6 channels (4 window blocks + flags), one network (N = 32)
+    (150, 16, 16, 8, 5, 2, False),    # tcgen05 route: more images than SMs' segments are long (several images per CTA)
+    (2, 21, 32, 11, 5, 2, False),     # tcgen05 route: odd height (last row has no pooled gradient), widest window (7 + 1 blocks)
 ]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,KS,nets,pieces", WGRAD, ids=["%dx%dx%dx%d_k%d_n%d_p%d" % w for w in WGRAD])
 def test_conv_wgrad_mma(B, H, W, Cin, KS, nets, pieces):
   print("wgrad_mma (dw, db) rel err vs fp64:", run_wgrad_mma(B, H, W, Cin, KS, nets, seed=B + H + Cin + nets, pieces=pieces))
+
+
+def test_conv_wgrad_route_switch():
+  """cpp_set_option("wgrad_tc", 0) sends the same call down the mma.sync kernel: both routes hold the same bound"""
+  L, lib = _lib()
+  try:
+    L.check(lib.cpp_set_option(b"wgrad_tc", 0))
+    print("wgrad mma.sync route c3 shape:", run_wgrad_mma(8, 64, 64, 9, 5, 2, seed=21))
+  finally:
+    L.check(lib.cpp_set_option(b"wgrad_tc", 1))
+  print("wgrad tcgen05 route c3 shape:", run_wgrad_mma(8, 64, 64, 9, 5, 2, seed=21))
 
 
 def test_conv_wgrad_mma_full_batch_c3():
