@@ -22,6 +22,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (!ok && ++spins > (1u << 24)) __trap();   // a lost arrival must fail loudly, never hang the GPU
   } while (!ok);
 }
+// the same wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or the hint, in ns,
+// expires) instead of re-issuing the poll - a waiting warp then costs no issue slots
+__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
+    if (!ok && ++spins > (1u << 20)) __trap();
+  } while (!ok);
+}
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // the same wait for roles that may sit idle for microseconds (epilogue between flush periods, producer ahead of the fill): a
 // spinning warp takes issue slots from the warps that do the work, so back off between polls
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {

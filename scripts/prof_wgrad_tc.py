@@ -8,9 +8,9 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-NAMES = ["kernel", "mma loop", "mma waits FULL (fill-bound)", "mma waits EMPTY_ACC (epilogue-bound)", "fill loop",
-         "fill waits FREE (mma-bound)", "fill waits STAGE (TMA latency)", "epi loop", "epi waits FULL_ACC", "producer waits FULL",
-         "steps", "-"]
+NAMES = ["kernel", "mma loop", "mma waits FULL (fill-bound)", "mma waits EMPTY_ACC (epilogue-bound)", "warp 0 loop",
+         "warp 0 (X items) waits FREE (mma-bound)", "warp 0 waits STAGE_FULL (TMA)", "warp 0 item work", "warp 4 (dY items) waits FREE",
+         "producer waits STAGE_FREE", "warp 4 item work", "warp 4 waits STAGE_FULL"]
 
 
 def main():
