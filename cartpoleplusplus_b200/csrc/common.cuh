@@ -31,6 +31,7 @@ extern int g_fwd_actor_sms;
 extern int g_conv1_split;
 extern int g_wgrad_flush_steps;   // mma.sync weight gradient: MMA K-steps accumulated on the tensor cores between two fp32 flushes
 extern int g_wgrad_tc;            // 1: conv1 weight gradient on tcgen05 (conv_wgrad_tc.cu) where supported, 0: always mma.sync
+extern int g_fc_tc;               // FC passes on tcgen05 (fc_tc.cu): 1 forward, 2 input gradient, 4 weight gradient, 8 = also GEMMs below the size where it pays
 extern int g_cta_cap;               // SMs a persistent kernel may occupy (agents lower it while independent chains share the GPU)
 static inline int sm_budget() { return g_cta_cap < 1 ? 1 : (g_cta_cap > 148 ? 148 : g_cta_cap); }
 #define CPP_CHECK_LAUNCH() do { ++cpp::g_launch_count; CPP_CHECK_CUDA(cudaGetLastError()); } while (0)
@@ -87,8 +88,13 @@ struct GemmArgs {
   int M, N, K;
   int epi; const float* bias; int act;      // EPI_BIAS_ACT
   const float* aux; int aux_ld; int mask_cols;   // EPI_RELU_MASK: C[m][n] *= (aux[m][n] > 0) for n < mask_cols
+  float* colsum;                            // tensor-core route, transA only: also out[n] = sum_k B[k][n] (an all-ones row appended to A);
+                                            // the FFMA route ignores it (callers check gemm_tc_wanted and launch colsum themselves)
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t s);
+// fc_tc.cu: the same contract on tcgen05 (three bf16 pieces per fp32 operand)
+bool gemm_tc_wanted(const GemmArgs& g);
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t s);
 
 // conv.cu
 struct ConvLayer {

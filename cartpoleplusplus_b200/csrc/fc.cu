@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(128) gemm_kernel(GemmArgs g) {
 
 int launch_gemm(const GemmArgs& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return CPP_OK;
+  if (gemm_tc_wanted(g)) return launch_gemm_tc(g, s);
   dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM));
   if (g.transA && g.transB) gemm_kernel<true, true><<<grid, 128, 0, s>>>(g);
   else if (g.transA) gemm_kernel<true, false><<<grid, 128, 0, s>>>(g);

@@ -268,6 +268,19 @@ int trunk_forward_group(int n, const Net* const* nets, const float* const* param
   return CPP_OK;
 }
 
+// dW = x^T . dPre and db = column sums of dPre of one FC layer: one tcgen05 GEMM with an all-ones row appended to x^T when the
+// tensor-core route takes the layer (fc_tc.cu), else the FFMA GEMM + the column-sum kernel
+static int fc_wgrad(const float* x, int xld, const float* dpre, int dld, int B, int in, int out, float* dw, float* db, cudaStream_t sw) {
+  GemmArgs g{};
+  g.A = x; g.lda = xld; g.transA = 1;
+  g.B = dpre; g.ldb = dld; g.transB = 0;
+  g.C = dw; g.ldc = out;
+  g.M = in; g.N = out; g.K = B; g.epi = EPI_NONE;
+  if (gemm_tc_wanted(g)) { g.colsum = db; return launch_gemm(g, sw); }
+  CPP_TRY(launch_gemm(g, sw));
+  return launch_colsum(dpre, dld, B, out, db, sw);
+}
+
 int Net::backward(const float* params, const void* state, int is_f16, const float* mean_inv, int B, void* ws_,
                   const float* d_out, float* grads, float* d_action, cudaStream_t s, int defer_conv1, void* wg_scratch,
                   void* tc_scratch, BackwardAux* aux, const float* d_rep_extra) const {
@@ -300,13 +313,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
         const float* x = fc_input(L, ws, i, &xld);
         const float* dpre = i == last ? reinterpret_cast<const float*>(ws + L.dTop) : reinterpret_cast<const float*>(ws + L.dX[i + 1]);
         const int dld = i == last ? out_dim[last] : in_dim[i + 1];
-        GemmArgs g{};                                        // dW = x^T . dPre
-        g.A = x; g.lda = xld; g.transA = 1;
-        g.B = dpre; g.ldb = dld; g.transB = 0;
-        g.C = grads + off_fc_w[i]; g.ldc = out_dim[i];
-        g.M = in_dim[i]; g.N = out_dim[i]; g.K = B; g.epi = EPI_NONE;
-        CPP_TRY(launch_gemm(g, sw));
-        CPP_TRY(launch_colsum(dpre, dld, B, out_dim[i], grads + off_fc_b[i], sw));
+        CPP_TRY(fc_wgrad(x, xld, dpre, dld, B, in_dim[i], out_dim[i], grads + off_fc_w[i], grads + off_fc_b[i], sw));
       }
     }
   }
@@ -324,13 +331,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
       const float* x = fc_input(L, ws, i, &xld);
       const float* dpre = i == last ? reinterpret_cast<const float*>(ws + L.dTop) : reinterpret_cast<const float*>(ws + L.dX[last]);
       const int pld = i == last ? out_dim[last] : in_dim[last];
-      GemmArgs g{};                                        // dW = x^T . dPre
-      g.A = x; g.lda = xld; g.transA = 1;
-      g.B = dpre; g.ldb = pld; g.transB = 0;
-      g.C = grads + off_fc_w[i]; g.ldc = out_dim[i];
-      g.M = in_dim[i]; g.N = out_dim[i]; g.K = B; g.epi = EPI_NONE;
-      CPP_TRY(launch_gemm(g, sw));
-      CPP_TRY(launch_colsum(dpre, pld, B, out_dim[i], grads + off_fc_b[i], sw));
+      CPP_TRY(fc_wgrad(x, xld, dpre, pld, B, in_dim[i], out_dim[i], grads + off_fc_w[i], grads + off_fc_b[i], sw));
     }
     dcur = reinterpret_cast<float*>(ws + L.dX[concat_at]);
     dld = in_dim[concat_at];
@@ -348,13 +349,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     const float* x = fc_input(L, ws, i, &xld);
     if (grads != nullptr) {
       CPP_TRY(ready());
-      GemmArgs g{};                                        // dW = x^T . dPre
-      g.A = x; g.lda = xld; g.transA = 1;
-      g.B = dcur; g.ldb = dld; g.transB = 0;
-      g.C = grads + off_fc_w[i]; g.ldc = out_dim[i];
-      g.M = in_dim[i]; g.N = out_dim[i]; g.K = B; g.epi = EPI_NONE;
-      CPP_TRY(launch_gemm(g, sw));
-      CPP_TRY(launch_colsum(dcur, dld, B, out_dim[i], grads + off_fc_b[i], sw));
+      CPP_TRY(fc_wgrad(x, xld, dcur, dld, B, in_dim[i], out_dim[i], grads + off_fc_w[i], grads + off_fc_b[i], sw));
     }
     const bool need_dx = (i > stop_at) || (i == 0 && pixels && grads != nullptr) || (concat_at == i && d_action != nullptr);
     if (!need_dx) break;     // (a low-dim network without hidden layers: the representation is the state, nothing to send)

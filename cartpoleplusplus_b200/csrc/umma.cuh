@@ -17,8 +17,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok, spins = 0;
   do {
+#ifdef UMMA_SPIN_WAIT
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+#else
+    // suspend-time hint (ns): the hardware parks the thread until the phase completes instead of re-issuing the poll, so a
+    // waiting role costs no issue slots of the roles that work
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
+#endif
     if (!ok && ++spins > (1u << 24)) __trap();   // a lost arrival must fail loudly, never hang the GPU
   } while (!ok);
 }

@@ -243,6 +243,10 @@ class NAFEngine(EngineBase):
       raise _lib.CppError(-4, "check_numerics: non-finite l_values / L / loss (naf_cartpole.py:242-245)")
     return float(lf[0])
 
+  def update_targets(self):
+    """target_value_net.update_weights() (naf_cartpole.py:373) as one launch"""
+    _lib.check(self.lib.cpp_naf_update_targets(self.handle, C.c_float(self.o.target_update_rate), self._stream()))
+
   def train(self, batch, moments=None, sync=True):
     """naf.train(batch) (naf_cartpole.py:264-272).  moments: optional (mean_inv_s1, mean_inv_s2) device tensors with the
     whitening statistics of the GLOBAL batch (data parallel: every rank trains on a slice of it)"""

@@ -51,7 +51,12 @@ int64_t cpp_launch_count(void);
  * "prep_hoist" = 1 (default) runs the conv2/conv3 weight-prep kernels of the whole step at its start on idle streams,
  * "conv1_split" = 1 (default) runs the two conv1 passes side by side on half of the SMs each, "critic_tail" = 1 (default) evaluates
  * the pixel critic's [hidden2, action] -> hidden3 -> q head (incl. dQ/da) as one kernel, "bwd_critic_sms" (default 74) and
- * "fwd_actor_sms" (default 37) set the SM budgets of the critic's backward and the actor's forward chain.
+ * "fwd_actor_sms" (default 37) set the SM budgets of the critic's backward and the actor's forward chain;
+ * "wgrad_tc" = 1 (default) computes the conv1 weight gradient with the tcgen05 kernel (conv_wgrad_tc.cu) where the layer shape
+ * allows, 0 with the mma.sync kernel; "wgrad_flush_steps" (default 32) = tensor-core K-steps between two fp32 flushes of the
+ * weight-gradient accumulators; "fc_tc" = mask of the fully connected passes that run on tcgen05 (fc_tc.cu): 1 forward,
+ * 2 input gradient, 4 weight gradient (with the bias gradient folded in), + 8 to include GEMMs below 64 M MACs (default 0: measured
+ * slower than the FFMA kernels at the BASELINE sizes, profiles/r4/fc_tc.md; CARTPOLEPP_FC_TC sets the start-up value).
  * Process-wide state: set options from the (single) caller thread, between steps. */
 int cpp_set_option(const char* name, int32_t value);
 

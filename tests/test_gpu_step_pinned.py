@@ -119,3 +119,22 @@ def test_naf_backward_graph_replay_vs_oracle_with_pinned_routing(share):
   print("pinned-routing NAF c4 shard (share=%s):" % share, json.dumps(report))
   print("per-variable gradient errors vs fp64 (pinned routing):", json.dumps({k: "%.2e" % v for k, v in rep.items()}))
   U.assert_all_within(rep, "NAF c4 shard share=%s" % share)
+
+
+@pytest.mark.parametrize("fused_mlp", [0, 1], ids=["per_layer_forward", "fused_forward"])
+def test_fc_on_tensor_cores_whole_step(fused_mlp):
+  """cpp_set_option("fc_tc", 15): every fully connected GEMM with M >= 64 rows - forward (when the stacks run per layer),
+  input gradients, weight gradients - goes through the tcgen05 kernel of fc_tc.cu (three bf16 pieces per fp32 operand).  The
+  whole c3 step, graph-replayed, has to hold the same 1e-5 bound against the fp64 oracle with the routing pinned."""
+  lib = _lib.lib()
+  try:
+    _lib.check(lib.cpp_set_option(b"fc_tc", 15))
+    _lib.check(lib.cpp_set_option(b"fused_mlp", fused_mlp))
+    n0 = int(lib.cpp_launch_count())
+    report, rep = run_ddpg_pinned((64, 64, 3, 1, 3), 256, seed=81)
+    print("fc_tc=15 fused_mlp=%d whole step:" % fused_mlp, json.dumps(report), "launches", int(lib.cpp_launch_count()) - n0)
+    print("per-variable gradient errors vs fp64 (pinned routing):", json.dumps({k: "%.2e" % v for k, v in rep.items()}))
+    U.assert_all_within(rep, "DDPG c3 with the FC layers on tcgen05")
+  finally:
+    _lib.check(lib.cpp_set_option(b"fc_tc", 0))
+    _lib.check(lib.cpp_set_option(b"fused_mlp", -1))
