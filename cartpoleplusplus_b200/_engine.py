@@ -117,6 +117,11 @@ class EngineBase(object):
     self.lib_comm, self.transport = False, None
     if not dp.enabled:
       return
+    nets = getattr(self, "nets", None) or {}
+    if any(getattr(getattr(n, "_final", None), "bn", False) for n in nets.values()):
+      # slim.batch_norm statistics of a sharded batch are the shard's, not the global batch's: a per-layer exchange of the
+      # channel sums (forward and backward) would be needed to stay equal to the single-replica result - not built
+      raise NotImplementedError("--use-batch-norm under data parallelism needs a per-layer statistics all-reduce (not built)")
     for name in ("params", "target_params", "slots", "opt_state"):
       if name in self.buffers:
         dp.broadcast(self.buffers[name], 0)

@@ -19,8 +19,8 @@ import numpy as np
 
 from . import _lib
 
-# base_network.py:11 - a global flag fed to every Session.run.  It only matters for dropout / batch norm,
-# neither of which is on the default hot path; kept so callers that set it keep working.
+# base_network.py:11 - a global flag fed to every Session.run.  It only matters for dropout / batch norm; the library's
+# agent entry points set it per call exactly as the reference's feed_dicts do (train ops True, everything else False).
 IS_TRAINING = False
 
 ACT = {None: 0, "relu": 1, "tanh": 2}
@@ -40,8 +40,9 @@ class Placeholder(object):
 class Layer(object):
   """symbolic output of a builder call: the layers stacked so far on top of a Placeholder"""
 
-  def __init__(self, source, conv=False, fc=(), flat=False, concat=None):
+  def __init__(self, source, conv=False, fc=(), flat=False, concat=None, bn=False):
     self.source = source          # Placeholder
+    self.bn = bool(bn)            # --use-batch-norm: slim.batch_norm after every conv of the trunk (base_network.py:74-79)
     self.conv = conv              # True once simple_conv_net_on was applied
     self.fc = list(fc)            # [(scope, out, act)]
     self.flat = flat
@@ -60,13 +61,13 @@ def fully_connected(layer, num_outputs, scope, activation="relu"):
   """slim.fully_connected on a (flattened) symbolic layer"""
   if not isinstance(layer, Layer):
     layer = Layer(layer)
-  return Layer(layer.source, layer.conv, layer.fc + [(scope, int(num_outputs), activation)], True, layer.concat)
+  return Layer(layer.source, layer.conv, layer.fc + [(scope, int(num_outputs), activation)], True, layer.concat, layer.bn)
 
 
 def flatten(layer):
   if not isinstance(layer, Layer):
     layer = Layer(layer)
-  return Layer(layer.source, layer.conv, layer.fc, True, layer.concat)
+  return Layer(layer.source, layer.conv, layer.fc, True, layer.concat, layer.bn)
 
 
 def concat_action(layer, action_dim):
@@ -74,7 +75,7 @@ def concat_action(layer, action_dim):
   if not isinstance(layer, Layer):
     layer = Layer(layer)
   assert layer.concat is None
-  return Layer(layer.source, layer.conv, layer.fc, True, (len(layer.fc), int(action_dim)))
+  return Layer(layer.source, layer.conv, layer.fc, True, (len(layer.fc), int(action_dim)), layer.bn)
 
 
 Var = collections.namedtuple("Var", "name shape offset size")
@@ -104,15 +105,14 @@ class Network(object):
     return layer
 
   def simple_conv_net_on(self, input_layer, opts):
-    if getattr(opts, "use_batch_norm", False):
-      raise NotImplementedError("--use-batch-norm is outside the hot-path scope (SURVEY.md 8f row 4)")
     src = input_layer.source if isinstance(input_layer, Layer) else input_layer
     if len(src.shape) < 3:
       raise ValueError("simple_conv_net_on needs a (H, W, ...) state, got %s" % (src.shape,))
     height, width = src.shape[0], src.shape[1]
     num_channels = int(np.prod(src.shape[2:]))
     sys.stderr.write("input_layer (?, %d, %d, %d) #%d\n" % (height, width, num_channels, height * width * num_channels))
-    return Layer(src, conv=True)
+    # normalizer_fn=slim.batch_norm, normalizer_params={'is_training': IS_TRAINING} (base_network.py:74-79)
+    return Layer(src, conv=True, bn=bool(getattr(opts, "use_batch_norm", False)))
 
   def input_state_network(self, input_state, opts):
     if opts.use_raw_pixels:
@@ -138,6 +138,7 @@ class Network(object):
       spec.fc_out[i], spec.fc_act[i] = out, ACT[act]
     spec.concat_at = layer.concat[0] if layer.concat else -1
     spec.action_dim = layer.concat[1] if layer.concat else 0
+    spec.batch_norm = 1 if (layer.conv and layer.bn) else 0
     self._spec = spec
     return spec
 
@@ -153,7 +154,11 @@ class Network(object):
     if layer.conv:
       cin = int(np.prod(layer.source.shape[2:]))
       for name, k in (("conv1", 5), ("conv2", 5), ("conv3", 3)):
-        add(name + "/weights", (k, k, cin, 10)); add(name + "/biases", (10,))
+        add(name + "/weights", (k, k, cin, 10))
+        if layer.bn:     # slim.conv2d creates no bias under a normalizer_fn; slim.batch_norm(center=True, scale=False)
+          add(name + "/BatchNorm/beta", (10,)); add(name + "/BatchNorm/moving_mean", (10,)); add(name + "/BatchNorm/moving_variance", (10,))
+        else:
+          add(name + "/biases", (10,))
         cin = 10
     d = int(np.prod(layer.feature_shape()))
     for i, (scope, o, _) in enumerate(layer.fc):
@@ -171,7 +176,10 @@ class Network(object):
     (ddpg_cartpole.py:94, naf_cartpole.py:155).  Returns a flat float32 vector."""
     flat = np.zeros(self.num_params(), dtype=np.float32)
     for v in self._variables():
-      if v.name.endswith("/biases"):
+      if v.name.endswith("/moving_variance"):
+        flat[v.offset:v.offset + v.size] = 1.0      # slim.batch_norm initialiser; never updated by the reference (Appendix A-5)
+        continue
+      if v.name.endswith("/biases") or v.name.endswith("/beta") or v.name.endswith("/moving_mean"):
         continue
       if len(v.shape) == 4:
         kh, kw, ci, co = v.shape

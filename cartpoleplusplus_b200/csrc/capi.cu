@@ -19,6 +19,7 @@ int g_conv1_split = 1;     // the two conv1 passes of the DDPG step side by side
 int g_fwd_actor_sms = 37;  // SM budget of the actor's forward chain (mu is needed first); the other three chains share the rest
 int g_bwd_critic_sms = 74; // SM budget of the critic's backward chain in the fused DDPG step (the actor's gets the rest of the 148)
 int g_critic_tail = 1;     // the pixel critic's [hidden2, action] -> hidden3 -> q head as one kernel per evaluation / backward (mlp.cu)
+int g_is_training = 1;
 int g_wgrad_tc = 1;
 int g_fc_tc = [] { const char* e = getenv("CARTPOLEPP_FC_TC"); return e ? (atoi(e) & 15) : 0; }();   // off by default: measured slower than the FFMA kernels at every BASELINE size (profiles/r4/fc_tc.md)
 int g_wgrad_flush_steps = 32;     // the tensor-core accumulator truncates: 128-step chains cost 1.3e-5 on the conv1 weight gradient, 32 keep it at 5e-6 (profiles/r3/wgrad_flush.md)
@@ -82,6 +83,8 @@ struct cpp_naf { NAF a; };
 struct cpp_lrpg { LRPG a; };
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
+// the reference feeds ONE global IS_TRAINING placeholder per Session.run (base_network.py:11): train ops True, the rest False
+struct TrainingMode { int saved; explicit TrainingMode(int v) : saved(g_is_training) { g_is_training = v; } ~TrainingMode() { g_is_training = saved; } };
 #define API_BEGIN try {
 #define API_END } catch (const std::exception& e) { set_error("exception: %s", e.what()); return CPP_ERR_INVALID; } \
                   catch (...) { set_error("unknown exception"); return CPP_ERR_INVALID; }
@@ -102,6 +105,7 @@ int cpp_set_option(const char* name, int32_t value) {
   if (strcmp(name, "graphs") == 0) { set_step_options(-2, value); return CPP_OK; }
   if (strcmp(name, "prep_hoist") == 0) { g_prep_hoist = value != 0; return CPP_OK; }
   if (strcmp(name, "wgrad_flush_steps") == 0) { g_wgrad_flush_steps = value < 16 ? 16 : (value > 1024 ? 1024 : value); return CPP_OK; }
+  if (strcmp(name, "is_training") == 0) { g_is_training = value != 0; return CPP_OK; }
   if (strcmp(name, "fc_tc") == 0) { g_fc_tc = value & 15; return CPP_OK; }
   if (strcmp(name, "wgrad_tc") == 0) { g_wgrad_tc = value != 0; return CPP_OK; }
   if (strcmp(name, "conv1_split") == 0) { g_conv1_split = value != 0; return CPP_OK; }
@@ -363,11 +367,11 @@ int cpp_ddpg_set_moments(cpp_ddpg* a, const float* m1, const float* m2) {
   API_BEGIN NEED(a); a->a.pinned1 = m1; a->a.pinned2 = m2; a->a.critic_trunk_valid = false; return CPP_OK; API_END
 }
 int cpp_ddpg_actor_backward(cpp_ddpg* a, const void* s1, int32_t is_f16, int32_t B, int32_t B_global, void* stream) {
-  API_BEGIN NEED(a); NEED(s1); return a->a.actor_backward(s1, is_f16, B, B_global, ST(stream)); API_END
+  API_BEGIN TrainingMode tm_(1); NEED(a); NEED(s1); return a->a.actor_backward(s1, is_f16, B, B_global, ST(stream)); API_END
 }
 int cpp_ddpg_actor_apply(cpp_ddpg* a, void* stream) { API_BEGIN NEED(a); return a->a.actor_apply(ST(stream)); API_END }
 int cpp_ddpg_actor_train(cpp_ddpg* a, const void* s1, int32_t is_f16, int32_t B, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(1);
   NEED(a); NEED(s1);
   CPP_TRY(a->a.actor_backward(s1, is_f16, B, B, ST(stream)));
   return a->a.actor_apply(ST(stream));
@@ -375,7 +379,7 @@ int cpp_ddpg_actor_train(cpp_ddpg* a, const void* s1, int32_t is_f16, int32_t B,
 }
 int cpp_ddpg_critic_backward(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask,
                              const void* s2, int32_t is_f16, int32_t B, int32_t B_global, int32_t reuse, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(1);
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
   CPP_REQUIRE(B_global >= B, "B_global %d < B %d", B_global, B);
   return a->a.critic_backward(s1, action, reward, mask, s2, is_f16, B, B_global, reuse, ST(stream));
@@ -384,7 +388,7 @@ int cpp_ddpg_critic_backward(cpp_ddpg* a, const void* s1, const float* action, c
 int cpp_ddpg_critic_apply(cpp_ddpg* a, void* stream) { API_BEGIN NEED(a); return a->a.critic_apply(ST(stream)); API_END }
 int cpp_ddpg_critic_train(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
                           int32_t is_f16, int32_t B, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(1);
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
   CPP_TRY(a->a.critic_backward(s1, action, reward, mask, s2, is_f16, B, B, 0, ST(stream)));
   return a->a.critic_apply(ST(stream));
@@ -392,7 +396,7 @@ int cpp_ddpg_critic_train(cpp_ddpg* a, const void* s1, const float* action, cons
 }
 int cpp_ddpg_step_backward(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask,
                            const void* s2, int32_t is_f16, int32_t B, int32_t B_global, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(1);
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
   CPP_REQUIRE(B_global >= B, "B_global %d < B %d", B_global, B);
   return a->a.step_backward(s1, action, reward, mask, s2, is_f16, B, B_global, ST(stream));
@@ -400,7 +404,7 @@ int cpp_ddpg_step_backward(cpp_ddpg* a, const void* s1, const float* action, con
 }
 int cpp_ddpg_train_step(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask,
                         const void* s2, int32_t is_f16, int32_t B, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(1);
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
   return a->a.step(s1, action, reward, mask, s2, is_f16, B, B * a->a.comm.world, true, ST(stream));
   API_END
@@ -413,16 +417,16 @@ int cpp_ddpg_step_apply(cpp_ddpg* a, void* stream) {
 }
 int cpp_ddpg_check_loss(cpp_ddpg* a, const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
                         int32_t is_f16, int32_t B, float* loss, float* td, float* q, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(0);
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2); NEED(loss); NEED(td); NEED(q);
   return a->a.check_loss(s1, action, reward, mask, s2, is_f16, B, loss, td, q, ST(stream));
   API_END
 }
 int cpp_ddpg_action_given(cpp_ddpg* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
-  API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.action_given(state, is_f16, B, out, ST(stream)); API_END
+  API_BEGIN TrainingMode tm_(0); NEED(a); NEED(state); NEED(out); return a->a.action_given(state, is_f16, B, out, ST(stream)); API_END
 }
 int cpp_ddpg_action_given_fast(cpp_ddpg* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
-  API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.action_given_fast(state, is_f16, B, out, ST(stream)); API_END
+  API_BEGIN TrainingMode tm_(0); NEED(a); NEED(state); NEED(out); return a->a.action_given_fast(state, is_f16, B, out, ST(stream)); API_END
 }
 int cpp_ddpg_update_targets(cpp_ddpg* a, float coeff, void* stream) { API_BEGIN NEED(a); return a->a.update_targets(coeff, ST(stream)); API_END }
 
@@ -492,7 +496,7 @@ int cpp_naf_bind(cpp_naf* a, const cpp_naf_buffers* b) { API_BEGIN NEED(a); NEED
 int cpp_naf_set_moments(cpp_naf* a, const float* m1, const float* m2) { API_BEGIN NEED(a); a->a.pinned1 = m1; a->a.pinned2 = m2; return CPP_OK; API_END }
 int cpp_naf_backward(cpp_naf* a, const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
                      int32_t is_f16, int32_t B, int32_t B_global, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(1);
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
   CPP_REQUIRE(B_global >= B, "B_global %d < B %d", B_global, B);
   return a->a.backward(s1, action, reward, mask, s2, is_f16, B, B_global, ST(stream));
@@ -501,7 +505,7 @@ int cpp_naf_backward(cpp_naf* a, const void* s1, const float* action, const floa
 int cpp_naf_apply(cpp_naf* a, int32_t check, float* loss_host, void* stream) { API_BEGIN NEED(a); return a->a.apply(check, loss_host, ST(stream)); API_END }
 int cpp_naf_train(cpp_naf* a, const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
                   int32_t is_f16, int32_t B, float* loss_host, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(1);
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2);
   CPP_TRY(a->a.backward(s1, action, reward, mask, s2, is_f16, B, B, ST(stream)));
   return a->a.apply(1, loss_host, ST(stream));
@@ -509,19 +513,19 @@ int cpp_naf_train(cpp_naf* a, const void* s1, const float* action, const float* 
 }
 int cpp_naf_debug_values(cpp_naf* a, const void* s1, const float* action, const float* reward, const float* mask, const void* s2,
                          int32_t is_f16, int32_t B, float* l_values, float* loss, float* V, float* Aout, float* V2, void* stream) {
-  API_BEGIN
+  API_BEGIN TrainingMode tm_(0);
   NEED(a); NEED(s1); NEED(action); NEED(reward); NEED(mask); NEED(s2); NEED(l_values); NEED(loss); NEED(V); NEED(Aout); NEED(V2);
   return a->a.debug_values(s1, action, reward, mask, s2, is_f16, B, l_values, loss, V, Aout, V2, ST(stream));
   API_END
 }
 int cpp_naf_action_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
-  API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.action_given(state, is_f16, B, out, ST(stream)); API_END
+  API_BEGIN TrainingMode tm_(0); NEED(a); NEED(state); NEED(out); return a->a.action_given(state, is_f16, B, out, ST(stream)); API_END
 }
 int cpp_naf_action_given_fast(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
-  API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.action_given_fast(state, is_f16, B, out, ST(stream)); API_END
+  API_BEGIN TrainingMode tm_(0); NEED(a); NEED(state); NEED(out); return a->a.action_given_fast(state, is_f16, B, out, ST(stream)); API_END
 }
 int cpp_naf_value_given(cpp_naf* a, const void* state, int32_t is_f16, int32_t B, float* out, void* stream) {
-  API_BEGIN NEED(a); NEED(state); NEED(out); return a->a.value_given(state, is_f16, B, out, ST(stream)); API_END
+  API_BEGIN TrainingMode tm_(0); NEED(a); NEED(state); NEED(out); return a->a.value_given(state, is_f16, B, out, ST(stream)); API_END
 }
 int cpp_naf_update_targets(cpp_naf* a, float coeff, void* stream) { API_BEGIN NEED(a); return a->a.update_targets(coeff, ST(stream)); API_END }
 

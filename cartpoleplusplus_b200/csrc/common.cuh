@@ -32,6 +32,7 @@ extern int g_conv1_split;
 extern int g_wgrad_flush_steps;   // mma.sync weight gradient: MMA K-steps accumulated on the tensor cores between two fp32 flushes
 extern int g_wgrad_tc;            // 1: conv1 weight gradient on tcgen05 (conv_wgrad_tc.cu) where supported, 0: always mma.sync
 extern int g_fc_tc;               // FC passes on tcgen05 (fc_tc.cu): 1 forward, 2 input gradient, 4 weight gradient, 8 = also GEMMs below the size where it pays
+extern int g_is_training;         // base_network.py:11 IS_TRAINING: batch statistics (1) or moving statistics (0) in slim.batch_norm; dropout on / off
 extern int g_cta_cap;               // SMs a persistent kernel may occupy (agents lower it while independent chains share the GPU)
 static inline int sm_budget() { return g_cta_cap < 1 ? 1 : (g_cta_cap > 148 ? 148 : g_cta_cap); }
 #define CPP_CHECK_LAUNCH() do { ++cpp::g_launch_count; CPP_CHECK_CUDA(cudaGetLastError()); } while (0)
@@ -108,7 +109,11 @@ int launch_conv_fwd(const ConvLayer& L, const void* x, int x_is_f16, const float
 // d(x) of the layer, from the pooled-output gradient: dx f32 [B][H][W][Cin==10]
 int launch_conv_dgrad(const ConvLayer& L, const float* d_pooled, const uint8_t* amax, const float* w,
                       int B, float* dx, cudaStream_t s);
-// d(w), d(b); partials scratch f32[conv_wgrad_scratch_floats(L)]
+// --use-batch-norm route: raw SAME conv without bias (B,H,W,10), and d(x) from a dense gradient wrt the conv output
+int launch_conv_raw(const ConvLayer& L, const void* x, int x_is_f16, const float* mean_inv, const float* w, int B, float* raw,
+                    cudaStream_t s);
+int launch_conv_dgrad_dense(const ConvLayer& L, const float* d_conv, const float* w, int B, float* dx, cudaStream_t s);
+// d(w), d(b); partials scratch f32[conv_wgrad_scratch_floats(L)]; amax == NULL: d_pooled is the DENSE gradient (B,H,W,10)
 int64_t conv_wgrad_scratch_floats(const ConvLayer& L);
 int launch_conv_wgrad(const ConvLayer& L, const void* x, int x_is_f16, const float* mean_inv,
                       const float* d_pooled, const uint8_t* amax, int B,

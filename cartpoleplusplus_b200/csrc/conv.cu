@@ -13,7 +13,7 @@ constexpr int CO = kConvCout;   // 10 output channels
 constexpr int CP = 12;          // padded to 3 x float4 in shared memory
 
 struct ConvParams {
-  const void* x;            // IN 0: fp16 NHWC ; IN 1: fp32 NHWC ; IN 2: pooled gradient f32 (B,PH,PW,10)
+  const void* x;            // IN 0: fp16 NHWC ; IN 1: fp32 NHWC ; IN 2: pooled gradient f32 (B,PH,PW,10) ; IN 3: dense gradient (B,H,W,10)
   const uint8_t* gamax;     // IN 2
   const float* mean_inv;    // IN 0: [mean(Cin) | inv(Cin)]
   const float* w;           // HWIO
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128, 4) conv_kernel(ConvParams p) {
       const int o = i % CO, c = (i / CO) % p.CC, tap = i / (CO * p.CC);
       float v = 0.f;
       if (c0 + c < p.Cin) {
-        if (IN_MODE == 2) v = p.w[((KS * KS - 1 - tap) * CO + o) * CO + (c0 + c)];   // flipped taps, in/out swapped
+        if (IN_MODE >= 2) v = p.w[((KS * KS - 1 - tap) * CO + o) * CO + (c0 + c)];   // flipped taps, in/out swapped
         else v = p.w[(tap * p.Cin + c0 + c) * CO + o];
       }
       w_s[(tap * p.CC + c) * CP + o] = v;
@@ -78,12 +78,14 @@ __global__ void __launch_bounds__(128, 4) conv_kernel(ConvParams p) {
             const float inv = p.mean_inv[p.Cin + ch];
             v = __fsub_rn(__fmul_rn(v, inv), __fmul_rn(p.mean_inv[ch], inv));
           }
-        } else {
+        } else if (IN_MODE == 2) {
           const int py = gy >> 1, px = gx >> 1;
           if (py < p.PH && px < p.PW) {
             const size_t idx = (((size_t)b * p.PH + py) * p.PW + px) * CO + ch;
             if (p.gamax[idx] == (((gy & 1) << 1) | (gx & 1))) v = reinterpret_cast<const float*>(p.x)[idx];
           }
+        } else {                                                  // IN 3: dense gradient wrt the conv output (batch-norm route)
+          v = reinterpret_cast<const float*>(p.x)[(((size_t)b * p.H + gy) * p.W + gx) * CO + ch];
         }
       }
       in_s[(z * p.CC + c) * p.chpitch + iy * TWP + ix] = v;
@@ -225,6 +227,34 @@ int launch_conv_dgrad(const ConvLayer& L, const float* d_pooled, const uint8_t* 
   return L.KS == 5 ? launch_conv_t<5, 2, 1>(p, t, s) : launch_conv_t<3, 2, 1>(p, t, s);
 }
 
+// --use-batch-norm route (base_network.py:74-79): slim.conv2d with a normalizer_fn has no bias and hands its raw output to
+// slim.batch_norm, so the layer is split: raw SAME conv here, statistics / normalise / ReLU / pool in bn.cu
+int launch_conv_raw(const ConvLayer& L, const void* x, int x_is_f16, const float* mean_inv, const float* w, int B, float* raw,
+                    cudaStream_t s) {
+  CPP_REQUIRE(L.KS == 5 || L.KS == 3, "conv: kernel size %d unsupported", L.KS);
+  CPP_REQUIRE(!x_is_f16 || mean_inv != nullptr, "conv: fp16 input needs whitening stats");
+  if (B <= 0) return CPP_OK;
+  ConvParams p{};
+  p.x = x; p.mean_inv = mean_inv; p.w = w; p.out = raw;
+  p.B = B; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.PH = L.PH(); p.PW = L.PW();
+  ConvTile t = pick_tile(L.H, L.W, L.Cin, L.KS, B);
+  p.CC = t.CC; p.chpitch = t.chpitch;
+  if (x_is_f16) return L.KS == 5 ? launch_conv_t<5, 0, 1>(p, t, s) : launch_conv_t<3, 0, 1>(p, t, s);
+  return L.KS == 5 ? launch_conv_t<5, 1, 1>(p, t, s) : launch_conv_t<3, 1, 1>(p, t, s);
+}
+
+// d(x) from the DENSE gradient wrt the conv output (B,H,W,10)
+int launch_conv_dgrad_dense(const ConvLayer& L, const float* d_conv, const float* w, int B, float* dx, cudaStream_t s) {
+  CPP_REQUIRE(L.Cin == CO, "conv dgrad is only needed for conv2/conv3 (Cin == 10), got %d", L.Cin);
+  if (B <= 0) return CPP_OK;
+  ConvParams p{};
+  p.x = d_conv; p.w = w; p.out = dx;
+  p.B = B; p.H = L.H; p.W = L.W; p.Cin = CO; p.PH = L.PH(); p.PW = L.PW();
+  ConvTile t = pick_tile(L.H, L.W, CO, L.KS, B);
+  p.CC = t.CC; p.chpitch = t.chpitch;
+  return L.KS == 5 ? launch_conv_t<5, 3, 1>(p, t, s) : launch_conv_t<3, 3, 1>(p, t, s);
+}
+
 // ------------------------------------------------------------------------------------------ wgrad
 
 struct WgradParams {
@@ -287,7 +317,9 @@ __global__ void __launch_bounds__(256, 2) conv_wgrad_kernel(WgradParams p) {
       const int o = e % CO, x = (e / CO) % TWt, y = e / (CO * TWt);
       const int gy = y0 + y, gx = x0 + x, py = gy >> 1, px = gx >> 1;
       float v = 0.f;
-      if (gy < p.H && gx < p.W && py < p.PH && px < p.PW) {
+      if (p.gamax == nullptr) {                                    // dense gradient wrt the conv output (batch-norm route)
+        if (gy < p.H && gx < p.W) v = p.gp[(((size_t)b * p.H + gy) * p.W + gx) * CO + o];
+      } else if (gy < p.H && gx < p.W && py < p.PH && px < p.PW) {
         const size_t idx = (((size_t)b * p.PH + py) * p.PW + px) * CO + o;
         if (p.gamax[idx] == (((gy & 1) << 1) | (gx & 1))) v = p.gp[idx];
       }

@@ -10,6 +10,7 @@ namespace cpp {
 int Net::init(const cpp_net_spec& s) {
   spec = s;
   pixels = s.pixels != 0;
+  bn = pixels && s.batch_norm != 0;
   n_fc = s.n_fc;
   concat_at = s.concat_at;
   action_dim = s.action_dim;
@@ -31,7 +32,11 @@ int Net::init(const cpp_net_spec& s) {
     for (int i = 0; i < 3; ++i) {
       conv[i].H = h; conv[i].W = w; conv[i].Cin = cin; conv[i].KS = ks[i];
       off_conv_w[i] = off; add_var(4, ks[i], ks[i], cin, kConvCout);
-      off_conv_b[i] = off; add_var(1, kConvCout, 1, 1, 1);
+      off_conv_b[i] = off; add_var(1, kConvCout, 1, 1, 1);                 // biases, or BatchNorm/beta (no bias with a normalizer_fn)
+      if (bn) {                                                            // slim.batch_norm(center=True, scale=False): TF creation order
+        off_bn_mean[i] = off; add_var(1, kConvCout, 1, 1, 1);              // BatchNorm/moving_mean
+        off_bn_var[i] = off; add_var(1, kConvCout, 1, 1, 1);               // BatchNorm/moving_variance
+      }
       h /= 2; w /= 2; cin = kConvCout;
     }
     feat = h * w * kConvCout;
@@ -76,6 +81,14 @@ Net::Layout Net::layout(int B) const {
     L.wgrad = take((size_t)wg * sizeof(float));
     L.dyp = take((size_t)B * conv[1].H * conv[1].W * tc::kC24 * sizeof(__half));   // un-pooled gradient pieces (dgrad on tensor cores)
     L.gsc = take(8 * sizeof(float));                                                      // {max|g|, 1/scale} per conv layer
+    if (bn) {
+      for (int i = 0; i < 3; ++i) {
+        L.raw[i] = take((size_t)B * conv[i].H * conv[i].W * kConvCout * sizeof(float));
+        L.bnscr[i] = take((size_t)bn_scratch_bytes());
+      }
+      L.dconv = take((size_t)B * conv[0].H * conv[0].W * kConvCout * sizeof(float));
+      L.bnjunk = take(64);
+    }
   } else {
     L.x0 = take((size_t)B * in_dim[0] * sizeof(float));
   }
@@ -99,7 +112,7 @@ const float* Net::fc_input(const Layout& L, char* ws, int i, int* ld) const {
 }
 
 bool Net::tc_route(int is_f16) const {
-  return pixels && is_f16 && conv1_tc_enabled() && tc::conv_tc_supported(1, conv[0].H, conv[0].W, conv[0].Cin, conv[0].KS) &&
+  return pixels && !bn && is_f16 && conv1_tc_enabled() && tc::conv_tc_supported(1, conv[0].H, conv[0].W, conv[0].Cin, conv[0].KS) &&
          tc::conv_tc_supported(1, conv[1].H, conv[1].W, tc::kC24, conv[1].KS) &&
          tc::conv_tc_supported(1, conv[2].H, conv[2].W, tc::kC24, conv[2].KS);
 }
@@ -124,6 +137,12 @@ int Net::forward_trunk(const float* params, const void* state, int is_f16, const
         CPP_TRY(tc::launch_conv_fwd_tc(ws + L.hl[i - 1], nullptr, nullptr, 1, w, b, B, conv[i].H, conv[i].W, tc::kC24, conv[i].KS,
                                        po, am, reinterpret_cast<char*>(tc_scratch) + i * trunk_slot_bytes(*this), s, 2, hl,
                                        g_tc_prepped ? tc::kPhaseMain : tc::kPhaseBoth));
+      } else if (bn) {
+        // raw conv (no bias) -> batch statistics (IS_TRAINING) or moving statistics -> normalise + beta -> ReLU -> pool
+        float* raw = reinterpret_cast<float*>(ws + L.raw[i]);
+        CPP_TRY(launch_conv_raw(conv[i], x, xf16, mi, params + off_conv_w[i], B, raw, s));
+        CPP_TRY(launch_bn_forward(raw, params + off_conv_b[i], params + off_bn_mean[i], params + off_bn_var[i], g_is_training, B,
+                                  conv[i].H, conv[i].W, ws + L.bnscr[i], pooled, amax, s));
       } else {
         CPP_TRY(launch_conv_fwd(conv[i], x, xf16, mi, params + off_conv_w[i], params + off_conv_b[i], B, pooled, amax, s));
       }
@@ -204,7 +223,11 @@ int conv1_wgrad_group(int n, const Net* const* nets, char* const* ws, float* con
                                      gmax_from_dgrad ? gm : nullptr);
   for (int i = 0; i < n; ++i) {
     const Net::Layout L = nets[i]->layout(B);
-    CPP_TRY(launch_conv_wgrad(c1, state, is_f16, mean_inv, gp[i], am[i], B, dw[i], db[i], reinterpret_cast<float*>(ws[i] + L.wgrad), s));
+    if (nets[i]->bn)   // batch norm: Net::backward left the dense d(conv1) (and wrote d(beta) itself)
+      CPP_TRY(launch_conv_wgrad(c1, state, is_f16, mean_inv, reinterpret_cast<const float*>(ws[i] + L.dconv), nullptr, B, dw[i],
+                                reinterpret_cast<float*>(ws[i] + L.bnjunk), reinterpret_cast<float*>(ws[i] + L.wgrad), s));
+    else
+      CPP_TRY(launch_conv_wgrad(c1, state, is_f16, mean_inv, gp[i], am[i], B, dw[i], db[i], reinterpret_cast<float*>(ws[i] + L.wgrad), s));
   }
   return CPP_OK;
 }
@@ -289,7 +312,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
   char* ws = reinterpret_cast<char*>(ws_);
   const Layout L = layout(B);
   const int last = n_fc - 1;
-  const bool fork = aux != nullptr && aux->stream != nullptr && grads != nullptr;
+  const bool fork = aux != nullptr && aux->stream != nullptr && grads != nullptr && !bn;   // (batch norm: one dense d(conv) buffer shared by the layers)
   cudaStream_t sw = fork ? aux->stream : s;              // weight / bias gradients
   int ev = 0;
   auto ready = [&]() -> int {                            // the gradient produced last on `s` may now be consumed on `sw`
@@ -384,6 +407,22 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     if (i == 0) { x = state; xf16 = is_f16; mi = mean_inv; }
     else { x = ws + L.pooled[i - 1]; xf16 = 0; mi = nullptr; }
     const uint8_t* amax = reinterpret_cast<const uint8_t*>(ws + L.amax[i]);
+    if (bn) {
+      // through slim.batch_norm with batch statistics: dense d(conv) for EVERY position, d(beta); then the dense-gradient kernels
+      CPP_REQUIRE(g_is_training, "backward through batch norm needs the batch statistics of a training-mode forward");
+      float* dconv = reinterpret_cast<float*>(ws + L.dconv);
+      CPP_TRY(launch_bn_backward(gp, amax, reinterpret_cast<const float*>(ws + L.raw[i]), B, conv[i].H, conv[i].W, ws + L.bnscr[i], dconv,
+                                 grads + off_conv_b[i], s));
+      if (i == 0 && defer_conv1) break;                     // d(conv1) stays in ws: picked up by conv1_wgrad_group
+      CPP_TRY(launch_conv_wgrad(conv[i], x, xf16, mi, dconv, nullptr, B, grads + off_conv_w[i], reinterpret_cast<float*>(ws + L.bnjunk),
+                                reinterpret_cast<float*>(ws + L.wgrad), s));
+      if (i > 0) {
+        float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);
+        CPP_TRY(launch_conv_dgrad_dense(conv[i], dconv, params + off_conv_w[i], B, dx, s));
+        gp = dx;
+      }
+      continue;
+    }
     if (i == 0 && defer_conv1) break;                       // gp == ws + L.dpool[1]: picked up by conv1_wgrad_group
     // tensor-core route for conv3/conv2: the un-pool + split pass also yields max|gp|, shared by wgrad and dgrad
     const bool tc_dg = i > 0 && tc_scratch != nullptr && tc_route(is_f16);

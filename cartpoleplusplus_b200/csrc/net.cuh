@@ -1,6 +1,7 @@
 // One reference network (base_network.Network subclass): optional conv trunk -> flatten -> FC stack.
 #pragma once
 #include <vector>
+#include <algorithm>
 #include "common.cuh"
 
 namespace cpp {
@@ -20,17 +21,20 @@ struct BackwardAux {
 struct Net {
   cpp_net_spec spec;
   bool pixels = false;
+  bool bn = false;                    // --use-batch-norm: conv layers are raw conv -> slim.batch_norm -> ReLU -> pool (bn.cu), no conv bias
   ConvLayer conv[3];
   int feat = 0;                       // flattened trunk features, or input_dim
   int n_fc = 0;
   int in_dim[CPP_MAX_FC], out_dim[CPP_MAX_FC], act[CPP_MAX_FC], out_ld[CPP_MAX_FC];
   int concat_at = -1, action_dim = 0;
-  int64_t off_conv_w[3], off_conv_b[3], off_fc_w[CPP_MAX_FC], off_fc_b[CPP_MAX_FC];
+  int64_t off_conv_w[3], off_conv_b[3], off_fc_w[CPP_MAX_FC], off_fc_b[CPP_MAX_FC];   // off_conv_b: biases, or BatchNorm/beta
+  int64_t off_bn_mean[3], off_bn_var[3];                                              // BatchNorm/moving_mean, moving_variance
   int64_t nparams = 0;
   std::vector<VarInfo> vars;
 
   struct Layout {
     size_t pooled[3], amax[3], hl[2], x0, h[CPP_MAX_FC], dX[CPP_MAX_FC], dTop, dpool[2], wgrad, dyp, gsc, total;
+    size_t raw[3], bnscr[3], dconv, bnjunk;     // batch norm: raw conv outputs, statistics scratch, dense d(conv), sink for the unused bias gradient
   };
 
   int init(const cpp_net_spec& s);
@@ -112,6 +116,13 @@ int launch_critic_tail_fwd(const Net& net, const float* params, const float* act
                            float* neg_dqda, cudaStream_t s);
 // needs d_out [B] (= dq); leaves dTop, dX[last], dX[concat_at] in the workspace exactly like the per-layer path
 int launch_critic_tail_bwd(const Net& net, const float* params, const float* dq, int B, void* ws, cudaStream_t s);
+
+// bn.cu (--use-batch-norm, base_network.py:74-79)
+int64_t bn_scratch_bytes();
+int launch_bn_forward(const float* raw, const float* beta, const float* moving_mean, const float* moving_var, int training, int B,
+                      int H, int W, void* scratch, float* pooled, uint8_t* amax, cudaStream_t s);
+int launch_bn_backward(const float* d_pooled, const uint8_t* amax, const float* raw, int B, int H, int W, void* scratch,
+                       float* dconv, float* dbeta, cudaStream_t s);
 
 // elementwise.cu
 int64_t moments_scratch_doubles(int C);

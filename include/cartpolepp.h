@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define CPP_ABI_VERSION 3
+#define CPP_ABI_VERSION 4
 #define CPP_MAX_FC 8
 
 typedef enum {
@@ -57,6 +57,9 @@ int64_t cpp_launch_count(void);
  * weight-gradient accumulators; "fc_tc" = mask of the fully connected passes that run on tcgen05 (fc_tc.cu): 1 forward,
  * 2 input gradient, 4 weight gradient (with the bias gradient folded in), + 8 to include GEMMs below 64 M MACs (default 0: measured
  * slower than the FFMA kernels at the BASELINE sizes, profiles/r4/fc_tc.md; CARTPOLEPP_FC_TC sets the start-up value).
+ * "is_training" = the reference's global IS_TRAINING placeholder (base_network.py:11) for the raw cpp_net_* calls: batch (1,
+ * default) or moving (0) statistics in slim.batch_norm; the agent entry points set it themselves (train ops: 1; action_given,
+ * check_loss, debug_values, value_given: 0).
  * Process-wide state: set options from the (single) caller thread, between steps. */
 int cpp_set_option(const char* name, int32_t value);
 
@@ -109,6 +112,10 @@ typedef struct {
   int32_t fc_act[CPP_MAX_FC];  /* 0 linear, 1 relu, 2 tanh */
   int32_t concat_at;           /* -1: no action input */
   int32_t action_dim;
+  int32_t batch_norm;          /* --use-batch-norm (base_network.py:74-79): every conv layer is conv (no bias) -> slim.batch_norm
+                                * (center, no scale, eps 1e-3) -> ReLU -> pool; variables per conv layer: weights,
+                                * BatchNorm/beta, BatchNorm/moving_mean, BatchNorm/moving_variance (the last two are never
+                                * updated by the reference and only copied by the target update) */
 } cpp_net_spec;
 
 typedef struct cpp_net cpp_net;

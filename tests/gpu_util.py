@@ -157,6 +157,16 @@ def names_of(net):
   return [v.name for v in net._variables()]
 
 
+def with_moving(net, trainable_list):
+  """the oracle's gradient list covers tf.trainable_variables; the library's flat gradient buffer has a (zero) slot for every
+  variable, the batch-norm moving statistics included: pad the list with zeros at their places"""
+  out, it = [], iter(trainable_list)
+  for v in [v for n in (net if isinstance(net, (list, tuple)) else [net]) for v in n._variables()]:
+    out.append(np.zeros(v.shape) if "/moving_" in v.name else next(it))
+  assert next(it, None) is None
+  return out
+
+
 def golden_flat(g, net, prefix):
   return np.concatenate([np.asarray(g[prefix + n], dtype=np.float64).reshape(-1) for n in names_of(net)])
 

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(lib, name), "libcartpolepp.so does not export %s" % name
   assert sorted(_lib.SYMBOLS) == declared, "python binding list and header disagree"
-  assert lib.cpp_version() == 3
+  assert lib.cpp_version() == 4
 
 
 def test_error_reporting_is_c_abi_clean():

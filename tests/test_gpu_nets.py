@@ -28,7 +28,7 @@ def _golden_P(g, dtype=torch.float64):
 
 
 @pytest.mark.parametrize("tc", [False, True], ids=["cudacore", "tensorcore"])
-@pytest.mark.parametrize("name", ["ddpg_pixel", "ddpg_pixel_odd", "ddpg_lowdim"])
+@pytest.mark.parametrize("name", ["ddpg_pixel", "ddpg_pixel_odd", "ddpg_lowdim", "ddpg_pixel_bn"])
 def test_ddpg_golden(golden_dir, name, tc):
   """committed golden vectors: forward observables against the fixture; gradients and parameters against the fp64 oracle run
   alongside from the fixture's weights and batches WITH the GPU's routing (gpu_util, 'routing-pinned gradient parity'), which
@@ -36,8 +36,9 @@ def test_ddpg_golden(golden_dir, name, tc):
   U.set_route(tc)
   g, meta = U.load_golden(golden_dir, name)
   shape, pixels, B = tuple(meta["state_shape"]), meta["pixels"], meta["B"]
-  nets, eng, o = U.make_ddpg(shape, pixels, U.golden_values(g), batch_size=B)
-  orc = no.DDPGOracle(shape, pixels, _golden_P(g))
+  bn = bool(meta.get("batch_norm", False))       # --use-batch-norm (base_network.py:74-79): exact-fp32 route only, `tc` changes nothing
+  nets, eng, o = U.make_ddpg(shape, pixels, U.golden_values(g), batch_size=B, extra=["--use-batch-norm"] if bn else [])
+  orc = no.DDPGOracle(shape, pixels, _golden_P(g), batch_norm=bn)
   worst, differing = {}, 0
   for step in range(2):
     batch = U.golden_batch(g, step)
@@ -50,7 +51,7 @@ def test_ddpg_golden(golden_dir, name, tc):
     with no.gates(U.conv_routing(eng, DDPG_PARTS, shape, B) if pixels else {}) as stats:
       ra = orc.actor_train(tuple(batch)[0])
     n_diff = U.check_gate_stats(stats)
-    rep = U.per_variable_errors(U.names_of(nets["actor"]), ga, [x.numpy() for x in ra["grads"]])
+    rep = U.per_variable_errors(U.names_of(nets["actor"]), ga, U.with_moving(nets["actor"], [x.numpy() for x in ra["grads"]]))
     worst["actor_grads"] = max(worst.get("actor_grads", 0), U.assert_all_within(rep, "step %d actor grads" % step))
     if n_diff == 0 and differing == 0:
       U.assert_close(torch.cat([x.reshape(-1) for x in ra["grads"]]).numpy(), g["step%d/actor_grads" % step], tol=1e-9, what="live oracle vs fixture")
@@ -61,7 +62,7 @@ def test_ddpg_golden(golden_dir, name, tc):
     with no.gates(U.conv_routing(eng, DDPG_PARTS[1:], shape, B) if pixels else {}) as stats:
       rc = orc.critic_train(tuple(batch))
     n_diff = U.check_gate_stats(stats)
-    rep = U.per_variable_errors(U.names_of(nets["critic"]), gc, [x.numpy() for x in rc["grads"]])
+    rep = U.per_variable_errors(U.names_of(nets["critic"]), gc, U.with_moving(nets["critic"], [x.numpy() for x in rc["grads"]]))
     worst["critic_grads"] = max(worst.get("critic_grads", 0), U.assert_all_within(rep, "step %d critic grads" % step))
     if n_diff == 0 and differing == 0:
       U.assert_close(torch.cat([x.reshape(-1) for x in rc["grads"]]).numpy(), g["step%d/critic_grads" % step], tol=1e-9, what="live oracle vs fixture")
@@ -205,18 +206,20 @@ def test_target_update_properties():
 
 # ------------------------------------------------------------------------------------------ NAF
 @pytest.mark.parametrize("tc", [False, True], ids=["cudacore", "tensorcore"])
-@pytest.mark.parametrize("name", ["naf_pixel", "naf_lowdim", "naf_pixel_shared", "naf_lowdim_shared"])
+@pytest.mark.parametrize("name", ["naf_pixel", "naf_lowdim", "naf_pixel_shared", "naf_lowdim_shared", "naf_pixel_bn_shared"])
 def test_naf_golden(golden_dir, name, tc):
   U.set_route(tc)
   g, meta = U.load_golden(golden_dir, name)
   shape, pixels, share, B = tuple(meta["state_shape"]), meta["pixels"], bool(meta.get("share", False)), meta["B"]
+  bn = bool(meta.get("batch_norm", False))
   naf, nets, eng, o = U.make_naf(shape, pixels, U.golden_values(g), batch_size=B,
                                  optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"],
-                                 extra=["--share-input-state-representation"] if share else [])
+                                 extra=(["--share-input-state-representation"] if share else []) + (["--use-batch-norm"] if bn else []))
   # the fp64 oracle run alongside with the GPU's routing (the reference the gradients are held to), and the fp32 CPU path for
   # the conditioning of the Adam / Momentum parameter updates
-  orc = no.NAFOracle(shape, pixels, _golden_P(g), optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"], share=share)
-  orc32 = no.NAFOracle(shape, pixels, _golden_P(g, torch.float32), optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"], share=share)
+  orc = no.NAFOracle(shape, pixels, _golden_P(g), optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"], share=share, batch_norm=bn)
+  orc32 = no.NAFOracle(shape, pixels, _golden_P(g, torch.float32), optimiser=meta["optimiser"], optimiser_args=meta["optimiser_args"], share=share,
+                       batch_norm=bn)
   parts = NAF_PARTS[:1] if share else NAF_PARTS
   names = U.names_of(nets["value"]) + U.names_of(nets["mu"]) + U.names_of(nets["l"])
   worst, differing = {}, 0
@@ -236,8 +239,10 @@ def test_naf_golden(golden_dir, name, tc):
     r32 = orc32.train(tuple(batch))
     gr = eng.buffers["grads"].cpu().numpy()
     got = np.concatenate([gr[:eng.n_v], gr[eng.off_m:eng.off_m + eng.n_m], gr[eng.off_l:eng.off_l + eng.n_l]])
-    rep = U.per_variable_errors(names, got, [x.numpy() for x in r["grads"]])
-    c32 = U.per_variable_errors(names, torch.cat([x.reshape(-1) for x in r32["grads"]]).numpy(), [x.numpy() for x in r["grads"]])
+    three = [nets["value"], nets["mu"], nets["l"]]
+    rep = U.per_variable_errors(names, got, U.with_moving(three, [x.numpy() for x in r["grads"]]))
+    c32 = U.per_variable_errors(names, np.concatenate([np.asarray(x).reshape(-1) for x in U.with_moving(three, [x.numpy() for x in r32["grads"]])]),
+                                U.with_moving(three, [x.numpy() for x in r["grads"]]))
     worst["grads"] = max(worst.get("grads", 0), U.assert_all_within(rep, "step %d grads" % step, cpu32=c32 if step > 0 else None))
     if n_diff == 0 and differing == 0:
       U.assert_close(torch.cat([x.reshape(-1) for x in r["grads"]]).numpy(), g["step%d/grads" % step], tol=1e-9, what="live oracle vs fixture")

@@ -41,12 +41,14 @@ def test_ddpg_train_step_graph_replay_vs_oracle_with_pinned_routing(shape, B):
   U.assert_all_within(rep, "DDPG %s B=%d" % (shape, B))
 
 
-def run_ddpg_pinned(shape, B, seed=77):
-  from tests.test_gpu_nets import _oracle_ddpg
+def run_ddpg_pinned(shape, B, seed=77, bn=False):
+  from oracle.make_golden import ddpg_params, _batch
   lib = _lib.lib()
   Cin = int(np.prod(shape[2:]))
-  P, batch = _oracle_ddpg(shape, True, B, seed)
-  nets, eng, o = U.make_ddpg(shape, True, {k: v.numpy() for k, v in P.items()}, batch_size=B)
+  rs = np.random.RandomState(seed)
+  P = ddpg_params(rs, shape, True, batch_norm=bn) if bn else ddpg_params(rs, shape, True)
+  batch = _batch(rs, B, shape)
+  nets, eng, o = U.make_ddpg(shape, True, {k: v.numpy() for k, v in P.items()}, batch_size=B, extra=["--use-batch-norm"] if bn else [])
   db = U.Batch(*[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in batch])
   moms = (_moments(lib, db.state_1, B * shape[0] * shape[1], Cin), _moments(lib, db.state_2, B * shape[0] * shape[1], Cin))
   p0, t0 = eng.buffers["params"].clone(), eng.buffers["target_params"].clone()
@@ -62,14 +64,14 @@ def run_ddpg_pinned(shape, B, seed=77):
   routing = U.conv_routing(eng, DDPG_PARTS, shape, B)
   grads = eng.buffers["grads"].cpu().numpy()
   report = {}
-  orc = no.DDPGOracle(shape, True, P)
+  orc = no.DDPGOracle(shape, True, P, batch_norm=bn)
   with no.gates(routing) as stats:
     ra = orc.actor_train(batch[0])                       # updates orc.P[actor/*]; the critic step below does not read them
     rc = orc.critic_train(batch)
   U.check_gate_stats(stats, report)
-  rep = U.per_variable_errors(U.names_of(nets["actor"]), grads[:eng.n_actor], [x.numpy() for x in ra["grads"]])
+  rep = U.per_variable_errors(U.names_of(nets["actor"]), grads[:eng.n_actor], U.with_moving(nets["actor"], [x.numpy() for x in ra["grads"]]))
   rep.update(U.per_variable_errors(U.names_of(nets["critic"]), grads[eng.off_critic:eng.off_critic + eng.n_critic],
-                                   [x.numpy() for x in rc["grads"]]))
+                                   U.with_moving(nets["critic"], [x.numpy() for x in rc["grads"]])))
   report["loss"] = U.assert_close(grads[eng.off_loss], float(rc["loss"]), what="loss")
   for k in ("actor", "critic"):
     want = np.concatenate([orc.P[n].numpy().reshape(-1) for n in U.names_of(nets[k])])
@@ -138,3 +140,17 @@ def test_fc_on_tensor_cores_whole_step(fused_mlp):
   finally:
     _lib.check(lib.cpp_set_option(b"fc_tc", 0))
     _lib.check(lib.cpp_set_option(b"fused_mlp", -1))
+
+
+@pytest.mark.parametrize("shape,B", [((64, 64, 3, 1, 3), 64), ((50, 50, 3, 1, 2), 32)], ids=["c3shape", "default50"])
+def test_ddpg_batch_norm_train_step_vs_oracle_with_pinned_routing(shape, B):
+  """--use-batch-norm (base_network.py:74-79; nearly every pixel experiment of the reference, exps/run_8*.sh): the same fused,
+  graph-replayed call with slim.batch_norm in every conv layer of all four networks (batch statistics also in the targets,
+  SURVEY.md Appendix A-5): every gradient tensor - BatchNorm/beta included, moving statistics exactly zero - within 1e-5 of
+  the fp64 oracle with the routing pinned"""
+  import time
+  report, rep = run_ddpg_pinned(shape, B, seed=83, bn=True)
+  print("pinned-routing whole step with batch norm %s B=%d:" % (shape, B), json.dumps(report))
+  print("per-variable gradient errors vs fp64 (pinned routing):", json.dumps({k: "%.2e" % v for k, v in rep.items()}))
+  U.assert_all_within(rep, "DDPG + batch norm %s B=%d" % (shape, B))
+  assert all(v == 0.0 for k, v in rep.items() if "/moving_" in k), "moving statistics must not receive a gradient"
