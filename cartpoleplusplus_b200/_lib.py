@@ -19,7 +19,7 @@ class NetSpec(C.Structure):
   _fields_ = [("pixels", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
               ("input_dim", C.c_int32), ("n_fc", C.c_int32),
               ("fc_out", C.c_int32 * CPP_MAX_FC), ("fc_act", C.c_int32 * CPP_MAX_FC),
-              ("concat_at", C.c_int32), ("action_dim", C.c_int32), ("batch_norm", C.c_int32)]
+              ("concat_at", C.c_int32), ("action_dim", C.c_int32), ("fc_dropout", C.c_int32 * CPP_MAX_FC), ("batch_norm", C.c_int32)]
 
 
 class DDPGConfig(C.Structure):

@@ -44,7 +44,7 @@ class Layer(object):
     self.source = source          # Placeholder
     self.bn = bool(bn)            # --use-batch-norm: slim.batch_norm after every conv of the trunk (base_network.py:74-79)
     self.conv = conv              # True once simple_conv_net_on was applied
-    self.fc = list(fc)            # [(scope, out, act)]
+    self.fc = list(fc)            # [(scope, out, act, dropout)]
     self.flat = flat
     self.concat = concat          # (index of the FC layer the action is concatenated in front of, action_dim)
 
@@ -57,11 +57,11 @@ class Layer(object):
     return self.source.shape
 
 
-def fully_connected(layer, num_outputs, scope, activation="relu"):
-  """slim.fully_connected on a (flattened) symbolic layer"""
+def fully_connected(layer, num_outputs, scope, activation="relu", dropout=False):
+  """slim.fully_connected on a (flattened) symbolic layer; dropout: followed by slim.dropout(keep_prob 0.5, is_training=IS_TRAINING)"""
   if not isinstance(layer, Layer):
     layer = Layer(layer)
-  return Layer(layer.source, layer.conv, layer.fc + [(scope, int(num_outputs), activation)], True, layer.concat, layer.bn)
+  return Layer(layer.source, layer.conv, layer.fc + [(scope, int(num_outputs), activation, bool(dropout))], True, layer.concat, layer.bn)
 
 
 def flatten(layer):
@@ -98,10 +98,9 @@ class Network(object):
     if not isinstance(layer_sizes, list):
       layer_sizes = [int(s) for s in layer_sizes.split(",")]
     assert len(layer_sizes) > 0
-    if opts is not None and getattr(opts, "use_dropout", False):
-      raise NotImplementedError("--use-dropout is outside the hot-path scope (SURVEY.md 8f row 4)")
-    for i, size in enumerate(layer_sizes):     # Appendix C-1: opts=None means no dropout
-      layer = fully_connected(layer, size, scope="h%d" % i, activation="relu")
+    use_dropout = opts is not None and bool(getattr(opts, "use_dropout", False))     # Appendix C-1: opts=None means no dropout
+    for i, size in enumerate(layer_sizes):
+      layer = fully_connected(layer, size, scope="h%d" % i, activation="relu", dropout=use_dropout)   # slim.dropout scope "do%d", :69-70
     return layer
 
   def simple_conv_net_on(self, input_layer, opts):
@@ -134,8 +133,8 @@ class Network(object):
     if len(layer.fc) > _lib.CPP_MAX_FC:
       raise ValueError("at most %d fully connected layers" % _lib.CPP_MAX_FC)
     spec.n_fc = len(layer.fc)
-    for i, (_, out, act) in enumerate(layer.fc):
-      spec.fc_out[i], spec.fc_act[i] = out, ACT[act]
+    for i, (_, out, act, drop) in enumerate(layer.fc):
+      spec.fc_out[i], spec.fc_act[i], spec.fc_dropout[i] = out, ACT[act], int(drop)
     spec.concat_at = layer.concat[0] if layer.concat else -1
     spec.action_dim = layer.concat[1] if layer.concat else 0
     spec.batch_norm = 1 if (layer.conv and layer.bn) else 0
@@ -161,7 +160,7 @@ class Network(object):
           add(name + "/biases", (10,))
         cin = 10
     d = int(np.prod(layer.feature_shape()))
-    for i, (scope, o, _) in enumerate(layer.fc):
+    for i, (scope, o, _, _) in enumerate(layer.fc):
       if layer.concat and layer.concat[0] == i:
         d += layer.concat[1]
       add(scope + "/weights", (d, o)); add(scope + "/biases", (o,))

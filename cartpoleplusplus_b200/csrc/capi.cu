@@ -20,6 +20,7 @@ int g_fwd_actor_sms = 37;  // SM budget of the actor's forward chain (mu is need
 int g_bwd_critic_sms = 74; // SM budget of the critic's backward chain in the fused DDPG step (the actor's gets the rest of the 148)
 int g_critic_tail = 1;     // the pixel critic's [hidden2, action] -> hidden3 -> q head as one kernel per evaluation / backward (mlp.cu)
 int g_is_training = 1;
+int g_dropout_seed = 1, g_dropout_external = 0;
 int g_wgrad_tc = 1;
 int g_fc_tc = [] { const char* e = getenv("CARTPOLEPP_FC_TC"); return e ? (atoi(e) & 15) : 0; }();   // off by default: measured slower than the FFMA kernels at every BASELINE size (profiles/r4/fc_tc.md)
 int g_wgrad_flush_steps = 32;     // the tensor-core accumulator truncates: 128-step chains cost 1.3e-5 on the conv1 weight gradient, 32 keep it at 5e-6 (profiles/r3/wgrad_flush.md)
@@ -105,6 +106,8 @@ int cpp_set_option(const char* name, int32_t value) {
   if (strcmp(name, "graphs") == 0) { set_step_options(-2, value); return CPP_OK; }
   if (strcmp(name, "prep_hoist") == 0) { g_prep_hoist = value != 0; return CPP_OK; }
   if (strcmp(name, "wgrad_flush_steps") == 0) { g_wgrad_flush_steps = value < 16 ? 16 : (value > 1024 ? 1024 : value); return CPP_OK; }
+  if (strcmp(name, "dropout_seed") == 0) { g_dropout_seed = value; return CPP_OK; }
+  if (strcmp(name, "dropout_external") == 0) { g_dropout_external = value != 0; return CPP_OK; }
   if (strcmp(name, "is_training") == 0) { g_is_training = value != 0; return CPP_OK; }
   if (strcmp(name, "fc_tc") == 0) { g_fc_tc = value & 15; return CPP_OK; }
   if (strcmp(name, "wgrad_tc") == 0) { g_wgrad_tc = value != 0; return CPP_OK; }
@@ -442,6 +445,9 @@ static int debug_view(const Net& net, const char* ws_part, const void* ws_base, 
   } else if (kind == 2) {
     CPP_REQUIRE(index >= 0 && index < net.n_fc, "debug_view: FC layer %d", index);
     off = L.h[index]; per = net.out_ld[index]; valid = net.out_dim[index];
+  } else if (kind == 3) {
+    CPP_REQUIRE(index >= 0 && index < net.n_fc && net.drop[index], "debug_view: FC layer %d has no dropout", index);
+    off = L.mask[index]; per = valid = net.out_dim[index];
   } else {
     set_error("debug_view: kind %d", kind);
     return CPP_ERR_INVALID;

@@ -33,6 +33,7 @@ extern int g_wgrad_flush_steps;   // mma.sync weight gradient: MMA K-steps accum
 extern int g_wgrad_tc;            // 1: conv1 weight gradient on tcgen05 (conv_wgrad_tc.cu) where supported, 0: always mma.sync
 extern int g_fc_tc;               // FC passes on tcgen05 (fc_tc.cu): 1 forward, 2 input gradient, 4 weight gradient, 8 = also GEMMs below the size where it pays
 extern int g_is_training;         // base_network.py:11 IS_TRAINING: batch statistics (1) or moving statistics (0) in slim.batch_norm; dropout on / off
+extern int g_dropout_seed, g_dropout_external;   // cpp_set_option: mask generator seed; 1 = masks are supplied by the caller (tests)
 extern int g_cta_cap;               // SMs a persistent kernel may occupy (agents lower it while independent chains share the GPU)
 static inline int sm_budget() { return g_cta_cap < 1 ? 1 : (g_cta_cap > 148 ? 148 : g_cta_cap); }
 #define CPP_CHECK_LAUNCH() do { ++cpp::g_launch_count; CPP_CHECK_CUDA(cudaGetLastError()); } while (0)
@@ -75,7 +76,11 @@ int launch_copy_cols(const float* src, int src_ld, int B, int cols, float* dst, 
 int launch_act_grad(const float* d_out, int d_ld, const float* out, int out_ld, int act, int B, int n, float* d_pre, int p_ld, cudaStream_t s);
 int launch_heads_dgrad(const float* dmu_pre, const float* Wmu, int A, const float* dl_pre, const float* Wl, int NL, int B, int D,
                        float* out, cudaStream_t s);
-int launch_add_gated(float* d, int d_ld, const float* extra, const float* x, int x_ld, int B, int n, cudaStream_t s);
+int launch_add_gated(float* d, int d_ld, const float* extra, const float* x, int x_ld, int B, int n, cudaStream_t s, float scale = 1.f);
+// slim.dropout(keep_prob 0.5) in training mode: h *= 2 * mask; mask u8 [B][n] is drawn here (counter-based hash of seed, *counter,
+// layer, element) unless external; launch_dropout_tick advances the device-side counter once per forward
+int launch_dropout(float* h, int ld, int B, int n, uint8_t* mask, const unsigned long long* counter, int layer, cudaStream_t s);
+int launch_dropout_tick(unsigned long long* counter, cudaStream_t s);
 int launch_colsum(const float* x, int ld, int B, int n, float* out, cudaStream_t s);
 int launch_scale_copy(const float* src, float scale, int64_t n, float* dst, cudaStream_t s);
 int launch_fill(float* dst, float v, int64_t n, cudaStream_t s);
@@ -89,6 +94,7 @@ struct GemmArgs {
   int M, N, K;
   int epi; const float* bias; int act;      // EPI_BIAS_ACT
   const float* aux; int aux_ld; int mask_cols;   // EPI_RELU_MASK: C[m][n] *= (aux[m][n] > 0) for n < mask_cols
+  float mask_scale;                         // EPI_RELU_MASK: factor of the open positions (0 reads as 1; 2 behind a dropout layer: d(2 m relu(z)))
   float* colsum;                            // tensor-core route, transA only: also out[n] = sum_k B[k][n] (an all-ones row appended to A);
                                             // the FFMA route ignores it (callers check gemm_tc_wanted and launch colsum themselves)
 };

@@ -318,15 +318,51 @@ int launch_heads_dgrad(const float* dmu_pre, const float* Wmu, int A, const floa
 
 // d[b][j] += extra[b][j], gated by the ReLU below (x = that layer's output; NULL: no gate)
 __global__ void add_gated_kernel(float* __restrict__ d, int d_ld, const float* __restrict__ extra, const float* __restrict__ x, int x_ld,
-                                 int B, int n) {
+                                 int B, int n, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n) return;
   const int b = i / n, j = i - b * n;
   const bool open = x == nullptr || x[(size_t)b * x_ld + j] > 0.f;
-  if (open) d[(size_t)b * d_ld + j] += extra[i];
+  if (open) d[(size_t)b * d_ld + j] += extra[i] * scale;
 }
-int launch_add_gated(float* d, int d_ld, const float* extra, const float* x, int x_ld, int B, int n, cudaStream_t s) {
-  add_gated_kernel<<<(unsigned)ceil_div(B * n, 256), 256, 0, s>>>(d, d_ld, extra, x, x_ld, B, n);
+int launch_add_gated(float* d, int d_ld, const float* extra, const float* x, int x_ld, int B, int n, cudaStream_t s, float scale) {
+  add_gated_kernel<<<(unsigned)ceil_div(B * n, 256), 256, 0, s>>>(d, d_ld, extra, x, x_ld, B, n, scale);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+
+// --use-dropout (base_network.py:69-70): slim.dropout(layer, keep_prob 0.5, is_training=IS_TRAINING) = inverted dropout
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void dropout_kernel(float* __restrict__ h, int ld, int B, int n, uint8_t* __restrict__ mask, const unsigned long long* __restrict__ counter,
+                               unsigned long long key, int external) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n) return;
+  const int b = i / n, j = i - b * n;
+  uint8_t m;
+  if (external) m = mask[i];
+  else {
+    m = (uint8_t)(splitmix64(splitmix64(key ^ *counter) + (unsigned long long)i) >> 63);     // Bernoulli(0.5)
+    mask[i] = m;
+  }
+  float* p = h + (size_t)b * ld + j;
+  *p = m ? *p * 2.f : 0.f;
+}
+__global__ void dropout_tick_kernel(unsigned long long* counter) { *counter += 1; }
+int launch_dropout(float* h, int ld, int B, int n, uint8_t* mask, const unsigned long long* counter, int layer, cudaStream_t s) {
+  // distinct streams per seed, layer and network (the counter lives in that network's workspace: its address tells them apart)
+  const unsigned long long key = ((unsigned long long)(unsigned)g_dropout_seed << 32) ^ ((unsigned long long)(unsigned)layer * 0x9E3779B1ull) ^
+                                 ((unsigned long long)reinterpret_cast<uintptr_t>(counter) * 0xD6E8FEB86659FD93ull);
+  dropout_kernel<<<(unsigned)ceil_div(B * n, 256), 256, 0, s>>>(h, ld, B, n, mask, counter, key, g_dropout_external);
+  CPP_CHECK_LAUNCH();
+  return CPP_OK;
+}
+int launch_dropout_tick(unsigned long long* counter, cudaStream_t s) {
+  dropout_tick_kernel<<<1, 1, 0, s>>>(counter);
   CPP_CHECK_LAUNCH();
   return CPP_OK;
 }

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               if (g.act == 1) v = fmaxf(v, 0.f);
               else if (g.act == 2) v = tanhf(v);
             } else if (g.epi == EPI_RELU_MASK) {
-              if (n < g.mask_cols && !(g.aux[(size_t)m * g.aux_ld + n] > 0.f)) v = 0.f;
+              if (n < g.mask_cols) v = (g.aux[(size_t)m * g.aux_ld + n] > 0.f) ? (g.mask_scale != 0.f ? v * g.mask_scale : v) : 0.f;
             }
             g.C[(size_t)m * g.ldc + n] = v;
           }

@@ -18,6 +18,7 @@ int Net::init(const cpp_net_spec& s) {
   CPP_REQUIRE(concat_at < n_fc, "concat_at=%d out of range", concat_at);
   CPP_REQUIRE(concat_at < 0 || action_dim >= 1, "action concat needs action_dim >= 1");
   vars.clear();
+  any_drop = false;
   int64_t off = 0;
   auto add_var = [&](int nd, int64_t a, int64_t b, int64_t c, int64_t d) {
     VarInfo v; v.offset = off; v.ndim = nd; v.shape[0] = a; v.shape[1] = b; v.shape[2] = c; v.shape[3] = d;
@@ -52,6 +53,9 @@ int Net::init(const cpp_net_spec& s) {
     in_dim[i] = d + (concat_at == i ? action_dim : 0);
     out_dim[i] = s.fc_out[i];
     act[i] = s.fc_act[i];
+    drop[i] = s.fc_dropout[i] != 0;
+    CPP_REQUIRE(!drop[i] || (i < n_fc - 1 && act[i] == 1), "dropout follows hidden ReLU layers only (layer %d)", i);
+    any_drop = any_drop || drop[i];
     off_fc_w[i] = off; add_var(2, in_dim[i], out_dim[i], 1, 1);
     off_fc_b[i] = off; add_var(1, out_dim[i], 1, 1, 1);
     d = out_dim[i];
@@ -97,6 +101,10 @@ Net::Layout Net::layout(int B) const {
   // layer i after the main chain has moved on) and the gradient wrt the last pre-activation
   for (int i = 0; i < n_fc; ++i) L.dX[i] = take((size_t)B * in_dim[i] * sizeof(float));
   L.dTop = take((size_t)B * out_dim[n_fc - 1] * sizeof(float));
+  if (any_drop) {
+    for (int i = 0; i < n_fc; ++i) if (drop[i]) L.mask[i] = take((size_t)B * out_dim[i]);
+    L.dropctr = take(sizeof(unsigned long long));
+  }
   L.total = off;
   return L;
 }
@@ -160,9 +168,11 @@ int Net::forward_fc(const float* params, const float* action, int B, void* ws_, 
   CPP_REQUIRE(B >= 1, "batch %d", B);
   if (end_fc < 0 || end_fc > n_fc) end_fc = n_fc;
   CPP_REQUIRE(concat_at < 0 || concat_at < first_fc || concat_at >= end_fc || action != nullptr, "this network needs an action input");
-  if (fused_mlp_enabled() && mlp_fits(*this)) return launch_mlp_forward(*this, params, action, B, ws_, out, s, first_fc, end_fc);
+  const bool dropping = any_drop && g_is_training;      // slim.dropout is the identity unless IS_TRAINING (base_network.py:69-70)
+  if (!dropping && fused_mlp_enabled() && mlp_fits(*this)) return launch_mlp_forward(*this, params, action, B, ws_, out, s, first_fc, end_fc);
   char* ws = reinterpret_cast<char*>(ws_);
   const Layout L = layout(B);
+  if (dropping) CPP_TRY(launch_dropout_tick(reinterpret_cast<unsigned long long*>(ws + L.dropctr), s));
   for (int i = first_fc; i < end_fc; ++i) {
     int ld;
     const float* x = fc_input(L, ws, i, &ld);
@@ -175,6 +185,9 @@ int Net::forward_fc(const float* params, const float* action, int B, void* ws_, 
     g.M = B; g.N = out_dim[i]; g.K = in_dim[i];
     g.epi = EPI_BIAS_ACT; g.bias = params + off_fc_b[i]; g.act = act[i];
     CPP_TRY(launch_gemm(g, s));
+    if (dropping && drop[i])
+      CPP_TRY(launch_dropout(reinterpret_cast<float*>(ws + L.h[i]), out_ld[i], B, out_dim[i], reinterpret_cast<uint8_t*>(ws + L.mask[i]),
+                             reinterpret_cast<const unsigned long long*>(ws + L.dropctr), i, s));
   }
   if (out != nullptr && end_fc == n_fc) {
     const int n = out_dim[n_fc - 1];
@@ -323,7 +336,8 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     return CPP_OK;
   };
   CPP_REQUIRE(d_rep_extra == nullptr || (grads != nullptr && concat_at < 0), "d_rep_extra needs a full backward pass of a network without action input");
-  const bool fused = fused_mlp_level() >= 2 && mlp_fits(*this) && d_rep_extra == nullptr;
+  const bool dropping = any_drop && g_is_training;
+  const bool fused = fused_mlp_level() >= 2 && mlp_fits(*this) && d_rep_extra == nullptr && !dropping;
   const int stop_at_f = (grads == nullptr) ? concat_at : 0;
   if (fused) {
     // one launch for the whole chain of input gradients; every weight / bias gradient afterwards (side stream if given)
@@ -382,11 +396,13 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     g.B = params + off_fc_w[i]; g.ldb = out_dim[i]; g.transB = 1;
     g.C = dnext; g.ldc = in_dim[i];
     g.M = B; g.N = in_dim[i]; g.K = out_dim[i];
-    if (i > 0) { g.epi = EPI_RELU_MASK; g.aux = x; g.aux_ld = xld; g.mask_cols = out_dim[i - 1]; }
+    // behind a dropout layer the input is 2 m relu(z): the stored activation is > 0 exactly where m = 1 and the ReLU is open
+    const float gate_scale = (i > 0 && dropping && drop[i - 1]) ? 2.f : 1.f;
+    if (i > 0) { g.epi = EPI_RELU_MASK; g.aux = x; g.aux_ld = xld; g.mask_cols = out_dim[i - 1]; g.mask_scale = gate_scale; }
     else g.epi = EPI_NONE;
     CPP_TRY(launch_gemm(g, s));
     if (i == last && d_rep_extra != nullptr)
-      CPP_TRY(launch_add_gated(dnext, in_dim[i], d_rep_extra, i > 0 ? x : nullptr, xld, B, in_dim[i], s));
+      CPP_TRY(launch_add_gated(dnext, in_dim[i], d_rep_extra, i > 0 ? x : nullptr, xld, B, in_dim[i], s, gate_scale));
     if (concat_at == i && d_action != nullptr)
       CPP_TRY(launch_copy_cols(dnext + (in_dim[i] - action_dim), in_dim[i], B, action_dim, d_action, action_dim, 0, s));
     dcur = dnext;

@@ -27,6 +27,8 @@ struct Net {
   int n_fc = 0;
   int in_dim[CPP_MAX_FC], out_dim[CPP_MAX_FC], act[CPP_MAX_FC], out_ld[CPP_MAX_FC];
   int concat_at = -1, action_dim = 0;
+  int drop[CPP_MAX_FC] = {};          // slim.dropout after this FC layer (--use-dropout)
+  bool any_drop = false;
   int64_t off_conv_w[3], off_conv_b[3], off_fc_w[CPP_MAX_FC], off_fc_b[CPP_MAX_FC];   // off_conv_b: biases, or BatchNorm/beta
   int64_t off_bn_mean[3], off_bn_var[3];                                              // BatchNorm/moving_mean, moving_variance
   int64_t nparams = 0;
@@ -34,6 +36,7 @@ struct Net {
 
   struct Layout {
     size_t pooled[3], amax[3], hl[2], x0, h[CPP_MAX_FC], dX[CPP_MAX_FC], dTop, dpool[2], wgrad, dyp, gsc, total;
+    size_t mask[CPP_MAX_FC], dropctr;           // dropout: u8 masks [B][out] of the last training forward, device-side draw counter
     size_t raw[3], bnscr[3], dconv, bnjunk;     // batch norm: raw conv outputs, statistics scratch, dense d(conv), sink for the unused bias gradient
   };
 

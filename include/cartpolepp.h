@@ -57,6 +57,10 @@ int64_t cpp_launch_count(void);
  * weight-gradient accumulators; "fc_tc" = mask of the fully connected passes that run on tcgen05 (fc_tc.cu): 1 forward,
  * 2 input gradient, 4 weight gradient (with the bias gradient folded in), + 8 to include GEMMs below 64 M MACs (default 0: measured
  * slower than the FFMA kernels at the BASELINE sizes, profiles/r4/fc_tc.md; CARTPOLEPP_FC_TC sets the start-up value).
+ * "dropout_seed" = seed of the library's own counter-based mask generator (TensorFlow's random stream cannot be reproduced;
+ * every training forward of a dropout network advances a device-side counter, so graph replays draw fresh masks),
+ * "dropout_external" = 1: masks are NOT generated - the caller has written 0/1 bytes into the mask buffers
+ * (cpp_*_debug_view kind 3) - for parity tests against an oracle that takes the masks as inputs;
  * "is_training" = the reference's global IS_TRAINING placeholder (base_network.py:11) for the raw cpp_net_* calls: batch (1,
  * default) or moving (0) statistics in slim.batch_norm; the agent entry points set it themselves (train ops: 1; action_given,
  * check_loss, debug_values, value_given: 0).
@@ -112,6 +116,8 @@ typedef struct {
   int32_t fc_act[CPP_MAX_FC];  /* 0 linear, 1 relu, 2 tanh */
   int32_t concat_at;           /* -1: no action input */
   int32_t action_dim;
+  int32_t fc_dropout[CPP_MAX_FC];  /* 1: slim.dropout(keep_prob 0.5) after this FC layer (--use-dropout, base_network.py:69-70): under
+                                * IS_TRAINING the output is multiplied by a Bernoulli(0.5) mask and by 2, else the identity */
   int32_t batch_norm;          /* --use-batch-norm (base_network.py:74-79): every conv layer is conv (no bias) -> slim.batch_norm
                                 * (center, no scale, eps 1e-3) -> ReLU -> pool; variables per conv layer: weights,
                                 * BatchNorm/beta, BatchNorm/moving_mean, BatchNorm/moving_variance (the last two are never
