@@ -21,7 +21,7 @@ int g_bwd_critic_sms = 74; // SM budget of the critic's backward chain in the fu
 int g_critic_tail = 1;     // the pixel critic's [hidden2, action] -> hidden3 -> q head as one kernel per evaluation / backward (mlp.cu)
 int g_is_training = 1;
 int g_dropout_seed = 1, g_dropout_external = 0;
-int g_wgrad_tc = 1;
+int g_wgrad_tc = 1;     // conv1 only: the piece-mode kernel (bit 1) is parity green but +40 us per c3 step (profiles/r4/wgrad_tc.md)
 int g_fc_tc = [] { const char* e = getenv("CARTPOLEPP_FC_TC"); return e ? (atoi(e) & 15) : 0; }();   // off by default: measured slower than the FFMA kernels at every BASELINE size (profiles/r4/fc_tc.md)
 int g_wgrad_flush_steps = 32;     // the tensor-core accumulator truncates: 128-step chains cost 1.3e-5 on the conv1 weight gradient, 32 keep it at 5e-6 (profiles/r3/wgrad_flush.md)
 int g_prep_hoist = 1;      // cpp_set_option("prep_hoist", 0): weight prep kernels stay in front of their main kernels (A/B timing)
@@ -110,7 +110,7 @@ int cpp_set_option(const char* name, int32_t value) {
   if (strcmp(name, "dropout_external") == 0) { g_dropout_external = value != 0; return CPP_OK; }
   if (strcmp(name, "is_training") == 0) { g_is_training = value != 0; return CPP_OK; }
   if (strcmp(name, "fc_tc") == 0) { g_fc_tc = value & 15; return CPP_OK; }
-  if (strcmp(name, "wgrad_tc") == 0) { g_wgrad_tc = value != 0; return CPP_OK; }
+  if (strcmp(name, "wgrad_tc") == 0) { g_wgrad_tc = value & 3; return CPP_OK; }
   if (strcmp(name, "conv1_split") == 0) { g_conv1_split = value != 0; return CPP_OK; }
   if (strcmp(name, "critic_tail") == 0) { g_critic_tail = value != 0; return CPP_OK; }
   if (strcmp(name, "fwd_actor_sms") == 0) { g_fwd_actor_sms = value < 16 ? 16 : (value > 100 ? 100 : value); return CPP_OK; }
@@ -262,7 +262,11 @@ int cpp_conv_dgrad_tc(const float* d_pooled, const uint8_t* amax, const float* w
   API_END
 }
 int64_t cpp_conv_wgrad_mma_scratch_bytes(int32_t nets, int32_t H, int32_t W, int32_t Cin, int32_t KS) {
-  return wg::conv_wgrad_mma_scratch_bytes(nets, H, W, Cin, KS);
+  // the same buffer serves every x_is_pieces value the caller may pass for this channel count
+  int64_t b = wg::conv_wgrad_mma_scratch_bytes(nets, H, W, Cin, KS);
+  if (Cin % 2 == 0) b = std::max(b, wg::conv_wgrad_mma_scratch_bytes(nets, H, W, Cin, KS, 1));
+  if (Cin == tc::kC24) b = std::max(b, wg::conv_wgrad_mma_scratch_bytes(nets, H, W, Cin, KS, 2));
+  return b;
 }
 int cpp_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int32_t x_is_pieces, int32_t nets, const float* const* d_pooled,
                        const uint8_t* const* amax, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t KS, float* const* dw,

@@ -537,7 +537,7 @@ int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS, int 
   Plan P{};
   if (build_plan(nets, 1, H, W, C, KS, &P, dup) != CPP_OK) return -1;
   const int64_t own = (int64_t)(al256(16) + al256((size_t)2 * kNumSMs * P.part_floats * 4) + al256((size_t)P.part_floats * 4));
-  const int64_t tcb = dup == 0 ? (int64_t)al256(16) + wgtc::scratch_bytes(nets, H, W, C, KS) : 0;     // the tcgen05 route shares the scratch
+  const int64_t tcb = (dup == 0 || dup == 2) ? (int64_t)al256(16) + wgtc::scratch_bytes(nets, H, W, C, KS, dup == 2) : 0;     // the tcgen05 route shares the scratch
   return std::max(own, tcb);
 }
 
@@ -589,8 +589,10 @@ int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int
     wgrad_absmax_kernel<<<dim3(blocks, nets), 256, 0, s>>>(P);
     CPP_CHECK_LAUNCH();
   }
-  if (dup == 0 && g_wgrad_tc && wgtc::supported(nets, H, W, C, KS))       // tcgen05 route (conv_wgrad_tc.cu): conv1 of c3-class inputs
-    return wgtc::launch(x_f16, mean_inv, nets, d_pooled, amax, B, H, W, C, KS, dw, db, P.gmax, reinterpret_cast<char*>(scratch) + al256(16), s);
+  // tcgen05 route (conv_wgrad_tc.cu): conv1 of c3-class inputs (wgrad_tc bit 0), conv2 / conv3 on the 24-channel pieces (bit 1)
+  if ((dup == 0 && (g_wgrad_tc & 1) && wgtc::supported(nets, H, W, C, KS, 0)) || (dup == 2 && (g_wgrad_tc & 2) && wgtc::supported(nets, H, W, C, KS, 1)))
+    return wgtc::launch(x_f16, mean_inv, nets, d_pooled, amax, B, H, W, C, KS, dw, db, P.gmax, reinterpret_cast<char*>(scratch) + al256(16), s,
+                        dup == 2);
   int st;
   switch (P.MT) {
     case 1: st = launch_nt<1>(P, s); break;

@@ -140,7 +140,7 @@ def kernel_table(only=None, reps=10, rm=None):
   # tail twice), FC bwd of 2
   kernels = [
       ("conv1_fwd_tc", conv1_fwd_tc, 2.0 * mac1, 2, "conv1 5x5 9->10 fwd, 2 sibling nets in one pass, incl. weight prep"),
-      ("conv1_wgrad_mma", conv1_wgrad_mma, 2.0 * mac1, 1, "conv1 weight gradient, actor+critic, incl. absmax/reduce/finalize"),
+      ("conv1_wgrad_mma", conv1_wgrad_mma, 2.0 * mac1, 1, "conv1 weight gradient, actor+critic (tcgen05, csrc/conv_wgrad_tc.cu), incl. absmax/reduce/finalize"),
       ("conv2_fwd_tc", c2[0], 2.0 * mac2, 4, "conv2 5x5 10->10 fwd, one network, incl. weight prep"),
       ("conv2_dgrad_tc", c2[1], 2.0 * mac2, 2, "conv2 input gradient, incl. un-pool/split + prep"),
       ("conv2_wgrad_mma", c2[2], 2.0 * mac2, 2, "conv2 weight gradient, one network"),

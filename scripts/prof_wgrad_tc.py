@@ -18,14 +18,17 @@ def main():
   import torch
   lib = L.lib()
   import scripts.bench_kernels as bk
-  sys.argv = ["bench_kernels.py", "--only", "conv1_wgrad_mma", "--reps", "3"]
+  if len(sys.argv) > 2:
+    bk.B = int(sys.argv[2])          # batch (default 256): kernel cycles vs number of steps separates fixed from per-step cost
+  which = sys.argv[1] if len(sys.argv) > 1 else "conv1_wgrad_mma"
+  sys.argv = ["bench_kernels.py", "--only", which, "--reps", "3"]
   bk.main()
   torch.cuda.synchronize()
   buf = (C.c_ulonglong * (160 * 12))()
   assert lib.cpp_debug_wgrad_tc_prof(buf) == 0
   a = np.frombuffer(buf, dtype=np.uint64).reshape(160, 12).astype(np.float64)
   a = a[a[:, 0] > 0]
-  print("== conv_wgrad_tc: %d CTAs" % a.shape[0])
+  print("== conv_wgrad_tc (%s): %d CTAs" % (which, a.shape[0]))
   for i, n in enumerate(NAMES):
     print("  %-42s mean %9.0f   min %9.0f   max %9.0f" % (n, a[:, i].mean(), a[:, i].min(), a[:, i].max()))
 

@@ -232,12 +232,22 @@ WGRAD = [
     (2, 40, 48, 6, 5, 1, False),      # tcgen05 route: 6 channels (4 window blocks + flags), one network (N = 32)
     (150, 16, 16, 8, 5, 2, False),    # tcgen05 route: more images than SMs' segments are long (several images per CTA)
     (2, 21, 32, 11, 5, 2, False),     # tcgen05 route: odd height (last row has no pooled gradient), widest window (7 + 1 blocks)
+    (40, 64, 64, 10, 5, 1, 2),        # tcgen05 route, pieces: c5 conv2 shape (64 wide: 4 K-steps per row)
+    (9, 48, 32, 10, 3, 1, 2),         # tcgen05 route, pieces: 3x3 on a non-square image
+    (256, 16, 16, 10, 3, 1, 2),       # c3 conv3 at full batch
 ]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,KS,nets,pieces", WGRAD, ids=["%dx%dx%dx%d_k%d_n%d_p%d" % w for w in WGRAD])
 def test_conv_wgrad_mma(B, H, W, Cin, KS, nets, pieces):
-  print("wgrad_mma (dw, db) rel err vs fp64:", run_wgrad_mma(B, H, W, Cin, KS, nets, seed=B + H + Cin + nets, pieces=pieces))
+  """every supported shape through the tcgen05 kernel (wgrad_tc = 3: conv1 on raw pixels AND conv2 / conv3 on pieces; the
+  library default is 1), everything else through the mma.sync kernel"""
+  L, lib = _lib()
+  try:
+    L.check(lib.cpp_set_option(b"wgrad_tc", 3))
+    print("wgrad_mma (dw, db) rel err vs fp64:", run_wgrad_mma(B, H, W, Cin, KS, nets, seed=B + H + Cin + nets, pieces=pieces))
+  finally:
+    L.check(lib.cpp_set_option(b"wgrad_tc", 1))
 
 
 def test_conv_wgrad_route_switch():
@@ -246,6 +256,7 @@ def test_conv_wgrad_route_switch():
   try:
     L.check(lib.cpp_set_option(b"wgrad_tc", 0))
     print("wgrad mma.sync route c3 shape:", run_wgrad_mma(8, 64, 64, 9, 5, 2, seed=21))
+    print("wgrad mma.sync route conv2 pieces:", run_wgrad_mma(8, 32, 32, 10, 5, 1, seed=22, pieces=2))
   finally:
     L.check(lib.cpp_set_option(b"wgrad_tc", 1))
   print("wgrad tcgen05 route c3 shape:", run_wgrad_mma(8, 64, 64, 9, 5, 2, seed=21))
