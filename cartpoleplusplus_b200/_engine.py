@@ -107,6 +107,17 @@ class EngineBase(object):
     self.world_size, self.rank = 1, 0
 
   # ---- data parallel -----------------------------------------------------------------------------------
+  def check_piece_overflow(self, reset=True):
+    """raise if an activation exceeded what the fp16 hi + lo piece copy between conv layers can hold (2 x 65504) since the last
+    check - the tensor-core route would then have clipped it for the next layer.  Synchronises the device: call it at
+    checkpoints / evaluation time, not every step (the CLIs do so once per STATS line)."""
+    n = int(self.lib.cpp_piece_overflow_count(1 if reset else 0))
+    if n < 0:
+      raise _lib.CppError(-2, self.lib.cpp_last_error().decode("utf-8", "replace"))
+    if n > 0:
+      raise _lib.CppError(-4, "%d conv activations exceeded 131008: the fp16 piece copy of the tensor-core route saturated; "
+                              "rerun with cpp_set_option('conv1_tc', 0) (exact fp32 route)" % n)
+
   def set_data_parallel(self, dp, lib_comm=True, transport=None):
     """make this engine one replica of `dp.world_size`: rank 0's parameters, targets and optimiser state are broadcast (replicas
     must start from identical bits: only gradients are exchanged afterwards), and - on GPUs - the gradient all-reduce moves

@@ -61,7 +61,7 @@ class LRPGBuffers(C.Structure):
 
 
 # every symbol include/cartpolepp.h declares (tests/test_abi.py checks the list against the header)
-SYMBOLS = """cpp_version cpp_last_error cpp_launch_count cpp_set_option
+SYMBOLS = """cpp_version cpp_last_error cpp_launch_count cpp_piece_overflow_count cpp_set_option
 cpp_conv_wgrad_mma_scratch_bytes cpp_conv_wgrad_mma cpp_conv_dgrad_tc_scratch_bytes cpp_conv_dgrad_tc cpp_ddpg_step_backward cpp_ddpg_step_apply cpp_ddpg_train_step
 cpp_conv_forward cpp_conv_dgrad cpp_conv_wgrad_scratch_floats cpp_conv_wgrad
 cpp_conv_tc_scratch_bytes cpp_conv_forward_tc
@@ -79,7 +79,7 @@ cpp_naf_update_targets cpp_naf_debug_view
 cpp_lrpg_create cpp_lrpg_destroy cpp_lrpg_workspace_bytes cpp_lrpg_num_params cpp_lrpg_bind cpp_lrpg_train
 cpp_lrpg_logits""".split()
 
-_INT64_RET = {"cpp_launch_count", "cpp_conv_dgrad_tc_scratch_bytes", "cpp_conv_wgrad_mma_scratch_bytes", "cpp_conv_tc_scratch_bytes", "cpp_conv_wgrad_scratch_floats", "cpp_moments_scratch_doubles", "cpp_net_num_params", "cpp_net_workspace_bytes", "cpp_norm_scratch_doubles",
+_INT64_RET = {"cpp_launch_count", "cpp_piece_overflow_count", "cpp_conv_dgrad_tc_scratch_bytes", "cpp_conv_wgrad_mma_scratch_bytes", "cpp_conv_tc_scratch_bytes", "cpp_conv_wgrad_scratch_floats", "cpp_moments_scratch_doubles", "cpp_net_num_params", "cpp_net_workspace_bytes", "cpp_norm_scratch_doubles",
               "cpp_ddpg_workspace_bytes", "cpp_naf_workspace_bytes", "cpp_lrpg_workspace_bytes", "cpp_lrpg_num_params"}
 
 

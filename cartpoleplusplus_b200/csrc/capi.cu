@@ -97,6 +97,12 @@ int cpp_version(void) { return CPP_ABI_VERSION; }
 const char* cpp_last_error(void) { return get_error(); }
 int64_t cpp_launch_count(void) { return g_launch_count; }
 
+int64_t cpp_piece_overflow_count(int32_t reset) {
+  unsigned int n = 0;
+  if (tc::piece_overflow_count(reset, &n) != CPP_OK) return -1;
+  return (int64_t)n;
+}
+
 int cpp_set_option(const char* name, int32_t value) {
   API_BEGIN
   NEED(name);

@@ -34,6 +34,14 @@ constexpr int kSmemLimit = 224 * 1024;   // dynamic shared memory one CTA may us
 
 using namespace umma;
 
+// activations whose fp16 piece pair saturated since the last reset (cpp_piece_overflow_count)
+__device__ unsigned int g_piece_overflow = 0;
+int piece_overflow_count(int reset, unsigned int* out) {
+  CPP_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_piece_overflow, sizeof(unsigned int)));
+  if (reset) { const unsigned int z = 0; CPP_CHECK_CUDA(cudaMemcpyToSymbol(g_piece_overflow, &z, sizeof(unsigned int))); }
+  return CPP_OK;
+}
+
 // instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N
 __host__ __device__ inline uint32_t make_idesc(int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
@@ -347,6 +355,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
                 const float v0 = fmaxf(best[o], 0.f), v1 = fmaxf(best[o + 1], 0.f);
                 const __half h0 = __float2half_rn(fminf(v0, 65504.f)), h1 = __float2half_rn(fminf(v1, 65504.f));
                 const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+                // hi + lo represent activations up to 65504 + 65504: beyond that the piece copy (not the fp32 output) saturates -
+                // never silently: the counter is read by cpp_piece_overflow_count (the engines raise on it)
+                if (fmaxf(v0, v1) > 131000.f) atomicAdd(&g_piece_overflow, 1u);
                 hi[o >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
                 lo[o >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
               }

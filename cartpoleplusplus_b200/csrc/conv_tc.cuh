@@ -61,6 +61,8 @@ struct PrepArgs {
   float* corr;
 };
 
+// number of activations > 131 008 (= 2 x the fp16 maximum) that the hi + lo piece copy for the next layer could not represent
+int piece_overflow_count(int reset, unsigned int* out);
 int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS);
 bool conv_tc_supported(int nets, int H, int W, int C, int KS);
 // y_n = maxpool2x2(relu(conv_same(whiten(x), w_n) + b_n)) for n < nets sibling networks in ONE pass over x.

@@ -332,6 +332,7 @@ class NormalizedAdvantageFunctionAgent(object):
       stats["total_reward"] = float(np.sum(rewards))
       stats["episode_len"] = len(rewards)
       stats["replay_memory_stats"] = self.replay_memory.current_stats()
+      self.naf._engine.check_piece_overflow()      # (one device sync per STATS line)
       print("STATS %s\t%s" % (datetime.datetime.now().strftime('%Y-%m-%d %H:%M:%S'), json.dumps(stats)))
       sys.stdout.flush()
       if saver_util is not None:

@@ -41,6 +41,10 @@ int cpp_version(void);
 const char* cpp_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches) */
 int64_t cpp_launch_count(void);
+/* The tensor-core route hands the fp32 activation between conv layers on as two fp16 pieces (hi + lo); a value above
+ * 2 x 65504 saturates that copy (the fp32 output itself is exact).  Number of such values since the last reset, synchronises
+ * the device; -1 on a CUDA error.  The Python engines check it after a step when CARTPOLEPP_CHECK_OVERFLOW=1. */
+int64_t cpp_piece_overflow_count(int32_t reset);
 
 /* runtime switches (tests and A/B timing): "conv1_tc" = 1 routes conv1 forward / weight gradient of fp16 states through the
  * tensor-core kernels (default, also CARTPOLEPP_CONV1=tc), 0 through the exact-fp32 CUDA-core kernels, -1 = environment default;

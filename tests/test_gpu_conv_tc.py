@@ -208,3 +208,29 @@ def run_dgrad_tc(B, H, W, KS, seed):
                                       (256, 16, 16, 3), (1, 4, 4, 3)])
 def test_conv_dgrad_tc(B, H, W, KS):
   print("dgrad_tc B%d %dx%d k%d: rel err vs fp64 %.2e" % (B, H, W, KS, run_dgrad_tc(B, H, W, KS, seed=B + H + KS)))
+
+
+def test_piece_overflow_is_counted_not_silent():
+  """an activation above 2 x 65504 cannot be carried by the fp16 hi + lo piece copy that feeds the next tensor-core layer: the
+  fp32 output stays exact, the copy saturates, and cpp_piece_overflow_count reports it (EngineBase.check_piece_overflow raises)"""
+  import ctypes as C
+  from cartpoleplusplus_b200 import _lib as L
+  lib = L.lib()
+  B, H, W, Cin = 2, 16, 16, 9
+  dev = "cuda"
+  x = torch.ones(B, H, W, Cin, dtype=torch.float16, device=dev)
+  mi = torch.cat([torch.zeros(Cin), torch.ones(Cin)]).to(dev)                 # no whitening: mean 0, inv 1
+  w = [torch.full((5, 5, Cin, 10), 1000.0, device=dev)]                       # 225 taps x 1000 = 225 000 > 131 008 in the interior
+  b = [torch.zeros(10, device=dev)]
+  pooled = [torch.zeros(B, H // 2, W // 2, 10, device=dev)]
+  amax = [torch.zeros(B, H // 2, W // 2, 10, dtype=torch.uint8, device=dev)]
+  hl = [torch.zeros(B, H // 2, W // 2, 24, dtype=torch.float16, device=dev)]
+  scr = torch.zeros(int(lib.cpp_conv_tc_scratch_bytes(1, H, W, Cin, 5)), dtype=torch.uint8, device=dev)
+  assert int(lib.cpp_piece_overflow_count(1)) >= 0
+  L.check(lib.cpp_conv_forward_tc(L.ptr(x), None, L.ptr(mi), 1, L.ptr_array(w), L.ptr_array(b), B, H, W, Cin, 5, L.ptr_array(pooled),
+                                  L.ptr_array(amax), L.ptr(scr), L.stream_ptr(), 0, L.ptr_array(hl)))
+  torch.cuda.synchronize()
+  assert abs(float(pooled[0].max()) - 225000.0) < 1.0                          # the fp32 output is exact
+  n = int(lib.cpp_piece_overflow_count(1))
+  assert n > 0, "saturated piece copies were not counted"
+  assert int(lib.cpp_piece_overflow_count(0)) == 0                             # reset
