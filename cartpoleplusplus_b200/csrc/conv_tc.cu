@@ -24,6 +24,7 @@
 #include <vector>
 #include <algorithm>
 #include "conv_tc.cuh"
+#include "conv_row_tc.cuh"
 #include "umma.cuh"
 
 namespace cpp {
@@ -39,6 +40,9 @@ __device__ unsigned int g_piece_overflow = 0;
 int piece_overflow_count(int reset, unsigned int* out) {
   CPP_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_piece_overflow, sizeof(unsigned int)));
   if (reset) { const unsigned int z = 0; CPP_CHECK_CUDA(cudaMemcpyToSymbol(g_piece_overflow, &z, sizeof(unsigned int))); }
+  unsigned int row = 0;
+  CPP_TRY(tcr::piece_overflow_count(reset, &row));               // the row-sweep kernel of conv2 / conv3 keeps its own counter
+  *out += row;
   return CPP_OK;
 }
 
@@ -763,7 +767,9 @@ int64_t conv_tc_scratch_bytes(int nets, int H, int W, int C, int KS) {
   FwdPlan P{};
   if (build_plan(nets, 1, H, W, C, KS, &P) != CPP_OK) return -1;
   const int ncls = 2 * P.PAD + 1;
-  return (int64_t)bpack_bytes(P) + (int64_t)round_up((int64_t)(ncls * ncls * nets * CO + 4) * 4, 256);
+  const int64_t b = (int64_t)bpack_bytes(P) + (int64_t)round_up((int64_t)(ncls * ncls * nets * CO + 4) * 4, 256);
+  // the same scratch serves the row-sweep kernel (conv_row_tc.cu) when the layer is a piece-layout one it covers
+  return C == kC24 && nets == 1 ? std::max(b, tcr::scratch_bytes(H, W, KS)) : b;
 }
 
 template <int KS, int R>
@@ -784,6 +790,11 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
                        float* const* pooled, uint8_t* const* amax, void* scratch, cudaStream_t s,
                        int x_is_pieces, __half* const* pooled_hl, int phase) {
   if (B <= 0) return CPP_OK;
+  if (x_is_pieces == 2 && nets == 1 && rows == nullptr && mean_inv == nullptr && C == kC24 && tcr::supported(H, W, KS)) {
+    CPP_REQUIRE(w[0] && bias[0], "conv_tc: null pointer for network 0");
+    return tcr::launch(x_f16, w[0], bias[0], B, H, W, KS, 0, phase == kPhasePrep ? nullptr : pooled[0], phase == kPhasePrep ? nullptr : amax[0],
+                       phase != kPhasePrep && pooled_hl ? pooled_hl[0] : nullptr, nullptr, nullptr, scratch, s, phase);
+  }
   FwdPlan P{};
   CPP_TRY(build_plan(nets, B, H, W, C, KS, &P));
   CPP_REQUIRE(x_is_pieces == 0 || (mean_inv == nullptr && C == (x_is_pieces == 2 ? kC24 : 2 * CO)), "conv_tc: piece input has 20 or 24 channels and no whitening");
@@ -821,10 +832,12 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
 int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
                          void* scratch, cudaStream_t s, float* out_absmax, int phase) {
   if (B <= 0) return CPP_OK;
+  if (out_absmax != nullptr && phase != kPhasePrep) CPP_CHECK_CUDA(cudaMemsetAsync(out_absmax, 0, sizeof(float), s));
+  if (tcr::supported(H, W, KS))
+    return tcr::launch(dy_pieces, w, nullptr, B, H, W, KS, 1, dx, nullptr, nullptr, inv_scale, out_absmax, scratch, s, phase);
   FwdPlan P{};
   CPP_TRY(build_plan(1, B, H, W, kC24, KS, &P, 1));
   P.out_absmax = out_absmax;
-  if (out_absmax != nullptr && phase != kPhasePrep) CPP_CHECK_CUDA(cudaMemsetAsync(out_absmax, 0, sizeof(float), s));
   CPP_REQUIRE(((uintptr_t)dy_pieces & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "conv_tc: unaligned buffers");
   P.Cw = CO; P.in_layout = 2;
   P.x = reinterpret_cast<const __half*>(dy_pieces); P.rows = nullptr;

@@ -37,6 +37,8 @@ def kernel_table(only=None, reps=10, rm=None):
   """[{kernel, what, launches_per_step, us_median, us_min, useful_gflop | bytes, ...}] at the c3 layer shapes; rm: a filled
   ReplayMemory for the gather line (bench.py passes its own)"""
   lib = L.lib()
+  if os.environ.get("CONV_ROW") is not None:     # A/B of the conv2 / conv3 route: 1 row-sweep kernel (default), 0 parity-plane kernel
+    L.check(lib.cpp_set_option(b"conv_row", int(os.environ["CONV_ROW"])))
   dev = "cuda"
   g = torch.Generator(device=dev); g.manual_seed(0)
   rs = np.random.RandomState(0)
@@ -154,7 +156,7 @@ def kernel_table(only=None, reps=10, rm=None):
   ]
   rows = []
   for name, fn, flops, per_step, what in kernels:
-    if only and only != name:
+    if only and name not in only.split(","):
       continue
     med, mn = timeit(fn, flush, reps)
     rows.append(dict(kernel=name, what=what, launches_per_step=per_step, us_median=med, us_min=mn, useful_gflop=flops / 1e9,
