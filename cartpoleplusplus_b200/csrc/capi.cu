@@ -22,7 +22,7 @@ int g_bwd_critic_sms = 74; // SM budget of the critic's backward chain in the fu
 int g_critic_tail = 1;     // the pixel critic's [hidden2, action] -> hidden3 -> q head as one kernel per evaluation / backward (mlp.cu)
 int g_is_training = 1;
 int g_dropout_seed = 1, g_dropout_external = 0;
-int g_wgrad_tc = 1;     // conv1 only: the piece-mode kernel (bit 1) is parity green but +40 us per c3 step (profiles/r4/wgrad_tc.md)
+int g_wgrad_tc = 5;     // bit 0: conv1 on tcgen05 (conv_wgrad_tc.cu); bit 2: conv2 / conv3 on the row-sweep tcgen05 kernel (conv_wgrad_row_tc.cu); bit 1: the older piece-mode kernel (parity green, +40 us per c3 step: profiles/r4/wgrad_tc.md)
 int g_fc_tc = [] { const char* e = getenv("CARTPOLEPP_FC_TC"); return e ? (atoi(e) & 15) : 0; }();   // off by default: measured slower than the FFMA kernels at every BASELINE size (profiles/r4/fc_tc.md)
 int g_wgrad_flush_steps = 32;     // the tensor-core accumulator truncates: 128-step chains cost 1.3e-5 on the conv1 weight gradient, 32 keep it at 5e-6 (profiles/r3/wgrad_flush.md)
 int g_prep_hoist = 1;      // cpp_set_option("prep_hoist", 0): weight prep kernels stay in front of their main kernels (A/B timing)
@@ -117,7 +117,7 @@ int cpp_set_option(const char* name, int32_t value) {
   if (strcmp(name, "dropout_external") == 0) { g_dropout_external = value != 0; return CPP_OK; }
   if (strcmp(name, "is_training") == 0) { g_is_training = value != 0; return CPP_OK; }
   if (strcmp(name, "fc_tc") == 0) { g_fc_tc = value & 15; return CPP_OK; }
-  if (strcmp(name, "wgrad_tc") == 0) { g_wgrad_tc = value & 3; return CPP_OK; }
+  if (strcmp(name, "wgrad_tc") == 0) { g_wgrad_tc = value & 7; return CPP_OK; }
   if (strcmp(name, "conv_row") == 0) { tcr::set_conv_row(value); return CPP_OK; }
   if (strcmp(name, "conv1_split") == 0) { g_conv1_split = value != 0; return CPP_OK; }
   if (strcmp(name, "critic_tail") == 0) { g_critic_tail = value != 0; return CPP_OK; }
@@ -265,6 +265,8 @@ int cpp_conv_dgrad_tc(const float* d_pooled, const uint8_t* amax, const float* w
   float* gsc = reinterpret_cast<float*>(sc);
   __half* dyp = reinterpret_cast<__half*>(sc + 256);
   void* pk = sc + 256 + round_up((int64_t)B * H * W * tc::kC24 * 2, 256);
+  if (tc::conv_dgrad_fused_supported(H, W, KS))
+    return tc::launch_conv_dgrad_tc_fused(d_pooled, amax, gsc, gsc + 1, 0, w, B, H, W, KS, dx, pk, ST(stream));
   CPP_TRY(tc::launch_unpool_split(d_pooled, amax, B, H, W, gsc, gsc + 1, dyp, ST(stream)));
   return tc::launch_conv_dgrad_tc(dyp, gsc + 1, w, B, H, W, KS, dx, pk, ST(stream));
   API_END

@@ -43,7 +43,9 @@ constexpr int kStages = 8;                    // input-row strips in flight
 constexpr int kAhead = 6;                     // cp.async route: row strips whose copies are in flight before the oldest is awaited
 constexpr int kMaxSteps = 8;                  // K16 instructions per input row (KS = 5: 15 K8 halves)
 constexpr int kEpiWarps = 8;                  // two groups of four (one warp per TMEM lane quarter); group e drains pairs of parity e
-constexpr int kThreads = 32 * (kEpiWarps + 2);   // + TMA producer warp + MMA warp
+constexpr int kProdWarps = 8;                 // producer warps: TMA / cp.async use the first; the fused un-pool route all of them (two groups
+                                              // of four, group q builds the strips of rows n = q mod 2)
+constexpr int kThreads = 32 * (kEpiWarps + kProdWarps + 1);   // + MMA warp
 constexpr int kMinSmem = 116 * 1024;          // more than half an SM: two CTAs of concurrent chains must never share an SM - the
                                               // second would sit in tcgen05.alloc until the first is done while other SMs idle
 
@@ -59,6 +61,12 @@ struct RowPlan {
   int n_steps, N;
   int use_tma;              // 1: input strips by TMA tensor-map boxes (OOB zero fill, default); 0: 16-byte cp.async into pre-zeroed strips
   const __half* x;          // fp16 pieces [B][H][W][24] (cp.async route)
+  // fused un-pool route (dgrad): the strips are built from the pooled-output gradient and the arg-max side band, no piece tensor
+  int unpool;
+  const float* gp;          // d(pooled) fp32 [B][H/2][W/2][10]
+  const uint8_t* gamax;     // arg-max side band of the layer's forward pass
+  const float* gmax;        // device float: max |gp| (power-of-two scaling of the fp16 pieces)
+  float* inv_scale_out;     // optional: receives 1 / scale
   int plane_bytes, stage_bytes;
   int8_t kx[kMaxSteps][2], g[kMaxSteps][2];   // (tap column, channel group) of the two K8 halves of a step; g = -1: zero half
   uint32_t a_lo[kMaxSteps];                   // low word of the A descriptor of a step relative to the stage base: (offset >> 4) | (LBO >> 4) << 16
@@ -164,6 +172,13 @@ __host__ __device__ inline uint32_t make_idesc(int N) {      // D fp32, A/B fp16
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// power of two that brings max |g| just under 2^15 (the un-pool / split pass of conv_tc.cu uses the same rule)
+__device__ __forceinline__ float piece_scale(float mx) {
+  float scale = 1.f;
+  if (mx > 0.f && isfinite(mx)) { int e; frexpf(mx, &e); scale = ldexpf(1.f, 15 - e); }
+  return scale;
+}
+
 // Work distribution: the pooled rows (output row pairs) of all tiles, tile-major, are cut into one contiguous range per CTA; a
 // CTA walks its range in segments (tile, output rows [ya, yb)) that never cross a tile.  A segment that starts or ends inside an
 // image re-reads PAD input rows of its neighbour - the price of an even split when there are fewer tiles than 3 per SM.
@@ -204,14 +219,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_tc_kernel(const __grid_c
   const int H = P.H, W = P.W, E = P.E, HP = H / 2;
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars[BAR_FULL_A + i], 1); mbar_init(&bars[BAR_EMPTY_A + i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars[BAR_FULL_A + i], P.unpool ? 4 : 1); mbar_init(&bars[BAR_EMPTY_A + i], 1); }
     for (int i = 0; i < kPairs; ++i) { mbar_init(&bars[BAR_ACC_FULL + i], 1); mbar_init(&bars[BAR_ACC_FREE + i], 4); }
     mbar_init(&bars[BAR_W], 1);
     fence_mbar_init();
   }
-  if (warp == kEpiWarps + 1) tmem_alloc(tmem_slot, 512);
+  if (warp == kEpiWarps + kProdWarps) tmem_alloc(tmem_slot, 512);
   if (tid < CO + 1) tab_s[tid] = P.tab[tid];
-  if (!P.use_tma) {
+  if (!P.use_tma && !P.unpool) {
     // cp.async route: only image pixels are ever copied, the SAME-padding halo entries (and the tail past the last image) stay zero
     uint4* st = reinterpret_cast<uint4*>(stage_base);
     for (int i = tid; i < kStages * P.stage_bytes / 16; i += kThreads) st[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_tc_kernel(const __grid_c
     float bias[CO];
 #pragma unroll
     for (int o = 0; o < CO; ++o) bias[o] = tab_s[o];
-    const float osc = P.dgrad ? scale_inv * P.out_scale[0] : 0.f;
+    const float osc = P.dgrad ? scale_inv * (P.unpool ? 1.f / piece_scale(P.gmax[0]) : P.out_scale[0]) : 0.f;
     float amx = 0.f;
     int gp = 0;
     int tile, ya, yb;
@@ -360,6 +375,67 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_tc_kernel(const __grid_c
 #ifdef CONV_ROW_PROF
     if (warp == 0) { RPROF_PUT(7, clock64() - pf_start); RPROF_PUT(8, pf_w0); }
 #endif
+  } else if (warp < kEpiWarps + kProdWarps && P.unpool) {
+    // =========================================================================== producer warps, fused un-pool route (dgrad)
+    // The A strips are built on the fly: entry (image, x) of input row r = the un-pooled output gradient at (r, x) - d(pooled) of the
+    // window where the arg-max byte points at this position, else 0 - times a power of two, as hi / lo fp16 pieces.  Thread j of a
+    // group owns strip entry j; group q takes the rows with n = q mod 2, so that the L2 latency of one row's loads hides behind
+    // the other group's row.
+    const int pw = warp - kEpiWarps, grp = pw >> 2, j = 32 * (pw & 3) + lane;
+    if (pw == 0 && lane == 0) {
+      const uint32_t wbytes = (uint32_t)(NSTEPS * 2 * N * 16);
+      mbar_expect_tx(&bars[BAR_W], wbytes);
+      bulk_g2s(bsm, P.bpack, wbytes, &bars[BAR_W]);
+    }
+    const float scale = piece_scale(P.gmax[0]);
+    if (blockIdx.x == 0 && pw == 0 && lane == 0 && P.inv_scale_out != nullptr) P.inv_scale_out[0] = 1.f / scale;
+    const int img_l = j / E, xe = j - img_l * E, x = xe - PAD, PW = W / 2;
+    const bool col_ok = img_l < P.ipt && x >= 0 && x < W;
+    const bool entry_ok = j < P.ipt * E;
+    uint32_t n = 0;
+    int tile, ya, yb;
+    for (SegIter it(P); it.next(tile, ya, yb);) {
+      const int ra = max(0, ya - PAD), rb = min(H - 1, yb - 1 + PAD);
+      const int b = tile * P.ipt + img_l;
+      const bool ok = col_ok && b < P.B;
+      for (int r = ra; r <= rb; ++r, ++n) {
+        if ((int)(n & 1u) != grp) continue;
+        uint32_t hi[5] = {0u, 0u, 0u, 0u, 0u}, lo[5] = {0u, 0u, 0u, 0u, 0u};
+        if (ok) {
+          const size_t idx = (((size_t)b * HP + (r >> 1)) * PW + (x >> 1)) * CO;
+          const uint32_t pa = (uint32_t)(((r & 1) << 1) | (x & 1));
+          float2 g[5];
+          uint32_t am[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            g[k] = *reinterpret_cast<const float2*>(P.gp + idx + 2 * k);
+            am[k] = *reinterpret_cast<const uint16_t*>(P.gamax + idx + 2 * k);
+          }
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const float v0 = (am[k] & 0xffu) == pa ? g[k].x * scale : 0.f, v1 = (am[k] >> 8) == pa ? g[k].y * scale : 0.f;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+            hi[k] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo[k] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          }
+        }
+        const uint32_t s = n % kStages;
+        RPROF_WAIT(pf_w0, mbar_wait(&bars[BAR_EMPTY_A + s], ((n / kStages) & 1u) ^ 1u));
+        if (entry_ok) {                                            // halo entries and images past the batch: zeros
+          uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + (size_t)j * 16;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + P.plane_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(dst + 2 * P.plane_bytes) = make_uint4(hi[4], lo[4], 0u, 0u);    // the constant channel stays 0 in a gradient
+        }
+        fence_proxy_async();                                       // generic-proxy strip writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BAR_FULL_A + s]);
+      }
+    }
+#ifdef CONV_ROW_PROF
+    if (pw == 0) { RPROF_PUT(4, clock64() - pf_start); RPROF_PUT(5, pf_w0); }
+#endif
   } else if (warp == kEpiWarps) {
     // =========================================================================== producer warp
     if (lane == 0) {                                             // packed weights: one bulk copy, awaited by the MMA thread only
@@ -418,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_tc_kernel(const __grid_c
       }
       RPROF_PUT(4, clock64() - pf_start); RPROF_PUT(5, pf_w0);
     }
-  } else {
+  } else if (warp == kEpiWarps + kProdWarps) {
     // =========================================================================== MMA warp (one elected lane issues)
     // One instruction per (input row, K16 step): N = nt * 32 columns = the nt output rows this input row contributes to, which are
     // consecutive ring slots; windows that start in the last slots run on into the shadow slots behind the ring instead of
@@ -467,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_tc_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kEpiWarps + 1) tmem_dealloc(tmem_base, 512);
+  if (warp == kEpiWarps + kProdWarps) tmem_dealloc(tmem_base, 512);
 #ifdef CONV_ROW_PROF
   if (tid == 0) g_rprof[blockIdx.x][9] = (unsigned long long)(clock64() - pf_k0);
 #endif
@@ -483,14 +559,16 @@ extern "C" __attribute__((visibility("default"))) int cpp_debug_conv_row_prof(un
 #endif
 
 // ------------------------------------------------------------------------------------------ host
-static int g_conv_row = 1;      // bit 0: route on; bit 1: input strips by 16-byte cp.async instead of TMA tensor-map boxes
-void set_conv_row(int on) { g_conv_row = on & 3; }
+static int g_conv_row = 1;      // bit 0: route on; bit 1: input strips by 16-byte cp.async instead of TMA tensor-map boxes; bit 2: input
+                                // gradient from a piece tensor written by a separate un-pool / split pass instead of the fused producer
+void set_conv_row(int on) { g_conv_row = on & 7; }
 int conv_row_enabled() { return g_conv_row; }
 
 bool shape_ok(int H, int W, int KS) {
   return (KS == 5 || KS == 3) && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && W + KS - 1 <= 128;
 }
 bool supported(int H, int W, int KS) { return (g_conv_row & 1) && shape_ok(H, W, KS); }
+bool fused_unpool(int H, int W, int KS) { return supported(H, W, KS) && !(g_conv_row & 4); }
 
 static int build_plan(int B, int H, int W, int KS, int dgrad, RowPlan* P) {
   CPP_REQUIRE(shape_ok(H, W, KS), "conv_row: %dx%d k%d not supported", H, W, KS);
@@ -545,7 +623,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 int launch(const void* x_pieces, const float* w, const float* bias, int B, int H, int W, int KS, int dgrad, float* out, uint8_t* amax,
-           __half* out_hl, const float* out_scale, float* out_absmax, void* scratch, cudaStream_t s, int phase) {
+           __half* out_hl, const float* out_scale, float* out_absmax, void* scratch, cudaStream_t s, int phase,
+           const float* unpool_gp, const uint8_t* unpool_amax, const float* unpool_gmax, float* unpool_inv_scale) {
   if (B <= 0) return CPP_OK;
   RowPlan P{};
   CPP_TRY(build_plan(B, H, W, KS, dgrad, &P));
@@ -559,11 +638,17 @@ int launch(const void* x_pieces, const float* w, const float* bias, int B, int H
     CPP_CHECK_LAUNCH();
   }
   if (phase == tc::kPhasePrep) return CPP_OK;
-  CPP_REQUIRE(x_pieces != nullptr && out != nullptr && (dgrad ? out_scale != nullptr : amax != nullptr), "conv_row: null pointer");
-  CPP_REQUIRE(((uintptr_t)x_pieces & 15) == 0, "conv_row: unaligned input");
+  P.unpool = unpool_gp != nullptr ? 1 : 0;
+  if (P.unpool) {
+    CPP_REQUIRE(dgrad && unpool_amax != nullptr && unpool_gmax != nullptr && out != nullptr, "conv_row: fused un-pool needs dgrad mode, the arg-max band and max|g|");
+    P.gp = unpool_gp; P.gamax = unpool_amax; P.gmax = unpool_gmax; P.inv_scale_out = unpool_inv_scale;
+  } else {
+    CPP_REQUIRE(x_pieces != nullptr && out != nullptr && (dgrad ? out_scale != nullptr : amax != nullptr), "conv_row: null pointer");
+    CPP_REQUIRE(((uintptr_t)x_pieces & 15) == 0, "conv_row: unaligned input");
+  }
   P.out = out; P.amax = amax; P.out_hl = out_hl; P.out_scale = out_scale; P.out_absmax = out_absmax;
   P.x = reinterpret_cast<const __half*>(x_pieces);
-  P.use_tma = (g_conv_row & 2) ? 0 : 1;
+  P.use_tma = ((g_conv_row & 2) || P.unpool) ? 0 : 1;
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   if (P.use_tma) {

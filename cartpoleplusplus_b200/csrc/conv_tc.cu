@@ -908,18 +908,34 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ g
   }
 }
 
+int launch_absmax(const float* g, int64_t n, float* gmax, cudaStream_t s) {
+  CPP_CHECK_CUDA(cudaMemsetAsync(gmax, 0, sizeof(float), s));
+  if (n > 0) {
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, ceil_div(n, 256 * 8)));
+    absmax_kernel<<<blocks, 256, 0, s>>>(g, n, gmax);
+    CPP_CHECK_LAUNCH();
+  }
+  return CPP_OK;
+}
+
+bool conv_dgrad_fused_supported(int H, int W, int KS) { return tcr::fused_unpool(H, W, KS); }
+
+int launch_conv_dgrad_tc_fused(const float* d_pooled, const uint8_t* amax, float* gmax, float* inv_scale, int gmax_ready, const float* w,
+                               int B, int H, int W, int KS, float* dx, void* scratch, cudaStream_t s, float* out_absmax, int phase) {
+  if (B <= 0) return CPP_OK;
+  CPP_REQUIRE(conv_dgrad_fused_supported(H, W, KS), "conv_tc: fused un-pool input gradient does not cover %dx%d k%d", H, W, KS);
+  if (phase != kPhasePrep) {
+    if (!gmax_ready) CPP_TRY(launch_absmax(d_pooled, (int64_t)B * (H / 2) * (W / 2) * CO, gmax, s));
+    if (out_absmax != nullptr) CPP_CHECK_CUDA(cudaMemsetAsync(out_absmax, 0, sizeof(float), s));
+  }
+  return tcr::launch(nullptr, w, nullptr, B, H, W, KS, 1, dx, nullptr, nullptr, nullptr, out_absmax, scratch, s, phase, d_pooled, amax, gmax,
+                     inv_scale);
+}
+
 int launch_unpool_split(const float* d_pooled, const uint8_t* amax, int B, int H, int W, float* gmax, float* inv_scale,
                         __half* dy_pieces, cudaStream_t s, int gmax_ready) {
   if (B <= 0) return CPP_OK;
-  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * CO;
-  if (!gmax_ready) {
-    CPP_CHECK_CUDA(cudaMemsetAsync(gmax, 0, sizeof(float), s));
-    if (n > 0) {
-      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, ceil_div(n, 256 * 8)));
-      absmax_kernel<<<blocks, 256, 0, s>>>(d_pooled, n, gmax);
-      CPP_CHECK_LAUNCH();
-    }
-  }
+  if (!gmax_ready) CPP_TRY(launch_absmax(d_pooled, (int64_t)B * (H / 2) * (W / 2) * CO, gmax, s));
   const int64_t items = (int64_t)B * H * W * 3;
   unpool_split_kernel<<<(unsigned)ceil_div(items, 256), 256, 0, s>>>(d_pooled, amax, B, H, W, gmax, inv_scale,
                                                                     reinterpret_cast<uint4*>(dy_pieces));

@@ -83,6 +83,13 @@ int launch_conv_fwd_tc(const void* x_f16, const int32_t* rows, const float* mean
 // dx fp32 [B][H][W][10].
 int launch_conv_dgrad_tc(const void* dy_pieces, const float* inv_scale, const float* w, int B, int H, int W, int KS, float* dx,
                          void* scratch, cudaStream_t s, float* out_absmax = nullptr, int phase = kPhaseBoth);
+// the same input gradient with the un-pool / split pass fused into the row-sweep kernel's producer warps (conv_row_tc.cu): no piece
+// tensor is written.  gmax: device float, receives max|d_pooled| here unless gmax_ready; inv_scale (optional) receives 1 / scale
+bool conv_dgrad_fused_supported(int H, int W, int KS);
+int launch_absmax(const float* g, int64_t n, float* gmax, cudaStream_t s);      // *gmax = max |g[i]| (zeroed here)
+int launch_conv_dgrad_tc_fused(const float* d_pooled, const uint8_t* amax, float* gmax, float* inv_scale, int gmax_ready, const float* w,
+                               int B, int H, int W, int KS, float* dx, void* scratch, cudaStream_t s, float* out_absmax = nullptr,
+                               int phase = kPhaseBoth);
 // un-pool + split: d_pooled fp32 [B][H/2][W/2][10] and the arg-max side band -> dy_pieces fp16 [B][H][W][24], scaled by
 // a power of two from max|d_pooled| (gmax: device float, zeroed and filled here); inv_scale receives 1/scale
 // gmax_ready: *gmax already holds max|d_pooled| (left there by the kernel that produced d_pooled)

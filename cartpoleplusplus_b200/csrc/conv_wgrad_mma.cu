@@ -23,6 +23,7 @@
 #include <algorithm>
 #include "conv_wgrad_mma.cuh"
 #include "conv_wgrad_tc.cuh"
+#include "conv_wgrad_row_tc.cuh"
 
 namespace cpp {
 namespace wg {
@@ -538,7 +539,8 @@ int64_t conv_wgrad_mma_scratch_bytes(int nets, int H, int W, int C, int KS, int 
   if (build_plan(nets, 1, H, W, C, KS, &P, dup) != CPP_OK) return -1;
   const int64_t own = (int64_t)(al256(16) + al256((size_t)2 * kNumSMs * P.part_floats * 4) + al256((size_t)P.part_floats * 4));
   const int64_t tcb = (dup == 0 || dup == 2) ? (int64_t)al256(16) + wgtc::scratch_bytes(nets, H, W, C, KS, dup == 2) : 0;     // the tcgen05 route shares the scratch
-  return std::max(own, tcb);
+  const int64_t rowb = dup == 2 ? (int64_t)al256(16) + wgr::scratch_bytes(H, W, KS) : 0;      // ... and the row-sweep route
+  return std::max(std::max(own, tcb), rowb);
 }
 
 template <int MT, int NT>
@@ -589,6 +591,9 @@ int launch_conv_wgrad_mma(const void* x_f16, const float* mean_inv, int dup, int
     wgrad_absmax_kernel<<<dim3(blocks, nets), 256, 0, s>>>(P);
     CPP_CHECK_LAUNCH();
   }
+  // row-sweep tcgen05 route (conv_wgrad_row_tc.cu, wgrad_tc bit 2): conv2 / conv3 on the 24-channel pieces, one network
+  if (dup == 2 && nets == 1 && (g_wgrad_tc & 4) && wgr::shape_ok(H, W, KS))
+    return wgr::launch(x_f16, d_pooled[0], amax[0], P.gmax[0], B, H, W, KS, dw[0], db[0], reinterpret_cast<char*>(scratch) + al256(16), s);
   // tcgen05 route (conv_wgrad_tc.cu): conv1 of c3-class inputs (wgrad_tc bit 0), conv2 / conv3 on the 24-channel pieces (bit 1)
   if ((dup == 0 && (g_wgrad_tc & 1) && wgtc::supported(nets, H, W, C, KS, 0)) || (dup == 2 && (g_wgrad_tc & 2) && wgtc::supported(nets, H, W, C, KS, 1)))
     return wgtc::launch(x_f16, mean_inv, nets, d_pooled, amax, B, H, W, C, KS, dw, db, P.gmax, reinterpret_cast<char*>(scratch) + al256(16), s,

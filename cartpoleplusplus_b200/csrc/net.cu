@@ -443,12 +443,26 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     // tensor-core route for conv3/conv2: the un-pool + split pass also yields max|gp|, shared by wgrad and dgrad
     const bool tc_dg = i > 0 && tc_scratch != nullptr && tc_route(is_f16);
     float* gsc = reinterpret_cast<float*>(ws + L.gsc) + 2 * i;
-    if (tc_dg) {
-      // i == 1: conv3's input-gradient kernel has already left max|gp| in gsc[0] (its epilogue), no separate max pass
+    // i == 1: conv3's input-gradient kernel has already left max|gp| in gsc[0] (its epilogue), no separate max pass - and the
+    // weight gradient (side stream) can start before the un-pool / split pass instead of behind it
+    const bool early_wgrad = tc_dg && i == 1;
+    // fused: the row-sweep kernel builds its input strips from gp + arg-max itself (conv_row_tc.cu) - no un-pool / split launch, no
+    // piece tensor; conv3's max|gp| then needs its own small pass (conv2's comes from conv3's input-gradient epilogue)
+    const bool fused_dg = tc_dg && tc::conv_dgrad_fused_supported(conv[i].H, conv[i].W, conv[i].KS);
+    auto unpool = [&]() -> int {
+      if (fused_dg) {
+        if (i != 1) {
+          CPP_TRY(tc::launch_absmax(gp, (int64_t)B * conv[i].PH() * conv[i].PW() * kConvCout, gsc, s));
+          trace_mark("   . conv3 max|g|", s);
+        }
+        return CPP_OK;
+      }
       CPP_TRY(tc::launch_unpool_split(gp, amax, B, conv[i].H, conv[i].W, gsc, gsc + 1, reinterpret_cast<__half*>(ws + L.dyp), s,
                                       i == 1 ? 1 : 0));
       trace_mark(i == 2 ? "   . conv3 un-pool/split" : "   . conv2 un-pool/split", s);
-    }
+      return CPP_OK;
+    };
+    if (tc_dg && !early_wgrad) CPP_TRY(unpool());
     CPP_TRY(ready());                                      // gp (and its max) are complete on the main stream
     const int cap_saved = g_cta_cap;
     if (fork && aux->cta_cap > 0) g_cta_cap = aux->cta_cap;
@@ -466,9 +480,15 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     }
     g_cta_cap = cap_saved;
     trace_mark(i == 2 ? "   . conv3 wgrad (side)" : (i == 1 ? "   . conv2 wgrad (side)" : "   . conv1 wgrad"), sw);
+    if (early_wgrad) CPP_TRY(unpool());
     if (i > 0) {
       float* dx = reinterpret_cast<float*>(ws + L.dpool[2 - i]);   // i=2 -> dpool[0] (pooled2 grad), i=1 -> dpool[1]
-      if (tc_dg) {
+      if (fused_dg) {
+        CPP_TRY(tc::launch_conv_dgrad_tc_fused(gp, amax, gsc, gsc + 1, 1, params + off_conv_w[i], B, conv[i].H, conv[i].W, conv[i].KS, dx,
+                                               reinterpret_cast<char*>(tc_scratch) + (i == 2 ? 3 : 4) * trunk_slot_bytes(*this), s,
+                                               reinterpret_cast<float*>(ws + L.gsc) + (i == 1 ? 6 : 2),
+                                               g_tc_prepped ? tc::kPhaseMain : tc::kPhaseBoth));
+      } else if (tc_dg) {
         CPP_TRY(tc::launch_conv_dgrad_tc(reinterpret_cast<__half*>(ws + L.dyp), gsc + 1, params + off_conv_w[i], B, conv[i].H, conv[i].W,
                                          conv[i].KS, dx, reinterpret_cast<char*>(tc_scratch) + (i == 2 ? 3 : 4) * trunk_slot_bytes(*this), s,
                                          // max|dx| for the next consumer: conv1's wgrad (i == 1), conv2's un-pool/split (i == 2)

@@ -39,6 +39,8 @@ def kernel_table(only=None, reps=10, rm=None):
   lib = L.lib()
   if os.environ.get("CONV_ROW") is not None:     # A/B of the conv2 / conv3 route: 1 row-sweep kernel (default), 0 parity-plane kernel
     L.check(lib.cpp_set_option(b"conv_row", int(os.environ["CONV_ROW"])))
+  if os.environ.get("WGRAD_TC") is not None:     # conv weight-gradient routes: bit 0 conv1 tcgen05, bit 1 conv2/3 tcgen05 (old), bit 2 conv2/3 row-sweep
+    L.check(lib.cpp_set_option(b"wgrad_tc", int(os.environ["WGRAD_TC"])))
   dev = "cuda"
   g = torch.Generator(device=dev); g.manual_seed(0)
   rs = np.random.RandomState(0)

@@ -13,13 +13,18 @@ NAMES = ["prologue", "mma total", "mma waits FULL_A (producer-bound)", "mma wait
          "producer waits EMPTY_A (mma-bound)", "producer waits copies", "epi total", "epi waits ACC_FULL (mma-bound)", "kernel", "rows", "tiles"]
 
 
+WNAMES = ["prologue", "mma total", "mma waits DFULL (dY producers)", "mma waits XFULL (TMA)", "mma waits ACC_EMPTY (epilogue)",
+          "dY group 0 total", "dY group 0 waits DONE (mma-bound)", "epi total", "epi waits ACC_FULL", "kernel", "steps", "X steps"]
+
+
 def main():
   which = sys.argv[1:] or ["conv2_fwd_tc"]
   from cartpoleplusplus_b200 import _lib as L
   import torch
   lib = L.lib()
-  fn = lib.cpp_debug_conv_row_prof
   for name in which:
+    wg = "wgrad" in name                       # -DWGROW_PROF build, WGRAD_TC=5
+    fn = lib.cpp_debug_wgrad_row_prof if wg else lib.cpp_debug_conv_row_prof
     import scripts.bench_kernels as bk
     sys.argv = ["bench_kernels.py", "--only", name, "--reps", "3"]
     bk.main()
@@ -29,7 +34,7 @@ def main():
     a = np.frombuffer(buf, dtype=np.uint64).reshape(160, 12).astype(np.float64)
     a = a[a[:, 9] > 0]
     print("== %s (CONV_ROW=%s): %d CTAs" % (name, os.environ.get("CONV_ROW", "default"), a.shape[0]))
-    for i, n in enumerate(NAMES):
+    for i, n in enumerate(WNAMES if wg else NAMES):
       print("  %-42s mean %9.0f   min %9.0f   max %9.0f" % (n, a[:, i].mean(), a[:, i].min(), a[:, i].max()))
 
 

@@ -166,7 +166,7 @@ def run_tc_pieces(B, H, W, KS, seed):
 
 
 def _with_route(row, fn):
-  """row = 1: the row-sweep kernel (conv_row_tc.cu, ky taps along N; TMA tensor-map strips) where it covers the shape, 3: the same with cp.async strips;
+  """row = 1: the row-sweep kernel (conv_row_tc.cu, ky taps along N; TMA tensor-map strips) where it covers the shape (input gradient: fused un-pool producer), 3: the same with cp.async strips, 5: input gradient from a piece tensor;
   row = 0: the parity-plane kernel (conv_tc.cu) everywhere"""
   L, lib = _lib()
   L.check(lib.cpp_set_option(b"conv_row", row))
@@ -176,7 +176,7 @@ def _with_route(row, fn):
     L.check(lib.cpp_set_option(b"conv_row", 1))
 
 
-@pytest.mark.parametrize("row", [1, 3, 0])
+@pytest.mark.parametrize("row", [1, 3, 5, 0])
 @pytest.mark.parametrize("B,H,W,KS", [(8, 32, 32, 5), (8, 16, 16, 3), (2, 64, 64, 5), (4, 32, 32, 3), (3, 25, 25, 5), (3, 12, 12, 3),
                                       (256, 32, 32, 5), (256, 16, 16, 3), (1, 32, 32, 5), (7, 16, 16, 3), (5, 32, 48, 5), (3, 48, 32, 3),
                                       (2, 124, 64, 5), (2, 16, 124, 5), (130, 2, 2, 3), (9, 6, 4, 5)])
@@ -218,7 +218,7 @@ def run_dgrad_tc(B, H, W, KS, seed):
   return e
 
 
-@pytest.mark.parametrize("row", [1, 3, 0])
+@pytest.mark.parametrize("row", [1, 3, 5, 0])
 @pytest.mark.parametrize("B,H,W,KS", [(8, 32, 32, 5), (8, 16, 16, 3), (2, 64, 64, 5), (3, 25, 25, 5), (3, 12, 13, 3), (256, 32, 32, 5),
                                       (256, 16, 16, 3), (1, 4, 4, 3), (5, 32, 48, 5), (2, 124, 64, 5), (130, 2, 2, 3)])
 def test_conv_dgrad_tc(B, H, W, KS, row):

@@ -247,7 +247,23 @@ def test_conv_wgrad_mma(B, H, W, Cin, KS, nets, pieces):
     L.check(lib.cpp_set_option(b"wgrad_tc", 3))
     print("wgrad_mma (dw, db) rel err vs fp64:", run_wgrad_mma(B, H, W, Cin, KS, nets, seed=B + H + Cin + nets, pieces=pieces))
   finally:
-    L.check(lib.cpp_set_option(b"wgrad_tc", 1))
+    L.check(lib.cpp_set_option(b"wgrad_tc", 5))
+
+
+WGRAD_ROW = [(8, 32, 32, 5), (8, 16, 16, 3), (256, 32, 32, 5), (256, 16, 16, 3), (40, 64, 64, 5), (9, 48, 32, 3), (1, 32, 32, 5), (7, 16, 16, 3),
+             (5, 32, 48, 5), (2, 16, 124, 5), (130, 2, 2, 3), (9, 6, 4, 5), (300, 8, 8, 3)]
+
+
+@pytest.mark.parametrize("B,H,W,KS", WGRAD_ROW, ids=["%dx%dx%d_k%d" % w for w in WGRAD_ROW])
+def test_conv_wgrad_row(B, H, W, KS):
+  """wgrad_tc bit 2: the row-sweep tcgen05 weight gradient of conv2 / conv3 (conv_wgrad_row_tc.cu - TMA tensor-map strips as the B
+  operand, un-pooled gradient windows built on the fly as the A operand) on the 24-channel piece layout"""
+  L, lib = _lib()
+  try:
+    L.check(lib.cpp_set_option(b"wgrad_tc", 5))
+    print("wgrad_row (dw, db) rel err vs fp64:", run_wgrad_mma(B, H, W, 10, KS, 1, seed=B + H + KS, pieces=2))
+  finally:
+    L.check(lib.cpp_set_option(b"wgrad_tc", 5))
 
 
 def test_conv_wgrad_route_switch():
@@ -258,7 +274,7 @@ def test_conv_wgrad_route_switch():
     print("wgrad mma.sync route c3 shape:", run_wgrad_mma(8, 64, 64, 9, 5, 2, seed=21))
     print("wgrad mma.sync route conv2 pieces:", run_wgrad_mma(8, 32, 32, 10, 5, 1, seed=22, pieces=2))
   finally:
-    L.check(lib.cpp_set_option(b"wgrad_tc", 1))
+    L.check(lib.cpp_set_option(b"wgrad_tc", 5))
   print("wgrad tcgen05 route c3 shape:", run_wgrad_mma(8, 64, 64, 9, 5, 2, seed=21))
 
 
