@@ -243,11 +243,16 @@ int DDPG::step_body(const void* s1, const float* action, const float* reward, co
   enum { E_PREP = 8, E_PREP2 = 9 };
   if (multi && g_prep_hoist && actor.pixels && actor.tc_route(is_f16)) {
     CPP_TRY(wait(sc, E_START)); CPP_TRY(wait(stc, E_START));
-    CPP_TRY(actor.prep_trunk_tc(P, B, tcs[0], true, sc));
-    CPP_TRY(critic.prep_trunk_tc(P + off_c, B, tcs[1], true, stc));
-    CPP_TRY(actor.prep_trunk_tc(T, B, tcs[2], false, sc));
-    CPP_TRY(critic.prep_trunk_tc(T + off_c, B, tcs[3], false, stc));
-    CPP_TRY(record(E_PREP, sc)); CPP_TRY(record(E_PREP2, stc));
+    // row-sweep route (conv_row_tc.cu): the twelve packs are collected and written by ONE kernel on sc; passes the route does not
+    // cover launch their own prep kernels as before
+    tcr::prep_batch_begin();
+    int prc = actor.prep_trunk_tc(P, B, tcs[0], true, sc);
+    if (prc == CPP_OK) prc = critic.prep_trunk_tc(P + off_c, B, tcs[1], true, stc);
+    if (prc == CPP_OK) prc = actor.prep_trunk_tc(T, B, tcs[2], false, sc);
+    if (prc == CPP_OK) prc = critic.prep_trunk_tc(T + off_c, B, tcs[3], false, stc);
+    const int frc = tcr::prep_batch_flush(sc);
+    CPP_TRY(prc); CPP_TRY(frc);
+    CPP_TRY(record(E_PREP, sc)); CPP_TRY(wait(stc, E_PREP)); CPP_TRY(record(E_PREP2, stc));
     g_tc_prepped = 1;
   }
   cudaStream_t sx = g_conv1_split ? sta : s0;                    // stream of the conv1 pass over state_2

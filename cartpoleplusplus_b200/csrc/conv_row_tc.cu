@@ -121,6 +121,62 @@ __global__ void __launch_bounds__(256) conv_row_prep_kernel(const __grid_constan
   if (blockIdx.x == 0 && tid < CO) A.tab[tid] = A.bias ? A.bias[tid] : 0.f;
 }
 
+// (kx, channel group) of K8 half h of step i; g = -1: the zero-weight half in front of the odd tap left over (build_plan)
+__host__ __device__ inline void step_half(int KS, int i, int h, int* kx, int* g) {
+  if (i < KS) { *kx = i; *g = h; return; }
+  const int k0 = 2 * (i - KS);
+  if (k0 + 1 < KS) { *kx = k0 + h; *g = 2; }
+  else if (h == 0) { *kx = k0 - 1; *g = -1; }
+  else { *kx = k0; *g = 2; }
+}
+
+// The weight packs of MANY layer passes in one launch (blockIdx.y = job): the fused steps prepare every conv2 / conv3 forward and
+// input-gradient pass of a step at t = 0 (Net::prep_trunk_tc under tcr::prep_batch_begin / prep_batch_flush).
+constexpr int kMaxPrepJobs = 16;
+struct PrepJob { const float* w; const float* bias; __half* bpack; float* tab; int KS, dgrad; };
+struct PrepBatch { int n; PrepJob job[kMaxPrepJobs]; };
+
+__global__ void __launch_bounds__(256) conv_row_prep_batch_kernel(const __grid_constant__ PrepBatch Bt) {
+  __shared__ float red[256];
+  __shared__ float s_scale;
+  const PrepJob& J = Bt.job[blockIdx.y];
+  const int tid = threadIdx.x, KS = J.KS, nw = KS * KS * CO * CO;
+  float mx = 0.f;
+  for (int i = tid; i < nw; i += blockDim.x) mx = fmaxf(mx, fabsf(J.w[i]));
+  red[tid] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]); __syncthreads(); }
+  if (tid == 0) {
+    int e = 0;
+    const float m = red[0];
+    if (m > 0.f && isfinite(m)) frexpf(m, &e); else e = 15;
+    s_scale = ldexpf(1.f, 15 - e);
+    if (blockIdx.x == 0) J.tab[CO] = ldexpf(1.f, e - 15);
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  const int N = KS * kSlotCols, n_steps = KS == 5 ? 8 : 5, total = n_steps * 2 * N * 8;
+  for (int idx = blockIdx.x * blockDim.x + tid; idx < total; idx += gridDim.x * blockDim.x) {
+    const int e = idx & 7, n = (idx >> 3) % N, h = ((idx >> 3) / N) & 1, i = (idx >> 3) / (2 * N);
+    int kx, g;
+    step_half(KS, i, h, &kx, &g);
+    const int t = n / kSlotCols, j = n % kSlotCols;
+    __half out = __float2half_rn(0.f);
+    if (g >= 0 && j < 2 * CO) {
+      const int piece = j / CO, o = j % CO, ky = KS - 1 - t, chw = c24_weight_channel(8 * g + e);
+      if (chw >= 0) {
+        const float wv = J.dgrad ? J.w[(((KS - 1 - ky) * KS + (KS - 1 - kx)) * CO + o) * CO + chw]
+                                 : J.w[((ky * KS + kx) * CO + chw) * CO + o];
+        const float v = wv * scale;
+        const __half hi = __float2half_rn(v);
+        out = piece == 0 ? hi : __float2half_rn(v - __half2float(hi));
+      }
+    }
+    J.bpack[idx] = out;
+  }
+  if (blockIdx.x == 0 && tid < CO) J.tab[tid] = J.bias ? J.bias[tid] : 0.f;
+}
+
 // Pipeline diagnosis build (nvcc -DCONV_ROW_PROF, scripts/prof_conv_row.py): cycles per CTA.  Slots: 0 prologue, 1 MMA total,
 // 2 MMA waits FULL_A, 3 MMA waits ACC_FREE, 4 producer total, 5 producer waits EMPTY_A, 6 producer waits copies, 7 epilogue
 // total (group 0 quarter 0), 8 epilogue waits ACC_FULL, 9 whole kernel, 10 rows, 11 tiles
@@ -564,6 +620,18 @@ static int g_conv_row = 1;      // bit 0: route on; bit 1: input strips by 16-by
 void set_conv_row(int on) { g_conv_row = on & 7; }
 int conv_row_enabled() { return g_conv_row; }
 
+static bool g_batching = false;
+static PrepBatch g_batch;
+void prep_batch_begin() { g_batching = true; g_batch.n = 0; }
+int prep_batch_flush(cudaStream_t s) {
+  g_batching = false;
+  if (g_batch.n == 0) return CPP_OK;
+  conv_row_prep_batch_kernel<<<dim3(8, g_batch.n), 256, 0, s>>>(g_batch);
+  CPP_CHECK_LAUNCH();
+  g_batch.n = 0;
+  return CPP_OK;
+}
+
 bool shape_ok(int H, int W, int KS) {
   return (KS == 5 || KS == 3) && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && W + KS - 1 <= 128;
 }
@@ -580,16 +648,16 @@ static int build_plan(int B, int H, int W, int KS, int dgrad, RowPlan* P) {
   P->N = KS * kSlotCols;
   P->plane_bytes = (int)round_up((int64_t)(128 + KS) * 16, 128);
   P->stage_bytes = 3 * P->plane_bytes;
-  // K8 halves: (kx, channel group); a step pairs two of them with the second at the higher shared-memory address
-  int ns = 0;
-  for (int kx = 0; kx < KS; ++kx) { P->kx[ns][0] = (int8_t)kx; P->g[ns][0] = 0; P->kx[ns][1] = (int8_t)kx; P->g[ns][1] = 1; ++ns; }
-  for (int kx = 0; kx < KS; kx += 2) {
-    if (kx + 1 < KS) { P->kx[ns][0] = (int8_t)kx; P->g[ns][0] = 2; P->kx[ns][1] = (int8_t)(kx + 1); P->g[ns][1] = 2; }
-    // the odd tap left over: a zero-weight half (g = -1) in FRONT of it that re-reads the previous tap's entries - every entry a
-    // valid lane reads must be one the TMA unit wrote (0 x an uninitialised NaN pattern would poison the lane)
-    else { P->kx[ns][0] = (int8_t)(kx - 1); P->g[ns][0] = -1; P->kx[ns][1] = (int8_t)kx; P->g[ns][1] = 2; }
-    ++ns;
-  }
+  // K8 halves: (kx, channel group); a step pairs two of them with the second at the higher shared-memory address.  The odd tap left
+  // over gets a zero-weight half (g = -1) in FRONT of it that re-reads the previous tap's entries - every entry a valid lane reads
+  // must be one the TMA unit wrote (0 x an uninitialised NaN pattern would poison the lane)
+  const int ns = KS + (KS + 1) / 2;
+  for (int i = 0; i < ns && i < kMaxSteps; ++i)
+    for (int h = 0; h < 2; ++h) {
+      int kx, g;
+      step_half(KS, i, h, &kx, &g);
+      P->kx[i][h] = (int8_t)kx; P->g[i][h] = (int8_t)g;
+    }
   CPP_REQUIRE(ns <= kMaxSteps, "conv_row: %d K steps", ns);
   P->n_steps = ns;
   for (int i = 0; i < ns; ++i) {
@@ -633,6 +701,10 @@ int launch(const void* x_pieces, const float* w, const float* bias, int B, int H
   P.tab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(scratch) + bpack_bytes(P));
   if (phase != tc::kPhaseMain) {
     CPP_REQUIRE(w != nullptr, "conv_row: null weights");
+    if (g_batching && phase == tc::kPhasePrep && g_batch.n < kMaxPrepJobs) {
+      g_batch.job[g_batch.n++] = PrepJob{w, bias, const_cast<__half*>(P.bpack), const_cast<float*>(P.tab), KS, dgrad};
+      return CPP_OK;
+    }
     PrepArgs A{w, bias, const_cast<__half*>(P.bpack), const_cast<float*>(P.tab)};
     conv_row_prep_kernel<<<32, 256, 0, s>>>(P, A);
     CPP_CHECK_LAUNCH();

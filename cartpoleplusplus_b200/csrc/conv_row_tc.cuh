@@ -12,6 +12,9 @@ bool shape_ok(int H, int W, int KS);  // even H, W; W + KS - 1 <= 128
 bool supported(int H, int W, int KS); // shape_ok and enabled
 bool fused_unpool(int H, int W, int KS);   // supported, and the input gradient builds its strips from d(pooled) + arg-max itself
 int64_t scratch_bytes(int H, int W, int KS);
+// between begin and flush every launch(..., kPhasePrep) is collected; flush packs the weights of all of them in ONE kernel on `s`
+void prep_batch_begin();
+int prep_batch_flush(cudaStream_t s);
 int piece_overflow_count(int reset, unsigned int* out);
 // dgrad = 0: out = pooled fp32 [B][H/2][W/2][10], amax, optional out_hl (piece copy); y = maxpool2x2(relu(conv_same(x, w) + bias))
 // dgrad = 1: out = dense fp32 [B][H][W][10] = conv_same(x, flip(w)^T) * *out_scale; optional max|out| into *out_absmax (atomic max)
