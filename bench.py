@@ -371,8 +371,8 @@ def run_native(args):
                 step_achieved=step_tf, step_frac=step_tf / peaks["bf16_tflops"], step_frac_of_sustained=step_tf / peaks["bf16_tflops_sustained"],
                 step_algorithmic_gflop_per_gpu=step_flops / 1e9,
                 step_note="algorithmic FLOPs of the minimum necessary graph (SURVEY.md Appendix B) / measured step time; the convs "
-                          "issue 2.7x (conv1: N 20 of 48 columns, K 225 of 256) to 7.7x (conv2: fp16 hi+lo pieces of activations AND "
-                          "weights) more MMA work than that to stay within 1e-5 of fp32")
+                          "issue 2.7x (conv1: N 20 of 48 columns, K 225 of 256) to ~11x (conv2: fp16 hi+lo pieces of activations AND "
+                          "weights, 20 of 32 columns per tap row, 96 of 128 lanes) more MMA work than that to stay within 1e-5 of fp32")
     if args.config == "c3":
       from scripts.bench_kernels import kernel_table
       rows = kernel_table(rm=rm)

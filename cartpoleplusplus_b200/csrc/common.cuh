@@ -95,6 +95,8 @@ struct GemmArgs {
   int epi; const float* bias; int act;      // EPI_BIAS_ACT
   const float* aux; int aux_ld; int mask_cols;   // EPI_RELU_MASK: C[m][n] *= (aux[m][n] > 0) for n < mask_cols
   float mask_scale;                         // EPI_RELU_MASK: factor of the open positions (0 reads as 1; 2 behind a dropout layer: d(2 m relu(z)))
+  float* absmax;                            // FFMA route, optional: max |C[m][n]| is atomically max-ed into this device float (the caller zeroes
+                                            // it; callers that set it must check !gemm_tc_wanted first)
   float* colsum;                            // tensor-core route, transA only: also out[n] = sum_k B[k][n] (an all-ones row appended to A);
                                             // the FFMA route ignores it (callers check gemm_tc_wanted and launch colsum themselves)
 };

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(128) gemm_kernel(GemmArgs g) {
     __syncthreads();
   }
 
+  float amx = 0.f;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int m = m0 + 2 * tm + i;
@@ -95,7 +96,13 @@ __global__ void __launch_bounds__(128) gemm_kernel(GemmArgs g) {
         if (n < g.mask_cols) v = (g.aux[(size_t)m * g.aux_ld + n] > 0.f) ? (g.mask_scale != 0.f ? v * g.mask_scale : v) : 0.f;
       }
       g.C[(size_t)m * g.ldc + n] = v;
+      amx = fmaxf(amx, fabsf(v));
     }
+  }
+  if (g.absmax != nullptr) {                                       // max is order independent: an atomic keeps the result deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+    if ((tid & 31) == 0 && amx > 0.f) atomicMax(reinterpret_cast<int*>(g.absmax), __float_as_int(amx));
   }
 }
 

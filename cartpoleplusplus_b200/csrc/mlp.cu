@@ -32,6 +32,8 @@ struct MlpArgs {
   float* dTop;                      // [B][out(end-1)] gradient wrt its pre-activation (kept for the weight gradient)
   float* d_action;                  // [B][action_dim] or NULL
   int need_dx_first;                // 1: also produce dX of layer `first`
+  float* absmax_first;              // optional: max |dX of layer `first`| is atomically max-ed into this device float (zeroed by the caller):
+                                    // the power-of-two scale of conv3's input / weight gradient pieces without a pass of its own
   int maxw;
 };
 
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
   const int nrow = min(kRows, A.B - row0);
   const int last = A.end - 1;
   const int lowest = A.need_dx_first ? A.first : A.first + 1;      // lowest layer whose input gradient is produced
+  float amx = 0.f;
   if (last >= lowest) {
     const MlpLayer& L0 = A.L[last];
     const bool vec4 = ((reinterpret_cast<uintptr_t>(L0.W) & 15) == 0) && (L0.out % 4 == 0);
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
           db[k * kRows + r] = v;
           if (r < nrow) {
             Ly.dX[(size_t)(row0 + r) * K + k] = v;
+            if (l == A.first) amx = fmaxf(amx, fabsf(v));
             if (Ly.action_in && A.d_action && k >= K - A.action_dim) A.d_action[(size_t)(row0 + r) * A.action_dim + (k - (K - A.action_dim))] = v;
           }
         }
@@ -269,6 +273,11 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
       for (int t = 0; t < kStages - 1; ++t) issue_tile(Ln.W, Ln.in, Ln.out, KTn, t, wt + t * kTileFloats, tid, v4);
     }
     float* tsw = da; da = db; db = tsw;
+  }
+  if (A.absmax_first != nullptr) {                                 // max is order independent: an atomic keeps the result deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+    if (lane == 0 && amx > 0.f) atomicMax(reinterpret_cast<int*>(A.absmax_first), __float_as_int(amx));
   }
 }
 
@@ -332,13 +341,14 @@ int launch_mlp_forward(const Net& net, const float* params, const float* action,
 
 // gradients wrt the inputs of layers last .. stop_at (dTop and every dX[i] land in the workspace); d_action optional
 int launch_mlp_dgrad(const Net& net, const float* params, int B, void* ws_, const float* d_out, int stop_at, int need_dx_first,
-                     float* d_action, cudaStream_t s) {
+                     float* d_action, cudaStream_t s, float* absmax_first) {
   char* ws = reinterpret_cast<char*>(ws_);
   const Net::Layout L = net.layout(B);
   MlpArgs A{};
   fill_layers(net, params, ws, L, &A);
   A.first = stop_at; A.end = net.n_fc; A.B = B;
   A.d_out = d_out; A.dTop = reinterpret_cast<float*>(ws + L.dTop); A.d_action = d_action; A.need_dx_first = need_dx_first;
+  A.absmax_first = need_dx_first ? absmax_first : nullptr;
   const size_t smem = (size_t)2 * A.maxw * kRows * sizeof(float) + (size_t)kStages * kTileFloats * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {

@@ -337,12 +337,19 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
   };
   CPP_REQUIRE(d_rep_extra == nullptr || (grads != nullptr && concat_at < 0), "d_rep_extra needs a full backward pass of a network without action input");
   const bool dropping = any_drop && g_is_training;
+  float* gmax3 = nullptr;                                 // set when the fused FC input-gradient kernel has left max |gp| of conv3
   const bool fused = fused_mlp_level() >= 2 && mlp_fits(*this) && d_rep_extra == nullptr && !dropping;
   const int stop_at_f = (grads == nullptr) ? concat_at : 0;
   if (fused) {
     // one launch for the whole chain of input gradients; every weight / bias gradient afterwards (side stream if given)
     const bool need_first = (stop_at_f == 0 && pixels && grads != nullptr) || (concat_at == stop_at_f && d_action != nullptr);
-    CPP_TRY(launch_mlp_dgrad(*this, params, B, ws, d_out, stop_at_f, need_first ? 1 : 0, d_action, s));
+    // tensor-core route: the kernel also leaves max |d(flattened conv3 output)| for conv3's gradient pieces (no max pass later)
+    if (stop_at_f == 0 && need_first && pixels && !bn && tc_scratch != nullptr && tc_route(is_f16) &&
+        tc::conv_dgrad_fused_supported(conv[2].H, conv[2].W, conv[2].KS)) {
+      gmax3 = reinterpret_cast<float*>(ws + L.gsc) + 4;
+      CPP_CHECK_CUDA(cudaMemsetAsync(gmax3, 0, sizeof(float), s));
+    }
+    CPP_TRY(launch_mlp_dgrad(*this, params, B, ws, d_out, stop_at_f, need_first ? 1 : 0, d_action, s, gmax3));
     if (grads != nullptr) {
       CPP_TRY(ready());
       for (int i = last; i >= 0; --i) {
@@ -400,6 +407,13 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     const float gate_scale = (i > 0 && dropping && drop[i - 1]) ? 2.f : 1.f;
     if (i > 0) { g.epi = EPI_RELU_MASK; g.aux = x; g.aux_ld = xld; g.mask_cols = out_dim[i - 1]; g.mask_scale = gate_scale; }
     else g.epi = EPI_NONE;
+    // tensor-core route: the layer-0 input gradient is conv3's gp - its GEMM also leaves max |gp| (no max pass before conv3's kernels)
+    if (i == 0 && pixels && !bn && grads != nullptr && d_rep_extra == nullptr && tc_scratch != nullptr && tc_route(is_f16) &&
+        tc::conv_dgrad_fused_supported(conv[2].H, conv[2].W, conv[2].KS) && !gemm_tc_wanted(g)) {
+      gmax3 = reinterpret_cast<float*>(ws + L.gsc) + 4;
+      CPP_CHECK_CUDA(cudaMemsetAsync(gmax3, 0, sizeof(float), s));
+      g.absmax = gmax3;
+    }
     CPP_TRY(launch_gemm(g, s));
     if (i == last && d_rep_extra != nullptr)
       CPP_TRY(launch_add_gated(dnext, in_dim[i], d_rep_extra, i > 0 ? x : nullptr, xld, B, in_dim[i], s, gate_scale));
@@ -451,7 +465,7 @@ int Net::backward(const float* params, const void* state, int is_f16, const floa
     const bool fused_dg = tc_dg && tc::conv_dgrad_fused_supported(conv[i].H, conv[i].W, conv[i].KS);
     auto unpool = [&]() -> int {
       if (fused_dg) {
-        if (i != 1) {
+        if (i != 1 && gmax3 == nullptr) {
           CPP_TRY(tc::launch_absmax(gp, (int64_t)B * conv[i].PH() * conv[i].PW() * kConvCout, gsc, s));
           trace_mark("   . conv3 max|g|", s);
         }

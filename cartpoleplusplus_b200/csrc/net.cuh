@@ -111,7 +111,7 @@ bool mlp_fits(const Net& net);
 int launch_mlp_forward(const Net& net, const float* params, const float* action, int B, void* ws, float* out, cudaStream_t s,
                        int first_fc, int end_fc);
 int launch_mlp_dgrad(const Net& net, const float* params, int B, void* ws, const float* d_out, int stop_at, int need_dx_first,
-                     float* d_action, cudaStream_t s);
+                     float* d_action, cudaStream_t s, float* absmax_first = nullptr);
 
 // critic tail (mlp.cu): [hidden2, action] -> hidden3 -> q of the pixel critic in one launch per evaluation / per backward
 bool critic_tail_ok(const Net& net);

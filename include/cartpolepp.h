@@ -56,8 +56,14 @@ int64_t cpp_piece_overflow_count(int32_t reset);
  * "conv1_split" = 1 (default) runs the two conv1 passes side by side on half of the SMs each, "critic_tail" = 1 (default) evaluates
  * the pixel critic's [hidden2, action] -> hidden3 -> q head (incl. dQ/da) as one kernel, "bwd_critic_sms" (default 74) and
  * "fwd_actor_sms" (default 37) set the SM budgets of the critic's backward and the actor's forward chain;
- * "wgrad_tc" = mask (default 1) of the conv weight gradients that take the tcgen05 kernel (conv_wgrad_tc.cu) where the layer
- * shape allows: 1 conv1 on raw pixels, 2 conv2 / conv3 on the fp16 piece layout; 0: always the mma.sync kernel; "wgrad_flush_steps" (default 32) = tensor-core K-steps between two fp32 flushes of the
+ * "wgrad_tc" = mask (default 5) of the conv weight gradients that run on tcgen05 where the layer shape allows: 1 conv1 on raw
+ * pixels (conv_wgrad_tc.cu), 4 conv2 / conv3 on the fp16 piece layout through the row-sweep kernel (conv_wgrad_row_tc.cu: TMA
+ * tensor-map strips, dY windows built on the fly), 2 conv2 / conv3 through the older piece mode of conv_wgrad_tc.cu; 0: always the
+ * mma.sync kernel; "conv_row" = mask (default 1) for the conv2 / conv3 forward and input-gradient passes: 1 the row-sweep tcgen05
+ * kernel (conv_row_tc.cu: ky taps along N into a ring of TMEM slots, input strips by TMA tensor-map boxes), + 2 strips by 16-byte
+ * cp.async instead of TMA, + 4 input gradient from a piece tensor written by a separate un-pool / split pass instead of the fused
+ * producer warps; 0: the parity-plane kernel of conv_tc.cu everywhere (it also takes the shapes the row-sweep kernel does not
+ * cover: odd sizes, rows wider than 124 pixels); "wgrad_flush_steps" (default 32) = tensor-core K-steps between two fp32 flushes of the
  * weight-gradient accumulators; "fc_tc" = mask of the fully connected passes that run on tcgen05 (fc_tc.cu): 1 forward,
  * 2 input gradient, 4 weight gradient (with the bias gradient folded in), + 8 to include GEMMs below 64 M MACs (default 0: measured
  * slower than the FFMA kernels at the BASELINE sizes, profiles/r4/fc_tc.md; CARTPOLEPP_FC_TC sets the start-up value).

@@ -145,12 +145,12 @@ def kernel_table(only=None, reps=10, rm=None):
   kernels = [
       ("conv1_fwd_tc", conv1_fwd_tc, 2.0 * mac1, 2, "conv1 5x5 9->10 fwd, 2 sibling nets in one pass, incl. weight prep"),
       ("conv1_wgrad_mma", conv1_wgrad_mma, 2.0 * mac1, 1, "conv1 weight gradient, actor+critic (tcgen05, csrc/conv_wgrad_tc.cu), incl. absmax/reduce/finalize"),
-      ("conv2_fwd_tc", c2[0], 2.0 * mac2, 4, "conv2 5x5 10->10 fwd, one network, incl. weight prep"),
-      ("conv2_dgrad_tc", c2[1], 2.0 * mac2, 2, "conv2 input gradient, incl. un-pool/split + prep"),
-      ("conv2_wgrad_mma", c2[2], 2.0 * mac2, 2, "conv2 weight gradient, one network"),
-      ("conv3_fwd_tc", c3[0], 2.0 * mac3, 4, "conv3 3x3 10->10 fwd"),
-      ("conv3_dgrad_tc", c3[1], 2.0 * mac3, 2, "conv3 input gradient"),
-      ("conv3_wgrad_mma", c3[2], 2.0 * mac3, 2, "conv3 weight gradient"),
+      ("conv2_fwd_tc", c2[0], 2.0 * mac2, 4, "conv2 5x5 10->10 fwd, one network, row-sweep tcgen05 kernel (csrc/conv_row_tc.cu, TMA tensor-map strips), incl. weight prep"),
+      ("conv2_dgrad_tc", c2[1], 2.0 * mac2, 2, "conv2 input gradient (row-sweep kernel, un-pool / split fused into its producer warps), incl. max|g| pass + weight prep"),
+      ("conv2_wgrad_mma", c2[2], 2.0 * mac2, 2, "conv2 weight gradient, one network (row-sweep tcgen05, csrc/conv_wgrad_row_tc.cu), incl. max|g| pass + finalize"),
+      ("conv3_fwd_tc", c3[0], 2.0 * mac3, 4, "conv3 3x3 10->10 fwd (row-sweep kernel), incl. weight prep"),
+      ("conv3_dgrad_tc", c3[1], 2.0 * mac3, 2, "conv3 input gradient (row-sweep kernel, fused un-pool), incl. max|g| pass + weight prep"),
+      ("conv3_wgrad_mma", c3[2], 2.0 * mac3, 2, "conv3 weight gradient (row-sweep tcgen05), incl. max|g| pass + finalize"),
       ("fc_actor_fwd", fa[0], 2.0 * B * fa[2], 2, "actor FC stack 640-100-100-50-2 forward (actor, target actor)"),
       ("fc_actor_bwd", fa[1], 4.0 * B * fa[2], 1, "actor FC stack backward: input gradients + weight / bias gradients"),
       ("fc_critic_fwd", fcr[0], 2.0 * B * fcr[2], 2, "critic FC stack 640-200-50(+2)-50-1 forward (critic, target critic)"),
