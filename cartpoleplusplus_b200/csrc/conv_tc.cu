@@ -587,8 +587,8 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_fwd_tc_kernel(const __grid_
         PROF_WAIT(pf_w1, mbar_wait(&bars[BAR_EMPTY_ACC + ab], ((tc >> 1) & 1) ^ 1)); // the epilogue drained these accumulators
         tc_fence_after();
         const uint32_t a_add = pl16 + (uint32_t)(128 * t - py_first * Pq);
-        // K step outermost, the four pool positions (independent accumulators) innermost: back-to-back MMAs into the SAME
-        // accumulator serialise on its read-modify-write latency (scripts/micro/umma_rate.cu: nacc = 1 vs 4)
+        // K step outermost, the four pool positions (independent accumulators) innermost.  (Round 5 measured that consecutive MMAs
+        // into the SAME accumulator run at the full rate too - profiles/umma_rate_nacc_r5.txt - so the order is a matter of taste.)
         for (int i = 0; i < P.n_pairs; ++i) {
           const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(i * 2 * N));
 #pragma unroll

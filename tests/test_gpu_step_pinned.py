@@ -123,6 +123,24 @@ def test_naf_backward_graph_replay_vs_oracle_with_pinned_routing(share):
   U.assert_all_within(rep, "NAF c4 shard share=%s" % share)
 
 
+@pytest.mark.parametrize("conv_row,wgrad_tc", [(0, 1), (5, 5), (1, 3), (3, 0)],
+                         ids=["round4_kernels", "separate_unpool", "piece_mode_wgrad", "cp_async_strips_mma_sync_wgrad"])
+def test_ddpg_whole_step_on_the_alternative_conv_routes(conv_row, wgrad_tc):
+  """The routes the row-sweep kernels replaced stay selectable (`conv_row`, `wgrad_tc`: include/cartpolepp.h) and take the shapes
+  those kernels do not cover; inside the fused, graph-replayed c3 step each combination has to hold the same 1e-5 bound against
+  the fp64 oracle with the routing pinned."""
+  lib = _lib.lib()
+  try:
+    _lib.check(lib.cpp_set_option(b"conv_row", conv_row))
+    _lib.check(lib.cpp_set_option(b"wgrad_tc", wgrad_tc))
+    report, rep = run_ddpg_pinned((64, 64, 3, 1, 3), 64, seed=85)
+    print("conv_row=%d wgrad_tc=%d whole step:" % (conv_row, wgrad_tc), json.dumps(report))
+    U.assert_all_within(rep, "DDPG c3 shape, conv_row=%d wgrad_tc=%d" % (conv_row, wgrad_tc))
+  finally:
+    _lib.check(lib.cpp_set_option(b"conv_row", 1))
+    _lib.check(lib.cpp_set_option(b"wgrad_tc", 5))
+
+
 @pytest.mark.parametrize("fused_mlp", [0, 1], ids=["per_layer_forward", "fused_forward"])
 def test_fc_on_tensor_cores_whole_step(fused_mlp):
   """cpp_set_option("fc_tc", 15): every fully connected GEMM with M >= 64 rows - forward (when the stacks run per layer),
