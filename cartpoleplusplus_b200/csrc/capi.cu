@@ -18,7 +18,8 @@ int g_cta_cap = 148;
 int g_tc_prepped = 0;
 int g_conv1_split = 1;     // the two conv1 passes of the DDPG step side by side on half of the SMs each (1) or one after the other on all (0)
 int g_fwd_actor_sms = 37;  // SM budget of the actor's forward chain (mu is needed first); the other three chains share the rest
-int g_bwd_critic_sms = 74; // SM budget of the critic's backward chain in the fused DDPG step (the actor's gets the rest of the 148)
+int g_bwd_critic_sms = 92; // SM budget of the critic's backward chain in the fused DDPG step (the actor's gets the rest of the 148); round 5
+                           // A/B (profiles/r5/ab_r5s.txt): 74: 0.459, 88-96: 0.4495, 104: 0.454, 120: 0.486 ms - the critic's chain starts later (TD target)
 int g_critic_tail = 1;     // the pixel critic's [hidden2, action] -> hidden3 -> q head as one kernel per evaluation / backward (mlp.cu)
 int g_is_training = 1;
 int g_dropout_seed = 1, g_dropout_external = 0;

@@ -395,20 +395,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
 #endif
 }
 
-// gsum[i] = sum over CTAs of partials[cta][i] in fixed order; block (32, 8)
+// gsum[i] = sum over CTAs of partials[cta][i] in fixed order; block (32, 8), four consecutive floats per thread (part_floats is a
+// multiple of 128, the buffers are 256-byte aligned): a warp reads 512 contiguous bytes of every partial
 __global__ void __launch_bounds__(256) wgtc_reduce_kernel(const float* __restrict__ partials, int nparts, int part_floats, float* __restrict__ gsum) {
-  __shared__ float sh[8][33];
-  const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
+  __shared__ float4 sh[8][33];
+  const int i = (blockIdx.x * 32 + threadIdx.x) * 4, y = threadIdx.y;
   const int per = (nparts + 7) / 8, k0 = y * per, k1 = min(nparts, k0 + per);
-  float s = 0.f;
-  if (i < part_floats) for (int k = k0; k < k1; ++k) s += partials[(size_t)k * part_floats + i];
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < part_floats)
+    for (int k = k0; k < k1; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(partials + (size_t)k * part_floats + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   sh[y][threadIdx.x] = s;
   __syncthreads();
   if (y == 0 && i < part_floats) {
-    float t = 0.f;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += sh[r][threadIdx.x];
-    gsum[i] = t;
+    for (int r = 0; r < 8; ++r) { const float4 v = sh[r][threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    *reinterpret_cast<float4*>(gsum + i) = t;
   }
 }
 
@@ -530,7 +535,7 @@ int launch(const void* x_f16, const float* mean_inv, int nets, const float* cons
   }
   conv_wgrad_tc_kernel<<<P.grid, kThreads, P.smem_bytes, s>>>(P);
   CPP_CHECK_LAUNCH();
-  wgtc_reduce_kernel<<<(unsigned)ceil_div(P.part_floats, 32), dim3(32, 8), 0, s>>>(P.partials, P.grid, P.part_floats, P.gsum);
+  wgtc_reduce_kernel<<<(unsigned)ceil_div(P.part_floats, 128), dim3(32, 8), 0, s>>>(P.partials, P.grid, P.part_floats, P.gsum);
   CPP_CHECK_LAUNCH();
   const int Cr = pieces ? CO : C;
   const int total = nets * (KS * KS * Cr * CO + CO);

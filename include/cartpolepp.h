@@ -54,7 +54,7 @@ int64_t cpp_piece_overflow_count(int32_t reset);
  * input-gradient chain); schedule of the fused DDPG step, all for A/B timing, results are unchanged up to summation order:
  * "prep_hoist" = 1 (default) runs the conv2/conv3 weight-prep kernels of the whole step at its start on idle streams,
  * "conv1_split" = 1 (default) runs the two conv1 passes side by side on half of the SMs each, "critic_tail" = 1 (default) evaluates
- * the pixel critic's [hidden2, action] -> hidden3 -> q head (incl. dQ/da) as one kernel, "bwd_critic_sms" (default 74) and
+ * the pixel critic's [hidden2, action] -> hidden3 -> q head (incl. dQ/da) as one kernel, "bwd_critic_sms" (default 92) and
  * "fwd_actor_sms" (default 37) set the SM budgets of the critic's backward and the actor's forward chain;
  * "wgrad_tc" = mask (default 5) of the conv weight gradients that run on tcgen05 where the layer shape allows: 1 conv1 on raw
  * pixels (conv_wgrad_tc.cu), 4 conv2 / conv3 on the fp16 piece layout through the row-sweep kernel (conv_wgrad_row_tc.cu: TMA

@@ -399,7 +399,7 @@ def test_ddpg_schedule_switches_do_not_change_results():
   P, batch = _oracle_ddpg(shape, True, B, 22)
   values = {k: v.numpy() for k, v in P.items()}
   dev_batch = U.Batch(*[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in batch])
-  defaults = dict(prep_hoist=1, conv1_split=1, critic_tail=1, bwd_critic_sms=74, fwd_actor_sms=37)
+  defaults = dict(prep_hoist=1, conv1_split=1, critic_tail=1, bwd_critic_sms=92, fwd_actor_sms=37)
   variants = [dict(), dict(prep_hoist=0), dict(conv1_split=0), dict(critic_tail=0), dict(bwd_critic_sms=100, fwd_actor_sms=60),
               dict(prep_hoist=0, conv1_split=0, critic_tail=0)]
   outs = []
