@@ -720,7 +720,8 @@ int launch(const void* x_pieces, const float* w, const float* bias, int B, int H
   }
   P.out = out; P.amax = amax; P.out_hl = out_hl; P.out_scale = out_scale; P.out_absmax = out_absmax;
   P.x = reinterpret_cast<const __half*>(x_pieces);
-  P.use_tma = ((g_conv_row & 2) || P.unpool) ? 0 : 1;
+  // (a driver without cuTensorMapEncodeTiled: the cp.async producer carries the strips - same results)
+  P.use_tma = ((g_conv_row & 2) || P.unpool || encode_fn() == nullptr) ? 0 : 1;
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   if (P.use_tma) {

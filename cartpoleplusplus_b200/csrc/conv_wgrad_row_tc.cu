@@ -362,7 +362,11 @@ __global__ void __launch_bounds__(256) wgrad_row_finalize_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn();
 bool shape_ok(int H, int W, int KS) {
+  if (encode_fn() == nullptr) return false;      // the strips come in through TMA tensor maps only: without the driver entry point the mma.sync kernel takes the layer
   return (KS == 5 || KS == 3) && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && W + KS - 1 <= 128;
 }
 
@@ -395,8 +399,6 @@ int64_t scratch_bytes(int H, int W, int KS) {
   return (int64_t)round_up((int64_t)kNumSMs * 3 * kNCols * 128 * 4, 256);
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = [] {
     void* p = nullptr;

@@ -42,6 +42,20 @@ def test_error_reporting_is_c_abi_clean():
   lib.cpp_mt_destroy(h)
 
 
+def test_runtime_switches_are_known_and_unknown_names_are_rejected():
+  """cpp_set_option (include/cartpolepp.h): every documented switch is accepted without a GPU (they only select routes for later
+  launches), defaults are restored, an unknown name is an error with a message - not a silent no-op"""
+  lib = _lib.lib()
+  header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cartpolepp.h")).read()
+  defaults = {"conv1_tc": -1, "fused_mlp": -1, "prep_hoist": 1, "conv1_split": 1, "critic_tail": 1, "bwd_critic_sms": 92, "fwd_actor_sms": 37,
+              "wgrad_tc": 5, "conv_row": 1, "wgrad_flush_steps": 32, "fc_tc": 0, "is_training": 1, "dropout_external": 0}
+  for name, value in defaults.items():
+    assert '"%s"' % name in header, "switch %s is not documented in the header" % name
+    _lib.check(lib.cpp_set_option(name.encode(), value))
+  st = lib.cpp_set_option(b"no_such_switch", 1)
+  assert st != 0 and b"no_such_switch" in lib.cpp_last_error()
+
+
 def _randint(lib, h, high, n):
   out = np.empty(n, dtype=np.int64)
   _lib.check(lib.cpp_mt_randint(h, C.c_int64(high), C.c_int64(n), out.ctypes.data_as(C.c_void_p)))
