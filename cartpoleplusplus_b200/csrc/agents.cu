@@ -550,6 +550,22 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
     CPP_TRY(value.forward_fc(buf.target_params, nullptr, B, ws_t, V2, st));
     CPP_TRY(record(E_V2, st));
   }
+  // ---- weight packs of every conv2 / conv3 pass of the three online networks (forward + input gradient: twelve) in ONE launch on the
+  // mu stream, which idles until conv1 is done (row-sweep route; passes it does not cover keep their own prep kernels)
+  struct PrepGuard { ~PrepGuard() { g_tc_prepped = 0; } } prep_guard;
+  enum { E_PREP = 8 };
+  bool hoisted = false;
+  if (multi && !share && g_prep_hoist && value.pixels && value.tc_route(is_f16)) {
+    CPP_TRY(wait(sm, E_START));
+    tcr::prep_batch_begin();
+    int prc = value.prep_trunk_tc(P, B, tcs[0], true, sm);
+    if (prc == CPP_OK) prc = mu.prep_trunk_tc(P + off_m, B, tcs[1], true, sm);
+    if (prc == CPP_OK) prc = l.prep_trunk_tc(P + off_l, B, tcs[2], true, sm);
+    const int frc = tcr::prep_batch_flush(sm);
+    CPP_TRY(prc); CPP_TRY(frc);
+    CPP_TRY(record(E_PREP, sm));
+    hoisted = true;
+  }
   // ---- conv1 of the three networks on state_1 in one pass
   if (multi) g_cta_cap = kNumSMs - kNumSMs / 4;
   CPP_TRY(stats_for(s1, is_f16, B, mi1, pinned1, &m1, s0));
@@ -584,6 +600,7 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
   CPP_TRY(conv1_forward_group(3, g3, pp3, ws3, s1, is_f16, m1, B, tcs[0], s0, &tc1));
   CPP_TRY(record(E_C1, s0));
   CPP_TRY(wait(sm, E_C1)); CPP_TRY(wait(sl, E_C1));
+  if (hoisted) { CPP_TRY(wait(s0, E_PREP)); CPP_TRY(wait(sl, E_PREP)); g_tc_prepped = 1; }
   // ---- three forward chains
   if (multi) g_cta_cap = kNumSMs / 4;
   CPP_TRY(value.forward_trunk(P, s1, is_f16, m1, B, ws_v, s0, tc1, tc1 ? tcs[0] : nullptr));
@@ -666,7 +683,7 @@ int NAF::backward(const void* s1, const float* action, const float* reward, cons
   if (multi || graphs) CPP_TRY(ensure_streams());
   if (!graphs) return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, comm.key()};
-  const int ikey[5] = {is_f16, B, B_global, (multi ? 1 : 0) | (g_fc_tc << 1) | (g_wgrad_tc << 5) | (tcr::conv_row_enabled() << 8), (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | ((g_wgrad_flush_steps / 16) << 24)};
+  const int ikey[5] = {is_f16, B, B_global, (multi ? 1 : 0) | (g_fc_tc << 1) | (g_wgrad_tc << 5) | (tcr::conv_row_enabled() << 8), (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | ((g_wgrad_flush_steps / 16) << 24)};
   return run_graphed(graph, key, ikey, s, cap_stream, [&](cudaStream_t x) {
     return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, x);
   });
