@@ -509,6 +509,11 @@ NAF::~NAF() {
   if (streams_ready) {
     for (auto& st : side) if (st) cudaStreamDestroy(st);
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    for (auto& a : aux) {
+      if (a.stream) cudaStreamDestroy(a.stream);
+      for (auto& e : a.ready) if (e) cudaEventDestroy(e);
+      if (a.done) cudaEventDestroy(a.done);
+    }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
 }
@@ -517,6 +522,11 @@ int NAF::ensure_streams() {
   if (streams_ready) return CPP_OK;
   for (auto& st : side) CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  for (auto& a : aux) {
+    CPP_CHECK_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    for (auto& e : a.ready) CPP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CPP_CHECK_CUDA(cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming));
+  }
   for (auto& e : ev) CPP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   streams_ready = true;
   return CPP_OK;
@@ -618,13 +628,16 @@ int NAF::backward_body(const void* s1, const float* action, const float* reward,
   CPP_TRY(record(E_HEAD, s0));
   CPP_TRY(wait(sm, E_HEAD)); CPP_TRY(wait(sl, E_HEAD));
   // ---- three backward chains (conv1 weight gradients deferred)
+  // (every weight / bias gradient on a side stream per chain, as in the DDPG step: the chains of input gradients stay short)
   if (multi) g_cta_cap = kNumSMs / 3;
-  CPP_TRY(value.backward(P, s1, is_f16, m1, B, ws_v, dV, buf.grads, nullptr, s0, 1, wgs[0], tcs[0]));
-  CPP_TRY(mu.backward(P + off_m, s1, is_f16, m1, B, ws_m, dmu, buf.grads + off_m, nullptr, sm, 1, wgs[1], tcs[1]));
+  for (auto& a : aux) { a.used = false; a.cta_cap = kNumSMs / 3; }
+  CPP_TRY(value.backward(P, s1, is_f16, m1, B, ws_v, dV, buf.grads, nullptr, s0, 1, wgs[0], tcs[0], multi ? &aux[0] : nullptr));
+  CPP_TRY(mu.backward(P + off_m, s1, is_f16, m1, B, ws_m, dmu, buf.grads + off_m, nullptr, sm, 1, wgs[1], tcs[1], multi ? &aux[1] : nullptr));
   CPP_TRY(record(E_BM, sm));
-  CPP_TRY(l.backward(P + off_l, s1, is_f16, m1, B, ws_l, dl, buf.grads + off_l, nullptr, sl, 1, wgs[2], tcs[2]));
+  CPP_TRY(l.backward(P + off_l, s1, is_f16, m1, B, ws_l, dl, buf.grads + off_l, nullptr, sl, 1, wgs[2], tcs[2], multi ? &aux[2] : nullptr));
   CPP_TRY(record(E_BL, sl));
   CPP_TRY(wait(s0, E_BM)); CPP_TRY(wait(s0, E_BL));
+  if (multi) for (auto& a : aux) if (a.used) CPP_CHECK_CUDA(cudaStreamWaitEvent(s0, a.done, 0));     // join the weight-gradient side streams
   g_cta_cap = kNumSMs;
   {
     float* gr[3] = {buf.grads, buf.grads + off_m, buf.grads + off_l};

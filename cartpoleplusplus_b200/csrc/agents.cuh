@@ -179,6 +179,7 @@ struct NAF {
   bool streams_ready = false;
   void* tcs[4] = {nullptr, nullptr, nullptr, nullptr};    // packed-weight scratch per chain (value, mu, l, target value)
   void* wgs[3] = {nullptr, nullptr, nullptr};
+  BackwardAux aux[3];                                     // side streams of the value / mu / l backward chains (weight gradients)
   double* mom_scratch2 = nullptr;
   GraphCache graph;
 };
