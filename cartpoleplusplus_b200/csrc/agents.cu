@@ -363,7 +363,7 @@ int DDPG::step(const void* s1, const float* action, const float* reward, const f
   if (multi || use_graphs()) CPP_TRY(ensure_streams());
   if (!use_graphs()) return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, comm.key()};
-  const int ikey[5] = {is_f16, B, B_global, (multi ? 1 : 0) | (g_fc_tc << 1) | (g_wgrad_tc << 5) | (tcr::conv_row_enabled() << 8), (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | (g_conv1_split << 5) | (g_critic_tail << 6) | (g_bwd_critic_sms << 8) | (g_fwd_actor_sms << 16) | ((g_wgrad_flush_steps / 16) << 24)};
+  const int ikey[5] = {is_f16, B, B_global, (multi ? 1 : 0) | (g_fc_tc << 1) | (g_wgrad_tc << 5) | (tcr::conv_row_enabled() << 8) | (g_mlp_fast << 11), (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | (g_conv1_split << 5) | (g_critic_tail << 6) | (g_bwd_critic_sms << 8) | (g_fwd_actor_sms << 16) | ((g_wgrad_flush_steps / 16) << 24)};
   const int rc = run_graphed(graph[with_apply ? 1 : 0], key, ikey, s, cap_stream, [&](cudaStream_t st) {
     return step_body(s1, action, reward, mask, s2, is_f16, B, B_global, with_apply, multi, st);
   });
@@ -696,7 +696,7 @@ int NAF::backward(const void* s1, const float* action, const float* reward, cons
   if (multi || graphs) CPP_TRY(ensure_streams());
   if (!graphs) return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, s);
   const void* const key[8] = {s1, action, reward, mask, s2, pinned1, pinned2, comm.key()};
-  const int ikey[5] = {is_f16, B, B_global, (multi ? 1 : 0) | (g_fc_tc << 1) | (g_wgrad_tc << 5) | (tcr::conv_row_enabled() << 8), (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | ((g_wgrad_flush_steps / 16) << 24)};
+  const int ikey[5] = {is_f16, B, B_global, (multi ? 1 : 0) | (g_fc_tc << 1) | (g_wgrad_tc << 5) | (tcr::conv_row_enabled() << 8) | (g_mlp_fast << 11), (conv1_tc_enabled() ? 1 : 0) | (fused_mlp_level() << 1) | (g_prep_hoist << 4) | ((g_wgrad_flush_steps / 16) << 24)};
   return run_graphed(graph, key, ikey, s, cap_stream, [&](cudaStream_t x) {
     return backward_body(s1, action, reward, mask, s2, is_f16, B, B_global, multi, x);
   });

@@ -31,6 +31,7 @@ extern int g_fwd_actor_sms;
 extern int g_conv1_split;
 extern int g_wgrad_flush_steps;   // mma.sync weight gradient: MMA K-steps accumulated on the tensor cores between two fp32 flushes
 extern int g_wgrad_tc;            // conv weight gradients on tcgen05 (conv_wgrad_tc.cu) where supported: bit 0 conv1 on raw pixels, bit 1 conv2 / conv3 on pieces; 0: always mma.sync
+extern int g_mlp_fast;         // mlp_forward_kernel variants (mlp.cu): bit 0 register-tiled inner loop, bit 1 bulk-copy weight tiles
 extern int g_fc_tc;               // FC passes on tcgen05 (fc_tc.cu): 1 forward, 2 input gradient, 4 weight gradient, 8 = also GEMMs below the size where it pays
 extern int g_is_training;         // base_network.py:11 IS_TRAINING: batch statistics (1) or moving statistics (0) in slim.batch_norm; dropout on / off
 extern int g_dropout_seed, g_dropout_external;   // cpp_set_option: mask generator seed; 1 = masks are supplied by the caller (tests)

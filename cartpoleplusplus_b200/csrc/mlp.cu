@@ -6,6 +6,7 @@
 // both writing every intermediate (activations h_i, gradients dPre_i) to the workspace, because the weight gradients
 // (x^T . dPre, the plain GEMM of fc.cu on a side stream) need them.  Exact fp32 FFMA with a fixed summation order.
 #include "net.cuh"
+#include "umma.cuh"
 
 namespace cpp {
 
@@ -31,6 +32,8 @@ struct MlpArgs {
   const float* d_out;               // [B][out(end-1)] gradient wrt the post-activation output of layer end-1
   float* dTop;                      // [B][out(end-1)] gradient wrt its pre-activation (kept for the weight gradient)
   float* d_action;                  // [B][action_dim] or NULL
+  int tiled;                        // forward: register-tiled inner loop (4 columns x 8 rows per thread) - CARTPOLEPP_MLP_TILED
+  int bulk;                         // forward: weight tiles by bulk copies (TMA engine) instead of per-thread cp.async - CARTPOLEPP_MLP_BULK
   int need_dx_first;                // 1: also produce dX of layer `first`
   float* absmax_first;              // optional: max |dX of layer `first`| is atomically max-ed into this device float (zeroed by the caller):
                                     // the power-of-two scale of conv3's input / weight gradient pieces without a pass of its own
@@ -71,23 +74,67 @@ __device__ __forceinline__ void issue_tile(const float* __restrict__ W, int K, i
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// The same tile as ONE bulk copy (TMA engine, cp.async.bulk global -> shared, mbarrier completion) issued by thread 0: a CTA's
+// 256 threads x 16-byte cp.async keep only ~11 bytes / clk in flight from L2 (3 k clk per 32 KB tile whatever the FMA loop costs,
+// scripts/prof_mlp.py); the bulk engine moves the tile without occupying load/store slots.  Needs 16-byte sizes and addresses.
+__device__ __forceinline__ bool bulk_ok(const float* W, int K, int N) {
+  return ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((((K & 3) * N) & 3) == 0);
+}
+__device__ __forceinline__ void issue_tile_bulk(const float* __restrict__ W, int K, int N, int KT, int t, float* dst, uint64_t* bar, int tid) {
+  const int k0 = t * KT;
+  if (tid == 0 && k0 < K) {
+    const uint32_t bytes = (uint32_t)(min(KT, K - k0) * N) * 4u;
+    umma::fence_proxy_async();                                    // the stage was read through the generic proxy before
+    umma::mbar_expect_tx(bar, bytes);
+    umma::bulk_g2s(dst, W + (size_t)k0 * N, bytes, bar);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ forward
 // shared: xa / xb [maxw][kRows] (k-major so that one k is two float4 loads for all 8 rows), red [kMlpThreads][kRows],
 // wt [kStages][kTileFloats]
+#ifdef MLP_PROF
+__device__ long long g_mlp_prof[64][8];
+extern "C" __attribute__((visibility("default"))) int cpp_debug_mlp_prof(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_mlp_prof, sizeof(long long) * 64 * 8);
+}
+#define MLP_STAMP(i) { if (threadIdx.x == 0 && blockIdx.x < 64) g_mlp_prof[blockIdx.x][i] = clock64(); }
+#else
+#define MLP_STAMP(i)
+#endif
 __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_constant__ MlpArgs A) {
   extern __shared__ __align__(16) float sm[];
+  MLP_STAMP(0)
   float* xa = sm;
   float* xb = sm + (size_t)A.maxw * kRows;
   float* red = xb + (size_t)A.maxw * kRows;
   float* wt = red + (size_t)kMlpThreads * kRows;
   const int tid = threadIdx.x, row0 = blockIdx.x * kRows;
   const int nrow = min(kRows, A.B - row0);
+  __shared__ uint64_t wbar[kStages];                             // bulk route: one mbarrier per weight stage
+  uint32_t wphase = 0;                                           // bit s: parity the next wait on stage s expects
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) umma::mbar_init(&wbar[i], 1);
+    umma::fence_mbar_init();
+  }
+  __syncthreads();
+  // tile t of a layer -> stage t % kStages, by bulk copy when the layer allows it, else by per-thread cp.async
+  auto issue = [&](const float* W, int K, int N, int KT, int t, bool bulk, bool v4) {
+    float* dst = wt + (t % kStages) * kTileFloats;
+    if (bulk) { issue_tile_bulk(W, K, N, KT, t, dst, &wbar[t % kStages], tid); asm volatile("cp.async.commit_group;" ::: "memory"); }
+    else issue_tile(W, K, N, KT, t, dst, tid, v4);
+  };
+  auto wait_tile = [&](int t, bool bulk) {
+    if (bulk) { const int st = t % kStages; umma::mbar_wait(&wbar[st], (wphase >> st) & 1u); wphase ^= 1u << st; }
+    else asm volatile("cp.async.wait_group 2;" ::: "memory");
+  };
   // start streaming the first layer's weights, then fetch its input (coalesced along k) and its action columns
   {
     const MlpLayer& L0 = A.L[A.first];
     const bool vec4 = ((reinterpret_cast<uintptr_t>(L0.W) & 15) == 0) && (L0.out % 4 == 0);
     const int KT = tile_rows(L0.in, L0.out);
-    for (int t = 0; t < kStages - 1; ++t) issue_tile(L0.W, L0.in, L0.out, KT, t, wt + t * kTileFloats, tid, vec4);
+    const bool bulk0 = A.bulk && bulk_ok(L0.W, L0.in, L0.out);
+    for (int t = 0; t < kStages - 1; ++t) issue(L0.W, L0.in, L0.out, KT, t, bulk0, vec4);
   }
   for (int k = tid; k < A.x_cols; k += kMlpThreads) {
     float v[kRows];
@@ -104,62 +151,149 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
       if (r < nrow && A.x_tail) A.x_tail[(size_t)(row0 + r) * A.x_ld + j] = v;
     }
   }
+  MLP_STAMP(1)
   for (int l = A.first; l < A.end; ++l) {
+    MLP_STAMP(2 + (l - A.first))
     const MlpLayer& Ly = A.L[l];
     const int N = Ly.out, K = Ly.in;
     const bool vec4 = ((reinterpret_cast<uintptr_t>(Ly.W) & 15) == 0) && (N % 4 == 0);
     const int KT = tile_rows(K, N), ntiles = (K + KT - 1) / KT;
-    const int npad = (N + 31) & ~31;
-    const int ks = max(1, min(8, kMlpThreads / npad));          // K slices: threads beyond one column set split the reduction
-    const int slice = tid / npad, n = tid - slice * npad;
-    const bool active = slice < ks && n < N;
-    float acc[kRows];
+    const bool bulk = A.bulk && bulk_ok(Ly.W, K, N);
+    const bool more = l + 1 < A.end;
+    const int ngrp = (N + 3) >> 2;
+    if (ngrp <= 64 && A.tiled && K >= 256) {
+      // Register-tiled: a thread owns 4 output columns (and 4 more, 128 columns further, when N > 128) x the 8 rows; the 8 K
+      // slices of a column group sit in ONE warp (lane = slice * 4 + group), so the reduction over them is three shuffles.  Per k:
+      // two 16-byte x loads + one 16-byte w load for 32 FMAs (the one-column mapping below needs 3 loads for 8).
+      const int warp = tid >> 5, lane = tid & 31, slice = lane >> 2;
+      const int c0 = 4 * (warp * 4 + (lane & 3)), c1 = c0 + 128;
+      const bool a0 = c0 < N, a1 = c1 < N;
+      float acc0[4][kRows], acc1[4][kRows];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
-    for (int t = 0; t < ntiles; ++t) {
-      asm volatile("cp.async.wait_group 2;" ::: "memory");        // tile t has landed (kStages - 2 younger groups may be in flight)
-      __syncthreads();                                           // ... for every thread; the stage of tile t-1 is free again; xa is complete
-      issue_tile(Ly.W, K, N, KT, t + kStages - 1, wt + ((t + kStages - 1) % kStages) * kTileFloats, tid, vec4);
-      if (active) {
-        const float* w = wt + (t % kStages) * kTileFloats + n;
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) { acc0[c][r] = 0.f; acc1[c][r] = 0.f; }
+      auto load4 = [&](const float* p, int avail) -> float4 {     // 4 weights of one k; columns past N read as 0
+        if (vec4) return *reinterpret_cast<const float4*>(p);
+        return make_float4(p[0], avail > 1 ? p[1] : 0.f, avail > 2 ? p[2] : 0.f, avail > 3 ? p[3] : 0.f);
+      };
+      for (int t = 0; t < ntiles; ++t) {
+        wait_tile(t, bulk);                                       // tile t has landed (kStages - 2 younger tiles may be in flight)
+        __syncthreads();                                         // ... for every thread; the stage of tile t-1 is free again; xa is complete
+        issue(Ly.W, K, N, KT, t + kStages - 1, bulk, vec4);
+        const float* wtile = wt + (t % kStages) * kTileFloats;
         const int k0 = t * KT, rows = min(KT, K - k0);
-#pragma unroll 4
-        for (int kk = slice; kk < rows; kk += ks) {
-          const float wv = w[kk * N];
-          const float* xp = xa + (k0 + kk) * kRows;
-          const float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
-          acc[0] = fmaf(x0.x, wv, acc[0]); acc[1] = fmaf(x0.y, wv, acc[1]); acc[2] = fmaf(x0.z, wv, acc[2]); acc[3] = fmaf(x0.w, wv, acc[3]);
-          acc[4] = fmaf(x1.x, wv, acc[4]); acc[5] = fmaf(x1.y, wv, acc[5]); acc[6] = fmaf(x1.z, wv, acc[6]); acc[7] = fmaf(x1.w, wv, acc[7]);
+        if (a0) {
+#pragma unroll 2
+          for (int kk = slice; kk < rows; kk += 8) {
+            const float* xp = xa + (k0 + kk) * kRows;
+            const float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
+            const float xv[kRows] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            const float4 w0 = load4(wtile + kk * N + c0, N - c0);
+            const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int r = 0; r < kRows; ++r) acc0[c][r] = fmaf(xv[r], wv[c], acc0[c][r]);
+            if (a1) {
+              const float4 w1 = load4(wtile + kk * N + c1, N - c1);
+              const float wu[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) acc1[c][r] = fmaf(xv[r], wu[c], acc1[c][r]);
+            }
+          }
         }
       }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                                             // all weight stages idle: the next layer may start streaming
-    const bool more = l + 1 < A.end;
-    if (more) {
-      const MlpLayer& Ln = A.L[l + 1];
-      const bool v4 = ((reinterpret_cast<uintptr_t>(Ln.W) & 15) == 0) && (Ln.out % 4 == 0);
-      const int KTn = tile_rows(Ln.in, Ln.out);
-      for (int t = 0; t < kStages - 1; ++t) issue_tile(Ln.W, Ln.in, Ln.out, KTn, t, wt + t * kTileFloats, tid, v4);
-    }
-    if (ks > 1) {                                                // fixed-order reduction over the K slices
-      if (slice > 0 && active) {
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) red[(size_t)tid * kRows + r] = acc[r];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                                           // all weight stages idle: the next layer may start streaming
+      if (more) {
+        const MlpLayer& Ln = A.L[l + 1];
+        const bool v4 = ((reinterpret_cast<uintptr_t>(Ln.W) & 15) == 0) && (Ln.out % 4 == 0);
+        const int KTn = tile_rows(Ln.in, Ln.out);
+        { const bool bn = A.bulk && bulk_ok(Ln.W, Ln.in, Ln.out); for (int t = 0; t < kStages - 1; ++t) issue(Ln.W, Ln.in, Ln.out, KTn, t, bn, v4); }
       }
-      __syncthreads();
-      if (slice == 0 && n < N)
-        for (int s2 = 1; s2 < ks; ++s2)
+      // fixed-order butterfly over the 8 K slices: afterwards every lane holds the sums; lane `slice` finishes row r = slice
 #pragma unroll
-          for (int r = 0; r < kRows; ++r) acc[r] += red[(size_t)(s2 * npad + n) * kRows + r];
-    }
-    if (slice == 0 && n < N) {
-      const float bv = Ly.b[n];
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        const float v = act_fwd(acc[r] + bv, Ly.act);
-        if (more) xb[n * kRows + r] = v;
-        if (r < nrow) Ly.h[(size_t)(row0 + r) * Ly.h_ld + n] = v;
+        for (int r = 0; r < kRows; ++r) {
+          float v = acc0[c][r];
+          v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+          acc0[c][r] = v;
+          float u = acc1[c][r];
+          u += __shfl_xor_sync(0xffffffffu, u, 4); u += __shfl_xor_sync(0xffffffffu, u, 8); u += __shfl_xor_sync(0xffffffffu, u, 16);
+          acc1[c][r] = u;
+        }
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        const int cb = blk ? c1 : c0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int n = cb + c;
+          if (n < N) {
+            float sum = 0.f;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) if (r == slice) sum = blk ? acc1[c][r] : acc0[c][r];
+            const float v = act_fwd(sum + Ly.b[n], Ly.act);
+            if (more) xb[n * kRows + slice] = v;
+            if (slice < nrow) Ly.h[(size_t)(row0 + slice) * Ly.h_ld + n] = v;
+          }
+        }
+      }
+    } else {
+      const int npad = (N + 31) & ~31;
+      const int ks = max(1, min(8, kMlpThreads / npad));          // K slices: threads beyond one column set split the reduction
+      const int slice = tid / npad, n = tid - slice * npad;
+      const bool active = slice < ks && n < N;
+      float acc[kRows];
+  #pragma unroll
+      for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+      for (int t = 0; t < ntiles; ++t) {
+        wait_tile(t, bulk);                                         // tile t has landed (kStages - 2 younger tiles may be in flight)
+        __syncthreads();                                           // ... for every thread; the stage of tile t-1 is free again; xa is complete
+        issue(Ly.W, K, N, KT, t + kStages - 1, bulk, vec4);
+        if (active) {
+          const float* w = wt + (t % kStages) * kTileFloats + n;
+          const int k0 = t * KT, rows = min(KT, K - k0);
+  #pragma unroll 4
+          for (int kk = slice; kk < rows; kk += ks) {
+            const float wv = w[kk * N];
+            const float* xp = xa + (k0 + kk) * kRows;
+            const float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
+            acc[0] = fmaf(x0.x, wv, acc[0]); acc[1] = fmaf(x0.y, wv, acc[1]); acc[2] = fmaf(x0.z, wv, acc[2]); acc[3] = fmaf(x0.w, wv, acc[3]);
+            acc[4] = fmaf(x1.x, wv, acc[4]); acc[5] = fmaf(x1.y, wv, acc[5]); acc[6] = fmaf(x1.z, wv, acc[6]); acc[7] = fmaf(x1.w, wv, acc[7]);
+          }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                                             // all weight stages idle: the next layer may start streaming
+      if (more) {
+        const MlpLayer& Ln = A.L[l + 1];
+        const bool v4 = ((reinterpret_cast<uintptr_t>(Ln.W) & 15) == 0) && (Ln.out % 4 == 0);
+        const int KTn = tile_rows(Ln.in, Ln.out);
+        { const bool bn = A.bulk && bulk_ok(Ln.W, Ln.in, Ln.out); for (int t = 0; t < kStages - 1; ++t) issue(Ln.W, Ln.in, Ln.out, KTn, t, bn, v4); }
+      }
+      if (ks > 1) {                                                // fixed-order reduction over the K slices
+        if (slice > 0 && active) {
+  #pragma unroll
+          for (int r = 0; r < kRows; ++r) red[(size_t)tid * kRows + r] = acc[r];
+        }
+        __syncthreads();
+        if (slice == 0 && n < N)
+          for (int s2 = 1; s2 < ks; ++s2)
+  #pragma unroll
+            for (int r = 0; r < kRows; ++r) acc[r] += red[(size_t)(s2 * npad + n) * kRows + r];
+      }
+      if (slice == 0 && n < N) {
+        const float bv = Ly.b[n];
+  #pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const float v = act_fwd(acc[r] + bv, Ly.act);
+          if (more) xb[n * kRows + r] = v;
+          if (r < nrow) Ly.h[(size_t)(row0 + r) * Ly.h_ld + n] = v;
+        }
       }
     }
     if (more && A.L[l + 1].action_in) {                          // the next layer reads [h | action]
@@ -172,6 +306,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
     }
     float* tsw = xa; xa = xb; xb = tsw;                          // the first sync of the next layer's tile loop publishes xb
   }
+  MLP_STAMP(7)
 }
 
 // ------------------------------------------------------------------------------------------ input-gradient chain
@@ -281,6 +416,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
   }
 }
 
+// cpp_set_option("mlp_fast"): bit 0 register-tiled inner loop for layers with >= 256 inputs, bit 1 weight tiles by bulk copies
+int g_mlp_fast = [] { const char* e = getenv("CARTPOLEPP_MLP_FAST"); return e ? (atoi(e) & 3) : 3; }();
 // 0: one GEMM per layer; 1: fused forward stacks only; 2: fused forward and fused input-gradient chain
 static int g_use_fused_mlp = -1;
 void set_fused_mlp(int on) { g_use_fused_mlp = on; }
@@ -319,6 +456,7 @@ int launch_mlp_forward(const Net& net, const float* params, const float* action,
   MlpArgs A{};
   fill_layers(net, params, ws, L, &A);
   A.first = first_fc; A.end = end_fc; A.B = B; A.action = action;
+  A.tiled = g_mlp_fast & 1; A.bulk = (g_mlp_fast >> 1) & 1;
   int ld;
   const float* x = net.fc_input(L, ws, first_fc, &ld);
   A.x = x; A.x_ld = ld;

@@ -67,6 +67,9 @@ int64_t cpp_piece_overflow_count(int32_t reset);
  * weight-gradient accumulators; "fc_tc" = mask of the fully connected passes that run on tcgen05 (fc_tc.cu): 1 forward,
  * 2 input gradient, 4 weight gradient (with the bias gradient folded in), + 8 to include GEMMs below 64 M MACs (default 0: measured
  * slower than the FFMA kernels at the BASELINE sizes, profiles/r4/fc_tc.md; CARTPOLEPP_FC_TC sets the start-up value).
+ * "mlp_fast" = mask (default 3, CARTPOLEPP_MLP_FAST) for the fused FC forward kernel (mlp.cu): 1 register-tiled inner loop (4 output
+ * columns x 8 rows per thread) for layers with >= 256 inputs, 2 weight tiles by bulk copies (TMA engine) instead of per-thread
+ * cp.async; results differ from 0 only in summation order;
  * "dropout_seed" = seed of the library's own counter-based mask generator (TensorFlow's random stream cannot be reproduced;
  * every training forward of a dropout network advances a device-side counter, so graph replays draw fresh masks),
  * "dropout_external" = 1: masks are NOT generated - the caller has written 0/1 bytes into the mask buffers

@@ -48,7 +48,7 @@ def test_runtime_switches_are_known_and_unknown_names_are_rejected():
   lib = _lib.lib()
   header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cartpolepp.h")).read()
   defaults = {"conv1_tc": -1, "fused_mlp": -1, "prep_hoist": 1, "conv1_split": 1, "critic_tail": 1, "bwd_critic_sms": 92, "fwd_actor_sms": 37,
-              "wgrad_tc": 5, "conv_row": 1, "wgrad_flush_steps": 32, "fc_tc": 0, "is_training": 1, "dropout_external": 0}
+              "wgrad_tc": 5, "conv_row": 1, "mlp_fast": 3, "wgrad_flush_steps": 32, "fc_tc": 0, "is_training": 1, "dropout_external": 0}
   for name, value in defaults.items():
     assert '"%s"' % name in header, "switch %s is not documented in the header" % name
     _lib.check(lib.cpp_set_option(name.encode(), value))
