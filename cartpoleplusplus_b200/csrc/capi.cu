@@ -120,7 +120,7 @@ int cpp_set_option(const char* name, int32_t value) {
   if (strcmp(name, "fc_tc") == 0) { g_fc_tc = value & 15; return CPP_OK; }
   if (strcmp(name, "wgrad_tc") == 0) { g_wgrad_tc = value & 7; return CPP_OK; }
   if (strcmp(name, "conv_row") == 0) { tcr::set_conv_row(value); return CPP_OK; }
-  if (strcmp(name, "mlp_fast") == 0) { g_mlp_fast = value & 3; return CPP_OK; }
+  if (strcmp(name, "mlp_fast") == 0) { g_mlp_fast = value & 7; return CPP_OK; }
   if (strcmp(name, "conv1_split") == 0) { g_conv1_split = value != 0; return CPP_OK; }
   if (strcmp(name, "critic_tail") == 0) { g_critic_tail = value != 0; return CPP_OK; }
   if (strcmp(name, "fwd_actor_sms") == 0) { g_fwd_actor_sms = value < 16 ? 16 : (value > 100 ? 100 : value); return CPP_OK; }

@@ -33,6 +33,7 @@ struct MlpArgs {
   float* dTop;                      // [B][out(end-1)] gradient wrt its pre-activation (kept for the weight gradient)
   float* d_action;                  // [B][action_dim] or NULL
   int tiled;                        // forward: register-tiled inner loop (4 columns x 8 rows per thread) - CARTPOLEPP_MLP_TILED
+  int rotate;                       // forward: CTA b starts its tile sequence at tile b mod ntiles (mlp_fast bit 2)
   int bulk;                         // forward: weight tiles by bulk copies (TMA engine) instead of per-thread cp.async - CARTPOLEPP_MLP_BULK
   int need_dx_first;                // 1: also produce dX of layer `first`
   float* absmax_first;              // optional: max |dX of layer `first`| is atomically max-ed into this device float (zeroed by the caller):
@@ -119,10 +120,15 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
   }
   __syncthreads();
   // tile t of a layer -> stage t % kStages, by bulk copy when the layer allows it, else by per-thread cp.async
+  // Position t of a layer's tile sequence goes to stage t % kStages; the tile it holds is (t + rot) % ntiles with rot = this CTA's
+  // index (A.rotate): the CTAs then pull DIFFERENT weight tiles at any moment instead of all hitting the same L2 lines.  The order
+  // in which a row's K range is summed depends on the CTA that owns the row - a fixed function of the row, so still deterministic.
+  auto tile_at = [&](int t, int ntl) { return t < ntl ? (A.rotate ? (t + (int)blockIdx.x) % ntl : t) : ntl; };
   auto issue = [&](const float* W, int K, int N, int KT, int t, bool bulk, bool v4) {
     float* dst = wt + (t % kStages) * kTileFloats;
-    if (bulk) { issue_tile_bulk(W, K, N, KT, t, dst, &wbar[t % kStages], tid); asm volatile("cp.async.commit_group;" ::: "memory"); }
-    else issue_tile(W, K, N, KT, t, dst, tid, v4);
+    const int tt = tile_at(t, (K + KT - 1) / KT);                // (past the end: nothing to copy, an empty group keeps the counts)
+    if (bulk) { issue_tile_bulk(W, K, N, KT, tt, dst, &wbar[t % kStages], tid); asm volatile("cp.async.commit_group;" ::: "memory"); }
+    else issue_tile(W, K, N, KT, tt, dst, tid, v4);
   };
   auto wait_tile = [&](int t, bool bulk) {
     if (bulk) { const int st = t % kStages; umma::mbar_wait(&wbar[st], (wphase >> st) & 1u); wphase ^= 1u << st; }
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
         __syncthreads();                                         // ... for every thread; the stage of tile t-1 is free again; xa is complete
         issue(Ly.W, K, N, KT, t + kStages - 1, bulk, vec4);
         const float* wtile = wt + (t % kStages) * kTileFloats;
-        const int k0 = t * KT, rows = min(KT, K - k0);
+        const int k0 = tile_at(t, ntiles) * KT, rows = min(KT, K - k0);
         if (a0) {
 #pragma unroll 2
           for (int kk = slice; kk < rows; kk += 8) {
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_forward_kernel(const __grid_c
         issue(Ly.W, K, N, KT, t + kStages - 1, bulk, vec4);
         if (active) {
           const float* w = wt + (t % kStages) * kTileFloats + n;
-          const int k0 = t * KT, rows = min(KT, K - k0);
+          const int k0 = tile_at(t, ntiles) * KT, rows = min(KT, K - k0);
   #pragma unroll 4
           for (int kk = slice; kk < rows; kk += ks) {
             const float wv = w[kk * N];
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_dgrad_kernel(const __grid_con
 }
 
 // cpp_set_option("mlp_fast"): bit 0 register-tiled inner loop for layers with >= 256 inputs, bit 1 weight tiles by bulk copies
-int g_mlp_fast = [] { const char* e = getenv("CARTPOLEPP_MLP_FAST"); return e ? (atoi(e) & 3) : 3; }();
+int g_mlp_fast = [] { const char* e = getenv("CARTPOLEPP_MLP_FAST"); return e ? (atoi(e) & 7) : 3; }();
 // 0: one GEMM per layer; 1: fused forward stacks only; 2: fused forward and fused input-gradient chain
 static int g_use_fused_mlp = -1;
 void set_fused_mlp(int on) { g_use_fused_mlp = on; }
@@ -456,7 +462,7 @@ int launch_mlp_forward(const Net& net, const float* params, const float* action,
   MlpArgs A{};
   fill_layers(net, params, ws, L, &A);
   A.first = first_fc; A.end = end_fc; A.B = B; A.action = action;
-  A.tiled = g_mlp_fast & 1; A.bulk = (g_mlp_fast >> 1) & 1;
+  A.tiled = g_mlp_fast & 1; A.bulk = (g_mlp_fast >> 1) & 1; A.rotate = (g_mlp_fast >> 2) & 1;
   int ld;
   const float* x = net.fc_input(L, ws, first_fc, &ld);
   A.x = x; A.x_ld = ld;

@@ -69,7 +69,8 @@ int64_t cpp_piece_overflow_count(int32_t reset);
  * slower than the FFMA kernels at the BASELINE sizes, profiles/r4/fc_tc.md; CARTPOLEPP_FC_TC sets the start-up value).
  * "mlp_fast" = mask (default 3, CARTPOLEPP_MLP_FAST) for the fused FC forward kernel (mlp.cu): 1 register-tiled inner loop (4 output
  * columns x 8 rows per thread) for layers with >= 256 inputs, 2 weight tiles by bulk copies (TMA engine) instead of per-thread
- * cp.async; results differ from 0 only in summation order;
+ * cp.async, 4 every CTA starts its tile sequence at a different tile (measured slower, off); results differ from 0 only in
+ * summation order;
  * "dropout_seed" = seed of the library's own counter-based mask generator (TensorFlow's random stream cannot be reproduced;
  * every training forward of a dropout network advances a device-side counter, so graph replays draw fresh masks),
  * "dropout_external" = 1: masks are NOT generated - the caller has written 0/1 bytes into the mask buffers
