@@ -5,10 +5,12 @@
 //    read of its A operand (40 clk) and every output pixel pays 25 taps x 3 channel groups of them.
 //  * Here an instruction covers one INPUT row r and one tap column kx, and the FIVE ky taps sit side by side along N:
 //    column block t holds w[ky = KS-1-t] and lands in the accumulator of output row y = r - PAD + t.  Output rows live in a ring
-//    of 16 TMEM slots (32 columns each: 10 filters x hi/lo weight piece, padded), so the N = KS*32 columns of the instruction are
-//    KS consecutive slots: the tensor core accumulates every output row over its KS input rows IN TENSOR MEMORY, nothing is
-//    summed in registers.  A read of A is now amortised over 160 columns: the instruction is tensor-rate bound (N/2 clk), and a
-//    row of 3 images costs 8 instructions (5 kx x 3 channel groups = 15 K8 halves) instead of 3 x 38 x 4 / 2.
+//    of 12 TMEM slots (32 columns each: 10 filters x hi/lo weight piece, padded) plus 4 shadow slots behind it, so the N = KS*32
+//    columns of the instruction are KS consecutive slots (a window that starts in the last ring slots runs on into the shadows
+//    instead of wrapping: always ONE instruction; the epilogue adds the two halves): the tensor core accumulates every output row
+//    over its KS input rows IN TENSOR MEMORY, nothing is summed in registers.  A read of A is now amortised over 160 columns:
+//    the instruction is tensor-rate bound (N/2 clk), and a row of 3 images costs 8 instructions (5 kx x 3 channel groups = 15
+//    K8 halves) instead of 3 x 38 x 4 / 2.
 //  * M = 128 lanes = a strip of `ipt` whole image rows including their zero halo: entry e of image i is pixel e - PAD, lane
 //    (i, x) reads entries x .. x + KS - 1, so tap kx is the SAME strip shifted by kx 16-byte entries - a no-swizzle K-major
 //    descriptor pointing into the strip.  The strip of a row is three TMA tensor-map boxes (one per 8-channel group of the
@@ -17,7 +19,13 @@
 //  * The epilogue drains two finished output rows at a time (tcgen05.ld), zeroes their slots (tcgen05.st) for the rows that
 //    reuse them, and does bias + ReLU + 2x2 max-pool (x partner = the neighbouring lane: one shuffle) + arg-max byte + fp16
 //    piece copy, or (input-gradient mode) writes the dense fp32 rows and max|dx|.
+//  * Input-gradient mode builds its strips itself: eight producer warps un-pool d(pooled) through the arg-max side band, scale by a
+//    power of two and split into hi / lo pieces straight into shared memory (no piece tensor, no separate pass).
+//  * Work = the pooled rows of all tiles, cut into one contiguous range per CTA (segments never cross a tile; a segment that starts
+//    inside an image re-reads PAD input rows).  Roles: 8 epilogue warps, 8 producer warps (TMA: one lane), 1 MMA warp that walks
+//    its loop with warp-uniform values only - one elected lane issues, the descriptors stay in uniform registers.
 // Deterministic: every output accumulates its taps in a fixed order; no atomics on sums.
+// Measured, role cycle accounting and the versions that did not work: DESIGN.md 3.3, profiles/r5/.
 #include <cuda.h>
 #include <algorithm>
 #include <string.h>
